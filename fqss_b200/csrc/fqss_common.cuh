@@ -1,0 +1,157 @@
+// fqss_b200 -- common device helpers for the sm_100a kernels.
+//
+// Arithmetic contract (verified against qat_quant.py:88-147):
+// every fake-quant op is a separately rounded fp32 operation (PyTorch eager never contracts to
+// FMA), so the helpers below use the explicit round-to-nearest intrinsics; a plain `a*b+c` would be
+// fused by nvcc and flip codes that sit on a rounding boundary.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/fqss.h"
+
+namespace fqss {
+
+// ---------------------------------------------------------------------------------------------
+// host side: error convention
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);
+
+#define FQSS_REQUIRE(cond, code, ...)          \
+    do {                                       \
+        if (!(cond)) {                         \
+            ::fqss::set_error(__VA_ARGS__);    \
+            return (code);                     \
+        }                                      \
+    } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------------------------------
+// quantiser parameter blocks, computed once per thread from the device-resident range tensors
+// ---------------------------------------------------------------------------------------------
+struct ActQ {
+    float mn;      // zero point = min_range
+    float delta;   // (max - min) / levels
+    float levels;  // 2^bits - 1
+};
+
+__device__ __forceinline__ ActQ load_actq(const float* __restrict__ rmin, const float* __restrict__ rmax, int n_bits) {
+    ActQ q;
+    q.mn = __ldg(rmin);
+    q.levels = (float)((1 << n_bits) - 1);
+    q.delta = __fdiv_rn(__fsub_rn(__ldg(rmax), q.mn), q.levels);   // qat_quant.py:140
+    return q;
+}
+
+// t = (x - min) / delta, X = rint(t)  (qat_quant.py:144; round_ste value == rint, half-to-even)
+__device__ __forceinline__ float actq_t(const ActQ& q, float x) { return __fdiv_rn(__fsub_rn(x, q.mn), q.delta); }
+
+__device__ __forceinline__ float actq_code(const ActQ& q, float x) {
+    float X = rintf(actq_t(q, x));
+    return fminf(fmaxf(X, 0.f), q.levels);
+}
+
+// y = delta * code + min, two roundings (qat_quant.py:145)
+__device__ __forceinline__ float actq_decode(const ActQ& q, float code) {
+    return __fadd_rn(__fmul_rn(q.delta, code), q.mn);
+}
+
+__device__ __forceinline__ float actq_fq(const ActQ& q, float x) { return actq_decode(q, actq_code(q, x)); }
+
+// Backward pieces for one element.  Returns the gradient w.r.t. the pre-quant value and
+// accumulates the two range sums:  sD += g * (clip(X) - m*t),  sZ += g * (1 - m).
+//   g_max = sD / levels ;  g_min = sZ - sD / levels         
+__device__ __forceinline__ float actq_bwd(const ActQ& q, float x, float g, float& sD, float& sZ) {
+    float t = actq_t(q, x);
+    float X = rintf(t);
+    bool in = (X >= 0.f) && (X <= q.levels);
+    float c = fminf(fmaxf(X, 0.f), q.levels);
+    float D = in ? __fsub_rn(X, t) : c;
+    sD = fmaf(g, D, sD);
+    sZ += in ? 0.f : g;
+    // ((g * delta) * m) / delta : the exact op chain autograd runs (mul, clip-mask, div)
+    return in ? __fdiv_rn(__fmul_rn(g, q.delta), q.delta) : 0.f;
+}
+
+struct WQ {
+    float delta;
+    float lo, hi;
+};
+
+__device__ __forceinline__ WQ make_wq(float rmin, float rmax, int n_bits) {
+    WQ q;
+    float a = fmaxf(fabsf(rmin), fabsf(rmax));
+    float levels = (float)((1 << n_bits) - 1);
+    q.delta = __fdiv_rn(__fmul_rn(2.f, a), levels);   // qat_quant.py:131
+    q.lo = -(float)(1 << (n_bits - 1));
+    q.hi = (float)((1 << (n_bits - 1)) - 1);
+    return q;
+}
+
+__device__ __forceinline__ float wq_code(const WQ& q, float w) {
+    float X = rintf(__fdiv_rn(w, q.delta));
+    return fminf(fmaxf(X, q.lo), q.hi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of NV values per thread; result valid in thread 0.  `sh` needs NV*32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[i * 32 + wid] = v[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = lane < nw ? sh[i * 32 + lane] : 0.0;
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit global access
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// streaming variants: data touched exactly once should not displace L2-resident operands
+__device__ __forceinline__ float4 ldg4_stream(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+}  // namespace fqss

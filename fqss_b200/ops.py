@@ -1,0 +1,477 @@
+"""Autograd wrappers over the C ABI (include/fqss.h).  Host-side plumbing only: shapes, pitches,
+saved tensors.  Every op requires CUDA tensors and raises otherwise (no CPU / eager fallback).
+
+Row-tensor layout: activations [..., C, M] are allocated with a row pitch padded to a multiple of
+4 floats so that every row starts 16-byte aligned (M = 3999 in the recipe).  They are ordinary
+torch tensors (non-contiguous views), so foreign code can consume them; foreign inputs that do not
+have the layout are repacked once at the boundary.
+"""
+import ctypes as C
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _native as N
+from ._native import PwDesc, PwGrads, check, lib, ptr, stream_ptr, workspace
+
+PAD = 4
+
+
+def _pitch(m):
+    return (m + PAD - 1) // PAD * PAD
+
+
+def alloc_rows(shape, device, dtype=torch.float32):
+    """Uninitialised tensor of `shape` whose last-dim rows sit at a 16-byte aligned pitch."""
+    shape = tuple(int(s) for s in shape)
+    m = shape[-1]
+    rows = 1
+    for s in shape[:-1]:
+        rows *= s
+    base = torch.empty((rows, _pitch(m)), device=device, dtype=dtype)
+    return base[:, :m].view(shape)
+
+
+def _row_layout(t):
+    """(ok, ld): whether `t` is a uniformly pitched, 16-byte aligned row tensor, and its pitch."""
+    cols = t.shape[-1]
+    if t.dim() == 0 or (t.stride(-1) != 1 and cols != 1):
+        return False, 0
+    dims = [(t.shape[i], t.stride(i)) for i in range(t.dim() - 1) if t.shape[i] > 1]
+    if dims:
+        ld = dims[-1][1]
+        exp = ld
+        for size, stride in reversed(dims):
+            if stride != exp:
+                return False, 0
+            exp *= size
+    else:
+        ld = _pitch(cols)
+    return (ld >= cols and ld % PAD == 0 and t.data_ptr() % 16 == 0), ld
+
+
+def ld_of(t):
+    ok, ld = _row_layout(t)
+    if not ok:
+        raise N.FqssError("internal: tensor is not a pitched row tensor")
+    return ld
+
+
+def rows_view(t):
+    """-> (tensor, rows, cols, ld).  Repacks `t` into the padded layout when its strides do not
+    describe uniformly pitched rows (or the pitch / base is not 16-byte aligned)."""
+    if t.dtype != torch.float32:
+        raise N.FqssError("fqss_b200 ops are fp32; got %s" % t.dtype)
+    ok, ld = _row_layout(t)
+    if not ok:
+        new = alloc_rows(t.shape, t.device)
+        new.copy_(t)
+        t = new
+        ok, ld = _row_layout(t)
+    cols = t.shape[-1]
+    rows = t.numel() // cols if cols else 0
+    return t, rows, cols, ld
+
+
+def _scalar_like(p):
+    return torch.empty_like(p, memory_format=torch.contiguous_format)
+
+
+# =============================================================================================
+# Q2: standalone activation fake-quant (GradientActivationFakeQuantize.forward, quantise branch)
+# =============================================================================================
+class FakeQuantAct(Function):
+    @staticmethod
+    def forward(ctx, x, rmin, rmax, n_bits):
+        N.require_cuda(x, rmin, rmax)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        check(lib().fqss_fq_act_fwd(ptr(xc), ptr(y), None, xc.numel(), ptr(rmin), ptr(rmax), n_bits, stream_ptr()))
+        ctx.save_for_backward(xc, rmin, rmax)
+        ctx.n_bits = n_bits
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, rmin, rmax = ctx.saved_tensors
+        g = g.contiguous()
+        gx = torch.empty_like(x)
+        gmin, gmax = _scalar_like(rmin), _scalar_like(rmax)
+        ws = workspace(0, x.device)
+        check(lib().fqss_fq_act_bwd(ptr(g), ptr(x), ptr(gx), ptr(gmin), ptr(gmax), x.numel(), ptr(rmin), ptr(rmax),
+                                    ctx.n_bits, ptr(ws), ws.numel(), stream_ptr()))
+        return gx, gmin, gmax, None
+
+
+def fake_quant_codes(x, rmin, rmax, n_bits=8):
+    """(y, uint8 codes) of the activation quantiser -- test / export helper."""
+    N.require_cuda(x, rmin, rmax)
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    code = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device)
+    check(lib().fqss_fq_act_fwd(ptr(xc), ptr(y), ptr(code), xc.numel(), ptr(rmin), ptr(rmax), n_bits, stream_ptr()))
+    return y, code
+
+
+# =============================================================================================
+# Q3: weight fake-quant
+# =============================================================================================
+def _w_geometry(w, axis):
+    outer = 1
+    for s in w.shape[:axis]:
+        outer *= s
+    inner = 1
+    for s in w.shape[axis + 1:]:
+        inner *= s
+    return int(outer), int(w.shape[axis]), int(inner)
+
+
+class FakeQuantWeight(Function):
+    @staticmethod
+    def forward(ctx, w, rmin, rmax, axis, n_bits):
+        N.require_cuda(w, rmin, rmax)
+        wc = w.contiguous()
+        outer, ch, inner = _w_geometry(wc, axis)
+        if rmin.numel() != ch:
+            raise N.FqssError("weight quantiser: %d ranges for %d channels" % (rmin.numel(), ch))
+        wq = torch.empty_like(wc)
+        check(lib().fqss_fq_weight_fwd(ptr(wc), ptr(wq), None, outer, ch, inner, ptr(rmin), ptr(rmax), n_bits, stream_ptr()))
+        ctx.save_for_backward(wc, rmin, rmax)
+        ctx.geom = (outer, ch, inner, n_bits)
+        return wq
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        w, rmin, rmax = ctx.saved_tensors
+        outer, ch, inner, n_bits = ctx.geom
+        g = g.contiguous()
+        gw = torch.empty_like(w)
+        gmin, gmax = _scalar_like(rmin), _scalar_like(rmax)
+        check(lib().fqss_fq_weight_bwd(ptr(g), ptr(w), ptr(gw), ptr(gmin), ptr(gmax), outer, ch, inner, ptr(rmin), ptr(rmax),
+                                       n_bits, stream_ptr()))
+        return gw, gmin, gmax, None, None
+
+
+def weight_codes(w, rmin, rmax, axis=0, n_bits=8):
+    wc = w.contiguous()
+    outer, ch, inner = _w_geometry(wc, axis)
+    code = torch.empty(wc.shape, dtype=torch.int8, device=wc.device)
+    check(lib().fqss_fq_weight_fwd(ptr(wc), None, ptr(code), outer, ch, inner, ptr(rmin), ptr(rmax), n_bits, stream_ptr()))
+    return code
+
+
+def weight_observe_(w, rmin, rmax, axis):
+    N.require_cuda(w, rmin, rmax)
+    wc = w.detach().contiguous()
+    outer, ch, inner = _w_geometry(wc, axis)
+    check(lib().fqss_weight_observe(ptr(wc), outer, ch, inner, ptr(rmin), ptr(rmax), stream_ptr()))
+
+
+def act_observe_(x, rmin, rmax, alpha):
+    N.require_cuda(x, rmin, rmax)
+    x, rows, cols, ld = rows_view(x.detach())
+    ws = workspace(rows, x.device)
+    check(lib().fqss_act_observe(ptr(x), rows, cols, ld, ptr(rmin), ptr(rmax), float(alpha), ptr(ws), ws.numel(), stream_ptr()))
+
+
+# =============================================================================================
+# L1: op -> nonlinearity -> fake-quant in one pass
+# =============================================================================================
+def _desc(kind, quant, n_bits, x1, r1, x2, r2, y, ry, slope, gamma, beta, stats, eps, rmin, rmax, C_, bcast):
+    d = PwDesc()
+    d.kind, d.quant, d.n_bits, d.C, d.bcast = kind, int(bool(quant)), int(n_bits), int(C_), int(bcast)
+    d.rows, d.cols = r1[0], r1[1]
+    d.x1, d.ld1 = ptr(x1), r1[2]
+    d.x2, d.ld2 = (ptr(x2), r2[2]) if x2 is not None else (None, 0)
+    d.y, d.ldy = (ptr(y), ry) if y is not None else (None, 0)
+    d.slope, d.gamma, d.beta, d.stats = ptr(slope) or None, ptr(gamma) or None, ptr(beta) or None, ptr(stats) or None
+    d.eps = float(eps)
+    d.rmin, d.rmax = ptr(rmin) or None, ptr(rmax) or None
+    return d
+
+
+class PointwiseFQ(Function):
+    """y = FQ(op(x1[, x2])) for op in {ident, prelu, relu, add, sub, mul(bcast), gLN}."""
+
+    @staticmethod
+    def forward(ctx, kind, x1, x2, slope, gamma, beta, rmin, rmax, quant, n_bits, eps):
+        N.require_cuda(x1, x2, slope, gamma, beta, rmin, rmax)
+        x1, rows, cols, ld1 = rows_view(x1)
+        C_, bcast, r2, stats = 1, 1, None, None
+        if x2 is not None:
+            if kind == N.PW_MUL and x2.shape != x1.shape:
+                # MulQ: mask [B,S,N,M] * feats [B,1,N,M]
+                if not (x1.dim() == 4 and x2.dim() == 4 and x2.shape[1] == 1 and x2.shape[0] == x1.shape[0]
+                        and x2.shape[2:] == x1.shape[2:]):
+                    raise N.FqssError("MulQ: unsupported broadcast %s * %s" % (tuple(x1.shape), tuple(x2.shape)))
+                bcast, C_ = x1.shape[1], x1.shape[2]
+            elif x2.shape != x1.shape:
+                raise N.FqssError("binary op shapes differ: %s vs %s" % (tuple(x1.shape), tuple(x2.shape)))
+            elif kind == N.PW_MUL:
+                C_ = 1
+            x2, rows2, _, ld2 = rows_view(x2)
+            r2 = (rows2, cols, ld2)
+        if kind == N.PW_GLN:
+            C_ = x1.shape[-2]
+            B = rows // C_
+            stats = torch.empty(2 * B, dtype=torch.float64, device=x1.device)
+            check(lib().fqss_gln_stats(ptr(x1), rows, cols, ld1, C_, ptr(stats), stream_ptr()))
+        y = alloc_rows(x1.shape, x1.device)
+        d = _desc(kind, quant, n_bits, x1, (rows, cols, ld1), x2, r2, y, ld_of(y),
+                  slope, gamma, beta, stats, eps, rmin, rmax, C_, bcast)
+        check(lib().fqss_pw_fwd(C.byref(d), stream_ptr()))
+        ctx.save_for_backward(x1, x2, slope, gamma, beta, rmin, rmax, stats)
+        ctx.meta = (kind, quant, n_bits, eps, C_, bcast, rows, cols, ld1, r2)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x1, x2, slope, gamma, beta, rmin, rmax, stats = ctx.saved_tensors
+        kind, quant, n_bits, eps, C_, bcast, rows, cols, ld1, r2 = ctx.meta
+        g, _, _, ldg = rows_view(g)
+        dev = x1.device
+        gx1 = alloc_rows(x1.shape, dev)
+        gx2 = None
+        if x2 is not None and kind in (N.PW_SUB, N.PW_MUL) and ctx.needs_input_grad[2]:
+            gx2 = alloc_rows(x2.shape, dev)
+        gmin = _scalar_like(rmin) if quant and rmin is not None else None
+        gmax = _scalar_like(rmax) if quant and rmax is not None else None
+        gslope = _scalar_like(slope) if kind == N.PW_PRELU else None
+        ggamma = torch.empty_like(gamma) if kind == N.PW_GLN else None
+        gbeta = torch.empty_like(beta) if kind == N.PW_GLN else None
+        d = _desc(kind, quant, n_bits, x1, (rows, cols, ld1), x2, r2, None, 0, slope, gamma, beta, stats, eps, rmin, rmax,
+                  C_, bcast)
+        o = PwGrads()
+        o.g, o.ldg = ptr(g), ldg
+        o.gx1, o.ldg1 = (ptr(gx1), ld_of(gx1)) if gx1 is not None else (None, 0)
+        o.gx2, o.ldg2 = (ptr(gx2), ld_of(gx2)) if gx2 is not None else (None, 0)
+        o.g_rmin, o.g_rmax, o.g_slope = ptr(gmin) or None, ptr(gmax) or None, ptr(gslope) or None
+        o.g_gamma, o.g_beta = ptr(ggamma) or None, ptr(gbeta) or None
+        ws = workspace(rows, dev)
+        check(lib().fqss_pw_bwd(C.byref(d), C.byref(o), ptr(ws), ws.numel(), stream_ptr()))
+        if kind == N.PW_ADD:
+            gx2 = gx1
+        return None, gx1, gx2, gslope, ggamma, gbeta, gmin, gmax, None, None, None
+
+
+def pointwise_fq(kind, x1, x2=None, slope=None, gamma=None, beta=None, rmin=None, rmax=None, quant=False, n_bits=8, eps=0.0):
+    return PointwiseFQ.apply(kind, x1, x2, slope, gamma, beta, rmin, rmax, bool(quant), int(n_bits), float(eps))
+
+
+# =============================================================================================
+# convolutions
+# =============================================================================================
+class Conv1x1(Function):
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        N.require_cuda(x, w, bias)
+        x, rows, M, ldx = rows_view(x)
+        Co, Ci = w.shape[0], w.shape[1]
+        B = rows // Ci
+        wc = w.contiguous()
+        y = alloc_rows(x.shape[:-2] + (Co, M), x.device)
+        check(lib().fqss_conv1x1_fwd(ptr(x), ldx, ptr(wc), ptr(bias), ptr(y), ld_of(y), B, Ci, Co, M, stream_ptr()))
+        ctx.save_for_backward(x, wc)
+        ctx.meta = (B, Ci, Co, M, ldx, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, Ci, Co, M, ldx, has_bias = ctx.meta
+        g, _, _, ldg = rows_view(g)
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = alloc_rows(x.shape, x.device)
+            check(lib().fqss_conv1x1_dgrad(ptr(g), ldg, ptr(w), ptr(gx), ld_of(gx), B, Ci, Co, M, stream_ptr()))
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            gw = torch.empty_like(w)
+            gb = torch.empty(Co, device=x.device) if has_bias else None
+            ws = workspace(Co, x.device)
+            check(lib().fqss_conv1x1_wgrad(ptr(g), ldg, ptr(x), ldx, ptr(gw), ptr(gb) or None, B, Ci, Co, M, ptr(ws), ws.numel(),
+                                           stream_ptr()))
+        return gx, gw, gb
+
+
+class DepthwiseConv(Function):
+    @staticmethod
+    def forward(ctx, x, w, bias, dil):
+        N.require_cuda(x, w, bias)
+        x, rows, M, ldx = rows_view(x)
+        Cc, K = w.shape[0], w.shape[-1]
+        B = rows // Cc
+        wc = w.contiguous()
+        y = alloc_rows(x.shape, x.device)
+        check(lib().fqss_dwconv_fwd(ptr(x), ldx, ptr(wc), ptr(bias), ptr(y), ld_of(y), B, Cc, M, K, dil, stream_ptr()))
+        ctx.save_for_backward(x, wc)
+        ctx.meta = (B, Cc, M, K, dil, ldx, bias is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, Cc, M, K, dil, ldx, has_bias = ctx.meta
+        g, _, _, ldg = rows_view(g)
+        gx = alloc_rows(x.shape, x.device) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w)
+        gb = torch.empty(Cc, device=x.device) if has_bias else None
+        ws = workspace(Cc * 2, x.device)
+        check(lib().fqss_dwconv_bwd(ptr(g), ldg, ptr(x), ldx, ptr(w), ptr(gx) or None, ld_of(gx) if gx is not None else 0,
+                                    ptr(gw), ptr(gb) or None, B, Cc, M, K, dil, ptr(ws), ws.numel(), stream_ptr()))
+        return gx, gw, gb, None
+
+
+class StridedConv(Function):
+    """Encoder-type conv: no padding, no bias, dilation 1 (qat_layers.py:1030, :1189)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        N.require_cuda(x, w)
+        x, rows, T, ldx = rows_view(x)
+        Co, Cin, K = w.shape
+        B = rows // Cin
+        Mo = (T - K) // stride + 1
+        wc = w.contiguous()
+        y = alloc_rows(x.shape[:-2] + (Co, Mo), x.device)
+        check(lib().fqss_sconv_fwd(ptr(x), ldx, ptr(wc), ptr(y), ld_of(y), B, Cin, Co, T, K, stride, stream_ptr()))
+        ctx.save_for_backward(x, wc)
+        ctx.meta = (B, Cin, Co, T, K, stride, ldx)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, Cin, Co, T, K, stride, ldx = ctx.meta
+        g, _, _, ldg = rows_view(g)
+        gx = alloc_rows(x.shape, x.device) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        ws = workspace(Co * Cin * K // 4 + 1, x.device)
+        check(lib().fqss_sconv_bwd(ptr(g), ldg, ptr(x), ldx, ptr(w), ptr(gx) or None, ld_of(gx) if gx is not None else 0,
+                                   ptr(gw) or None, B, Cin, Co, T, K, stride, ptr(ws), ws.numel(), stream_ptr()))
+        return gx, gw, None
+
+
+class TransposedConv1(Function):
+    """Decoder-type ConvTranspose1d to one channel, no padding / bias (qat_layers.py:1332, :1194)."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride):
+        N.require_cuda(x, w)
+        x, rows, M, ldx = rows_view(x)
+        Ci, one, K = w.shape
+        if one != 1:
+            raise N.FqssError("transposed conv: only 1 output channel is implemented (decoder)")
+        B = rows // Ci
+        T = (M - 1) * stride + K
+        wc = w.contiguous()
+        y = alloc_rows(x.shape[:-2] + (1, T), x.device)
+        check(lib().fqss_tconv_fwd(ptr(x), ldx, ptr(wc), ptr(y), ld_of(y), B, Ci, M, K, stride, stream_ptr()))
+        ctx.save_for_backward(x, wc)
+        ctx.meta = (B, Ci, M, K, stride, ldx)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        B, Ci, M, K, stride, ldx = ctx.meta
+        g, _, _, ldg = rows_view(g)
+        gx = alloc_rows(x.shape, x.device) if ctx.needs_input_grad[0] else None
+        gw = torch.empty_like(w) if ctx.needs_input_grad[1] else None
+        ws = workspace(Ci * K // 4 + 1, x.device)
+        check(lib().fqss_tconv_bwd(ptr(g), ldg, ptr(x), ldx, ptr(w), ptr(gx) or None, ld_of(gx) if gx is not None else 0,
+                                   ptr(gw) or None, B, Ci, M, K, stride, ptr(ws), ws.numel(), stream_ptr()))
+        return gx, gw, None
+
+
+# =============================================================================================
+# P1: splitter / reconstructor
+# =============================================================================================
+def split_input(x, n_split, n_bits=8):
+    """process.preprocess for n_splitter >= 2: [B,1,T] -> [B,n_split,T] (no gradient: model input)."""
+    N.require_cuda(x)
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    if x.dim() != 3 or x.shape[1] != 1:
+        raise N.FqssError("splitter expects [B,T] or [B,1,T] (mono), got %s" % (tuple(x.shape),))
+    x, rows, T, ldx = rows_view(x.detach())
+    B = x.shape[0]
+    peak = torch.empty(1, device=x.device)
+    ws = workspace(rows, x.device)
+    check(lib().fqss_absmax(ptr(x), rows, T, ldx, ptr(peak), ptr(ws), ws.numel(), stream_ptr()))
+    y = alloc_rows((B, n_split, T), x.device)
+    check(lib().fqss_split(ptr(x), ldx, ptr(peak), ptr(y), ld_of(y), B, T, n_split, n_bits, stream_ptr()))
+    return y
+
+
+class Combine(Function):
+    """process.postprocess for n_combiner >= 2: parts [n, ..., T] -> sum_i parts[i]*(0.5/128)^i."""
+
+    @staticmethod
+    def forward(ctx, parts, n_bits):
+        N.require_cuda(parts)
+        n = parts.shape[0]
+        p, rows_all, T, ld = rows_view(parts)
+        rows = rows_all // n
+        y = alloc_rows(parts.shape[1:], parts.device)
+        check(lib().fqss_combine(ptr(p), rows * ld, ld, ptr(y), ld_of(y), rows, T, n, n_bits,
+                                 stream_ptr()))
+        ctx.meta = (n, n_bits)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        n, n_bits = ctx.meta
+        base = 0.5 / (2 ** (n_bits - 1))
+        # d/d parts[i] = g * base^i : tiny [n,B,S,1,T] tensor, assembled with two strided copies
+        out = alloc_rows((n,) + tuple(g.shape), g.device)
+        for i in range(n):
+            out[i].copy_(g) if i == 0 else torch.mul(g, base ** i, out=out[i])
+        return out, None
+
+
+# =============================================================================================
+# S1-S3: KD SI-SDR loss
+# =============================================================================================
+class KDLoss(Function):
+    """returns a 3-vector: [loss, kd_loss (logged), val_loss]; gradient flows from element 0 to est."""
+
+    @staticmethod
+    def forward(ctx, est, fest, tgt, kd_lambda):
+        N.require_cuda(est, fest, tgt)
+        if est.dim() != 3 or est.shape[1] != 2 or est.shape != fest.shape or est.shape != tgt.shape:
+            raise N.FqssError("kd_loss expects est/fest/tgt of shape [B,2,T]")
+        est_r, _, T, lde = rows_view(est)
+        fest_r, _, _, ldf = rows_view(fest.detach())
+        tgt_r, _, _, ldt = rows_view(tgt.detach())
+        B = est.shape[0]
+        out = torch.empty(3, device=est.device)
+        gest = alloc_rows(est.shape, est.device) if est.requires_grad else None
+        ws = workspace(B * 8, est.device)
+        check(lib().fqss_kd_loss(ptr(est_r), lde, ptr(fest_r), ldf, ptr(tgt_r), ldt, B, T, float(kd_lambda), ptr(out),
+                                 ptr(gest) or None, ld_of(gest) if gest is not None else 0, ptr(ws), ws.numel(),
+                                 stream_ptr()))
+        ctx.gest = gest
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        gest = ctx.gest
+        ctx.gest = None
+        if gest is None:
+            return None, None, None, None
+        # dL/dest was produced in forward for d(loss)=1; scale by the incoming scalar (1.0 in training)
+        return gest * gout[0], None, None, None
+
+
+def kd_loss(est, fest, tgt, kd_lambda=0.1):
+    return KDLoss.apply(est, fest, tgt, kd_lambda)

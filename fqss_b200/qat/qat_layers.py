@@ -1,0 +1,303 @@
+"""B200 mirror of `quantization/qat/qat_layers.py` (the nine wrappers ConvTasNetQ uses; SURVEY.md
+8a rows L1/L2).  Class names, constructor signatures and attribute names (= state_dict keys) match
+the reference; each forward is a short sequence of libfqss_sm100 kernels:
+
+    conv kernel (1x1 SGEMM / depthwise / strided / transposed)  ->  one fused pass that applies the
+    nonlinearity and the activation fake-quant (or, while observing, the nonlinearity + range EMA).
+
+Reference: LayerQ :49-59, AddQ :62, SubQ :74, MulQ :86, Conv1dQ :124, Conv1dNlQ :188, GroupNormQ :438,
+NlQ :511, Conv1dEncoderQ :993, ResidualErrorBlock :1105, ConvTr1dDecoderQ :1305.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import _native as N
+from .. import ops
+from .qat_quant import GradientActivationFakeQuantize, get_activation_quantizer, get_weight_quantizer
+
+
+class Add(nn.Module):
+    def forward(self, x1, x2):
+        return torch.add(x1, x2)
+
+
+class Sub(nn.Module):
+    def forward(self, x1, x2):
+        return torch.sub(x1, x2)
+
+
+class Mul(nn.Module):
+    def forward(self, x1, x2):
+        return torch.mul(x1, x2)
+
+
+class LayerQ(nn.Module):
+    """Base: owns `activation_fake_quantize` / `weight_fake_quantize` (Identity when disabled)."""
+
+    def __init__(self, gradient_based=True, weight_quant=False, act_quant=False, act_nl_quantizer=False,
+                 weight_shape=(1, 1, 1), ch_out_idx=0, act_n_bits=8, weight_n_bits=8, do_mac_op=False):
+        super().__init__()
+        self.weight_quant = weight_quant
+        self.act_quant = act_quant
+        self.gradient_based = gradient_based
+        self.activation_fake_quantize = (get_activation_quantizer(gradient_based, n_bits=act_n_bits, nl=act_nl_quantizer)
+                                         if act_quant else nn.Identity())
+        self.weight_fake_quantize = (get_weight_quantizer(gradient_based, weight_shape, ch_out_idx=ch_out_idx,
+                                                          n_bits=weight_n_bits) if weight_quant else nn.Identity())
+        self.do_mac_op = do_mac_op
+        self.mac_op = 0
+
+    # one fused pass: y = FQ(op(x1[,x2])); while the quantiser observes: y = op(...), ranges <- EMA
+    def _finish(self, kind, x1, x2=None, slope=None, gamma=None, beta=None, eps=0.0, quantizer=None):
+        q = self.activation_fake_quantize if quantizer is None else quantizer
+        if isinstance(q, GradientActivationFakeQuantize):
+            if q.observing():
+                y = ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, quant=False, eps=eps)
+                q.observe_(y)
+                return y
+            return ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, q.min_range, q.max_range, True, q.n_bits, eps)
+        if isinstance(q, nn.Identity):
+            return ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, quant=False, eps=eps)
+        raise NotImplementedError("unsupported activation quantiser %s" % type(q).__name__)
+
+
+def _nl_kind(nl):
+    """(kernel kind, slope tensor) for the nonlinearities the recipe uses."""
+    if nl is None or isinstance(nl, nn.Identity):
+        return N.PW_IDENT, None
+    if isinstance(nl, nn.PReLU):
+        if nl.weight.numel() != 1:
+            raise NotImplementedError("per-channel PReLU is not on the ConvTasNet path")
+        return N.PW_PRELU, nl.weight
+    if isinstance(nl, nn.ReLU):
+        return N.PW_RELU, None
+    raise NotImplementedError("nonlinearity %s has no sm_100a kernel here" % type(nl).__name__)
+
+
+def _conv1d(x, w, conv):
+    """Dispatch an nn.Conv1d geometry to its kernel; anything else is out of scope (no fallback)."""
+    k, s, p, d, g = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0], conv.groups
+    if isinstance(p, str):
+        raise NotImplementedError("string padding")
+    if k == 1 and s == 1 and p == 0 and g == 1:
+        return ops.Conv1x1.apply(x, w, conv.bias)
+    if g == conv.in_channels == conv.out_channels and s == 1 and (k % 2) == 1 and p == d * (k - 1) // 2:
+        return ops.DepthwiseConv.apply(x, w, conv.bias, d)
+    if g == 1 and p == 0 and d == 1 and conv.bias is None:
+        return ops.StridedConv.apply(x, w, s)
+    raise NotImplementedError("Conv1d geometry k=%d s=%d p=%d d=%d groups=%d bias=%s is not on the FQSS ConvTasNet path"
+                              % (k, s, p, d, g, conv.bias is not None))
+
+
+def _conv_out_len(conv, L):
+    return math.floor((L + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) / conv.stride[0] + 1)
+
+
+class AddQ(LayerQ):
+    def __init__(self, add, gradient_based=True, act_quant=True, act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
+        if not isinstance(add, Add):
+            raise Exception("AddQ wraps Add, got %s" % type(add))
+        self.add = add
+
+    def forward(self, x1, x2):
+        return self._finish(N.PW_ADD, x1, x2)
+
+
+class SubQ(LayerQ):
+    def __init__(self, sub, gradient_based=True, act_quant=True, act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
+        if not isinstance(sub, Sub):
+            raise Exception("SubQ wraps Sub, got %s" % type(sub))
+        self.sub = sub
+
+    def forward(self, x1, x2):
+        return self._finish(N.PW_SUB, x1, x2)
+
+
+class MulQ(LayerQ):
+    def __init__(self, mul, gradient_based=True, act_quant=True, act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
+        if not isinstance(mul, Mul):
+            raise Exception("MulQ wraps Mul, got %s" % type(mul))
+        self.mul = mul
+
+    def forward(self, x1, x2):
+        if self.do_mac_op:
+            self.mac_op = x1.numel()
+        return self._finish(N.PW_MUL, x1, x2)
+
+
+class Conv1dQ(LayerQ):
+    def __init__(self, conv1d, gradient_based=True, weight_quant=True, act_quant=True, act_n_bits=8, weight_n_bits=8):
+        super().__init__(gradient_based=gradient_based, weight_quant=weight_quant, act_quant=act_quant,
+                         weight_shape=conv1d.weight.shape, act_n_bits=act_n_bits, weight_n_bits=weight_n_bits)
+        if not isinstance(conv1d, nn.Conv1d):
+            raise Exception("Conv1dQ wraps Conv1d, got %s" % type(conv1d))
+        self.conv1d = conv1d
+
+    def forward(self, x):
+        y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
+        self.calc_mac_op(x.shape)
+        return self._finish(N.PW_IDENT, y)
+
+    def calc_mac_op(self, x_shape):
+        if self.do_mac_op:
+            Co, Ci, k = self.conv1d.weight.shape
+            self.mac_op = x_shape[0] * Co * _conv_out_len(self.conv1d, x_shape[-1]) * Ci * k
+
+
+class Conv1dNlQ(LayerQ):
+    def __init__(self, conv1d, nl, gradient_based=True, weight_quant=True, act_quant=True, act_n_bits=8, weight_n_bits=8):
+        super().__init__(gradient_based=gradient_based, weight_quant=weight_quant, act_quant=act_quant,
+                         weight_shape=conv1d.weight.shape, act_n_bits=act_n_bits, weight_n_bits=weight_n_bits)
+        if not isinstance(conv1d, nn.Conv1d):
+            raise Exception("Conv1dNlQ wraps Conv1d, got %s" % type(conv1d))
+        self.conv1d = conv1d
+        self.nl = nl
+
+    def forward(self, x):
+        y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
+        self.calc_mac_op(x.shape)
+        kind, slope = _nl_kind(self.nl)
+        return self._finish(kind, y, slope=slope)
+
+    calc_mac_op = Conv1dQ.calc_mac_op
+
+
+class GroupNormQ(LayerQ):
+    def __init__(self, groupnorm, gradient_based=True, act_quant=True, act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
+        if not isinstance(groupnorm, nn.GroupNorm):
+            raise Exception("GroupNormQ wraps GroupNorm, got %s" % type(groupnorm))
+        self.groupnorm = groupnorm
+
+    def forward(self, x):
+        gn = self.groupnorm
+        if gn.num_groups != 1 or not gn.affine:
+            raise NotImplementedError("only gLN = GroupNorm(1, C, affine=True) is on the ConvTasNet path")
+        if self.do_mac_op:
+            self.mac_op = 2 * x.numel()
+        return self._finish(N.PW_GLN, x, gamma=gn.weight, beta=gn.bias, eps=gn.eps)
+
+
+class NlQ(LayerQ):
+    def __init__(self, nl, gradient_based=True, act_quant=True, act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
+        self.nl = nl
+
+    def forward(self, x):
+        kind, slope = _nl_kind(self.nl)
+        return self._finish(kind, x, slope=slope)
+
+
+class Conv1dEncoderQ(LayerQ):
+    """Analysis filterbank; with n_splitter >= 2 the conv is rebuilt with n_splitter input channels:
+    channel 0 copies the float filters, the others are drawn around their mean (qat_layers.py:1009-1026)."""
+
+    def __init__(self, encoder, n_splitter=1, gradient_based=True, weight_quant=True, act_quant=True, in_quant=False,
+                 inout_nl_quant=False, act_n_bits=8, weight_n_bits=8, in_act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, weight_quant=weight_quant, act_quant=act_quant,
+                         weight_shape=encoder[0].weight.shape, act_n_bits=act_n_bits, weight_n_bits=weight_n_bits)
+        if not isinstance(encoder[0], nn.Conv1d):
+            raise Exception("Conv1dEncoderQ wraps Conv1d, got %s" % type(encoder[0]))
+        self.in_quantizer = (get_activation_quantizer(self.gradient_based, nl=inout_nl_quant, n_bits=in_act_n_bits)
+                             if in_quant else nn.Identity())
+        self.conv1d = encoder[0]
+        self.nl = nn.Identity() if len(encoder) == 1 else encoder[1]
+        if n_splitter >= 2:
+            old = self.conv1d
+            cin = old.in_channels
+            grown = nn.Conv1d(n_splitter * cin, old.out_channels, old.kernel_size, stride=old.stride,
+                              padding=old.padding, bias=old.bias is not None).to(old.weight.device)
+            with torch.no_grad():
+                w0 = old.weight.detach()
+                w = w0.repeat(1, n_splitter, 1)
+                for rep in range(1, n_splitter):
+                    for c in range(cin):
+                        col = w0[:, c, :]
+                        # same RNG draw order as the reference: one randn_like per (rep, channel)
+                        w[:, rep * cin + c, :] = torch.mean(col) + torch.randn_like(col) * (torch.std(col) ** rep)
+                grown.weight.copy_(w)
+                if old.bias is not None:
+                    grown.bias.copy_(old.bias)
+            self.conv1d = grown
+
+    def forward(self, x):
+        if not isinstance(self.in_quantizer, nn.Identity):
+            x = self.in_quantizer(x)
+        y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
+        if self.do_mac_op:
+            Co, Ci, k = self.conv1d.weight.shape
+            self.mac_op = x.shape[0] * Ci * Co * _conv_out_len(self.conv1d, x.shape[-1]) * k
+        kind, slope = _nl_kind(self.nl)
+        return self._finish(kind, y, slope=slope)
+
+
+class ResidualErrorBlock(LayerQ):
+    """RQB: re-encode the quantised output, quantise the feature-domain error, decode it with the
+    SAME quantised decoder weight (qat_layers.py:1188-1202, ConvTranspose1d branch only)."""
+
+    def __init__(self, decoder, gradient_based, weight_quant, act_quant, act_nl_quantizer=False, act_n_bits=8,
+                 weight_n_bits=8, train_res_dec=False):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_nl_quantizer=act_nl_quantizer,
+                         act_n_bits=act_n_bits)
+        if type(decoder) is not nn.ConvTranspose1d or train_res_dec:
+            raise NotImplementedError("RQB is implemented for the ConvTranspose1d decoder without train_res_dec")
+        if decoder.bias is not None or decoder.padding[0] or decoder.output_padding[0] or decoder.dilation[0] != 1:
+            raise NotImplementedError("decoder geometry not on the ConvTasNet path")
+        self.decoder_type = nn.ConvTranspose1d
+        self.train_res_dec = train_res_dec
+        self.residual_encoder = nn.Conv1d(decoder.out_channels, decoder.in_channels, decoder.kernel_size,
+                                          stride=decoder.stride, bias=False).to(decoder.weight.device)
+        self.decoder_bias = None
+        self.decoder_kernel, self.decoder_stride = decoder.kernel_size, decoder.stride
+        self.decoder_padding, self.decoder_output_padding = decoder.padding, decoder.output_padding
+        self.decoder_dilation, self.decoder_groups = decoder.dilation, decoder.groups
+        self.decoder_in_channels, self.decoder_out_channels = decoder.in_channels, decoder.out_channels
+        self.weight_fake_quantize = (get_weight_quantizer(gradient_based, self.residual_encoder.weight.shape,
+                                                          n_bits=weight_n_bits) if weight_quant else nn.Identity())
+
+    def forward(self, Y, y_q, w_decoder):
+        Yq = ops.StridedConv.apply(y_q, self.weight_fake_quantize(self.residual_encoder.weight), self.decoder_stride[0])
+        Y1 = self._finish(N.PW_SUB, Y, Yq)
+        return ops.TransposedConv1.apply(Y1, w_decoder, self.decoder_stride[0])
+
+
+class ConvTr1dDecoderQ(LayerQ):
+    def __init__(self, decoder, n_combiner=1, gradient_based=True, weight_quant=True, weight_n_bits=8, act_quant=True,
+                 act_n_bits=8, inout_nl_quant=False, out_quant=True, out_act_n_bits=8, train_res_dec=False):
+        super().__init__(gradient_based=gradient_based, weight_quant=weight_quant, act_quant=out_quant,
+                         act_nl_quantizer=inout_nl_quant, weight_shape=decoder[0].weight.shape, ch_out_idx=1,
+                         act_n_bits=out_act_n_bits, weight_n_bits=weight_n_bits)
+        dec = decoder[0]
+        if not isinstance(dec, nn.ConvTranspose1d):
+            raise Exception("ConvTr1dDecoderQ wraps ConvTranspose1d, got %s" % type(dec))
+        if dec.out_channels != 1 or dec.bias is not None or dec.padding[0] or dec.output_padding[0] or dec.groups != 1:
+            raise NotImplementedError("decoder geometry not on the ConvTasNet path")
+        self.n_combiner = n_combiner
+        self.convTr1d = dec
+        if self.n_combiner >= 2:
+            self.residual_error_block = ResidualErrorBlock(dec, gradient_based, weight_quant=weight_quant,
+                                                           act_quant=act_quant, weight_n_bits=weight_n_bits,
+                                                           act_n_bits=act_n_bits, train_res_dec=train_res_dec)
+            self.activation_fake_quantize_residual = (get_activation_quantizer(gradient_based, n_bits=out_act_n_bits)
+                                                      if out_quant else nn.Identity())
+
+    def forward(self, x):
+        stride = self.convTr1d.stride[0]
+        w_dec = self.weight_fake_quantize(self.convTr1d.weight)
+        y = self._finish(N.PW_IDENT, ops.TransposedConv1.apply(x, w_dec, stride))
+        if self.do_mac_op:
+            Ci, Co, k = self.convTr1d.weight.shape
+            self.mac_op = x.shape[0] * Co * Ci * ((x.shape[-1] - 1) * stride + k) * (k // stride)
+        if self.n_combiner == 1:
+            return y
+        outs = [y]
+        for _ in range(1, self.n_combiner):
+            x = self.residual_error_block(x, y, w_dec)
+            y = self._finish(N.PW_IDENT, x, quantizer=self.activation_fake_quantize_residual)
+            outs.append(y)
+        return torch.stack(outs)

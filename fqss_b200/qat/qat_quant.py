@@ -1,0 +1,127 @@
+"""B200 mirror of `quantization/qat/qat_quant.py` (hot-path subset).
+
+Same public names, constructor signatures, Parameter names/shapes and observer semantics as the
+reference; the arithmetic runs in libfqss_sm100.so (no torch elementwise chain, no host syncs):
+  round_ste / linear_quantize ............ qat_quant.py:88-89, :124-147
+  GradientActivationFakeQuantize ......... qat_quant.py:206-242
+  GradientWeightFakeQuantize ............. qat_quant.py:350-381
+  get_activation_quantizer / get_weight_quantizer ... :384-396
+Not provided (never reached by the ConvTasNet recipe): mu-law quantiser (`nl=True`), MSE-histogram
+observer, dynamic quantiser, export-only Torch*FakeQuantize, scale_grad=True.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def _default_device():
+    return torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def round_ste(x):
+    """rint with identity gradient.  Kept for API parity; the kernels fuse it."""
+    return x + (torch.round(x) - x).detach()
+
+
+def linear_quantize(x, min_range, max_range, n_bits, sign=True, sym=False, scale_grad=False):
+    """Uniform (sym=False) / symmetric per-channel (sym=True) fake-quant with STE gradients."""
+    if scale_grad:
+        raise NotImplementedError("scale_grad=True is not on the FQSS ConvTasNet path")
+    if not sym:
+        if min_range.numel() != 1:
+            raise NotImplementedError("activation quantiser is per-tensor")
+        return ops.FakeQuantAct.apply(x, min_range, max_range, int(n_bits))
+    if not sign:
+        raise NotImplementedError("unsigned symmetric weights are not on the FQSS ConvTasNet path")
+    axis = 0
+    for d in range(min_range.dim()):
+        if min_range.shape[d] > 1:
+            axis = d
+            break
+    else:
+        # per-tensor range: any size-1 axis of x works as the "channel" axis (decoder: [Ci,1,K] -> axis 1)
+        ones = [d for d in range(x.dim()) if x.shape[d] == 1]
+        if not ones:
+            raise NotImplementedError("per-tensor symmetric range needs a size-1 channel axis")
+        axis = ones[0]
+    return ops.FakeQuantWeight.apply(x, min_range, max_range, axis, int(n_bits))
+
+
+class GradientActivationFakeQuantize(nn.Module):
+    """Per-tensor asymmetric activation quantiser with learnable range and an EMA observer."""
+
+    def __init__(self, gradient_based, n_bits=8, sym=False, scale_grad=False):
+        super().__init__()
+        if sym or scale_grad:
+            raise NotImplementedError("sym / scale_grad activation quantisers are not on the ConvTasNet path")
+        self.n_bits = n_bits
+        self.sym = sym
+        self.min_range = nn.Parameter(torch.tensor([-0.5]), requires_grad=gradient_based)
+        self.max_range = nn.Parameter(torch.tensor([0.5]), requires_grad=gradient_based)
+        self.max_observations = 50
+        self.observer_mode = True
+        self.alpha = 0.9
+        self.n_iter = 0
+        self.sign = True
+        self.scale_grad = scale_grad
+
+    def enable_observer(self, observer_mode):
+        self.observer_mode = observer_mode
+
+    # -- protocol used by the fused LayerQ wrappers -------------------------------------------
+    def observing(self):
+        """True while this call must record ranges and pass data through (qat_quant.py:228)."""
+        return self.observer_mode and self.n_iter < self.max_observations
+
+    def observe_(self, x):
+        """min/max EMA update on the device (no .item(), no assert): qat_quant.py:229-232."""
+        self.n_iter += 1
+        ops.act_observe_(x, self.min_range.data, self.max_range.data, self.alpha)
+
+    def forward(self, x):
+        if self.observing():
+            self.observe_(x)
+            return x
+        return ops.FakeQuantAct.apply(x, self.min_range, self.max_range, self.n_bits)
+
+
+class GradientWeightFakeQuantize(nn.Module):
+    """Per-output-channel symmetric signed weight quantiser; first call captures amin/amax."""
+
+    def __init__(self, gradient_based, weight_shape, n_bits=8, sym=True, ch_out_idx=0, scale_grad=False):
+        super().__init__()
+        if not sym or scale_grad:
+            raise NotImplementedError("only the symmetric weight quantiser is on the ConvTasNet path")
+        self.n_bits = n_bits
+        self.sym = sym
+        self.axis = ch_out_idx
+        self.x_dims = [d for d in range(len(weight_shape)) if d != ch_out_idx]
+        shape = [1] * len(weight_shape)
+        shape[ch_out_idx] = weight_shape[ch_out_idx]
+        dev = _default_device()
+        self.min_range = nn.Parameter(-0.5 * torch.ones(shape, device=dev), requires_grad=gradient_based)
+        self.max_range = nn.Parameter(0.5 * torch.ones(shape, device=dev), requires_grad=gradient_based)
+        self.observer_mode = True
+        self.sign = True
+        self.scale_grad = scale_grad
+
+    def enable_observer(self, observer_mode):
+        self.observer_mode = observer_mode
+
+    def forward(self, w):
+        if self.observer_mode:
+            ops.weight_observe_(w, self.min_range.data, self.max_range.data, self.axis)
+            self.observer_mode = False
+            return w
+        return ops.FakeQuantWeight.apply(w, self.min_range, self.max_range, self.axis, self.n_bits)
+
+
+def get_activation_quantizer(gradient_based=True, nl=False, n_bits=8):
+    if nl:
+        raise NotImplementedError("mu-law (inout_nl_quant) quantiser is not on the FQSS ConvTasNet path")
+    return GradientActivationFakeQuantize(gradient_based, n_bits=n_bits)
+
+
+def get_weight_quantizer(gradient_based=True, weight_shape=(1, 1, 1), n_bits=8, ch_out_idx=0):
+    return GradientWeightFakeQuantize(gradient_based, weight_shape, n_bits=n_bits, ch_out_idx=ch_out_idx)

@@ -1,0 +1,188 @@
+/* fqss.h -- C ABI of libfqss_sm100.so: the B200 (sm_100a) kernels behind the FQSS
+ * `quantization/qat` operator API (ssi-research/FQSS).
+ *
+ * The reference has no native code; every entry point below replaces a chain of ATen library
+ * calls issued by a reference Python function (cited as file:line under the reference tree).
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers owned by the caller
+ *     (PyTorch caching allocator); the library never allocates, frees or retains device memory.
+ *   - activations are "row tensors": `rows` rows of `cols` fp32 values, row r starting at
+ *     base + r*ld (ld >= cols, in elements).  A [B,C,M] tensor has rows=B*C, cols=M.  The fast
+ *     (128-bit) path needs ld % 4 == 0 and a 16-byte aligned base; other layouts run a scalar path.
+ *   - quantiser ranges (min_range / max_range Parameters) are read on the device; no host syncs.
+ *   - every call is asynchronous and enqueues on `stream` (a cudaStream_t passed as void*).
+ *   - return 0 on success; <0 on error: -1 bad argument, -2 misaligned, -3 workspace too small,
+ *     -4 CUDA launch error.  fqss_last_error() returns a thread-local message.
+ *   - `ws` is caller-provided scratch (device); required size from fqss_ws_bytes().
+ */
+#ifndef FQSS_H_
+#define FQSS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQSS_ABI_VERSION 2
+
+int fqss_abi_version(void);
+const char* fqss_last_error(void);
+/* scratch bytes sufficient for ANY single call below on tensors of up to `rows` rows. */
+size_t fqss_ws_bytes(int64_t rows);
+
+/* ---------------------------------------------------------------------------------------------
+ * Q2  activation fake-quant, standalone  (qat_quant.py:136-147 linear_quantize sym=False;
+ *     module GradientActivationFakeQuantize.forward :227-242)
+ *   y = delta*clip(rint((x-min)/delta),0,2^b-1)+min ; code (optional, may be NULL) = the clipped integer
+ *   bwd: gx = ((g*delta)*mask)/delta ; g_rmin/g_rmax = range gradients (overwritten, 1 float each)
+ * ------------------------------------------------------------------------------------------- */
+int fqss_fq_act_fwd(const float* x, float* y, uint8_t* code, int64_t n,
+                    const float* rmin, const float* rmax, int n_bits, void* stream);
+int fqss_fq_act_bwd(const float* g, const float* x, float* gx, float* g_rmin, float* g_rmax, int64_t n,
+                    const float* rmin, const float* rmax, int n_bits, void* ws, size_t ws_bytes, void* stream);
+
+/* Q3  weight fake-quant, symmetric signed per-channel (qat_quant.py:126-135; module :350-381).
+ *     w viewed as [outer, ch, inner]; ranges have `ch` entries (ch_out_idx=0: outer=1; =1: outer=d0). */
+int fqss_fq_weight_fwd(const float* w, float* wq, int8_t* code, int outer, int ch, int inner,
+                       const float* rmin, const float* rmax, int n_bits, void* stream);
+int fqss_fq_weight_bwd(const float* g, const float* w, float* gw, float* g_rmin, float* g_rmax,
+                       int outer, int ch, int inner, const float* rmin, const float* rmax, int n_bits,
+                       void* stream);
+/* first-call observer: max_range = amax, min_range = amin over non-channel dims (qat_quant.py:373-375) */
+int fqss_weight_observe(const float* w, int outer, int ch, int inner, float* rmin, float* rmax, void* stream);
+
+/* Q4  activation observer: min <- a*min + (1-a)*x.min(), max likewise (qat_quant.py:228-232) */
+int fqss_act_observe(const float* x, int64_t rows, int64_t cols, int64_t ld, float* rmin, float* rmax,
+                     double alpha, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * L1  fused "op -> nonlinearity -> fake-quant" pointwise layers (qat_layers.py: AddQ :62, MulQ :86,
+ *     GroupNormQ :438, NlQ :511, and the nl+FQ tail of Conv1dQ :124 / Conv1dNlQ :188)
+ * ------------------------------------------------------------------------------------------- */
+enum {
+    FQSS_PW_IDENT = 0, /* z = x1                         (tail of Conv1dQ)            */
+    FQSS_PW_PRELU = 1, /* z = x1>0 ? x1 : slope*x1       (Conv1dNlQ / NlQ with PReLU)  */
+    FQSS_PW_RELU = 2,  /* z = max(x1,0)                                                */
+    FQSS_PW_ADD = 3,   /* z = x1 + x2                    (AddQ)                        */
+    FQSS_PW_SUB = 4,   /* z = x1 - x2                    (RQB: Y - Y_q)                */
+    FQSS_PW_MUL = 5,   /* z = x1 * x2, x2 broadcast over `bcast` sources (MulQ)        */
+    FQSS_PW_GLN = 6    /* z = gLN(x1) = (x1-mu_b)*rstd_b*gamma_c + beta_c (GroupNormQ) */
+};
+
+typedef struct fqss_pw_desc {
+    int32_t kind;    /* FQSS_PW_*                                                       */
+    int32_t quant;   /* 1: y = FQ(z) with (rmin,rmax,n_bits); 0: y = z (observer/float) */
+    int32_t n_bits;
+    int32_t C;       /* channels per sample: channel of row r is r % C, sample r / C    */
+    int32_t bcast;   /* MUL: x1 has rows [B,bcast,C], x2 has rows [B,C]                 */
+    int32_t _pad;
+    int64_t rows, cols;
+    const float* x1; int64_t ld1;
+    const float* x2; int64_t ld2;
+    float* y;        int64_t ldy;
+    const float* slope;   /* PRELU: 1 element                                           */
+    const float* gamma;   /* GLN: C                                                     */
+    const float* beta;    /* GLN: C                                                     */
+    const double* stats;  /* GLN: per sample {sum, sum of squares} from fqss_gln_stats   */
+    float eps;
+    float _pad2;
+    const float* rmin; const float* rmax;
+} fqss_pw_desc;
+
+int fqss_pw_fwd(const fqss_pw_desc* d, void* stream);
+
+/* backward of fqss_pw_fwd.  g = dL/dy (rows x cols, ld ldg).  Outputs (each may be NULL if unused):
+ *   gx1 (ld ldg1), gx2 (SUB/MUL only; MUL: rows/bcast rows), g_rmin/g_rmax (1), g_slope (1),
+ *   g_gamma/g_beta (C).  Small outputs are OVERWRITTEN. */
+typedef struct fqss_pw_grads {
+    const float* g; int64_t ldg;
+    float* gx1; int64_t ldg1;
+    float* gx2; int64_t ldg2;
+    float* g_rmin; float* g_rmax;
+    float* g_slope;
+    float* g_gamma; float* g_beta;
+} fqss_pw_grads;
+
+int fqss_pw_bwd(const fqss_pw_desc* d, const fqss_pw_grads* o, void* ws, size_t ws_bytes, void* stream);
+
+/* per-sample {sum, sumsq} over C*cols elements -> stats[2*B] (double), for gLN (GroupNorm(1,C)) */
+int fqss_gln_stats(const float* x, int64_t rows, int64_t cols, int64_t ld, int C, double* stats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * L1/L2  convolutions of the separator (F.conv1d / F.conv_transpose1d call sites in
+ *        qat_layers.py:138,203,1030,1189,1194,1332).  Weights are the already fake-quantised values.
+ * ------------------------------------------------------------------------------------------- */
+/* 1x1 conv:  y[b,o,m] = bias[o] + sum_i w[o,i] x[b,i,m]      (fp32 FFMA path, "rel 1e-3" tier) */
+int fqss_conv1x1_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy,
+                     int B, int Ci, int Co, int M, void* stream);
+/* gx[b,i,m] = sum_o w[o,i] gy[b,o,m] */
+int fqss_conv1x1_dgrad(const float* gy, int64_t ldgy, const float* w, float* gx, int64_t ldgx,
+                       int B, int Ci, int Co, int M, void* stream);
+/* gw[o,i] = sum_{b,m} gy[b,o,m] x[b,i,m] ; gbias[o] = sum_{b,m} gy[b,o,m]  (gbias may be NULL) */
+int fqss_conv1x1_wgrad(const float* gy, int64_t ldgy, const float* x, int64_t ldx, float* gw, float* gbias,
+                       int B, int Ci, int Co, int M, void* ws, size_t ws_bytes, void* stream);
+
+/* depthwise k-tap dilated conv, zero padding = dil*(k-1)/2 ("same"): convtasnetq.py:28-29 */
+int fqss_dwconv_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy,
+                    int B, int C, int M, int K, int dil, void* stream);
+int fqss_dwconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, const float* w,
+                    float* gx, int64_t ldgx, float* gw, float* gbias,
+                    int B, int C, int M, int K, int dil, void* ws, size_t ws_bytes, void* stream);
+
+/* encoder-type strided conv, no padding, no bias: y[b,o,m] = sum_{c,k} w[o,c,k] x[b,c,m*stride+k] */
+int fqss_sconv_fwd(const float* x, int64_t ldx, const float* w, float* y, int64_t ldy,
+                   int B, int Cin, int Co, int T, int K, int stride, void* stream);
+/* gx (may be NULL) [B,Cin,T]; gw (may be NULL) [Co,Cin,K] */
+int fqss_sconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, const float* w,
+                   float* gx, int64_t ldgx, float* gw, int B, int Cin, int Co, int T, int K, int stride,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* decoder-type transposed conv to ONE output channel (overlap-add), weight [Ci,1,K]:
+ *   y[b,t] = sum_{c,m,k: m*stride+k=t} w[c,k] x[b,c,m] */
+int fqss_tconv_fwd(const float* x, int64_t ldx, const float* w, float* y, int64_t ldy,
+                   int B, int Ci, int M, int K, int stride, void* stream);
+int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, const float* w,
+                   float* gx, int64_t ldgx, float* gw, int B, int Ci, int M, int K, int stride,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * P1  FQSS splitter / reconstructor (process.py:10-52)
+ * ------------------------------------------------------------------------------------------- */
+/* peak[0] = max |x| over the whole batch (one scalar, process.py:23) */
+int fqss_absmax(const float* x, int64_t rows, int64_t cols, int64_t ld, float* peak,
+                void* ws, size_t ws_bytes, void* stream);
+/* y[b, s, t], s < n_split: successive 8-bit floor quantisations of x[b,t]/peak */
+int fqss_split(const float* x, int64_t ldx, const float* peak, float* y, int64_t ldy,
+               int B, int T, int n_split, int n_bits, void* stream);
+/* y[r,t] = sum_i parts[i][r,t] * (0.5*2^-(n_bits-1))^i ; parts stacked with stride part_stride */
+int fqss_combine(const float* parts, int64_t part_stride, int64_t ld, float* y, int64_t ldy,
+                 int64_t rows, int T, int n_comb, int n_bits, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * S1-S3  FQSS KD SI-SDR loss (mysystem.py:124-151, wsdr.py:46-95, asteroid PIT), n_src == 2
+ *   est, fest, tgt: [B,2,T] (ld = row pitch).  out[0]=loss, out[1]=kd_loss(logged), out[2]=val_loss
+ *   (mean_b PIT neg-SI-SDR dB of est vs tgt).  gest (may be NULL): dL/dest, same layout as est.
+ * ------------------------------------------------------------------------------------------- */
+int fqss_kd_loss(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt,
+                 int B, int T, float kd_lambda, float* out, float* gest, int64_t ldg,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * D1  flat gradient arena helpers for the data-parallel exchange (asteroid_librimix_trainer.py:125-135)
+ *   sumsq[0] = sum g^2 (for the global-norm clip, gradient_clip_val=5.0)
+ *   scale_clip: g *= pre_scale * min(1, max_norm / (sqrt(sumsq*pre_scale^2) + 1e-6))
+ * ------------------------------------------------------------------------------------------- */
+int fqss_arena_sumsq(const float* g, int64_t n, float* sumsq, void* ws, size_t ws_bytes, void* stream);
+int fqss_arena_scale_clip(float* g, int64_t n, const float* sumsq, float pre_scale, float max_norm, void* stream);
+/* fused Adam step over the flat arena (torch.optim.Adam semantics, weight_decay=0, amsgrad=False) */
+int fqss_arena_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                    float eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQSS_H_ */
