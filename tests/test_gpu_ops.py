@@ -1,0 +1,259 @@
+"""GPU: kernel-level parity of the C-ABI ops against the golden vectors of the UNMODIFIED reference
+and against the CPU oracle.  Integer codes / quantised values are bit-exact; reductions (range
+gradients, weight gradients) agree to fp32 summation round-off."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import fqss_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_act_fake_quant_bit_exact(golden):
+    from fqss_b200 import ops
+    g = golden("q_ops.npz")
+    for ci in range(6):
+        x = T(g[f"act{ci}_x"]).to(DEV).requires_grad_(True)
+        lo, hi = g[f"act{ci}_range"]
+        rmin = torch.tensor([lo], device=DEV, requires_grad=True)
+        rmax = torch.tensor([hi], device=DEV, requires_grad=True)
+        y = ops.FakeQuantAct.apply(x, rmin, rmax, 8)
+        _, code = ops.fake_quant_codes(x.detach(), rmin.detach(), rmax.detach())
+        assert torch.equal(code.cpu(), T(g[f"act{ci}_code"])), "codes differ (case %d)" % ci
+        assert torch.equal(y.detach().cpu(), T(g[f"act{ci}_y"]))
+        y.backward(T(g[f"act{ci}_go"]).to(DEV))
+        assert torch.equal(x.grad.cpu(), T(g[f"act{ci}_gx"]))
+        for got, want in ((rmin.grad, g[f"act{ci}_gmin"]), (rmax.grad, g[f"act{ci}_gmax"])):
+            assert abs(got.item() - float(want[0])) <= 2e-5 * max(1.0, abs(float(want[0]))), (ci, got.item(), want)
+
+
+def test_weight_fake_quant_bit_exact(golden):
+    from fqss_b200 import ops
+    g = golden("q_ops.npz")
+    for ci in range(4):
+        axis = int(g[f"w{ci}_axis"])
+        w = T(g[f"w{ci}_w"]).to(DEV).requires_grad_(True)
+        rmin = T(g[f"w{ci}_min"]).to(DEV).requires_grad_(True)
+        rmax = T(g[f"w{ci}_max"]).to(DEV).requires_grad_(True)
+        y = ops.FakeQuantWeight.apply(w, rmin, rmax, axis, 8)
+        assert torch.equal(ops.weight_codes(w.detach(), rmin.detach(), rmax.detach(), axis).cpu(), T(g[f"w{ci}_code"]))
+        assert torch.equal(y.detach().cpu(), T(g[f"w{ci}_y"]))
+        y.backward(T(g[f"w{ci}_go"]).to(DEV))
+        assert torch.equal(w.grad.cpu(), T(g[f"w{ci}_gw"]))
+        assert torch.allclose(rmin.grad.cpu(), T(g[f"w{ci}_gmin"]), rtol=1e-4, atol=1e-6)
+        assert torch.allclose(rmax.grad.cpu(), T(g[f"w{ci}_gmax"]), rtol=1e-4, atol=1e-6)
+
+
+def test_observers(golden):
+    from fqss_b200.qat.qat_quant import GradientActivationFakeQuantize, GradientWeightFakeQuantize
+    g = golden("q_ops.npz")
+    q = GradientActivationFakeQuantize(True).to(DEV)
+    for x, (emin, emax) in zip(T(g["obs_x"]), g["obs_trace"]):
+        xd = x.to(DEV)
+        assert q(xd) is xd                               # observer passes data through (qat_quant.py:233)
+        assert q.min_range.item() == emin and q.max_range.item() == emax
+    w = T(g["w0_w"]).to(DEV)
+    wq = GradientWeightFakeQuantize(True, w.shape).to(DEV)
+    assert wq(w) is w and wq.observer_mode is False
+    lo, hi = O.observe_weight(w.cpu(), 0)
+    assert torch.equal(wq.min_range.detach().cpu(), lo) and torch.equal(wq.max_range.detach().cpu(), hi)
+
+
+def test_splitter_reconstructor_bit_exact(golden):
+    from fqss_b200.process import postprocess, preprocess
+    g = golden("split.npz")
+    x = T(g["x"]).to(DEV)
+    assert torch.equal(preprocess(x, n_splitter=2).cpu(), T(g["y2"]))
+    assert torch.equal(preprocess(x, n_splitter=3).cpu(), T(g["y3"]))
+    dec = T(g["dec"]).to(DEV).requires_grad_(True)
+    z = postprocess(dec, n_combiner=2)
+    assert torch.equal(z.detach().cpu(), T(g["z"]))
+    z.sum().backward()
+    assert torch.equal(dec.grad[0].cpu(), torch.ones_like(z).cpu())
+    assert torch.allclose(dec.grad[1].cpu(), torch.full_like(z, 0.5 / 128).cpu())
+    # ragged / odd lengths and a 2-D input
+    x2 = torch.randn(3, 1001, device=DEV)
+    assert torch.equal(preprocess(x2, n_splitter=2).cpu(), O.split_input(x2.cpu(), 2))
+
+
+def test_kd_loss_golden(golden):
+    from fqss_b200.losses import fqss_kd_loss
+    g = golden("loss.npz")
+    est = T(g["est"]).to(DEV).requires_grad_(True)
+    loss, kd, val = fqss_kd_loss(est, T(g["fest"]).to(DEV), T(g["tgt"]).to(DEV), 0.1)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss"])) < 2e-4
+    assert rel(est.grad, T(g["gest"])) < 1e-4
+    _, per_b = O.neg_sisdr_db_pit(T(g["est"]), T(g["tgt"]))
+    assert abs(val.item() - per_b.mean().item()) < 2e-4
+
+
+@pytest.mark.parametrize("B,T_", [(1, 257), (5, 4001)])
+def test_kd_loss_vs_oracle_random(B, T_):
+    from fqss_b200.losses import fqss_kd_loss
+    gen = torch.Generator().manual_seed(B)
+    tgt = torch.randn(B, 2, T_, generator=gen) * 0.1 + 0.02
+    est = (tgt[:, [1, 0]] * 0.9 + 0.03 * torch.randn(B, 2, T_, generator=gen)).requires_grad_(True)
+    fest = tgt[:, [1, 0]] + 0.01 * torch.randn(B, 2, T_, generator=gen)
+    lo, kdo = O.fqss_kd_loss(est, fest, tgt, 0.1)
+    lo.backward()
+    e2 = est.detach().to(DEV).requires_grad_(True)
+    l, kd, _ = fqss_kd_loss(e2, fest.to(DEV), tgt.to(DEV), 0.1)
+    l.backward()
+    assert abs(l.item() - lo.item()) < 2e-4 and abs(kd.item() - kdo.item()) < 2e-4
+    assert rel(e2.grad, est.grad) < 2e-4
+
+
+def _pw_case(kind, shape, seed=0, quant=True):
+    """run one pointwise+FQ layer on GPU and through the oracle's torch ops on CPU"""
+    from fqss_b200 import _native as N
+    from fqss_b200 import ops
+    gen = torch.Generator().manual_seed(seed)
+    x1 = torch.randn(shape, generator=gen)
+    x2 = None
+    slope = torch.tensor([0.25])
+    C = shape[-2]
+    gamma, beta = torch.rand(C, generator=gen) + 0.5, torch.randn(C, generator=gen) * 0.1
+    if kind in (N.PW_ADD, N.PW_SUB):
+        x2 = torch.randn(shape, generator=gen)
+    if kind == N.PW_MUL:
+        x2 = torch.rand((shape[0], 1) + tuple(shape[2:]), generator=gen)
+    rmin, rmax = torch.tensor([-1.3]), torch.tensor([1.9])
+    go = torch.randn(shape, generator=gen)
+
+    def leaf(t):
+        return None if t is None else t.clone().requires_grad_(True)
+    c = [leaf(t) for t in (x1, x2, slope, gamma, beta, rmin, rmax)]
+    z = {N.PW_IDENT: lambda: c[0], N.PW_PRELU: lambda: F.prelu(c[0], c[2]), N.PW_RELU: lambda: F.relu(c[0]),
+         N.PW_ADD: lambda: c[0] + c[1], N.PW_SUB: lambda: c[0] - c[1], N.PW_MUL: lambda: c[0] * c[1],
+         N.PW_GLN: lambda: F.group_norm(c[0], 1, c[3], c[4], 1e-8)}[kind]()
+    yo = O.fq_act(z, c[5], c[6]) if quant else z
+    yo.backward(go)
+    d = [None if t is None else t.clone().to(DEV).requires_grad_(True) for t in (x1, x2, slope, gamma, beta, rmin, rmax)]
+    y = ops.pointwise_fq(kind, d[0], d[1], d[2] if kind == N.PW_PRELU else None, d[3] if kind == N.PW_GLN else None,
+                         d[4] if kind == N.PW_GLN else None, d[5], d[6], quant, 8, 1e-8)
+    y.backward(go.to(DEV))
+    return z, yo, c, y, d
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 999), (1, 3, 4100), (3, 16, 64)])
+def test_pointwise_fq_layers_vs_oracle(shape):
+    from fqss_b200 import _native as N
+    for kind in (N.PW_IDENT, N.PW_PRELU, N.PW_RELU, N.PW_ADD, N.PW_SUB, N.PW_GLN):
+        for quant in (True, False):
+            z, yo, c, y, d = _pw_case(kind, shape, seed=kind, quant=quant)
+            if kind == N.PW_GLN:
+                # statistics are reduced in a different order: allow rare +-1 code flips
+                step = (1.9 + 1.3) / 255
+                diff = (y.detach().cpu() - yo.detach()).abs()
+                assert diff.max() <= step * 1.001 + 1e-5 and (diff > 1e-5).float().mean() < 2e-3
+            else:
+                assert torch.equal(y.detach().cpu(), yo.detach()), (kind, quant)
+            assert rel(d[0].grad, c[0].grad) < (2e-3 if kind == N.PW_GLN else 1e-6), (kind, quant)
+            if kind in (N.PW_ADD, N.PW_SUB):
+                assert rel(d[1].grad, c[1].grad) < 1e-6
+            if kind == N.PW_PRELU:
+                assert rel(d[2].grad, c[2].grad) < 1e-4
+            if kind == N.PW_GLN:
+                assert rel(d[3].grad, c[3].grad) < 2e-3 and rel(d[4].grad, c[4].grad) < 2e-3
+            if quant:
+                tol = 5e-3 if kind == N.PW_GLN else 1e-4
+                assert rel(d[5].grad, c[5].grad) < tol and rel(d[6].grad, c[6].grad) < tol, (kind,)
+
+
+def test_mulq_broadcast_vs_oracle():
+    from fqss_b200 import _native as N
+    z, yo, c, y, d = _pw_case(N.PW_MUL, (2, 2, 8, 999), seed=5)
+    assert torch.equal(y.detach().cpu(), yo.detach())
+    assert rel(d[0].grad, c[0].grad) < 1e-6 and rel(d[1].grad, c[1].grad) < 1e-5
+    assert rel(d[5].grad, c[5].grad) < 1e-4 and rel(d[6].grad, c[6].grad) < 1e-4
+
+
+def _grads(fn, tensors, go):
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in tensors]
+    y = fn(*leaves)
+    y.backward(go)
+    return y.detach(), [None if l is None else l.grad for l in leaves]
+
+
+@pytest.mark.parametrize("B,Ci,Co,M", [(2, 32, 64, 999), (1, 128, 512, 300), (3, 24, 8, 131)])
+def test_conv1x1_vs_torch(B, Ci, Co, M):
+    from fqss_b200 import ops
+    gen = torch.Generator().manual_seed(M)
+    x, w, b = torch.randn(B, Ci, M, generator=gen), torch.randn(Co, Ci, 1, generator=gen) * 0.1, torch.randn(Co, generator=gen)
+    go = torch.randn(B, Co, M, generator=gen)
+    yo, gso = _grads(lambda x, w, b: F.conv1d(x, w, b), (x, w, b), go)
+    y, gs = _grads(lambda x, w, b: ops.Conv1x1.apply(x, w, b), (x.to(DEV), w.to(DEV), b.to(DEV)), go.to(DEV))
+    assert rel(y, yo) < 1e-5
+    for a, bb in zip(gs, gso):
+        assert rel(a, bb) < 1e-5
+
+
+@pytest.mark.parametrize("dil", [1, 4, 128])
+def test_depthwise_vs_torch(dil):
+    from fqss_b200 import ops
+    B, C, M = 2, 16, 1000
+    gen = torch.Generator().manual_seed(dil)
+    x, w, b = torch.randn(B, C, M, generator=gen), torch.randn(C, 1, 3, generator=gen), torch.randn(C, generator=gen)
+    go = torch.randn(B, C, M, generator=gen)
+    yo, gso = _grads(lambda x, w, b: F.conv1d(x, w, b, padding=dil, dilation=dil, groups=C), (x, w, b), go)
+    y, gs = _grads(lambda x, w, b: ops.DepthwiseConv.apply(x, w, b, dil), (x.to(DEV), w.to(DEV), b.to(DEV)), go.to(DEV))
+    assert rel(y, yo) < 1e-6
+    for a, bb in zip(gs, gso):
+        assert rel(a, bb) < 1e-5
+
+
+@pytest.mark.parametrize("Cin", [1, 2])
+def test_strided_and_transposed_conv_vs_torch(Cin):
+    from fqss_b200 import ops
+    B, Co, T_, K, s = 3, 48, 1208, 16, 8
+    gen = torch.Generator().manual_seed(Cin)
+    x, w = torch.randn(B, Cin, T_, generator=gen), torch.randn(Co, Cin, K, generator=gen) * 0.1
+    Mo = (T_ - K) // s + 1
+    go = torch.randn(B, Co, Mo, generator=gen)
+    yo, gso = _grads(lambda x, w: F.conv1d(x, w, None, stride=s), (x, w), go)
+    xin = x.to(DEV)
+    if Cin == 1:
+        y, gs = _grads(lambda x, w: ops.StridedConv.apply(x, w, s), (xin, w.to(DEV)), go.to(DEV))
+        assert rel(gs[0], gso[0]) < 1e-5
+    else:   # main encoder: the input needs no gradient
+        wl = w.to(DEV).requires_grad_(True)
+        yy = ops.StridedConv.apply(xin, wl, s)
+        yy.backward(go.to(DEV))
+        y, gs = yy.detach(), [None, wl.grad]
+    assert rel(y, yo) < 1e-5 and rel(gs[1], gso[1]) < 1e-5
+    # decoder
+    X, wd = torch.randn(B, Co, Mo, generator=gen), torch.randn(Co, 1, K, generator=gen) * 0.1
+    god = torch.randn(B, 1, (Mo - 1) * s + K, generator=gen)
+    yo, gso = _grads(lambda x, w: F.conv_transpose1d(x, w, None, stride=s), (X, wd), god)
+    y, gs = _grads(lambda x, w: ops.TransposedConv1.apply(x, w, s), (X.to(DEV), wd.to(DEV)), god.to(DEV))
+    assert rel(y, yo) < 1e-5 and rel(gs[0], gso[0]) < 1e-5 and rel(gs[1], gso[1]) < 1e-5
+
+
+def test_fq_act_full_size_properties():
+    """BASELINE-size tensor (B=32 x 512 x 3999 would be 262 MB; use B=8): idempotence, code range,
+    monotonicity -- size-independent properties of the quantiser."""
+    from fqss_b200 import ops
+    x = torch.randn(8 * 512 * 3999, device=DEV)
+    rmin, rmax = torch.tensor([-2.0], device=DEV), torch.tensor([3.0], device=DEV)
+    y, code = ops.fake_quant_codes(x, rmin, rmax)
+    y2, code2 = ops.fake_quant_codes(y, rmin, rmax)
+    assert torch.equal(code, code2) and torch.equal(y, y2)                   # FQ(FQ(x)) == FQ(x)
+    assert int(code.max()) == 255 and int(code.min()) == 0
+    xs, idx = torch.sort(x[: 1 << 20])
+    assert bool((code[: 1 << 20][idx].to(torch.int16).diff() >= 0).all())    # monotone in x
+    step = 5.0 / 255
+    inside = (x > -2.0) & (x < 3.0)
+    assert float((y - x)[inside].abs().max()) <= step / 2 * 1.0001
