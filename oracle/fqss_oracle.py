@@ -261,6 +261,8 @@ def _tcn_block(c: _Ctx, i: int, x):
     skip = c.aq(p + "skip_conv.activation_fake_quantize", F.conv1d(y, w, P.get(p + "skip_conv.conv1d.bias")))
     # AddQ                               (qat_layers.py:62-71)
     out = c.aq(p + "add.activation_fake_quantize", x + res)
+    c.rec(p + "in", x)
+    c.rec(p + "skip", skip)
     return out, skip
 
 

@@ -81,8 +81,8 @@ def test_splitter_reconstructor_bit_exact(golden):
     z = postprocess(dec, n_combiner=2)
     assert torch.equal(z.detach().cpu(), T(g["z"]))
     z.sum().backward()
-    assert torch.equal(dec.grad[0].cpu(), torch.ones_like(z).cpu())
-    assert torch.allclose(dec.grad[1].cpu(), torch.full_like(z, 0.5 / 128).cpu())
+    assert torch.equal(dec.grad[0].squeeze(-2).cpu(), torch.ones_like(z).cpu())
+    assert torch.allclose(dec.grad[1].squeeze(-2).cpu(), torch.full_like(z, 0.5 / 128).cpu())
     # ragged / odd lengths and a 2-D input
     x2 = torch.randn(3, 1001, device=DEV)
     assert torch.equal(preprocess(x2, n_splitter=2).cpu(), O.split_input(x2.cpu(), 2))
@@ -169,7 +169,8 @@ def test_pointwise_fq_layers_vs_oracle(shape):
             if kind == N.PW_GLN:
                 assert rel(d[3].grad, c[3].grad) < 2e-3 and rel(d[4].grad, c[4].grad) < 2e-3
             if quant:
-                tol = 5e-3 if kind == N.PW_GLN else 1e-4
+                # the oracle's own range-gradient sums are fp32 (ours fp64): agreement to fp32 summation error
+                tol = 5e-3 if kind == N.PW_GLN else 1e-3
                 assert rel(d[5].grad, c[5].grad) < tol and rel(d[6].grad, c[6].grad) < tol, (kind,)
 
 
