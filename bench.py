@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- FQSS ConvTasNet QAT train throughput (audio-seconds per second) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank/GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+A "step" is one full QAT step of BASELINE.json configs[1]: fake-quantised ConvTasNet student forward,
+float-teacher forward, FQSS KD SI-SDR loss, backward, gradient all-reduce, global-norm clip and Adam,
+on synthetic 4 s / 8 kHz two-speaker mixtures.  `value` times steps whose inputs are already in HBM;
+`e2e` times the same steps fed from pinned HOST buffers (H2D of mixture+sources and D2H of the loss
+inside the timed region).  Scaling is weak: the per-GPU batch is fixed (32), global batch = 32*N.
+
+`--impl reference` times the reference's CPU implementation of the same step -- the oracle port
+(oracle/fqss_oracle.py, bit-identical to ssi-research/FQSS on CPU; the reference itself is a Python
+tree that does not exist on the GPU box) -- on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEG_SECONDS = 4.0
+SAMPLE_RATE = 8000
+T = int(SEG_SECONDS * SAMPLE_RATE)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="fqss_b200", choices=["fqss_b200", "reference"])
+    ap.add_argument("--per-gpu-batch", type=int, default=32)
+    ap.add_argument("--global-batch", type=int, default=0, help=">0: strong scaling with this global batch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--small", action="store_true", help="reduced model (debug only; never a reported number)")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm, smax, reasons = [], 0, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = max(smax, float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step_factory(small=False):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fqss_oracle as O
+    from fqss_b200.testing import FULL_KW, SMALL_KW, _oracle_cfg, model_pair, oracle_params
+    torch.set_num_threads(os.cpu_count() or 1)
+    kw = SMALL_KW if small else FULL_KW
+    cfg = _oracle_cfg(kw)
+    model, fmodel = model_pair(kw, "cpu", seed=0)
+    P, fP = oracle_params(model), oracle_params(fmodel)
+    del model, fmodel
+    gen = torch.Generator().manual_seed(0)
+
+    def batch(B):
+        src = torch.randn(B, 2, T, generator=gen) * 0.05
+        return src.sum(1, keepdim=True), src
+    mix, src = batch(1)
+    st = O.calibrate(P, mix, cfg, passes=2)
+
+    def step(B):
+        mix, src = batch(B)
+        P.leafify()
+        t0 = time.perf_counter()
+        O.qat_step(P, fP, mix, src, cfg, st, 0.1)
+        return time.perf_counter() - t0
+    return step, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, cores = cpu_step_factory(args.small)
+    t_probe = step(1)                                   # also the first warm-up
+    total = max(1, args.steps + max(args.warmup - 1, 0))
+    B = 1
+    for cand in (4, 2):
+        if t_probe * cand * total <= 150.0:
+            B = cand
+            break
+    for _ in range(max(args.warmup - 1, 0)):
+        step(B)
+    times = [step(B) for _ in range(args.steps)]
+    dt = sum(times)
+    val = B * SEG_SECONDS * args.steps / dt
+    line = {"impl": "reference", "metric": "ConvTasNet QAT train audio-sec/sec", "value": val, "unit": "audio-s/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, B, 1),
+            "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": "oracle port of the reference step (bit-identical to ssi-research/FQSS on CPU), "
+                                       "batch %d x 4 s per step, %d steps" % (B, args.steps)},
+            "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_batch, world):
+    return {"workload": "ConvTasNet 2spk 8 kHz full FQSS QAT (W8A8, splitter/combiner 2/2, KD SI-SDR vs float teacher, "
+                        "lambda 0.1), 4 s segments" + (" [REDUCED MODEL - debug]" if args.small else ""),
+            "global_batch": per_gpu_batch * world, "per_gpu_batch": per_gpu_batch, "segment_s": SEG_SECONDS,
+            "sample_rate": SAMPLE_RATE, "parallelism": "dp%d" % world,
+            "l2": "inputs+activations per step (>10 GB) exceed the 126 MB L2; no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from fqss_b200 import _native as N
+    from fqss_b200.losses import fqss_kd_loss
+    from fqss_b200.parallel import ParamArena
+    from fqss_b200.qat.models.load_model import enable_observer
+    from fqss_b200.testing import FULL_KW, SMALL_KW, model_pair
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the fqss_b200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N.lib()
+    B = args.per_gpu_batch if not args.global_batch else args.global_batch // world
+    model, fmodel = model_pair(SMALL_KW if args.small else FULL_KW, dev, seed=0)
+    gen = torch.Generator().manual_seed(1000 + rank)
+    n_host = 2                                              # two pinned host batches, alternated
+    host = []
+    for _ in range(n_host):
+        src = (torch.randn(B, 2, T, generator=gen) * 0.05).pin_memory()
+        host.append((src.sum(1, keepdim=True).pin_memory(), src))
+    dev_batches = [(m.to(dev), s.to(dev)) for m, s in host]
+    # calibration: 2 observer passes, then steady state
+    with torch.no_grad():
+        for _ in range(2):
+            model(dev_batches[0][0][: min(B, 4)])
+    enable_observer(model, False)
+    arena = ParamArena(list(model.parameters()))
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(mix, src):
+        arena.zero_grad()
+        est = model(mix)
+        with torch.no_grad():
+            fest = fmodel(mix)
+        loss, _, _ = fqss_kd_loss(est, fest, src, 0.1)
+        loss.backward()
+        arena.gather_grads()
+        scale = arena.allreduce_mean()
+        arena.clip_and_step(pre_scale=scale, max_norm=5.0, lr=1e-3)
+        return loss
+
+    def timed(n, from_host):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record()
+        for i in range(n):
+            if from_host:
+                m, s = host[i % n_host]
+                mix, src = m.to(dev, non_blocking=True), s.to(dev, non_blocking=True)
+            else:
+                mix, src = dev_batches[i % n_host]
+            loss = step(mix, src)
+            if from_host:
+                loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, t0, time.time()
+
+    timed(max(args.warmup, 3), False)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    c0 = N.launch_count
+    ms, t0, t1 = timed(args.steps, False)
+    launches = (N.launch_count - c0)
+    ms_e2e, _, t2 = timed(args.steps, True)
+    clocks = sampler.stop(t0, t2) if rank == 0 else None
+    final_loss = float(loss_host.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    gb = B * world
+    val = gb * SEG_SECONDS * args.steps / (ms / 1e3)
+    val_e2e = gb * SEG_SECONDS * args.steps / (ms_e2e / 1e3)
+    line = {"metric": "ConvTasNet QAT train audio-sec/sec", "value": val, "unit": "audio-s/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
+            "dtype": "f32 (8-bit fake-quant codes, fp32 accumulate)", "data": "synthetic",
+            "config": workload_config(args, B, world),
+            "e2e": {"value": val_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * 3 * T * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss}
+    if world == 1 and not args.no_roofline:
+        try:
+            from fqss_b200.roofline import dominant_kernel_roofline
+            line["roofline"] = dominant_kernel_roofline(dev, B, ms / args.steps)
+        except Exception as e:      # never lose the bench line over the side measurement
+            line["roofline"] = {"error": repr(e)}
+    if world == 1 and not args.no_cpu_baseline:
+        del model, fmodel, arena
+        torch.cuda.empty_cache()
+        cstep, cores = cpu_step_factory(args.small)
+        cstep(1)
+        Bc = 2
+        ts = [cstep(Bc) for _ in range(2)]
+        cv = Bc * SEG_SECONDS * len(ts) / sum(ts)
+        line["cpu_baseline"] = {"value": cv, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                                "sample": "oracle port of the reference QAT step on host cores: batch %d x 4 s, %d timed steps "
+                                          "after 1 warm-up (%.1f s/step)" % (Bc, len(ts), sum(ts) / len(ts))}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

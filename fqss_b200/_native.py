@@ -61,6 +61,7 @@ _SIGS = {
     "fqss_sconv_bwd": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "fqss_tconv_fwd": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "fqss_tconv_bwd": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
+    "fqss_pw_gemm": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
     "fqss_absmax": (i32, [vp, i64, i64, i64, vp, vp, sz, vp]),
     "fqss_split": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),
     "fqss_combine": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp]),

@@ -68,7 +68,7 @@ def build(force=False, verbose=False):
                 sys.stderr.write("\n".join(bad[:40]) + "\n")
     if failed:
         raise RuntimeError("nvcc build failed")
-    cmd = [nvcc_path(), "-shared", "-o", LIB] + objs + ["-lcudart", "-lcuda"]
+    cmd = [nvcc_path(), "-shared", "-o", LIB] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
     with open(STAMP, "w") as f:
         f.write(dig)

@@ -76,6 +76,62 @@ __device__ __forceinline__ float actq_bwd(const ActQ& q, float x, float g, float
     return in ? __fdiv_rn(__fmul_rn(g, q.delta), q.delta) : 0.f;
 }
 
+// ---------------------------------------------------------------------------------------------
+// "fast-exact" activation quantiser for the ALU-bound fused kernels: the code is computed with a
+// reciprocal multiply and falls back to the IEEE division only when the result sits within 1e-3 of
+// a rounding boundary, so codes stay bit-identical to actq_code() at ~1/3 of the instructions.
+// ---------------------------------------------------------------------------------------------
+struct ActQF {
+    float mn, delta, inv, levels;
+};
+
+__device__ __forceinline__ ActQF load_actqf(const float* __restrict__ rmin, const float* __restrict__ rmax, int n_bits) {
+    ActQF q;
+    q.mn = __ldg(rmin);
+    q.levels = (float)((1 << n_bits) - 1);
+    q.delta = __fdiv_rn(__fsub_rn(__ldg(rmax), q.mn), q.levels);
+    q.inv = __fdiv_rn(1.f, q.delta);
+    return q;
+}
+
+// un-clamped rounded code X and the (approximate) pre-round value t
+__device__ __forceinline__ float actqf_round(const ActQF& q, float x, float& t) {
+    float d = __fsub_rn(x, q.mn);
+    t = d * q.inv;
+    float X = rintf(t);
+    if (fabsf(t - X) > 0.499f && fabsf(t) < 1024.f) {      // rare: ~2e-3 of elements
+        t = __fdiv_rn(d, q.delta);
+        X = rintf(t);
+    }
+    return X;
+}
+
+__device__ __forceinline__ float actqf_code(const ActQF& q, float x) {
+    float t;
+    float X = actqf_round(q, x, t);
+    return fminf(fmaxf(X, 0.f), q.levels);
+}
+
+__device__ __forceinline__ float actqf_decode(const ActQF& q, float c) { return __fadd_rn(__fmul_rn(q.delta, c), q.mn); }
+__device__ __forceinline__ float actqf_fq(const ActQF& q, float x) { return actqf_decode(q, actqf_code(q, x)); }
+
+// statistics-only variant (never decides a stored code): no boundary check
+__device__ __forceinline__ float actqf_fq_approx(const ActQF& q, float x) {
+    float X = rintf((x - q.mn) * q.inv);
+    return fmaf(fminf(fmaxf(X, 0.f), q.levels), q.delta, q.mn);
+}
+
+// backward through the quantiser: returns g * mask, accumulates sD += g*(clip(X) - m*t), sZ += g*(1-m)
+__device__ __forceinline__ float actqf_bwd(const ActQF& q, float x, float g, float& sD, float& sZ) {
+    float t;
+    float X = actqf_round(q, x, t);
+    bool in = (X >= 0.f) && (X <= q.levels);
+    float c = fminf(fmaxf(X, 0.f), q.levels);
+    sD = fmaf(g, in ? (X - t) : c, sD);
+    sZ += in ? 0.f : g;
+    return in ? g : 0.f;
+}
+
 struct WQ {
     float delta;
     float lo, hi;

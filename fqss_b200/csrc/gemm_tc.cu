@@ -1,0 +1,406 @@
+// gemm_tc.cu -- the 1x1 convolutions of the fused TCN path as persistent, warp-specialised
+// tcgen05 GEMMs (north_star item (c)).
+//
+//   D[frame, o] = sum_k A[frame, k] * Wc[o, k]          (frames on the 128 TMEM lanes, channels on columns)
+//
+// * A = activations [B][K][Mp] in bf16, read by TMA straight from the NCL layout as an MN-major operand
+//   (64-frame x 64-channel boxes, 128B swizzle); frames beyond M are zero-filled by TMA.
+// * Wc = weights [N][K] in bf16, K-major.  In the quantised model both operands are INTEGER CODES
+//   (activations 0..255, weights -128..127): every product and every partial sum (< 2^24) is exact in
+//   the fp32 accumulator, so the result is independent of accumulation order and differs from the
+//   reference's fp32 conv only by the final affine  y = s1[o]*acc + s0[o]  (two roundings).
+// * Epilogue (8 warps): tcgen05.ld -> registers -> fused tail (affine, PReLU, fake-quant, residual /
+//   skip adds, gLN statistics) -> coalesced global stores: one warp-store covers 32 consecutive frames
+//   of one channel row, so no shared-memory transpose is needed.
+// * Roles: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warp 2 TMEM allocator,
+//   warps 4-11 epilogue.  4-stage smem ring (A 16 KB + B up to 32 KB per stage), 2 TMEM accumulator
+//   stages so the epilogue of tile i overlaps the MMAs of tile i+1.  Grid = one CTA per SM.
+#include <cuda.h>
+
+#include "fqss_common.cuh"
+#include "tc_common.cuh"
+
+namespace fqss {
+
+int num_sms();
+
+namespace tcg {
+
+using namespace tc;
+
+constexpr int BM = 128;          // frames per tile (TMEM lanes)
+constexpr int BK = 64;           // channels per k-chunk (128 B of bf16 along K for the weights)
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB: two 64-frame boxes of 64 rows x 128 B
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr int MAXN = 1024;
+
+enum { EPI_STORE = 0, EPI_EXPAND = 1, EPI_RESSKIP = 2, EPI_BF16 = 3, EPI_ADD = 4 };
+
+struct Args {
+    int B, M, K, N;              // batch, valid frames, reduction channels, output channels
+    int64_t ld;                  // row pitch (elements) of every [.,.,Mp] activation tensor involved
+    const float* s1;             // [N] per-output-channel scale   (delta_w[o]*delta_a, or 1)
+    const float* s0;             // [N] per-output-channel offset  (delta_w[o]*min_a*R[o] + bias[o])
+    int quant;                   // 0: float model (no fake-quant in the tails)
+    // EPI_STORE / EPI_EXPAND / EPI_ADD: fp32 output [B][N][ld]
+    float* out_f32;
+    // EPI_BF16 (and optional for STORE): bf16 output [B][N][ld]
+    __nv_bfloat16* out_bf16;
+    // EPI_ADD: addend [B][N][ld]
+    const float* addend;
+    // EPI_EXPAND: gLN statistics of FQ(PReLU(y)) -> stats[2*B] (double, pre-zeroed)
+    const float* slope;
+    const float* q1_min; const float* q1_max;
+    double* stats;
+    // EPI_RESSKIP: columns [0,Nres) = residual conv, [Nres,N) = skip conv
+    int n_res;                   // 128, or 0 for the last block (no residual path)
+    int first_block;             // 1: skip accumulator starts here (no adds-quantiser)
+    float* res_y; float* skip_y;                 // pre-quant conv outputs (saved for backward) [B][128][ld]
+    const float* x_in;                           // block input (fake-quantised values) [B][128][ld]
+    float* x_out; __nv_bfloat16* x_out_op;       // block output: values and GEMM operand (codes, or values when !quant)
+    const float* skip_in; float* skip_out;       // running skip sum [B][128][ld]
+    const float* qres_min; const float* qres_max;
+    const float* qskip_min; const float* qskip_max;
+    const float* qadd_min; const float* qadd_max;
+    const float* qadds_min; const float* qadds_max;
+};
+
+struct __align__(8) Barriers {
+    uint64_t full[STAGES];
+    uint64_t empty[STAGES];
+    uint64_t tmem_full[2];
+    uint64_t tmem_empty[2];
+    uint32_t tmem_base;
+};
+
+template <int NT>
+__host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + NT * BK * 2; }
+
+template <int NT>
+__host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<NT>() + 2 * MAXN * 4 + (int)sizeof(Barriers) + 1024; }
+
+__device__ __forceinline__ float prelu(float y, float a) { return y > 0.f ? y : a * y; }
+
+template <int NT, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* s1s = reinterpret_cast<float*>(smem + STAGES * stage_bytes<NT>());
+    float* s0s = s1s + MAXN;
+    Barriers* bar = reinterpret_cast<Barriers*>(s0s + MAXN);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int mt = (p.M + BM - 1) / BM;
+    const int nt = p.N / NT;
+    const int num_tiles = p.B * mt * nt;
+    const int kchunks = p.K / BK;
+
+    for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {
+        s1s[i] = __ldg(p.s1 + i);
+        s0s[i] = __ldg(p.s0 + i);
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&bar->full[s], 1);
+            mbar_init(&bar->empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&bar->tmem_full[a], 1);
+            mbar_init(&bar->tmem_empty[a], EPI_WARPS);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bar->tmem_base, 2 * NT);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bar->tmem_base;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_idx = t % nt, mrow = t / nt;
+                const int b = mrow / mt, m0 = (mrow % mt) * BM;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&bar->empty[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * stage_bytes<NT>();
+                    uint8_t* sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(&bar->full[stage], stage_bytes<NT>());
+                    tma_load_3d(sa, &tmA, &bar->full[stage], m0, kc * BK, b);
+                    tma_load_3d(sa + A_STAGE_BYTES / 2, &tmA, &bar->full[stage], m0 + 64, kc * BK, b);
+                    tma_load_2d(sb, &tmB, &bar->full[stage], kc * BK, n_idx * NT);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(BM, NT, /*A MN-major*/ true, /*B K-major*/ false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                mbar_wait(&bar->tmem_empty[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * NT);
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&bar->full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * stage_bytes<NT>());
+                    const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // A (MN-major, SW128): 16 K-rows = 2048 B per UMMA_K step; LBO = next 64-frame box, SBO = 8 rows
+                        const uint64_t adesc = smem_desc_sw128(sa + k * 2048, A_STAGE_BYTES / 2, 1024);
+                        // B (K-major, SW128): 32 B per UMMA_K step inside the 128 B row; SBO = 8 rows
+                        const uint64_t bdesc = smem_desc_sw128(sb + k * 32, 16, 1024);
+                        umma_bf16(tmem_d, adesc, bdesc, idesc, (kc | k) ? 1u : 0u);
+                    }
+                    umma_commit(&bar->empty[stage]);
+                    if (kc == kchunks - 1) umma_commit(&bar->tmem_full[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue =================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may touch
+        const int h = (warp - 4) >> 2;          // column half
+        constexpr int COLS = NT / 2;
+        ActQF q1, qres, qskip, qadd, qadds;
+        float slope = 0.f;
+        if (EPI == EPI_EXPAND) {
+            slope = __ldg(p.slope);
+            if (p.quant) q1 = load_actqf(p.q1_min, p.q1_max, 8);
+        }
+        if (EPI == EPI_RESSKIP && p.quant) {
+            qskip = load_actqf(p.qskip_min, p.qskip_max, 8);
+            if (p.n_res) {
+                qres = load_actqf(p.qres_min, p.qres_max, 8);
+                qadd = load_actqf(p.qadd_min, p.qadd_max, 8);
+            }
+            if (!p.first_block) qadds = load_actqf(p.qadds_min, p.qadds_max, 8);
+        }
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n_idx = t % nt, mrow = t / nt;
+            const int b = mrow / mt, m0 = (mrow % mt) * BM;
+            const int m = m0 + q * 32 + lane;
+            const bool valid = m < p.M;
+            mbar_wait(&bar->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            float st_s = 0.f, st_ss = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS; c0 += 32) {
+                uint32_t v[32];
+                const int col = h * COLS + c0;
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + col), v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int o = n_idx * NT + col + j;
+                    const float y = fmaf(__uint_as_float(v[j]), s1s[o], s0s[o]);
+                    const int64_t idx = ((int64_t)b * p.N + o) * p.ld + m;
+                    if (EPI == EPI_STORE) {
+                        if (valid) {
+                            p.out_f32[idx] = y;
+                            if (p.out_bf16) p.out_bf16[idx] = __float2bfloat16_rn(y);
+                        }
+                    } else if (EPI == EPI_EXPAND) {
+                        if (valid) {
+                            p.out_f32[idx] = y;
+                            float z = prelu(y, slope);
+                            float a = p.quant ? actqf_fq_approx(q1, z) : z;
+                            st_s += a;
+                            st_ss = fmaf(a, a, st_ss);
+                        }
+                    } else if (EPI == EPI_BF16) {
+                        if (valid) p.out_bf16[idx] = __float2bfloat16_rn(y);
+                    } else if (EPI == EPI_ADD) {
+                        if (valid) p.out_f32[idx] = y + __ldg(p.addend + idx);
+                    } else if (EPI == EPI_RESSKIP) {
+                        if (valid) {
+                            if (o < p.n_res) {          // residual conv -> FQ -> (x + res) -> FQ
+                                const int64_t i2 = ((int64_t)b * p.n_res + o) * p.ld + m;
+                                p.res_y[i2] = y;
+                                float r = p.quant ? actqf_fq(qres, y) : y;
+                                float z = __fadd_rn(__ldg(p.x_in + i2), r);
+                                if (p.quant) {
+                                    float c = actqf_code(qadd, z);
+                                    p.x_out[i2] = actqf_decode(qadd, c);
+                                    p.x_out_op[i2] = __float2bfloat16_rn(c);
+                                } else {
+                                    p.x_out[i2] = z;
+                                    p.x_out_op[i2] = __float2bfloat16_rn(z);
+                                }
+                            } else {                    // skip conv -> FQ -> (skip_sum + skip) -> FQ
+                                const int os = o - p.n_res;
+                                const int64_t i2 = ((int64_t)b * (p.N - p.n_res) + os) * p.ld + m;
+                                p.skip_y[i2] = y;
+                                float sk = p.quant ? actqf_fq(qskip, y) : y;
+                                if (p.first_block) {
+                                    p.skip_out[i2] = sk;
+                                } else {
+                                    float z = __fadd_rn(__ldg(p.skip_in + i2), sk);
+                                    p.skip_out[i2] = p.quant ? actqf_fq(qadds, z) : z;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
+            if (EPI == EPI_EXPAND) {
+                double ds = warp_sum((double)st_s), dss = warp_sum((double)st_ss);
+                if (lane == 0) {
+                    atomicAdd(p.stats + 2 * b, ds);
+                    atomicAdd(p.stats + 2 * b + 1, dss);
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * NT);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// resolved through the runtime so that the library has no link-time dependency on libcuda
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+static int make_act_map(CUtensorMap* tm, const void* base, int B, int C, int M, int64_t ld) {
+    cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)C * (cuuint64_t)ld * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BK, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return -999;
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int make_w_map(CUtensorMap* tm, const void* base, int N, int K, int box_rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t es[2] = {1, 1};
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return -999;
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int NT, int EPI>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, cudaStream_t s) {
+    static bool configured = false;
+    constexpr int smem = smem_bytes<NT>();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("pw_gemm: cannot set %d B dynamic smem: %s", smem, cudaGetErrorString(e));
+            return -4;
+        }
+        configured = true;
+    }
+    const int mt = (a.M + BM - 1) / BM;
+    const int tiles = a.B * mt * (a.N / NT);
+    int grid = num_sms();
+    if (grid > tiles) grid = tiles;
+    pw_gemm_kernel<NT, EPI><<<grid, NUM_THREADS, smem, s>>>(ta, tb, a);
+    return check_launch("pw_gemm");
+}
+
+int run(int epi, const void* act_bf16, const void* w_bf16, const Args& a, cudaStream_t s) {
+    FQSS_REQUIRE(act_bf16 && w_bf16 && a.s1 && a.s0, -1, "pw_gemm: null operand");
+    FQSS_REQUIRE(a.B > 0 && a.M > 0 && a.K >= BK && a.K % BK == 0 && a.N >= 128 && a.N % 128 == 0 && a.N <= MAXN, -1,
+                 "pw_gemm: unsupported shape B=%d M=%d K=%d N=%d (K %% 64 == 0, N %% 128 == 0, N <= %d)", a.B, a.M, a.K, a.N, MAXN);
+    FQSS_REQUIRE(a.ld >= a.M && a.ld % 8 == 0, -2, "pw_gemm: row pitch must be a multiple of 8 elements (TMA 16 B strides)");
+    FQSS_REQUIRE(aligned16(act_bf16) && aligned16(w_bf16), -2, "pw_gemm: operands must be 16-byte aligned");
+    CUtensorMap ta, tb;
+    int r = make_act_map(&ta, act_bf16, a.B, a.K, a.M, a.ld);
+    FQSS_REQUIRE(r == 0, -4, "pw_gemm: cuTensorMapEncodeTiled(activations) failed (%d)", r);
+    const bool wide = (a.N % 256 == 0);
+    r = make_w_map(&tb, w_bf16, a.N, a.K, wide ? 256 : 128);
+    FQSS_REQUIRE(r == 0, -4, "pw_gemm: cuTensorMapEncodeTiled(weights) failed (%d)", r);
+#define FQSS_GEMM_CASE(E)                                 \
+    case E:                                               \
+        return wide ? launch<256, E>(ta, tb, a, s) : launch<128, E>(ta, tb, a, s);
+    switch (epi) {
+        FQSS_GEMM_CASE(EPI_STORE)
+        FQSS_GEMM_CASE(EPI_EXPAND)
+        FQSS_GEMM_CASE(EPI_RESSKIP)
+        FQSS_GEMM_CASE(EPI_BF16)
+        FQSS_GEMM_CASE(EPI_ADD)
+    }
+#undef FQSS_GEMM_CASE
+    set_error("pw_gemm: unknown epilogue %d", epi);
+    return -1;
+}
+
+}  // namespace tcg
+}  // namespace fqss
+
+using namespace fqss;
+
+extern "C" {
+
+// Generic entry (also the isolated test vehicle of the tensor path):
+//   out[b,o,m] = s1[o] * sum_k act[b,k,m] * w[o,k] + s0[o]     (+ addend[b,o,m] when given)
+// act, w: bf16.  out_f32 and/or out_bf16 may be given.
+int fqss_pw_gemm(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32, void* out_bf16,
+                 const float* addend, int B, int K, int N, int M, int64_t ld, void* stream) {
+    tcg::Args a{};
+    a.B = B; a.M = M; a.K = K; a.N = N; a.ld = ld; a.s1 = s1; a.s0 = s0; a.quant = 0;
+    a.out_f32 = out_f32; a.out_bf16 = (__nv_bfloat16*)out_bf16; a.addend = addend;
+    int epi = tcg::EPI_STORE;
+    if (addend) {
+        FQSS_REQUIRE(out_f32, -1, "pw_gemm: addend needs an fp32 output");
+        epi = tcg::EPI_ADD;
+    } else if (!out_f32) {
+        FQSS_REQUIRE(out_bf16, -1, "pw_gemm: no output given");
+        epi = tcg::EPI_BF16;
+    }
+    return tcg::run(epi, act_bf16, w_bf16, a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

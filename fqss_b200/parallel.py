@@ -1,0 +1,92 @@
+"""Data-parallel QAT plumbing: one process per GPU, batch sharded
+contiguously across ranks, ONE collective per step -- an all-reduce (sum, then 1/n) of a flat fp32
+gradient arena holding all 948 parameter tensors (5 133 123 floats = 20.5 MB) -- followed by the
+global-norm clip (gradient_clip_val=5.0) and Adam on the arena, both as single sm_100a kernels.
+
+Reference: pl.Trainer(strategy="ddp", gradient_clip_val=5.0) + make_optimizer(adam, lr 1e-3)
+(train_env/asteroid_librimix/asteroid_librimix_trainer.py:94,125-135).  Parameters that receive no
+gradient (block 23's dead res_conv/add) stay zero in the arena, which is what DDP's
+find_unused_parameters gives the reference.
+"""
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+from ._native import check, lib, ptr, stream_ptr, workspace
+
+
+def shard_bounds(global_batch, rank, world):
+    """Contiguous shard [lo, hi) of the global batch owned by `rank`."""
+    if global_batch % world != 0:
+        raise ValueError("global batch %d is not divisible by world size %d" % (global_batch, world))
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+class ParamArena:
+    """Flat fp32 storage for parameters, gradients and Adam moments.  `p.data` of every parameter is
+    re-pointed at a view into the arena so optimiser and collective work on one buffer."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        self.numel = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        pad = (-self.numel) % 4
+        self.flat = torch.zeros(self.numel + pad, device=dev)
+        self.grad = torch.zeros_like(self.flat)
+        self.exp_avg = torch.zeros_like(self.flat)
+        self.exp_avg_sq = torch.zeros_like(self.flat)
+        self.sumsq = torch.zeros(1, device=dev)
+        self.step_count = 0
+        self.views, self.grad_views = [], []
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            v = self.flat[off:off + n].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            self.views.append(v)
+            self.grad_views.append(self.grad[off:off + n].view(p.shape))
+            off += n
+
+    def gather_grads(self):
+        """Collect p.grad of every parameter into the gradient arena (zeros where a parameter got none)."""
+        have_dst, have_src = [], []
+        for p, gv in zip(self.params, self.grad_views):
+            if p.grad is None:
+                gv.zero_()
+            else:
+                have_dst.append(gv)
+                have_src.append(p.grad)
+        if have_dst:
+            torch._foreach_copy_(have_dst, have_src)
+
+    def allreduce_mean(self, group=None):
+        """The one exchange step of the path.  Returns the 1/world factor still to be applied (folded
+        into the clip kernel so the arena is touched once)."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+            return 1.0 / dist.get_world_size(group)
+        return 1.0
+
+    def clip_and_step(self, pre_scale=1.0, max_norm=5.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        if not self.flat.is_cuda:
+            raise N.FqssError("ParamArena.clip_and_step needs CUDA (no CPU fallback)")
+        n = self.flat.numel()
+        ws = workspace(0, self.flat.device)
+        s = stream_ptr()
+        check(lib().fqss_arena_sumsq(ptr(self.grad), n, ptr(self.sumsq), ptr(ws), ws.numel(), s))
+        check(lib().fqss_arena_scale_clip(ptr(self.grad), n, ptr(self.sumsq), float(pre_scale), float(max_norm), s))
+        self.step_count += 1
+        check(lib().fqss_arena_adam(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), self.step_count, s))
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+
+def reference_ddp_step_cpu(per_rank_grads):
+    """Semantics of the exchange on plain tensors (used by the gloo test): mean over ranks."""
+    n = len(per_rank_grads)
+    return [sum(gs) / n for gs in zip(*per_rank_grads)]

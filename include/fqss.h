@@ -150,6 +150,16 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
                    void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor-core (tcgen05 / TMEM / TMA) 1x1 convolution used by the fused TCN path:
+ *   out[b,o,m] = s1[o] * sum_k act[b,k,m] * w[o,k] + s0[o]  (+ addend[b,o,m])
+ * act [B][K][ld] and w [N][K] are bf16.  With integer fake-quant codes as operands the accumulation is
+ * exact (order independent); s1/s0 carry the de-quantisation affine and the bias.  K % 64 == 0,
+ * N % 128 == 0, ld % 8 == 0.  Outputs: out_f32 and/or out_bf16 ([B][N][ld]); addend needs out_f32.
+ * ------------------------------------------------------------------------------------------- */
+int fqss_pw_gemm(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32,
+                 void* out_bf16, const float* addend, int B, int K, int N, int M, int64_t ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * P1  FQSS splitter / reconstructor (process.py:10-52)
  * ------------------------------------------------------------------------------------------- */
 /* peak[0] = max |x| over the whole batch (one scalar, process.py:23) */

@@ -258,3 +258,32 @@ def test_fq_act_full_size_properties():
     step = 5.0 / 255
     inside = (x > -2.0) & (x < 3.0)
     assert float((y - x)[inside].abs().max()) <= step / 2 * 1.0001
+
+
+@pytest.mark.parametrize("B,K,N,M", [(2, 128, 512, 3999), (1, 512, 256, 1000), (3, 64, 128, 100), (2, 128, 1024, 257)])
+def test_tcgen05_pw_gemm_exact_integer_codes(B, K, N, M):
+    """The tensor-core 1x1 conv on integer fake-quant codes: every product / partial sum is an integer
+    < 2^24, so the fp32 accumulator is exact and must equal an int64 reference bit for bit."""
+    from fqss_b200 import tcn_engine as E
+    gen = torch.Generator().manual_seed(K + N)
+    ld = (M + 7) // 8 * 8
+    act = torch.randint(0, 256, (B, K, ld), generator=gen)
+    w = torch.randint(-128, 128, (N, K), generator=gen)
+    ref = torch.einsum("ok,bkm->bom", w.double(), act[:, :, :M].double())
+    s1 = torch.ones(N, device=DEV)
+    s0 = torch.zeros(N, device=DEV)
+    out = E.pw_gemm(act.to(DEV).to(torch.bfloat16), w.to(DEV).to(torch.bfloat16), s1, s0, M)
+    assert torch.equal(out[:, :, :M].double().cpu(), ref)
+    # affine + bf16 output + addend variants on real-valued operands
+    actf = (torch.randn(B, K, ld, generator=gen)).to(torch.bfloat16)
+    wf = (torch.randn(N, K, generator=gen) * 0.1).to(torch.bfloat16)
+    s1 = torch.rand(N, generator=gen) + 0.5
+    s0 = torch.randn(N, generator=gen)
+    add = torch.randn(B, N, ld, generator=gen)
+    ref = torch.einsum("ok,bkm->bom", wf.double(), actf[:, :, :M].double()) * s1.double()[None, :, None] + s0.double()[None, :, None]
+    o1 = E.pw_gemm(actf.to(DEV), wf.to(DEV), s1.to(DEV), s0.to(DEV), M)
+    assert rel(o1[:, :, :M], ref) < 1e-5
+    o2 = E.pw_gemm(actf.to(DEV), wf.to(DEV), s1.to(DEV), s0.to(DEV), M, addend=add.to(DEV))
+    assert rel(o2[:, :, :M], ref + add[:, :, :M].double()) < 1e-5
+    o3 = E.pw_gemm(actf.to(DEV), wf.to(DEV), s1.to(DEV), s0.to(DEV), M, out_dtype=torch.bfloat16)
+    assert rel(o3[:, :, :M].float(), ref) < 5e-3
