@@ -19,6 +19,7 @@
 
 #include "fqss_common.cuh"
 #include "tc_common.cuh"
+#include "gemm_tc.cuh"
 
 namespace fqss {
 
@@ -35,37 +36,6 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB: two 64-frame boxes of
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_WARPS = 8;
 constexpr int MAXN = 1024;
-
-enum { EPI_STORE = 0, EPI_EXPAND = 1, EPI_RESSKIP = 2, EPI_BF16 = 3, EPI_ADD = 4 };
-
-struct Args {
-    int B, M, K, N;              // batch, valid frames, reduction channels, output channels
-    int64_t ld;                  // row pitch (elements) of every [.,.,Mp] activation tensor involved
-    const float* s1;             // [N] per-output-channel scale   (delta_w[o]*delta_a, or 1)
-    const float* s0;             // [N] per-output-channel offset  (delta_w[o]*min_a*R[o] + bias[o])
-    int quant;                   // 0: float model (no fake-quant in the tails)
-    // EPI_STORE / EPI_EXPAND / EPI_ADD: fp32 output [B][N][ld]
-    float* out_f32;
-    // EPI_BF16 (and optional for STORE): bf16 output [B][N][ld]
-    __nv_bfloat16* out_bf16;
-    // EPI_ADD: addend [B][N][ld]
-    const float* addend;
-    // EPI_EXPAND: gLN statistics of FQ(PReLU(y)) -> stats[2*B] (double, pre-zeroed)
-    const float* slope;
-    const float* q1_min; const float* q1_max;
-    double* stats;
-    // EPI_RESSKIP: columns [0,Nres) = residual conv, [Nres,N) = skip conv
-    int n_res;                   // 128, or 0 for the last block (no residual path)
-    int first_block;             // 1: skip accumulator starts here (no adds-quantiser)
-    float* res_y; float* skip_y;                 // pre-quant conv outputs (saved for backward) [B][128][ld]
-    const float* x_in;                           // block input (fake-quantised values) [B][128][ld]
-    float* x_out; __nv_bfloat16* x_out_op;       // block output: values and GEMM operand (codes, or values when !quant)
-    const float* skip_in; float* skip_out;       // running skip sum [B][128][ld]
-    const float* qres_min; const float* qres_max;
-    const float* qskip_min; const float* qskip_max;
-    const float* qadd_min; const float* qadd_max;
-    const float* qadds_min; const float* qadds_max;
-};
 
 struct __align__(8) Barriers {
     uint64_t full[STAGES];

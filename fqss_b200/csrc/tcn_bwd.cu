@@ -1,0 +1,442 @@
+// tcn_bwd.cu -- backward of the fused TCN ConvBlock.  Every quantised activation is RECOMPUTED from
+// the saved pre-activations (y1, y3, res_y, skip_y) with the same device functions forward used, so
+// the straight-through masks match the forward codes exactly.  Stages (one launch each):
+//
+//   T   tail          g_x_out, g_skip_out -> dY2 (bf16, res|skip rows, pre-scaled by delta_w), g_xd, g_skip_in
+//   G   dgrad GEMM    dY2 x Wc2T -> g_a4 (bf16)                                    [tcgen05]
+//   W   wgrad GEMM    dY2 x a4_op -> dW2q                                          [tcgen05, split-K]
+//   P1  gLN2 sums     g_a4, y3 -> per-row {sum g_n3, sum g_n3*xhat3}, range sums of FQ4
+//   R   reduce        per-sample S1,S2 and per-channel dgamma,dbeta
+//   P2  gLN2/FQ3/PReLU backward  g_a4, y3 -> g_y3 (bf16)
+//   D   depthwise     g_y3, y1 -> g_n1 (bf16), dW_dw, db_dw, per-row gLN1 sums, range sums of FQ2   (row in smem)
+//   R   reduce
+//   Q   gLN1/FQ1/PReLU backward  g_n1, y1 -> dY1 (bf16, pre-scaled), db1
+//   G   dgrad GEMM    dY1 x Wc1T (+ g_xd) -> g_x_in (fp32)                          [tcgen05]
+//   W   wgrad GEMM    dY1 x x_op -> dW1q                                           [tcgen05, split-K]
+//   F   finalise      fp64 accumulators -> fp32 parameter gradients
+//
+// The 512-wide gradient tensors travel in bf16 (the "1e-2 bf16 GEMM path"); the residual-stream and
+// skip-sum gradients (128-wide) stay fp32 end to end.
+#include "fqss_common.cuh"
+#include "gemm_tc.cuh"
+#include "tcn_common.cuh"
+#include "wgrad_tc.cuh"
+
+namespace fqss {
+
+int num_sms();
+
+// fp64 accumulator block inside the workspace
+struct AccLayout {
+    int64_t q, slope, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, total;
+    __host__ __device__ AccLayout(int B, int Cio, int Chid) {
+        int64_t o = 0;
+        q = o; o += 16;
+        slope = o; o += 2;
+        db1 = o; o += Chid;
+        db2 = o; o += 2 * Cio;
+        dbdw = o; o += Chid;
+        dwdw = o; o += 3 * Chid;
+        row1 = o; o += 2 * (int64_t)B * Chid;
+        row2 = o; o += 2 * (int64_t)B * Chid;
+        samp1 = o; o += 2 * B;
+        samp2 = o; o += 2 * B;
+        total = o;
+    }
+};
+
+enum { Q1 = 0, Q2 = 1, Q3 = 2, Q4 = 3, QRES = 4, QSKIP = 5, QADD = 6, QADDS = 7 };
+
+__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ---------------------------------------------------------------------------------------------
+// T: tail backward over the 128-wide tensors.  grid = B*Cio rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    __shared__ double sh[10 * 32];
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Cio), o = (int)(r % p.Cio);
+    const int M = p.M;
+    const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
+    ActQF qres, qskip, qadd, qadds;
+    if (p.quant) {
+        qskip = load_actqf(p.qskip.rmin, p.qskip.rmax, 8);
+        if (p.has_res) {
+            qres = load_actqf(p.qres.rmin, p.qres.rmax, 8);
+            qadd = load_actqf(p.qadd.rmin, p.qadd.rmax, 8);
+        }
+        if (!p.first_block) qadds = load_actqf(p.qadds.rmin, p.qadds.rmax, 8);
+    }
+    const float sc_res = p.has_res ? __ldg(p.dws2 + o) : 0.f;
+    const float sc_skip = __ldg(p.dws2 + (p.has_res ? p.Cio : 0) + o);
+    __nv_bfloat16* dY = reinterpret_cast<__nv_bfloat16*>(g.dY2);
+    __nv_bfloat16* dres = dY + ((int64_t)b * n2 + o) * p.ld;
+    __nv_bfloat16* dskip = dY + ((int64_t)b * n2 + (p.has_res ? p.Cio : 0) + o) * p.ld;
+    float s[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) s[i] = 0.f;      // 0,1 qadd | 2,3 qres | 4,5 qadds | 6,7 qskip | 8 db_res | 9 db_skip
+    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
+        const int64_t i = r * p.ld + m;
+        if (p.has_res) {
+            const float gxo = __ldg(g.g_x_out + i);
+            const float ry = __ldg(p.res_y + i);
+            float gz = gxo, gry;
+            if (p.quant) {
+                const float rq = actqf_fq(qres, ry);
+                const float z = __fadd_rn(__ldg(p.x_in + i), rq);
+                gz = actqf_bwd(qadd, z, gxo, s[0], s[1]);
+                gry = actqf_bwd(qres, ry, gz, s[2], s[3]);
+            } else {
+                gry = gz;
+            }
+            g.g_xd[i] = gz;
+            s[8] += gry;
+            dres[m] = __float2bfloat16_rn(gry * sc_res);
+        }
+        {
+            const float gso = __ldg(g.g_skip_out + i);
+            const float sy = __ldg(p.skip_y + i);
+            float gz = gso, gsy;
+            if (p.quant) {
+                if (!p.first_block) {
+                    const float sq = actqf_fq(qskip, sy);
+                    const float z = __fadd_rn(__ldg(p.skip_in + i), sq);
+                    gz = actqf_bwd(qadds, z, gso, s[4], s[5]);
+                }
+                gsy = actqf_bwd(qskip, sy, gz, s[6], s[7]);
+            } else {
+                gsy = gz;
+            }
+            if (!p.first_block) g.g_skip_in[i] = gz;
+            s[9] += gsy;
+            dskip[m] = __float2bfloat16_rn(gsy * sc_skip);
+        }
+    }
+    double v[10];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = (double)s[i];
+    block_sum<10>(v, sh);
+    if (threadIdx.x == 0) {
+        if (p.quant) {
+            if (p.has_res) {
+                atomicAdd(acc + L.q + 2 * QADD, v[0]); atomicAdd(acc + L.q + 2 * QADD + 1, v[1]);
+                atomicAdd(acc + L.q + 2 * QRES, v[2]); atomicAdd(acc + L.q + 2 * QRES + 1, v[3]);
+            }
+            if (!p.first_block) { atomicAdd(acc + L.q + 2 * QADDS, v[4]); atomicAdd(acc + L.q + 2 * QADDS + 1, v[5]); }
+            atomicAdd(acc + L.q + 2 * QSKIP, v[6]); atomicAdd(acc + L.q + 2 * QSKIP + 1, v[7]);
+        }
+        if (p.has_res) atomicAdd(acc + L.db2 + o, v[8]);
+        atomicAdd(acc + L.db2 + (p.has_res ? p.Cio : 0) + o, v[9]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P1 / P2: gLN2 + FQ4 (+ FQ3 + PReLU3 in P2).  grid = B*Chid rows.  g_a4 in g_hid_a (bf16).
+// ---------------------------------------------------------------------------------------------
+template <int PHASE>
+__global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    __shared__ double sh[5 * 32];
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
+    const Hidden3 h = load_hidden3(p, b, c);
+    const float* y3 = p.y3 + r * p.ld;
+    const __nv_bfloat16* ga4 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
+    __nv_bfloat16* gy3 = reinterpret_cast<__nv_bfloat16*>(g.g_hid_b) + r * p.ld;
+    float S1 = 0.f, S2 = 0.f, invN = 0.f;
+    if (PHASE == 2) {
+        S1 = (float)acc[L.samp2 + 2 * b];
+        S2 = (float)acc[L.samp2 + 2 * b + 1];
+        invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+    }
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // P1: q4 sD,sZ, r1, r2 | P2: q3 sD,sZ, slope3
+    for (int m = threadIdx.x; m < p.M; m += ROW_THREADS) {
+        const float y = __ldg(y3 + m);
+        const float gin = bf2f(ga4[m]);
+        const float a3 = hidden3_a3(h, y);
+        const float n3 = hidden3_n3(h, a3);
+        const float xh = (a3 - h.g.mu) * h.g.rstd;
+        float d0 = 0.f, d1 = 0.f;
+        const float gn = h.quant ? actqf_bwd(h.q4, n3, gin, d0, d1) : gin;
+        if (PHASE == 1) {
+            s[0] += d0; s[1] += d1; s[2] += gn; s[3] = fmaf(gn, xh, s[3]);
+        } else {
+            const float ga3 = h.g.rstd * (h.g.gamma * gn - (S1 + xh * S2) * invN);
+            const float z = prelu_f(y, h.slope);
+            const float gz = h.quant ? actqf_bwd(h.q3, z, ga3, s[0], s[1]) : ga3;
+            const float gy = y > 0.f ? gz : h.slope * gz;
+            s[2] += y > 0.f ? 0.f : y * gz;
+            gy3[m] = __float2bfloat16_rn(gy);
+        }
+    }
+    double v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = (double)s[i];
+    block_sum<5>(v, sh);
+    if (threadIdx.x == 0) {
+        if (PHASE == 1) {
+            if (p.quant) { atomicAdd(acc + L.q + 2 * Q4, v[0]); atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]); }
+            acc[L.row2 + 2 * r] = v[2];
+            acc[L.row2 + 2 * r + 1] = v[3];
+        } else {
+            if (p.quant) { atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]); }
+            atomicAdd(acc + L.slope + 1, v[2]);
+        }
+    }
+}
+
+// R: per-sample {S1,S2} and per-channel dgamma/dbeta from the per-row sums
+__global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, int C, const float* __restrict__ gamma,
+                                      float* __restrict__ g_gamma, float* __restrict__ g_beta, double* __restrict__ samp) {
+    __shared__ double sh[2 * 32];
+    if ((int)blockIdx.x < B) {
+        const int b = blockIdx.x;
+        double s1 = 0.0, s2 = 0.0;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            const double gm = (double)gamma[c];
+            s1 += gm * rowacc[2 * ((int64_t)b * C + c)];
+            s2 += gm * rowacc[2 * ((int64_t)b * C + c) + 1];
+        }
+        double v[2] = {s1, s2};
+        block_sum<2>(v, sh);
+        if (threadIdx.x == 0) { samp[2 * b] = v[0]; samp[2 * b + 1] = v[1]; }
+    } else {
+        const int nb = gridDim.x - B;
+        for (int c = (blockIdx.x - B) * blockDim.x + threadIdx.x; c < C; c += nb * blockDim.x) {
+            double gb = 0.0, gg = 0.0;
+            for (int b = 0; b < B; ++b) {
+                gb += rowacc[2 * ((int64_t)b * C + c)];
+                gg += rowacc[2 * ((int64_t)b * C + c) + 1];
+            }
+            g_beta[c] = (float)gb;
+            g_gamma[c] = (float)gg;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row; a1, a2 and g_y3 rows in smem.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    extern __shared__ float rows[];
+    __shared__ double sh[8 * 32];
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
+    const int M = p.M;
+    float* a1r = rows;
+    float* a2r = rows + p.ld;
+    float* gyr = rows + 2 * p.ld;
+    const Hidden1 h = load_hidden1(p, b, c);
+    const float* y1 = p.y1 + r * p.ld;
+    const __nv_bfloat16* gy3 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld;
+    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
+        const float a1 = hidden1_a1(h, __ldg(y1 + m));
+        const float n1 = hidden1_n1(h, a1);
+        a1r[m] = a1;
+        a2r[m] = h.quant ? actqf_fq(h.q2, n1) : n1;
+        gyr[m] = bf2f(gy3[m]);
+    }
+    __syncthreads();
+    const float w0 = __ldg(p.wdw + c * 3), w1 = __ldg(p.wdw + c * 3 + 1), w2 = __ldg(p.wdw + c * 3 + 2);
+    const int d = p.dil;
+    __nv_bfloat16* gn1o = reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld;
+    float s[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;       // 0,1 q2 | 2,3 row sums | 4,5,6 dW taps | 7 db
+    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
+        const float gl = (m - d >= 0) ? gyr[m - d] : 0.f;
+        const float gr = (m + d < M) ? gyr[m + d] : 0.f;
+        const float g0 = gyr[m];
+        // y3[m'] = sum_k w_k a2[m' + (k-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
+        const float ga2 = fmaf(w0, gr, fmaf(w1, g0, w2 * gl));
+        const float al = (m - d >= 0) ? a2r[m - d] : 0.f;
+        const float ar = (m + d < M) ? a2r[m + d] : 0.f;
+        s[4] = fmaf(g0, al, s[4]);
+        s[5] = fmaf(g0, a2r[m], s[5]);
+        s[6] = fmaf(g0, ar, s[6]);
+        s[7] += g0;
+        const float a1 = a1r[m];
+        const float n1 = hidden1_n1(h, a1);
+        const float gn1 = h.quant ? actqf_bwd(h.q2, n1, ga2, s[0], s[1]) : ga2;
+        const float xh = (a1 - h.g.mu) * h.g.rstd;
+        s[2] += gn1;
+        s[3] = fmaf(gn1, xh, s[3]);
+        gn1o[m] = __float2bfloat16_rn(gn1);
+    }
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (double)s[i];
+    block_sum<8>(v, sh);
+    if (threadIdx.x == 0) {
+        if (p.quant) { atomicAdd(acc + L.q + 2 * Q2, v[0]); atomicAdd(acc + L.q + 2 * Q2 + 1, v[1]); }
+        acc[L.row1 + 2 * r] = v[2];
+        acc[L.row1 + 2 * r + 1] = v[3];
+        atomicAdd(acc + L.dwdw + 3 * c, v[4]);
+        atomicAdd(acc + L.dwdw + 3 * c + 1, v[5]);
+        atomicAdd(acc + L.dwdw + 3 * c + 2, v[6]);
+        atomicAdd(acc + L.dbdw + c, v[7]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    __shared__ double sh[4 * 32];
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
+    const Hidden1 h = load_hidden1(p, b, c);
+    const float* y1 = p.y1 + r * p.ld;
+    const __nv_bfloat16* gn1 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
+    __nv_bfloat16* dY1 = reinterpret_cast<__nv_bfloat16*>(g.dY1) + r * p.ld;
+    const float S1 = (float)acc[L.samp1 + 2 * b], S2 = (float)acc[L.samp1 + 2 * b + 1];
+    const float invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+    const float sc = __ldg(p.dws1 + c);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};            // q1 sD,sZ | slope1 | db1
+    for (int m = threadIdx.x; m < p.M; m += ROW_THREADS) {
+        const float y = __ldg(y1 + m);
+        const float z = prelu_f(y, h.slope);
+        const float a1 = h.quant ? actqf_fq(h.q1, z) : z;
+        const float xh = (a1 - h.g.mu) * h.g.rstd;
+        const float gn = bf2f(gn1[m]);
+        const float ga1 = h.g.rstd * (h.g.gamma * gn - (S1 + xh * S2) * invN);
+        const float gz = h.quant ? actqf_bwd(h.q1, z, ga1, s[0], s[1]) : ga1;
+        const float gy = y > 0.f ? gz : h.slope * gz;
+        s[2] += y > 0.f ? 0.f : y * gz;
+        s[3] += gy;
+        dY1[m] = __float2bfloat16_rn(gy * sc);
+    }
+    double v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = (double)s[i];
+    block_sum<4>(v, sh);
+    if (threadIdx.x == 0) {
+        if (p.quant) { atomicAdd(acc + L.q + 2 * Q1, v[0]); atomicAdd(acc + L.q + 2 * Q1 + 1, v[1]); }
+        atomicAdd(acc + L.slope, v[2]);
+        atomicAdd(acc + L.db1 + c, v[3]);
+    }
+}
+
+// F: fp64 accumulators -> fp32 outputs
+__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc) {
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 8 && p.quant) {
+        const double sD = acc[L.q + 2 * i], sZ = acc[L.q + 2 * i + 1];
+        g.g_q[2 * i] = (float)(sZ - sD / 255.0);      // d/d min_range
+        g.g_q[2 * i + 1] = (float)(sD / 255.0);       // d/d max_range
+    }
+    if (i == 0) {
+        g.g_slope1[0] = (float)acc[L.slope];
+        g.g_slope3[0] = (float)acc[L.slope + 1];
+    }
+    if (i < p.Chid) {
+        g.db1[i] = (float)acc[L.db1 + i];
+        g.dbdw[i] = (float)acc[L.dbdw + i];
+        for (int k = 0; k < 3; ++k) g.dwdw[3 * i + k] = (float)acc[L.dwdw + 3 * i + k];
+    }
+    if (i < n2) g.db2[i] = (float)acc[L.db2 + i];
+}
+
+__global__ void fill_consts_kernel(float* ones, float* zeros, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { ones[i] = 1.f; zeros[i] = 0.f; }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace fqss
+
+using namespace fqss;
+
+extern "C" {
+
+size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid) {
+    AccLayout L(B, Cio, Chid);
+    size_t acc = align_up((size_t)L.total * sizeof(double), 256);
+    size_t cst = align_up((size_t)2 * 1024 * sizeof(float), 256);
+    // the partial buffer is sized for the longest sequence the row kernels accept (M <= 16K); the actual need
+    // depends only on the split count, which is capped by the SM count
+    size_t p1 = (size_t)160 * Chid * Cio * sizeof(float);
+    size_t p2 = (size_t)160 * 2 * Cio * Chid * sizeof(float);
+    return acc + cst + (p1 > p2 ? p1 : p2) + 1024;
+}
+
+int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, void* stream) {
+    int rc = tcn_validate_block(p, "tcn_block_bwd");
+    if (rc) return rc;
+    FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->g_hid_b && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
+    FQSS_REQUIRE(!p->has_res || (g->g_x_out && g->g_xd), -1, "tcn_block_bwd: residual path needs g_x_out / g_xd");
+    FQSS_REQUIRE(p->first_block || g->g_skip_in, -1, "tcn_block_bwd: g_skip_in missing");
+    FQSS_REQUIRE(g->dW1q && g->db1 && g->dW2q && g->db2 && g->dwdw && g->dbdw && g->g_gn1_w && g->g_gn1_b && g->g_gn2_w && g->g_gn2_b &&
+                     g->g_slope1 && g->g_slope3 && g->g_q, -1, "tcn_block_bwd: null parameter-gradient output");
+    FQSS_REQUIRE(g->ws_bytes >= fqss_tcn_ws_bytes(p->B, p->Cio, p->Chid), -3, "tcn_block_bwd: workspace too small");
+    FQSS_REQUIRE(p->Chid <= 1024 && 2 * p->Cio <= 1024, -1, "tcn_block_bwd: channel count too large");
+    cudaStream_t s = (cudaStream_t)stream;
+    const AccLayout L(p->B, p->Cio, p->Chid);
+    const size_t acc_bytes = align_up((size_t)L.total * sizeof(double), 256);
+    double* acc = (double*)g->ws;
+    float* ones = (float*)((char*)g->ws + acc_bytes);
+    float* zeros = ones + 1024;
+    float* part = (float*)((char*)g->ws + acc_bytes + align_up((size_t)2 * 1024 * sizeof(float), 256));
+    const size_t part_cap = g->ws_bytes - ((char*)part - (char*)g->ws);
+    const int n2 = p->has_res ? 2 * p->Cio : p->Cio;
+    const int rows_h = p->B * p->Chid, rows_io = p->B * p->Cio;
+
+    cudaMemsetAsync(acc, 0, (size_t)L.total * sizeof(double), s);
+    fill_consts_kernel<<<4, 256, 0, s>>>(ones, zeros, 1024);
+    // T
+    tcn_tail_bwd_kernel<<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    rc = check_launch("tcn_block_bwd(tail)");
+    if (rc) return rc;
+    // G: g_a4 = Wc2T-GEMM(dY2)   (K = n2, N = Chid) -> bf16
+    {
+        tcg::Args a{};
+        a.B = p->B; a.M = p->M; a.K = n2; a.N = p->Chid; a.ld = p->ld; a.s1 = ones; a.s0 = zeros; a.out_bf16 = (__nv_bfloat16*)g->g_hid_a;
+        rc = tcg::run(tcg::EPI_BF16, g->dY2, p->Wc2T, a, s);
+        if (rc) return rc;
+    }
+    // W: dW2q
+    rc = tcw::run(g->dY2, p->a4_op, p->B, p->M, p->ld, n2, p->Chid, part, part_cap, p->quant ? p->q4.rmin : nullptr,
+                  p->quant ? p->q4.rmax : nullptr, p->dws2, acc + L.db2, g->dW2q, s);
+    if (rc) return rc;
+    // P1, R, P2
+    tcn_gln2_bwd_kernel<1><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
+                                                                     acc + L.samp2);
+    tcn_gln2_bwd_kernel<2><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    // D, R, Q
+    static bool cfg = false;
+    if (!cfg) {
+        cudaFuncSetAttribute(tcn_dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cfg = true;
+    }
+    tcn_dw_bwd_kernel<<<rows_h, ROW_THREADS, (size_t)3 * p->ld * sizeof(float), s>>>(*p, *g, acc);
+    tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
+                                                                     acc + L.samp1);
+    tcn_gln1_bwd_kernel<<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    rc = check_launch("tcn_block_bwd(hidden)");
+    if (rc) return rc;
+    // G: g_x_in = Wc1T-GEMM(dY1) (+ g_xd)   (K = Chid, N = Cio) -> fp32
+    {
+        tcg::Args a{};
+        a.B = p->B; a.M = p->M; a.K = p->Chid; a.N = p->Cio; a.ld = p->ld; a.s1 = ones; a.s0 = zeros; a.out_f32 = g->g_x_in;
+        a.addend = p->has_res ? g->g_xd : nullptr;
+        rc = tcg::run(p->has_res ? tcg::EPI_ADD : tcg::EPI_STORE, g->dY1, p->Wc1T, a, s);
+        if (rc) return rc;
+    }
+    // W: dW1q
+    rc = tcw::run(g->dY1, p->x_op, p->B, p->M, p->ld, p->Chid, p->Cio, part, part_cap, p->quant ? p->q_in.rmin : nullptr,
+                  p->quant ? p->q_in.rmax : nullptr, p->dws1, acc + L.db1, g->dW1q, s);
+    if (rc) return rc;
+    // F
+    const int nf = p->Chid > n2 ? p->Chid : n2;
+    tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc);
+    return check_launch("tcn_block_bwd(finalize)");
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// wgrad_tc.cu -- weight gradients of the 1x1 convolutions as a split-K tcgen05 GEMM.
+//
+//   G[o, i] = sum_{b, m} dY[b, o, m] * X[b, i, m]          (reduction over ALL frames of ALL samples)
+//
+// Both operands are K-major (frames are contiguous in the NCL layout), so TMA boxes of
+// {64 frames x rows} with 128B swizzle feed the MMA directly.  The output is tiny (<= 256x512) and
+// the reduction is long (B*M ~ 128K), so the work is split along K: every CTA owns a contiguous range
+// of 64-frame chunks, keeps a [MT*128] x [NW] fp32 accumulator in TMEM (MT*NW <= 512 columns) for the
+// whole range and writes ONE partial tile at the end; a small second kernel reduces the partials
+// deterministically and applies the de-quantisation affine:
+//   dWq[o,i] = (da * G[o,i]) / dws[o] + min_a * db[o]
+// (X holds integer codes c with x = da*c + min_a; dY was pre-scaled by dws[o] for the dgrad GEMM).
+#include <cuda.h>
+
+#include "fqss_common.cuh"
+#include "tc_common.cuh"
+#include "wgrad_tc.cuh"
+
+namespace fqss {
+
+int num_sms();
+
+namespace tcw {
+
+using namespace tc;
+
+constexpr int BKF = 64;                 // frames per k-chunk (128 B of bf16)
+constexpr int NUM_THREADS = 256;        // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 4-7 epilogue
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+struct __align__(8) Bars {
+    uint64_t full[4];
+    uint64_t empty[4];
+    uint64_t done;
+    uint32_t tmem_base;
+};
+
+template <int MT, int NW>
+__host__ __device__ constexpr int stage_bytes() { return (MT * 128 + NW) * BKF * 2; }
+template <int MT, int NW>
+__host__ __device__ constexpr int num_stages() { return stage_bytes<MT, NW>() > 72 * 1024 ? 2 : 3; }
+template <int MT, int NW>
+__host__ __device__ constexpr int smem_bytes() { return num_stages<MT, NW>() * stage_bytes<MT, NW>() + (int)sizeof(Bars) + 1024; }
+
+struct KArgs {
+    int B, M, O, I;           // O rows of dY, I rows of X
+    int chunks_per_sample;    // ceil(M / 64)
+    int nsplit;               // gridDim.x
+    float* part;              // [nsplit][O][I]
+};
+
+template <int MT, int NW>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const KArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int ST = num_stages<MT, NW>();
+    constexpr int SB = stage_bytes<MT, NW>();
+    Bars* bar = reinterpret_cast<Bars*>(smem + ST * SB);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // blockIdx.y enumerates (o-group, i-chunk)
+    const int n_ichunks = p.I / NW;
+    const int og = blockIdx.y / n_ichunks, ic = blockIdx.y % n_ichunks;
+    const int o0 = og * MT * 128, i0 = ic * NW;
+    const int total = p.B * p.chunks_per_sample;
+    const int per = (total + p.nsplit - 1) / p.nsplit;
+    const int cbeg = blockIdx.x * per;
+    const int cend = min(total, cbeg + per);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmY);
+        tma_prefetch_desc(&tmX);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < ST; ++s) {
+            mbar_init(&bar->full[s], 1);
+            mbar_init(&bar->empty[s], 1);
+        }
+        mbar_init(&bar->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(&bar->tmem_base, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bar->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = cbeg; c < cend; ++c) {
+                const int b = c / p.chunks_per_sample, f0 = (c % p.chunks_per_sample) * BKF;
+                mbar_wait(&bar->empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * SB;
+                mbar_expect_tx(&bar->full[stage], SB);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) tma_load_3d(sa + mt * 128 * BKF * 2, &tmY, &bar->full[stage], f0, o0 + mt * 128, b);
+                tma_load_3d(sa + MT * 128 * BKF * 2, &tmX, &bar->full[stage], f0, i0, b);
+                if (++stage == ST) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_bf16(128, NW, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int c = cbeg; c < cend; ++c) {
+                mbar_wait(&bar->full[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * SB);
+                const uint32_t sb = sa + MT * 128 * BKF * 2;
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+                    for (int k = 0; k < BKF / 16; ++k) {
+                        const uint64_t adesc = smem_desc_sw128(sa + mt * 128 * BKF * 2 + k * 32, 16, 1024);
+                        const uint64_t bdesc = smem_desc_sw128(sb + k * 32, 16, 1024);
+                        umma_bf16(tmem_base + (uint32_t)(mt * NW), adesc, bdesc, idesc, (c > cbeg || k > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&bar->empty[stage]);
+                if (++stage == ST) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&bar->done);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        float* out = p.part + (int64_t)blockIdx.x * p.O * p.I;
+        if (cend > cbeg) {
+            mbar_wait(&bar->done, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+            const int o = o0 + mt * 128 + q * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NW; c0 += 32) {
+                uint32_t v[32];
+                if (cend > cbeg) {
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * NW + c0), v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = 0u;
+                }
+                float4* dst = reinterpret_cast<float4*>(out + (int64_t)o * p.I + i0 + c0);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                         __uint_as_float(v[4 * j + 3]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// dWq[o,i] = (da * sum_p part[p][o][i]) / dws[o] + min_a * db[o]
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ part, int nsplit, int O, int I,
+                                                            const float* __restrict__ amin, const float* __restrict__ amax,
+                                                            const float* __restrict__ dws, const double* __restrict__ db,
+                                                            float* __restrict__ dWq) {
+    const int64_t n = (int64_t)O * I;
+    float da = 1.f, mn = 0.f;
+    if (amin) {
+        mn = __ldg(amin);
+        da = __fdiv_rn(__fsub_rn(__ldg(amax), mn), 255.f);
+    }
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int o = (int)(e / I);
+        float acc = 0.f;
+        for (int s = 0; s < nsplit; ++s) acc += __ldg(part + (int64_t)s * n + e);
+        dWq[e] = (da * acc) / __ldg(dws + o) + mn * (float)db[o];
+    }
+}
+
+static int make_map(CUtensorMap* tm, const void* base, int B, int C, int M, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return -999;
+    cuuint64_t dims[3] = {(cuuint64_t)M, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)C * (cuuint64_t)ld * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BKF, (cuuint32_t)box_rows, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+template <int MT, int NW>
+static int launch(const CUtensorMap& ty, const CUtensorMap& tx, const KArgs& a, int gy, cudaStream_t s) {
+    static bool configured = false;
+    constexpr int smem = smem_bytes<MT, NW>();
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) {
+            set_error("wgrad: cannot set %d B dynamic smem: %s", smem, cudaGetErrorString(e));
+            return -4;
+        }
+        configured = true;
+    }
+    wgrad_kernel<MT, NW><<<dim3(a.nsplit, gy), NUM_THREADS, smem, s>>>(ty, tx, a);
+    return check_launch("wgrad");
+}
+
+int plan_splits(int B, int M, int O, int I) {
+    const int NW = I >= 256 ? 256 : 128;
+    const int ot = O / 128;
+    const int MT = (ot >= 4 && NW == 128) ? 4 : (ot >= 2 ? 2 : 1);
+    const int gy = (ot / MT) * (I / NW);
+    int ns = num_sms() / gy;
+    const int total = B * ((M + BKF - 1) / BKF);
+    if (ns > total) ns = total;
+    if (ns < 1) ns = 1;
+    return ns;
+}
+
+size_t part_bytes(int B, int M, int O, int I) { return (size_t)plan_splits(B, M, O, I) * O * I * sizeof(float); }
+
+int run(const void* dY, const void* X, int B, int M, int64_t ld, int O, int I, float* part, size_t part_cap, const float* amin,
+        const float* amax, const float* dws, const double* db, float* dWq, cudaStream_t s) {
+    FQSS_REQUIRE(dY && X && part && dws && db && dWq, -1, "wgrad: null argument");
+    FQSS_REQUIRE(O % 128 == 0 && I % 128 == 0 && O >= 128 && I >= 128, -1, "wgrad: O and I must be multiples of 128 (O=%d I=%d)", O, I);
+    FQSS_REQUIRE(ld >= M && ld % 8 == 0, -2, "wgrad: bad pitch");
+    const int NW = I >= 256 ? 256 : 128;
+    FQSS_REQUIRE(I % NW == 0, -1, "wgrad: I=%d not a multiple of %d", I, NW);
+    const int ot = O / 128;
+    const int MT = (ot >= 4 && NW == 128) ? 4 : (ot >= 2 ? 2 : 1);
+    FQSS_REQUIRE(ot % MT == 0, -1, "wgrad: O=%d not a multiple of %d", O, MT * 128);
+    const int gy = (ot / MT) * (I / NW);
+    KArgs a;
+    a.B = B; a.M = M; a.O = O; a.I = I;
+    a.chunks_per_sample = (M + BKF - 1) / BKF;
+    a.nsplit = plan_splits(B, M, O, I);
+    a.part = part;
+    FQSS_REQUIRE(part_cap >= (size_t)a.nsplit * O * I * sizeof(float), -3, "wgrad: partial buffer too small");
+    CUtensorMap ty, tx;
+    int r = make_map(&ty, dY, B, O, M, ld, 128);
+    FQSS_REQUIRE(r == 0, -4, "wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", r);
+    r = make_map(&tx, X, B, I, M, ld, NW);
+    FQSS_REQUIRE(r == 0, -4, "wgrad: cuTensorMapEncodeTiled(X) failed (%d)", r);
+    if (NW == 128) {
+        if (MT == 4) r = launch<4, 128>(ty, tx, a, gy, s);
+        else if (MT == 2) r = launch<2, 128>(ty, tx, a, gy, s);
+        else r = launch<1, 128>(ty, tx, a, gy, s);
+    } else {
+        if (MT == 2) r = launch<2, 256>(ty, tx, a, gy, s);
+        else r = launch<1, 256>(ty, tx, a, gy, s);
+    }
+    if (r) return r;
+    const int64_t n = (int64_t)O * I;
+    int grid = (int)((n + 255) / 256);
+    if (grid > num_sms() * 4) grid = num_sms() * 4;
+    wgrad_finalize_kernel<<<grid, 256, 0, s>>>(part, a.nsplit, O, I, amin, amax, dws, db, dWq);
+    return check_launch("wgrad_finalize");
+}
+
+}  // namespace tcw
+}  // namespace fqss

@@ -15,7 +15,7 @@ from torch.autograd.function import once_differentiable
 from . import _native as N
 from ._native import PwDesc, PwGrads, check, lib, ptr, stream_ptr, workspace
 
-PAD = 4
+PAD = 8      # row pitch in floats: 32-byte rows keep fp32 (16 B) and bf16 (TMA: 16 B strides) views aligned
 
 
 def _pitch(m):

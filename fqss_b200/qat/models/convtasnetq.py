@@ -69,13 +69,21 @@ class MaskGenerator(nn.Module):
             raise ValueError(f"Unsupported activation {msk_activate}")
         self.mask_net = nn.Sequential(nn.PReLU(), nn.Conv1d(num_feats, input_dim * n_srcs, 1), act)
 
+    use_fused = True      # class-level switch: False forces the per-layer wrappers (tests / debugging)
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         batch = x.shape[0]
         feats = self.bottleneck(x)
-        feats, total = self.TCN[0](feats)
-        for i, block in enumerate(self.TCN[1:]):
-            feats, skip = block(feats)
-            total = self.adds[i](total, skip)
+        from ... import tcn_engine as E
+        if self.use_fused and E.fused_eligible(self, feats):
+            q = self.bottleneck[1].activation_fake_quantize
+            adds = [None] + list(self.adds)
+            _, total = E.fused_tcn(feats, list(self.TCN), adds, True, (q.min_range, q.max_range))
+        else:
+            feats, total = self.TCN[0](feats)
+            for i, block in enumerate(self.TCN[1:]):
+                feats, skip = block(feats)
+                total = self.adds[i](total, skip)
         out = self.mask_net(total)
         return out.reshape(batch, self.n_srcs, self.input_dim, -1)
 

@@ -1,9 +1,62 @@
 """Fused TCN engine (host side): drives the tensor-core / fused kernels of libfqss_sm100 for the
-24 ConvBlocks of the separator.  Plumbing only -- buffers, pointers, launch order."""
+ConvBlocks of the separator (`MaskGenerator.TCN` + `MaskGenerator.adds`).  Plumbing only -- buffer
+allocation, pointer tables, launch order; all arithmetic is in csrc/tcn_fwd.cu, tcn_bwd.cu,
+gemm_tc.cu, wgrad_tc.cu.
+
+The whole stack is ONE autograd node: forward launches 4 kernels per block, backward 9, and the
+residual-stream / skip-sum gradients never leave fp32.  Used when the quantised model is in steady
+state (observers off); the per-layer wrappers in qat_layers.py remain the general path (observer
+calibration, foreign compositions) and the definition of the drop-in API.
+"""
+import ctypes as C
+
 import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
 
 from . import _native as N
-from ._native import check, lib, ptr, stream_ptr
+from ._native import check, i64, lib, ptr, stream_ptr, vp
+
+f32p = vp
+
+
+class QRange(C.Structure):
+    _fields_ = [("rmin", vp), ("rmax", vp)]
+
+
+class TcnBlock(C.Structure):
+    _fields_ = [("B", C.c_int32), ("M", C.c_int32), ("dil", C.c_int32), ("quant", C.c_int32), ("first_block", C.c_int32),
+                ("has_res", C.c_int32), ("Cio", C.c_int32), ("Chid", C.c_int32), ("ld", i64),
+                ("Wc1", vp), ("Wc1T", vp), ("s1_1", vp), ("s0_1", vp), ("dws1", vp),
+                ("Wc2", vp), ("Wc2T", vp), ("s1_2", vp), ("s0_2", vp), ("dws2", vp),
+                ("wdw", vp), ("bdw", vp),
+                ("slope1", vp), ("slope3", vp), ("gn1_w", vp), ("gn1_b", vp), ("gn2_w", vp), ("gn2_b", vp),
+                ("q_in", QRange), ("q1", QRange), ("q2", QRange), ("q3", QRange), ("q4", QRange), ("qres", QRange),
+                ("qskip", QRange), ("qadd", QRange), ("qadds", QRange),
+                ("x_op", vp), ("x_in", vp), ("skip_in", vp),
+                ("y1", vp), ("stats1", vp), ("y3", vp), ("stats3", vp), ("a4_op", vp),
+                ("res_y", vp), ("skip_y", vp), ("x_out", vp), ("x_out_op", vp), ("skip_out", vp)]
+
+
+class TcnBlockGrads(C.Structure):
+    _fields_ = [("g_x_out", vp), ("g_skip_out", vp), ("g_x_in", vp), ("g_skip_in", vp),
+                ("dY2", vp), ("g_hid_a", vp), ("g_hid_b", vp), ("dY1", vp), ("g_xd", vp),
+                ("dW1q", vp), ("db1", vp), ("dW2q", vp), ("db2", vp), ("dwdw", vp), ("dbdw", vp),
+                ("g_gn1_w", vp), ("g_gn1_b", vp), ("g_gn2_w", vp), ("g_gn2_b", vp), ("g_slope1", vp), ("g_slope3", vp),
+                ("g_q", vp), ("ws", vp), ("ws_bytes", C.c_size_t)]
+
+
+_L = None
+
+
+def _libx():
+    global _L
+    if _L is None:
+        L = lib()
+        L.fqss_tcn_block_fwd.argtypes = [C.POINTER(TcnBlock), vp]
+        L.fqss_tcn_block_bwd.argtypes = [C.POINTER(TcnBlock), C.POINTER(TcnBlockGrads), vp]
+        _L = L
+    return _L
 
 
 def pw_gemm(act_bf16, w_bf16, s1, s0, M, addend=None, out_dtype=torch.float32):
@@ -18,3 +71,316 @@ def pw_gemm(act_bf16, w_bf16, s1, s0, M, addend=None, out_dtype=torch.float32):
     check(lib().fqss_pw_gemm(ptr(act_bf16), ptr(w_bf16), ptr(s1), ptr(s0), ptr(f32) or None, ptr(b16) or None,
                              ptr(addend) or None, B, K, Nn, M, ld, stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter layout of one ConvBlock as seen by the engine
+# ---------------------------------------------------------------------------------------------
+# order of the per-block tensors handed to the autograd node (and of the gradients it returns)
+_BLOCK_SLOTS = ("W1", "b1", "w1min", "w1max", "slope1", "q1min", "q1max", "g1w", "g1b", "q2min", "q2max",
+                "Wdw", "bdw", "wdmin", "wdmax", "slope3", "q3min", "q3max", "g2w", "g2b", "q4min", "q4max",
+                "Wres", "bres", "wrmin", "wrmax", "qresmin", "qresmax", "Wskip", "bskip", "wsmin", "wsmax",
+                "qskipmin", "qskipmax", "qaddmin", "qaddmax", "qaddsmin", "qaddsmax")
+
+
+def _aq(mod):
+    q = getattr(mod, "activation_fake_quantize", None)
+    if q is None or isinstance(q, torch.nn.Identity):
+        return None, None
+    return q.min_range, q.max_range
+
+
+def _wq(mod):
+    q = getattr(mod, "weight_fake_quantize", None)
+    if q is None or isinstance(q, torch.nn.Identity):
+        return None, None
+    return q.min_range, q.max_range
+
+
+def block_tensors(block, adds_mod, quant):
+    """dict slot -> tensor (or None) for a quantised (`quant`) or float ConvBlock."""
+    sb = block.shared_block
+    if quant:
+        c1, n1, dw, n2 = sb[0], sb[2], sb[3], sb[5]
+        d = dict(W1=c1.conv1d.weight, b1=c1.conv1d.bias, slope1=c1.nl.weight, g1w=n1.groupnorm.weight, g1b=n1.groupnorm.bias,
+                 Wdw=dw.conv1d.weight, bdw=dw.conv1d.bias, slope3=dw.nl.weight, g2w=n2.groupnorm.weight, g2b=n2.groupnorm.bias,
+                 Wres=block.res_conv.conv1d.weight, bres=block.res_conv.conv1d.bias,
+                 Wskip=block.skip_conv.conv1d.weight, bskip=block.skip_conv.conv1d.bias)
+        d["w1min"], d["w1max"] = _wq(c1)
+        d["wdmin"], d["wdmax"] = _wq(dw)
+        d["wrmin"], d["wrmax"] = _wq(block.res_conv)
+        d["wsmin"], d["wsmax"] = _wq(block.skip_conv)
+        d["q1min"], d["q1max"] = _aq(c1)
+        d["q2min"], d["q2max"] = _aq(n1)
+        d["q3min"], d["q3max"] = _aq(dw)
+        d["q4min"], d["q4max"] = _aq(n2)
+        d["qresmin"], d["qresmax"] = _aq(block.res_conv)
+        d["qskipmin"], d["qskipmax"] = _aq(block.skip_conv)
+        d["qaddmin"], d["qaddmax"] = _aq(block.add)
+        d["qaddsmin"], d["qaddsmax"] = _aq(adds_mod) if adds_mod is not None else (None, None)
+        dil = dw.conv1d.dilation[0]
+    else:
+        d = dict(W1=sb[0].weight, b1=sb[0].bias, slope1=sb[1].weight, g1w=sb[2].weight, g1b=sb[2].bias,
+                 Wdw=sb[3].weight, bdw=sb[3].bias, slope3=sb[4].weight, g2w=sb[5].weight, g2b=sb[5].bias,
+                 Wres=block.res_conv.weight, bres=block.res_conv.bias, Wskip=block.skip_conv.weight, bskip=block.skip_conv.bias)
+        dil = sb[3].dilation[0]
+    return {k: d.get(k) for k in _BLOCK_SLOTS}, dil
+
+
+class BlockState:
+    """Prepared weights + saved activations of one block for one forward/backward."""
+    __slots__ = ("t", "dil", "first", "has_res", "prep", "act", "blk")
+
+
+def _prep_block(t, quant, first, has_res, q_in, dev):
+    """Run the per-step weight preparation for one block; returns the dict of prepared buffers."""
+    L = _libx()
+    Chid, Cio = t["W1"].shape[0], t["W1"].shape[1]
+    n2 = 2 * Cio if has_res else Cio
+    bf = torch.bfloat16
+    P = dict(Wc1=torch.empty((Chid, Cio), dtype=bf, device=dev), Wc1T=torch.empty((Cio, Chid), dtype=bf, device=dev),
+             s1_1=torch.empty(Chid, device=dev), s0_1=torch.empty(Chid, device=dev), dws1=torch.empty(Chid, device=dev),
+             Wc2=torch.empty((n2, Chid), dtype=bf, device=dev), Wc2T=torch.empty((Chid, n2), dtype=bf, device=dev),
+             s1_2=torch.empty(n2, device=dev), s0_2=torch.empty(n2, device=dev), dws2=torch.empty(n2, device=dev))
+    s = stream_ptr()
+    qi = q_in if quant else (None, None)
+    check(L.fqss_tcn_prep(ptr(t["W1"]), ptr(t["w1min"]) or None, ptr(t["w1max"]) or None, ptr(t["b1"]) or None,
+                          ptr(qi[0]) or None, ptr(qi[1]) or None, ptr(P["Wc1"]), ptr(P["Wc1T"]), ptr(P["s1_1"]), ptr(P["s0_1"]),
+                          ptr(P["dws1"]), Chid, Cio, Chid, 0, s))
+    off = 0
+    q4 = (t["q4min"], t["q4max"]) if quant else (None, None)
+    if has_res:
+        check(L.fqss_tcn_prep(ptr(t["Wres"]), ptr(t["wrmin"]) or None, ptr(t["wrmax"]) or None, ptr(t["bres"]) or None,
+                              ptr(q4[0]) or None, ptr(q4[1]) or None, ptr(P["Wc2"]), ptr(P["Wc2T"]), ptr(P["s1_2"]),
+                              ptr(P["s0_2"]), ptr(P["dws2"]), Cio, Chid, n2, 0, s))
+        off = Cio
+    check(L.fqss_tcn_prep(ptr(t["Wskip"]), ptr(t["wsmin"]) or None, ptr(t["wsmax"]) or None, ptr(t["bskip"]) or None,
+                          ptr(q4[0]) or None, ptr(q4[1]) or None, ptr(P["Wc2"]), ptr(P["Wc2T"]), ptr(P["s1_2"]), ptr(P["s0_2"]),
+                          ptr(P["dws2"]), Cio, Chid, n2, off, s))
+    if quant:
+        wdw = torch.empty_like(t["Wdw"], memory_format=torch.contiguous_format)
+        check(lib().fqss_fq_weight_fwd(ptr(t["Wdw"]), ptr(wdw), None, 1, Chid, t["Wdw"].shape[-1], ptr(t["wdmin"]), ptr(t["wdmax"]), 8, s))
+    else:
+        wdw = t["Wdw"]
+    P["wdw"] = wdw
+    return P
+
+
+def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
+    blk.B, blk.M, blk.dil, blk.quant, blk.first_block, blk.has_res = B, M, dil, int(quant), int(first), int(has_res)
+    blk.Chid, blk.Cio, blk.ld = t["W1"].shape[0], t["W1"].shape[1], ld
+    for k in ("Wc1", "Wc1T", "s1_1", "s0_1", "dws1", "Wc2", "Wc2T", "s1_2", "s0_2", "dws2", "wdw"):
+        setattr(blk, k, ptr(P[k]))
+    blk.bdw = ptr(t["bdw"])
+    blk.slope1, blk.slope3 = ptr(t["slope1"]), ptr(t["slope3"])
+    blk.gn1_w, blk.gn1_b, blk.gn2_w, blk.gn2_b = ptr(t["g1w"]), ptr(t["g1b"]), ptr(t["g2w"]), ptr(t["g2b"])
+
+    def qr(a, b):
+        r = QRange()
+        r.rmin, r.rmax = (ptr(a) or None), (ptr(b) or None)
+        return r
+    blk.q_in = qr(*q_in) if quant else qr(None, None)
+    for name, lo, hi in (("q1", "q1min", "q1max"), ("q2", "q2min", "q2max"), ("q3", "q3min", "q3max"), ("q4", "q4min", "q4max"),
+                         ("qres", "qresmin", "qresmax"), ("qskip", "qskipmin", "qskipmax"), ("qadd", "qaddmin", "qaddmax"),
+                         ("qadds", "qaddsmin", "qaddsmax")):
+        setattr(blk, name, qr(t[lo], t[hi]))
+
+
+def _alloc_acts(B, Cio, Chid, ld, has_res, dev):
+    bf = torch.bfloat16
+    A = dict(y1=torch.empty((B, Chid, ld), device=dev), y3=torch.empty((B, Chid, ld), device=dev),
+             stats1=torch.empty(2 * B, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B, dtype=torch.float64, device=dev),
+             a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), skip_y=torch.empty((B, Cio, ld), device=dev),
+             skip_out=torch.empty((B, Cio, ld), device=dev))
+    if has_res:
+        A.update(res_y=torch.empty((B, Cio, ld), device=dev), x_out=torch.empty((B, Cio, ld), device=dev),
+                 x_out_op=torch.empty((B, Cio, ld), dtype=bf, device=dev))
+    return A
+
+
+def _as_pitched(x, ld):
+    """[B,C,M] tensor with row pitch exactly `ld` (view when possible, else one repack)."""
+    B, Cc, M = x.shape
+    if x.stride(2) == 1 and x.stride(1) == ld and x.stride(0) == Cc * ld and x.data_ptr() % 16 == 0:
+        return x
+    buf = torch.empty((B, Cc, ld), device=x.device, dtype=x.dtype)
+    buf[:, :, :M].copy_(x)
+    return buf[:, :, :M]
+
+
+class FusedTCNFunction(Function):
+    @staticmethod
+    def forward(ctx, x, skip_in, meta, *flat):
+        """x: [B,Cio,M] fake-quantised values entering block `start`; skip_in: running skip sum (None when
+        start == 0); meta: (quant, dils, q_in, start, total) -- `start`/`total` place the given blocks inside
+        the full stack (block 0 starts the skip sum, block total-1 has no residual output); flat: the
+        per-block tensors in _BLOCK_SLOTS order (None where a block has no such parameter)."""
+        N.require_cuda(x)
+        L = _libx()
+        quant, dils, q_in, start, total = meta
+        nb = len(dils)
+        ns = len(_BLOCK_SLOTS)
+        dev = x.device
+        B, Cio, M = x.shape
+        ld = (M + 7) // 8 * 8
+        x = _as_pitched(x.detach(), ld)
+        s = stream_ptr()
+        x_op = torch.empty((B, Cio, ld), dtype=torch.bfloat16, device=dev)
+        qi = q_in if quant else (None, None)
+        check(L.fqss_tcn_encode(ptr(x), ld, ptr(x_op), ld, B * Cio, M, ptr(qi[0]) or None, ptr(qi[1]) or None, s))
+        states = []
+        cur_x, cur_op = x, x_op
+        cur_skip = _as_pitched(skip_in.detach(), ld) if skip_in is not None else None
+        cur_q = q_in
+        for i in range(nb):
+            t = dict(zip(_BLOCK_SLOTS, flat[i * ns:(i + 1) * ns]))
+            first, has_res = (start + i) == 0, (start + i) < total - 1
+            Chid = t["W1"].shape[0]
+            P = _prep_block(t, quant, first, has_res, cur_q, dev)
+            A = _alloc_acts(B, Cio, Chid, ld, has_res, dev)
+            blk = TcnBlock()
+            _fill_block(blk, t, P, quant, first, has_res, dils[i], B, M, ld, cur_q)
+            blk.x_op, blk.x_in, blk.skip_in = ptr(cur_op), ptr(cur_x), ptr(cur_skip) or None
+            for k in ("y1", "stats1", "y3", "stats3", "a4_op", "skip_y", "skip_out"):
+                setattr(blk, k, ptr(A[k]))
+            if has_res:
+                blk.res_y, blk.x_out, blk.x_out_op = ptr(A["res_y"]), ptr(A["x_out"]), ptr(A["x_out_op"])
+            check(L.fqss_tcn_block_fwd(C.byref(blk), s))
+            st = BlockState()
+            st.t, st.dil, st.first, st.has_res, st.prep, st.act, st.blk = t, dils[i], first, has_res, P, A, blk
+            A["x_in"], A["x_op"], A["skip_in"] = cur_x, cur_op, cur_skip
+            states.append(st)
+            if has_res:
+                cur_x, cur_op = A["x_out"], A["x_out_op"]
+            cur_skip = A["skip_out"]
+            cur_q = (t["qaddmin"], t["qaddmax"])
+        ctx.states = states
+        ctx.meta = (quant, B, Cio, M, ld)
+        ctx.nflat = len(flat)
+        x_last = states[-1].act.get("x_out")
+        if x_last is None:
+            x_last = torch.zeros((B, Cio, M), device=dev)          # dead output of the last block
+            ctx.mark_non_differentiable(x_last)
+            return x_last, cur_skip[:, :, :M]
+        return x_last[:, :, :M], cur_skip[:, :, :M]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_xo, g_skip):
+        L = _libx()
+        quant, B, Cio, M, ld = ctx.meta
+        states = ctx.states
+        ctx.states = None
+        dev = g_skip.device
+        nb = len(states)
+        ns = len(_BLOCK_SLOTS)
+        Chid = states[0].t["W1"].shape[0]
+        bf = torch.bfloat16
+        s = stream_ptr()
+        g_ss = torch.zeros((B, Cio, ld), device=dev)
+        if g_skip is not None:
+            g_ss[:, :, :M].copy_(g_skip)
+        g_x = torch.zeros((B, Cio, ld), device=dev)
+        if g_xo is not None and states[-1].has_res:
+            g_x[:, :, :M].copy_(g_xo)
+        scratch = dict(dY2=torch.empty((B, 2 * Cio, ld), dtype=bf, device=dev), ga=torch.empty((B, Chid, ld), dtype=bf, device=dev),
+                       gb=torch.empty((B, Chid, ld), dtype=bf, device=dev), dY1=torch.empty((B, Chid, ld), dtype=bf, device=dev),
+                       gxd=torch.empty((B, Cio, ld), device=dev))
+        ws = torch.empty(int(L.fqss_tcn_ws_bytes(B, Cio, Chid)), dtype=torch.uint8, device=dev)
+        grads = [None] * ctx.nflat
+        for i in range(nb - 1, -1, -1):
+            st = states[i]
+            t = st.t
+            n2 = 2 * Cio if st.has_res else Cio
+            G = dict(dW1q=torch.empty((Chid, Cio), device=dev), db1=torch.empty(Chid, device=dev),
+                     dW2q=torch.empty((n2, Chid), device=dev), db2=torch.empty(n2, device=dev),
+                     dwdw=torch.empty((Chid, 3), device=dev), dbdw=torch.empty(Chid, device=dev),
+                     g1w=torch.empty(Chid, device=dev), g1b=torch.empty(Chid, device=dev),
+                     g2w=torch.empty(Chid, device=dev), g2b=torch.empty(Chid, device=dev),
+                     sl1=torch.empty(1, device=dev), sl3=torch.empty(1, device=dev), gq=torch.zeros(16, device=dev))
+            g = TcnBlockGrads()
+            g.g_x_out, g.g_skip_out, g.g_x_in, g.g_skip_in = ptr(g_x), ptr(g_ss), ptr(g_x), ptr(g_ss)
+            g.dY2, g.g_hid_a, g.g_hid_b, g.dY1, g.g_xd = ptr(scratch["dY2"]), ptr(scratch["ga"]), ptr(scratch["gb"]), ptr(scratch["dY1"]), ptr(scratch["gxd"])
+            g.dW1q, g.db1, g.dW2q, g.db2, g.dwdw, g.dbdw = ptr(G["dW1q"]), ptr(G["db1"]), ptr(G["dW2q"]), ptr(G["db2"]), ptr(G["dwdw"]), ptr(G["dbdw"])
+            g.g_gn1_w, g.g_gn1_b, g.g_gn2_w, g.g_gn2_b = ptr(G["g1w"]), ptr(G["g1b"]), ptr(G["g2w"]), ptr(G["g2b"])
+            g.g_slope1, g.g_slope3, g.g_q = ptr(G["sl1"]), ptr(G["sl3"]), ptr(G["gq"])
+            g.ws, g.ws_bytes = ptr(ws), ws.numel()
+            check(L.fqss_tcn_block_bwd(C.byref(st.blk), C.byref(g), s))
+            base = i * ns
+            out = {}
+            # gradients w.r.t. the fake-quantised weights -> raw weights + per-channel ranges
+            def wback(gq, wname, lo, hi, shape):
+                w = t[wname]
+                if quant:
+                    gw = torch.empty_like(w, memory_format=torch.contiguous_format)
+                    gmin, gmax = torch.empty_like(t[lo]), torch.empty_like(t[hi])
+                    ch = w.shape[0]
+                    inner = w.numel() // ch
+                    check(lib().fqss_fq_weight_bwd(ptr(gq), ptr(w), ptr(gw), ptr(gmin), ptr(gmax), 1, ch, inner, ptr(t[lo]), ptr(t[hi]), 8, s))
+                    return gw, gmin, gmax
+                return gq.view(shape), None, None
+            out["W1"], out["w1min"], out["w1max"] = wback(G["dW1q"], "W1", "w1min", "w1max", t["W1"].shape)
+            out["b1"] = G["db1"]
+            out["Wdw"], out["wdmin"], out["wdmax"] = wback(G["dwdw"], "Wdw", "wdmin", "wdmax", t["Wdw"].shape)
+            out["bdw"] = G["dbdw"]
+            off = 0
+            if st.has_res:
+                out["Wres"], out["wrmin"], out["wrmax"] = wback(G["dW2q"][:Cio], "Wres", "wrmin", "wrmax", t["Wres"].shape)
+                out["bres"] = G["db2"][:Cio]
+                off = Cio
+            out["Wskip"], out["wsmin"], out["wsmax"] = wback(G["dW2q"][off:off + Cio], "Wskip", "wsmin", "wsmax", t["Wskip"].shape)
+            out["bskip"] = G["db2"][off:off + Cio]
+            out["slope1"], out["slope3"] = G["sl1"], G["sl3"]
+            out["g1w"], out["g1b"], out["g2w"], out["g2b"] = G["g1w"], G["g1b"], G["g2w"], G["g2b"]
+            if quant:
+                gq = G["gq"]
+                for j, nm in enumerate(("q1", "q2", "q3", "q4", "qres", "qskip", "qadd", "qadds")):
+                    if t[nm + "min"] is not None and not (nm in ("qres", "qadd") and not st.has_res) and not (nm == "qadds" and st.first):
+                        out[nm + "min"], out[nm + "max"] = gq[2 * j:2 * j + 1], gq[2 * j + 1:2 * j + 2]
+            for j, name in enumerate(_BLOCK_SLOTS):
+                if t[name] is not None and name in out and out[name] is not None and ctx.needs_input_grad[3 + base + j]:
+                    grads[base + j] = out[name].reshape(t[name].shape)
+        g_skip_in = g_ss[:, :, :M] if (not states[0].first and ctx.needs_input_grad[1]) else None
+        return (g_x[:, :, :M], g_skip_in, None) + tuple(grads)
+
+
+def fused_tcn(x, blocks, adds, quant, q_in, start=0, total=None, skip_in=None):
+    """Run blocks [start, start+len(blocks)) of a stack of `total` blocks.  blocks: ConvBlock modules; adds: the
+    AddQ that merges each block's skip into the running sum (entry i belongs to blocks[i]; None for block 0).
+    Returns (x_out, skip_sum)."""
+    total = len(blocks) if total is None else total
+    flat, dils = [], []
+    for i, blk in enumerate(blocks):
+        t, dil = block_tensors(blk, adds[i] if adds is not None else None, quant)
+        dils.append(dil)
+        flat.extend(t[k] for k in _BLOCK_SLOTS)
+    return FusedTCNFunction.apply(x, skip_in, (quant, tuple(dils), q_in, start, total), *flat)
+
+
+def fused_eligible(masker, x):
+    """True when MaskGenerator can hand its TCN stack to the fused engine (quantised, steady state)."""
+    from .qat import qat_layers as QL
+    from .qat.qat_quant import GradientActivationFakeQuantize as AQ, GradientWeightFakeQuantize as WQm
+    if not x.is_cuda or x.dtype != torch.float32:
+        return False
+    blocks = list(masker.TCN)
+    b0 = blocks[0]
+    sb = b0.shared_block
+    if not (isinstance(sb[0], QL.Conv1dNlQ) and isinstance(sb[2], QL.GroupNormQ) and isinstance(sb[3], QL.Conv1dNlQ)
+            and isinstance(sb[5], QL.GroupNormQ) and isinstance(b0.res_conv, QL.Conv1dQ) and isinstance(b0.add, QL.AddQ)):
+        return False
+    Chid, Cio = sb[0].conv1d.weight.shape[0], sb[0].conv1d.weight.shape[1]
+    if Cio % 128 or Chid % 128 or sb[3].conv1d.kernel_size[0] != 3:
+        return False
+    for m in masker.modules():
+        if isinstance(m, AQ) and (m.observing() or m.n_bits != 8):
+            return False
+        if isinstance(m, WQm) and (m.observer_mode or m.n_bits != 8):
+            return False
+        if isinstance(m, QL.LayerQ) and type(m).__name__ in ("Conv1dNlQ", "Conv1dQ") and isinstance(m.weight_fake_quantize, torch.nn.Identity):
+            return False
+        if isinstance(m, QL.LayerQ) and isinstance(m.activation_fake_quantize, torch.nn.Identity):
+            return False
+        if isinstance(m, torch.nn.PReLU) and m.weight.numel() != 1:
+            return False
+    return True

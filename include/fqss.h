@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 2
+#define FQSS_ABI_VERSION 3
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -158,6 +158,69 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
  * ------------------------------------------------------------------------------------------- */
 int fqss_pw_gemm(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32,
                  void* out_bf16, const float* addend, int B, int K, int N, int M, int64_t ld, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * M1  fused ConvBlock of the TCN (convtasnetq.py:11-42 after quantize_model :270-277), forward and
+ *     backward, for the steady state (observers off).  Four forward launches per block:
+ *       K1 expand GEMM (+bias, PReLU/FQ statistics for the first gLN)          x_op  -> y1, stats1
+ *       K2 depthwise kernel (PReLU+FQ, gLN+FQ on load; 3-tap dilated FIR; stats) y1   -> y3, stats3
+ *       K3a hidden quantiser (PReLU+FQ, gLN+FQ -> bf16 operand)                  y3   -> a4_op
+ *       K3 res/skip GEMM (+bias, FQ, residual add + FQ, skip accumulate + FQ)    a4_op-> res_y, skip_y, x_out, skip_out
+ *     Tensors: [B][C][ld] with ld % 8 == 0; *_op tensors are bf16 GEMM operands holding the integer
+ *     fake-quant codes (quant=1) or the real values (quant=0, the float teacher).  Every q* entry is
+ *     {min_range, max_range} device pointers of a GradientActivationFakeQuantize.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct fqss_qrange { const float* rmin; const float* rmax; } fqss_qrange;
+
+typedef struct fqss_tcn_block {
+    int32_t B, M, dil, quant, first_block, has_res, Cio, Chid;
+    int64_t ld;
+    /* prepared by fqss_tcn_prep (per step) */
+    const void* Wc1;  const void* Wc1T; const float* s1_1; const float* s0_1; const float* dws1;   /* expand [Chid,Cio] */
+    const void* Wc2;  const void* Wc2T; const float* s1_2; const float* s0_2; const float* dws2;   /* res|skip [2*Cio,Chid] */
+    const float* wdw; const float* bdw;                                                          /* depthwise [Chid,3], [Chid] */
+    /* layer parameters */
+    const float* slope1; const float* slope3;
+    const float* gn1_w; const float* gn1_b; const float* gn2_w; const float* gn2_b;
+    fqss_qrange q_in, q1, q2, q3, q4, qres, qskip, qadd, qadds;
+    /* activations */
+    const void* x_op; const float* x_in; const float* skip_in;
+    float* y1; double* stats1; float* y3; double* stats3; void* a4_op;
+    float* res_y; float* skip_y; float* x_out; void* x_out_op; float* skip_out;
+} fqss_tcn_block;
+
+/* Weight preparation for one 1x1 conv of the fused path: fake-quantise W [N][K] per output channel
+ * (wmin/wmax NULL: float model, Wc = bf16(W)) and fold the input quantiser (amin/amax NULL: identity)
+ * and the bias into the GEMM epilogue constants:
+ *   Wc  [N][K] bf16 written at row offset n_off of a [Ntot][K] matrix, WcT [K][Ntot] bf16 (for dgrad),
+ *   s1[n_off+o] = dw[o]*da, s0[n_off+o] = dw[o]*min_a*sum_k code[o,k] + bias[o], dws[n_off+o] = dw[o]. */
+int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const float* bias, const float* amin,
+                  const float* amax, void* Wc, void* WcT, float* s1, float* s0, float* dws, int N, int K, int Ntot,
+                  int n_off, void* stream);
+
+/* fp32 values -> bf16 GEMM operand of the first block (codes w.r.t. {rmin,rmax}; NULL ranges: plain cast) */
+int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int M, const float* rmin,
+                    const float* rmax, void* stream);
+
+int fqss_tcn_block_fwd(const fqss_tcn_block* blk, void* stream);
+
+/* Backward of one block.  In: g_x_out, g_skip_out (fp32 [B][Cio][ld]).  Out: g_x_in, g_skip_in (may alias the
+ * inputs).  Scratch (caller-owned, reusable across blocks): dY2 bf16 [B][2Cio][ld], g_hid_a/g_hid_b bf16
+ * [B][Chid][ld], dY1 bf16 [B][Chid][ld], g_xd fp32 [B][Cio][ld], wpart fp32 (fqss_tcn_ws_bytes).  Parameter
+ * gradients are WRITTEN (not accumulated): dW1q [Chid][Cio], db1, dW2q [2Cio][Chid], db2 (w.r.t. the
+ * FAKE-QUANTISED weights: run fqss_fq_weight_bwd on them), dwdw [Chid][3] (same), dbdw, g_gn*, slopes,
+ * and 2 floats {g_min,g_max} per activation quantiser in g_q (order: q1,q2,q3,q4,qres,qskip,qadd,qadds). */
+typedef struct fqss_tcn_block_grads {
+    const float* g_x_out; const float* g_skip_out; float* g_x_in; float* g_skip_in;
+    void* dY2; void* g_hid_a; void* g_hid_b; void* dY1; float* g_xd;
+    float* dW1q; float* db1; float* dW2q; float* db2; float* dwdw; float* dbdw;
+    float* g_gn1_w; float* g_gn1_b; float* g_gn2_w; float* g_gn2_b; float* g_slope1; float* g_slope3;
+    float* g_q;        /* 16 floats */
+    void* ws; size_t ws_bytes;
+} fqss_tcn_block_grads;
+
+size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid);
+int fqss_tcn_block_bwd(const fqss_tcn_block* blk, const fqss_tcn_block_grads* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * P1  FQSS splitter / reconstructor (process.py:10-52)

@@ -1,0 +1,179 @@
+"""GPU: the fused tensor-core TCN path (tcgen05 GEMMs + fused row kernels, fqss_b200.tcn_engine).
+
+ * float mode (no quantisers): the whole stack against plain torch modules -- validates the GEMM
+   orientation, depthwise / gLN / PReLU forward and every backward stage without quantisation chaos
+   (tolerance = bf16 operands, "1e-2 path").
+ * quantised mode, teacher forced: each block is fed the ORACLE's exact input / output gradients
+   (codes must sit on the oracle's grid up to rare +-1 moves; gradients to the 1e-2 path tolerance).
+ * quantised mode, free running: fused stack vs the per-layer fp32 path on the same GPU.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import fqss_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+MED_KW = dict(n_spks=2, kernel_size=16, stride=8, n_filters=128, bn_chan=128, hid_chan=256, n_blocks=2, n_repeats=2)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def test_fused_float_stack_vs_torch():
+    from fqss_b200 import tcn_engine as E
+    from fqss_b200.qat.models.convtasnetq import ConvTasNetQ
+    torch.manual_seed(0)
+    model = ConvTasNetQ(**MED_KW).to(DEV)
+    blocks = list(model.masker.TCN)
+    for blk in blocks:                       # make slopes / affine params non-trivial
+        with torch.no_grad():
+            for p in blk.parameters():
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn_like(p))
+    B, M = 3, 499
+    x = (torch.randn(B, 128, M, device=DEV) * 0.5).requires_grad_(True)
+    # torch reference (bf16-rounded GEMM operands are part of the fused path; reference stays fp32)
+    feats, tot = x, None
+    for i, blk in enumerate(blocks):
+        feats, skip = blk(feats)
+        tot = skip if tot is None else tot + skip
+    gsk = torch.randn_like(tot)
+    tot.backward(gsk)
+    ref_gx = x.grad.clone()
+    ref_grads = {n: p.grad.clone() for n, p in model.masker.TCN.named_parameters() if p.grad is not None}
+    model.zero_grad()
+    x2 = x.detach().clone().requires_grad_(True)
+    xo, ss = E.fused_tcn(x2, blocks, None, False, (None, None))
+    assert rel(ss, tot) < 1e-2, rel(ss, tot)
+    ss.backward(gsk)
+    assert rel(x2.grad, ref_gx) < 2e-2, rel(x2.grad, ref_gx)
+    worst = ("", 0.0)
+    for n, p in model.masker.TCN.named_parameters():
+        if n in ref_grads:
+            assert p.grad is not None, n
+            r = rel(p.grad, ref_grads[n])
+            if r > worst[1]:
+                worst = (n, r)
+    assert worst[1] < 3e-2, worst
+
+
+def _medium_pair():
+    from fqss_b200.testing import _oracle_cfg, model_pair, oracle_params
+    model, fmodel = model_pair(MED_KW, DEV, seed=0)
+    cfg = _oracle_cfg(MED_KW)
+    gen = torch.Generator().manual_seed(1)
+    src = torch.randn(2, 2, 4000, generator=gen) * 0.05
+    mix = src.sum(1, keepdim=True)
+    P, fP = oracle_params(model), oracle_params(fmodel)
+    st = O.calibrate(P, mix, cfg, passes=2)
+    model.load_state_dict({k: v for k, v in P.items()}, strict=True)
+    for m in model.modules():
+        if hasattr(m, "observer_mode"):
+            m.observer_mode = False
+    return model, fmodel, cfg, P, fP, st, mix, src
+
+
+def test_fused_quant_blocks_teacher_forced():
+    from fqss_b200 import tcn_engine as E
+    model, fmodel, cfg, P, fP, st, mix, src = _medium_pair()
+    P.leafify()
+    taps = {}
+    est = O.separator_forward(P, mix, cfg, st, quant=True, tap=taps)
+    names = []
+    for i in range(cfg.n_tcn):
+        names += ["masker.TCN.%d.in" % i, "masker.TCN.%d.out" % i, "masker.TCN.%d.skip" % i]
+    for k in names:
+        taps[k].retain_grad()
+    with torch.no_grad():
+        fest = O.separator_forward(fP, mix, cfg, quant=False)
+    loss, _ = O.fqss_kd_loss(est, fest, src, 0.1)
+    loss.backward()
+    nb = cfg.n_tcn
+    masker = model.masker
+    for i in range(nb):
+        pre = "masker.TCN.%d." % i
+        blk = masker.TCN[i]
+        # quantiser that produced this block's input
+        qin = masker.bottleneck[1].activation_fake_quantize if i == 0 else masker.TCN[i - 1].add.activation_fake_quantize
+        x = taps[pre + "in"].detach().to(DEV).requires_grad_(True)
+        # emulate the skip merge of the reference: total_i = adds[i-1](total_{i-1}, skip_i); feed a zero running sum so
+        # that skip_out = FQ_adds(0 + FQ_skip(skip)) is directly comparable with the oracle's AddQ of (0, skip)
+        adds = [masker.adds[i - 1] if i > 0 else None]
+        skip_in = torch.zeros_like(x) if i > 0 else None
+        if skip_in is not None:
+            skip_in.requires_grad_(True)
+        model.zero_grad(set_to_none=True)
+        xo, ss = E.fused_tcn(x, [blk], adds, True, (qin.min_range, qin.max_range), start=i, total=nb, skip_in=skip_in)
+        # oracle for the same sub-graph
+        ctx = O._Ctx(P, cfg, st, True, None)
+        xin_o = taps[pre + "in"].detach().clone().requires_grad_(True)
+        out_o, skip_o = O._tcn_block(ctx, i, xin_o)
+        if i > 0:
+            ss_o = ctx.aq("masker.adds.%d.activation_fake_quantize" % (i - 1), torch.zeros_like(skip_o) + skip_o)
+        else:
+            ss_o = skip_o
+        qs = "masker.adds.%d.activation_fake_quantize." % (i - 1) if i > 0 else pre + "skip_conv.activation_fake_quantize."
+        step = (P[qs + "max_range"] - P[qs + "min_range"]).item() / 255
+        d = (ss.detach().cpu() - ss_o.detach()).abs()
+        assert d.max() <= 2.01 * step and (d > 0.5 * step).float().mean() < 1e-2, (i, "skip", d.max() / step, (d > 0.5 * step).float().mean())
+        if i < nb - 1:
+            qa = pre + "add.activation_fake_quantize."
+            step = (P[qa + "max_range"] - P[qa + "min_range"]).item() / 255
+            d = (xo.detach().cpu() - out_o.detach()).abs()
+            assert d.max() <= 2.01 * step and (d > 0.5 * step).float().mean() < 1e-2, (i, "out", d.max() / step)
+        # backward with the oracle's gradients
+        for k in P:
+            P[k].grad = None
+        g_skip = taps[pre + "skip"].grad
+        if i < nb - 1:
+            g_out = taps[pre + "out"].grad
+            torch.autograd.backward([out_o, ss_o], [g_out, g_skip])
+            torch.autograd.backward([xo, ss], [g_out.to(DEV), g_skip.to(DEV)])
+        else:
+            ss_o.backward(g_skip)
+            ss.backward(g_skip.to(DEV))
+        assert rel(x.grad, xin_o.grad) < 3e-2, (i, "gx", rel(x.grad, xin_o.grad))
+        worst = ("", 0.0)
+        for k, p in blk.named_parameters():
+            go = P[pre + k].grad
+            if go is None:
+                assert p.grad is None or float(p.grad.abs().max()) == 0.0, (i, k)
+                continue
+            assert p.grad is not None, (i, k)
+            r = rel(p.grad, go)
+            if "range" in k and (p.grad.cpu() - go).abs().max() < 1e-5:
+                continue
+            if r > worst[1]:
+                worst = (k, r)
+        assert worst[1] < 6e-2, (i, worst)
+
+
+def test_fused_vs_per_layer_path_end_to_end():
+    """Same model, same inputs on the GPU: fused tensor-core stack vs per-layer fp32 wrappers."""
+    from fqss_b200.losses import fqss_training_step
+    from fqss_b200.qat.models.convtasnetq import MaskGenerator
+    model, fmodel, cfg, P, fP, st, mix, src = _medium_pair()
+    mixd, srcd = mix.to(DEV), src.to(DEV)
+    out = {}
+    for fused in (False, True):
+        MaskGenerator.use_fused = fused
+        try:
+            model.zero_grad(set_to_none=True)
+            loss, _, est = fqss_training_step(model, fmodel, mixd, srcd, 0.1)
+            loss.backward()
+            out[fused] = (loss.item(), est.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+        finally:
+            MaskGenerator.use_fused = True
+    assert abs(out[True][0] - out[False][0]) < 0.3, (out[True][0], out[False][0])
+    assert rel(out[True][1], out[False][1]) < 0.1
+    assert set(out[True][2].keys()) == set(out[False][2].keys())
+    num = sum((out[True][2][k].double() * out[False][2][k].double()).sum().item() for k in out[True][2])
+    n1 = sum(out[True][2][k].double().pow(2).sum().item() for k in out[True][2]) ** 0.5
+    n2 = sum(out[False][2][k].double().pow(2).sum().item() for k in out[False][2]) ** 0.5
+    assert num / (n1 * n2) > 0.9 and abs(n1 / n2 - 1) < 0.2, (num / (n1 * n2), n1 / n2)
