@@ -38,10 +38,26 @@ def test_fused_float_stack_vs_torch():
                     p.add_(0.1 * torch.randn_like(p))
     B, M = 3, 499
     x = (torch.randn(B, 128, M, device=DEV) * 0.5).requires_grad_(True)
-    # torch reference (bf16-rounded GEMM operands are part of the fused path; reference stays fp32)
+    # torch reference with the SAME operand rounding as the fused float path (bf16 GEMM operands, STE), so
+    # that PReLU sign decisions coincide and the comparison isolates the backward arithmetic
+    import torch.nn.functional as F
+
+    def r16(t):
+        return t + (t.bfloat16().float() - t).detach()
+
+    def ref_block(blk, xin):
+        sb = blk.shared_block
+        h = F.prelu(F.conv1d(r16(xin), r16(sb[0].weight), sb[0].bias), sb[1].weight)
+        h = sb[2](h)
+        h = F.prelu(F.conv1d(h, sb[3].weight, sb[3].bias, padding=sb[3].padding[0], dilation=sb[3].dilation[0],
+                             groups=h.shape[1]), sb[4].weight)
+        h = r16(sb[5](h))
+        res = F.conv1d(h, r16(blk.res_conv.weight), blk.res_conv.bias)
+        skip = F.conv1d(h, r16(blk.skip_conv.weight), blk.skip_conv.bias)
+        return xin + res, skip
     feats, tot = x, None
     for i, blk in enumerate(blocks):
-        feats, skip = blk(feats)
+        feats, skip = ref_block(blk, feats)
         tot = skip if tot is None else tot + skip
     gsk = torch.randn_like(tot)
     tot.backward(gsk)
@@ -50,13 +66,17 @@ def test_fused_float_stack_vs_torch():
     model.zero_grad()
     x2 = x.detach().clone().requires_grad_(True)
     xo, ss = E.fused_tcn(x2, blocks, None, False, (None, None))
-    assert rel(ss, tot) < 1e-2, rel(ss, tot)
+    assert rel(ss, tot) < 1e-3, rel(ss, tot)
     ss.backward(gsk)
     assert rel(x2.grad, ref_gx) < 2e-2, rel(x2.grad, ref_gx)
     worst = ("", 0.0)
+    slope_scale = max(float(g.abs().max()) for n, g in ref_grads.items() if g.numel() == 1)
     for n, p in model.masker.TCN.named_parameters():
         if n in ref_grads:
             assert p.grad is not None, n
+            if p.numel() == 1:      # PReLU slopes: one scalar = a sum with heavy cancellation -> absolute scale
+                assert abs(float(p.grad) - float(ref_grads[n])) < 3e-2 * slope_scale, (n, float(p.grad), float(ref_grads[n]))
+                continue
             r = rel(p.grad, ref_grads[n])
             if r > worst[1]:
                 worst = (n, r)
