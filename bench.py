@@ -41,6 +41,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; never a reported number)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket ONE extra step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
+                         "numbers printed by such a run are never bench values")
     return ap.parse_args()
 
 
@@ -242,6 +245,12 @@ def run_ours(args):
         return ms, t0, time.time()
 
     timed(max(args.warmup, 3), False)
+    if args.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(*dev_batches[0])
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
