@@ -61,8 +61,10 @@ _SIGS = {
     "fqss_sconv_bwd": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, i32, i32, vp, sz, vp]),
     "fqss_tconv_fwd": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "fqss_tconv_bwd": (i32, [vp, i64, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp, sz, vp]),
-    "fqss_pw_gemm": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
-    "fqss_tcn_prep": (i32, [vp] * 11 + [i32] * 4 + [vp]),
+    "fqss_pw_gemm": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, i32, vp]),
+    "fqss_pw_gemm_ex": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i32, vp]),
+    "fqss_split_bf16": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, vp]),
+    "fqss_tcn_prep": (i32, [vp] * 11 + [i32] * 5 + [vp]),
     "fqss_tcn_encode": (i32, [vp, i64, vp, i64, i64, i32, vp, vp, vp]),
     "fqss_tcn_block_fwd": (i32, [vp, vp]),
     "fqss_tcn_block_bwd": (i32, [vp, vp, vp]),
@@ -94,7 +96,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 3:
+                if L.fqss_abi_version() != 4:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

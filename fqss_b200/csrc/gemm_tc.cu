@@ -67,6 +67,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int nt = p.N / NT;
     const int num_tiles = p.B * mt * nt;
     const int kchunks = p.K / BK;
+    const int a_rows = p.a_rows > 0 ? p.a_rows : p.K;
 
     for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {
         s1s[i] = __ldg(p.s1 + i);
@@ -106,8 +107,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sa = smem + stage * stage_bytes<NT>();
                     uint8_t* sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(&bar->full[stage], stage_bytes<NT>());
-                    tma_load_3d(sa, &tmA, &bar->full[stage], m0, kc * BK, b);
-                    tma_load_3d(sa + A_STAGE_BYTES / 2, &tmA, &bar->full[stage], m0 + 64, kc * BK, b);
+                    const int ak = (kc * BK) % a_rows;
+                    tma_load_3d(sa, &tmA, &bar->full[stage], m0, ak, b);
+                    tma_load_3d(sa + A_STAGE_BYTES / 2, &tmA, &bar->full[stage], m0 + 64, ak, b);
                     tma_load_2d(sb, &tmB, &bar->full[stage], kc * BK, n_idx * NT);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -202,17 +204,25 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         if (valid) p.out_bf16[idx] = __float2bfloat16_rn(y);
                     } else if (EPI == EPI_ADD) {
                         if (valid) p.out_f32[idx] = y + __ldg(p.addend + idx);
+                    } else if (EPI == EPI_RELU_MUL) {       // float mask head: relu(conv) * encoder features
+                        if (valid) p.out_f32[idx] = fmaxf(y, 0.f) * __ldg(p.addend + ((int64_t)b * p.mul_C + (o % p.mul_C)) * p.ld + m);
                     } else if (EPI == EPI_RESSKIP) {
                         if (valid) {
                             if (o < p.n_res) {          // residual conv -> FQ -> (x + res) -> FQ
                                 const int64_t i2 = ((int64_t)b * p.n_res + o) * p.ld + m;
-                                p.res_y[i2] = y;
+                                if (p.res_y) p.res_y[i2] = y;
                                 float r = p.quant ? actqf_fq(qres, y) : y;
                                 float z = __fadd_rn(__ldg(p.x_in + i2), r);
                                 if (p.quant) {
                                     float c = actqf_code(qadd, z);
                                     p.x_out[i2] = actqf_decode(qadd, c);
                                     p.x_out_op[i2] = __float2bfloat16_rn(c);
+                                } else if (p.split) {
+                                    p.x_out[i2] = z;
+                                    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
+                                    const int64_t ih = ((int64_t)b * 2 * p.n_res + o) * p.ld + m;
+                                    p.x_out_op[ih] = hi;
+                                    p.x_out_op[ih + (int64_t)p.n_res * p.ld] = __float2bfloat16_rn(z - __bfloat162float(hi));
                                 } else {
                                     p.x_out[i2] = z;
                                     p.x_out_op[i2] = __float2bfloat16_rn(z);
@@ -220,7 +230,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             } else {                    // skip conv -> FQ -> (skip_sum + skip) -> FQ
                                 const int os = o - p.n_res;
                                 const int64_t i2 = ((int64_t)b * (p.N - p.n_res) + os) * p.ld + m;
-                                p.skip_y[i2] = y;
+                                if (p.skip_y) p.skip_y[i2] = y;
                                 float sk = p.quant ? actqf_fq(qskip, y) : y;
                                 if (p.first_block) {
                                     p.skip_out[i2] = sk;
@@ -326,8 +336,9 @@ int run(int epi, const void* act_bf16, const void* w_bf16, const Args& a, cudaSt
                  "pw_gemm: unsupported shape B=%d M=%d K=%d N=%d (K %% 64 == 0, N %% 128 == 0, N <= %d)", a.B, a.M, a.K, a.N, MAXN);
     FQSS_REQUIRE(a.ld >= a.M && a.ld % 8 == 0, -2, "pw_gemm: row pitch must be a multiple of 8 elements (TMA 16 B strides)");
     FQSS_REQUIRE(aligned16(act_bf16) && aligned16(w_bf16), -2, "pw_gemm: operands must be 16-byte aligned");
+    FQSS_REQUIRE(a.a_rows >= 0 && a.a_rows <= a.K && a.a_rows % BK == 0, -1, "pw_gemm: a_rows=%d must be a multiple of %d and <= K", a.a_rows, BK);
     CUtensorMap ta, tb;
-    int r = make_act_map(&ta, act_bf16, a.B, a.K, a.M, a.ld);
+    int r = make_act_map(&ta, act_bf16, a.B, a.a_rows > 0 ? a.a_rows : a.K, a.M, a.ld);
     FQSS_REQUIRE(r == 0, -4, "pw_gemm: cuTensorMapEncodeTiled(activations) failed (%d)", r);
     const bool wide = (a.N % 256 == 0);
     r = make_w_map(&tb, w_bf16, a.N, a.K, wide ? 256 : 128);
@@ -341,6 +352,7 @@ int run(int epi, const void* act_bf16, const void* w_bf16, const Args& a, cudaSt
         FQSS_GEMM_CASE(EPI_RESSKIP)
         FQSS_GEMM_CASE(EPI_BF16)
         FQSS_GEMM_CASE(EPI_ADD)
+        FQSS_GEMM_CASE(EPI_RELU_MUL)
     }
 #undef FQSS_GEMM_CASE
     set_error("pw_gemm: unknown epilogue %d", epi);
@@ -358,12 +370,22 @@ extern "C" {
 //   out[b,o,m] = s1[o] * sum_k act[b,k,m] * w[o,k] + s0[o]     (+ addend[b,o,m] when given)
 // act, w: bf16.  out_f32 and/or out_bf16 may be given.
 int fqss_pw_gemm(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32, void* out_bf16,
-                 const float* addend, int B, int K, int N, int M, int64_t ld, void* stream) {
+                 const float* addend, int B, int K, int N, int M, int64_t ld, int a_rows, void* stream) {
+    return fqss_pw_gemm_ex(act_bf16, w_bf16, s1, s0, out_f32, out_bf16, addend, 0, B, K, N, M, ld, a_rows, stream);
+}
+
+// mul_C > 0: out_f32[b,o,m] = relu(s1*acc + s0) * addend[b, o % mul_C, m]   (mask head of the float model)
+int fqss_pw_gemm_ex(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32, void* out_bf16,
+                    const float* addend, int mul_C, int B, int K, int N, int M, int64_t ld, int a_rows, void* stream) {
     tcg::Args a{};
-    a.B = B; a.M = M; a.K = K; a.N = N; a.ld = ld; a.s1 = s1; a.s0 = s0; a.quant = 0;
+    a.B = B; a.M = M; a.K = K; a.N = N; a.ld = ld; a.s1 = s1; a.s0 = s0; a.quant = 0; a.a_rows = a_rows;
     a.out_f32 = out_f32; a.out_bf16 = (__nv_bfloat16*)out_bf16; a.addend = addend;
     int epi = tcg::EPI_STORE;
-    if (addend) {
+    if (mul_C > 0) {
+        FQSS_REQUIRE(out_f32 && addend && N % mul_C == 0, -1, "pw_gemm_ex: relu-mul needs an fp32 output, a multiplicand and N %% mul_C == 0");
+        a.mul_C = mul_C;
+        epi = tcg::EPI_RELU_MUL;
+    } else if (addend) {
         FQSS_REQUIRE(out_f32, -1, "pw_gemm: addend needs an fp32 output");
         epi = tcg::EPI_ADD;
     } else if (!out_f32) {

@@ -7,10 +7,12 @@
 namespace fqss {
 namespace tcg {
 
-enum { EPI_STORE = 0, EPI_EXPAND = 1, EPI_RESSKIP = 2, EPI_BF16 = 3, EPI_ADD = 4 };
+enum { EPI_STORE = 0, EPI_EXPAND = 1, EPI_RESSKIP = 2, EPI_BF16 = 3, EPI_ADD = 4, EPI_RELU_MUL = 5 };
 
 struct Args {
     int B, M, K, N;              // batch, valid frames, reduction channels, output channels
+    int a_rows;                  // activation rows per sample (0: = K); reduction index k reads row k % a_rows
+    int split;                   // EPI_RESSKIP, float model: x_out_op is a [hi ; lo] bf16 pair ([B][2*n_res][ld])
     int64_t ld;                  // row pitch (elements) of every [.,.,Mp] activation tensor involved
     const float* s1;             // [N] per-output-channel scale   (delta_w[o]*delta_a, or 1)
     const float* s0;             // [N] per-output-channel offset  (delta_w[o]*min_a*R[o] + bias[o])
@@ -19,8 +21,9 @@ struct Args {
     float* out_f32;
     // EPI_BF16 (and optional for STORE): bf16 output [B][N][ld]
     __nv_bfloat16* out_bf16;
-    // EPI_ADD: addend [B][N][ld]
+    // EPI_ADD: addend [B][N][ld].  EPI_RELU_MUL: multiplicand [B][mul_C][ld], out = relu(y) * addend[b][o % mul_C][m]
     const float* addend;
+    int mul_C;
     // EPI_EXPAND: gLN statistics of FQ(PReLU(y)) -> stats[2*B] (double, pre-zeroed)
     const float* slope;
     const float* q1_min; const float* q1_max;

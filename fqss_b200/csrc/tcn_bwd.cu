@@ -369,6 +369,8 @@ size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid) {
 int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, void* stream) {
     int rc = tcn_validate_block(p, "tcn_block_bwd");
     if (rc) return rc;
+    FQSS_REQUIRE(!p->split && p->skip_y && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
+                 "tcn_block_bwd: block was run in inference mode (split operands / no saved pre-activations)");
     FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->g_hid_b && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
     FQSS_REQUIRE(!p->has_res || (g->g_x_out && g->g_xd), -1, "tcn_block_bwd: residual path needs g_x_out / g_xd");
     FQSS_REQUIRE(p->first_block || g->g_skip_in, -1, "tcn_block_bwd: g_skip_in missing");

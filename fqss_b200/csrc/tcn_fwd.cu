@@ -22,7 +22,7 @@ namespace fqss {
 __global__ void tcn_prep_kernel(const float* __restrict__ W, const float* __restrict__ wmin, const float* __restrict__ wmax,
                                 const float* __restrict__ bias, const float* __restrict__ amin, const float* __restrict__ amax,
                                 __nv_bfloat16* __restrict__ Wc, __nv_bfloat16* __restrict__ WcT, float* __restrict__ s1,
-                                float* __restrict__ s0, float* __restrict__ dws, int K, int Ntot, int n_off) {
+                                float* __restrict__ s0, float* __restrict__ dws, int K, int Ntot, int n_off, int split) {
     __shared__ double sh[32];
     const int o = blockIdx.x;
     const bool quant = wmin != nullptr;
@@ -33,8 +33,15 @@ __global__ void tcn_prep_kernel(const float* __restrict__ W, const float* __rest
         float w = W[(int64_t)o * K + k];
         float c = quant ? wq_code(q, w) : w;
         __nv_bfloat16 cb = __float2bfloat16_rn(c);          // codes -128..127 are exact in bf16
-        Wc[(int64_t)(n_off + o) * K + k] = cb;
-        WcT[(int64_t)k * Ntot + n_off + o] = cb;
+        if (split) {                                        // float model, fp32-grade: [hi | hi | lo]
+            __nv_bfloat16* row = Wc + (int64_t)(n_off + o) * 3 * K;
+            row[k] = cb;
+            row[K + k] = cb;
+            row[2 * K + k] = __float2bfloat16_rn(c - __bfloat162float(cb));
+        } else {
+            Wc[(int64_t)(n_off + o) * K + k] = cb;
+        }
+        if (WcT) WcT[(int64_t)k * Ntot + n_off + o] = cb;
         rsum += (double)c;
     }
     double v[1] = {rsum};
@@ -121,12 +128,52 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_t
     const int nvec = (p.M + 3) >> 2;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
         float4 y = ldg4_stream(y3 + 4 * v);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(hidden3_op(h, y.x), hidden3_op(h, y.y));
-        __nv_bfloat162 hi = __floats2bfloat162_rn(hidden3_op(h, y.z), hidden3_op(h, y.w));
+        const float o0 = hidden3_op(h, y.x), o1 = hidden3_op(h, y.y), o2 = hidden3_op(h, y.z), o3 = hidden3_op(h, y.w);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(o2, o3);
         uint2 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&lo);
         pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        *reinterpret_cast<uint2*>(out + 4 * v) = pk;
+        if (!p.split) {
+            *reinterpret_cast<uint2*>(out + 4 * v) = pk;
+        } else {
+            // [hi ; lo] pair: sample b owns rows [2*b*Chid, 2*(b+1)*Chid); residual = value - bf16(value)
+            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + ((int64_t)b * 2 * p.Chid + c) * p.ld;
+            __nv_bfloat16* ol = oh + (int64_t)p.Chid * p.ld;
+            *reinterpret_cast<uint2*>(oh + 4 * v) = pk;
+            __nv_bfloat162 rl = __floats2bfloat162_rn(o0 - __low2float(lo), o1 - __high2float(lo));
+            __nv_bfloat162 rh = __floats2bfloat162_rn(o2 - __low2float(hi), o3 - __high2float(hi));
+            pk.x = *reinterpret_cast<uint32_t*>(&rl);
+            pk.y = *reinterpret_cast<uint32_t*>(&rh);
+            *reinterpret_cast<uint2*>(ol + 4 * v) = pk;
+        }
+    }
+}
+
+// fp32 -> [hi | hi | lo] (weights, layout 0) or per-sample [hi rows ; lo rows] (activations, layout 1)
+__global__ void __launch_bounds__(ROW_THREADS) split_bf16_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
+                                                                int64_t ldo, int cols, int C, int layout) {
+    const int64_t r = blockIdx.x;
+    const float* src = x + r * ldx;
+    if (layout == 0) {
+        __nv_bfloat16* row = out + r * 3 * (int64_t)cols;
+        for (int k = threadIdx.x; k < cols; k += ROW_THREADS) {
+            const float v = src[k];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            row[k] = hi;
+            row[cols + k] = hi;
+            row[2 * cols + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
+    } else {
+        const int64_t b = r / C, c = r % C;
+        __nv_bfloat16* oh = out + (b * 2 * C + c) * ldo;
+        __nv_bfloat16* ol = oh + (int64_t)C * ldo;
+        for (int m = threadIdx.x; m < cols; m += ROW_THREADS) {
+            const float v = src[m];
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+            oh[m] = hi;
+            ol[m] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        }
     }
 }
 
@@ -152,9 +199,10 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
     FQSS_REQUIRE((size_t)p->ld * sizeof(float) * 3 <= 200 * 1024, -1, "%s: row too long for shared-memory staging (M=%d)", who, p->M);
     FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
-    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && p->y3 && p->stats1 && p->stats3 && p->a4_op && p->skip_y && p->skip_out, -1,
+    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && p->y3 && p->stats1 && p->stats3 && p->a4_op && p->skip_out, -1,
                  "%s: missing activation buffers", who);
-    if (p->has_res) FQSS_REQUIRE(p->res_y && p->x_out && p->x_out_op, -1, "%s: missing residual buffers", who);
+    FQSS_REQUIRE(!p->split || !p->quant, -1, "%s: split operands are a float-model (quant == 0) feature", who);
+    if (p->has_res) FQSS_REQUIRE(p->x_out && p->x_out_op, -1, "%s: missing residual buffers", who);
     if (!p->first_block) FQSS_REQUIRE(p->skip_in, -1, "%s: missing skip_in", who);
     if (p->quant) {
         const fqss_qrange* qs[] = {&p->q1, &p->q2, &p->q3, &p->q4, &p->qskip};
@@ -174,11 +222,13 @@ using namespace fqss;
 extern "C" {
 
 int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const float* bias, const float* amin, const float* amax,
-                  void* Wc, void* WcT, float* s1, float* s0, float* dws, int N, int K, int Ntot, int n_off, void* stream) {
-    FQSS_REQUIRE(W && Wc && WcT && s1 && s0 && dws && N > 0 && K > 0 && n_off >= 0 && n_off + N <= Ntot, -1, "tcn_prep: bad argument");
+                  void* Wc, void* WcT, float* s1, float* s0, float* dws, int N, int K, int Ntot, int n_off, int split, void* stream) {
+    FQSS_REQUIRE(W && Wc && s1 && s0 && dws && N > 0 && K > 0 && n_off >= 0 && n_off + N <= Ntot, -1, "tcn_prep: bad argument");
+    FQSS_REQUIRE(WcT || split, -1, "tcn_prep: WcT may be NULL only for split (inference) operands");
+    FQSS_REQUIRE(!split || (wmin == nullptr && amin == nullptr), -1, "tcn_prep: split operands are for the float model");
     FQSS_REQUIRE((wmin == nullptr) == (wmax == nullptr) && (amin == nullptr) == (amax == nullptr), -1, "tcn_prep: ranges come in pairs");
     tcn_prep_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(W, wmin, wmax, bias, amin, amax, (__nv_bfloat16*)Wc, (__nv_bfloat16*)WcT, s1,
-                                                         s0, dws, K, Ntot, n_off);
+                                                         s0, dws, K, Ntot, n_off, split);
     return check_launch("tcn_prep");
 }
 
@@ -187,6 +237,13 @@ int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, in
     FQSS_REQUIRE(x && out_bf16 && rows > 0 && M > 0 && ldx >= M && ldo >= M, -1, "tcn_encode: bad argument");
     tcn_encode_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)out_bf16, ldo, M, rmin, rmax);
     return check_launch("tcn_encode");
+}
+
+int fqss_split_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int cols, int C, int layout, void* stream) {
+    FQSS_REQUIRE(x && out_bf16 && rows > 0 && cols > 0 && ldx >= cols && (layout == 0 || (layout == 1 && C > 0 && rows % C == 0 && ldo >= cols)),
+                 -1, "split_bf16: bad argument");
+    split_bf16_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)out_bf16, ldo, cols, C, layout);
+    return check_launch("split_bf16");
 }
 
 int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
@@ -199,6 +256,7 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     // K1
     tcg::Args a{};
     a.B = p->B; a.M = p->M; a.K = p->Cio; a.N = p->Chid; a.ld = p->ld; a.s1 = p->s1_1; a.s0 = p->s0_1; a.quant = p->quant;
+    if (p->split) { a.K = 3 * p->Cio; a.a_rows = 2 * p->Cio; }
     a.out_f32 = p->y1; a.slope = p->slope1; a.q1_min = p->q1.rmin; a.q1_max = p->q1.rmax; a.stats = p->stats1;
     rc = tcg::run(tcg::EPI_EXPAND, p->x_op, p->Wc1, a, s);
     if (rc) return rc;
@@ -217,6 +275,7 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     // K3
     tcg::Args k{};
     k.B = p->B; k.M = p->M; k.K = p->Chid; k.N = p->has_res ? 2 * p->Cio : p->Cio; k.ld = p->ld;
+    if (p->split) { k.K = 3 * p->Chid; k.a_rows = 2 * p->Chid; k.split = 1; }
     k.s1 = p->s1_2; k.s0 = p->s0_2; k.quant = p->quant;
     k.n_res = p->has_res ? p->Cio : 0; k.first_block = p->first_block;
     k.res_y = p->res_y; k.skip_y = p->skip_y; k.x_in = p->x_in; k.x_out = p->x_out; k.x_out_op = (__nv_bfloat16*)p->x_out_op;

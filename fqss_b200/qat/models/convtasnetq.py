@@ -110,7 +110,13 @@ class ConvTasNetQ(nn.Module):
     def post_process(self, x):
         return postprocess(x, n_combiner=self.n_combiner)
 
+    use_float_engine = True   # class-level switch: False keeps the un-quantised model on plain torch modules
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.use_float_engine and x.is_cuda and type(self.encoder) is nn.Conv1d:
+            from ... import float_engine as FE          # float (teacher) inference on the sm_100a kernels
+            if FE.eligible(self, x):
+                return FE.forward(self, x)
         x = self.pre_process(x)                                    # [B, n_splitter, T]
         batch = x.shape[0]
         feats = self.encoder(x)                                    # [B, F, M]

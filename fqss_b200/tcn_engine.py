@@ -26,7 +26,8 @@ class QRange(C.Structure):
 
 class TcnBlock(C.Structure):
     _fields_ = [("B", C.c_int32), ("M", C.c_int32), ("dil", C.c_int32), ("quant", C.c_int32), ("first_block", C.c_int32),
-                ("has_res", C.c_int32), ("Cio", C.c_int32), ("Chid", C.c_int32), ("ld", i64),
+                ("has_res", C.c_int32), ("Cio", C.c_int32), ("Chid", C.c_int32), ("split", C.c_int32), ("_pad0", C.c_int32),
+                ("ld", i64),
                 ("Wc1", vp), ("Wc1T", vp), ("s1_1", vp), ("s0_1", vp), ("dws1", vp),
                 ("Wc2", vp), ("Wc2T", vp), ("s1_2", vp), ("s0_2", vp), ("dws2", vp),
                 ("wdw", vp), ("bdw", vp),
@@ -59,17 +60,42 @@ def _libx():
     return _L
 
 
-def pw_gemm(act_bf16, w_bf16, s1, s0, M, addend=None, out_dtype=torch.float32):
-    """out[b,o,m] = s1[o] * sum_k act[b,k,m] w[o,k] + s0[o] (+ addend) on tcgen05; act [B,K,ld], w [N,K] bf16."""
+def pw_gemm(act_bf16, w_bf16, s1, s0, M, addend=None, out_dtype=torch.float32, mul=None):
+    """out[b,o,m] = s1[o] * sum_k act[b, k % rows, m] w[o,k] + s0[o] (+ addend) on tcgen05; act [B,rows,ld], w [N,K]
+    bf16 (rows < K: split [hi ; lo] activations against [hi | hi | lo] weights, see include/fqss.h)."""
     N.require_cuda(act_bf16, w_bf16, s1, s0, addend)
-    B, K, ld = act_bf16.shape
-    Nn = w_bf16.shape[0]
-    assert act_bf16.is_contiguous() and w_bf16.is_contiguous() and w_bf16.shape[1] == K
+    B, a_rows, ld = act_bf16.shape
+    Nn, K = w_bf16.shape
+    assert act_bf16.is_contiguous() and w_bf16.is_contiguous() and a_rows <= K
     out = torch.empty((B, Nn, ld), device=act_bf16.device, dtype=out_dtype)
+    if mul is not None:          # out = relu(.) * mul[b, o % C, m]; mul: fp32 [B,C,M] with row pitch ld
+        Cm = mul.shape[1]
+        assert mul.stride(2) == 1 and mul.stride(1) == ld and mul.stride(0) == Cm * ld and out_dtype == torch.float32
+        check(lib().fqss_pw_gemm_ex(ptr(act_bf16), ptr(w_bf16), ptr(s1), ptr(s0), ptr(out), None, ptr(mul), Cm, B, K, Nn, M, ld,
+                                    a_rows, stream_ptr()))
+        return out
     f32 = out if out_dtype == torch.float32 else None
     b16 = out if out_dtype == torch.bfloat16 else None
     check(lib().fqss_pw_gemm(ptr(act_bf16), ptr(w_bf16), ptr(s1), ptr(s0), ptr(f32) or None, ptr(b16) or None,
-                             ptr(addend) or None, B, K, Nn, M, ld, stream_ptr()))
+                             ptr(addend) or None, B, K, Nn, M, ld, a_rows, stream_ptr()))
+    return out
+
+
+def split_bf16_weights(w):
+    """fp32 [N,K] -> bf16 [N,3K] = [hi | hi | lo]."""
+    w = w.detach().reshape(w.shape[0], -1).contiguous()
+    out = torch.empty((w.shape[0], 3 * w.shape[1]), dtype=torch.bfloat16, device=w.device)
+    check(lib().fqss_split_bf16(ptr(w), w.shape[1], ptr(out), 0, w.shape[0], w.shape[1], 1, 0, stream_ptr()))
+    return out
+
+
+def split_bf16_acts(x, ld):
+    """fp32 [B,C,M] (any row pitch) -> bf16 [B,2C,ld] = per sample [hi rows ; lo rows]."""
+    B, Cc, M = x.shape
+    if x.stride(2) != 1 or x.stride(0) != Cc * x.stride(1):
+        x = x.contiguous()
+    out = torch.empty((B, 2 * Cc, ld), dtype=torch.bfloat16, device=x.device)
+    check(lib().fqss_split_bf16(ptr(x), x.stride(1), ptr(out), ld, B * Cc, M, Cc, 1, stream_ptr()))
     return out
 
 
@@ -146,17 +172,17 @@ def _prep_block(t, quant, first, has_res, q_in, dev):
     qi = q_in if quant else (None, None)
     check(L.fqss_tcn_prep(ptr(t["W1"]), ptr(t["w1min"]) or None, ptr(t["w1max"]) or None, ptr(t["b1"]) or None,
                           ptr(qi[0]) or None, ptr(qi[1]) or None, ptr(P["Wc1"]), ptr(P["Wc1T"]), ptr(P["s1_1"]), ptr(P["s0_1"]),
-                          ptr(P["dws1"]), Chid, Cio, Chid, 0, s))
+                          ptr(P["dws1"]), Chid, Cio, Chid, 0, 0, s))
     off = 0
     q4 = (t["q4min"], t["q4max"]) if quant else (None, None)
     if has_res:
         check(L.fqss_tcn_prep(ptr(t["Wres"]), ptr(t["wrmin"]) or None, ptr(t["wrmax"]) or None, ptr(t["bres"]) or None,
                               ptr(q4[0]) or None, ptr(q4[1]) or None, ptr(P["Wc2"]), ptr(P["Wc2T"]), ptr(P["s1_2"]),
-                              ptr(P["s0_2"]), ptr(P["dws2"]), Cio, Chid, n2, 0, s))
+                              ptr(P["s0_2"]), ptr(P["dws2"]), Cio, Chid, n2, 0, 0, s))
         off = Cio
     check(L.fqss_tcn_prep(ptr(t["Wskip"]), ptr(t["wsmin"]) or None, ptr(t["wsmax"]) or None, ptr(t["bskip"]) or None,
                           ptr(q4[0]) or None, ptr(q4[1]) or None, ptr(P["Wc2"]), ptr(P["Wc2T"]), ptr(P["s1_2"]), ptr(P["s0_2"]),
-                          ptr(P["dws2"]), Cio, Chid, n2, off, s))
+                          ptr(P["dws2"]), Cio, Chid, n2, off, 0, s))
     if quant:
         wdw = torch.empty_like(t["Wdw"], memory_format=torch.contiguous_format)
         check(lib().fqss_fq_weight_fwd(ptr(t["Wdw"]), ptr(wdw), None, 1, Chid, t["Wdw"].shape[-1], ptr(t["wdmin"]), ptr(t["wdmax"]), 8, s))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 3
+#define FQSS_ABI_VERSION 4
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -152,12 +152,28 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core (tcgen05 / TMEM / TMA) 1x1 convolution used by the fused TCN path:
  *   out[b,o,m] = s1[o] * sum_k act[b,k,m] * w[o,k] + s0[o]  (+ addend[b,o,m])
- * act [B][K][ld] and w [N][K] are bf16.  With integer fake-quant codes as operands the accumulation is
+ * act [B][a_rows][ld] and w [N][K] are bf16.  With integer fake-quant codes as operands the accumulation is
  * exact (order independent); s1/s0 carry the de-quantisation affine and the bias.  K % 64 == 0,
  * N % 128 == 0, ld % 8 == 0.  Outputs: out_f32 and/or out_bf16 ([B][N][ld]); addend needs out_f32.
+ * a_rows = 0 means a_rows = K.  a_rows < K (a_rows % 64 == 0) makes reduction index k read activation row
+ * k % a_rows: with act = [hi ; lo] (a_rows = 2C, x = hi + lo in bf16 pairs) and w = [w_hi | w_hi | w_lo]
+ * (K = 3C) one launch computes the three-term split product hi*w_hi + lo*w_hi + hi*w_lo, i.e. an fp32-grade
+ * (2^-16) contraction on the bf16 tensor pipe -- the float teacher's 1x1 convolutions.
  * ------------------------------------------------------------------------------------------- */
 int fqss_pw_gemm(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32,
-                 void* out_bf16, const float* addend, int B, int K, int N, int M, int64_t ld, void* stream);
+                 void* out_bf16, const float* addend, int B, int K, int N, int M, int64_t ld, int a_rows, void* stream);
+
+/* as fqss_pw_gemm; mul_C > 0 selects the float mask-head epilogue (convtasnetq.py:97-99,204-205):
+ *   out_f32[b,o,m] = relu(s1[o]*acc + s0[o]) * addend[b, o % mul_C, m],  addend = encoder features [B][mul_C][ld] */
+int fqss_pw_gemm_ex(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32,
+                    void* out_bf16, const float* addend, int mul_C, int B, int K, int N, int M, int64_t ld, int a_rows,
+                    void* stream);
+
+/* fp32 [rows][ldw] -> bf16 split pair for the float (teacher) GEMMs.
+ *   layout 0 (weights [N][K]):   out [N][3K]  = [hi | hi | lo]      (rows = N, cols = K)
+ *   layout 1 (activations [B][C][M]): out [B][2C][ldo] = per sample [hi rows ; lo rows]  (rows = B*C, cols = M) */
+int fqss_split_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int cols, int C, int layout,
+                    void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * M1  fused ConvBlock of the TCN (convtasnetq.py:11-42 after quantize_model :270-277), forward and
@@ -174,6 +190,9 @@ typedef struct fqss_qrange { const float* rmin; const float* rmax; } fqss_qrange
 
 typedef struct fqss_tcn_block {
     int32_t B, M, dil, quant, first_block, has_res, Cio, Chid;
+    int32_t split;   /* quant == 0 only: *_op tensors are bf16 [hi ; lo] pairs with 2x the rows, Wc1/Wc2 are
+                        [N][3K] = [hi | hi | lo] (fp32-grade float model; forward / inference only)          */
+    int32_t _pad0;
     int64_t ld;
     /* prepared by fqss_tcn_prep (per step) */
     const void* Wc1;  const void* Wc1T; const float* s1_1; const float* s0_1; const float* dws1;   /* expand [Chid,Cio] */
@@ -193,10 +212,11 @@ typedef struct fqss_tcn_block {
  * (wmin/wmax NULL: float model, Wc = bf16(W)) and fold the input quantiser (amin/amax NULL: identity)
  * and the bias into the GEMM epilogue constants:
  *   Wc  [N][K] bf16 written at row offset n_off of a [Ntot][K] matrix, WcT [K][Ntot] bf16 (for dgrad),
- *   s1[n_off+o] = dw[o]*da, s0[n_off+o] = dw[o]*min_a*sum_k code[o,k] + bias[o], dws[n_off+o] = dw[o]. */
+ *   s1[n_off+o] = dw[o]*da, s0[n_off+o] = dw[o]*min_a*sum_k code[o,k] + bias[o], dws[n_off+o] = dw[o].
+ * split != 0 (float model only): Wc is [Ntot][3K] = [hi | hi | lo] bf16 pairs of W, WcT may be NULL. */
 int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const float* bias, const float* amin,
                   const float* amax, void* Wc, void* WcT, float* s1, float* s0, float* dws, int N, int K, int Ntot,
-                  int n_off, void* stream);
+                  int n_off, int split, void* stream);
 
 /* fp32 values -> bf16 GEMM operand of the first block (codes w.r.t. {rmin,rmax}; NULL ranges: plain cast) */
 int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int M, const float* rmin,

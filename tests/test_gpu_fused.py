@@ -197,3 +197,45 @@ def test_fused_vs_per_layer_path_end_to_end():
     n1 = sum(out[True][2][k].double().pow(2).sum().item() for k in out[True][2]) ** 0.5
     n2 = sum(out[False][2][k].double().pow(2).sum().item() for k in out[False][2]) ** 0.5
     assert num / (n1 * n2) > 0.9 and abs(n1 / n2 - 1) < 0.2, (num / (n1 * n2), n1 / n2)
+
+
+def test_float_teacher_engine_vs_torch_and_oracle():
+    """The KD teacher (un-quantised ConvTasNetQ under no_grad) through the sm_100a float engine: split-bf16
+    tcgen05 GEMMs must reproduce the fp32 forward (torch modules with TF32 off, and the CPU oracle)."""
+    from fqss_b200.qat.models.convtasnetq import ConvTasNetQ
+    from fqss_b200.testing import _oracle_cfg, oracle_params
+    from fqss_b200 import _native as N
+    torch.manual_seed(3)
+    model = ConvTasNetQ(**MED_KW).to(DEV)
+    with torch.no_grad():
+        for p in model.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    gen = torch.Generator().manual_seed(5)
+    mix = (torch.randn(3, 2, 4000, generator=gen) * 0.05).sum(1, keepdim=True).to(DEV)
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            ConvTasNetQ.use_float_engine = False
+            ref = model(mix)
+            ConvTasNetQ.use_float_engine = True
+            c0 = N.launch_count
+            got = model(mix)
+            assert N.launch_count > c0, "float engine did not run"
+            got2 = model(mix)                      # cached weight preparation
+    finally:
+        ConvTasNetQ.use_float_engine = True
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert got.shape == ref.shape == (3, 2, 4000)
+    assert torch.equal(got, got2)
+    assert rel(got, ref) < 2e-4, rel(got, ref)
+    cfg = _oracle_cfg(MED_KW)
+    with torch.no_grad():
+        est_o = O.separator_forward(oracle_params(model), mix.cpu(), cfg, quant=False)
+    assert rel(got, est_o) < 2e-4, rel(got, est_o)
+    # a parameter update invalidates the cached operands
+    with torch.no_grad():
+        model.masker.TCN[1].res_conv.weight.mul_(1.5)
+        got3 = model(mix)
+    assert rel(got3, got) > 1e-4
