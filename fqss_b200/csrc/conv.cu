@@ -9,6 +9,15 @@ namespace fqss {
 
 int num_sms();
 
+// tiled kernels for the recipe's filterbank geometry (kernel 16, hop 8): conv_edge.cu.  Return 1 when a shape
+// is not handled there (the generic kernels below then run).
+bool edge_geometry_ok(int K, int stride);
+int edge_analysis_fwd(const float* x, int64_t ldx, int T, const float* w, float* y, int64_t ldy, int B, int Cin, int Co, int Mo,
+                      cudaStream_t s);
+int edge_synthesis_fwd(const float* x, int64_t ldx, const float* w, int64_t wstride, float* y, int64_t ldy, int B, int Ci, int M, int T,
+                       cudaStream_t s);
+int edge_wgrad(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Cin, int Co, int Mo, double* acc, cudaStream_t s);
+
 // =============================================================================================
 // batched SGEMM, 128x128x8 tiles, 256 threads, 8x8 register tile per thread
 //   MODE 0 fwd  : C[o,m] = sum_i W[o,i]   X_b[i,m]  (+bias[o])
@@ -346,6 +355,8 @@ int fqss_sconv_fwd(const float* x, int64_t ldx, const float* w, float* y, int64_
                  "sconv_fwd: bad argument (Cin*K <= %d)", SC_MAXCK);
     const int Mo = (T - K) / stride + 1;
     FQSS_REQUIRE(ldx >= T && ldy >= Mo, -1, "sconv_fwd: bad pitch");
+    if (edge_geometry_ok(K, stride) && aligned16(y) && edge_analysis_fwd(x, ldx, T, w, y, ldy, B, Cin, Co, Mo, (cudaStream_t)stream) == 0)
+        return check_launch("sconv_fwd(tiled)");
     dim3 grid((Mo + 127) / 128, (Co + SC_OT - 1) / SC_OT, B);
     sconv_fwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(x, ldx, w, y, ldy, Cin, Co, Mo, K, stride);
     return check_launch("sconv_fwd");
@@ -359,15 +370,22 @@ int fqss_sconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     if (gx) {
         // gx[b,c,t] = sum_o sum_{m,k} w[o,c,k] gy[b,o,m]: the overlap-add kernel with weight row stride Cin*K
         FQSS_REQUIRE(Cin == 1, -1, "sconv_bwd: input gradient implemented for Cin == 1 (RQB re-encoder)");
-        dim3 grid((T + 255) / 256, B);
-        tconv_fwd_kernel<<<grid, 256, 0, s>>>(gy, ldgy, w, (int64_t)Cin * K, gx, ldgx, Co, Mo, K, stride, T);
+        // samples beyond the last frame's support receive no gradient
+        const int Tc = (Mo - 1) * stride + K;
+        if (Tc < T) cudaMemset2DAsync(gx + Tc, (size_t)ldgx * sizeof(float), 0, (size_t)(T - Tc) * sizeof(float), (size_t)B, s);
+        if (!(edge_geometry_ok(K, stride) && edge_synthesis_fwd(gy, ldgy, w, (int64_t)Cin * K, gx, ldgx, B, Co, Mo, Tc, s) == 0)) {
+            dim3 grid((T + 255) / 256, B);
+            tconv_fwd_kernel<<<grid, 256, 0, s>>>(gy, ldgy, w, (int64_t)Cin * K, gx, ldgx, Co, Mo, K, stride, T);
+        }
     }
     if (gw) {
         size_t need = (size_t)Co * Cin * K * sizeof(double);
         FQSS_REQUIRE(ws && ws_bytes >= need, -3, "sconv_bwd: workspace too small");
         cudaMemsetAsync(ws, 0, need, s);
-        dim3 grid((Mo + 1023) / 1024, Co, B);
-        sconv_gw_kernel<<<grid, 256, 0, s>>>(gy, ldgy, x, ldx, Cin, Co, Mo, K, stride, (double*)ws);
+        if (!(edge_geometry_ok(K, stride) && edge_wgrad(gy, ldgy, x, ldx, T, B, Cin, Co, Mo, (double*)ws, s) == 0)) {
+            dim3 grid((Mo + 1023) / 1024, Co, B);
+            sconv_gw_kernel<<<grid, 256, 0, s>>>(gy, ldgy, x, ldx, Cin, Co, Mo, K, stride, (double*)ws);
+        }
         int n = Co * Cin * K;
         f64_store_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)ws, gw, n);
     }
@@ -379,6 +397,8 @@ int fqss_tconv_fwd(const float* x, int64_t ldx, const float* w, float* y, int64_
     FQSS_REQUIRE(x && w && y && B > 0 && Ci > 0 && M > 0 && K > 0 && stride > 0 && ldx >= M, -1, "tconv_fwd: bad argument");
     const int T = (M - 1) * stride + K;
     FQSS_REQUIRE(ldy >= T, -1, "tconv_fwd: bad output pitch");
+    if (edge_geometry_ok(K, stride) && edge_synthesis_fwd(x, ldx, w, (int64_t)K, y, ldy, B, Ci, M, T, (cudaStream_t)stream) == 0)
+        return check_launch("tconv_fwd(tiled)");
     dim3 grid((T + 255) / 256, B);
     tconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, (int64_t)K, y, ldy, Ci, M, K, stride, T);
     return check_launch("tconv_fwd");
@@ -390,15 +410,19 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     const int T = (M - 1) * stride + K;
     cudaStream_t s = (cudaStream_t)stream;
     if (gx) {   // gx[b,c,m] = sum_k w[c,k] gy[b, m*stride+k]  == analysis conv with Cin=1, Co=Ci
-        dim3 grid((M + 127) / 128, (Ci + SC_OT - 1) / SC_OT, B);
-        sconv_fwd_kernel<<<grid, 128, 0, s>>>(gy, ldgy, w, gx, ldgx, 1, Ci, M, K, stride);
+        if (!(edge_geometry_ok(K, stride) && aligned16(gx) && edge_analysis_fwd(gy, ldgy, T, w, gx, ldgx, B, 1, Ci, M, s) == 0)) {
+            dim3 grid((M + 127) / 128, (Ci + SC_OT - 1) / SC_OT, B);
+            sconv_fwd_kernel<<<grid, 128, 0, s>>>(gy, ldgy, w, gx, ldgx, 1, Ci, M, K, stride);
+        }
     }
     if (gw) {   // gw[c,k] = sum_{b,m} x[b,c,m] gy[b, m*stride+k]
         size_t need = (size_t)Ci * K * sizeof(double);
         FQSS_REQUIRE(ws && ws_bytes >= need, -3, "tconv_bwd: workspace too small");
         cudaMemsetAsync(ws, 0, need, s);
-        dim3 grid((M + 1023) / 1024, Ci, B);
-        sconv_gw_kernel<<<grid, 256, 0, s>>>(x, ldx, gy, ldgy, 1, Ci, M, K, stride, (double*)ws);
+        if (!(edge_geometry_ok(K, stride) && edge_wgrad(x, ldx, gy, ldgy, T, B, 1, Ci, M, (double*)ws, s) == 0)) {
+            dim3 grid((M + 1023) / 1024, Ci, B);
+            sconv_gw_kernel<<<grid, 256, 0, s>>>(x, ldx, gy, ldgy, 1, Ci, M, K, stride, (double*)ws);
+        }
         int n = Ci * K;
         f64_store_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)ws, gw, n);
     }

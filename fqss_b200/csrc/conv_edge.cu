@@ -1,0 +1,241 @@
+// conv_edge.cu -- the filterbank convolutions at the two ends of the separator, tiled for B200:
+//   * analysis conv  (encoder, RQB re-encoder, and the decoder's input gradient):
+//         y[b,o,m] = sum_{c,k} w[o,c,k] x[b,c,8m+k]                      qat_layers.py:1030,1189
+//   * synthesis conv (decoder, and the re-encoder's input gradient):   overlap-add of 16-tap frames
+//         y[b,8q+r] = sum_c ( w[c,r] x[b,c,q] + w[c,r+8] x[b,c,q-1] )    qat_layers.py:1332,1194
+//   * their weight gradient  gw[o,c,k] = sum_{b,m} gy[b,o,m] x[b,c,8m+k]
+// Geometry of the recipe only: kernel 16, stride 8 (50 % overlapped frames; configs/convtasnet_2spks_8k.yaml).
+// Other geometries fall back to the generic kernels in conv.cu.
+//
+// All three are HBM-bound on the 512-channel tensor ([B,512,M] fp32, read or written exactly once):
+// the contraction is tiny (K*Cin = 16..32) so it runs on the FFMA pipe out of registers / shared memory,
+// with frames on lanes so that every global access is a coalesced 128-bit (or 64-bit) row segment.
+#include "fqss_common.cuh"
+
+namespace fqss {
+
+constexpr int EK = 16, ES = 8;          // taps, hop
+
+// ---------------------------------------------------------------------------------------------
+// analysis conv: CTA = 128 frames x 64 output channels, thread = 4 frames x 8 channels
+// ---------------------------------------------------------------------------------------------
+constexpr int AF = 128, AO = 64, AX = 132;      // AX: row stride of the de-interleaved window (bank-conflict free)
+constexpr int A_MAXCIN = 4;
+
+__global__ void __launch_bounds__(256) analysis_fwd_kernel(const float* __restrict__ x, int64_t ldx, int T, const float* __restrict__ w,
+                                                          float* __restrict__ y, int64_t ldy, int Cin, int Co, int Mo) {
+    __shared__ __align__(16) float xs[A_MAXCIN][ES][AX];      // xs[c][r][q] = x[c][8(m0+q)+r], q in [0,129]
+    __shared__ __align__(16) float ws[A_MAXCIN * EK][AO];      // ws[j][o]
+    const int b = blockIdx.z, o0 = blockIdx.y * AO, m0 = blockIdx.x * AF;
+    const int tid = threadIdx.x;
+    const int CK = Cin * EK;
+    for (int i = tid; i < CK * AO; i += 256) {
+        const int o = i / CK, j = i - o * CK;
+        ws[j][o] = (o0 + o < Co) ? __ldg(w + (int64_t)(o0 + o) * CK + j) : 0.f;
+    }
+    for (int c = 0; c < Cin; ++c) {
+        const float* xr = x + ((int64_t)b * Cin + c) * ldx;
+        const int t0 = m0 * ES;
+        for (int i = tid; i < (AF + 2) * ES; i += 256) {
+            const int t = t0 + i;
+            xs[c][i & 7][i >> 3] = (t < T) ? __ldg(xr + t) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int fg = tid & 31, og = tid >> 5;
+    float acc[4][8];
+#pragma unroll
+    for (int f = 0; f < 4; ++f)
+#pragma unroll
+        for (int o = 0; o < 8; ++o) acc[f][o] = 0.f;
+    for (int c = 0; c < Cin; ++c) {
+#pragma unroll
+        for (int r = 0; r < ES; ++r) {
+            const float4 xa = *reinterpret_cast<const float4*>(&xs[c][r][4 * fg]);
+            const float x4 = xs[c][r][4 * fg + 4];
+            const float xv[5] = {xa.x, xa.y, xa.z, xa.w, x4};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {                       // tap k = r + 8h reads frame q + h
+                const float4 wa = *reinterpret_cast<const float4*>(&ws[c * EK + r + ES * h][8 * og]);
+                const float4 wb = *reinterpret_cast<const float4*>(&ws[c * EK + r + ES * h][8 * og + 4]);
+                const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+#pragma unroll
+                    for (int o = 0; o < 8; ++o) acc[f][o] = fmaf(wv[o], xv[f + h], acc[f][o]);
+            }
+        }
+    }
+    const int m = m0 + 4 * fg;
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        const int oc = o0 + 8 * og + o;
+        if (oc >= Co) continue;
+        float* yr = y + ((int64_t)b * Co + oc) * ldy + m;
+        if (m + 3 < Mo || (m < Mo && m + 3 < ldy && (ldy & 3) == 0)) {
+            stg4(yr, make_float4(acc[0][o], acc[1][o], acc[2][o], acc[3][o]));   // pad columns may take garbage
+        } else {
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+                if (m + f < Mo) yr[f] = acc[f][o];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// synthesis conv: CTA = (sample, 63 owned hops q); 8 warps split the channels, lanes own 2 frames.
+//   Z[f][k] = sum_c w[c*wstride + k] x[b,c,f]  for the 64 frames f = q0-1 .. q0+62, then
+//   y[8q+r] = Z[q][r] + Z[q-1][r+8]  for q = q0 .. q0+62.
+// ---------------------------------------------------------------------------------------------
+constexpr int SQ = 63;
+
+__global__ void __launch_bounds__(256) synthesis_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                           int64_t wstride, float* __restrict__ y, int64_t ldy, int Ci, int M, int T) {
+    extern __shared__ __align__(16) float sm[];
+    float* wsm = sm;                         // [Ci][16]
+    float* zs = sm + (size_t)Ci * EK;        // [8 warps][64 frames][17]
+    const int b = blockIdx.y, q0 = blockIdx.x * SQ;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    for (int i = tid; i < Ci * EK; i += 256) wsm[i] = __ldg(w + (int64_t)(i >> 4) * wstride + (i & 15));
+    __syncthreads();
+    const int f0 = q0 - 1 + 2 * lane;        // this lane's frames f0, f0+1
+    const bool v0 = f0 >= 0 && f0 < M, v1 = f0 + 1 >= 0 && f0 + 1 < M;
+    const int cper = Ci >> 3;
+    const int cb = wp * cper;
+    float a0[EK], a1[EK];
+#pragma unroll
+    for (int k = 0; k < EK; ++k) a0[k] = a1[k] = 0.f;
+    const float* xb = x + ((int64_t)b * Ci + cb) * ldx;
+#pragma unroll 4
+    for (int c = 0; c < cper; ++c) {
+        const float* xr = xb + (int64_t)c * ldx;
+        const float x0 = v0 ? __ldg(xr + f0) : 0.f;
+        const float x1 = v1 ? __ldg(xr + f0 + 1) : 0.f;
+        const float4* wr = reinterpret_cast<const float4*>(wsm + (size_t)(cb + c) * EK);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const float4 wv = wr[g];
+            a0[4 * g] = fmaf(wv.x, x0, a0[4 * g]);         a1[4 * g] = fmaf(wv.x, x1, a1[4 * g]);
+            a0[4 * g + 1] = fmaf(wv.y, x0, a0[4 * g + 1]); a1[4 * g + 1] = fmaf(wv.y, x1, a1[4 * g + 1]);
+            a0[4 * g + 2] = fmaf(wv.z, x0, a0[4 * g + 2]); a1[4 * g + 2] = fmaf(wv.z, x1, a1[4 * g + 2]);
+            a0[4 * g + 3] = fmaf(wv.w, x0, a0[4 * g + 3]); a1[4 * g + 3] = fmaf(wv.w, x1, a1[4 * g + 3]);
+        }
+    }
+    float* zw = zs + (size_t)wp * 64 * 17;
+#pragma unroll
+    for (int k = 0; k < EK; ++k) {
+        zw[(2 * lane) * 17 + k] = a0[k];
+        zw[(2 * lane + 1) * 17 + k] = a1[k];
+    }
+    __syncthreads();
+    // 63 hops x 8 samples; frame index inside the tile: q - (q0 - 1) = jq + 1
+    for (int i = tid; i < SQ * ES; i += 256) {
+        const int jq = i >> 3, r = i & 7;
+        const int t = (q0 + jq) * ES + r;
+        if (t >= T) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) s += zs[((size_t)ww * 64 + jq + 1) * 17 + r] + zs[((size_t)ww * 64 + jq) * 17 + r + ES];
+        y[(int64_t)b * ldy + t] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient: gw[o, c*16+k] = sum_{b,m} g[b,o,m] * xs[b,c,8m+k]
+//   CTA = (frame chunk of 1024, 16 rows o, sample b); warp = 2 rows, lanes = frames; the signal window
+//   is de-interleaved in shared memory once per CTA and shared by all 16 rows.
+// ---------------------------------------------------------------------------------------------
+constexpr int WG_CHUNK = 1024, WG_ROWS = 16, WG_X = WG_CHUNK + 4;
+
+template <int CIN>
+__global__ void __launch_bounds__(256) edge_wgrad_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
+                                                        int T, int Co, int Mo, double* __restrict__ acc) {
+    extern __shared__ __align__(16) float xw[];            // [CIN][8][WG_X]: xw[c][r][q] = x[c][8(m0+q)+r]
+    const int b = blockIdx.z, o0 = blockIdx.y * WG_ROWS, m0 = blockIdx.x * WG_CHUNK;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int nfr = min(WG_CHUNK, Mo - m0);
+    for (int c = 0; c < CIN; ++c) {
+        const float* xr = x + ((int64_t)b * CIN + c) * ldx;
+        const int t0 = m0 * ES;
+        for (int i = tid; i < (WG_CHUNK + 1) * ES; i += 256) {
+            const int t = t0 + i;
+            xw[((size_t)c * ES + (i & 7)) * WG_X + (i >> 3)] = (t < T) ? __ldg(xr + t) : 0.f;
+        }
+    }
+    __syncthreads();
+    const int oa = o0 + 2 * wp, ob = oa + 1;
+    const bool va = oa < Co, vb = ob < Co;
+    const float* ga = g + ((int64_t)b * Co + (va ? oa : 0)) * ldg + m0;
+    const float* gb = g + ((int64_t)b * Co + (vb ? ob : 0)) * ldg + m0;
+    float sa[CIN * EK], sb[CIN * EK];
+#pragma unroll
+    for (int j = 0; j < CIN * EK; ++j) sa[j] = sb[j] = 0.f;
+    for (int q = lane; q < nfr; q += 32) {
+        const float g0 = va ? __ldg(ga + q) : 0.f;
+        const float g1 = vb ? __ldg(gb + q) : 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+#pragma unroll
+            for (int r = 0; r < ES; ++r) {
+                const float* row = xw + ((size_t)c * ES + r) * WG_X + q;
+                const float xlo = row[0], xhi = row[1];           // taps r and r+8
+                sa[c * EK + r] = fmaf(g0, xlo, sa[c * EK + r]);
+                sb[c * EK + r] = fmaf(g1, xlo, sb[c * EK + r]);
+                sa[c * EK + r + ES] = fmaf(g0, xhi, sa[c * EK + r + ES]);
+                sb[c * EK + r + ES] = fmaf(g1, xhi, sb[c * EK + r + ES]);
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < CIN * EK; ++j) {
+        const float ta = warp_sum(sa[j]), tb = warp_sum(sb[j]);
+        if (lane == 0) {
+            if (va) atomicAdd(acc + (int64_t)oa * (CIN * EK) + j, (double)ta);
+            if (vb) atomicAdd(acc + (int64_t)ob * (CIN * EK) + j, (double)tb);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side dispatch (called from the C ABI functions in conv.cu)
+// ---------------------------------------------------------------------------------------------
+bool edge_geometry_ok(int K, int stride) { return K == EK && stride == ES; }
+
+int edge_analysis_fwd(const float* x, int64_t ldx, int T, const float* w, float* y, int64_t ldy, int B, int Cin, int Co, int Mo,
+                      cudaStream_t s) {
+    if (Cin > A_MAXCIN) return 1;      // not handled here
+    dim3 grid((Mo + AF - 1) / AF, (Co + AO - 1) / AO, B);
+    analysis_fwd_kernel<<<grid, 256, 0, s>>>(x, ldx, T, w, y, ldy, Cin, Co, Mo);
+    return 0;
+}
+
+int edge_synthesis_fwd(const float* x, int64_t ldx, const float* w, int64_t wstride, float* y, int64_t ldy, int B, int Ci, int M, int T,
+                       cudaStream_t s) {
+    if (Ci % 8 != 0) return 1;
+    const size_t smem = ((size_t)Ci * EK + (size_t)8 * 64 * 17) * sizeof(float);
+    if (smem > 200 * 1024) return 1;
+    static bool cfg = false;
+    if (!cfg) {
+        cudaFuncSetAttribute(synthesis_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cfg = true;
+    }
+    dim3 grid((M + 1 + SQ - 1) / SQ, B);      // hops q = 0 .. M
+    synthesis_fwd_kernel<<<grid, 256, smem, s>>>(x, ldx, w, wstride, y, ldy, Ci, M, T);
+    return 0;
+}
+
+int edge_wgrad(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Cin, int Co, int Mo, double* acc, cudaStream_t s) {
+    if (Cin != 1 && Cin != 2) return 1;
+    const size_t smem = (size_t)Cin * ES * WG_X * sizeof(float);
+    static bool cfg = false;
+    if (!cfg) {
+        cudaFuncSetAttribute(edge_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(edge_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cfg = true;
+    }
+    dim3 grid((Mo + WG_CHUNK - 1) / WG_CHUNK, (Co + WG_ROWS - 1) / WG_ROWS, B);
+    if (Cin == 1) edge_wgrad_kernel<1><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
+    else edge_wgrad_kernel<2><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
+    return 0;
+}
+
+}  // namespace fqss

@@ -216,10 +216,12 @@ def test_depthwise_vs_torch(dil):
         assert rel(a, bb) < 1e-5
 
 
-@pytest.mark.parametrize("Cin", [1, 2])
-def test_strided_and_transposed_conv_vs_torch(Cin):
+@pytest.mark.parametrize("Cin,B,Co,T_,K,s", [(1, 3, 48, 1208, 16, 8), (2, 3, 48, 1208, 16, 8), (2, 2, 512, 32000, 16, 8),
+                                             (1, 2, 512, 32000, 16, 8), (1, 2, 40, 1003, 16, 8), (1, 2, 24, 700, 10, 5)])
+def test_strided_and_transposed_conv_vs_torch(Cin, B, Co, T_, K, s):
+    """Encoder / RQB re-encoder / decoder filterbank convs (tiled kernels for kernel 16 / hop 8, generic otherwise):
+    forward, input gradient and weight gradient against torch fp32; ragged tails (T not a multiple of the hop)."""
     from fqss_b200 import ops
-    B, Co, T_, K, s = 3, 48, 1208, 16, 8
     gen = torch.Generator().manual_seed(Cin)
     x, w = torch.randn(B, Cin, T_, generator=gen), torch.randn(Co, Cin, K, generator=gen) * 0.1
     Mo = (T_ - K) // s + 1
