@@ -77,10 +77,18 @@ __device__ __forceinline__ float actq_bwd(const ActQ& q, float x, float g, float
 }
 
 // ---------------------------------------------------------------------------------------------
-// "fast-exact" activation quantiser for the ALU-bound fused kernels: the code is computed with a
-// reciprocal multiply and falls back to the IEEE division only when the result sits within 1e-3 of
-// a rounding boundary, so codes stay bit-identical to actq_code() at ~1/3 of the instructions.
+// Exact activation quantiser for the fused (ALU-bound) kernels -- same bits as actq_*(), ~1/3 of the
+// issue slots and no MUFU / conversion-pipe instructions:
+//  * IEEE quotient without a division: with inv = RN(1/delta), q = RN(d*inv), r = d - q*delta (exact
+//    in one FMA), t = RN(q + r*inv) is the correctly rounded d/delta (Markstein's correction step);
+//    3 FMA-pipe instructions, branch-free.
+//  * rint (half-to-even) by the 1.5*2^23 magic constant on a value pre-clamped to [0, levels]:
+//    rint(clamp(t)) == clamp(rint(t)).  The low byte of (clamp(t) + MAGIC) is the integer code.
+//  * STE mask without rounding: 0 <= rint(t) <= levels  <=>  -0.5 <= t < levels + 0.5 (ties go to
+//    even: -0.5 -> -0 is inside, levels + 0.5 -> levels + 1 is outside).
 // ---------------------------------------------------------------------------------------------
+constexpr float RINT_MAGIC = 12582912.f;      // 1.5 * 2^23
+
 struct ActQF {
     float mn, delta, inv, levels;
 };
@@ -94,42 +102,46 @@ __device__ __forceinline__ ActQF load_actqf(const float* __restrict__ rmin, cons
     return q;
 }
 
-// un-clamped rounded code X and the (approximate) pre-round value t
-__device__ __forceinline__ float actqf_round(const ActQF& q, float x, float& t) {
-    float d = __fsub_rn(x, q.mn);
-    t = d * q.inv;
-    float X = rintf(t);
-    if (fabsf(t - X) > 0.499f && fabsf(t) < 1024.f) {      // rare: ~2e-3 of elements
-        t = __fdiv_rn(d, q.delta);
-        X = rintf(t);
-    }
-    return X;
+__device__ __forceinline__ float exact_div(float d, float delta, float inv) {
+    const float q = __fmul_rn(d, inv);
+    const float r = __fmaf_rn(-q, delta, d);
+    return __fmaf_rn(r, inv, q);
 }
 
-__device__ __forceinline__ float actqf_code(const ActQF& q, float x) {
-    float t;
-    float X = actqf_round(q, x, t);
-    return fminf(fmaxf(X, 0.f), q.levels);
+// t = (x - min) / delta, bit-identical to actq_t()
+__device__ __forceinline__ float actqf_t(const ActQF& q, float x) { return exact_div(__fsub_rn(x, q.mn), q.delta, q.inv); }
+
+// clamp(t) + MAGIC: low mantissa bits hold the integer code
+__device__ __forceinline__ float actqf_biased(const ActQF& q, float t) {
+    return __fadd_rn(fminf(fmaxf(t, 0.f), q.levels), RINT_MAGIC);
 }
+__device__ __forceinline__ unsigned actqf_index(float biased) { return __float_as_uint(biased) & 0xFFFFu; }
+__device__ __forceinline__ float actqf_unbias(float biased) { return __fsub_rn(biased, RINT_MAGIC); }
+
+__device__ __forceinline__ float actqf_code(const ActQF& q, float x) { return actqf_unbias(actqf_biased(q, actqf_t(q, x))); }
+__device__ __forceinline__ bool actqf_inside(const ActQF& q, float t) { return t >= -0.5f && t < q.levels + 0.5f; }
 
 __device__ __forceinline__ float actqf_decode(const ActQF& q, float c) { return __fadd_rn(__fmul_rn(q.delta, c), q.mn); }
 __device__ __forceinline__ float actqf_fq(const ActQF& q, float x) { return actqf_decode(q, actqf_code(q, x)); }
 
-// statistics-only variant (never decides a stored code): no boundary check
+// statistics-only variant (never decides a stored code): reciprocal multiply, fused decode
 __device__ __forceinline__ float actqf_fq_approx(const ActQF& q, float x) {
-    float X = rintf((x - q.mn) * q.inv);
-    return fmaf(fminf(fmaxf(X, 0.f), q.levels), q.delta, q.mn);
+    const float t = (x - q.mn) * q.inv;
+    const float c = (fminf(fmaxf(t, 0.f), q.levels) + RINT_MAGIC) - RINT_MAGIC;
+    return fmaf(c, q.delta, q.mn);
 }
 
-// backward through the quantiser: returns g * mask, accumulates sD += g*(clip(X) - m*t), sZ += g*(1-m)
-__device__ __forceinline__ float actqf_bwd(const ActQF& q, float x, float g, float& sD, float& sZ) {
-    float t;
-    float X = actqf_round(q, x, t);
-    bool in = (X >= 0.f) && (X <= q.levels);
-    float c = fminf(fmaxf(X, 0.f), q.levels);
-    sD = fmaf(g, in ? (X - t) : c, sD);
+// backward through the quantiser given t = actqf_t(q, x): returns g * mask, accumulates
+// sD += g*(clip(X) - m*t), sZ += g*(1-m)   (g_max = sD/levels, g_min = sZ - sD/levels)
+__device__ __forceinline__ float actqf_bwd_t(const ActQF& q, float t, float g, float& sD, float& sZ) {
+    const bool in = actqf_inside(q, t);
+    const float c = actqf_unbias(actqf_biased(q, t));
+    sD = fmaf(g, in ? (c - t) : c, sD);
     sZ += in ? 0.f : g;
     return in ? g : 0.f;
+}
+__device__ __forceinline__ float actqf_bwd(const ActQF& q, float x, float g, float& sD, float& sZ) {
+    return actqf_bwd_t(q, actqf_t(q, x), g, sD, sZ);
 }
 
 struct WQ {

@@ -149,6 +149,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
+        // One warp = 32 consecutive frames (TMEM lanes) x 32-column chunks.  Per chunk: issue the TMEM load and ALL
+        // global loads the tail needs (32 independent requests in flight), then compute + store; pointers advance by
+        // one row pitch per column, so a warp store is one coalesced 128 B row segment.
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
         const int h = (warp - 4) >> 2;          // column half
         constexpr int COLS = NT / 2;
@@ -166,6 +169,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (!p.first_block) qadds = load_actqf(p.qadds_min, p.qadds_max, 8);
         }
+        const int64_t ld = p.ld;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -180,63 +184,123 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c0 = 0; c0 < COLS; c0 += 32) {
                 uint32_t v[32];
                 const int col = h * COLS + c0;
+                const int o0 = n_idx * NT + col;            // first output channel of this chunk
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + col), v);
-                tmem_ld_wait();
+                const float* s1c = s1s + o0;
+                const float* s0c = s0s + o0;
+                if (EPI == EPI_STORE) {
+                    tmem_ld_wait();
+                    if (valid) {
+                        const int64_t base = ((int64_t)b * p.N + o0) * ld + m;
+                        float* of = p.out_f32 ? p.out_f32 + base : nullptr;
+                        __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + base : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int o = n_idx * NT + col + j;
-                    const float y = fmaf(__uint_as_float(v[j]), s1s[o], s0s[o]);
-                    const int64_t idx = ((int64_t)b * p.N + o) * p.ld + m;
-                    if (EPI == EPI_STORE) {
-                        if (valid) {
-                            p.out_f32[idx] = y;
-                            if (p.out_bf16) p.out_bf16[idx] = __float2bfloat16_rn(y);
+                        for (int j = 0; j < 32; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            if (of) of[j * ld] = y;
+                            if (ob) ob[j * ld] = __float2bfloat16_rn(y);
                         }
-                    } else if (EPI == EPI_EXPAND) {
-                        if (valid) {
-                            p.out_f32[idx] = y;
-                            float z = prelu(y, slope);
-                            float a = p.quant ? actqf_fq_approx(q1, z) : z;
-                            st_s += a;
-                            st_ss = fmaf(a, a, st_ss);
+                    }
+                } else if (EPI == EPI_BF16) {
+                    tmem_ld_wait();
+                    if (valid) {
+                        __nv_bfloat16* ob = p.out_bf16 + ((int64_t)b * p.N + o0) * ld + m;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) ob[j * ld] = __float2bfloat16_rn(fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]));
+                    }
+                } else if (EPI == EPI_EXPAND) {
+                    tmem_ld_wait();
+                    if (valid) {
+                        float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
+                        if (p.quant) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                of[j * ld] = y;
+                                const float a = actqf_fq_approx(q1, prelu(y, slope));
+                                st_s += a;
+                                st_ss = fmaf(a, a, st_ss);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                of[j * ld] = y;
+                                const float a = prelu(y, slope);
+                                st_s += a;
+                                st_ss = fmaf(a, a, st_ss);
+                            }
                         }
-                    } else if (EPI == EPI_BF16) {
-                        if (valid) p.out_bf16[idx] = __float2bfloat16_rn(y);
-                    } else if (EPI == EPI_ADD) {
-                        if (valid) p.out_f32[idx] = y + __ldg(p.addend + idx);
-                    } else if (EPI == EPI_RELU_MUL) {       // float mask head: relu(conv) * encoder features
-                        if (valid) p.out_f32[idx] = fmaxf(y, 0.f) * __ldg(p.addend + ((int64_t)b * p.mul_C + (o % p.mul_C)) * p.ld + m);
-                    } else if (EPI == EPI_RESSKIP) {
-                        if (valid) {
-                            if (o < p.n_res) {          // residual conv -> FQ -> (x + res) -> FQ
-                                const int64_t i2 = ((int64_t)b * p.n_res + o) * p.ld + m;
-                                if (p.res_y) p.res_y[i2] = y;
-                                float r = p.quant ? actqf_fq(qres, y) : y;
-                                float z = __fadd_rn(__ldg(p.x_in + i2), r);
-                                if (p.quant) {
-                                    float c = actqf_code(qadd, z);
-                                    p.x_out[i2] = actqf_decode(qadd, c);
-                                    p.x_out_op[i2] = __float2bfloat16_rn(c);
-                                } else if (p.split) {
-                                    p.x_out[i2] = z;
-                                    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
-                                    const int64_t ih = ((int64_t)b * 2 * p.n_res + o) * p.ld + m;
-                                    p.x_out_op[ih] = hi;
-                                    p.x_out_op[ih + (int64_t)p.n_res * p.ld] = __float2bfloat16_rn(z - __bfloat162float(hi));
-                                } else {
-                                    p.x_out[i2] = z;
-                                    p.x_out_op[i2] = __float2bfloat16_rn(z);
+                    }
+                } else if (EPI == EPI_ADD || EPI == EPI_RELU_MUL) {
+                    float pre[32];
+                    const int64_t base = ((int64_t)b * p.N + o0) * ld + m;
+                    const float* ap = (EPI == EPI_ADD) ? p.addend + base
+                                                       : p.addend + ((int64_t)b * p.mul_C + (o0 % p.mul_C)) * ld + m;   // mul_C % 32 == 0
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) pre[j] = valid ? __ldg(ap + j * ld) : 0.f;
+                    tmem_ld_wait();
+                    if (valid) {
+                        float* of = p.out_f32 + base;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            of[j * ld] = (EPI == EPI_ADD) ? y + pre[j] : fmaxf(y, 0.f) * pre[j];
+                        }
+                    }
+                } else if (EPI == EPI_RESSKIP) {
+                    const bool is_res = o0 < p.n_res;           // warp-uniform: a chunk never straddles the two convs
+                    const int n_loc = is_res ? p.n_res : p.N - p.n_res;
+                    const int64_t i0 = ((int64_t)b * n_loc + (is_res ? o0 : o0 - p.n_res)) * ld + m;
+                    const float* src = is_res ? p.x_in + i0 : (p.first_block ? nullptr : p.skip_in + i0);
+                    float pre[32];
+                    if (src) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) pre[j] = valid ? __ldg(src + j * ld) : 0.f;
+                    }
+                    tmem_ld_wait();
+                    if (valid) {
+                        if (is_res) {                           // residual conv -> FQ -> (x + res) -> FQ
+                            float* ry = p.res_y ? p.res_y + i0 : nullptr;
+                            float* xo = p.x_out + i0;
+                            if (p.quant) {
+                                __nv_bfloat16* xop = p.x_out_op + i0;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                    if (ry) ry[j * ld] = y;
+                                    const float z = __fadd_rn(pre[j], actqf_fq(qres, y));
+                                    const float c = actqf_code(qadd, z);
+                                    xo[j * ld] = actqf_decode(qadd, c);
+                                    xop[j * ld] = __float2bfloat16_rn(c);
                                 }
-                            } else {                    // skip conv -> FQ -> (skip_sum + skip) -> FQ
-                                const int os = o - p.n_res;
-                                const int64_t i2 = ((int64_t)b * (p.N - p.n_res) + os) * p.ld + m;
-                                if (p.skip_y) p.skip_y[i2] = y;
-                                float sk = p.quant ? actqf_fq(qskip, y) : y;
+                            } else {
+                                __nv_bfloat16* xop = p.x_out_op + (p.split ? ((int64_t)b * 2 * p.n_res + o0) * ld + m : i0);
+                                const int64_t lo_off = (int64_t)p.n_res * ld;
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) {
+                                    const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                    if (ry) ry[j * ld] = y;
+                                    const float z = __fadd_rn(pre[j], y);
+                                    xo[j * ld] = z;
+                                    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
+                                    xop[j * ld] = hi;
+                                    if (p.split) xop[j * ld + lo_off] = __float2bfloat16_rn(z - __bfloat162float(hi));
+                                }
+                            }
+                        } else {                                // skip conv -> FQ -> (skip_sum + skip) -> FQ
+                            float* sy = p.skip_y ? p.skip_y + i0 : nullptr;
+                            float* so = p.skip_out + i0;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                if (sy) sy[j * ld] = y;
+                                const float sk = p.quant ? actqf_fq(qskip, y) : y;
                                 if (p.first_block) {
-                                    p.skip_out[i2] = sk;
+                                    so[j * ld] = sk;
                                 } else {
-                                    float z = __fadd_rn(__ldg(p.skip_in + i2), sk);
-                                    p.skip_out[i2] = p.quant ? actqf_fq(qadds, z) : z;
+                                    const float z = __fadd_rn(pre[j], sk);
+                                    so[j * ld] = p.quant ? actqf_fq(qadds, z) : z;
                                 }
                             }
                         }
@@ -382,7 +446,8 @@ int fqss_pw_gemm_ex(const void* act_bf16, const void* w_bf16, const float* s1, c
     a.out_f32 = out_f32; a.out_bf16 = (__nv_bfloat16*)out_bf16; a.addend = addend;
     int epi = tcg::EPI_STORE;
     if (mul_C > 0) {
-        FQSS_REQUIRE(out_f32 && addend && N % mul_C == 0, -1, "pw_gemm_ex: relu-mul needs an fp32 output, a multiplicand and N %% mul_C == 0");
+        FQSS_REQUIRE(out_f32 && addend && N % mul_C == 0 && mul_C % 32 == 0, -1,
+                     "pw_gemm_ex: relu-mul needs an fp32 output, a multiplicand, N %% mul_C == 0 and mul_C %% 32 == 0");
         a.mul_C = mul_C;
         epi = tcg::EPI_RELU_MUL;
     } else if (addend) {

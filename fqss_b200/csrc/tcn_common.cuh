@@ -1,6 +1,12 @@
 // tcn_common.cuh -- the recompute-on-load chains shared by forward and backward of the fused ConvBlock.
 // The SAME device functions produce the quantised activations in forward and re-derive them in
 // backward, so the STE masks of backward see exactly the codes forward used.
+//
+// Code-indexed tables.  Everything downstream of an 8-bit quantiser is, per (sample, channel) row, a
+// function of the 8-bit code alone: a1 = FQ1(.) takes 256 values, hence so do gLN1(a1), FQ2(gLN1(a1)),
+// the STE mask and range-gradient weight of FQ2, the normalised value xhat ...  Each row CTA therefore
+// tabulates those chains once (256 entries, exact slow-path arithmetic) and the per-element work is
+// "quantise the continuous input, look the rest up" -- one LDS instead of ~15 dependent FP32 ops.
 #pragma once
 #include "fqss_common.cuh"
 
@@ -28,6 +34,8 @@ __device__ __forceinline__ GlnRow load_gln_row(const double* __restrict__ stats,
 }
 
 __device__ __forceinline__ float prelu_f(float y, float a) { return y > 0.f ? y : __fmul_rn(a, y); }
+__device__ __forceinline__ float gln_apply(const GlnRow& g, float a) { return __fadd_rn(__fmul_rn(a, g.scale), g.shift); }
+__device__ __forceinline__ float gln_xhat(const GlnRow& g, float a) { return (a - g.mu) * g.rstd; }
 
 // ---- y1 -> a1 = FQ1(PReLU(y1)) -> n1 = gLN1(a1) -> a2 = FQ2(n1)
 struct Hidden1 {
@@ -52,7 +60,7 @@ __device__ __forceinline__ float hidden1_a1(const Hidden1& h, float y) {
     float z = prelu_f(y, h.slope);
     return h.quant ? actqf_fq(h.q1, z) : z;
 }
-__device__ __forceinline__ float hidden1_n1(const Hidden1& h, float a1) { return __fadd_rn(__fmul_rn(a1, h.g.scale), h.g.shift); }
+__device__ __forceinline__ float hidden1_n1(const Hidden1& h, float a1) { return gln_apply(h.g, a1); }
 __device__ __forceinline__ float hidden1_a2(const Hidden1& h, float y) {
     float n1 = hidden1_n1(h, hidden1_a1(h, y));
     return h.quant ? actqf_fq(h.q2, n1) : n1;
@@ -81,12 +89,66 @@ __device__ __forceinline__ float hidden3_a3(const Hidden3& h, float y) {
     float z = prelu_f(y, h.slope);
     return h.quant ? actqf_fq(h.q3, z) : z;
 }
-__device__ __forceinline__ float hidden3_n3(const Hidden3& h, float a3) { return __fadd_rn(__fmul_rn(a3, h.g.scale), h.g.shift); }
+__device__ __forceinline__ float hidden3_n3(const Hidden3& h, float a3) { return gln_apply(h.g, a3); }
 // GEMM operand of the res/skip conv: the integer code of FQ4 (quant) or the value itself (float model)
 __device__ __forceinline__ float hidden3_op(const Hidden3& h, float y) {
     float n3 = hidden3_n3(h, hidden3_a3(h, y));
     return h.quant ? actqf_code(h.q4, n3) : n3;
 }
+
+// ---------------------------------------------------------------------------------------------
+// code-indexed tables (256 entries; built by the first 256 threads of a row CTA, then __syncthreads)
+// ---------------------------------------------------------------------------------------------
+// index of the table entry for a continuous pre-quantiser value z (w.r.t. quantiser q); also returns t
+__device__ __forceinline__ unsigned code_index(const ActQF& q, float z, float& t, float& biased) {
+    t = actqf_t(q, z);
+    biased = actqf_biased(q, t);
+    return actqf_index(biased);
+}
+__device__ __forceinline__ unsigned code_index(const ActQF& q, float z) {
+    float t, bz;
+    return code_index(q, z, t, bz);
+}
+
+// forward chain after quantiser A (code i): a = decode_A(i); n = gLN(a); value of FQ_B(n)
+__device__ __forceinline__ float chain_fq_value(const ActQF& qa, const GlnRow& g, const ActQF& qb, int i) {
+    return actqf_fq(qb, gln_apply(g, actqf_decode(qa, (float)i)));
+}
+__device__ __forceinline__ float chain_fq_code(const ActQF& qa, const GlnRow& g, const ActQF& qb, int i) {
+    return actqf_code(qb, gln_apply(g, actqf_decode(qa, (float)i)));
+}
+// backward view of the same chain: {value or xhat, STE mask of FQ_B (1/0), range weight D_B, xhat of a}
+__device__ __forceinline__ float4 chain_bwd_entry(const ActQF& qa, const GlnRow& g, const ActQF& qb, int i, bool want_value) {
+    const float a = actqf_decode(qa, (float)i);
+    const float n = gln_apply(g, a);
+    const float t = actqf_t(qb, n);
+    const bool in = actqf_inside(qb, t);
+    const float c = actqf_unbias(actqf_biased(qb, t));
+    float4 e;
+    e.x = want_value ? actqf_decode(qb, c) : 0.f;
+    e.y = in ? 1.f : 0.f;
+    e.z = in ? (c - t) : c;
+    e.w = gln_xhat(g, a);
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small vector helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 bf16x4_to_float4(uint2 v) {
+    const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&v.x);
+    const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&v.y);
+    const float2 a = __bfloat1622float2(lo), b = __bfloat1622float2(hi);
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ uint2 float4_to_bf16x4(float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 v;
+    v.x = *reinterpret_cast<uint32_t*>(&lo);
+    v.y = *reinterpret_cast<uint32_t*>(&hi);
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_bf16x4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 
 int tcn_validate_block(const fqss_tcn_block* p, const char* who);
 

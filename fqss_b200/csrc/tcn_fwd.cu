@@ -60,53 +60,108 @@ __global__ void tcn_prep_kernel(const float* __restrict__ W, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: depthwise kernel
+// K2: depthwise kernel.  One CTA per (sample, channel) row.
+//   phase 0  (quantised model) tabulate code1 -> a2 = FQ2(gLN1(decode1(code1)))        256 entries
+//   phase 1  y1 (128-bit loads) -> PReLU -> code1 -> table -> a2 row in shared memory, zero halo of
+//            `dil` frames on both sides (so the taps need no boundary predicates)
+//   phase 2  3-tap dilated FIR from shared memory (128-bit reads) + bias -> y3 (128-bit stores);
+//            gLN statistics of a3 = FQ3(PReLU(y3)) for the next normalisation
+// HBM bytes: read y1 + write y3 = 8 B/element.
 // ---------------------------------------------------------------------------------------------
+template <int DMODE>
+__device__ __forceinline__ void dw_taps(const float* row, int v, int d, float4& L, float4& C, float4& R) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    C = r4[v];
+    if (DMODE == 0) {                    // d % 4 == 0
+        L = r4[v - (d >> 2)];
+        R = r4[v + (d >> 2)];
+    } else if (DMODE == 1) {             // d == 1
+        const float4 a = r4[v - 1], b = r4[v + 1];
+        L = make_float4(a.w, C.x, C.y, C.z);
+        R = make_float4(C.y, C.z, C.w, b.x);
+    } else if (DMODE == 2) {             // d == 2
+        const float4 a = r4[v - 1], b = r4[v + 1];
+        L = make_float4(a.z, a.w, C.x, C.y);
+        R = make_float4(C.z, C.w, b.x, b.y);
+    } else {                             // any other dilation: scalar reads
+        const int m = 4 * v;
+        L = make_float4(row[m - d], row[m + 1 - d], row[m + 2 - d], row[m + 3 - d]);
+        R = make_float4(row[m + d], row[m + 1 + d], row[m + 2 + d], row[m + 3 + d]);
+    }
+}
+
+__host__ __device__ inline int dw_pad(int dil) { return (dil + 3) & ~3; }
+__host__ __device__ inline int dw_mode(int dil) { return (dil & 3) == 0 ? 0 : (dil == 1 ? 1 : (dil == 2 ? 2 : 3)); }
+
+template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_block p) {
-    extern __shared__ float row[];                   // a2[0..M)
+    extern __shared__ __align__(16) float dsm[];     // [dpad | ld | dpad] a2 row with zero halo, then the table
     __shared__ double sh[2 * 32];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const int M = p.M;
-    Hidden1 h = load_hidden1(p, b, c);
+    const int M = p.M, d = p.dil, dpad = dw_pad(d);
+    const int ld = (int)p.ld;
+    float* row = dsm + dpad;
+    float* lut = dsm + ld + 2 * dpad;
+    const Hidden1 h = load_hidden1(p, b, c);
+    for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
+        dsm[i] = 0.f;
+        row[ld + i] = 0.f;
+    }
+    if (QUANT) {
+        if (threadIdx.x < 256) lut[threadIdx.x] = chain_fq_value(h.q1, h.g, h.q2, threadIdx.x);
+        __syncthreads();
+    }
     const float* y1 = p.y1 + r * p.ld;
-    const int nvec = (M + 3) >> 2;
+    const int nvec = ld >> 2;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        float4 y = ldg4_stream(y1 + 4 * v);
+        const float4 y = ldg4_stream(y1 + 4 * v);
         float4 a;
-        a.x = hidden1_a2(h, y.x); a.y = hidden1_a2(h, y.y); a.z = hidden1_a2(h, y.z); a.w = hidden1_a2(h, y.w);
-        *reinterpret_cast<float4*>(row + 4 * v) = a;  // pad columns hold garbage; never read below (index < M)
+        if (QUANT) {
+            a.x = lut[code_index(h.q1, prelu_f(y.x, h.slope))];
+            a.y = lut[code_index(h.q1, prelu_f(y.y, h.slope))];
+            a.z = lut[code_index(h.q1, prelu_f(y.z, h.slope))];
+            a.w = lut[code_index(h.q1, prelu_f(y.w, h.slope))];
+        } else {
+            a.x = gln_apply(h.g, prelu_f(y.x, h.slope));
+            a.y = gln_apply(h.g, prelu_f(y.y, h.slope));
+            a.z = gln_apply(h.g, prelu_f(y.z, h.slope));
+            a.w = gln_apply(h.g, prelu_f(y.w, h.slope));
+        }
+        if (4 * v + 3 >= M) {            // ragged tail / pad columns: the FIR must see zeros there
+            if (4 * v + 0 >= M) a.x = 0.f;
+            if (4 * v + 1 >= M) a.y = 0.f;
+            if (4 * v + 2 >= M) a.z = 0.f;
+            a.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(row + 4 * v) = a;
     }
     __syncthreads();
     const float w0 = __ldg(p.wdw + c * 3), w1 = __ldg(p.wdw + c * 3 + 1), w2 = __ldg(p.wdw + c * 3 + 2);
     const float bias = __ldg(p.bdw + c);
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
-    if (p.quant) q3 = load_actqf(p.q3.rmin, p.q3.rmax, 8);
-    const int d = p.dil;
+    if (QUANT) q3 = load_actqf(p.q3.rmin, p.q3.rmax, 8);
     float* y3 = p.y3 + r * p.ld;
     float s = 0.f, ss = 0.f;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+        float4 L, C, R;
+        dw_taps<DMODE>(row, v, d, L, C, R);
         float o[4];
+        o[0] = fmaf(w2, R.x, fmaf(w1, C.x, fmaf(w0, L.x, 0.f))) + bias;
+        o[1] = fmaf(w2, R.y, fmaf(w1, C.y, fmaf(w0, L.y, 0.f))) + bias;
+        o[2] = fmaf(w2, R.z, fmaf(w1, C.z, fmaf(w0, L.z, 0.f))) + bias;
+        o[3] = fmaf(w2, R.w, fmaf(w1, C.w, fmaf(w0, L.w, 0.f))) + bias;
+        stg4(y3 + 4 * v, make_float4(o[0], o[1], o[2], o[3]));
+        const int nval = M - 4 * v;      // statistics over valid frames only
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int m = 4 * v + k;
-            float acc = 0.f;
-            if (m < M) {
-                const float xl = (m - d >= 0) ? row[m - d] : 0.f;
-                const float xr = (m + d < M) ? row[m + d] : 0.f;
-                acc = fmaf(w0, xl, acc);
-                acc = fmaf(w1, row[m], acc);
-                acc = fmaf(w2, xr, acc);
-                acc += bias;
-                float z = acc > 0.f ? acc : slope3 * acc;
-                float a3 = p.quant ? actqf_fq_approx(q3, z) : z;
-                s += a3;
-                ss = fmaf(a3, a3, ss);
-            }
-            o[k] = acc;
+            const float z = o[k] > 0.f ? o[k] : slope3 * o[k];
+            float a3 = QUANT ? actqf_fq_approx(q3, z) : z;
+            if (k >= nval) a3 = 0.f;
+            s += a3;
+            ss = fmaf(a3, a3, ss);
         }
-        stg4(y3 + 4 * v, make_float4(o[0], o[1], o[2], o[3]));
     }
     double vv[2] = {(double)s, (double)ss};
     block_sum<2>(vv, sh);
@@ -117,35 +172,46 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3a: hidden quantiser  y3 -> a4 operand (bf16 code / value)
+// K3a: hidden quantiser  y3 -> a4 operand (bf16 code / value).  Quantised model: PReLU -> code3 ->
+// table (code3 -> code4 = FQ4-code(gLN2(decode3(code3)))).  6 B/element.
 // ---------------------------------------------------------------------------------------------
+template <bool QUANT>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_tcn_block p) {
+    __shared__ float lut[256];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    Hidden3 h = load_hidden3(p, b, c);
+    const Hidden3 h = load_hidden3(p, b, c);
+    if (QUANT) {
+        if (threadIdx.x < 256) lut[threadIdx.x] = chain_fq_code(h.q3, h.g, h.q4, threadIdx.x);
+        __syncthreads();
+    }
     const float* y3 = p.y3 + r * p.ld;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + r * p.ld;
     const int nvec = (p.M + 3) >> 2;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        float4 y = ldg4_stream(y3 + 4 * v);
-        const float o0 = hidden3_op(h, y.x), o1 = hidden3_op(h, y.y), o2 = hidden3_op(h, y.z), o3 = hidden3_op(h, y.w);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(o0, o1);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(o2, o3);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
-        if (!p.split) {
+        const float4 y = ldg4_stream(y3 + 4 * v);
+        float o0, o1, o2, o3;
+        if (QUANT) {
+            o0 = lut[code_index(h.q3, prelu_f(y.x, h.slope))];
+            o1 = lut[code_index(h.q3, prelu_f(y.y, h.slope))];
+            o2 = lut[code_index(h.q3, prelu_f(y.z, h.slope))];
+            o3 = lut[code_index(h.q3, prelu_f(y.w, h.slope))];
+        } else {
+            o0 = gln_apply(h.g, prelu_f(y.x, h.slope));
+            o1 = gln_apply(h.g, prelu_f(y.y, h.slope));
+            o2 = gln_apply(h.g, prelu_f(y.z, h.slope));
+            o3 = gln_apply(h.g, prelu_f(y.w, h.slope));
+        }
+        const uint2 pk = float4_to_bf16x4(o0, o1, o2, o3);
+        if (QUANT || !p.split) {
             *reinterpret_cast<uint2*>(out + 4 * v) = pk;
         } else {
             // [hi ; lo] pair: sample b owns rows [2*b*Chid, 2*(b+1)*Chid); residual = value - bf16(value)
             __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + ((int64_t)b * 2 * p.Chid + c) * p.ld;
             __nv_bfloat16* ol = oh + (int64_t)p.Chid * p.ld;
             *reinterpret_cast<uint2*>(oh + 4 * v) = pk;
-            __nv_bfloat162 rl = __floats2bfloat162_rn(o0 - __low2float(lo), o1 - __high2float(lo));
-            __nv_bfloat162 rh = __floats2bfloat162_rn(o2 - __low2float(hi), o3 - __high2float(hi));
-            pk.x = *reinterpret_cast<uint32_t*>(&rl);
-            pk.y = *reinterpret_cast<uint32_t*>(&rh);
-            *reinterpret_cast<uint2*>(ol + 4 * v) = pk;
+            const float4 hv = bf16x4_to_float4(pk);
+            *reinterpret_cast<uint2*>(ol + 4 * v) = float4_to_bf16x4(o0 - hv.x, o1 - hv.y, o2 - hv.z, o3 - hv.w);
         }
     }
 }
@@ -196,7 +262,8 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
     FQSS_REQUIRE(p->Cio % 64 == 0 && p->Chid % 128 == 0 && p->Cio % 128 == 0, -1,
                  "%s: fused path needs Cio %% 128 == 0 and Chid %% 128 == 0 (got %d, %d)", who, p->Cio, p->Chid);
     FQSS_REQUIRE(p->ld >= p->M && p->ld % 8 == 0, -2, "%s: ld must be >= M and a multiple of 8", who);
-    FQSS_REQUIRE((size_t)p->ld * sizeof(float) * 3 <= 200 * 1024, -1, "%s: row too long for shared-memory staging (M=%d)", who, p->M);
+    FQSS_REQUIRE(((size_t)p->ld * 2 + 4 * (size_t)((p->dil + 3) & ~3) + 1280) * sizeof(float) + (size_t)p->ld <= 200 * 1024, -1,
+                 "%s: row too long for shared-memory staging (M=%d, dil=%d)", who, p->M, p->dil);
     FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
     FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && p->y3 && p->stats1 && p->stats3 && p->a4_op && p->skip_out, -1,
@@ -260,16 +327,32 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     a.out_f32 = p->y1; a.slope = p->slope1; a.q1_min = p->q1.rmin; a.q1_max = p->q1.rmax; a.stats = p->stats1;
     rc = tcg::run(tcg::EPI_EXPAND, p->x_op, p->Wc1, a, s);
     if (rc) return rc;
-    // K2
-    static bool cfg = false;
-    const size_t smem = (size_t)p->ld * sizeof(float);
-    if (!cfg) {
-        cudaFuncSetAttribute(tcn_dw_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cfg = true;
+    // K2 / K3a
+    {
+        const int dpad = dw_pad(p->dil);
+        const size_t smem = ((size_t)p->ld + 2 * dpad + 256) * sizeof(float);
+        FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_fwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
+        static bool cfg = false;
+        if (!cfg) {
+#define FQSS_DW_ATTR(Q, D) cudaFuncSetAttribute(tcn_dw_fwd_kernel<Q, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+            FQSS_DW_ATTR(true, 0); FQSS_DW_ATTR(true, 1); FQSS_DW_ATTR(true, 2); FQSS_DW_ATTR(true, 3);
+            FQSS_DW_ATTR(false, 0); FQSS_DW_ATTR(false, 1); FQSS_DW_ATTR(false, 2); FQSS_DW_ATTR(false, 3);
+#undef FQSS_DW_ATTR
+            cfg = true;
+        }
+#define FQSS_DW_LAUNCH(Q, D) tcn_dw_fwd_kernel<Q, D><<<rows, ROW_THREADS, smem, s>>>(*p)
+        const int mode = dw_mode(p->dil);
+        if (p->quant) {
+            if (mode == 0) FQSS_DW_LAUNCH(true, 0); else if (mode == 1) FQSS_DW_LAUNCH(true, 1);
+            else if (mode == 2) FQSS_DW_LAUNCH(true, 2); else FQSS_DW_LAUNCH(true, 3);
+            tcn_hidden_fq_kernel<true><<<rows, ROW_THREADS, 0, s>>>(*p);
+        } else {
+            if (mode == 0) FQSS_DW_LAUNCH(false, 0); else if (mode == 1) FQSS_DW_LAUNCH(false, 1);
+            else if (mode == 2) FQSS_DW_LAUNCH(false, 2); else FQSS_DW_LAUNCH(false, 3);
+            tcn_hidden_fq_kernel<false><<<rows, ROW_THREADS, 0, s>>>(*p);
+        }
+#undef FQSS_DW_LAUNCH
     }
-    tcn_dw_fwd_kernel<<<rows, ROW_THREADS, smem, s>>>(*p);
-    // K3a
-    tcn_hidden_fq_kernel<<<rows, ROW_THREADS, 0, s>>>(*p);
     rc = check_launch("tcn_block_fwd(K2/K3a)");
     if (rc) return rc;
     // K3
