@@ -295,6 +295,7 @@ int fqss_conv1x1_fwd(const float* x, int64_t ldx, const float* w, const float* b
     FQSS_REQUIRE(x && w && y && B > 0 && Ci > 0 && Co > 0 && M > 0 && ldx >= M && ldy >= M, -1, "conv1x1_fwd: bad argument");
     GemmArgs g{w, Ci, 0, x, ldx, (int64_t)Ci * ldx, y, ldy, (int64_t)Co * ldy, bias, Co, M, Ci, 0};
     dim3 grid((M + GB - 1) / GB, (Co + GB - 1) / GB, B);
+    FQSS_PROF("conv1x1_fwd(fp32)", stream);
     sgemm_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     return check_launch("conv1x1_fwd");
 }
@@ -304,6 +305,7 @@ int fqss_conv1x1_dgrad(const float* gy, int64_t ldgy, const float* w, float* gx,
     FQSS_REQUIRE(gy && w && gx && B > 0 && Ci > 0 && Co > 0 && M > 0 && ldgy >= M && ldgx >= M, -1, "conv1x1_dgrad: bad argument");
     GemmArgs g{w, Ci, 0, gy, ldgy, (int64_t)Co * ldgy, gx, ldgx, (int64_t)Ci * ldgx, nullptr, Ci, M, Co, 0};
     dim3 grid((M + GB - 1) / GB, (Ci + GB - 1) / GB, B);
+    FQSS_PROF("conv1x1_dgrad(fp32)", stream);
     sgemm_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(g);
     return check_launch("conv1x1_dgrad");
 }
@@ -313,6 +315,7 @@ int fqss_conv1x1_wgrad(const float* gy, int64_t ldgy, const float* x, int64_t ld
     FQSS_REQUIRE(gy && x && gw && B > 0 && Ci > 0 && Co > 0 && M > 0 && ldgy >= M && ldx >= M, -1, "conv1x1_wgrad: bad argument");
     FQSS_REQUIRE(!gbias || (ws && ws_bytes >= (size_t)Co * sizeof(double)), -3, "conv1x1_wgrad: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("conv1x1_wgrad(fp32)", s, gbias ? 3 : 1);
     cudaMemsetAsync(gw, 0, (size_t)Co * Ci * sizeof(float), s);
     const int kchunk = 1024;
     const int nchunk = (M + kchunk - 1) / kchunk;
@@ -332,6 +335,7 @@ int fqss_dwconv_fwd(const float* x, int64_t ldx, const float* w, const float* bi
     FQSS_REQUIRE(x && w && y && B > 0 && C > 0 && M > 0 && K >= 1 && K <= DW_MAXK && (K & 1) && dil >= 1 && ldx >= M && ldy >= M,
                  -1, "dwconv_fwd: bad argument (odd K <= %d)", DW_MAXK);
     dim3 grid(B * C, (M + 255) / 256);
+    FQSS_PROF("dwconv_fwd(layer)", stream);
     dwconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y, ldy, C, M, K, dil);
     return check_launch("dwconv_fwd");
 }
@@ -343,6 +347,7 @@ int fqss_dwconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, 
     size_t need = (size_t)C * (DW_MAXK + 1) * sizeof(double);
     FQSS_REQUIRE(ws && ws_bytes >= need, -3, "dwconv_bwd: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("dwconv_bwd(layer)", s, 2);
     cudaMemsetAsync(ws, 0, need, s);
     dwconv_bwd_kernel<<<B * C, 256, 0, s>>>(gy, ldgy, x, ldx, w, gx, ldgx, C, M, K, dil, (double*)ws);
     dwconv_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>((const double*)ws, gw, gbias, C, K);
@@ -355,6 +360,7 @@ int fqss_sconv_fwd(const float* x, int64_t ldx, const float* w, float* y, int64_
                  "sconv_fwd: bad argument (Cin*K <= %d)", SC_MAXCK);
     const int Mo = (T - K) / stride + 1;
     FQSS_REQUIRE(ldx >= T && ldy >= Mo, -1, "sconv_fwd: bad pitch");
+    FQSS_PROF("sconv_fwd", stream);
     if (edge_geometry_ok(K, stride) && aligned16(y) && edge_analysis_fwd(x, ldx, T, w, y, ldy, B, Cin, Co, Mo, (cudaStream_t)stream) == 0)
         return check_launch("sconv_fwd(tiled)");
     dim3 grid((Mo + 127) / 128, (Co + SC_OT - 1) / SC_OT, B);
@@ -367,6 +373,7 @@ int fqss_sconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     FQSS_REQUIRE(gy && x && w && B > 0 && Cin > 0 && Co > 0 && T >= K && K > 0 && stride > 0, -1, "sconv_bwd: bad argument");
     const int Mo = (T - K) / stride + 1;
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("sconv_bwd", s, (gx ? 1 : 0) + (gw ? 2 : 0));
     if (gx) {
         // gx[b,c,t] = sum_o sum_{m,k} w[o,c,k] gy[b,o,m]: the overlap-add kernel with weight row stride Cin*K
         FQSS_REQUIRE(Cin == 1, -1, "sconv_bwd: input gradient implemented for Cin == 1 (RQB re-encoder)");
@@ -397,6 +404,7 @@ int fqss_tconv_fwd(const float* x, int64_t ldx, const float* w, float* y, int64_
     FQSS_REQUIRE(x && w && y && B > 0 && Ci > 0 && M > 0 && K > 0 && stride > 0 && ldx >= M, -1, "tconv_fwd: bad argument");
     const int T = (M - 1) * stride + K;
     FQSS_REQUIRE(ldy >= T, -1, "tconv_fwd: bad output pitch");
+    FQSS_PROF("tconv_fwd", stream);
     if (edge_geometry_ok(K, stride) && edge_synthesis_fwd(x, ldx, w, (int64_t)K, y, ldy, B, Ci, M, T, (cudaStream_t)stream) == 0)
         return check_launch("tconv_fwd(tiled)");
     dim3 grid((T + 255) / 256, B);
@@ -409,6 +417,7 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     FQSS_REQUIRE(gy && x && w && B > 0 && Ci > 0 && M > 0 && K > 0 && stride > 0 && K <= SC_MAXCK, -1, "tconv_bwd: bad argument");
     const int T = (M - 1) * stride + K;
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("tconv_bwd", s, (gx ? 1 : 0) + (gw ? 2 : 0));
     if (gx) {   // gx[b,c,m] = sum_k w[c,k] gy[b, m*stride+k]  == analysis conv with Cin=1, Co=Ci
         if (!(edge_geometry_ok(K, stride) && aligned16(gx) && edge_analysis_fwd(gy, ldgy, T, w, gx, ldgx, B, 1, Ci, M, s) == 0)) {
             dim3 grid((M + 127) / 128, (Ci + SC_OT - 1) / SC_OT, B);

@@ -388,6 +388,7 @@ int fqss_fq_act_fwd(const float* x, float* y, uint8_t* code, int64_t n, const fl
     if (n == 0) return 0;
     int grid = grid_for((n >> 2) / FQ_UNROLL + 1, FQ_THREADS, 8);
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROF("fq_act_fwd", s);
     if (code)
         fq_act_fwd_kernel<true><<<grid, FQ_THREADS, 0, s>>>(x, y, code, n, rmin, rmax, n_bits);
     else
@@ -403,6 +404,7 @@ int fqss_fq_act_bwd(const float* g, const float* x, float* gx, float* g_rmin, fl
     FQSS_REQUIRE(ws && ws_bytes >= 64, -3, "fq_act_bwd: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
     double* acc = (double*)ws;
+    FQSS_PROFN("fq_act_bwd", s, 2);
     cudaMemsetAsync(acc, 0, 2 * sizeof(double), s);
     if (n > 0) {
         int grid = grid_for((n >> 2) / 2 + 1, FQ_THREADS, 8);
@@ -416,6 +418,7 @@ int fqss_fq_weight_fwd(const float* w, float* wq, int8_t* code, int outer, int c
                        const float* rmax, int n_bits, void* stream) {
     FQSS_REQUIRE(w && (wq || code) && rmin && rmax, -1, "fq_weight_fwd: null pointer");
     FQSS_REQUIRE(outer > 0 && ch > 0 && inner > 0 && n_bits >= 2 && n_bits <= 8, -1, "fq_weight_fwd: bad shape/bits");
+    FQSS_PROF("fq_weight_fwd", stream);
     fq_weight_fwd_kernel<<<ch, 128, 0, (cudaStream_t)stream>>>(w, wq, code, outer, ch, inner, rmin, rmax, n_bits);
     return check_launch("fq_weight_fwd");
 }
@@ -424,6 +427,7 @@ int fqss_fq_weight_bwd(const float* g, const float* w, float* gw, float* g_rmin,
                        int inner, const float* rmin, const float* rmax, int n_bits, void* stream) {
     FQSS_REQUIRE(g && w && rmin && rmax, -1, "fq_weight_bwd: null pointer");
     FQSS_REQUIRE(outer > 0 && ch > 0 && inner > 0 && n_bits >= 2 && n_bits <= 8, -1, "fq_weight_bwd: bad shape/bits");
+    FQSS_PROF("fq_weight_bwd", stream);
     fq_weight_bwd_kernel<<<ch, 128, 0, (cudaStream_t)stream>>>(g, w, gw, g_rmin, g_rmax, outer, ch, inner, rmin, rmax,
                                                                n_bits);
     return check_launch("fq_weight_bwd");
@@ -431,6 +435,7 @@ int fqss_fq_weight_bwd(const float* g, const float* w, float* gw, float* g_rmin,
 
 int fqss_weight_observe(const float* w, int outer, int ch, int inner, float* rmin, float* rmax, void* stream) {
     FQSS_REQUIRE(w && rmin && rmax && outer > 0 && ch > 0 && inner > 0, -1, "weight_observe: bad argument");
+    FQSS_PROF("weight_observe", stream);
     weight_observe_kernel<<<ch, 128, 0, (cudaStream_t)stream>>>(w, outer, ch, inner, rmin, rmax);
     return check_launch("weight_observe");
 }
@@ -441,6 +446,7 @@ static int minmax_common(const float* x, int64_t rows, int64_t cols, int64_t ld,
     int grid = grid_for(rows * cols, 256, 4);
     FQSS_REQUIRE(ws && ws_bytes >= (size_t)grid * 2 * sizeof(float), -3, "%s: workspace too small", who);
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN(who, s, 2);
     minmax_partial_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ld, (float*)ws, mode);
     minmax_final_kernel<<<1, 32, 0, s>>>((const float*)ws, grid, rmin, rmax, (float)alpha, (float)(1.0 - alpha), mode);
     return check_launch(who);
@@ -460,6 +466,7 @@ int fqss_absmax(const float* x, int64_t rows, int64_t cols, int64_t ld, float* p
 int fqss_split(const float* x, int64_t ldx, const float* peak, float* y, int64_t ldy, int B, int T, int n_split,
                int n_bits, void* stream) {
     FQSS_REQUIRE(x && peak && y && B > 0 && T > 0 && n_split >= 1 && ldx >= T && ldy >= T, -1, "split: bad argument");
+    FQSS_PROF("split", stream);
     split_kernel<<<grid_for((int64_t)B * T, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, ldx, peak, y, ldy, B, T, n_split,
                                                                                    n_bits);
     return check_launch("split");
@@ -468,6 +475,7 @@ int fqss_split(const float* x, int64_t ldx, const float* peak, float* y, int64_t
 int fqss_combine(const float* parts, int64_t part_stride, int64_t ld, float* y, int64_t ldy, int64_t rows, int T,
                  int n_comb, int n_bits, void* stream) {
     FQSS_REQUIRE(parts && y && rows > 0 && T > 0 && n_comb >= 1, -1, "combine: bad argument");
+    FQSS_PROF("combine", stream);
     combine_kernel<<<grid_for(rows * T, 256, 8), 256, 0, (cudaStream_t)stream>>>(parts, part_stride, ld, y, ldy, rows, T,
                                                                                  n_comb, n_bits);
     return check_launch("combine");
@@ -477,6 +485,7 @@ int fqss_arena_sumsq(const float* g, int64_t n, float* sumsq, void* ws, size_t w
     FQSS_REQUIRE(g && sumsq && n >= 0 && aligned16(g), -1, "arena_sumsq: bad argument");
     FQSS_REQUIRE(ws && ws_bytes >= 8, -3, "arena_sumsq: workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("arena_sumsq", s, 2);
     cudaMemsetAsync(ws, 0, sizeof(double), s);
     if (n > 0) sumsq_kernel<<<grid_for(n >> 2, 256, 4), 256, 0, s>>>(g, n, (double*)ws);
     f64_to_f32_kernel<<<1, 32, 0, s>>>((const double*)ws, sumsq, 1);
@@ -486,6 +495,7 @@ int fqss_arena_sumsq(const float* g, int64_t n, float* sumsq, void* ws, size_t w
 int fqss_arena_scale_clip(float* g, int64_t n, const float* sumsq, float pre_scale, float max_norm, void* stream) {
     FQSS_REQUIRE(g && sumsq && n >= 0, -1, "arena_scale_clip: bad argument");
     if (n == 0) return 0;
+    FQSS_PROF("arena_scale_clip", stream);
     scale_clip_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(g, n, sumsq, pre_scale, max_norm);
     return check_launch("arena_scale_clip");
 }
@@ -496,6 +506,7 @@ int fqss_arena_adam(float* p, const float* g, float* m, float* v, int64_t n, flo
     if (n == 0) return 0;
     float bc1 = 1.f - powf(beta1, (float)step);
     float bc2s = sqrtf(1.f - powf(beta2, (float)step));
+    FQSS_PROF("arena_adam", stream);
     adam_kernel<<<grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2s);
     return check_launch("arena_adam");
 }

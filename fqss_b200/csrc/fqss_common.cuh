@@ -27,6 +27,25 @@ int check_launch(const char* what);
         }                                      \
     } while (0)
 
+// Launch accounting + optional CUDA-event timing on the launching stream (prof.cu).  Every kernel
+// launch site sits inside one: FQSS_PROF("kernel_class", stream) or FQSS_PROFN(name, stream, n_kernels).
+class ProfScope {
+public:
+    ProfScope(const char* name, cudaStream_t s, int nkernels = 1);
+    ~ProfScope();
+    ProfScope(const ProfScope&) = delete;
+    ProfScope& operator=(const ProfScope&) = delete;
+
+private:
+    cudaStream_t stream_;
+    void* e1_;
+    int slot_;
+};
+#define FQSS_PROF_CAT2(a, b) a##b
+#define FQSS_PROF_CAT(a, b) FQSS_PROF_CAT2(a, b)
+#define FQSS_PROF(name, stream) ::fqss::ProfScope FQSS_PROF_CAT(fqss_prof_, __LINE__)(name, (cudaStream_t)(stream))
+#define FQSS_PROFN(name, stream, n) ::fqss::ProfScope FQSS_PROF_CAT(fqss_prof_, __LINE__)(name, (cudaStream_t)(stream), (n))
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // ---------------------------------------------------------------------------------------------

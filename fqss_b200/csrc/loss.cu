@@ -242,6 +242,7 @@ extern "C" int fqss_kd_loss(const float* est, int64_t lde, const float* fest, in
     cudaStream_t s = (cudaStream_t)stream;
     double* st = (double*)ws;
     float* coef = (float*)((char*)ws + st_bytes);
+    FQSS_PROFN("kd_loss", s, gest ? 4 : 3);
     cudaMemsetAsync(st, 0, st_bytes, s);
     dim3 grid((T + LS_CHUNK - 1) / LS_CHUNK, B);
     loss_mean_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, st);

@@ -383,6 +383,8 @@ int fqss_pw_fwd(const fqss_pw_desc* dp, void* stream) {
     const fqss_pw_desc& d = *dp;
     cudaStream_t s = (cudaStream_t)stream;
     dim3 grid((unsigned)d.rows, (unsigned)((d.cols + PW_CHUNK - 1) / PW_CHUNK));
+    static const char* const names[] = {"pw_fwd(ident)", "pw_fwd(prelu)", "pw_fwd(relu)", "pw_fwd(add)", "pw_fwd(sub)", "pw_fwd(mul)", "pw_fwd(gln)"};
+    FQSS_PROF(names[d.kind], s);
     switch (d.kind) {
         case FQSS_PW_IDENT: launch_fwd<FQSS_PW_IDENT>(d, grid, s); break;
         case FQSS_PW_PRELU: launch_fwd<FQSS_PW_PRELU>(d, grid, s); break;
@@ -408,6 +410,8 @@ int fqss_pw_bwd(const fqss_pw_desc* dp, const fqss_pw_grads* op, void* ws, size_
     double* acc = (double*)ws;
     double* rowacc = acc + 8;
     double* samp = rowacc + 2 * d.rows;
+    static const char* const names[] = {"pw_bwd(ident)", "pw_bwd(prelu)", "pw_bwd(relu)", "pw_bwd(add)", "pw_bwd(sub)", "pw_bwd(mul)", "pw_bwd(gln)"};
+    FQSS_PROFN(names[d.kind], s, d.kind == FQSS_PW_GLN ? 4 : 2);
     cudaMemsetAsync(ws, 0, need, s);
     bool vec = aligned16(d.x1) && aligned16(o.g) && d.ld1 % 4 == 0 && o.ldg % 4 == 0;
     if (o.gx1) vec = vec && aligned16(o.gx1) && o.ldg1 % 4 == 0;
@@ -443,6 +447,7 @@ int fqss_pw_bwd(const fqss_pw_desc* dp, const fqss_pw_grads* op, void* ws, size_
 int fqss_gln_stats(const float* x, int64_t rows, int64_t cols, int64_t ld, int C, double* stats, void* stream) {
     FQSS_REQUIRE(x && stats && rows > 0 && cols > 0 && ld >= cols && C > 0 && rows % C == 0, -1, "gln_stats: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROF("gln_stats", s);
     cudaMemsetAsync(stats, 0, (size_t)(rows / C) * 2 * sizeof(double), s);
     dim3 grid((unsigned)rows, (unsigned)((cols + PW_CHUNK - 1) / PW_CHUNK));
     if (aligned16(x) && ld % 4 == 0) gln_stats_kernel<true><<<grid, PW_THREADS, 0, s>>>(x, cols, ld, C, stats);

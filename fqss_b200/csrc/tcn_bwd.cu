@@ -390,9 +390,9 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     const int rows_h = p->B * p->Chid, rows_io = p->B * p->Cio;
 
     cudaMemsetAsync(acc, 0, (size_t)L.total * sizeof(double), s);
-    fill_consts_kernel<<<4, 256, 0, s>>>(ones, zeros, 1024);
+    { FQSS_PROF("tcn_bwd_misc", s); fill_consts_kernel<<<4, 256, 0, s>>>(ones, zeros, 1024); }
     // T
-    tcn_tail_bwd_kernel<<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    { FQSS_PROF("tcn_tail_bwd", s); tcn_tail_bwd_kernel<<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc); }
     rc = check_launch("tcn_block_bwd(tail)");
     if (rc) return rc;
     // G: g_a4 = Wc2T-GEMM(dY2)   (K = n2, N = Chid) -> bf16
@@ -407,20 +407,20 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
                   p->quant ? p->q4.rmax : nullptr, p->dws2, acc + L.db2, g->dW2q, s);
     if (rc) return rc;
     // P1, R, P2
-    tcn_gln2_bwd_kernel<1><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
-    tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
-                                                                     acc + L.samp2);
-    tcn_gln2_bwd_kernel<2><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    { FQSS_PROF("tcn_gln2_bwd<1>", s); tcn_gln2_bwd_kernel<1><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
+    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
+                                                                     acc + L.samp2); }
+    { FQSS_PROF("tcn_gln2_bwd<2>", s); tcn_gln2_bwd_kernel<2><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
     // D, R, Q
     static bool cfg = false;
     if (!cfg) {
         cudaFuncSetAttribute(tcn_dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         cfg = true;
     }
-    tcn_dw_bwd_kernel<<<rows_h, ROW_THREADS, (size_t)3 * p->ld * sizeof(float), s>>>(*p, *g, acc);
-    tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
-                                                                     acc + L.samp1);
-    tcn_gln1_bwd_kernel<<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    { FQSS_PROF("tcn_dw_bwd", s); tcn_dw_bwd_kernel<<<rows_h, ROW_THREADS, (size_t)3 * p->ld * sizeof(float), s>>>(*p, *g, acc); }
+    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
+                                                                     acc + L.samp1); }
+    { FQSS_PROF("tcn_gln1_bwd", s); tcn_gln1_bwd_kernel<<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
     rc = check_launch("tcn_block_bwd(hidden)");
     if (rc) return rc;
     // G: g_x_in = Wc1T-GEMM(dY1) (+ g_xd)   (K = Chid, N = Cio) -> fp32
@@ -437,7 +437,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (rc) return rc;
     // F
     const int nf = p->Chid > n2 ? p->Chid : n2;
-    tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc);
+    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc); }
     return check_launch("tcn_block_bwd(finalize)");
 }
 

@@ -294,6 +294,7 @@ int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const fl
     FQSS_REQUIRE(WcT || split, -1, "tcn_prep: WcT may be NULL only for split (inference) operands");
     FQSS_REQUIRE(!split || (wmin == nullptr && amin == nullptr), -1, "tcn_prep: split operands are for the float model");
     FQSS_REQUIRE((wmin == nullptr) == (wmax == nullptr) && (amin == nullptr) == (amax == nullptr), -1, "tcn_prep: ranges come in pairs");
+    FQSS_PROF("tcn_prep", stream);
     tcn_prep_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(W, wmin, wmax, bias, amin, amax, (__nv_bfloat16*)Wc, (__nv_bfloat16*)WcT, s1,
                                                          s0, dws, K, Ntot, n_off, split);
     return check_launch("tcn_prep");
@@ -302,6 +303,7 @@ int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const fl
 int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int M, const float* rmin,
                     const float* rmax, void* stream) {
     FQSS_REQUIRE(x && out_bf16 && rows > 0 && M > 0 && ldx >= M && ldo >= M, -1, "tcn_encode: bad argument");
+    FQSS_PROF("tcn_encode", stream);
     tcn_encode_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)out_bf16, ldo, M, rmin, rmax);
     return check_launch("tcn_encode");
 }
@@ -309,6 +311,7 @@ int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, in
 int fqss_split_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int cols, int C, int layout, void* stream) {
     FQSS_REQUIRE(x && out_bf16 && rows > 0 && cols > 0 && ldx >= cols && (layout == 0 || (layout == 1 && C > 0 && rows % C == 0 && ldo >= cols)),
                  -1, "split_bf16: bad argument");
+    FQSS_PROF("split_bf16", stream);
     split_bf16_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)out_bf16, ldo, cols, C, layout);
     return check_launch("split_bf16");
 }
@@ -340,16 +343,16 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
 #undef FQSS_DW_ATTR
             cfg = true;
         }
-#define FQSS_DW_LAUNCH(Q, D) tcn_dw_fwd_kernel<Q, D><<<rows, ROW_THREADS, smem, s>>>(*p)
+#define FQSS_DW_LAUNCH(Q, D) do { FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s); tcn_dw_fwd_kernel<Q, D><<<rows, ROW_THREADS, smem, s>>>(*p); } while (0)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DW_LAUNCH(true, 0); else if (mode == 1) FQSS_DW_LAUNCH(true, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(true, 2); else FQSS_DW_LAUNCH(true, 3);
-            tcn_hidden_fq_kernel<true><<<rows, ROW_THREADS, 0, s>>>(*p);
+            { FQSS_PROF("tcn_hidden_fq", s); tcn_hidden_fq_kernel<true><<<rows, ROW_THREADS, 0, s>>>(*p); }
         } else {
             if (mode == 0) FQSS_DW_LAUNCH(false, 0); else if (mode == 1) FQSS_DW_LAUNCH(false, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(false, 2); else FQSS_DW_LAUNCH(false, 3);
-            tcn_hidden_fq_kernel<false><<<rows, ROW_THREADS, 0, s>>>(*p);
+            { FQSS_PROF("tcn_hidden_fq(float)", s); tcn_hidden_fq_kernel<false><<<rows, ROW_THREADS, 0, s>>>(*p); }
         }
 #undef FQSS_DW_LAUNCH
     }

@@ -219,6 +219,7 @@ static int launch(const CUtensorMap& ty, const CUtensorMap& tx, const KArgs& a, 
         }
         configured = true;
     }
+    FQSS_PROF("wgrad", s);
     wgrad_kernel<MT, NW><<<dim3(a.nsplit, gy), NUM_THREADS, smem, s>>>(ty, tx, a);
     return check_launch("wgrad");
 }
@@ -271,6 +272,7 @@ int run(const void* dY, const void* X, int B, int M, int64_t ld, int O, int I, f
     const int64_t n = (int64_t)O * I;
     int grid = (int)((n + 255) / 256);
     if (grid > num_sms() * 4) grid = num_sms() * 4;
+    FQSS_PROF("wgrad_finalize", s);
     wgrad_finalize_kernel<<<grid, 256, 0, s>>>(part, a.nsplit, O, I, amin, amax, dws, db, dWq);
     return check_launch("wgrad_finalize");
 }
