@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; never a reported number)")
+    ap.add_argument("--breakdown-file", default="", help="write the per-kernel attribution table of one step here")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
                          "numbers printed by such a run are never bench values")
@@ -255,9 +256,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    c0 = N.launch_count
+    from fqss_b200 import roofline as R
+    c0 = R.launch_count()
     ms, t0, t1 = timed(args.steps, False)
-    launches = (N.launch_count - c0)
+    launches = R.launch_count() - c0          # kernels launched by libfqss_sm100 inside the timed region
     ms_e2e, _, t2 = timed(args.steps, True)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     final_loss = float(loss_host.item())
@@ -278,8 +280,11 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss}
     if world == 1 and not args.no_roofline:
         try:
-            from fqss_b200.roofline import dominant_kernel_roofline
-            line["roofline"] = dominant_kernel_roofline(dev, B, ms / args.steps)
+            Mfr = (T - 16) // 8 + 1
+            line["roofline"], line["kernels"] = R.step_roofline(lambda: step(*dev_batches[0]), B, Mfr, ms / args.steps)
+            if args.breakdown_file:
+                with open(args.breakdown_file, "w") as f:
+                    f.write(R.all_kernel_fractions(lambda: step(*dev_batches[0]), B, Mfr) + "\n")
         except Exception as e:      # never lose the bench line over the side measurement
             line["roofline"] = {"error": repr(e)}
     if world == 1 and not args.no_cpu_baseline:

@@ -76,6 +76,11 @@ _SIGS = {
     "fqss_arena_sumsq": (i32, [vp, i64, vp, vp, sz, vp]),
     "fqss_arena_scale_clip": (i32, [vp, i64, vp, f32, f32, vp]),
     "fqss_arena_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
+    "fqss_prof_enable": (i32, [i32]),
+    "fqss_prof_reset": (i32, []),
+    "fqss_prof_nslots": (i32, []),
+    "fqss_prof_read": (i32, [i32, C.c_char_p, i32, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
+    "fqss_launch_count": (i64, []),
 }
 
 EXPORTED = tuple(_SIGS.keys())
@@ -96,7 +101,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 4:
+                if L.fqss_abi_version() != 5:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

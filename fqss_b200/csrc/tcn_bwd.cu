@@ -50,24 +50,42 @@ enum { Q1 = 0, Q2 = 1, Q3 = 2, Q4 = 3, QRES = 4, QSKIP = 5, QADD = 6, QADDS = 7 
 __device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ---------------------------------------------------------------------------------------------
+// Row kernels.  One CTA per (sample, channel) row, every thread handles 4 consecutive frames per trip
+// (128-bit fp32 / 64-bit bf16 accesses), per-row constants and the code-indexed tables are built once
+// per CTA, partial sums are reduced fp32 -> warp -> fp64.  Frames m >= M (row padding up to ld) carry
+// no gradient: inputs are masked on load, outputs there are written as zeros.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = float4_to_bf16x4(a, b, c, d);
+}
+__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float f4_get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+
+// ---------------------------------------------------------------------------------------------
 // T: tail backward over the 128-wide tensors.  grid = B*Cio rows.
 // ---------------------------------------------------------------------------------------------
+struct TailQ {
+    ActQF qres, qskip, qadd, qadds;
+};
+
 __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[10 * 32];
+    __shared__ TailQ tq;
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Cio), o = (int)(r % p.Cio);
     const int M = p.M;
     const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
-    ActQF qres, qskip, qadd, qadds;
-    if (p.quant) {
-        qskip = load_actqf(p.qskip.rmin, p.qskip.rmax, 8);
+    if (p.quant && threadIdx.x == 0) {
+        tq.qskip = load_actqf(p.qskip.rmin, p.qskip.rmax, 8);
         if (p.has_res) {
-            qres = load_actqf(p.qres.rmin, p.qres.rmax, 8);
-            qadd = load_actqf(p.qadd.rmin, p.qadd.rmax, 8);
+            tq.qres = load_actqf(p.qres.rmin, p.qres.rmax, 8);
+            tq.qadd = load_actqf(p.qadd.rmin, p.qadd.rmax, 8);
         }
-        if (!p.first_block) qadds = load_actqf(p.qadds.rmin, p.qadds.rmax, 8);
+        if (!p.first_block) tq.qadds = load_actqf(p.qadds.rmin, p.qadds.rmax, 8);
     }
+    __syncthreads();
+    const ActQF qres = tq.qres, qskip = tq.qskip, qadd = tq.qadd, qadds = tq.qadds;
     const float sc_res = p.has_res ? __ldg(p.dws2 + o) : 0.f;
     const float sc_skip = __ldg(p.dws2 + (p.has_res ? p.Cio : 0) + o);
     __nv_bfloat16* dY = reinterpret_cast<__nv_bfloat16*>(g.dY2);
@@ -76,47 +94,67 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
     float s[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) s[i] = 0.f;      // 0,1 qadd | 2,3 qres | 4,5 qadds | 6,7 qskip | 8 db_res | 9 db_skip
-    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
-        const int64_t i = r * p.ld + m;
+    const int nvec = (int)(p.ld >> 2);
+    const int64_t rb = r * p.ld;
+    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+        const int m0 = 4 * v;
+        const int64_t i = rb + m0;
+        float4 gxo, ry, xin, gso, sy, sin;
+        // issue every load of this trip before the first use
         if (p.has_res) {
-            const float gxo = __ldg(g.g_x_out + i);
-            const float ry = __ldg(p.res_y + i);
-            float gz = gxo, gry;
-            if (p.quant) {
-                const float rq = actqf_fq(qres, ry);
-                const float z = __fadd_rn(__ldg(p.x_in + i), rq);
-                gz = actqf_bwd(qadd, z, gxo, s[0], s[1]);
-                gry = actqf_bwd(qres, ry, gz, s[2], s[3]);
-            } else {
-                gry = gz;
+            gxo = ld_f4(g.g_x_out + i);
+            ry = ldg4_stream(p.res_y + i);
+            if (p.quant) xin = ldg4_stream(p.x_in + i);
+        }
+        gso = ld_f4(g.g_skip_out + i);
+        sy = ldg4_stream(p.skip_y + i);
+        if (p.quant && !p.first_block) sin = ldg4_stream(p.skip_in + i);
+        if (p.has_res) {
+            float gz[4], gr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gk = (m0 + k < M) ? f4_get(gxo, k) : 0.f;
+                if (p.quant) {
+                    const float ryk = f4_get(ry, k);
+                    const float rq = actqf_fq(qres, ryk);
+                    const float z = __fadd_rn(f4_get(xin, k), rq);
+                    gz[k] = actqf_bwd(qadd, z, gk, s[0], s[1]);
+                    gr[k] = actqf_bwd(qres, ryk, gz[k], s[2], s[3]);
+                } else {
+                    gz[k] = gk;
+                    gr[k] = gk;
+                }
+                s[8] += gr[k];
             }
-            g.g_xd[i] = gz;
-            s[8] += gry;
-            dres[m] = __float2bfloat16_rn(gry * sc_res);
+            stg4(g.g_xd + i, make_float4(gz[0], gz[1], gz[2], gz[3]));
+            st_bf16x4(dres + m0, gr[0] * sc_res, gr[1] * sc_res, gr[2] * sc_res, gr[3] * sc_res);
         }
         {
-            const float gso = __ldg(g.g_skip_out + i);
-            const float sy = __ldg(p.skip_y + i);
-            float gz = gso, gsy;
-            if (p.quant) {
-                if (!p.first_block) {
-                    const float sq = actqf_fq(qskip, sy);
-                    const float z = __fadd_rn(__ldg(p.skip_in + i), sq);
-                    gz = actqf_bwd(qadds, z, gso, s[4], s[5]);
+            float gz[4], gs[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float gk = (m0 + k < M) ? f4_get(gso, k) : 0.f;
+                if (p.quant) {
+                    const float syk = f4_get(sy, k);
+                    gz[k] = gk;
+                    if (!p.first_block) {
+                        const float sq = actqf_fq(qskip, syk);
+                        const float z = __fadd_rn(f4_get(sin, k), sq);
+                        gz[k] = actqf_bwd(qadds, z, gk, s[4], s[5]);
+                    }
+                    gs[k] = actqf_bwd(qskip, syk, gz[k], s[6], s[7]);
+                } else {
+                    gz[k] = gk;
+                    gs[k] = gk;
                 }
-                gsy = actqf_bwd(qskip, sy, gz, s[6], s[7]);
-            } else {
-                gsy = gz;
+                s[9] += gs[k];
             }
-            if (!p.first_block) g.g_skip_in[i] = gz;
-            s[9] += gsy;
-            dskip[m] = __float2bfloat16_rn(gsy * sc_skip);
+            if (!p.first_block) stg4(g.g_skip_in + i, make_float4(gz[0], gz[1], gz[2], gz[3]));
+            st_bf16x4(dskip + m0, gs[0] * sc_skip, gs[1] * sc_skip, gs[2] * sc_skip, gs[3] * sc_skip);
         }
     }
     double v[10];
-#pragma unroll
-    for (int i = 0; i < 10; ++i) v[i] = (double)s[i];
-    block_sum<10>(v, sh);
+    block_sum_fd<10>(s, v, sh);
     if (threadIdx.x == 0) {
         if (p.quant) {
             if (p.has_res) {
@@ -133,47 +171,81 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
 
 // ---------------------------------------------------------------------------------------------
 // P1 / P2: gLN2 + FQ4 (+ FQ3 + PReLU3 in P2).  grid = B*Chid rows.  g_a4 in g_hid_a (bf16).
+// Everything downstream of FQ3 is a function of the 8-bit code of a3: tabX = xhat3 | mask4, tabD = D4.
 // ---------------------------------------------------------------------------------------------
 template <int PHASE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
-    __shared__ double sh[5 * 32];
+    __shared__ double sh[4 * 32];
+    __shared__ Hidden3 hs;
+    __shared__ float tabX[256], tabD[256];
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const Hidden3 h = load_hidden3(p, b, c);
+    const Hidden3 h = hidden3_cta(p, b, c, &hs);
+    if (h.quant) {
+        chain_bwd_tables(h.q3, h.g, h.q4, threadIdx.x, tabX, tabD);
+        __syncthreads();
+    }
+    const int M = p.M;
     const float* y3 = p.y3 + r * p.ld;
     const __nv_bfloat16* ga4 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
     __nv_bfloat16* gy3 = reinterpret_cast<__nv_bfloat16*>(g.g_hid_b) + r * p.ld;
-    float S1 = 0.f, S2 = 0.f, invN = 0.f;
+    float A = 0.f, Bc = 0.f, Cc = 0.f;
     if (PHASE == 2) {
-        S1 = (float)acc[L.samp2 + 2 * b];
-        S2 = (float)acc[L.samp2 + 2 * b + 1];
-        invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+        const float invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+        A = h.g.rstd * h.g.gamma;
+        Bc = h.g.rstd * invN * (float)acc[L.samp2 + 2 * b];
+        Cc = h.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1];
     }
-    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // P1: q4 sD,sZ, r1, r2 | P2: q3 sD,sZ, slope3
-    for (int m = threadIdx.x; m < p.M; m += ROW_THREADS) {
-        const float y = __ldg(y3 + m);
-        const float gin = bf2f(ga4[m]);
-        const float a3 = hidden3_a3(h, y);
-        const float n3 = hidden3_n3(h, a3);
-        const float xh = (a3 - h.g.mu) * h.g.rstd;
-        float d0 = 0.f, d1 = 0.f;
-        const float gn = h.quant ? actqf_bwd(h.q4, n3, gin, d0, d1) : gin;
-        if (PHASE == 1) {
-            s[0] += d0; s[1] += d1; s[2] += gn; s[3] = fmaf(gn, xh, s[3]);
-        } else {
-            const float ga3 = h.g.rstd * (h.g.gamma * gn - (S1 + xh * S2) * invN);
-            const float z = prelu_f(y, h.slope);
-            const float gz = h.quant ? actqf_bwd(h.q3, z, ga3, s[0], s[1]) : ga3;
-            const float gy = y > 0.f ? gz : h.slope * gz;
-            s[2] += y > 0.f ? 0.f : y * gz;
-            gy3[m] = __float2bfloat16_rn(gy);
-        }
-    }
-    double v[5];
+    float s[4] = {0.f, 0.f, 0.f, 0.f};   // P1: q4 sD,sZ, r1, r2 | P2: q3 sD,sZ, slope3
+    const int nvec = (int)(p.ld >> 2);
+    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+        const int m0 = 4 * v;
+        const float4 y = ldg4_stream(y3 + m0);
+        const float4 gi = bf16x4_to_float4(ldg_bf16x4(ga4 + m0));
+        float o[4];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = (double)s[i];
-    block_sum<5>(v, sh);
+        for (int k = 0; k < 4; ++k) {
+            const bool valid = m0 + k < M;
+            const float yk = f4_get(y, k);
+            const float gin = valid ? f4_get(gi, k) : 0.f;
+            const float z = prelu_f(yk, h.slope);
+            float xh, gn, t = 0.f, bz = 0.f;
+            if (h.quant) {
+                const unsigned idx = code_index(h.q3, z, t, bz);
+                const float xm = tabX[idx];
+                xh = xm;
+                gn = tab_mask(xm) ? gin : 0.f;
+                if (PHASE == 1) {
+                    s[0] = fmaf(gin, tabD[idx], s[0]);
+                    s[1] += gin - gn;
+                }
+            } else {
+                xh = gln_xhat(h.g, z);
+                gn = gin;
+            }
+            if (PHASE == 1) {
+                s[2] += gn;
+                s[3] = fmaf(gn, xh, s[3]);
+            } else {
+                float ga3 = fmaf(A, gn, -fmaf(xh, Cc, Bc));
+                ga3 = valid ? ga3 : 0.f;
+                float gz = ga3;
+                if (h.quant) {
+                    const bool in = actqf_inside(h.q3, t);
+                    const float c3 = actqf_unbias(bz);
+                    s[0] = fmaf(ga3, in ? (c3 - t) : c3, s[0]);
+                    s[1] += in ? 0.f : ga3;
+                    gz = in ? ga3 : 0.f;
+                }
+                o[k] = yk > 0.f ? gz : h.slope * gz;
+                s[2] += yk > 0.f ? 0.f : yk * gz;
+            }
+        }
+        if (PHASE == 2) st_bf16x4(gy3 + m0, o[0], o[1], o[2], o[3]);
+    }
+    double v[4];
+    block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
         if (PHASE == 1) {
             if (p.quant) { atomicAdd(acc + L.q + 2 * Q4, v[0]); atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]); }
@@ -216,61 +288,115 @@ __global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row; a1, a2 and g_y3 rows in smem.
+// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row.  Shared memory:
+//   a2 row and g_y3 row (fp32, zero halo of dw_pad(d) frames on both sides -> predicate-free taps),
+//   the code1 byte per frame (quantised model) or the xhat1 row (float model), and three 256-entry
+//   tables over code1: a2 = FQ2(gLN1(.)), xhat1 | mask2, D2.
 // ---------------------------------------------------------------------------------------------
+template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
-    extern __shared__ float rows[];
+    extern __shared__ __align__(16) float dsm[];
     __shared__ double sh[8 * 32];
+    __shared__ Hidden1 hs;
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const int M = p.M;
-    float* a1r = rows;
-    float* a2r = rows + p.ld;
-    float* gyr = rows + 2 * p.ld;
-    const Hidden1 h = load_hidden1(p, b, c);
+    const int M = p.M, d = p.dil, dpad = dw_pad(d);
+    const int ld = (int)p.ld;
+    const int rowlen = ld + 2 * dpad;
+    float* a2r = dsm + dpad;
+    float* gyr = dsm + rowlen + dpad;
+    float* tabA = dsm + 2 * rowlen;
+    float* tabX = tabA + 256;
+    float* tabD = tabX + 256;
+    float* aux = tabD + 256;                          // QUANT: ld code bytes; else: ld floats of xhat1
+    uint32_t* idx32 = reinterpret_cast<uint32_t*>(aux);
+    const Hidden1 h = hidden1_cta(p, b, c, &hs);
+    for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
+        dsm[i] = 0.f;
+        a2r[ld + i] = 0.f;
+        dsm[rowlen + i] = 0.f;
+        gyr[ld + i] = 0.f;
+    }
+    if (QUANT) {
+        const float4 e = chain_bwd_entry(h.q1, h.g, h.q2, threadIdx.x, true);
+        tabA[threadIdx.x] = e.x;
+        tabX[threadIdx.x] = __uint_as_float((__float_as_uint(e.w) & ~1u) | (e.y != 0.f ? 1u : 0u));
+        tabD[threadIdx.x] = e.z;
+        __syncthreads();
+    }
     const float* y1 = p.y1 + r * p.ld;
     const __nv_bfloat16* gy3 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld;
-    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
-        const float a1 = hidden1_a1(h, __ldg(y1 + m));
-        const float n1 = hidden1_n1(h, a1);
-        a1r[m] = a1;
-        a2r[m] = h.quant ? actqf_fq(h.q2, n1) : n1;
-        gyr[m] = bf2f(gy3[m]);
+    const int nvec = ld >> 2;
+    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+        const int m0 = 4 * v;
+        const float4 y = ldg4_stream(y1 + m0);
+        const float4 gi = bf16x4_to_float4(ldg_bf16x4(gy3 + m0));
+        float a[4], gg[4];
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool valid = m0 + k < M;
+            const float z = prelu_f(f4_get(y, k), h.slope);
+            if (QUANT) {
+                const unsigned idx = code_index(h.q1, z);
+                packed |= idx << (8 * k);
+                a[k] = valid ? tabA[idx] : 0.f;
+            } else {
+                a[k] = valid ? gln_apply(h.g, z) : 0.f;
+                aux[m0 + k] = gln_xhat(h.g, z);
+            }
+            gg[k] = valid ? f4_get(gi, k) : 0.f;
+        }
+        if (QUANT) idx32[v] = packed;
+        *reinterpret_cast<float4*>(a2r + m0) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(gyr + m0) = make_float4(gg[0], gg[1], gg[2], gg[3]);
     }
     __syncthreads();
     const float w0 = __ldg(p.wdw + c * 3), w1 = __ldg(p.wdw + c * 3 + 1), w2 = __ldg(p.wdw + c * 3 + 2);
-    const int d = p.dil;
     __nv_bfloat16* gn1o = reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld;
     float s[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = 0.f;       // 0,1 q2 | 2,3 row sums | 4,5,6 dW taps | 7 db
-    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
-        const float gl = (m - d >= 0) ? gyr[m - d] : 0.f;
-        const float gr = (m + d < M) ? gyr[m + d] : 0.f;
-        const float g0 = gyr[m];
-        // y3[m'] = sum_k w_k a2[m' + (k-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
-        const float ga2 = fmaf(w0, gr, fmaf(w1, g0, w2 * gl));
-        const float al = (m - d >= 0) ? a2r[m - d] : 0.f;
-        const float ar = (m + d < M) ? a2r[m + d] : 0.f;
-        s[4] = fmaf(g0, al, s[4]);
-        s[5] = fmaf(g0, a2r[m], s[5]);
-        s[6] = fmaf(g0, ar, s[6]);
-        s[7] += g0;
-        const float a1 = a1r[m];
-        const float n1 = hidden1_n1(h, a1);
-        const float gn1 = h.quant ? actqf_bwd(h.q2, n1, ga2, s[0], s[1]) : ga2;
-        const float xh = (a1 - h.g.mu) * h.g.rstd;
-        s[2] += gn1;
-        s[3] = fmaf(gn1, xh, s[3]);
-        gn1o[m] = __float2bfloat16_rn(gn1);
+    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+        const int m0 = 4 * v;
+        float4 gL, gC, gR, aL, aC, aR;
+        dw_taps<DMODE>(gyr, v, d, gL, gC, gR);
+        dw_taps<DMODE>(a2r, v, d, aL, aC, aR);
+        uint32_t packed = 0;
+        if (QUANT) packed = idx32[v];
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float g0 = f4_get(gC, k);
+            // y3[m'] = sum_j w_j a2[m' + (j-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
+            float ga2 = fmaf(w0, f4_get(gR, k), fmaf(w1, g0, w2 * f4_get(gL, k)));
+            ga2 = (m0 + k < M) ? ga2 : 0.f;
+            s[4] = fmaf(g0, f4_get(aL, k), s[4]);
+            s[5] = fmaf(g0, f4_get(aC, k), s[5]);
+            s[6] = fmaf(g0, f4_get(aR, k), s[6]);
+            s[7] += g0;
+            float gn1, xh;
+            if (QUANT) {
+                const unsigned idx = (packed >> (8 * k)) & 255u;
+                xh = tabX[idx];
+                gn1 = tab_mask(xh) ? ga2 : 0.f;
+                s[0] = fmaf(ga2, tabD[idx], s[0]);
+                s[1] += ga2 - gn1;
+            } else {
+                xh = aux[m0 + k];
+                gn1 = ga2;
+            }
+            s[2] += gn1;
+            s[3] = fmaf(gn1, xh, s[3]);
+            o[k] = gn1;
+        }
+        st_bf16x4(gn1o + m0, o[0], o[1], o[2], o[3]);
     }
     double v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (double)s[i];
-    block_sum<8>(v, sh);
+    block_sum_fd<8>(s, v, sh);
     if (threadIdx.x == 0) {
-        if (p.quant) { atomicAdd(acc + L.q + 2 * Q2, v[0]); atomicAdd(acc + L.q + 2 * Q2 + 1, v[1]); }
+        if (QUANT) { atomicAdd(acc + L.q + 2 * Q2, v[0]); atomicAdd(acc + L.q + 2 * Q2 + 1, v[1]); }
         acc[L.row1 + 2 * r] = v[2];
         acc[L.row1 + 2 * r + 1] = v[3];
         atomicAdd(acc + L.dwdw + 3 * c, v[4]);
@@ -285,34 +411,61 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
+    __shared__ Hidden1 hs;
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const Hidden1 h = load_hidden1(p, b, c);
+    const Hidden1 h = hidden1_cta(p, b, c, &hs);
+    const int M = p.M;
     const float* y1 = p.y1 + r * p.ld;
     const __nv_bfloat16* gn1 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
     __nv_bfloat16* dY1 = reinterpret_cast<__nv_bfloat16*>(g.dY1) + r * p.ld;
-    const float S1 = (float)acc[L.samp1 + 2 * b], S2 = (float)acc[L.samp1 + 2 * b + 1];
     const float invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+    const float A = h.g.rstd * h.g.gamma;
+    const float Bc = h.g.rstd * invN * (float)acc[L.samp1 + 2 * b];
+    const float Cc = h.g.rstd * invN * (float)acc[L.samp1 + 2 * b + 1];
+    // xhat1 = (a1 - mu) * rstd with a1 = delta1 * code + min1  ->  one FMA on the code
+    const float xa = h.quant ? h.q1.delta * h.g.rstd : 0.f;
+    const float xb = h.quant ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f;
     const float sc = __ldg(p.dws1 + c);
     float s[4] = {0.f, 0.f, 0.f, 0.f};            // q1 sD,sZ | slope1 | db1
-    for (int m = threadIdx.x; m < p.M; m += ROW_THREADS) {
-        const float y = __ldg(y1 + m);
-        const float z = prelu_f(y, h.slope);
-        const float a1 = h.quant ? actqf_fq(h.q1, z) : z;
-        const float xh = (a1 - h.g.mu) * h.g.rstd;
-        const float gn = bf2f(gn1[m]);
-        const float ga1 = h.g.rstd * (h.g.gamma * gn - (S1 + xh * S2) * invN);
-        const float gz = h.quant ? actqf_bwd(h.q1, z, ga1, s[0], s[1]) : ga1;
-        const float gy = y > 0.f ? gz : h.slope * gz;
-        s[2] += y > 0.f ? 0.f : y * gz;
-        s[3] += gy;
-        dY1[m] = __float2bfloat16_rn(gy * sc);
+    const int nvec = (int)(p.ld >> 2);
+    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+        const int m0 = 4 * v;
+        const float4 y = ldg4_stream(y1 + m0);
+        const float4 gi = bf16x4_to_float4(ldg_bf16x4(gn1 + m0));
+        float o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool valid = m0 + k < M;
+            const float yk = f4_get(y, k);
+            const float gn = valid ? f4_get(gi, k) : 0.f;
+            const float z = prelu_f(yk, h.slope);
+            float gz;
+            if (h.quant) {
+                const float t = actqf_t(h.q1, z);
+                const float c1 = actqf_unbias(actqf_biased(h.q1, t));
+                const float xh = fmaf(c1, xa, xb);
+                float ga1 = fmaf(A, gn, -fmaf(xh, Cc, Bc));
+                ga1 = valid ? ga1 : 0.f;
+                const bool in = actqf_inside(h.q1, t);
+                s[0] = fmaf(ga1, in ? (c1 - t) : c1, s[0]);
+                s[1] += in ? 0.f : ga1;
+                gz = in ? ga1 : 0.f;
+            } else {
+                const float xh = gln_xhat(h.g, z);
+                const float ga1 = fmaf(A, gn, -fmaf(xh, Cc, Bc));
+                gz = valid ? ga1 : 0.f;
+            }
+            const float gy = yk > 0.f ? gz : h.slope * gz;
+            s[2] += yk > 0.f ? 0.f : yk * gz;
+            s[3] += gy;
+            o[k] = gy * sc;
+        }
+        st_bf16x4(dY1 + m0, o[0], o[1], o[2], o[3]);
     }
     double v[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = (double)s[i];
-    block_sum<4>(v, sh);
+    block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
         if (p.quant) { atomicAdd(acc + L.q + 2 * Q1, v[0]); atomicAdd(acc + L.q + 2 * Q1 + 1, v[1]); }
         atomicAdd(acc + L.slope, v[2]);
@@ -412,12 +565,30 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
                                                                      acc + L.samp2); }
     { FQSS_PROF("tcn_gln2_bwd<2>", s); tcn_gln2_bwd_kernel<2><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
     // D, R, Q
-    static bool cfg = false;
-    if (!cfg) {
-        cudaFuncSetAttribute(tcn_dw_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        cfg = true;
+    {
+        const int dpad = dw_pad(p->dil);
+        const size_t smem = ((size_t)2 * (p->ld + 2 * dpad) + 768) * sizeof(float) + (p->quant ? (size_t)p->ld : (size_t)p->ld * sizeof(float));
+        FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
+        static bool cfg = false;
+        if (!cfg) {
+#define FQSS_DWB_ATTR(Q, D) cudaFuncSetAttribute(tcn_dw_bwd_kernel<Q, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+            FQSS_DWB_ATTR(true, 0); FQSS_DWB_ATTR(true, 1); FQSS_DWB_ATTR(true, 2); FQSS_DWB_ATTR(true, 3);
+            FQSS_DWB_ATTR(false, 0); FQSS_DWB_ATTR(false, 1); FQSS_DWB_ATTR(false, 2); FQSS_DWB_ATTR(false, 3);
+#undef FQSS_DWB_ATTR
+            cfg = true;
+        }
+        FQSS_PROF("tcn_dw_bwd", s);
+#define FQSS_DWB_LAUNCH(Q, D) tcn_dw_bwd_kernel<Q, D><<<rows_h, ROW_THREADS, smem, s>>>(*p, *g, acc)
+        const int mode = dw_mode(p->dil);
+        if (p->quant) {
+            if (mode == 0) FQSS_DWB_LAUNCH(true, 0); else if (mode == 1) FQSS_DWB_LAUNCH(true, 1);
+            else if (mode == 2) FQSS_DWB_LAUNCH(true, 2); else FQSS_DWB_LAUNCH(true, 3);
+        } else {
+            if (mode == 0) FQSS_DWB_LAUNCH(false, 0); else if (mode == 1) FQSS_DWB_LAUNCH(false, 1);
+            else if (mode == 2) FQSS_DWB_LAUNCH(false, 2); else FQSS_DWB_LAUNCH(false, 3);
+        }
+#undef FQSS_DWB_LAUNCH
     }
-    { FQSS_PROF("tcn_dw_bwd", s); tcn_dw_bwd_kernel<<<rows_h, ROW_THREADS, (size_t)3 * p->ld * sizeof(float), s>>>(*p, *g, acc); }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
                                                                      acc + L.samp1); }
     { FQSS_PROF("tcn_gln1_bwd", s); tcn_gln1_bwd_kernel<<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }

@@ -132,6 +132,52 @@ __device__ __forceinline__ float4 chain_bwd_entry(const ActQF& qa, const GlnRow&
     return e;
 }
 
+// Per-row constants are computed ONCE per CTA (thread 0: fp64 mean/variance, fp32 divisions of the quantiser
+// steps) and broadcast through shared memory -- with ~16 elements per thread the redundant per-thread
+// evaluation used to cost as many issue slots as the element loop itself.  Contains a __syncthreads().
+__device__ __forceinline__ Hidden1 hidden1_cta(const fqss_tcn_block& p, int b, int c, Hidden1* sh) {
+    if (threadIdx.x == 0) *sh = load_hidden1(p, b, c);
+    __syncthreads();
+    return *sh;
+}
+__device__ __forceinline__ Hidden3 hidden3_cta(const fqss_tcn_block& p, int b, int c, Hidden3* sh) {
+    if (threadIdx.x == 0) *sh = load_hidden3(p, b, c);
+    __syncthreads();
+    return *sh;
+}
+
+// backward tables: tabX[i] = xhat(decode_A(i)) with the STE mask of FQ_B in the mantissa LSB, tabD[i] = range weight
+// D_B (c - t inside, c outside).  One LDS.32 each per element instead of ~20 dependent FP32 ops.
+__device__ __forceinline__ void chain_bwd_tables(const ActQF& qa, const GlnRow& g, const ActQF& qb, int i, float* tabX, float* tabD) {
+    const float4 e = chain_bwd_entry(qa, g, qb, i, false);
+    tabX[i] = __uint_as_float((__float_as_uint(e.w) & ~1u) | (e.y != 0.f ? 1u : 0u));
+    tabD[i] = e.z;
+}
+__device__ __forceinline__ bool tab_mask(float xm) { return (__float_as_uint(xm) & 1u) != 0u; }
+
+// float per-thread partials -> warp sums in fp32 -> cross-warp sums in fp64; result valid in thread 0.
+// `sh` needs NV*32 doubles.
+template <int NV>
+__device__ __forceinline__ void block_sum_fd(const float (&s)[NV], double (&v)[NV], double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    float w[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) w[i] = warp_sum(s[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) sh[i * 32 + wid] = (double)w[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = lane < nw ? sh[i * 32 + lane] : 0.0;
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // small vector helpers
 // ---------------------------------------------------------------------------------------------
@@ -149,6 +195,34 @@ __device__ __forceinline__ uint2 float4_to_bf16x4(float a, float b, float c, flo
     return v;
 }
 __device__ __forceinline__ uint2 ldg_bf16x4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+
+// ---------------------------------------------------------------------------------------------
+// dilated 3-tap reads from a shared-memory row with a zero halo of dw_pad(d) floats on both sides
+// ---------------------------------------------------------------------------------------------
+template <int DMODE>
+__device__ __forceinline__ void dw_taps(const float* row, int v, int d, float4& L, float4& C, float4& R) {
+    const float4* r4 = reinterpret_cast<const float4*>(row);
+    C = r4[v];
+    if (DMODE == 0) {                    // d % 4 == 0
+        L = r4[v - (d >> 2)];
+        R = r4[v + (d >> 2)];
+    } else if (DMODE == 1) {             // d == 1
+        const float4 a = r4[v - 1], b = r4[v + 1];
+        L = make_float4(a.w, C.x, C.y, C.z);
+        R = make_float4(C.y, C.z, C.w, b.x);
+    } else if (DMODE == 2) {             // d == 2
+        const float4 a = r4[v - 1], b = r4[v + 1];
+        L = make_float4(a.z, a.w, C.x, C.y);
+        R = make_float4(C.z, C.w, b.x, b.y);
+    } else {                             // any other dilation: scalar reads
+        const int m = 4 * v;
+        L = make_float4(row[m - d], row[m + 1 - d], row[m + 2 - d], row[m + 3 - d]);
+        R = make_float4(row[m + d], row[m + 1 + d], row[m + 2 + d], row[m + 3 + d]);
+    }
+}
+
+__host__ __device__ inline int dw_pad(int dil) { return (dil + 3) & ~3; }
+__host__ __device__ inline int dw_mode(int dil) { return (dil & 3) == 0 ? 0 : (dil == 1 ? 1 : (dil == 2 ? 2 : 3)); }
 
 int tcn_validate_block(const fqss_tcn_block* p, const char* who);
 

@@ -68,31 +68,6 @@ __global__ void tcn_prep_kernel(const float* __restrict__ W, const float* __rest
 //            gLN statistics of a3 = FQ3(PReLU(y3)) for the next normalisation
 // HBM bytes: read y1 + write y3 = 8 B/element.
 // ---------------------------------------------------------------------------------------------
-template <int DMODE>
-__device__ __forceinline__ void dw_taps(const float* row, int v, int d, float4& L, float4& C, float4& R) {
-    const float4* r4 = reinterpret_cast<const float4*>(row);
-    C = r4[v];
-    if (DMODE == 0) {                    // d % 4 == 0
-        L = r4[v - (d >> 2)];
-        R = r4[v + (d >> 2)];
-    } else if (DMODE == 1) {             // d == 1
-        const float4 a = r4[v - 1], b = r4[v + 1];
-        L = make_float4(a.w, C.x, C.y, C.z);
-        R = make_float4(C.y, C.z, C.w, b.x);
-    } else if (DMODE == 2) {             // d == 2
-        const float4 a = r4[v - 1], b = r4[v + 1];
-        L = make_float4(a.z, a.w, C.x, C.y);
-        R = make_float4(C.z, C.w, b.x, b.y);
-    } else {                             // any other dilation: scalar reads
-        const int m = 4 * v;
-        L = make_float4(row[m - d], row[m + 1 - d], row[m + 2 - d], row[m + 3 - d]);
-        R = make_float4(row[m + d], row[m + 1 + d], row[m + 2 + d], row[m + 3 + d]);
-    }
-}
-
-__host__ __device__ inline int dw_pad(int dil) { return (dil + 3) & ~3; }
-__host__ __device__ inline int dw_mode(int dil) { return (dil & 3) == 0 ? 0 : (dil == 1 ? 1 : (dil == 2 ? 2 : 3)); }
-
 template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_block p) {
     extern __shared__ __align__(16) float dsm[];     // [dpad | ld | dpad] a2 row with zero halo, then the table
@@ -103,7 +78,10 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
     const int ld = (int)p.ld;
     float* row = dsm + dpad;
     float* lut = dsm + ld + 2 * dpad;
-    const Hidden1 h = load_hidden1(p, b, c);
+    __shared__ Hidden1 hs;
+    __shared__ ActQF q3s;
+    if (QUANT && threadIdx.x == 32) q3s = load_actqf(p.q3.rmin, p.q3.rmax, 8);
+    const Hidden1 h = hidden1_cta(p, b, c, &hs);
     for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
         dsm[i] = 0.f;
         row[ld + i] = 0.f;
@@ -141,7 +119,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
     const float bias = __ldg(p.bdw + c);
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
-    if (QUANT) q3 = load_actqf(p.q3.rmin, p.q3.rmax, 8);
+    if (QUANT) q3 = q3s;
     float* y3 = p.y3 + r * p.ld;
     float s = 0.f, ss = 0.f;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
@@ -180,7 +158,8 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_t
     __shared__ float lut[256];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const Hidden3 h = load_hidden3(p, b, c);
+    __shared__ Hidden3 hs;
+    const Hidden3 h = hidden3_cta(p, b, c, &hs);
     if (QUANT) {
         if (threadIdx.x < 256) lut[threadIdx.x] = chain_fq_code(h.q3, h.g, h.q4, threadIdx.x);
         __syncthreads();

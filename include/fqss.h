@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 4
+#define FQSS_ABI_VERSION 5
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -274,6 +274,19 @@ int fqss_arena_scale_clip(float* g, int64_t n, const float* sumsq, float pre_sca
 /* fused Adam step over the flat arena (torch.optim.Adam semantics, weight_decay=0, amsgrad=False) */
 int fqss_arena_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                     float eps, int step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Measurement support (nothing like it in the reference): launch accounting and per-kernel-class
+ * CUDA-event timing on the launching stream, used by bench.py's `roofline` / `gpu_launches`.
+ *   fqss_launch_count: kernels launched by this library in the process so far.
+ *   fqss_prof_enable(1): start bracketing every launch with events; (0): stop and resolve.
+ *   fqss_prof_read: per class name, summed milliseconds, timed scopes and kernels (synchronises the device).
+ * ------------------------------------------------------------------------------------------- */
+int64_t fqss_launch_count(void);
+int fqss_prof_enable(int on);
+int fqss_prof_reset(void);
+int fqss_prof_nslots(void);
+int fqss_prof_read(int slot, char* name, int name_cap, double* total_ms, int64_t* scopes, int64_t* kernels);
 
 #ifdef __cplusplus
 }
