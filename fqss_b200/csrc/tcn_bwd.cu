@@ -176,12 +176,11 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
 template <int PHASE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
-    __shared__ Hidden3 hs;
     __shared__ float tabX[256], tabD[256];
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const Hidden3 h = hidden3_cta(p, b, c, &hs);
+    const Hidden3 h = load_hidden3(p, b, c);
     if (h.quant) {
         chain_bwd_tables(h.q3, h.g, h.q4, threadIdx.x, tabX, tabD);
         __syncthreads();
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
     __nv_bfloat16* gy3 = reinterpret_cast<__nv_bfloat16*>(g.g_hid_b) + r * p.ld;
     float A = 0.f, Bc = 0.f, Cc = 0.f;
     if (PHASE == 2) {
-        const float invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+        const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
         A = h.g.rstd * h.g.gamma;
         Bc = h.g.rstd * invN * (float)acc[L.samp2 + 2 * b];
         Cc = h.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1];
@@ -297,7 +296,6 @@ template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     extern __shared__ __align__(16) float dsm[];
     __shared__ double sh[8 * 32];
-    __shared__ Hidden1 hs;
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
@@ -311,7 +309,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
     float* tabD = tabX + 256;
     float* aux = tabD + 256;                          // QUANT: ld code bytes; else: ld floats of xhat1
     uint32_t* idx32 = reinterpret_cast<uint32_t*>(aux);
-    const Hidden1 h = hidden1_cta(p, b, c, &hs);
+    const Hidden1 h = load_hidden1(p, b, c);
     for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
         dsm[i] = 0.f;
         a2r[ld + i] = 0.f;
@@ -411,16 +409,15 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
-    __shared__ Hidden1 hs;
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const Hidden1 h = hidden1_cta(p, b, c, &hs);
+    const Hidden1 h = load_hidden1(p, b, c);
     const int M = p.M;
     const float* y1 = p.y1 + r * p.ld;
     const __nv_bfloat16* gn1 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
     __nv_bfloat16* dY1 = reinterpret_cast<__nv_bfloat16*>(g.dY1) + r * p.ld;
-    const float invN = (float)(1.0 / ((double)p.Chid * (double)p.M));
+    const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
     const float A = h.g.rstd * h.g.gamma;
     const float Bc = h.g.rstd * invN * (float)acc[L.samp1 + 2 * b];
     const float Cc = h.g.rstd * invN * (float)acc[L.samp1 + 2 * b + 1];

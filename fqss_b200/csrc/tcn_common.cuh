@@ -19,14 +19,24 @@ struct GlnRow {
     float mu, rstd, gamma, scale, shift;
 };
 
-__device__ __forceinline__ GlnRow load_gln_row(const double* __restrict__ stats, int b, double n_elems, const float* __restrict__ gw,
+// Row constants (written once per block by tcn_rowconst_kernel, tcn_fwd.cu): rc[0..3] / rc[4..7] / rc[8..11] = {min,
+// delta, 1/delta, levels} of the quantiser before the gLN / after it / after the next op; rc[12+2b], rc[13+2b] = mean,
+// rstd of sample b.  Loading
+// them costs a handful of uniform LDGs per thread instead of fp64 divisions and a square root.
+constexpr int RC_HDR = 12;
+__device__ __forceinline__ ActQF load_actqf_rc(const float* __restrict__ rc) {
+    ActQF q;
+    q.mn = __ldg(rc);
+    q.delta = __ldg(rc + 1);
+    q.inv = __ldg(rc + 2);
+    q.levels = __ldg(rc + 3);
+    return q;
+}
+__device__ __forceinline__ GlnRow load_gln_row(const float* __restrict__ rc, int b, const float* __restrict__ gw,
                                                const float* __restrict__ gb, int c) {
     GlnRow g;
-    const double mean = stats[2 * b] / n_elems;
-    double var = stats[2 * b + 1] / n_elems - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    g.mu = (float)mean;
-    g.rstd = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+    g.mu = __ldg(rc + RC_HDR + 2 * b);
+    g.rstd = __ldg(rc + RC_HDR + 1 + 2 * b);
     g.gamma = __ldg(gw + c);
     g.scale = __fmul_rn(g.rstd, g.gamma);
     g.shift = __fadd_rn(__fmul_rn(-g.scale, g.mu), __ldg(gb + c));
@@ -50,10 +60,10 @@ __device__ __forceinline__ Hidden1 load_hidden1(const fqss_tcn_block& p, int b, 
     h.quant = p.quant;
     h.slope = __ldg(p.slope1);
     if (p.quant) {
-        h.q1 = load_actqf(p.q1.rmin, p.q1.rmax, 8);
-        h.q2 = load_actqf(p.q2.rmin, p.q2.rmax, 8);
+        h.q1 = load_actqf_rc(p.rc1);
+        h.q2 = load_actqf_rc(p.rc1 + 4);
     }
-    h.g = load_gln_row(p.stats1, b, (double)p.Chid * (double)p.M, p.gn1_w, p.gn1_b, c);
+    h.g = load_gln_row(p.rc1, b, p.gn1_w, p.gn1_b, c);
     return h;
 }
 __device__ __forceinline__ float hidden1_a1(const Hidden1& h, float y) {
@@ -79,10 +89,10 @@ __device__ __forceinline__ Hidden3 load_hidden3(const fqss_tcn_block& p, int b, 
     h.quant = p.quant;
     h.slope = __ldg(p.slope3);
     if (p.quant) {
-        h.q3 = load_actqf(p.q3.rmin, p.q3.rmax, 8);
-        h.q4 = load_actqf(p.q4.rmin, p.q4.rmax, 8);
+        h.q3 = load_actqf_rc(p.rc3);
+        h.q4 = load_actqf_rc(p.rc3 + 4);
     }
-    h.g = load_gln_row(p.stats3, b, (double)p.Chid * (double)p.M, p.gn2_w, p.gn2_b, c);
+    h.g = load_gln_row(p.rc3, b, p.gn2_w, p.gn2_b, c);
     return h;
 }
 __device__ __forceinline__ float hidden3_a3(const Hidden3& h, float y) {
@@ -130,20 +140,6 @@ __device__ __forceinline__ float4 chain_bwd_entry(const ActQF& qa, const GlnRow&
     e.z = in ? (c - t) : c;
     e.w = gln_xhat(g, a);
     return e;
-}
-
-// Per-row constants are computed ONCE per CTA (thread 0: fp64 mean/variance, fp32 divisions of the quantiser
-// steps) and broadcast through shared memory -- with ~16 elements per thread the redundant per-thread
-// evaluation used to cost as many issue slots as the element loop itself.  Contains a __syncthreads().
-__device__ __forceinline__ Hidden1 hidden1_cta(const fqss_tcn_block& p, int b, int c, Hidden1* sh) {
-    if (threadIdx.x == 0) *sh = load_hidden1(p, b, c);
-    __syncthreads();
-    return *sh;
-}
-__device__ __forceinline__ Hidden3 hidden3_cta(const fqss_tcn_block& p, int b, int c, Hidden3* sh) {
-    if (threadIdx.x == 0) *sh = load_hidden3(p, b, c);
-    __syncthreads();
-    return *sh;
 }
 
 // backward tables: tabX[i] = xhat(decode_A(i)) with the STE mask of FQ_B in the mantissa LSB, tabD[i] = range weight

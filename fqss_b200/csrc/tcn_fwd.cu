@@ -60,6 +60,30 @@ __global__ void tcn_prep_kernel(const float* __restrict__ W, const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// Row constants: one warp turns the finished fp64 statistics into {mean, rstd} per sample and the two
+// quantisers around the gLN into {min, delta, 1/delta, levels} (layout: tcn_common.cuh).
+// ---------------------------------------------------------------------------------------------
+__global__ void tcn_rowconst_kernel(const double* __restrict__ stats, int B, double n_elems, const float* qa_min, const float* qa_max,
+                                    const float* qb_min, const float* qb_max, const float* qc_min, const float* qc_max, float* __restrict__ rc) {
+    const int t = threadIdx.x;
+    if (t < 3) {
+        const float* mn = t == 0 ? qa_min : (t == 1 ? qb_min : qc_min);
+        const float* mx = t == 0 ? qa_max : (t == 1 ? qb_max : qc_max);
+        if (mn) {
+            const ActQF q = load_actqf(mn, mx, 8);
+            rc[4 * t] = q.mn; rc[4 * t + 1] = q.delta; rc[4 * t + 2] = q.inv; rc[4 * t + 3] = q.levels;
+        }
+    }
+    for (int b = t; b < B; b += blockDim.x) {
+        const double mean = stats[2 * b] / n_elems;
+        double var = stats[2 * b + 1] / n_elems - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        rc[RC_HDR + 2 * b] = (float)mean;
+        rc[RC_HDR + 1 + 2 * b] = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K2: depthwise kernel.  One CTA per (sample, channel) row.
 //   phase 0  (quantised model) tabulate code1 -> a2 = FQ2(gLN1(decode1(code1)))        256 entries
 //   phase 1  y1 (128-bit loads) -> PReLU -> code1 -> table -> a2 row in shared memory, zero halo of
@@ -78,10 +102,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
     const int ld = (int)p.ld;
     float* row = dsm + dpad;
     float* lut = dsm + ld + 2 * dpad;
-    __shared__ Hidden1 hs;
-    __shared__ ActQF q3s;
-    if (QUANT && threadIdx.x == 32) q3s = load_actqf(p.q3.rmin, p.q3.rmax, 8);
-    const Hidden1 h = hidden1_cta(p, b, c, &hs);
+    const Hidden1 h = load_hidden1(p, b, c);
     for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
         dsm[i] = 0.f;
         row[ld + i] = 0.f;
@@ -119,7 +140,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
     const float bias = __ldg(p.bdw + c);
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
-    if (QUANT) q3 = q3s;
+    if (QUANT) q3 = load_actqf_rc(p.rc1 + 8);
     float* y3 = p.y3 + r * p.ld;
     float s = 0.f, ss = 0.f;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
@@ -158,8 +179,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_t
     __shared__ float lut[256];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    __shared__ Hidden3 hs;
-    const Hidden3 h = hidden3_cta(p, b, c, &hs);
+    const Hidden3 h = load_hidden3(p, b, c);
     if (QUANT) {
         if (threadIdx.x < 256) lut[threadIdx.x] = chain_fq_code(h.q3, h.g, h.q4, threadIdx.x);
         __syncthreads();
@@ -245,7 +265,7 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
                  "%s: row too long for shared-memory staging (M=%d, dil=%d)", who, p->M, p->dil);
     FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
-    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && p->y3 && p->stats1 && p->stats3 && p->a4_op && p->skip_out, -1,
+    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && p->y3 && p->stats1 && p->stats3 && p->a4_op && p->skip_out && p->rc1 && p->rc3, -1,
                  "%s: missing activation buffers", who);
     FQSS_REQUIRE(!p->split || !p->quant, -1, "%s: split operands are a float-model (quant == 0) feature", who);
     if (p->has_res) FQSS_REQUIRE(p->x_out && p->x_out_op, -1, "%s: missing residual buffers", who);
@@ -309,6 +329,11 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     a.out_f32 = p->y1; a.slope = p->slope1; a.q1_min = p->q1.rmin; a.q1_max = p->q1.rmax; a.stats = p->stats1;
     rc = tcg::run(tcg::EPI_EXPAND, p->x_op, p->Wc1, a, s);
     if (rc) return rc;
+    const double n_elems = (double)p->Chid * (double)p->M;
+    {
+        FQSS_PROF("tcn_rowconst", s);
+        tcn_rowconst_kernel<<<1, 64, 0, s>>>(p->stats1, p->B, n_elems, p->q1.rmin, p->q1.rmax, p->q2.rmin, p->q2.rmax, p->q3.rmin, p->q3.rmax, p->rc1);
+    }
     // K2 / K3a
     {
         const int dpad = dw_pad(p->dil);
@@ -323,17 +348,21 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
             cfg = true;
         }
 #define FQSS_DW_LAUNCH(Q, D) do { FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s); tcn_dw_fwd_kernel<Q, D><<<rows, ROW_THREADS, smem, s>>>(*p); } while (0)
+#define FQSS_RC3_LAUNCH() do { FQSS_PROF("tcn_rowconst", s); tcn_rowconst_kernel<<<1, 64, 0, s>>>(p->stats3, p->B, n_elems, p->q3.rmin, p->q3.rmax, p->q4.rmin, p->q4.rmax, nullptr, nullptr, p->rc3); } while (0)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DW_LAUNCH(true, 0); else if (mode == 1) FQSS_DW_LAUNCH(true, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(true, 2); else FQSS_DW_LAUNCH(true, 3);
+            FQSS_RC3_LAUNCH();
             { FQSS_PROF("tcn_hidden_fq", s); tcn_hidden_fq_kernel<true><<<rows, ROW_THREADS, 0, s>>>(*p); }
         } else {
             if (mode == 0) FQSS_DW_LAUNCH(false, 0); else if (mode == 1) FQSS_DW_LAUNCH(false, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(false, 2); else FQSS_DW_LAUNCH(false, 3);
+            FQSS_RC3_LAUNCH();
             { FQSS_PROF("tcn_hidden_fq(float)", s); tcn_hidden_fq_kernel<false><<<rows, ROW_THREADS, 0, s>>>(*p); }
         }
 #undef FQSS_DW_LAUNCH
+#undef FQSS_RC3_LAUNCH
     }
     rc = check_launch("tcn_block_fwd(K2/K3a)");
     if (rc) return rc;

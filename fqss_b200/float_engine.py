@@ -108,6 +108,8 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
     a4 = torch.empty((B, 2 * Chid, ld), dtype=bf, device=dev)
     st1 = torch.empty(2 * B, dtype=torch.float64, device=dev)
     st3 = torch.empty(2 * B, dtype=torch.float64, device=dev)
+    rc1 = torch.empty(12 + 2 * B, device=dev)
+    rc3 = torch.empty(12 + 2 * B, device=dev)
     xs = [x0, torch.empty((B, Cio, ld), device=dev), torch.empty((B, Cio, ld), device=dev)]
     xops = [E.split_bf16_acts(x0[:, :, :M], ld), torch.empty((B, 2 * Cio, ld), dtype=bf, device=dev)]
     skips = [torch.empty((B, Cio, ld), device=dev), torch.empty((B, Cio, ld), device=dev)]
@@ -124,6 +126,7 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
         blk.x_op, blk.x_in = ptr(xops[cur_op]), ptr(xs[cur_x])
         blk.skip_in = ptr(skips[cur_skip]) if cur_skip is not None else None
         blk.y1, blk.stats1, blk.y3, blk.stats3, blk.a4_op = ptr(y1), ptr(st1), ptr(y3), ptr(st3), ptr(a4)
+        blk.rc1, blk.rc3 = ptr(rc1), ptr(rc3)
         nxt_skip = 0 if cur_skip is None else 1 - cur_skip
         blk.skip_out = ptr(skips[nxt_skip])
         if has_res:

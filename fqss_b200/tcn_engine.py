@@ -36,7 +36,7 @@ class TcnBlock(C.Structure):
                 ("qskip", QRange), ("qadd", QRange), ("qadds", QRange),
                 ("x_op", vp), ("x_in", vp), ("skip_in", vp),
                 ("y1", vp), ("stats1", vp), ("y3", vp), ("stats3", vp), ("a4_op", vp),
-                ("res_y", vp), ("skip_y", vp), ("x_out", vp), ("x_out_op", vp), ("skip_out", vp)]
+                ("res_y", vp), ("skip_y", vp), ("x_out", vp), ("x_out_op", vp), ("skip_out", vp), ("rc1", vp), ("rc3", vp)]
 
 
 class TcnBlockGrads(C.Structure):
@@ -217,7 +217,8 @@ def _alloc_acts(B, Cio, Chid, ld, has_res, dev):
     A = dict(y1=torch.empty((B, Chid, ld), device=dev), y3=torch.empty((B, Chid, ld), device=dev),
              stats1=torch.empty(2 * B, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B, dtype=torch.float64, device=dev),
              a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), skip_y=torch.empty((B, Cio, ld), device=dev),
-             skip_out=torch.empty((B, Cio, ld), device=dev))
+             skip_out=torch.empty((B, Cio, ld), device=dev), rc1=torch.empty(12 + 2 * B, device=dev),
+             rc3=torch.empty(12 + 2 * B, device=dev))
     if has_res:
         A.update(res_y=torch.empty((B, Cio, ld), device=dev), x_out=torch.empty((B, Cio, ld), device=dev),
                  x_out_op=torch.empty((B, Cio, ld), dtype=bf, device=dev))
@@ -267,7 +268,7 @@ class FusedTCNFunction(Function):
             blk = TcnBlock()
             _fill_block(blk, t, P, quant, first, has_res, dils[i], B, M, ld, cur_q)
             blk.x_op, blk.x_in, blk.skip_in = ptr(cur_op), ptr(cur_x), ptr(cur_skip) or None
-            for k in ("y1", "stats1", "y3", "stats3", "a4_op", "skip_y", "skip_out"):
+            for k in ("y1", "stats1", "y3", "stats3", "a4_op", "skip_y", "skip_out", "rc1", "rc3"):
                 setattr(blk, k, ptr(A[k]))
             if has_res:
                 blk.res_y, blk.x_out, blk.x_out_op = ptr(A["res_y"]), ptr(A["x_out"]), ptr(A["x_out_op"])

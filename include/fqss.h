@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 5
+#define FQSS_ABI_VERSION 6
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -177,7 +177,8 @@ int fqss_split_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, in
 
 /* ---------------------------------------------------------------------------------------------
  * M1  fused ConvBlock of the TCN (convtasnetq.py:11-42 after quantize_model :270-277), forward and
- *     backward, for the steady state (observers off).  Four forward launches per block:
+ *     backward, for the steady state (observers off).  Four forward launches per block (+ 2 one-warp
+ *     launches that turn the gLN statistics into per-sample constants):
  *       K1 expand GEMM (+bias, PReLU/FQ statistics for the first gLN)          x_op  -> y1, stats1
  *       K2 depthwise kernel (PReLU+FQ, gLN+FQ on load; 3-tap dilated FIR; stats) y1   -> y3, stats3
  *       K3a hidden quantiser (PReLU+FQ, gLN+FQ -> bf16 operand)                  y3   -> a4_op
@@ -206,6 +207,10 @@ typedef struct fqss_tcn_block {
     const void* x_op; const float* x_in; const float* skip_in;
     float* y1; double* stats1; float* y3; double* stats3; void* a4_op;
     float* res_y; float* skip_y; float* x_out; void* x_out_op; float* skip_out;
+    /* row constants written by forward right after the statistics are complete and re-read by backward:
+     * 12 + 2*B floats each = {min, delta, 1/delta, levels} of up to three quantisers, then {mean, rstd} per sample
+     * (rc1: q1, q2, q3 and gLN1 from stats1; rc3: q3, q4 and gLN2 from stats3) */
+    float* rc1; float* rc3;
 } fqss_tcn_block;
 
 /* Weight preparation for one 1x1 conv of the fused path: fake-quantise W [N][K] per output channel
