@@ -163,6 +163,29 @@ __device__ __forceinline__ float actqf_bwd(const ActQF& q, float x, float g, flo
     return actqf_bwd_t(q, actqf_t(q, x), g, sD, sZ);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed-pair variants for the issue-bound row kernels (sm_100 FADD2 / FMUL2 / FFMA2 process two fp32
+// lanes per issue slot; every op below is the same IEEE-rounded fp32 operation as its scalar twin):
+//   actqf_t2   : t = (x - min) / delta for two elements, bit-identical to actqf_t()
+//   code_u8    : clamp(rint(t), 0, 255) as an integer in ONE conversion (cvt.rni.sat.u8.f32, ties to even,
+//                NaN -> 0) -- identical to the fmaxf/fminf/magic-constant sequence for 8-bit quantisers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 exact_div2(float2 d, float delta, float inv) {
+    const float2 q = __fmul2_rn(d, f2s(inv));
+    const float2 r = __ffma2_rn(q, f2s(-delta), d);
+    return __ffma2_rn(r, f2s(inv), q);
+}
+__device__ __forceinline__ float2 actqf_t2(const ActQF& q, float2 x) { return exact_div2(__fadd2_rn(x, f2s(-q.mn)), q.delta, q.inv); }
+__device__ __forceinline__ unsigned code_u8(float t) {
+    unsigned r;
+    asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(t));
+    return r;
+}
+// STE mask of an 8-bit quantiser: inside <=> -0.5 <= t < 255.5 <=> 0 <= t + 0.5 < 256 (the sum is exact wherever it
+// could cross either bound; -0.5 -> +0 is inside, negatives have the sign bit set, NaN is outside): one unsigned compare
+__device__ __forceinline__ bool inside_u8(float t_plus_half) { return __float_as_uint(t_plus_half) < 0x43800000u; }
+
 struct WQ {
     float delta;
     float lo, hi;

@@ -17,6 +17,8 @@
 //
 // The 512-wide gradient tensors travel in bf16 (the "1e-2 bf16 GEMM path"); the residual-stream and
 // skip-sum gradients (128-wide) stay fp32 end to end.
+#include <type_traits>
+
 #include "fqss_common.cuh"
 #include "gemm_tc.cuh"
 #include "tcn_common.cuh"
@@ -173,7 +175,31 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
 // P1 / P2: gLN2 + FQ4 (+ FQ3 + PReLU3 in P2).  grid = B*Chid rows.  g_a4 in g_hid_a (bf16).
 // Everything downstream of FQ3 is a function of the 8-bit code of a3: tabX = xhat3 | mask4, tabD = D4.
 // ---------------------------------------------------------------------------------------------
-template <int PHASE>
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+__device__ __forceinline__ float hsum(float2 v) { return v.x + v.y; }
+// zero the components of a frame quad that lie at or beyond M (only the last quad of a row is affected)
+__device__ __forceinline__ void mask_tail(float2& a01, float2& a23, int nval) {
+    if (nval < 4) {
+        a23.y = 0.f;
+        if (nval < 3) a23.x = 0.f;
+        if (nval < 2) a01.y = 0.f;
+        if (nval < 1) a01.x = 0.f;
+    }
+}
+
+// Row loops run mask-free over the full frame quads (v < M/4); the one ragged quad of a row (M % 4 frames) is
+// handled once, by one thread, through the same body with TAIL = true.  Quads that are entirely padding
+// (ld - M >= 4) are never read or written.
+#define FQSS_ROW_LOOP(body, M)                                                                            \
+    do {                                                                                                  \
+        const int nfull_ = (M) >> 2;                                                                      \
+        for (int v_ = threadIdx.x; v_ < nfull_; v_ += ROW_THREADS) body(v_, std::false_type{});           \
+        if (((M)&3) && (int)threadIdx.x == (nfull_ & (ROW_THREADS - 1))) body(nfull_, std::true_type{});  \
+    } while (0)
+
+template <int PHASE, bool QUANT>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     __shared__ float tabX[256], tabD[256];
@@ -181,77 +207,88 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const Hidden3 h = load_hidden3(p, b, c);
-    if (h.quant) {
+    if (QUANT) {
         chain_bwd_tables(h.q3, h.g, h.q4, threadIdx.x, tabX, tabD);
         __syncthreads();
     }
     const int M = p.M;
-    const float* y3 = p.y3 + r * p.ld;
-    const __nv_bfloat16* ga4 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
-    __nv_bfloat16* gy3 = reinterpret_cast<__nv_bfloat16*>(g.g_hid_b) + r * p.ld;
-    float A = 0.f, Bc = 0.f, Cc = 0.f;
+    const float4* y3 = reinterpret_cast<const float4*>(p.y3 + r * p.ld);
+    const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    uint2* gy3 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.g_hid_b) + r * p.ld);
+    float2 A = f2s(0.f), nBc = f2s(0.f), nCc = f2s(0.f);
     if (PHASE == 2) {
         const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
-        A = h.g.rstd * h.g.gamma;
-        Bc = h.g.rstd * invN * (float)acc[L.samp2 + 2 * b];
-        Cc = h.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1];
+        A = f2s(h.g.rstd * h.g.gamma);
+        nBc = f2s(-h.g.rstd * invN * (float)acc[L.samp2 + 2 * b]);
+        nCc = f2s(-h.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1]);
     }
-    float s[4] = {0.f, 0.f, 0.f, 0.f};   // P1: q4 sD,sZ, r1, r2 | P2: q3 sD,sZ, slope3
-    const int nvec = (int)(p.ld >> 2);
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        const int m0 = 4 * v;
-        const float4 y = ldg4_stream(y3 + m0);
-        const float4 gi = bf16x4_to_float4(ldg_bf16x4(ga4 + m0));
-        float o[4];
+    const float slope = h.slope;
+    // P1: a0 = sum g*D4, a1 = sum g*(1-m4), a2 = sum g*m4, a3 = sum g*m4*xhat     (q4: sD = a0, sZ = a1)
+    // P2: a0 = sum ga3*D3, a1 = sum ga3*(1-m3), a3 = sum min(y,0)*gz              (q3: sD = a0, sZ = a1; slope3)
+    float2 a0 = f2s(0.f), a1 = f2s(0.f), a2 = f2s(0.f), a3 = f2s(0.f);
+    auto body = [&](int v, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const float4 y = __ldg(y3 + v);
+        const float4 gi = bf16x4_to_float4(__ldg(ga4 + v));
+        float2 gg[2] = {lo2(gi), hi2(gi)};
+        if (TAIL) mask_tail(gg[0], gg[1], M - 4 * v);
+        const float2 yy[2] = {lo2(y), hi2(y)};
+        float2 o[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool valid = m0 + k < M;
-            const float yk = f4_get(y, k);
-            const float gin = valid ? f4_get(gi, k) : 0.f;
-            const float z = prelu_f(yk, h.slope);
-            float xh, gn, t = 0.f, bz = 0.f;
-            if (h.quant) {
-                const unsigned idx = code_index(h.q3, z, t, bz);
-                const float xm = tabX[idx];
-                xh = xm;
-                gn = tab_mask(xm) ? gin : 0.f;
-                if (PHASE == 1) {
-                    s[0] = fmaf(gin, tabD[idx], s[0]);
-                    s[1] += gin - gn;
-                }
+        for (int j = 0; j < 2; ++j) {
+            const float2 z = make_float2(prelu_f(yy[j].x, slope), prelu_f(yy[j].y, slope));
+            float2 xh, gn, t = f2s(0.f);
+            unsigned ix = 0, iy = 0;
+            if (QUANT) {
+                t = actqf_t2(h.q3, z);
+                ix = code_u8(t.x);
+                iy = code_u8(t.y);
+                xh = make_float2(tabX[ix], tabX[iy]);
+                gn = make_float2(tab_mask(xh.x) ? gg[j].x : 0.f, tab_mask(xh.y) ? gg[j].y : 0.f);
             } else {
-                xh = gln_xhat(h.g, z);
-                gn = gin;
+                xh = make_float2(gln_xhat(h.g, z.x), gln_xhat(h.g, z.y));
+                gn = gg[j];
             }
             if (PHASE == 1) {
-                s[2] += gn;
-                s[3] = fmaf(gn, xh, s[3]);
-            } else {
-                float ga3 = fmaf(A, gn, -fmaf(xh, Cc, Bc));
-                ga3 = valid ? ga3 : 0.f;
-                float gz = ga3;
-                if (h.quant) {
-                    const bool in = actqf_inside(h.q3, t);
-                    const float c3 = actqf_unbias(bz);
-                    s[0] = fmaf(ga3, in ? (c3 - t) : c3, s[0]);
-                    s[1] += in ? 0.f : ga3;
-                    gz = in ? ga3 : 0.f;
+                if (QUANT) {
+                    a0 = __ffma2_rn(gg[j], make_float2(tabD[ix], tabD[iy]), a0);
+                    a1 = __fadd2_rn(a1, __fadd2_rn(gg[j], neg2(gn)));      // g*(1-m): exactly g or 0, no cancellation
                 }
-                o[k] = yk > 0.f ? gz : h.slope * gz;
-                s[2] += yk > 0.f ? 0.f : yk * gz;
+                a2 = __fadd2_rn(a2, gn);
+                a3 = __ffma2_rn(gn, xh, a3);
+            } else {
+                float2 ga3 = __ffma2_rn(A, gn, __ffma2_rn(xh, nCc, nBc));
+                if (TAIL) {
+                    if (4 * v + 2 * j + 1 >= M) ga3.y = 0.f;
+                    if (4 * v + 2 * j >= M) ga3.x = 0.f;
+                }
+                float2 gz = ga3;
+                if (QUANT) {
+                    const float2 cf = make_float2((float)ix, (float)iy);
+                    const float2 dd = __fadd2_rn(cf, neg2(t));
+                    const float2 th = __fadd2_rn(t, f2s(0.5f));
+                    const bool inx = inside_u8(th.x), iny = inside_u8(th.y);
+                    a0 = __ffma2_rn(ga3, make_float2(inx ? dd.x : cf.x, iny ? dd.y : cf.y), a0);
+                    gz = make_float2(inx ? ga3.x : 0.f, iny ? ga3.y : 0.f);
+                    a1 = __fadd2_rn(a1, __fadd2_rn(ga3, neg2(gz)));
+                }
+                o[j] = __fmul2_rn(gz, make_float2(yy[j].x > 0.f ? 1.f : slope, yy[j].y > 0.f ? 1.f : slope));
+                a3 = __ffma2_rn(make_float2(fminf(yy[j].x, 0.f), fminf(yy[j].y, 0.f)), gz, a3);
             }
         }
-        if (PHASE == 2) st_bf16x4(gy3 + m0, o[0], o[1], o[2], o[3]);
-    }
+        if (PHASE == 2) gy3[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
+    };
+    FQSS_ROW_LOOP(body, M);
+    const float s[4] = {hsum(a0), hsum(a1), PHASE == 1 ? hsum(a2) : hsum(a3), hsum(a3)};
     double v[4];
     block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
         if (PHASE == 1) {
-            if (p.quant) { atomicAdd(acc + L.q + 2 * Q4, v[0]); atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]); }
+            if (QUANT) { atomicAdd(acc + L.q + 2 * Q4, v[0]); atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]); }
             acc[L.row2 + 2 * r] = v[2];
             acc[L.row2 + 2 * r + 1] = v[3];
         } else {
-            if (p.quant) { atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]); }
+            if (QUANT) { atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]); }
             atomicAdd(acc + L.slope + 1, v[2]);
         }
     }
@@ -323,74 +360,88 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
         tabD[threadIdx.x] = e.z;
         __syncthreads();
     }
-    const float* y1 = p.y1 + r * p.ld;
-    const __nv_bfloat16* gy3 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld;
-    const int nvec = ld >> 2;
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        const int m0 = 4 * v;
-        const float4 y = ldg4_stream(y1 + m0);
-        const float4 gi = bf16x4_to_float4(ldg_bf16x4(gy3 + m0));
-        float a[4], gg[4];
-        uint32_t packed = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool valid = m0 + k < M;
-            const float z = prelu_f(f4_get(y, k), h.slope);
-            if (QUANT) {
-                const unsigned idx = code_index(h.q1, z);
-                packed |= idx << (8 * k);
-                a[k] = valid ? tabA[idx] : 0.f;
-            } else {
-                a[k] = valid ? gln_apply(h.g, z) : 0.f;
-                aux[m0 + k] = gln_xhat(h.g, z);
-            }
-            gg[k] = valid ? f4_get(gi, k) : 0.f;
-        }
-        if (QUANT) idx32[v] = packed;
-        *reinterpret_cast<float4*>(a2r + m0) = make_float4(a[0], a[1], a[2], a[3]);
-        *reinterpret_cast<float4*>(gyr + m0) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    const float4* y1 = reinterpret_cast<const float4*>(p.y1 + r * p.ld);
+    const uint2* gy3 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld);
+    const float slope = h.slope;
+    // frames of all-padding quads (ld - M >= 4) are never staged: the taps must still see zeros there
+    for (int i = ((M + 3) & ~3) + threadIdx.x; i < ld; i += ROW_THREADS) {
+        a2r[i] = 0.f;
+        gyr[i] = 0.f;
     }
+    auto stage = [&](int v, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const float4 y = __ldg(y1 + v);
+        const float4 gi = bf16x4_to_float4(__ldg(gy3 + v));
+        float2 g01 = lo2(gi), g23 = hi2(gi);
+        const float2 z01 = make_float2(prelu_f(y.x, slope), prelu_f(y.y, slope));
+        const float2 z23 = make_float2(prelu_f(y.z, slope), prelu_f(y.w, slope));
+        float2 a01, a23;
+        if (QUANT) {
+            const float2 t01 = actqf_t2(h.q1, z01), t23 = actqf_t2(h.q1, z23);
+            const unsigned i0 = code_u8(t01.x), i1 = code_u8(t01.y), i2 = code_u8(t23.x), i3 = code_u8(t23.y);
+            idx32[v] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
+            a01 = make_float2(tabA[i0], tabA[i1]);
+            a23 = make_float2(tabA[i2], tabA[i3]);
+        } else {
+            a01 = make_float2(gln_apply(h.g, z01.x), gln_apply(h.g, z01.y));
+            a23 = make_float2(gln_apply(h.g, z23.x), gln_apply(h.g, z23.y));
+            *reinterpret_cast<float4*>(aux + 4 * v) = make_float4(gln_xhat(h.g, z01.x), gln_xhat(h.g, z01.y), gln_xhat(h.g, z23.x), gln_xhat(h.g, z23.y));
+        }
+        if (TAIL) {
+            mask_tail(a01, a23, M - 4 * v);
+            mask_tail(g01, g23, M - 4 * v);
+        }
+        *reinterpret_cast<float4*>(a2r + 4 * v) = make_float4(a01.x, a01.y, a23.x, a23.y);
+        *reinterpret_cast<float4*>(gyr + 4 * v) = make_float4(g01.x, g01.y, g23.x, g23.y);
+    };
+    FQSS_ROW_LOOP(stage, M);
     __syncthreads();
-    const float w0 = __ldg(p.wdw + c * 3), w1 = __ldg(p.wdw + c * 3 + 1), w2 = __ldg(p.wdw + c * 3 + 2);
-    __nv_bfloat16* gn1o = reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld;
-    float s[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = 0.f;       // 0,1 q2 | 2,3 row sums | 4,5,6 dW taps | 7 db
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        const int m0 = 4 * v;
+    const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
+    uint2* gn1o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    // b0 = sum ga2*D2, b1 = sum ga2*(1-m2), b2 = sum gn1, b3 = sum gn1*xhat1 | taps: d0,d1,d2 = sum g*a2[-d,0,+d], d3 = sum g
+    float2 b0 = f2s(0.f), b1 = f2s(0.f), b2 = f2s(0.f), b3 = f2s(0.f), d0 = f2s(0.f), d1 = f2s(0.f), d2 = f2s(0.f), d3 = f2s(0.f);
+    auto fir = [&](int v, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         float4 gL, gC, gR, aL, aC, aR;
         dw_taps<DMODE>(gyr, v, d, gL, gC, gR);
         dw_taps<DMODE>(a2r, v, d, aL, aC, aR);
         uint32_t packed = 0;
+        float4 xq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (QUANT) packed = idx32[v];
-        float o[4];
+        else xq = *reinterpret_cast<const float4*>(aux + 4 * v);
+        float2 o[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float g0 = f4_get(gC, k);
+        for (int j = 0; j < 2; ++j) {
+            const float2 gc = j ? hi2(gC) : lo2(gC), gl = j ? hi2(gL) : lo2(gL), gr = j ? hi2(gR) : lo2(gR);
             // y3[m'] = sum_j w_j a2[m' + (j-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
-            float ga2 = fmaf(w0, f4_get(gR, k), fmaf(w1, g0, w2 * f4_get(gL, k)));
-            ga2 = (m0 + k < M) ? ga2 : 0.f;
-            s[4] = fmaf(g0, f4_get(aL, k), s[4]);
-            s[5] = fmaf(g0, f4_get(aC, k), s[5]);
-            s[6] = fmaf(g0, f4_get(aR, k), s[6]);
-            s[7] += g0;
-            float gn1, xh;
+            float2 ga2 = __ffma2_rn(w0, gr, __ffma2_rn(w1, gc, __fmul2_rn(w2, gl)));
+            if (TAIL) {
+                if (4 * v + 2 * j + 1 >= M) ga2.y = 0.f;
+                if (4 * v + 2 * j >= M) ga2.x = 0.f;
+            }
+            d0 = __ffma2_rn(gc, j ? hi2(aL) : lo2(aL), d0);
+            d1 = __ffma2_rn(gc, j ? hi2(aC) : lo2(aC), d1);
+            d2 = __ffma2_rn(gc, j ? hi2(aR) : lo2(aR), d2);
+            d3 = __fadd2_rn(d3, gc);
+            float2 gn1, xh;
             if (QUANT) {
-                const unsigned idx = (packed >> (8 * k)) & 255u;
-                xh = tabX[idx];
-                gn1 = tab_mask(xh) ? ga2 : 0.f;
-                s[0] = fmaf(ga2, tabD[idx], s[0]);
-                s[1] += ga2 - gn1;
+                const unsigned ix = (packed >> (16 * j)) & 255u, iy = (packed >> (16 * j + 8)) & 255u;
+                xh = make_float2(tabX[ix], tabX[iy]);
+                gn1 = make_float2(tab_mask(xh.x) ? ga2.x : 0.f, tab_mask(xh.y) ? ga2.y : 0.f);
+                b0 = __ffma2_rn(ga2, make_float2(tabD[ix], tabD[iy]), b0);
+                b1 = __fadd2_rn(b1, __fadd2_rn(ga2, neg2(gn1)));
             } else {
-                xh = aux[m0 + k];
+                xh = j ? hi2(xq) : lo2(xq);
                 gn1 = ga2;
             }
-            s[2] += gn1;
-            s[3] = fmaf(gn1, xh, s[3]);
-            o[k] = gn1;
+            b2 = __fadd2_rn(b2, gn1);
+            b3 = __ffma2_rn(gn1, xh, b3);
+            o[j] = gn1;
         }
-        st_bf16x4(gn1o + m0, o[0], o[1], o[2], o[3]);
-    }
+        gn1o[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
+    };
+    FQSS_ROW_LOOP(fir, M);
+    const float s[8] = {hsum(b0), hsum(b1), hsum(b2), hsum(b3), hsum(d0), hsum(d1), hsum(d2), hsum(d3)};
     double v[8];
     block_sum_fd<8>(s, v, sh);
     if (threadIdx.x == 0) {
@@ -407,6 +458,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
 // ---------------------------------------------------------------------------------------------
 // Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
 // ---------------------------------------------------------------------------------------------
+template <bool QUANT>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     const AccLayout L(p.B, p.Cio, p.Chid);
@@ -414,57 +466,67 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln1_bwd_kernel(const fqss_tc
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const Hidden1 h = load_hidden1(p, b, c);
     const int M = p.M;
-    const float* y1 = p.y1 + r * p.ld;
-    const __nv_bfloat16* gn1 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld;
-    __nv_bfloat16* dY1 = reinterpret_cast<__nv_bfloat16*>(g.dY1) + r * p.ld;
+    const float4* y1 = reinterpret_cast<const float4*>(p.y1 + r * p.ld);
+    const uint2* gn1 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    uint2* dY1 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.dY1) + r * p.ld);
     const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
-    const float A = h.g.rstd * h.g.gamma;
-    const float Bc = h.g.rstd * invN * (float)acc[L.samp1 + 2 * b];
-    const float Cc = h.g.rstd * invN * (float)acc[L.samp1 + 2 * b + 1];
+    const float2 A2 = f2s(h.g.rstd * h.g.gamma);
+    const float2 nBc = f2s(-h.g.rstd * invN * (float)acc[L.samp1 + 2 * b]);
+    const float2 nCc = f2s(-h.g.rstd * invN * (float)acc[L.samp1 + 2 * b + 1]);
     // xhat1 = (a1 - mu) * rstd with a1 = delta1 * code + min1  ->  one FMA on the code
-    const float xa = h.quant ? h.q1.delta * h.g.rstd : 0.f;
-    const float xb = h.quant ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f;
-    const float sc = __ldg(p.dws1 + c);
-    float s[4] = {0.f, 0.f, 0.f, 0.f};            // q1 sD,sZ | slope1 | db1
-    const int nvec = (int)(p.ld >> 2);
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        const int m0 = 4 * v;
-        const float4 y = ldg4_stream(y1 + m0);
-        const float4 gi = bf16x4_to_float4(ldg_bf16x4(gn1 + m0));
-        float o[4];
+    const float2 xa = f2s(QUANT ? h.q1.delta * h.g.rstd : 0.f);
+    const float2 xb = f2s(QUANT ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f);
+    const float2 sc = f2s(__ldg(p.dws1 + c));
+    const float slope = h.slope;
+    // a0 = sum ga1*D1, a1 = sum ga1*(1-m1), a3 = sum min(y,0)*gz, a4 = sum gy
+    float2 a0 = f2s(0.f), a1 = f2s(0.f), a3 = f2s(0.f), a4 = f2s(0.f);
+    auto body = [&](int v, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
+        const float4 y = __ldg(y1 + v);
+        const float4 gi = bf16x4_to_float4(__ldg(gn1 + v));
+        const float2 yy[2] = {lo2(y), hi2(y)};
+        const float2 gg[2] = {lo2(gi), hi2(gi)};
+        float2 o[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const bool valid = m0 + k < M;
-            const float yk = f4_get(y, k);
-            const float gn = valid ? f4_get(gi, k) : 0.f;
-            const float z = prelu_f(yk, h.slope);
-            float gz;
-            if (h.quant) {
-                const float t = actqf_t(h.q1, z);
-                const float c1 = actqf_unbias(actqf_biased(h.q1, t));
-                const float xh = fmaf(c1, xa, xb);
-                float ga1 = fmaf(A, gn, -fmaf(xh, Cc, Bc));
-                ga1 = valid ? ga1 : 0.f;
-                const bool in = actqf_inside(h.q1, t);
-                s[0] = fmaf(ga1, in ? (c1 - t) : c1, s[0]);
-                s[1] += in ? 0.f : ga1;
-                gz = in ? ga1 : 0.f;
+        for (int j = 0; j < 2; ++j) {
+            const float2 z = make_float2(prelu_f(yy[j].x, slope), prelu_f(yy[j].y, slope));
+            float2 gz;
+            if (QUANT) {
+                const float2 t = actqf_t2(h.q1, z);
+                const float2 cf = make_float2((float)code_u8(t.x), (float)code_u8(t.y));
+                const float2 xh = __ffma2_rn(cf, xa, xb);
+                float2 ga1 = __ffma2_rn(A2, gg[j], __ffma2_rn(xh, nCc, nBc));
+                if (TAIL) {
+                    if (4 * v + 2 * j + 1 >= M) ga1.y = 0.f;
+                    if (4 * v + 2 * j >= M) ga1.x = 0.f;
+                }
+                const float2 dd = __fadd2_rn(cf, neg2(t));
+                const float2 th = __fadd2_rn(t, f2s(0.5f));
+                    const bool inx = inside_u8(th.x), iny = inside_u8(th.y);
+                a0 = __ffma2_rn(ga1, make_float2(inx ? dd.x : cf.x, iny ? dd.y : cf.y), a0);
+                gz = make_float2(inx ? ga1.x : 0.f, iny ? ga1.y : 0.f);
+                a1 = __fadd2_rn(a1, __fadd2_rn(ga1, neg2(gz)));
             } else {
-                const float xh = gln_xhat(h.g, z);
-                const float ga1 = fmaf(A, gn, -fmaf(xh, Cc, Bc));
-                gz = valid ? ga1 : 0.f;
+                const float2 xh = make_float2(gln_xhat(h.g, z.x), gln_xhat(h.g, z.y));
+                gz = __ffma2_rn(A2, gg[j], __ffma2_rn(xh, nCc, nBc));
+                if (TAIL) {
+                    if (4 * v + 2 * j + 1 >= M) gz.y = 0.f;
+                    if (4 * v + 2 * j >= M) gz.x = 0.f;
+                }
             }
-            const float gy = yk > 0.f ? gz : h.slope * gz;
-            s[2] += yk > 0.f ? 0.f : yk * gz;
-            s[3] += gy;
-            o[k] = gy * sc;
+            const float2 gy = __fmul2_rn(gz, make_float2(yy[j].x > 0.f ? 1.f : slope, yy[j].y > 0.f ? 1.f : slope));
+            a3 = __ffma2_rn(make_float2(fminf(yy[j].x, 0.f), fminf(yy[j].y, 0.f)), gz, a3);
+            a4 = __fadd2_rn(a4, gy);
+            o[j] = __fmul2_rn(gy, sc);
         }
-        st_bf16x4(dY1 + m0, o[0], o[1], o[2], o[3]);
-    }
+        dY1[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
+    };
+    FQSS_ROW_LOOP(body, M);
+    const float s[4] = {hsum(a0), hsum(a1), hsum(a3), hsum(a4)};
     double v[4];
     block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
-        if (p.quant) { atomicAdd(acc + L.q + 2 * Q1, v[0]); atomicAdd(acc + L.q + 2 * Q1 + 1, v[1]); }
+        if (QUANT) { atomicAdd(acc + L.q + 2 * Q1, v[0]); atomicAdd(acc + L.q + 2 * Q1 + 1, v[1]); }
         atomicAdd(acc + L.slope, v[2]);
         atomicAdd(acc + L.db1 + c, v[3]);
     }
@@ -557,10 +619,18 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
                   p->quant ? p->q4.rmax : nullptr, p->dws2, acc + L.db2, g->dW2q, s);
     if (rc) return rc;
     // P1, R, P2
-    { FQSS_PROF("tcn_gln2_bwd<1>", s); tcn_gln2_bwd_kernel<1><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
+    {
+        FQSS_PROF("tcn_gln2_bwd<1>", s);
+        if (p->quant) tcn_gln2_bwd_kernel<1, true><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        else tcn_gln2_bwd_kernel<1, false><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
                                                                      acc + L.samp2); }
-    { FQSS_PROF("tcn_gln2_bwd<2>", s); tcn_gln2_bwd_kernel<2><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
+    {
+        FQSS_PROF("tcn_gln2_bwd<2>", s);
+        if (p->quant) tcn_gln2_bwd_kernel<2, true><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        else tcn_gln2_bwd_kernel<2, false><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    }
     // D, R, Q
     {
         const int dpad = dw_pad(p->dil);
@@ -588,7 +658,11 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
                                                                      acc + L.samp1); }
-    { FQSS_PROF("tcn_gln1_bwd", s); tcn_gln1_bwd_kernel<<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc); }
+    {
+        FQSS_PROF("tcn_gln1_bwd", s);
+        if (p->quant) tcn_gln1_bwd_kernel<true><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        else tcn_gln1_bwd_kernel<false><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    }
     rc = check_launch("tcn_block_bwd(hidden)");
     if (rc) return rc;
     // G: g_x_in = Wc1T-GEMM(dY1) (+ g_xd)   (K = Chid, N = Cio) -> fp32

@@ -92,10 +92,14 @@ __global__ void tcn_rowconst_kernel(const double* __restrict__ stats, int B, dou
 //            gLN statistics of a3 = FQ3(PReLU(y3)) for the next normalisation
 // HBM bytes: read y1 + write y3 = 8 B/element.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+
 template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_block p) {
     extern __shared__ __align__(16) float dsm[];     // [dpad | ld | dpad] a2 row with zero halo, then the table
     __shared__ double sh[2 * 32];
+    __shared__ unsigned shi[2 * 8];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const int M = p.M, d = p.dil, dpad = dw_pad(d);
@@ -117,10 +121,12 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
         const float4 y = ldg4_stream(y1 + 4 * v);
         float4 a;
         if (QUANT) {
-            a.x = lut[code_index(h.q1, prelu_f(y.x, h.slope))];
-            a.y = lut[code_index(h.q1, prelu_f(y.y, h.slope))];
-            a.z = lut[code_index(h.q1, prelu_f(y.z, h.slope))];
-            a.w = lut[code_index(h.q1, prelu_f(y.w, h.slope))];
+            const float2 t01 = actqf_t2(h.q1, make_float2(prelu_f(y.x, h.slope), prelu_f(y.y, h.slope)));
+            const float2 t23 = actqf_t2(h.q1, make_float2(prelu_f(y.z, h.slope), prelu_f(y.w, h.slope)));
+            a.x = lut[code_u8(t01.x)];
+            a.y = lut[code_u8(t01.y)];
+            a.z = lut[code_u8(t23.x)];
+            a.w = lut[code_u8(t23.y)];
         } else {
             a.x = gln_apply(h.g, prelu_f(y.x, h.slope));
             a.y = gln_apply(h.g, prelu_f(y.y, h.slope));
@@ -136,37 +142,72 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
         *reinterpret_cast<float4*>(row + 4 * v) = a;
     }
     __syncthreads();
-    const float w0 = __ldg(p.wdw + c * 3), w1 = __ldg(p.wdw + c * 3 + 1), w2 = __ldg(p.wdw + c * 3 + 2);
-    const float bias = __ldg(p.bdw + c);
+    const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
+    const float2 bias = f2s(__ldg(p.bdw + c));
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
-    if (QUANT) q3 = load_actqf_rc(p.rc1 + 8);
+    float2 qinv = f2s(0.f), qoff = f2s(0.f);
+    if (QUANT) {
+        q3 = load_actqf_rc(p.rc1 + 8);
+        qinv = f2s(q3.inv);
+        qoff = f2s(-q3.mn * q3.inv);
+    }
     float* y3 = p.y3 + r * p.ld;
+    // statistics of a3 = FQ3(PReLU(y3)): the quantised model accumulates the integer codes (sum c, sum c^2, exact),
+    // a3 = delta*c + min is expanded at the end; the float model sums the values
     float s = 0.f, ss = 0.f;
+    unsigned sc = 0u, scc = 0u;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
         float4 L, C, R;
         dw_taps<DMODE>(row, v, d, L, C, R);
-        float o[4];
-        o[0] = fmaf(w2, R.x, fmaf(w1, C.x, fmaf(w0, L.x, 0.f))) + bias;
-        o[1] = fmaf(w2, R.y, fmaf(w1, C.y, fmaf(w0, L.y, 0.f))) + bias;
-        o[2] = fmaf(w2, R.z, fmaf(w1, C.z, fmaf(w0, L.z, 0.f))) + bias;
-        o[3] = fmaf(w2, R.w, fmaf(w1, C.w, fmaf(w0, L.w, 0.f))) + bias;
-        stg4(y3 + 4 * v, make_float4(o[0], o[1], o[2], o[3]));
+        const float2 o01 = __ffma2_rn(w2, lo2(R), __ffma2_rn(w1, lo2(C), __ffma2_rn(w0, lo2(L), bias)));
+        const float2 o23 = __ffma2_rn(w2, hi2(R), __ffma2_rn(w1, hi2(C), __ffma2_rn(w0, hi2(L), bias)));
+        stg4(y3 + 4 * v, make_float4(o01.x, o01.y, o23.x, o23.y));
         const int nval = M - 4 * v;      // statistics over valid frames only
+        const float2 z01 = make_float2(prelu_f(o01.x, slope3), prelu_f(o01.y, slope3));
+        const float2 z23 = make_float2(prelu_f(o23.x, slope3), prelu_f(o23.y, slope3));
+        if (QUANT) {
+            const float2 t01 = __ffma2_rn(z01, qinv, qoff), t23 = __ffma2_rn(z23, qinv, qoff);
+            unsigned c0 = code_u8(t01.x), c1 = code_u8(t01.y), c2 = code_u8(t23.x), c3 = code_u8(t23.y);
+            if (nval < 4) {
+                c3 = 0u;
+                if (nval < 3) c2 = 0u;
+                if (nval < 2) c1 = 0u;
+                if (nval < 1) c0 = 0u;
+            }
+            sc += c0 + c1 + c2 + c3;
+            scc += c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+        } else {
+            float z[4] = {z01.x, z01.y, z23.x, z23.y};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float z = o[k] > 0.f ? o[k] : slope3 * o[k];
-            float a3 = QUANT ? actqf_fq_approx(q3, z) : z;
-            if (k >= nval) a3 = 0.f;
-            s += a3;
-            ss = fmaf(a3, a3, ss);
+            for (int k = 0; k < 4; ++k) {
+                const float a3 = k < nval ? z[k] : 0.f;
+                s += a3;
+                ss = fmaf(a3, a3, ss);
+            }
         }
     }
-    double vv[2] = {(double)s, (double)ss};
-    block_sum<2>(vv, sh);
-    if (threadIdx.x == 0) {
-        atomicAdd(p.stats3 + 2 * b, vv[0]);
-        atomicAdd(p.stats3 + 2 * b + 1, vv[1]);
+    if (QUANT) {
+        sc = __reduce_add_sync(0xffffffffu, sc);
+        scc = __reduce_add_sync(0xffffffffu, scc);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        if (lane == 0) { shi[wid] = sc; shi[8 + wid] = scc; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long tc = 0, tcc = 0;
+#pragma unroll
+            for (int w = 0; w < ROW_THREADS / 32; ++w) { tc += shi[w]; tcc += shi[8 + w]; }
+            const double dl = (double)q3.delta, mn = (double)q3.mn, n = (double)M;
+            atomicAdd(p.stats3 + 2 * b, dl * (double)tc + n * mn);
+            atomicAdd(p.stats3 + 2 * b + 1, dl * dl * (double)tcc + 2.0 * dl * mn * (double)tc + n * mn * mn);
+        }
+    } else {
+        double vv[2] = {(double)s, (double)ss};
+        block_sum<2>(vv, sh);
+        if (threadIdx.x == 0) {
+            atomicAdd(p.stats3 + 2 * b, vv[0]);
+            atomicAdd(p.stats3 + 2 * b + 1, vv[1]);
+        }
     }
 }
 
@@ -191,10 +232,12 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_t
         const float4 y = ldg4_stream(y3 + 4 * v);
         float o0, o1, o2, o3;
         if (QUANT) {
-            o0 = lut[code_index(h.q3, prelu_f(y.x, h.slope))];
-            o1 = lut[code_index(h.q3, prelu_f(y.y, h.slope))];
-            o2 = lut[code_index(h.q3, prelu_f(y.z, h.slope))];
-            o3 = lut[code_index(h.q3, prelu_f(y.w, h.slope))];
+            const float2 t01 = actqf_t2(h.q3, make_float2(prelu_f(y.x, h.slope), prelu_f(y.y, h.slope)));
+            const float2 t23 = actqf_t2(h.q3, make_float2(prelu_f(y.z, h.slope), prelu_f(y.w, h.slope)));
+            o0 = lut[code_u8(t01.x)];
+            o1 = lut[code_u8(t01.y)];
+            o2 = lut[code_u8(t23.x)];
+            o3 = lut[code_u8(t23.y)];
         } else {
             o0 = gln_apply(h.g, prelu_f(y.x, h.slope));
             o1 = gln_apply(h.g, prelu_f(y.y, h.slope));
