@@ -33,9 +33,10 @@ constexpr int BM = 128;          // frames per tile (TMEM lanes)
 constexpr int BK = 64;           // channels per k-chunk (128 B of bf16 along K for the weights)
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;       // 16 KB: two 64-frame boxes of 64 rows x 128 B
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter: the fused tails are latency-bound, not issue-bound
+constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int MAXN = 1024;
+constexpr int STAT_MAXB = 256;     // samples whose gLN statistics are accumulated in shared memory (EPI_EXPAND)
 
 struct __align__(8) Barriers {
     uint64_t full[STAGES];
@@ -49,7 +50,7 @@ template <int NT>
 __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + NT * BK * 2; }
 
 template <int NT>
-__host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<NT>() + 2 * MAXN * 4 + (int)sizeof(Barriers) + 1024; }
+__host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<NT>() + 2 * MAXN * 4 + (int)sizeof(Barriers) + 2 * STAT_MAXB * 8 + 1024; }
 
 __device__ __forceinline__ float prelu(float y, float a) { return y > 0.f ? y : a * y; }
 
@@ -61,6 +62,10 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s1s = reinterpret_cast<float*>(smem + STAGES * stage_bytes<NT>());
     float* s0s = s1s + MAXN;
     Barriers* bar = reinterpret_cast<Barriers*>(s0s + MAXN);
+    double* stat_sm = (EPI == EPI_EXPAND && p.B <= STAT_MAXB) ? reinterpret_cast<double*>(bar + 1) : nullptr;
+    if (stat_sm) {
+        for (int i = threadIdx.x; i < 2 * p.B; i += NUM_THREADS) stat_sm[i] = 0.0;
+    }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int mt = (p.M + BM - 1) / BM;
@@ -149,12 +154,16 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ================= epilogue =================
-        // One warp = 32 consecutive frames (TMEM lanes) x 32-column chunks.  Per chunk: issue the TMEM load and ALL
-        // global loads the tail needs (32 independent requests in flight), then compute + store; pointers advance by
-        // one row pitch per column, so a warp store is one coalesced 128 B row segment.
+        // One warp = 32 consecutive frames (TMEM lanes) x CW-column chunks of its column group.  The chunk loop is
+        // software-pipelined: while chunk c is computed, the TMEM load and the global loads (residual / skip-sum /
+        // addend) of chunk c+1 are already in flight.  Pointers advance by one row pitch per column, so a warp
+        // store is one coalesced 128 B row segment.
         const int q = warp & 3;                 // TMEM lane quarter this warp may touch
-        const int h = (warp - 4) >> 2;          // column half
-        constexpr int COLS = NT / 2;
+        const int h = (warp - 4) >> 2;          // column group
+        constexpr int COLS = NT / (EPI_WARPS / 4);
+        constexpr bool HAS_PRE = (EPI == EPI_RESSKIP || EPI == EPI_ADD || EPI == EPI_RELU_MUL);
+        constexpr int CW = HAS_PRE ? 8 : 16;    // columns per chunk (two chunks live in registers)
+        static_assert(COLS % (2 * CW) == 0, "chunk pipeline needs an even number of chunks");
         ActQF q1, qres, qskip, qadd, qadds;
         float slope = 0.f;
         if (EPI == EPI_EXPAND) {
@@ -177,144 +186,159 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int b = mrow / mt, m0 = (mrow % mt) * BM;
             const int m = m0 + q * 32 + lane;
             const bool valid = m < p.M;
-            mbar_wait(&bar->tmem_full[acc], acc_phase);
-            tc_fence_after();
             float st_s = 0.f, st_ss = 0.f;
-#pragma unroll 1
-            for (int c0 = 0; c0 < COLS; c0 += 32) {
-                uint32_t v[32];
-                const int col = h * COLS + c0;
-                const int o0 = n_idx * NT + col;            // first output channel of this chunk
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + col), v);
+            const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * COLS);
+            const int obase = n_idx * NT + h * COLS;      // first output channel of this warp's column group
+
+            // global operands of the tail for the chunk starting at column c0 of the group
+            auto load_pre = [&](float (&pre)[CW], int c0) {
+                if (!HAS_PRE) return;
+                const int o0 = obase + c0;
+                const float* src = nullptr;
+                if (EPI == EPI_ADD) {
+                    src = p.addend + ((int64_t)b * p.N + o0) * ld + m;
+                } else if (EPI == EPI_RELU_MUL) {
+                    src = p.addend + ((int64_t)b * p.mul_C + (o0 % p.mul_C)) * ld + m;      // mul_C % 32 == 0
+                } else {
+                    const bool is_res = o0 < p.n_res;
+                    const int n_loc = is_res ? p.n_res : p.N - p.n_res;
+                    const int64_t i0 = ((int64_t)b * n_loc + (is_res ? o0 : o0 - p.n_res)) * ld + m;
+                    src = is_res ? p.x_in + i0 : (p.first_block ? nullptr : p.skip_in + i0);
+                }
+#pragma unroll
+                for (int j = 0; j < CW; ++j) pre[j] = (valid && src) ? __ldg(src + j * ld) : 0.f;
+            };
+
+            auto compute = [&](const uint32_t (&v)[CW], const float (&pre)[CW], int c0) {
+                if (!valid) return;
+                const int o0 = obase + c0;
                 const float* s1c = s1s + o0;
                 const float* s0c = s0s + o0;
                 if (EPI == EPI_STORE) {
-                    tmem_ld_wait();
-                    if (valid) {
-                        const int64_t base = ((int64_t)b * p.N + o0) * ld + m;
-                        float* of = p.out_f32 ? p.out_f32 + base : nullptr;
-                        __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + base : nullptr;
+                    const int64_t base = ((int64_t)b * p.N + o0) * ld + m;
+                    float* of = p.out_f32 ? p.out_f32 + base : nullptr;
+                    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + base : nullptr;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                            if (of) of[j * ld] = y;
-                            if (ob) ob[j * ld] = __float2bfloat16_rn(y);
-                        }
+                    for (int j = 0; j < CW; ++j) {
+                        const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                        if (of) of[j * ld] = y;
+                        if (ob) ob[j * ld] = __float2bfloat16_rn(y);
                     }
                 } else if (EPI == EPI_BF16) {
-                    tmem_ld_wait();
-                    if (valid) {
-                        __nv_bfloat16* ob = p.out_bf16 + ((int64_t)b * p.N + o0) * ld + m;
+                    __nv_bfloat16* ob = p.out_bf16 + ((int64_t)b * p.N + o0) * ld + m;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) ob[j * ld] = __float2bfloat16_rn(fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]));
-                    }
+                    for (int j = 0; j < CW; ++j) ob[j * ld] = __float2bfloat16_rn(fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]));
                 } else if (EPI == EPI_EXPAND) {
-                    tmem_ld_wait();
-                    if (valid) {
-                        float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
-                        if (p.quant) {
+                    float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
+                    if (p.quant) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                of[j * ld] = y;
-                                const float a = actqf_fq_approx(q1, prelu(y, slope));
-                                st_s += a;
-                                st_ss = fmaf(a, a, st_ss);
-                            }
-                        } else {
+                        for (int j = 0; j < CW; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            of[j * ld] = y;
+                            const float a = actqf_fq_approx(q1, prelu(y, slope));
+                            st_s += a;
+                            st_ss = fmaf(a, a, st_ss);
+                        }
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                of[j * ld] = y;
-                                const float a = prelu(y, slope);
-                                st_s += a;
-                                st_ss = fmaf(a, a, st_ss);
-                            }
+                        for (int j = 0; j < CW; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            of[j * ld] = y;
+                            const float a = prelu(y, slope);
+                            st_s += a;
+                            st_ss = fmaf(a, a, st_ss);
                         }
                     }
                 } else if (EPI == EPI_ADD || EPI == EPI_RELU_MUL) {
-                    float pre[32];
-                    const int64_t base = ((int64_t)b * p.N + o0) * ld + m;
-                    const float* ap = (EPI == EPI_ADD) ? p.addend + base
-                                                       : p.addend + ((int64_t)b * p.mul_C + (o0 % p.mul_C)) * ld + m;   // mul_C % 32 == 0
+                    float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) pre[j] = valid ? __ldg(ap + j * ld) : 0.f;
-                    tmem_ld_wait();
-                    if (valid) {
-                        float* of = p.out_f32 + base;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                            of[j * ld] = (EPI == EPI_ADD) ? y + pre[j] : fmaxf(y, 0.f) * pre[j];
-                        }
+                    for (int j = 0; j < CW; ++j) {
+                        const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                        of[j * ld] = (EPI == EPI_ADD) ? y + pre[j] : fmaxf(y, 0.f) * pre[j];
                     }
                 } else if (EPI == EPI_RESSKIP) {
                     const bool is_res = o0 < p.n_res;           // warp-uniform: a chunk never straddles the two convs
                     const int n_loc = is_res ? p.n_res : p.N - p.n_res;
                     const int64_t i0 = ((int64_t)b * n_loc + (is_res ? o0 : o0 - p.n_res)) * ld + m;
-                    const float* src = is_res ? p.x_in + i0 : (p.first_block ? nullptr : p.skip_in + i0);
-                    float pre[32];
-                    if (src) {
+                    if (is_res) {                               // residual conv -> FQ -> (x + res) -> FQ
+                        float* ry = p.res_y ? p.res_y + i0 : nullptr;
+                        float* xo = p.x_out + i0;
+                        if (p.quant) {
+                            __nv_bfloat16* xop = p.x_out_op + i0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) pre[j] = valid ? __ldg(src + j * ld) : 0.f;
-                    }
-                    tmem_ld_wait();
-                    if (valid) {
-                        if (is_res) {                           // residual conv -> FQ -> (x + res) -> FQ
-                            float* ry = p.res_y ? p.res_y + i0 : nullptr;
-                            float* xo = p.x_out + i0;
-                            if (p.quant) {
-                                __nv_bfloat16* xop = p.x_out_op + i0;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                    if (ry) ry[j * ld] = y;
-                                    const float z = __fadd_rn(pre[j], actqf_fq(qres, y));
-                                    const float c = actqf_code(qadd, z);
-                                    xo[j * ld] = actqf_decode(qadd, c);
-                                    xop[j * ld] = __float2bfloat16_rn(c);
-                                }
-                            } else {
-                                __nv_bfloat16* xop = p.x_out_op + (p.split ? ((int64_t)b * 2 * p.n_res + o0) * ld + m : i0);
-                                const int64_t lo_off = (int64_t)p.n_res * ld;
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) {
-                                    const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                    if (ry) ry[j * ld] = y;
-                                    const float z = __fadd_rn(pre[j], y);
-                                    xo[j * ld] = z;
-                                    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
-                                    xop[j * ld] = hi;
-                                    if (p.split) xop[j * ld + lo_off] = __float2bfloat16_rn(z - __bfloat162float(hi));
-                                }
-                            }
-                        } else {                                // skip conv -> FQ -> (skip_sum + skip) -> FQ
-                            float* sy = p.skip_y ? p.skip_y + i0 : nullptr;
-                            float* so = p.skip_out + i0;
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
+                            for (int j = 0; j < CW; ++j) {
                                 const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                if (sy) sy[j * ld] = y;
-                                const float sk = p.quant ? actqf_fq(qskip, y) : y;
-                                if (p.first_block) {
-                                    so[j * ld] = sk;
-                                } else {
-                                    const float z = __fadd_rn(pre[j], sk);
-                                    so[j * ld] = p.quant ? actqf_fq(qadds, z) : z;
-                                }
+                                if (ry) ry[j * ld] = y;
+                                const float z = __fadd_rn(pre[j], actqf_fq(qres, y));
+                                const float c = actqf_code(qadd, z);
+                                xo[j * ld] = actqf_decode(qadd, c);
+                                xop[j * ld] = __float2bfloat16_rn(c);
+                            }
+                        } else {
+                            __nv_bfloat16* xop = p.x_out_op + (p.split ? ((int64_t)b * 2 * p.n_res + o0) * ld + m : i0);
+                            const int64_t lo_off = (int64_t)p.n_res * ld;
+#pragma unroll
+                            for (int j = 0; j < CW; ++j) {
+                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                if (ry) ry[j * ld] = y;
+                                const float z = __fadd_rn(pre[j], y);
+                                xo[j * ld] = z;
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(z);
+                                xop[j * ld] = hi;
+                                if (p.split) xop[j * ld + lo_off] = __float2bfloat16_rn(z - __bfloat162float(hi));
+                            }
+                        }
+                    } else {                                    // skip conv -> FQ -> (skip_sum + skip) -> FQ
+                        float* sy = p.skip_y ? p.skip_y + i0 : nullptr;
+                        float* so = p.skip_out + i0;
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            if (sy) sy[j * ld] = y;
+                            const float sk = p.quant ? actqf_fq(qskip, y) : y;
+                            if (p.first_block) {
+                                so[j * ld] = sk;
+                            } else {
+                                const float z = __fadd_rn(pre[j], sk);
+                                so[j * ld] = p.quant ? actqf_fq(qadds, z) : z;
                             }
                         }
                     }
                 }
+            };
+
+            uint32_t va[CW], vb[CW];
+            float pa[CW], pb[CW];
+            load_pre(pa, 0);                          // independent of the accumulator: issue before waiting for the MMAs
+            mbar_wait(&bar->tmem_full[acc], acc_phase);
+            tc_fence_after();
+            tmem_ld_cols<CW>(tbase, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < COLS; c0 += 2 * CW) {
+                tmem_ld_wait();
+                tmem_ld_cols<CW>(tbase + (uint32_t)(c0 + CW), vb);
+                load_pre(pb, c0 + CW);
+                compute(va, pa, c0);
+                tmem_ld_wait();
+                if (c0 + 2 * CW < COLS) {
+                    tmem_ld_cols<CW>(tbase + (uint32_t)(c0 + 2 * CW), va);
+                    load_pre(pa, c0 + 2 * CW);
+                }
+                compute(vb, pb, c0 + CW);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
             if (EPI == EPI_EXPAND) {
-                double ds = warp_sum((double)st_s), dss = warp_sum((double)st_ss);
+                const float ws = warp_sum(st_s), wss = warp_sum(st_ss);
                 if (lane == 0) {
-                    atomicAdd(p.stats + 2 * b, ds);
-                    atomicAdd(p.stats + 2 * b + 1, dss);
+                    if (stat_sm) {
+                        atomicAdd(stat_sm + 2 * b, (double)ws);
+                        atomicAdd(stat_sm + 2 * b + 1, (double)wss);
+                    } else {
+                        atomicAdd(p.stats + 2 * b, (double)ws);
+                        atomicAdd(p.stats + 2 * b + 1, (double)wss);
+                    }
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -322,6 +346,14 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (EPI == EPI_EXPAND && stat_sm) {
+        // one pair of global atomics per (CTA, sample) instead of one per (warp, tile): the per-sample accumulators
+        // are otherwise hit by every epilogue warp of every CTA working on the same sample at the same time
+        for (int i = threadIdx.x; i < 2 * p.B; i += NUM_THREADS) {
+            const double v = stat_sm[i];
+            if (v != 0.0) atomicAdd(p.stats + i, v);
+        }
+    }
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * NT);
