@@ -209,8 +209,12 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
     const Hidden3 h = load_hidden3(p, b, c);
     if (QUANT) {
         chain_bwd_tables(h.q3, h.g, h.q4, threadIdx.x, tabX, tabD);
+        if (PHASE == 1) {       // P1 reads only tabD: fold the mask into its LSB
+            tabD[threadIdx.x] = __uint_as_float((__float_as_uint(tabD[threadIdx.x]) & ~1u) | (tab_mask(tabX[threadIdx.x]) ? 1u : 0u));
+        }
         __syncthreads();
     }
+    const float2 xa3 = f2s(QUANT ? h.q3.delta * h.g.rstd : 0.f), xb3 = f2s(QUANT ? (h.q3.mn - h.g.mu) * h.g.rstd : 0.f);
     const int M = p.M;
     const float4* y3 = reinterpret_cast<const float4*>(p.y3 + r * p.ld);
     const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
@@ -226,9 +230,14 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
     // P1: a0 = sum g*D4, a1 = sum g*(1-m4), a2 = sum g*m4, a3 = sum g*m4*xhat     (q4: sD = a0, sZ = a1)
     // P2: a0 = sum ga3*D3, a1 = sum ga3*(1-m3), a3 = sum min(y,0)*gz              (q3: sD = a0, sZ = a1; slope3)
     float2 a0 = f2s(0.f), a1 = f2s(0.f), a2 = f2s(0.f), a3 = f2s(0.f);
+    constexpr bool CODES = (PHASE == 1 && QUANT);      // everything P1 needs is a function of the saved code of a3
+    const uint32_t* c3 = reinterpret_cast<const uint32_t*>(p.code3 + r * p.ld);
     auto body = [&](int v, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        const float4 y = __ldg(y3 + v);
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t packed = 0;
+        if (CODES) packed = __ldg(c3 + v);
+        else y = __ldg(y3 + v);
         const float4 gi = bf16x4_to_float4(__ldg(ga4 + v));
         float2 gg[2] = {lo2(gi), hi2(gi)};
         if (TAIL) mask_tail(gg[0], gg[1], M - 4 * v);
@@ -236,10 +245,21 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
         float2 o[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const float2 z = make_float2(prelu_f(yy[j].x, slope), prelu_f(yy[j].y, slope));
+            float2 z = f2s(0.f);
+            if (!CODES) z = make_float2(prelu_f(yy[j].x, slope), prelu_f(yy[j].y, slope));
             float2 xh, gn, t = f2s(0.f);
             unsigned ix = 0, iy = 0;
-            if (QUANT) {
+            if (CODES) {
+                // one LDS.32 per element (D4 with the STE mask in its LSB); xhat3 is one FMA on the code: shared-memory
+                // bandwidth under random bank conflicts, not issue slots, is what the table lookups cost
+                ix = (packed >> (16 * j)) & 255u;
+                iy = (packed >> (16 * j + 8)) & 255u;
+                const float2 dm = make_float2(tabD[ix], tabD[iy]);
+                xh = __ffma2_rn(make_float2((float)ix, (float)iy), xa3, xb3);
+                gn = make_float2(tab_mask(dm.x) ? gg[j].x : 0.f, tab_mask(dm.y) ? gg[j].y : 0.f);
+                a0 = __ffma2_rn(gg[j], dm, a0);
+                a1 = __fadd2_rn(a1, __fadd2_rn(gg[j], neg2(gn)));
+            } else if (QUANT) {
                 t = actqf_t2(h.q3, z);
                 ix = code_u8(t.x);
                 iy = code_u8(t.y);
@@ -250,7 +270,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
                 gn = gg[j];
             }
             if (PHASE == 1) {
-                if (QUANT) {
+                if (QUANT && !CODES) {
                     a0 = __ffma2_rn(gg[j], make_float2(tabD[ix], tabD[iy]), a0);
                     a1 = __fadd2_rn(a1, __fadd2_rn(gg[j], neg2(gn)));      // g*(1-m): exactly g or 0, no cancellation
                 }
@@ -324,10 +344,14 @@ __global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row.  Shared memory:
-//   a2 row and g_y3 row (fp32, zero halo of dw_pad(d) frames on both sides -> predicate-free taps),
-//   the code1 byte per frame (quantised model) or the xhat1 row (float model), and three 256-entry
-//   tables over code1: a2 = FQ2(gLN1(.)), xhat1 | mask2, D2.
+// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row.
+//   stage  y1 -> code1 (one byte per frame), g_y3 (bf16) -> fp32 row in shared memory with a zero halo of
+//          dw_pad(d) frames on both sides (predicate-free taps)
+//   fir    g_a2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d];  t2 = FQ2's pre-rounding value comes from one 32-bit table
+//          lookup on code1; code2, a2, the STE mask and the range weight follow arithmetically.  The tap gradients
+//          need only the centre a2:  dW_k = sum_m g[m] a2[m+(k-1)d] = sum_m a2[m] g[m-(k-1)d]  (zero halo), so a2 is
+//          never staged.
+// The float model keeps a2 and xhat1 of the row in shared memory instead of the code bytes.
 // ---------------------------------------------------------------------------------------------
 template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
@@ -339,101 +363,97 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
     const int M = p.M, d = p.dil, dpad = dw_pad(d);
     const int ld = (int)p.ld;
     const int rowlen = ld + 2 * dpad;
-    float* a2r = dsm + dpad;
-    float* gyr = dsm + rowlen + dpad;
-    float* tabA = dsm + 2 * rowlen;
-    float* tabX = tabA + 256;
-    float* tabD = tabX + 256;
-    float* aux = tabD + 256;                          // QUANT: ld code bytes; else: ld floats of xhat1
-    uint32_t* idx32 = reinterpret_cast<uint32_t*>(aux);
+    float* gyr = dsm + dpad;
+    float* tabT = dsm + rowlen;                                       // QUANT: t2 = (gLN1(decode1(code1)) - min2) / delta2
+    uint32_t* idx32 = reinterpret_cast<uint32_t*>(dsm + rowlen + 256);    // QUANT: ld code bytes
+    float* a2r = dsm + rowlen;                                        // float model: a2 row, then xhat1 row
+    float* xhr = a2r + ld;
     const Hidden1 h = load_hidden1(p, b, c);
     for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
         dsm[i] = 0.f;
-        a2r[ld + i] = 0.f;
-        dsm[rowlen + i] = 0.f;
         gyr[ld + i] = 0.f;
     }
-    if (QUANT) {
-        const float4 e = chain_bwd_entry(h.q1, h.g, h.q2, threadIdx.x, true);
-        tabA[threadIdx.x] = e.x;
-        tabX[threadIdx.x] = __uint_as_float((__float_as_uint(e.w) & ~1u) | (e.y != 0.f ? 1u : 0u));
-        tabD[threadIdx.x] = e.z;
-        __syncthreads();
-    }
+    // frames of all-padding quads (ld - M >= 4) are never staged: the taps must still see zeros there
+    for (int i = ((M + 3) & ~3) + threadIdx.x; i < ld; i += ROW_THREADS) gyr[i] = 0.f;
+    if (QUANT) tabT[threadIdx.x] = actqf_t(h.q2, gln_apply(h.g, actqf_decode(h.q1, (float)threadIdx.x)));
     const float4* y1 = reinterpret_cast<const float4*>(p.y1 + r * p.ld);
+    const uint32_t* c1 = reinterpret_cast<const uint32_t*>(p.code1 + r * p.ld);
     const uint2* gy3 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld);
     const float slope = h.slope;
-    // frames of all-padding quads (ld - M >= 4) are never staged: the taps must still see zeros there
-    for (int i = ((M + 3) & ~3) + threadIdx.x; i < ld; i += ROW_THREADS) {
-        a2r[i] = 0.f;
-        gyr[i] = 0.f;
-    }
     auto stage = [&](int v, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        const float4 y = __ldg(y1 + v);
         const float4 gi = bf16x4_to_float4(__ldg(gy3 + v));
         float2 g01 = lo2(gi), g23 = hi2(gi);
-        const float2 z01 = make_float2(prelu_f(y.x, slope), prelu_f(y.y, slope));
-        const float2 z23 = make_float2(prelu_f(y.z, slope), prelu_f(y.w, slope));
-        float2 a01, a23;
         if (QUANT) {
-            const float2 t01 = actqf_t2(h.q1, z01), t23 = actqf_t2(h.q1, z23);
-            const unsigned i0 = code_u8(t01.x), i1 = code_u8(t01.y), i2 = code_u8(t23.x), i3 = code_u8(t23.y);
-            idx32[v] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
-            a01 = make_float2(tabA[i0], tabA[i1]);
-            a23 = make_float2(tabA[i2], tabA[i3]);
+            idx32[v] = __ldg(c1 + v);                         // saved code of a1: no need to touch y1
         } else {
-            a01 = make_float2(gln_apply(h.g, z01.x), gln_apply(h.g, z01.y));
-            a23 = make_float2(gln_apply(h.g, z23.x), gln_apply(h.g, z23.y));
-            *reinterpret_cast<float4*>(aux + 4 * v) = make_float4(gln_xhat(h.g, z01.x), gln_xhat(h.g, z01.y), gln_xhat(h.g, z23.x), gln_xhat(h.g, z23.y));
+            const float4 y = __ldg(y1 + v);
+            const float2 z01 = make_float2(prelu_f(y.x, slope), prelu_f(y.y, slope));
+            const float2 z23 = make_float2(prelu_f(y.z, slope), prelu_f(y.w, slope));
+            *reinterpret_cast<float4*>(a2r + 4 * v) = make_float4(gln_apply(h.g, z01.x), gln_apply(h.g, z01.y), gln_apply(h.g, z23.x), gln_apply(h.g, z23.y));
+            *reinterpret_cast<float4*>(xhr + 4 * v) = make_float4(gln_xhat(h.g, z01.x), gln_xhat(h.g, z01.y), gln_xhat(h.g, z23.x), gln_xhat(h.g, z23.y));
         }
-        if (TAIL) {
-            mask_tail(a01, a23, M - 4 * v);
-            mask_tail(g01, g23, M - 4 * v);
-        }
-        *reinterpret_cast<float4*>(a2r + 4 * v) = make_float4(a01.x, a01.y, a23.x, a23.y);
+        if (TAIL) mask_tail(g01, g23, M - 4 * v);
         *reinterpret_cast<float4*>(gyr + 4 * v) = make_float4(g01.x, g01.y, g23.x, g23.y);
     };
     FQSS_ROW_LOOP(stage, M);
     __syncthreads();
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
+    const float2 xa1 = f2s(QUANT ? h.q1.delta * h.g.rstd : 0.f), xb1 = f2s(QUANT ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f);
     uint2* gn1o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld);
-    // b0 = sum ga2*D2, b1 = sum ga2*(1-m2), b2 = sum gn1, b3 = sum gn1*xhat1 | taps: d0,d1,d2 = sum g*a2[-d,0,+d], d3 = sum g
+    // b0 = sum ga2*D2, b1 = sum ga2*(1-m2), b2 = sum gn1, b3 = sum gn1*xhat1 | taps: d0,d1,d2 = sum a2*g[+d,0,-d], d3 = sum g
     float2 b0 = f2s(0.f), b1 = f2s(0.f), b2 = f2s(0.f), b3 = f2s(0.f), d0 = f2s(0.f), d1 = f2s(0.f), d2 = f2s(0.f), d3 = f2s(0.f);
     auto fir = [&](int v, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        float4 gL, gC, gR, aL, aC, aR;
+        float4 gL, gC, gR;
         dw_taps<DMODE>(gyr, v, d, gL, gC, gR);
-        dw_taps<DMODE>(a2r, v, d, aL, aC, aR);
         uint32_t packed = 0;
-        float4 xq = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (QUANT) packed = idx32[v];
-        else xq = *reinterpret_cast<const float4*>(aux + 4 * v);
+        float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), xq = aq;
+        if (QUANT) {
+            packed = idx32[v];
+        } else {
+            aq = *reinterpret_cast<const float4*>(a2r + 4 * v);
+            xq = *reinterpret_cast<const float4*>(xhr + 4 * v);
+        }
         float2 o[2];
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const float2 gc = j ? hi2(gC) : lo2(gC), gl = j ? hi2(gL) : lo2(gL), gr = j ? hi2(gR) : lo2(gR);
-            // y3[m'] = sum_j w_j a2[m' + (j-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
+            // y3[m'] = sum_k w_k a2[m' + (k-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
             float2 ga2 = __ffma2_rn(w0, gr, __ffma2_rn(w1, gc, __fmul2_rn(w2, gl)));
-            if (TAIL) {
-                if (4 * v + 2 * j + 1 >= M) ga2.y = 0.f;
-                if (4 * v + 2 * j >= M) ga2.x = 0.f;
-            }
-            d0 = __ffma2_rn(gc, j ? hi2(aL) : lo2(aL), d0);
-            d1 = __ffma2_rn(gc, j ? hi2(aC) : lo2(aC), d1);
-            d2 = __ffma2_rn(gc, j ? hi2(aR) : lo2(aR), d2);
-            d3 = __fadd2_rn(d3, gc);
-            float2 gn1, xh;
+            float2 a2, xh, gn1;
             if (QUANT) {
+                // ONE LDS.32 per element: t2 as a function of code1.  Code, value, STE mask and range weight of FQ2 follow
+                // from t2 with a handful of ALU ops (bit-identical to forward), xhat1 is one FMA on code1 -- under random
+                // bank conflicts a wider table would cost more shared-memory cycles than this arithmetic costs issue slots
                 const unsigned ix = (packed >> (16 * j)) & 255u, iy = (packed >> (16 * j + 8)) & 255u;
-                xh = make_float2(tabX[ix], tabX[iy]);
-                gn1 = make_float2(tab_mask(xh.x) ? ga2.x : 0.f, tab_mask(xh.y) ? ga2.y : 0.f);
-                b0 = __ffma2_rn(ga2, make_float2(tabD[ix], tabD[iy]), b0);
+                const float2 t2 = make_float2(tabT[ix], tabT[iy]);
+                const float2 c2 = make_float2((float)code_u8(t2.x), (float)code_u8(t2.y));
+                a2 = __fadd2_rn(__fmul2_rn(f2s(h.q2.delta), c2), f2s(h.q2.mn));
+                xh = __ffma2_rn(make_float2((float)ix, (float)iy), xa1, xb1);
+                if (TAIL) {                                   // frames >= M: no gradient, and a2 there is not part of the row
+                    if (4 * v + 2 * j + 1 >= M) { ga2.y = 0.f; a2.y = 0.f; }
+                    if (4 * v + 2 * j >= M) { ga2.x = 0.f; a2.x = 0.f; }
+                }
+                const float2 th = __fadd2_rn(t2, f2s(0.5f));
+                const bool inx = inside_u8(th.x), iny = inside_u8(th.y);
+                const float2 dd = __fadd2_rn(c2, neg2(t2));
+                gn1 = make_float2(inx ? ga2.x : 0.f, iny ? ga2.y : 0.f);
+                b0 = __ffma2_rn(ga2, make_float2(inx ? dd.x : c2.x, iny ? dd.y : c2.y), b0);
                 b1 = __fadd2_rn(b1, __fadd2_rn(ga2, neg2(gn1)));
             } else {
+                a2 = j ? hi2(aq) : lo2(aq);
                 xh = j ? hi2(xq) : lo2(xq);
+                if (TAIL) {
+                    if (4 * v + 2 * j + 1 >= M) { ga2.y = 0.f; a2.y = 0.f; }
+                    if (4 * v + 2 * j >= M) { ga2.x = 0.f; a2.x = 0.f; }
+                }
                 gn1 = ga2;
             }
+            d0 = __ffma2_rn(a2, gr, d0);      // dW_0 = sum_m a2[m] g[m+d]
+            d1 = __ffma2_rn(a2, gc, d1);
+            d2 = __ffma2_rn(a2, gl, d2);      // dW_2 = sum_m a2[m] g[m-d]
+            d3 = __fadd2_rn(d3, gc);
             b2 = __fadd2_rn(b2, gn1);
             b3 = __ffma2_rn(gn1, xh, b3);
             o[j] = gn1;
@@ -581,6 +601,7 @@ size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid) {
 int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, void* stream) {
     int rc = tcn_validate_block(p, "tcn_block_bwd");
     if (rc) return rc;
+    FQSS_REQUIRE(!p->quant || (p->code1 && p->code3), -1, "tcn_block_bwd: forward did not save the activation codes (code1 / code3)");
     FQSS_REQUIRE(!p->split && p->skip_y && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
                  "tcn_block_bwd: block was run in inference mode (split operands / no saved pre-activations)");
     FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->g_hid_b && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
@@ -634,7 +655,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // D, R, Q
     {
         const int dpad = dw_pad(p->dil);
-        const size_t smem = ((size_t)2 * (p->ld + 2 * dpad) + 768) * sizeof(float) + (p->quant ? (size_t)p->ld : (size_t)p->ld * sizeof(float));
+        const size_t smem = ((size_t)p->ld + 2 * dpad) * sizeof(float) + (p->quant ? 1024 + (size_t)p->ld : (size_t)2 * p->ld * sizeof(float));
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         static bool cfg = false;
         if (!cfg) {

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
         __syncthreads();
     }
     const float* y1 = p.y1 + r * p.ld;
+    uint32_t* code1 = p.code1 ? reinterpret_cast<uint32_t*>(p.code1 + r * p.ld) : nullptr;
     const int nvec = ld >> 2;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
         const float4 y = ldg4_stream(y1 + 4 * v);
@@ -123,10 +124,12 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
         if (QUANT) {
             const float2 t01 = actqf_t2(h.q1, make_float2(prelu_f(y.x, h.slope), prelu_f(y.y, h.slope)));
             const float2 t23 = actqf_t2(h.q1, make_float2(prelu_f(y.z, h.slope), prelu_f(y.w, h.slope)));
-            a.x = lut[code_u8(t01.x)];
-            a.y = lut[code_u8(t01.y)];
-            a.z = lut[code_u8(t23.x)];
-            a.w = lut[code_u8(t23.y)];
+            const unsigned i0 = code_u8(t01.x), i1 = code_u8(t01.y), i2 = code_u8(t23.x), i3 = code_u8(t23.y);
+            if (code1) code1[v] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
+            a.x = lut[i0];
+            a.y = lut[i1];
+            a.z = lut[i2];
+            a.w = lut[i3];
         } else {
             a.x = gln_apply(h.g, prelu_f(y.x, h.slope));
             a.y = gln_apply(h.g, prelu_f(y.y, h.slope));
@@ -227,6 +230,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_t
     }
     const float* y3 = p.y3 + r * p.ld;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + r * p.ld;
+    uint32_t* code3 = p.code3 ? reinterpret_cast<uint32_t*>(p.code3 + r * p.ld) : nullptr;
     const int nvec = (p.M + 3) >> 2;
     for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
         const float4 y = ldg4_stream(y3 + 4 * v);
@@ -234,10 +238,12 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_t
         if (QUANT) {
             const float2 t01 = actqf_t2(h.q3, make_float2(prelu_f(y.x, h.slope), prelu_f(y.y, h.slope)));
             const float2 t23 = actqf_t2(h.q3, make_float2(prelu_f(y.z, h.slope), prelu_f(y.w, h.slope)));
-            o0 = lut[code_u8(t01.x)];
-            o1 = lut[code_u8(t01.y)];
-            o2 = lut[code_u8(t23.x)];
-            o3 = lut[code_u8(t23.y)];
+            const unsigned i0 = code_u8(t01.x), i1 = code_u8(t01.y), i2 = code_u8(t23.x), i3 = code_u8(t23.y);
+            if (code3) code3[v] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
+            o0 = lut[i0];
+            o1 = lut[i1];
+            o2 = lut[i2];
+            o3 = lut[i3];
         } else {
             o0 = gln_apply(h.g, prelu_f(y.x, h.slope));
             o1 = gln_apply(h.g, prelu_f(y.y, h.slope));

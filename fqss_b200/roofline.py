@@ -64,17 +64,17 @@ def algorithmic_bytes(B, M, Cio=128, Chid=512):
     return {
         # forward
         "gemm_expand": 2 * I + w1 + 4 * H,                      # x_op bf16 in, y1 fp32 out
-        "tcn_dw_fwd": 4 * H + 4 * H,                            # y1 in, y3 out
-        "tcn_hidden_fq": 4 * H + 2 * H,                         # y3 in, a4 operand (bf16 codes) out
+        "tcn_dw_fwd": 4 * H + 4 * H + H,                        # y1 in, y3 + code1 (u8) out
+        "tcn_hidden_fq": 4 * H + 2 * H + H,                     # y3 in, a4 operand (bf16 codes) + code3 (u8) out
         "gemm_resskip": 2 * H + w2 + 4 * I * 2 + 4 * I * 4 + 2 * I,   # a4, x_in, skip_in -> res_y, skip_y, x_out, skip_out, x_out_op
         "tcn_dw_fwd(float)": 8 * H,
         "tcn_hidden_fq(float)": 4 * H + 4 * H,                  # [hi ; lo] bf16 pair out
         # backward
         "tcn_tail_bwd": 4 * I * 6 + 4 * I * 2 + 2 * I * 2,      # g_x, g_skip, res_y, skip_y, x_in, skip_in -> g_xd, g_skip_in, dY2
         "gemm_dgrad_bf16": 2 * 2 * I + w2 + 2 * H,              # dY2 in, g_a4 bf16 out
-        "tcn_gln2_bwd<1>": 4 * H + 2 * H,                       # y3, g_a4 in (sums out)
+        "tcn_gln2_bwd<1>": H + 2 * H,                           # code3 (u8), g_a4 (bf16) in (sums out)
         "tcn_gln2_bwd<2>": 4 * H + 2 * H + 2 * H,               # y3, g_a4 in, g_y3 bf16 out
-        "tcn_dw_bwd": 4 * H + 2 * H + 2 * H,                    # y1, g_y3 in, g_n1 bf16 out
+        "tcn_dw_bwd": H + 2 * H + 2 * H,                        # code1 (u8), g_y3 in, g_n1 bf16 out
         "tcn_gln1_bwd": 4 * H + 2 * H + 2 * H,                  # y1, g_n1 in, dY1 bf16 out
         "gemm_dgrad_add": 2 * H + w1 + 4 * I + 4 * I,           # dY1, g_xd in, g_x_in out
         "tcn_hid_bwd_a": 4 * H + 2 * H,

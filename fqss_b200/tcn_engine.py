@@ -36,7 +36,7 @@ class TcnBlock(C.Structure):
                 ("qskip", QRange), ("qadd", QRange), ("qadds", QRange),
                 ("x_op", vp), ("x_in", vp), ("skip_in", vp),
                 ("y1", vp), ("stats1", vp), ("y3", vp), ("stats3", vp), ("a4_op", vp),
-                ("res_y", vp), ("skip_y", vp), ("x_out", vp), ("x_out_op", vp), ("skip_out", vp), ("rc1", vp), ("rc3", vp)]
+                ("res_y", vp), ("skip_y", vp), ("x_out", vp), ("x_out_op", vp), ("skip_out", vp), ("rc1", vp), ("rc3", vp), ("code1", vp), ("code3", vp)]
 
 
 class TcnBlockGrads(C.Structure):
@@ -212,13 +212,16 @@ def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
         setattr(blk, name, qr(t[lo], t[hi]))
 
 
-def _alloc_acts(B, Cio, Chid, ld, has_res, dev):
+def _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant=True):
     bf = torch.bfloat16
     A = dict(y1=torch.empty((B, Chid, ld), device=dev), y3=torch.empty((B, Chid, ld), device=dev),
              stats1=torch.empty(2 * B, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B, dtype=torch.float64, device=dev),
              a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), skip_y=torch.empty((B, Cio, ld), device=dev),
              skip_out=torch.empty((B, Cio, ld), device=dev), rc1=torch.empty(12 + 2 * B, device=dev),
              rc3=torch.empty(12 + 2 * B, device=dev))
+    if quant:
+        A.update(code1=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev),
+                 code3=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev))
     if has_res:
         A.update(res_y=torch.empty((B, Cio, ld), device=dev), x_out=torch.empty((B, Cio, ld), device=dev),
                  x_out_op=torch.empty((B, Cio, ld), dtype=bf, device=dev))
@@ -264,7 +267,7 @@ class FusedTCNFunction(Function):
             first, has_res = (start + i) == 0, (start + i) < total - 1
             Chid = t["W1"].shape[0]
             P = _prep_block(t, quant, first, has_res, cur_q, dev)
-            A = _alloc_acts(B, Cio, Chid, ld, has_res, dev)
+            A = _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant)
             blk = TcnBlock()
             _fill_block(blk, t, P, quant, first, has_res, dils[i], B, M, ld, cur_q)
             blk.x_op, blk.x_in, blk.skip_in = ptr(cur_op), ptr(cur_x), ptr(cur_skip) or None
@@ -272,6 +275,8 @@ class FusedTCNFunction(Function):
                 setattr(blk, k, ptr(A[k]))
             if has_res:
                 blk.res_y, blk.x_out, blk.x_out_op = ptr(A["res_y"]), ptr(A["x_out"]), ptr(A["x_out_op"])
+            if quant:
+                blk.code1, blk.code3 = ptr(A["code1"]), ptr(A["code3"])
             check(L.fqss_tcn_block_fwd(C.byref(blk), s))
             st = BlockState()
             st.t, st.dil, st.first, st.has_res, st.prep, st.act, st.blk = t, dils[i], first, has_res, P, A, blk
