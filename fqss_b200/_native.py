@@ -65,6 +65,9 @@ _SIGS = {
     "fqss_pw_gemm_ex": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i32, vp]),
     "fqss_split_bf16": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, vp]),
     "fqss_tcn_prep": (i32, [vp] * 11 + [i32] * 5 + [vp]),
+    "fqss_rowscale_bf16": (i32, [vp, i64, vp, i64, i64, i32, i32, vp, vp, vp]),
+    "fqss_wgrad_codes_ws_bytes": (sz, [i32, i32, i32, i32]),
+    "fqss_wgrad_codes": (i32, [vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
     "fqss_tcn_encode": (i32, [vp, i64, vp, i64, i64, i32, vp, vp, vp]),
     "fqss_tcn_block_fwd": (i32, [vp, vp]),
     "fqss_tcn_block_bwd": (i32, [vp, vp, vp]),
@@ -101,7 +104,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 7:
+                if L.fqss_abi_version() != 8:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

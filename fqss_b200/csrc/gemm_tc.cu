@@ -423,7 +423,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, c
     int grid = num_sms();
     if (grid > tiles) grid = tiles;
     static const char* const names[] = {"gemm_store", "gemm_expand", "gemm_resskip", "gemm_dgrad_bf16", "gemm_dgrad_add", "gemm_relu_mul"};
-    FQSS_PROF(a.a_rows > 0 ? (EPI == EPI_EXPAND ? "gemm_expand(split3)" : EPI == EPI_RESSKIP ? "gemm_resskip(split3)" : EPI == EPI_RELU_MUL ? "gemm_relu_mul(split3)" : "gemm_store(split3)") : names[EPI], s);
+    FQSS_PROF((a.a_rows > 0 && a.a_rows < a.K) ? (EPI == EPI_EXPAND ? "gemm_expand(split3)" : EPI == EPI_RESSKIP ? "gemm_resskip(split3)" : EPI == EPI_RELU_MUL ? "gemm_relu_mul(split3)" : "gemm_store(split3)") : names[EPI], s);
     pw_gemm_kernel<NT, EPI><<<grid, NUM_THREADS, smem, s>>>(ta, tb, a);
     return check_launch("pw_gemm");
 }

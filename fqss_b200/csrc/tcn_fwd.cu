@@ -291,6 +291,41 @@ __global__ void __launch_bounds__(ROW_THREADS) split_bf16_kernel(const float* __
     }
 }
 
+// out[r][m] = bf16(scale[r % C] * g[r][m]), rowsum[r % C] += sum_m g[r][m] (fp64, unscaled): turns an fp32 output
+// gradient into the pre-scaled bf16 operand of the dgrad / wgrad GEMMs of a code-operand 1x1 conv and its bias grad
+__global__ void __launch_bounds__(ROW_THREADS) rowscale_bf16_kernel(const float* __restrict__ g, int64_t ldg, __nv_bfloat16* __restrict__ out,
+                                                                   int64_t ldo, int M, int C, const float* __restrict__ scale,
+                                                                   double* __restrict__ rowsum) {
+    __shared__ double sh[32];
+    const int64_t r = blockIdx.x;
+    const int ch = (int)(r % C);
+    const float sc = __ldg(scale + ch);
+    const float4* src = reinterpret_cast<const float4*>(g + r * ldg);
+    uint2* dst = reinterpret_cast<uint2*>(out + r * ldo);
+    float s = 0.f;
+    const int nfull = M >> 2;
+    for (int v = threadIdx.x; v < nfull; v += ROW_THREADS) {
+        const float4 x = ldg4_stream(reinterpret_cast<const float*>(src + v));
+        s += (x.x + x.y) + (x.z + x.w);
+        dst[v] = float4_to_bf16x4(x.x * sc, x.y * sc, x.z * sc, x.w * sc);
+    }
+    if ((M & 3) && (int)threadIdx.x == (nfull & (ROW_THREADS - 1))) {
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int k = 0; k < (M & 3); ++k) x[k] = g[r * ldg + 4 * nfull + k];
+        s += (x[0] + x[1]) + (x[2] + x[3]);
+        dst[nfull] = float4_to_bf16x4(x[0] * sc, x[1] * sc, x[2] * sc, x[3] * sc);
+    }
+    double v[1] = {(double)warp_sum(s)};
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sh[wid] = v[0];
+    __syncthreads();
+    if (threadIdx.x == 0 && rowsum) {
+        double t = 0.0;
+        for (int w = 0; w < ROW_THREADS / 32; ++w) t += sh[w];
+        atomicAdd(rowsum + ch, t);
+    }
+}
+
 // values -> GEMM operand of the first block: integer code w.r.t. the producer's quantiser, or the value itself
 __global__ void __launch_bounds__(ROW_THREADS) tcn_encode_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out,
                                                                 int64_t ldo, int M, const float* rmin, const float* rmax) {
@@ -362,6 +397,18 @@ int fqss_split_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, in
     FQSS_PROF("split_bf16", stream);
     split_bf16_kernel<<<(unsigned)rows, ROW_THREADS, 0, (cudaStream_t)stream>>>(x, ldx, (__nv_bfloat16*)out_bf16, ldo, cols, C, layout);
     return check_launch("split_bf16");
+}
+
+int fqss_rowscale_bf16(const float* g, int64_t ldg, void* out_bf16, int64_t ldo, int64_t rows, int M, int C, const float* scale,
+                       double* rowsum, void* stream) {
+    FQSS_REQUIRE(g && out_bf16 && scale && rows > 0 && M > 0 && C > 0 && rows % C == 0, -1, "rowscale_bf16: bad argument");
+    FQSS_REQUIRE(ldg >= M && ldo >= ((M + 3) & ~3) && ldg % 4 == 0 && ldo % 4 == 0 && aligned16(g) && aligned16(out_bf16), -2,
+                 "rowscale_bf16: rows must be 16-byte aligned with room for whole quads");
+    cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("rowscale_bf16", s, 1);
+    if (rowsum) cudaMemsetAsync(rowsum, 0, (size_t)C * sizeof(double), s);
+    rowscale_bf16_kernel<<<(unsigned)rows, ROW_THREADS, 0, s>>>(g, ldg, (__nv_bfloat16*)out_bf16, ldo, M, C, scale, rowsum);
+    return check_launch("rowscale_bf16");
 }
 
 int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {

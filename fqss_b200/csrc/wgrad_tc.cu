@@ -279,3 +279,19 @@ int run(const void* dY, const void* X, int B, int M, int64_t ld, int O, int I, f
 
 }  // namespace tcw
 }  // namespace fqss
+
+using namespace fqss;
+
+extern "C" {
+
+size_t fqss_wgrad_codes_ws_bytes(int B, int M, int O, int I) { return tcw::part_bytes(B, M, O, I) + 256; }
+
+// Weight gradient of a code-operand 1x1 conv (see fqss.h).
+int fqss_wgrad_codes(const void* dY_bf16, const void* x_op_bf16, int B, int M, int64_t ld, int O, int I, const float* amin,
+                     const float* amax, const float* dws, const double* db, float* dWq, void* ws, size_t ws_bytes, void* stream) {
+    FQSS_REQUIRE(ws && ws_bytes >= fqss_wgrad_codes_ws_bytes(B, M, O, I), -3, "wgrad_codes: workspace too small");
+    float* part = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+    return tcw::run(dY_bf16, x_op_bf16, B, M, ld, O, I, part, ws_bytes - 256, amin, amax, dws, db, dWq, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -73,8 +73,8 @@ class MaskGenerator(nn.Module):
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         batch = x.shape[0]
-        feats = self.bottleneck(x)
         from ... import tcn_engine as E
+        feats = self._conv_after(self.bottleneck[0], self.bottleneck[1], x, E)
         if self.use_fused and E.fused_eligible(self, feats):
             q = self.bottleneck[1].activation_fake_quantize
             adds = [None] + list(self.adds)
@@ -84,8 +84,22 @@ class MaskGenerator(nn.Module):
             for i, block in enumerate(self.TCN[1:]):
                 feats, skip = block(feats)
                 total = self.adds[i](total, skip)
-        out = self.mask_net(total)
+        out = self._conv_after(self.mask_net[0], self.mask_net[1], total, E)
+        out = self.mask_net[2](out)          # Identity after quantize_model (the ReLU moved into mask_net[1])
         return out.reshape(batch, self.n_srcs, self.input_dim, -1)
+
+    def _conv_after(self, first, conv_layer, x, E):
+        """conv_layer(first(x)); when `first` ends in an 8-bit activation quantiser and `conv_layer` is a quantised 1x1
+        conv in steady state, the conv runs on the tensor cores with integer-code operands."""
+        h = first(x)
+        q_in = getattr(first, "activation_fake_quantize", None)
+        if self.use_fused and q_in is not None and E.code_conv_eligible(conv_layer, q_in, h):
+            from ..qat_layers import _nl_kind
+            y = E.code_conv(conv_layer, q_in, h)
+            conv_layer.calc_mac_op(h.shape)
+            kind, slope = _nl_kind(getattr(conv_layer, "nl", None))
+            return conv_layer._finish(kind, y, slope=slope)
+        return conv_layer(h)
 
 
 class ConvTasNetQ(nn.Module):

@@ -238,6 +238,86 @@ def _as_pitched(x, ld):
     return buf[:, :, :M]
 
 
+class CodeConv1x1(Function):
+    """1x1 conv whose input is the output of an 8-bit activation quantiser and whose weight is fake-quantised per output
+    channel (the bottleneck and mask convs, qat_layers.py:137-141, 202-207): both operands become integer codes on the
+    tcgen05 GEMM, exactly as inside the ConvBlocks.  Returns the pre-activation y = conv(x, FQ(W)) + bias (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, qmin, qmax, W, wmin, wmax, bias):
+        N.require_cuda(x, qmin, qmax, W, wmin, wmax, bias)
+        L = _libx()
+        B, Ci, M = x.shape
+        Co = W.shape[0]
+        ld = (M + 7) // 8 * 8
+        dev = x.device
+        s = stream_ptr()
+        xv = _as_pitched(x.detach(), ld)
+        x_op = torch.empty((B, Ci, ld), dtype=torch.bfloat16, device=dev)
+        check(L.fqss_tcn_encode(ptr(xv), ld, ptr(x_op), ld, B * Ci, M, ptr(qmin), ptr(qmax), s))
+        Wf = W.detach().reshape(Co, Ci)
+        bf = torch.bfloat16
+        Wc, WcT = torch.empty((Co, Ci), dtype=bf, device=dev), torch.empty((Ci, Co), dtype=bf, device=dev)
+        s1, s0, dws = torch.empty(Co, device=dev), torch.empty(Co, device=dev), torch.empty(Co, device=dev)
+        check(L.fqss_tcn_prep(ptr(Wf), ptr(wmin), ptr(wmax), ptr(bias) or None, ptr(qmin), ptr(qmax), ptr(Wc), ptr(WcT), ptr(s1),
+                              ptr(s0), ptr(dws), Co, Ci, Co, 0, 0, s))
+        y = pw_gemm(x_op, Wc, s1, s0, M)
+        ctx.save_for_backward(x_op, WcT, dws, W, wmin, wmax, qmin, qmax)
+        ctx.meta = (B, Ci, Co, M, ld, bias is not None)
+        return y[:, :, :M]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        L = _libx()
+        x_op, WcT, dws, W, wmin, wmax, qmin, qmax = ctx.saved_tensors
+        B, Ci, Co, M, ld, has_bias = ctx.meta
+        dev = gy.device
+        s = stream_ptr()
+        gy = _as_pitched(gy, ld)
+        dY = torch.empty((B, Co, ld), dtype=torch.bfloat16, device=dev)
+        db = torch.empty(Co, dtype=torch.float64, device=dev)
+        check(L.fqss_rowscale_bf16(ptr(gy), ld, ptr(dY), ld, B * Co, M, Co, ptr(dws), ptr(db), s))
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = pw_gemm(dY, WcT, torch.ones(Ci, device=dev), torch.zeros(Ci, device=dev), M)[:, :, :M]
+        dWq = torch.empty((Co, Ci), device=dev)
+        ws = torch.empty(int(L.fqss_wgrad_codes_ws_bytes(B, M, Co, Ci)), dtype=torch.uint8, device=dev)
+        check(L.fqss_wgrad_codes(ptr(dY), ptr(x_op), B, M, ld, Co, Ci, ptr(qmin), ptr(qmax), ptr(dws), ptr(db), ptr(dWq), ptr(ws),
+                                 ws.numel(), s))
+        gW = torch.empty_like(W, memory_format=torch.contiguous_format)
+        gwmin, gwmax = torch.empty_like(wmin), torch.empty_like(wmax)
+        check(lib().fqss_fq_weight_bwd(ptr(dWq), ptr(W), ptr(gW), ptr(gwmin), ptr(gwmax), 1, Co, Ci, ptr(wmin), ptr(wmax), 8, s))
+        return gx, None, None, gW, gwmin, gwmax, (db.float() if has_bias else None)
+
+
+def code_conv_eligible(layer, q_in, x):
+    """True when a Conv1dQ / Conv1dNlQ fed by activation quantiser `q_in` can run as a code-operand tcgen05 GEMM."""
+    from .qat import qat_layers as QL
+    from .qat.qat_quant import GradientActivationFakeQuantize as AQ, GradientWeightFakeQuantize as WQm
+    if not isinstance(layer, (QL.Conv1dQ, QL.Conv1dNlQ)) or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3:
+        return False
+    conv, wq = layer.conv1d, layer.weight_fake_quantize
+    if conv.kernel_size[0] != 1 or conv.stride[0] != 1 or conv.padding[0] != 0 or conv.groups != 1:
+        return False
+    if not isinstance(wq, WQm) or wq.observer_mode or wq.n_bits != 8 or wq.min_range.numel() != conv.out_channels:
+        return False
+    if not isinstance(q_in, AQ) or q_in.observing() or q_in.n_bits != 8:
+        return False
+    return conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0 and conv.out_channels <= 1024 \
+        and W_contig(conv.weight)
+
+
+def W_contig(w):
+    return w.is_contiguous()
+
+
+def code_conv(layer, q_in, x):
+    """conv part of `layer.forward(x)` on the code-operand GEMM (caller applies the layer's nl + activation quantiser)."""
+    conv, wq = layer.conv1d, layer.weight_fake_quantize
+    return CodeConv1x1.apply(x, q_in.min_range, q_in.max_range, conv.weight, wq.min_range, wq.max_range, conv.bias)
+
+
 class FusedTCNFunction(Function):
     @staticmethod
     def forward(ctx, x, skip_in, meta, *flat):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 7
+#define FQSS_ABI_VERSION 8
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -174,6 +174,22 @@ int fqss_pw_gemm_ex(const void* act_bf16, const void* w_bf16, const float* s1, c
  *   layout 1 (activations [B][C][M]): out [B][2C][ldo] = per sample [hi rows ; lo rows]  (rows = B*C, cols = M) */
 int fqss_split_bf16(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int cols, int C, int layout,
                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Code-operand 1x1 convolution outside the ConvBlocks (bottleneck conv, mask conv: convtasnetq.py:67-70,
+ * 97-99 as Conv1dQ / Conv1dNlQ, qat_layers.py:137-141, 202-207): the input is the output of an 8-bit
+ * activation quantiser, so it is re-encoded to integer codes (fqss_tcn_encode), the weights are prepared by
+ * fqss_tcn_prep and the product runs on fqss_pw_gemm.  Backward:
+ *   fqss_rowscale_bf16: dY[b,o,m] = bf16(dws[o] * gy[b,o,m]), db[o] = sum gy (fp64; may be NULL)
+ *   input gradient    : fqss_pw_gemm(dY, WcT, ones, zeros) -- gx[b,i,m] = sum_o code_w[o,i] dY[b,o,m]
+ *   fqss_wgrad_codes  : dWq[o,i] = (delta_a * sum_{b,m} dY[b,o,m] code_a[b,i,m]) / dws[o] + min_a * db[o]
+ *                       (gradient w.r.t. the FAKE-QUANTISED weight; feed it to fqss_fq_weight_bwd)
+ * ------------------------------------------------------------------------------------------- */
+int fqss_rowscale_bf16(const float* g, int64_t ldg, void* out_bf16, int64_t ldo, int64_t rows, int M, int C, const float* scale,
+                       double* rowsum, void* stream);
+size_t fqss_wgrad_codes_ws_bytes(int B, int M, int O, int I);
+int fqss_wgrad_codes(const void* dY_bf16, const void* x_op_bf16, int B, int M, int64_t ld, int O, int I, const float* amin,
+                     const float* amax, const float* dws, const double* db, float* dWq, void* ws, size_t ws_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * M1  fused ConvBlock of the TCN (convtasnetq.py:11-42 after quantize_model :270-277), forward and

@@ -239,3 +239,38 @@ def test_float_teacher_engine_vs_torch_and_oracle():
         model.masker.TCN[1].res_conv.weight.mul_(1.5)
         got3 = model(mix)
     assert rel(got3, got) > 1e-4
+
+
+def test_code_conv1x1_vs_torch():
+    """Bottleneck / mask 1x1 convs on integer-code operands (tcn_engine.CodeConv1x1) against the fp32 definition
+    conv1d(x, FQ_w(W)) + b with autograd through the weight quantiser (qat_quant.py:126-135)."""
+    import torch.nn.functional as F
+    from fqss_b200 import tcn_engine as E
+    torch.manual_seed(3)
+    B, Ci, Co, M = 3, 128, 256, 1003
+    qmin, qmax = torch.tensor([-1.3], device=DEV), torch.tensor([2.1], device=DEV)
+    delta = torch.div(qmax - qmin, torch.full_like(qmax, 255.0))
+    codes = torch.randint(0, 256, (B, Ci, M), device=DEV).float()
+    x = (delta * codes + qmin).requires_grad_(True)                   # values on the input quantiser's grid
+    W = (torch.randn(Co, Ci, 1, device=DEV) * 0.1).requires_grad_(True)
+    bias = (torch.randn(Co, device=DEV) * 0.1).requires_grad_(True)
+    wmax = W.detach().amax(dim=(1, 2), keepdim=True).clone().requires_grad_(True)
+    wmin = W.detach().amin(dim=(1, 2), keepdim=True).clone().requires_grad_(True)
+    y = E.CodeConv1x1.apply(x, qmin, qmax, W, wmin, wmax, bias)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    got = dict(y=y.detach(), gx=x.grad.clone(), gW=W.grad.clone(), gb=bias.grad.clone(), gmin=wmin.grad.clone(), gmax=wmax.grad.clone())
+    for t in (x, W, bias, wmin, wmax):
+        t.grad = None
+    # fp32 definition (torch autograd through the reference weight-quantiser arithmetic)
+    a = torch.maximum(wmin.abs(), wmax.abs())
+    dl = torch.div(2 * a, torch.full_like(a, 255.0))   # true division as on the CPU oracle (CUDA eager folds x / scalar to x * (1/scalar))
+    t = W / dl
+    Wq = dl * torch.clamp(t + (torch.round(t) - t).detach(), -128, 127)
+    yr = F.conv1d(x.double(), Wq.double(), bias.double()).float()
+    yr.backward(gy)
+    assert rel(got["y"], yr) < 1e-5, rel(got["y"], yr)
+    assert rel(got["gx"], x.grad) < 1e-2, rel(got["gx"], x.grad)        # bf16 gradient operand tier
+    assert rel(got["gW"], W.grad) < 1e-2, rel(got["gW"], W.grad)
+    assert rel(got["gb"], bias.grad) < 1e-4
+    assert rel(got["gmin"], wmin.grad) < 2e-2 and rel(got["gmax"], wmax.grad) < 2e-2, (rel(got["gmin"], wmin.grad), rel(got["gmax"], wmax.grad))
