@@ -12,8 +12,30 @@ namespace fqss {
 
 int num_sms();
 
+// float per-thread partials -> warp sums in fp32 -> cross-warp sums in fp64 (valid in thread 0); sh: 5*32 doubles
+__device__ __forceinline__ void block_sum_fd5(const float (&s)[5], double (&v)[5], double* sh) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    float w[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) w[i] = warp_sum(s[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) sh[i * 32 + wid] = (double)w[i];
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            double x = lane < nw ? sh[i * 32 + lane] : 0.0;
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
 constexpr int PW_THREADS = 256;
-constexpr int PW_CHUNK = PW_THREADS * 4;
+constexpr int PW_QUADS = 4;                               // frame quads per thread
+constexpr int PW_CHUNK = PW_THREADS * 4 * PW_QUADS;       // elements of one row handled by one CTA
 
 struct RowCtx {
     float slope;          // PReLU
@@ -22,18 +44,23 @@ struct RowCtx {
     float gamma;
 };
 
-__device__ __forceinline__ void gln_row_consts(const fqss_pw_desc& d, int64_t row, RowCtx& c) {
-    const int64_t b = row / d.C;
-    const int ch = (int)(row - b * d.C);
-    const double N = (double)d.C * (double)d.cols;
-    const double mean = d.stats[2 * b] / N;
-    double var = d.stats[2 * b + 1] / N - mean * mean;
-    var = var > 0.0 ? var : 0.0;
-    c.mu = (float)mean;
-    c.rstd = (float)(1.0 / sqrt(var + (double)d.eps));
-    c.gamma = __ldg(d.gamma + ch);
-    c.scale = __fmul_rn(c.rstd, c.gamma);                              // ATen group_norm: scale = rstd*gamma
-    c.shift = __fadd_rn(__fmul_rn(-c.scale, c.mu), __ldg(d.beta + ch));   //                bias = -scale*mean + beta
+// Per-row gLN constants: fp64 mean / variance by ONE thread, broadcast through shared memory (contains a barrier).
+__device__ __forceinline__ void gln_row_consts(const fqss_pw_desc& d, int64_t row, RowCtx& c, float* sh5) {
+    if (threadIdx.x == 0) {
+        const int64_t b = row / d.C;
+        const int ch = (int)(row - b * d.C);
+        const double N = (double)d.C * (double)d.cols;
+        const double mean = d.stats[2 * b] / N;
+        double var = d.stats[2 * b + 1] / N - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        const float mu = (float)mean, rstd = (float)(1.0 / sqrt(var + (double)d.eps));
+        const float gamma = __ldg(d.gamma + ch);
+        const float scale = __fmul_rn(rstd, gamma);                          // ATen group_norm: scale = rstd*gamma
+        sh5[0] = mu; sh5[1] = rstd; sh5[2] = gamma; sh5[3] = scale;
+        sh5[4] = __fadd_rn(__fmul_rn(-scale, mu), __ldg(d.beta + ch));       //                bias = -scale*mean + beta
+    }
+    __syncthreads();
+    c.mu = sh5[0]; c.rstd = sh5[1]; c.gamma = sh5[2]; c.scale = sh5[3]; c.shift = sh5[4];
 }
 
 template <int KIND>
@@ -59,49 +86,66 @@ __device__ __forceinline__ int64_t x2_row(const fqss_pw_desc& d, int64_t row) {
 template <int KIND>
 __host__ __device__ constexpr bool pw_binary() { return KIND == FQSS_PW_ADD || KIND == FQSS_PW_SUB || KIND == FQSS_PW_MUL; }
 
-// ---------------------------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------------------------
-template <int KIND, bool VEC>
-__global__ void __launch_bounds__(PW_THREADS) pw_fwd_kernel(const fqss_pw_desc d) {
-    const int64_t row = blockIdx.x;
-    const int64_t c0 = (int64_t)blockIdx.y * PW_CHUNK + threadIdx.x * 4;
-    if (c0 >= d.cols) return;
-    RowCtx rc;
-    if (KIND == FQSS_PW_PRELU) rc.slope = __ldg(d.slope);
-    if (KIND == FQSS_PW_GLN) gln_row_consts(d, row, rc);
-    ActQ q;
-    if (d.quant) q = load_actq(d.rmin, d.rmax, d.n_bits);
-    const float* p1 = d.x1 + row * d.ld1 + c0;
-    const float* p2 = pw_binary<KIND>() ? d.x2 + x2_row<KIND>(d, row) * d.ld2 + c0 : nullptr;
-    float* py = d.y + row * d.ldy + c0;
-    float a[4], b[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
-    const int nv = (int)min((int64_t)4, d.cols - c0);
-    if (VEC) {
-        float4 v = ldg4(p1);
+// backward through the quantiser, bit-identical to the reference's autograd chain ((g*delta)*mask)/delta, with the
+// division-free exact quotient; accumulates sD += g*(in ? X - t : clip(X)), sZ += g*(1 - in)
+__device__ __forceinline__ float pw_fq_bwd(const ActQF& q, float z, float g, float& sD, float& sZ) {
+    const float t = actqf_t(q, z);
+    const bool in = actqf_inside(q, t);
+    const float c = actqf_unbias(actqf_biased(q, t));
+    sD = fmaf(g, in ? __fsub_rn(c, t) : c, sD);
+    sZ += in ? 0.f : g;
+    return in ? exact_div(__fmul_rn(g, q.delta), q.delta, q.inv) : 0.f;
+}
+
+__device__ __forceinline__ void ld_quad(const float* p, int nv, bool vec, float (&a)[4]) {
+    if (vec) {
+        const float4 v = ldg4(p);
         a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-        if (pw_binary<KIND>()) {
-            float4 w = ldg4(p2);
-            b[0] = w.x; b[1] = w.y; b[2] = w.z; b[3] = w.w;
-        }
     } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            a[k] = k < nv ? p1[k] : 0.f;
-            if (pw_binary<KIND>()) b[k] = k < nv ? p2[k] : 0.f;
-        }
+        for (int k = 0; k < 4; ++k) a[k] = k < nv ? p[k] : 0.f;
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float z = pw_z<KIND>(a[k], b[k], rc);
-        o[k] = d.quant ? actq_fq(q, z) : z;
-    }
-    if (VEC) {
-        stg4(py, make_float4(o[0], o[1], o[2], o[3]));      // pad columns (< ld) may be written: don't-care
+}
+__device__ __forceinline__ void st_quad(float* p, int nv, bool vec, const float (&a)[4]) {
+    if (vec) {
+        stg4(p, make_float4(a[0], a[1], a[2], a[3]));      // pad columns (< ld) may be written: don't-care
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (k < nv) py[k] = o[k];
+            if (k < nv) p[k] = a[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward: one CTA = PW_CHUNK consecutive elements of one row (4 quads per thread)
+// ---------------------------------------------------------------------------------------------
+template <int KIND, bool VEC>
+__global__ void __launch_bounds__(PW_THREADS) pw_fwd_kernel(const fqss_pw_desc d) {
+    __shared__ float sh5[5];
+    const int64_t row = blockIdx.x;
+    const int64_t chunk0 = (int64_t)blockIdx.y * PW_CHUNK;
+    RowCtx rc;
+    if (KIND == FQSS_PW_PRELU) rc.slope = __ldg(d.slope);
+    if (KIND == FQSS_PW_GLN) gln_row_consts(d, row, rc, sh5);
+    ActQF q;
+    if (d.quant) q = load_actqf(d.rmin, d.rmax, d.n_bits);
+    const float* r1 = d.x1 + row * d.ld1;
+    const float* r2 = pw_binary<KIND>() ? d.x2 + x2_row<KIND>(d, row) * d.ld2 : nullptr;
+    float* ry = d.y + row * d.ldy;
+#pragma unroll
+    for (int qd = 0; qd < PW_QUADS; ++qd) {
+        const int64_t c0 = chunk0 + ((int64_t)qd * PW_THREADS + threadIdx.x) * 4;
+        if (c0 >= d.cols) break;
+        const int nv = (int)min((int64_t)4, d.cols - c0);
+        float a[4], b[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
+        ld_quad(r1 + c0, nv, VEC, a);
+        if (pw_binary<KIND>()) ld_quad(r2 + c0, nv, VEC, b);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float z = pw_z<KIND>(a[k], b[k], rc);
+            o[k] = d.quant ? actqf_fq(q, z) : z;
+        }
+        st_quad(ry + c0, nv, VEC, o);
     }
 }
 
@@ -115,90 +159,66 @@ __global__ void __launch_bounds__(PW_THREADS) pw_bwd_kernel(const fqss_pw_desc d
                                                            double* __restrict__ acc, double* __restrict__ rowacc,
                                                            const double* __restrict__ samp) {
     __shared__ double sh[5 * 32];
+    __shared__ float sh5[5];
     const int64_t row = blockIdx.x;
-    const int64_t c0 = (int64_t)blockIdx.y * PW_CHUNK + threadIdx.x * 4;
-    const bool active = c0 < d.cols;
+    const int64_t chunk0 = (int64_t)blockIdx.y * PW_CHUNK;
     RowCtx rc;
     if (KIND == FQSS_PW_PRELU) rc.slope = __ldg(d.slope);
-    if (KIND == FQSS_PW_GLN) gln_row_consts(d, row, rc);
-    ActQ q;
-    if (d.quant) q = load_actq(d.rmin, d.rmax, d.n_bits);
-    float sD = 0.f, sZ = 0.f, sS = 0.f, r1 = 0.f, r2 = 0.f;
-    if (active) {
-        const int nv = (int)min((int64_t)4, d.cols - c0);
-        const float* p1 = d.x1 + row * d.ld1 + c0;
-        const float* p2 = pw_binary<KIND>() ? d.x2 + x2_row<KIND>(d, row) * d.ld2 + c0 : nullptr;
-        const float* pg = o.g + row * o.ldg + c0;
-        float a[4], b[4] = {0.f, 0.f, 0.f, 0.f}, g[4], g1[4], g2[4];
-        if (VEC) {
-            float4 v = ldg4(p1), w = ldg4(pg);
-            a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-            g[0] = w.x; g[1] = w.y; g[2] = w.z; g[3] = w.w;
-            if (pw_binary<KIND>()) {
-                float4 u = ldg4(p2);
-                b[0] = u.x; b[1] = u.y; b[2] = u.z; b[3] = u.w;
-            }
-        } else {
+    if (KIND == FQSS_PW_GLN) gln_row_consts(d, row, rc, sh5);
+    ActQF q;
+    if (d.quant) q = load_actqf(d.rmin, d.rmax, d.n_bits);
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};       // sD, sZ, slope, r1, r2
+    float S1 = 0.f, S2 = 0.f, invN = 0.f;
+    if (KIND == FQSS_PW_GLN && PHASE == 2) {
+        const int64_t bs = row / d.C;
+        invN = __fdividef(1.f, (float)d.C * (float)d.cols);
+        S1 = (float)samp[2 * bs];
+        S2 = (float)samp[2 * bs + 1];
+    }
+    const float* r1 = d.x1 + row * d.ld1;
+    const float* r2 = pw_binary<KIND>() ? d.x2 + x2_row<KIND>(d, row) * d.ld2 : nullptr;
+    const float* rg = o.g + row * o.ldg;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                a[k] = k < nv ? p1[k] : 0.f;
-                g[k] = k < nv ? pg[k] : 0.f;
-                if (pw_binary<KIND>()) b[k] = k < nv ? p2[k] : 0.f;
-            }
-        }
-        float S1 = 0.f, S2 = 0.f, invN = 0.f;
-        if (KIND == FQSS_PW_GLN && PHASE == 2) {
-            const int64_t bs = row / d.C;
-            invN = (float)(1.0 / ((double)d.C * (double)d.cols));
-            S1 = (float)samp[2 * bs];
-            S2 = (float)samp[2 * bs + 1];
-        }
+    for (int qd = 0; qd < PW_QUADS; ++qd) {
+        const int64_t c0 = chunk0 + ((int64_t)qd * PW_THREADS + threadIdx.x) * 4;
+        if (c0 >= d.cols) break;
+        const int nv = (int)min((int64_t)4, d.cols - c0);
+        float a[4], b[4] = {0.f, 0.f, 0.f, 0.f}, g[4], g1[4], g2[4];
+        ld_quad(r1 + c0, nv, VEC, a);
+        ld_quad(rg + c0, nv, VEC, g);
+        if (pw_binary<KIND>()) ld_quad(r2 + c0, nv, VEC, b);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const bool valid = k < nv;
             if (!valid) { a[k] = 0.f; b[k] = 0.f; }          // pad columns may hold NaN garbage
-            float z = pw_z<KIND>(a[k], b[k], rc);
-            float gk = valid ? g[k] : 0.f;
+            const float z = pw_z<KIND>(a[k], b[k], rc);
+            const float gk = valid ? g[k] : 0.f;
             float dsD = 0.f, dsZ = 0.f;
-            float gz = d.quant ? actq_bwd(q, z, gk, dsD, dsZ) : gk;
-            if (valid && PHASE != 2) { sD += dsD; sZ += dsZ; }
+            float gz = d.quant ? pw_fq_bwd(q, z, gk, dsD, dsZ) : gk;
+            if (valid && PHASE != 2) { s[0] += dsD; s[1] += dsZ; }
             if (!valid) gz = 0.f;
             if (KIND == FQSS_PW_IDENT || KIND == FQSS_PW_ADD) g1[k] = gz;
             if (KIND == FQSS_PW_SUB) { g1[k] = gz; g2[k] = -gz; }
             if (KIND == FQSS_PW_PRELU) {
                 g1[k] = a[k] > 0.f ? gz : rc.slope * gz;
-                sS += a[k] > 0.f ? 0.f : a[k] * gz;
+                s[2] += a[k] > 0.f ? 0.f : a[k] * gz;
             }
             if (KIND == FQSS_PW_RELU) g1[k] = a[k] > 0.f ? gz : 0.f;
             if (KIND == FQSS_PW_MUL) { g1[k] = gz * b[k]; g2[k] = gz * a[k]; }
             if (KIND == FQSS_PW_GLN) {
-                float xh = (a[k] - rc.mu) * rc.rstd;
-                if (PHASE == 1) { r1 += gz; r2 += gz * xh; }
+                const float xh = (a[k] - rc.mu) * rc.rstd;
+                if (PHASE == 1) { s[3] += gz; s[4] += gz * xh; }
                 if (PHASE == 2) g1[k] = rc.rstd * (rc.gamma * gz - (S1 + xh * S2) * invN);
             }
         }
         if (PHASE != 1) {
-            if (o.gx1) {
-                float* q1 = o.gx1 + row * o.ldg1 + c0;
-                if (VEC) stg4(q1, make_float4(g1[0], g1[1], g1[2], g1[3]));
-                else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (k < nv) q1[k] = g1[k];
-                }
-            }
-            if (KIND == FQSS_PW_SUB && o.gx2) {
-                float* q2 = o.gx2 + row * o.ldg2 + c0;
-                if (VEC) stg4(q2, make_float4(g2[0], g2[1], g2[2], g2[3]));
-                else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (k < nv) q2[k] = g2[k];
-                }
-            }
+            if (o.gx1) st_quad(o.gx1 + row * o.ldg1 + c0, nv, VEC, g1);
+            if (KIND == FQSS_PW_SUB && o.gx2) st_quad(o.gx2 + row * o.ldg2 + c0, nv, VEC, g2);
         }
     }
     if (PHASE == 2) return;
-    double v[5] = {(double)sD, (double)sZ, (double)sS, (double)r1, (double)r2};
-    block_sum<5>(v, sh);
+    double v[5];
+    block_sum_fd5(s, v, sh);
     if (threadIdx.x == 0) {
         if (d.quant) { atomicAdd(acc + 0, v[0]); atomicAdd(acc + 1, v[1]); }
         if (KIND == FQSS_PW_PRELU) atomicAdd(acc + 2, v[2]);
@@ -211,50 +231,43 @@ __global__ void __launch_bounds__(PW_THREADS) pw_bwd_kernel(const fqss_pw_desc d
 template <bool VEC>
 __global__ void __launch_bounds__(PW_THREADS) pw_mul_bwd_kernel(const fqss_pw_desc d, const fqss_pw_grads o,
                                                                double* __restrict__ acc) {
-    __shared__ double sh[2 * 32];
+    __shared__ double sh[5 * 32];
     const int64_t row2 = blockIdx.x;                         // (b, c)
-    const int64_t c0 = (int64_t)blockIdx.y * PW_CHUNK + threadIdx.x * 4;
-    ActQ q;
-    if (d.quant) q = load_actq(d.rmin, d.rmax, d.n_bits);
-    float sD = 0.f, sZ = 0.f;
-    if (c0 < d.cols) {
-        const int nv = (int)min((int64_t)4, d.cols - c0);
-        const int64_t bs = row2 / d.C, ch = row2 - bs * d.C;
-        float b[4], s2[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* p2 = d.x2 + row2 * d.ld2 + c0;
+    const int64_t chunk0 = (int64_t)blockIdx.y * PW_CHUNK;
+    ActQF q;
+    if (d.quant) q = load_actqf(d.rmin, d.rmax, d.n_bits);
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const int64_t bs = row2 / d.C, ch = row2 - bs * d.C;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) b[k] = (VEC || k < nv) ? p2[k] : 0.f;
-        for (int s = 0; s < d.bcast; ++s) {
-            const int64_t row1 = (bs * d.bcast + s) * d.C + ch;
-            const float* p1 = d.x1 + row1 * d.ld1 + c0;
-            const float* pg = o.g + row1 * o.ldg + c0;
-            float g1[4];
+    for (int qd = 0; qd < PW_QUADS; ++qd) {
+        const int64_t c0 = chunk0 + ((int64_t)qd * PW_THREADS + threadIdx.x) * 4;
+        if (c0 >= d.cols) break;
+        const int nv = (int)min((int64_t)4, d.cols - c0);
+        float b[4], s2[4] = {0.f, 0.f, 0.f, 0.f};
+        ld_quad(d.x2 + row2 * d.ld2 + c0, nv, VEC, b);
+        for (int sidx = 0; sidx < d.bcast; ++sidx) {
+            const int64_t row1 = (bs * d.bcast + sidx) * d.C + ch;
+            float a[4], g[4], g1[4];
+            ld_quad(d.x1 + row1 * d.ld1 + c0, nv, VEC, a);
+            ld_quad(o.g + row1 * o.ldg + c0, nv, VEC, g);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const bool valid = k < nv;
-                float a = (VEC || valid) ? p1[k] : 0.f;
-                float gk = valid ? pg[k] : 0.f;
-                float z = __fmul_rn(a, b[k]);
+                const float ak = valid ? a[k] : 0.f, bk = valid ? b[k] : 0.f;
+                const float gk = valid ? g[k] : 0.f;
+                const float z = __fmul_rn(ak, bk);
                 float dsD = 0.f, dsZ = 0.f;
-                float gz = d.quant ? actq_bwd(q, z, gk, dsD, dsZ) : gk;
-                if (valid) { sD += dsD; sZ += dsZ; } else gz = 0.f;
-                g1[k] = gz * b[k];
-                s2[k] += gz * a;
+                float gz = d.quant ? pw_fq_bwd(q, z, gk, dsD, dsZ) : gk;
+                if (valid) { s[0] += dsD; s[1] += dsZ; } else gz = 0.f;
+                g1[k] = gz * bk;
+                s2[k] += gz * ak;
             }
-            if (o.gx1) {
-                float* q1 = o.gx1 + row1 * o.ldg1 + c0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) if (k < nv) q1[k] = g1[k];
-            }
+            if (o.gx1) st_quad(o.gx1 + row1 * o.ldg1 + c0, nv, VEC, g1);
         }
-        if (o.gx2) {
-            float* q2 = o.gx2 + row2 * o.ldg2 + c0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) if (k < nv) q2[k] = s2[k];
-        }
+        if (o.gx2) st_quad(o.gx2 + row2 * o.ldg2 + c0, nv, VEC, s2);
     }
-    double v[2] = {(double)sD, (double)sZ};
-    block_sum<2>(v, sh);
+    double v[5];
+    block_sum_fd5(s, v, sh);
     if (threadIdx.x == 0 && d.quant) { atomicAdd(acc + 0, v[0]); atomicAdd(acc + 1, v[1]); }
 }
 
@@ -304,27 +317,23 @@ __global__ void pw_finalize_kernel(const double* __restrict__ acc, float* g_rmin
 template <bool VEC>
 __global__ void __launch_bounds__(PW_THREADS) gln_stats_kernel(const float* __restrict__ x, int64_t cols, int64_t ld, int C,
                                                               double* __restrict__ stats) {
-    __shared__ double sh[2 * 32];
+    __shared__ double sh[5 * 32];
     const int64_t row = blockIdx.x;
-    const int64_t c0 = (int64_t)blockIdx.y * PW_CHUNK + threadIdx.x * 4;
-    float s = 0.f, ss = 0.f;
-    if (c0 < cols) {
-        const int nv = (int)min((int64_t)4, cols - c0);
-        const float* p = x + row * ld + c0;
-        float a[4];
-        if (VEC) {
-            float4 v = ldg4(p);
-            a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
-        } else {
+    const int64_t chunk0 = (int64_t)blockIdx.y * PW_CHUNK;
+    float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) a[k] = k < nv ? p[k] : 0.f;
-        }
+    for (int qd = 0; qd < PW_QUADS; ++qd) {
+        const int64_t c0 = chunk0 + ((int64_t)qd * PW_THREADS + threadIdx.x) * 4;
+        if (c0 >= cols) break;
+        const int nv = (int)min((int64_t)4, cols - c0);
+        float a[4];
+        ld_quad(x + row * ld + c0, nv, VEC, a);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (k < nv) { s += a[k]; ss = fmaf(a[k], a[k], ss); }
+            if (k < nv) { s[0] += a[k]; s[1] = fmaf(a[k], a[k], s[1]); }
     }
-    double v[2] = {(double)s, (double)ss};
-    block_sum<2>(v, sh);
+    double v[5];
+    block_sum_fd5(s, v, sh);
     if (threadIdx.x == 0) {
         atomicAdd(stats + 2 * (row / C), v[0]);
         atomicAdd(stats + 2 * (row / C) + 1, v[1]);
