@@ -182,6 +182,10 @@ __device__ __forceinline__ unsigned code_u8(float t) {
     asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(r) : "f"(t));
     return r;
 }
+// integer code (0..255) -> float without the conversion pipe: OR into the mantissa of 2^23, subtract 2^23 (exact)
+__device__ __forceinline__ float2 u8x2_to_float2(unsigned a, unsigned b) {
+    return __fadd2_rn(make_float2(__uint_as_float(a | 0x4B000000u), __uint_as_float(b | 0x4B000000u)), f2s(-8388608.f));
+}
 // STE mask of an 8-bit quantiser: inside <=> -0.5 <= t < 255.5 <=> 0 <= t + 0.5 < 256 (the sum is exact wherever it
 // could cross either bound; -0.5 -> +0 is inside, negatives have the sign bit set, NaN is outside): one unsigned compare
 __device__ __forceinline__ bool inside_u8(float t_plus_half) { return __float_as_uint(t_plus_half) < 0x43800000u; }

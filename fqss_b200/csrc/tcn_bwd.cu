@@ -344,76 +344,68 @@ __global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row.
-//   stage  y1 -> code1 (one byte per frame), g_y3 (bf16) -> fp32 row in shared memory with a zero halo of
-//          dw_pad(d) frames on both sides (predicate-free taps)
-//   fir    g_a2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d];  t2 = FQ2's pre-rounding value comes from one 32-bit table
-//          lookup on code1; code2, a2, the STE mask and the range weight follow arithmetically.  The tap gradients
-//          need only the centre a2:  dW_k = sum_m g[m] a2[m+(k-1)d] = sum_m a2[m] g[m-(k-1)d]  (zero halo), so a2 is
-//          never staged.
-// The float model keeps a2 and xhat1 of the row in shared memory instead of the code bytes.
+// D: depthwise backward + FQ2 backward + gLN1 row sums.  One CTA per row, streaming (no staging, no barrier in
+// the element loop):
+//   g_a2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]   -- the three taps of g_y3 (bf16) are read straight from global memory;
+//             the row is 8 KB, so the two shifted reads hit L1/L2 and DRAM still sees each byte once
+//   FQ2: t2 = pre-rounding value of FQ2 as a function of the saved code of a1 (one 32-bit table lookup); code2, a2,
+//             the STE mask and the range weight follow arithmetically (bit-identical to forward); xhat1 is one FMA
+//   taps:     dW_k = sum_m g[m] a2[m+(k-1)d] = sum_m a2[m] g[m-(k-1)d]  (g is zero outside [0,M)), so only the
+//             centre a2 is needed
+// The float model derives a2 / xhat1 from y1 directly.
 // ---------------------------------------------------------------------------------------------
 template <bool QUANT, int DMODE>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
-    extern __shared__ __align__(16) float dsm[];
     __shared__ double sh[8 * 32];
+    __shared__ float tabT[256];                       // QUANT: t2 = (gLN1(decode1(code1)) - min2) / delta2
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
-    const int M = p.M, d = p.dil, dpad = dw_pad(d);
-    const int ld = (int)p.ld;
-    const int rowlen = ld + 2 * dpad;
-    float* gyr = dsm + dpad;
-    float* tabT = dsm + rowlen;                                       // QUANT: t2 = (gLN1(decode1(code1)) - min2) / delta2
-    uint32_t* idx32 = reinterpret_cast<uint32_t*>(dsm + rowlen + 256);    // QUANT: ld code bytes
-    float* a2r = dsm + rowlen;                                        // float model: a2 row, then xhat1 row
-    float* xhr = a2r + ld;
+    const int M = p.M, d = p.dil;
     const Hidden1 h = load_hidden1(p, b, c);
-    for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
-        dsm[i] = 0.f;
-        gyr[ld + i] = 0.f;
+    if (QUANT) {
+        tabT[threadIdx.x] = actqf_t(h.q2, gln_apply(h.g, actqf_decode(h.q1, (float)threadIdx.x)));
+        __syncthreads();
     }
-    // frames of all-padding quads (ld - M >= 4) are never staged: the taps must still see zeros there
-    for (int i = ((M + 3) & ~3) + threadIdx.x; i < ld; i += ROW_THREADS) gyr[i] = 0.f;
-    if (QUANT) tabT[threadIdx.x] = actqf_t(h.q2, gln_apply(h.g, actqf_decode(h.q1, (float)threadIdx.x)));
     const float4* y1 = reinterpret_cast<const float4*>(p.y1 + r * p.ld);
     const uint32_t* c1 = reinterpret_cast<const uint32_t*>(p.code1 + r * p.ld);
-    const uint2* gy3 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld);
+    const __nv_bfloat16* gy3 = reinterpret_cast<const __nv_bfloat16*>(g.g_hid_b) + r * p.ld;
+    const uint2* gq = reinterpret_cast<const uint2*>(gy3);
+    const int nq = (M + 3) >> 2;                      // quads holding valid frames; the ragged one carries zeros beyond M
     const float slope = h.slope;
-    auto stage = [&](int v, auto tail_tag) {
-        constexpr bool TAIL = decltype(tail_tag)::value;
-        const float4 gi = bf16x4_to_float4(__ldg(gy3 + v));
-        float2 g01 = lo2(gi), g23 = hi2(gi);
-        if (QUANT) {
-            idx32[v] = __ldg(c1 + v);                         // saved code of a1: no need to touch y1
-        } else {
-            const float4 y = __ldg(y1 + v);
-            const float2 z01 = make_float2(prelu_f(y.x, slope), prelu_f(y.y, slope));
-            const float2 z23 = make_float2(prelu_f(y.z, slope), prelu_f(y.w, slope));
-            *reinterpret_cast<float4*>(a2r + 4 * v) = make_float4(gln_apply(h.g, z01.x), gln_apply(h.g, z01.y), gln_apply(h.g, z23.x), gln_apply(h.g, z23.y));
-            *reinterpret_cast<float4*>(xhr + 4 * v) = make_float4(gln_xhat(h.g, z01.x), gln_xhat(h.g, z01.y), gln_xhat(h.g, z23.x), gln_xhat(h.g, z23.y));
-        }
-        if (TAIL) mask_tail(g01, g23, M - 4 * v);
-        *reinterpret_cast<float4*>(gyr + 4 * v) = make_float4(g01.x, g01.y, g23.x, g23.y);
-    };
-    FQSS_ROW_LOOP(stage, M);
-    __syncthreads();
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
     const float2 xa1 = f2s(QUANT ? h.q1.delta * h.g.rstd : 0.f), xb1 = f2s(QUANT ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f);
     uint2* gn1o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    auto ldq = [&](int vq) -> float4 {
+        if (vq < 0 || vq >= nq) return make_float4(0.f, 0.f, 0.f, 0.f);
+        return bf16x4_to_float4(__ldg(gq + vq));
+    };
+    auto ld1 = [&](int m) -> float { return (m >= 0 && m < M) ? __bfloat162float(gy3[m]) : 0.f; };
     // b0 = sum ga2*D2, b1 = sum ga2*(1-m2), b2 = sum gn1, b3 = sum gn1*xhat1 | taps: d0,d1,d2 = sum a2*g[+d,0,-d], d3 = sum g
     float2 b0 = f2s(0.f), b1 = f2s(0.f), b2 = f2s(0.f), b3 = f2s(0.f), d0 = f2s(0.f), d1 = f2s(0.f), d2 = f2s(0.f), d3 = f2s(0.f);
-    auto fir = [&](int v, auto tail_tag) {
+    auto body = [&](int v, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        float4 gL, gC, gR;
-        dw_taps<DMODE>(gyr, v, d, gL, gC, gR);
         uint32_t packed = 0;
-        float4 aq = make_float4(0.f, 0.f, 0.f, 0.f), xq = aq;
-        if (QUANT) {
-            packed = idx32[v];
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (QUANT) packed = __ldg(c1 + v);
+        else y = __ldg(y1 + v);
+        const float4 gC = ldq(v);
+        float4 gL, gR;
+        if (DMODE == 0) {                      // d % 4 == 0: whole quads
+            gL = ldq(v - (d >> 2));
+            gR = ldq(v + (d >> 2));
+        } else if (DMODE == 1) {
+            const float4 a = ldq(v - 1), e = ldq(v + 1);
+            gL = make_float4(a.w, gC.x, gC.y, gC.z);
+            gR = make_float4(gC.y, gC.z, gC.w, e.x);
+        } else if (DMODE == 2) {
+            const float4 a = ldq(v - 1), e = ldq(v + 1);
+            gL = make_float4(a.z, a.w, gC.x, gC.y);
+            gR = make_float4(gC.z, gC.w, e.x, e.y);
         } else {
-            aq = *reinterpret_cast<const float4*>(a2r + 4 * v);
-            xq = *reinterpret_cast<const float4*>(xhr + 4 * v);
+            const int m = 4 * v;
+            gL = make_float4(ld1(m - d), ld1(m + 1 - d), ld1(m + 2 - d), ld1(m + 3 - d));
+            gR = make_float4(ld1(m + d), ld1(m + 1 + d), ld1(m + 2 + d), ld1(m + 3 + d));
         }
         float2 o[2];
 #pragma unroll
@@ -423,9 +415,6 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
             float2 ga2 = __ffma2_rn(w0, gr, __ffma2_rn(w1, gc, __fmul2_rn(w2, gl)));
             float2 a2, xh, gn1;
             if (QUANT) {
-                // ONE LDS.32 per element: t2 as a function of code1.  Code, value, STE mask and range weight of FQ2 follow
-                // from t2 with a handful of ALU ops (bit-identical to forward), xhat1 is one FMA on code1 -- under random
-                // bank conflicts a wider table would cost more shared-memory cycles than this arithmetic costs issue slots
                 const unsigned ix = (packed >> (16 * j)) & 255u, iy = (packed >> (16 * j + 8)) & 255u;
                 const float2 t2 = make_float2(tabT[ix], tabT[iy]);
                 const float2 c2 = make_float2((float)code_u8(t2.x), (float)code_u8(t2.y));
@@ -442,8 +431,10 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
                 b0 = __ffma2_rn(ga2, make_float2(inx ? dd.x : c2.x, iny ? dd.y : c2.y), b0);
                 b1 = __fadd2_rn(b1, __fadd2_rn(ga2, neg2(gn1)));
             } else {
-                a2 = j ? hi2(aq) : lo2(aq);
-                xh = j ? hi2(xq) : lo2(xq);
+                const float2 yj = j ? hi2(y) : lo2(y);
+                const float2 z = make_float2(prelu_f(yj.x, slope), prelu_f(yj.y, slope));
+                a2 = make_float2(gln_apply(h.g, z.x), gln_apply(h.g, z.y));
+                xh = make_float2(gln_xhat(h.g, z.x), gln_xhat(h.g, z.y));
                 if (TAIL) {
                     if (4 * v + 2 * j + 1 >= M) { ga2.y = 0.f; a2.y = 0.f; }
                     if (4 * v + 2 * j >= M) { ga2.x = 0.f; a2.x = 0.f; }
@@ -460,7 +451,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
         }
         gn1o[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOP(fir, M);
+    FQSS_ROW_LOOP(body, M);
     const float s[8] = {hsum(b0), hsum(b1), hsum(b2), hsum(b3), hsum(d0), hsum(d1), hsum(d2), hsum(d3)};
     double v[8];
     block_sum_fd<8>(s, v, sh);
@@ -479,7 +470,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
 // Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
 // ---------------------------------------------------------------------------------------------
 template <bool QUANT>
-__global__ void __launch_bounds__(ROW_THREADS) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+__global__ void __launch_bounds__(ROW_THREADS, 6) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
@@ -654,19 +645,8 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     }
     // D, R, Q
     {
-        const int dpad = dw_pad(p->dil);
-        const size_t smem = ((size_t)p->ld + 2 * dpad) * sizeof(float) + (p->quant ? 1024 + (size_t)p->ld : (size_t)2 * p->ld * sizeof(float));
-        FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
-        static bool cfg = false;
-        if (!cfg) {
-#define FQSS_DWB_ATTR(Q, D) cudaFuncSetAttribute(tcn_dw_bwd_kernel<Q, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-            FQSS_DWB_ATTR(true, 0); FQSS_DWB_ATTR(true, 1); FQSS_DWB_ATTR(true, 2); FQSS_DWB_ATTR(true, 3);
-            FQSS_DWB_ATTR(false, 0); FQSS_DWB_ATTR(false, 1); FQSS_DWB_ATTR(false, 2); FQSS_DWB_ATTR(false, 3);
-#undef FQSS_DWB_ATTR
-            cfg = true;
-        }
         FQSS_PROF("tcn_dw_bwd", s);
-#define FQSS_DWB_LAUNCH(Q, D) tcn_dw_bwd_kernel<Q, D><<<rows_h, ROW_THREADS, smem, s>>>(*p, *g, acc)
+#define FQSS_DWB_LAUNCH(Q, D) tcn_dw_bwd_kernel<Q, D><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DWB_LAUNCH(true, 0); else if (mode == 1) FQSS_DWB_LAUNCH(true, 1);
