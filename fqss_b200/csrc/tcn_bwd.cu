@@ -192,15 +192,15 @@ __device__ __forceinline__ void mask_tail(float2& a01, float2& a23, int nval) {
 // Row loops run mask-free over the full frame quads (v < M/4); the one ragged quad of a row (M % 4 frames) is
 // handled once, by one thread, through the same body with TAIL = true.  Quads that are entirely padding
 // (ld - M >= 4) are never read or written.
-#define FQSS_ROW_LOOP(body, M)                                                                            \
+#define FQSS_ROW_LOOPN(NTH_, body, M)                                                                           \
     do {                                                                                                  \
         const int nfull_ = (M) >> 2;                                                                      \
-        for (int v_ = threadIdx.x; v_ < nfull_; v_ += ROW_THREADS) body(v_, std::false_type{});           \
-        if (((M)&3) && (int)threadIdx.x == (nfull_ & (ROW_THREADS - 1))) body(nfull_, std::true_type{});  \
+        for (int v_ = threadIdx.x; v_ < nfull_; v_ += (NTH_)) body(v_, std::false_type{});                \
+        if (((M)&3) && (int)threadIdx.x == (nfull_ % (NTH_))) body(nfull_, std::true_type{});             \
     } while (0)
 
-template <int PHASE, bool QUANT>
-__global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+template <int PHASE, bool QUANT, int NTH>
+__global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     __shared__ float tabX[256], tabD[256];
     const AccLayout L(p.B, p.Cio, p.Chid);
@@ -208,9 +208,10 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const Hidden3 h = load_hidden3(p, b, c);
     if (QUANT) {
-        chain_bwd_tables(h.q3, h.g, h.q4, threadIdx.x, tabX, tabD);
-        if (PHASE == 1) {       // P1 reads only tabD: fold the mask into its LSB
-            tabD[threadIdx.x] = __uint_as_float((__float_as_uint(tabD[threadIdx.x]) & ~1u) | (tab_mask(tabX[threadIdx.x]) ? 1u : 0u));
+        for (int i = threadIdx.x; i < 256; i += NTH) {
+            chain_bwd_tables(h.q3, h.g, h.q4, i, tabX, tabD);
+            if (PHASE == 1)         // P1 reads only tabD: fold the mask into its LSB
+                tabD[i] = __uint_as_float((__float_as_uint(tabD[i]) & ~1u) | (tab_mask(tabX[i]) ? 1u : 0u));
         }
         __syncthreads();
     }
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
         }
         if (PHASE == 2) gy3[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOP(body, M);
+    FQSS_ROW_LOOPN(NTH, body, M);
     const float s[4] = {hsum(a0), hsum(a1), PHASE == 1 ? hsum(a2) : hsum(a3), hsum(a3)};
     double v[4];
     block_sum_fd<4>(s, v, sh);
@@ -311,6 +312,75 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_gln2_bwd_kernel(const fqss_tc
             if (QUANT) { atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]); }
             atomicAdd(acc + L.slope + 1, v[2]);
         }
+    }
+}
+
+// P1 of the quantised model on the saved codes: 3 B/element of HBM traffic, so the kernel lives or dies by the number
+// of loads in flight.  Every thread first issues the loads of NQ quads (code word + bf16 gradient quad each), then
+// consumes them; quads at or beyond ceil(M/4) are predicated off, the ragged quad masks its gradient lanes.
+template <int NQ, int NTH>
+__global__ void __launch_bounds__(NTH) tcn_gln2_sums_codes_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    __shared__ double sh[4 * 32];
+    __shared__ float tabD[256];
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
+    const int M = p.M;
+    const int nq = (M + 3) >> 2;
+    const uint32_t* c3 = reinterpret_cast<const uint32_t*>(p.code3 + r * p.ld);
+    const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    uint32_t cw[NQ];
+    uint2 gw[NQ];
+    auto issue = [&](int base) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const int v = base + k * NTH;
+            const bool ok = v < nq;
+            cw[k] = ok ? __ldg(c3 + v) : 0u;
+            gw[k] = ok ? __ldg(ga4 + v) : make_uint2(0u, 0u);
+        }
+    };
+    // the first batch of row data is requested BEFORE the per-row constants and the table are built: one CTA handles one
+    // short row, so serialising "constants -> table -> barrier -> data" would expose two full memory latencies per CTA
+    issue(threadIdx.x);
+    const Hidden3 h = load_hidden3(p, b, c);
+    for (int i = threadIdx.x; i < 256; i += NTH) {
+        const float4 e = chain_bwd_entry(h.q3, h.g, h.q4, i, false);        // {-, mask4, D4, xhat3}
+        tabD[i] = __uint_as_float((__float_as_uint(e.z) & ~1u) | (e.y != 0.f ? 1u : 0u));
+    }
+    __syncthreads();
+    const float2 xa3 = f2s(h.q3.delta * h.g.rstd), xb3 = f2s((h.q3.mn - h.g.mu) * h.g.rstd);
+    // a0 = sum g*D4, a1 = sum g*(1-m4), a2 = sum g*m4, a3 = sum g*m4*xhat3
+    float2 a0 = f2s(0.f), a1 = f2s(0.f), a2 = f2s(0.f), a3 = f2s(0.f);
+    for (int base = threadIdx.x; base < nq; base += NQ * NTH) {
+        if (base != (int)threadIdx.x) issue(base);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const int v = base + k * NTH;
+            const float4 gi = bf16x4_to_float4(gw[k]);
+            float2 gg[2] = {lo2(gi), hi2(gi)};
+            if (4 * v + 3 >= M) mask_tail(gg[0], gg[1], M - 4 * v);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const unsigned ix = (cw[k] >> (16 * j)) & 255u, iy = (cw[k] >> (16 * j + 8)) & 255u;
+                const float2 dm = make_float2(tabD[ix], tabD[iy]);
+                const float2 xh = __ffma2_rn(make_float2((float)ix, (float)iy), xa3, xb3);
+                const float2 gn = make_float2(tab_mask(dm.x) ? gg[j].x : 0.f, tab_mask(dm.y) ? gg[j].y : 0.f);
+                a0 = __ffma2_rn(gg[j], dm, a0);
+                a1 = __fadd2_rn(a1, __fadd2_rn(gg[j], neg2(gn)));
+                a2 = __fadd2_rn(a2, gn);
+                a3 = __ffma2_rn(gn, xh, a3);
+            }
+        }
+    }
+    const float s[4] = {hsum(a0), hsum(a1), hsum(a2), hsum(a3)};
+    double v[4];
+    block_sum_fd<4>(s, v, sh);
+    if (threadIdx.x == 0) {
+        atomicAdd(acc + L.q + 2 * Q4, v[0]);
+        atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]);
+        acc[L.row2 + 2 * r] = v[2];
+        acc[L.row2 + 2 * r + 1] = v[3];
     }
 }
 
@@ -354,8 +424,8 @@ __global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, 
 //             centre a2 is needed
 // The float model derives a2 / xhat1 from y1 directly.
 // ---------------------------------------------------------------------------------------------
-template <bool QUANT, int DMODE>
-__global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+template <bool QUANT, int DMODE, int NTH>
+__global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[8 * 32];
     __shared__ float tabT[256];                       // QUANT: t2 = (gLN1(decode1(code1)) - min2) / delta2
     const AccLayout L(p.B, p.Cio, p.Chid);
@@ -364,7 +434,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
     const int M = p.M, d = p.dil;
     const Hidden1 h = load_hidden1(p, b, c);
     if (QUANT) {
-        tabT[threadIdx.x] = actqf_t(h.q2, gln_apply(h.g, actqf_decode(h.q1, (float)threadIdx.x)));
+        for (int i = threadIdx.x; i < 256; i += NTH) tabT[i] = actqf_t(h.q2, gln_apply(h.g, actqf_decode(h.q1, (float)i)));
         __syncthreads();
     }
     const float4* y1 = reinterpret_cast<const float4*>(p.y1 + r * p.ld);
@@ -451,7 +521,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
         }
         gn1o[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOP(body, M);
+    FQSS_ROW_LOOPN(NTH, body, M);
     const float s[8] = {hsum(b0), hsum(b1), hsum(b2), hsum(b3), hsum(d0), hsum(d1), hsum(d2), hsum(d3)};
     double v[8];
     block_sum_fd<8>(s, v, sh);
@@ -469,8 +539,8 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_bwd_kernel(const fqss_tcn_
 // ---------------------------------------------------------------------------------------------
 // Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
 // ---------------------------------------------------------------------------------------------
-template <bool QUANT>
-__global__ void __launch_bounds__(ROW_THREADS, 6) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+template <bool QUANT, int NTH>
+__global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int64_t r = blockIdx.x;
@@ -532,7 +602,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 6) tcn_gln1_bwd_kernel(const fqss
         }
         dY1[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOP(body, M);
+    FQSS_ROW_LOOPN(NTH, body, M);
     const float s[4] = {hsum(a0), hsum(a1), hsum(a3), hsum(a4)};
     double v[4];
     block_sum_fd<4>(s, v, sh);
@@ -633,20 +703,20 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // P1, R, P2
     {
         FQSS_PROF("tcn_gln2_bwd<1>", s);
-        if (p->quant) tcn_gln2_bwd_kernel<1, true><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
-        else tcn_gln2_bwd_kernel<1, false><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        if (p->quant) tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        else tcn_gln2_bwd_kernel<1, false, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
     }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
                                                                      acc + L.samp2); }
     {
         FQSS_PROF("tcn_gln2_bwd<2>", s);
-        if (p->quant) tcn_gln2_bwd_kernel<2, true><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
-        else tcn_gln2_bwd_kernel<2, false><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        if (p->quant) tcn_gln2_bwd_kernel<2, true, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        else tcn_gln2_bwd_kernel<2, false, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
     }
     // D, R, Q
     {
         FQSS_PROF("tcn_dw_bwd", s);
-#define FQSS_DWB_LAUNCH(Q, D) tcn_dw_bwd_kernel<Q, D><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc)
+#define FQSS_DWB_LAUNCH(Q, D) tcn_dw_bwd_kernel<Q, D, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DWB_LAUNCH(true, 0); else if (mode == 1) FQSS_DWB_LAUNCH(true, 1);
@@ -661,8 +731,8 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
                                                                      acc + L.samp1); }
     {
         FQSS_PROF("tcn_gln1_bwd", s);
-        if (p->quant) tcn_gln1_bwd_kernel<true><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
-        else tcn_gln1_bwd_kernel<false><<<rows_h, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        if (p->quant) tcn_gln1_bwd_kernel<true, 256><<<rows_h, 256, 0, s>>>(*p, *g, acc);
+        else tcn_gln1_bwd_kernel<false, 256><<<rows_h, 256, 0, s>>>(*p, *g, acc);
     }
     rc = check_launch("tcn_block_bwd(hidden)");
     if (rc) return rc;

@@ -12,7 +12,9 @@
 
 namespace fqss {
 
-constexpr int ROW_THREADS = 256;
+constexpr int ROW_THREADS = 256;     // default CTA width of the row kernels (one CTA per (sample, channel) row).  Kernels
+                                      // whose per-row fixed cost (constants, table build, reductions) dominated at 16 frames
+                                      // per thread are instantiated with NTH = 128 instead (measured per kernel on B200).
 constexpr float GLN_EPS = 1e-8f;      // convtasnetq.py:8
 
 struct GlnRow {

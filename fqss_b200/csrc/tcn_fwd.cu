@@ -10,6 +10,9 @@
 //
 // Only pre-activation tensors (y1, y3, res_y, skip_y) and the 128-wide block outputs are stored;
 // every quantised activation is recomputed on load by its consumer (and again in backward).
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "fqss_common.cuh"
 #include "gemm_tc.cuh"
 #include "tcn_common.cuh"
@@ -95,8 +98,8 @@ __global__ void tcn_rowconst_kernel(const double* __restrict__ stats, int B, dou
 __device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
 
-template <bool QUANT, int DMODE>
-__global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_block p) {
+template <bool QUANT, int DMODE, int NTH>
+__global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p) {
     extern __shared__ __align__(16) float dsm[];     // [dpad | ld | dpad] a2 row with zero halo, then the table
     __shared__ double sh[2 * 32];
     __shared__ unsigned shi[2 * 8];
@@ -107,18 +110,18 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
     float* row = dsm + dpad;
     float* lut = dsm + ld + 2 * dpad;
     const Hidden1 h = load_hidden1(p, b, c);
-    for (int i = threadIdx.x; i < dpad; i += ROW_THREADS) {
+    for (int i = threadIdx.x; i < dpad; i += NTH) {
         dsm[i] = 0.f;
         row[ld + i] = 0.f;
     }
     if (QUANT) {
-        if (threadIdx.x < 256) lut[threadIdx.x] = chain_fq_value(h.q1, h.g, h.q2, threadIdx.x);
+        for (int i = threadIdx.x; i < 256; i += NTH) lut[i] = chain_fq_value(h.q1, h.g, h.q2, i);
         __syncthreads();
     }
     const float* y1 = p.y1 + r * p.ld;
     uint32_t* code1 = p.code1 ? reinterpret_cast<uint32_t*>(p.code1 + r * p.ld) : nullptr;
     const int nvec = ld >> 2;
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+    for (int v = threadIdx.x; v < nvec; v += NTH) {
         const float4 y = ldg4_stream(y1 + 4 * v);
         float4 a;
         if (QUANT) {
@@ -160,7 +163,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
     // a3 = delta*c + min is expanded at the end; the float model sums the values
     float s = 0.f, ss = 0.f;
     unsigned sc = 0u, scc = 0u;
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+    for (int v = threadIdx.x; v < nvec; v += NTH) {
         float4 L, C, R;
         dw_taps<DMODE>(row, v, d, L, C, R);
         const float2 o01 = __ffma2_rn(w2, lo2(R), __ffma2_rn(w1, lo2(C), __ffma2_rn(w0, lo2(L), bias)));
@@ -199,7 +202,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
         if (threadIdx.x == 0) {
             unsigned long long tc = 0, tcc = 0;
 #pragma unroll
-            for (int w = 0; w < ROW_THREADS / 32; ++w) { tc += shi[w]; tcc += shi[8 + w]; }
+            for (int w = 0; w < NTH / 32; ++w) { tc += shi[w]; tcc += shi[8 + w]; }
             const double dl = (double)q3.delta, mn = (double)q3.mn, n = (double)M;
             atomicAdd(p.stats3 + 2 * b, dl * (double)tc + n * mn);
             atomicAdd(p.stats3 + 2 * b + 1, dl * dl * (double)tcc + 2.0 * dl * mn * (double)tc + n * mn * mn);
@@ -218,21 +221,21 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_dw_fwd_kernel(const fqss_tcn_
 // K3a: hidden quantiser  y3 -> a4 operand (bf16 code / value).  Quantised model: PReLU -> code3 ->
 // table (code3 -> code4 = FQ4-code(gLN2(decode3(code3)))).  6 B/element.
 // ---------------------------------------------------------------------------------------------
-template <bool QUANT>
-__global__ void __launch_bounds__(ROW_THREADS) tcn_hidden_fq_kernel(const fqss_tcn_block p) {
+template <bool QUANT, int NTH>
+__global__ void __launch_bounds__(NTH) tcn_hidden_fq_kernel(const fqss_tcn_block p) {
     __shared__ float lut[256];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const Hidden3 h = load_hidden3(p, b, c);
     if (QUANT) {
-        if (threadIdx.x < 256) lut[threadIdx.x] = chain_fq_code(h.q3, h.g, h.q4, threadIdx.x);
+        for (int i = threadIdx.x; i < 256; i += NTH) lut[i] = chain_fq_code(h.q3, h.g, h.q4, i);
         __syncthreads();
     }
     const float* y3 = p.y3 + r * p.ld;
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + r * p.ld;
     uint32_t* code3 = p.code3 ? reinterpret_cast<uint32_t*>(p.code3 + r * p.ld) : nullptr;
     const int nvec = (p.M + 3) >> 2;
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
+    for (int v = threadIdx.x; v < nvec; v += NTH) {
         const float4 y = ldg4_stream(y3 + 4 * v);
         float o0, o1, o2, o3;
         if (QUANT) {
@@ -309,7 +312,7 @@ __global__ void __launch_bounds__(ROW_THREADS) rowscale_bf16_kernel(const float*
         s += (x.x + x.y) + (x.z + x.w);
         dst[v] = float4_to_bf16x4(x.x * sc, x.y * sc, x.z * sc, x.w * sc);
     }
-    if ((M & 3) && (int)threadIdx.x == (nfull & (ROW_THREADS - 1))) {
+    if ((M & 3) && (int)threadIdx.x == (nfull % ROW_THREADS)) {
         float x[4] = {0.f, 0.f, 0.f, 0.f};
         for (int k = 0; k < (M & 3); ++k) x[k] = g[r * ldg + 4 * nfull + k];
         s += (x[0] + x[1]) + (x[2] + x[3]);
@@ -437,25 +440,25 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_fwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         static bool cfg = false;
         if (!cfg) {
-#define FQSS_DW_ATTR(Q, D) cudaFuncSetAttribute(tcn_dw_fwd_kernel<Q, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+#define FQSS_DW_ATTR(Q, D) cudaFuncSetAttribute(tcn_dw_fwd_kernel<Q, D, (Q ? 256 : 128)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
             FQSS_DW_ATTR(true, 0); FQSS_DW_ATTR(true, 1); FQSS_DW_ATTR(true, 2); FQSS_DW_ATTR(true, 3);
             FQSS_DW_ATTR(false, 0); FQSS_DW_ATTR(false, 1); FQSS_DW_ATTR(false, 2); FQSS_DW_ATTR(false, 3);
 #undef FQSS_DW_ATTR
             cfg = true;
         }
-#define FQSS_DW_LAUNCH(Q, D) do { FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s); tcn_dw_fwd_kernel<Q, D><<<rows, ROW_THREADS, smem, s>>>(*p); } while (0)
+#define FQSS_DW_LAUNCH(Q, D) do { FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s); tcn_dw_fwd_kernel<Q, D, (Q ? 256 : 128)><<<rows, (Q ? 256 : 128), smem, s>>>(*p); } while (0)
 #define FQSS_RC3_LAUNCH() do { FQSS_PROF("tcn_rowconst", s); tcn_rowconst_kernel<<<1, 64, 0, s>>>(p->stats3, p->B, n_elems, p->q3.rmin, p->q3.rmax, p->q4.rmin, p->q4.rmax, nullptr, nullptr, p->rc3); } while (0)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DW_LAUNCH(true, 0); else if (mode == 1) FQSS_DW_LAUNCH(true, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(true, 2); else FQSS_DW_LAUNCH(true, 3);
             FQSS_RC3_LAUNCH();
-            { FQSS_PROF("tcn_hidden_fq", s); tcn_hidden_fq_kernel<true><<<rows, ROW_THREADS, 0, s>>>(*p); }
+            { FQSS_PROF("tcn_hidden_fq", s); tcn_hidden_fq_kernel<true, 256><<<rows, 256, 0, s>>>(*p); }
         } else {
             if (mode == 0) FQSS_DW_LAUNCH(false, 0); else if (mode == 1) FQSS_DW_LAUNCH(false, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(false, 2); else FQSS_DW_LAUNCH(false, 3);
             FQSS_RC3_LAUNCH();
-            { FQSS_PROF("tcn_hidden_fq(float)", s); tcn_hidden_fq_kernel<false><<<rows, ROW_THREADS, 0, s>>>(*p); }
+            { FQSS_PROF("tcn_hidden_fq(float)", s); tcn_hidden_fq_kernel<false, 256><<<rows, 256, 0, s>>>(*p); }
         }
 #undef FQSS_DW_LAUNCH
 #undef FQSS_RC3_LAUNCH
