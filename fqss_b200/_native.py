@@ -32,6 +32,18 @@ class PwDesc(C.Structure):
                 ("rmin", vp), ("rmax", vp)]
 
 
+class WqItem(C.Structure):
+    _fields_ = [("g", vp), ("w", vp), ("out", vp), ("g_rmin", vp), ("g_rmax", vp), ("rmin", vp), ("rmax", vp),
+                ("outer", C.c_int32), ("ch", C.c_int32), ("inner", C.c_int32), ("n_bits", C.c_int32)]
+
+
+class PrepItem(C.Structure):
+    _fields_ = [("W", vp), ("wmin", vp), ("wmax", vp), ("bias", vp), ("amin", vp), ("amax", vp),
+                ("Wc", vp), ("WcT", vp), ("s1", vp), ("s0", vp), ("dws", vp),
+                ("N", C.c_int32), ("K", C.c_int32), ("Ntot", C.c_int32), ("n_off", C.c_int32), ("split", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
 class PwGrads(C.Structure):
     _fields_ = [("g", vp), ("ldg", i64), ("gx1", vp), ("ldg1", i64), ("gx2", vp), ("ldg2", i64),
                 ("g_rmin", vp), ("g_rmax", vp), ("g_slope", vp), ("g_gamma", vp), ("g_beta", vp)]
@@ -65,6 +77,9 @@ _SIGS = {
     "fqss_pw_gemm_ex": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i32, vp]),
     "fqss_split_bf16": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, vp]),
     "fqss_tcn_prep": (i32, [vp] * 11 + [i32] * 5 + [vp]),
+    "fqss_fq_weight_fwd_batch": (i32, [C.POINTER(WqItem), i32, vp]),
+    "fqss_fq_weight_bwd_batch": (i32, [C.POINTER(WqItem), i32, vp]),
+    "fqss_tcn_prep_batch": (i32, [C.POINTER(PrepItem), i32, vp]),
     "fqss_rowscale_bf16": (i32, [vp, i64, vp, i64, i64, i32, i32, vp, vp, vp]),
     "fqss_wgrad_codes_ws_bytes": (sz, [i32, i32, i32, i32]),
     "fqss_wgrad_codes": (i32, [vp, vp, i32, i32, i64, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]),
@@ -104,7 +119,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 8:
+                if L.fqss_abi_version() != 9:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

@@ -191,6 +191,57 @@ __global__ void fq_weight_bwd_kernel(const float* __restrict__ g, const float* _
     }
 }
 
+constexpr int WQ_BATCH = 48;
+struct WqBatch {
+    fqss_wq_item it[WQ_BATCH];
+};
+
+__global__ void fq_weight_bwd_batch_kernel(const __grid_constant__ WqBatch b) {
+    __shared__ double sh[32];
+    const fqss_wq_item& t = b.it[blockIdx.y];
+    const int c = blockIdx.x;
+    if (c >= t.ch) return;
+    const float mn = t.rmin[c], mx = t.rmax[c];
+    const WQ q = make_wq(mn, mx, t.n_bits);
+    const int per = t.outer * t.inner;
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < per; j += blockDim.x) {
+        int o = j / t.inner, i = j - o * t.inner;
+        int64_t idx = ((int64_t)o * t.ch + c) * t.inner + i;
+        float u = __fdiv_rn(t.w[idx], q.delta);
+        float X = rintf(u);
+        bool in = (X >= q.lo) && (X <= q.hi);
+        float cc = fminf(fmaxf(X, q.lo), q.hi);
+        float gi = t.g[idx];
+        if (t.out) t.out[idx] = in ? __fdiv_rn(__fmul_rn(gi, q.delta), q.delta) : 0.f;
+        acc += (double)gi * (double)(in ? __fsub_rn(X, u) : cc);
+    }
+    double v[1] = {acc};
+    block_sum<1>(v, sh);
+    if (threadIdx.x == 0) {
+        double ga = 2.0 * v[0] / (double)((1 << t.n_bits) - 1);
+        float amn = fabsf(mn), amx = fabsf(mx);
+        double fmx = amx > amn ? 1.0 : (amx == amn ? 0.5 : 0.0);
+        double fmn = 1.0 - fmx;
+        float smx = (mx > 0.f) - (mx < 0.f), smn = (mn > 0.f) - (mn < 0.f);
+        if (t.g_rmax) t.g_rmax[c] = (float)(ga * fmx * smx);
+        if (t.g_rmin) t.g_rmin[c] = (float)(ga * fmn * smn);
+    }
+}
+
+__global__ void fq_weight_fwd_batch_kernel(const __grid_constant__ WqBatch b) {
+    const fqss_wq_item& t = b.it[blockIdx.y];
+    const int c = blockIdx.x;
+    if (c >= t.ch) return;
+    const WQ q = make_wq(t.rmin[c], t.rmax[c], t.n_bits);
+    const int per = t.outer * t.inner;
+    for (int j = threadIdx.x; j < per; j += blockDim.x) {
+        int o = j / t.inner, i = j - o * t.inner;
+        int64_t idx = ((int64_t)o * t.ch + c) * t.inner + i;
+        t.out[idx] = __fmul_rn(q.delta, wq_code(q, t.w[idx]));
+    }
+}
+
 __global__ void weight_observe_kernel(const float* __restrict__ w, int outer, int ch, int inner,
                                       float* __restrict__ rmin, float* __restrict__ rmax) {
     __shared__ float smn[32], smx[32];
@@ -432,6 +483,31 @@ int fqss_fq_weight_bwd(const float* g, const float* w, float* gw, float* g_rmin,
                                                                n_bits);
     return check_launch("fq_weight_bwd");
 }
+
+static int wq_batch(const fqss_wq_item* items, int n, void* stream, bool bwd) {
+    const char* who = bwd ? "fq_weight_bwd_batch" : "fq_weight_fwd_batch";
+    FQSS_REQUIRE(items && n > 0, -1, "%s: empty batch", who);
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n; i0 += WQ_BATCH) {
+        WqBatch b;
+        const int m = n - i0 < WQ_BATCH ? n - i0 : WQ_BATCH;
+        int maxch = 0;
+        for (int i = 0; i < m; ++i) {
+            const fqss_wq_item& t = items[i0 + i];
+            FQSS_REQUIRE(t.w && t.rmin && t.rmax && (bwd ? t.g != nullptr : t.out != nullptr), -1, "%s: null pointer in item %d", who, i0 + i);
+            FQSS_REQUIRE(t.outer > 0 && t.ch > 0 && t.inner > 0 && t.n_bits >= 2 && t.n_bits <= 8, -1, "%s: bad shape/bits in item %d", who, i0 + i);
+            b.it[i] = t;
+            if (t.ch > maxch) maxch = t.ch;
+        }
+        FQSS_PROF(bwd ? "fq_weight_bwd(batch)" : "fq_weight_fwd(batch)", s);
+        if (bwd) fq_weight_bwd_batch_kernel<<<dim3(maxch, m), 128, 0, s>>>(b);
+        else fq_weight_fwd_batch_kernel<<<dim3(maxch, m), 128, 0, s>>>(b);
+    }
+    return check_launch(who);
+}
+
+int fqss_fq_weight_fwd_batch(const fqss_wq_item* items, int n, void* stream) { return wq_batch(items, n, stream, false); }
+int fqss_fq_weight_bwd_batch(const fqss_wq_item* items, int n, void* stream) { return wq_batch(items, n, stream, true); }
 
 int fqss_weight_observe(const float* w, int outer, int ch, int inner, float* rmin, float* rmax, void* stream) {
     FQSS_REQUIRE(w && rmin && rmax && outer > 0 && ch > 0 && inner > 0, -1, "weight_observe: bad argument");

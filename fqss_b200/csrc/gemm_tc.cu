@@ -75,8 +75,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int a_rows = p.a_rows > 0 ? p.a_rows : p.K;
 
     for (int i = threadIdx.x; i < p.N; i += NUM_THREADS) {
-        s1s[i] = __ldg(p.s1 + i);
-        s0s[i] = __ldg(p.s0 + i);
+        s1s[i] = p.s1 ? __ldg(p.s1 + i) : 1.f;
+        s0s[i] = p.s0 ? __ldg(p.s0 + i) : 0.f;
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -429,7 +429,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, c
 }
 
 int run(int epi, const void* act_bf16, const void* w_bf16, const Args& a, cudaStream_t s) {
-    FQSS_REQUIRE(act_bf16 && w_bf16 && a.s1 && a.s0, -1, "pw_gemm: null operand");
+    FQSS_REQUIRE(act_bf16 && w_bf16, -1, "pw_gemm: null operand");
     FQSS_REQUIRE(a.B > 0 && a.M > 0 && a.K >= BK && a.K % BK == 0 && a.N >= 128 && a.N % 128 == 0 && a.N <= MAXN, -1,
                  "pw_gemm: unsupported shape B=%d M=%d K=%d N=%d (K %% 64 == 0, N %% 128 == 0, N <= %d)", a.B, a.M, a.K, a.N, MAXN);
     FQSS_REQUIRE(a.ld >= a.M && a.ld % 8 == 0, -2, "pw_gemm: row pitch must be a multiple of 8 elements (TMA 16 B strides)");

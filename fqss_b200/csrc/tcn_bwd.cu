@@ -684,7 +684,6 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     const int rows_h = p->B * p->Chid, rows_io = p->B * p->Cio;
 
     cudaMemsetAsync(acc, 0, (size_t)L.total * sizeof(double), s);
-    { FQSS_PROF("tcn_bwd_misc", s); fill_consts_kernel<<<4, 256, 0, s>>>(ones, zeros, 1024); }
     // T
     { FQSS_PROF("tcn_tail_bwd", s); tcn_tail_bwd_kernel<<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc); }
     rc = check_launch("tcn_block_bwd(tail)");
@@ -692,7 +691,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // G: g_a4 = Wc2T-GEMM(dY2)   (K = n2, N = Chid) -> bf16
     {
         tcg::Args a{};
-        a.B = p->B; a.M = p->M; a.K = n2; a.N = p->Chid; a.ld = p->ld; a.s1 = ones; a.s0 = zeros; a.out_bf16 = (__nv_bfloat16*)g->g_hid_a;
+        a.B = p->B; a.M = p->M; a.K = n2; a.N = p->Chid; a.ld = p->ld; a.s1 = nullptr; a.s0 = nullptr; a.out_bf16 = (__nv_bfloat16*)g->g_hid_a;
         rc = tcg::run(tcg::EPI_BF16, g->dY2, p->Wc2T, a, s);
         if (rc) return rc;
     }
@@ -739,7 +738,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // G: g_x_in = Wc1T-GEMM(dY1) (+ g_xd)   (K = Chid, N = Cio) -> fp32
     {
         tcg::Args a{};
-        a.B = p->B; a.M = p->M; a.K = p->Chid; a.N = p->Cio; a.ld = p->ld; a.s1 = ones; a.s0 = zeros; a.out_f32 = g->g_x_in;
+        a.B = p->B; a.M = p->M; a.K = p->Chid; a.N = p->Cio; a.ld = p->ld; a.s1 = nullptr; a.s0 = nullptr; a.out_f32 = g->g_x_in;
         a.addend = p->has_res ? g->g_xd : nullptr;
         rc = tcg::run(p->has_res ? tcg::EPI_ADD : tcg::EPI_STORE, g->dY1, p->Wc1T, a, s);
         if (rc) return rc;

@@ -62,6 +62,51 @@ __global__ void tcn_prep_kernel(const float* __restrict__ W, const float* __rest
     }
 }
 
+constexpr int PREP_BATCH = 32;
+struct PrepBatch {
+    fqss_prep_item it[PREP_BATCH];
+};
+__global__ void tcn_prep_batch_kernel(const __grid_constant__ PrepBatch b) {
+    const fqss_prep_item& t = b.it[blockIdx.y];
+    if ((int)blockIdx.x >= t.N) return;
+    __shared__ double sh[32];
+    const int o = blockIdx.x, K = t.K;
+    const bool quant = t.wmin != nullptr;
+    WQ q;
+    if (quant) q = make_wq(t.wmin[o], t.wmax[o], 8);
+    __nv_bfloat16* Wc = reinterpret_cast<__nv_bfloat16*>(t.Wc);
+    __nv_bfloat16* WcT = reinterpret_cast<__nv_bfloat16*>(t.WcT);
+    double rsum = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = t.W[(int64_t)o * K + k];
+        const float c = quant ? wq_code(q, w) : w;
+        const __nv_bfloat16 cb = __float2bfloat16_rn(c);
+        if (t.split) {
+            __nv_bfloat16* row = Wc + (int64_t)(t.n_off + o) * 3 * K;
+            row[k] = cb;
+            row[K + k] = cb;
+            row[2 * K + k] = __float2bfloat16_rn(c - __bfloat162float(cb));
+        } else {
+            Wc[(int64_t)(t.n_off + o) * K + k] = cb;
+        }
+        if (WcT) WcT[(int64_t)k * t.Ntot + t.n_off + o] = cb;
+        rsum += (double)c;
+    }
+    double v[1] = {rsum};
+    block_sum<1>(v, sh);
+    if (threadIdx.x == 0) {
+        const float dw = quant ? q.delta : 1.f;
+        float da = 1.f, mn = 0.f;
+        if (t.amin) {
+            mn = *t.amin;
+            da = __fdiv_rn(__fsub_rn(*t.amax, mn), 255.f);
+        }
+        t.s1[t.n_off + o] = dw * da;
+        t.s0[t.n_off + o] = dw * mn * (float)v[0] + (t.bias ? t.bias[o] : 0.f);
+        t.dws[t.n_off + o] = dw;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Row constants: one warp turns the finished fp64 statistics into {mean, rstd} per sample and the two
 // quantisers around the gLN into {min, delta, 1/delta, levels} (layout: tcn_common.cuh).
@@ -384,6 +429,30 @@ int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const fl
     tcn_prep_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(W, wmin, wmax, bias, amin, amax, (__nv_bfloat16*)Wc, (__nv_bfloat16*)WcT, s1,
                                                          s0, dws, K, Ntot, n_off, split);
     return check_launch("tcn_prep");
+}
+
+int fqss_tcn_prep_batch(const fqss_prep_item* items, int n, void* stream) {
+    FQSS_REQUIRE(items && n > 0, -1, "tcn_prep_batch: empty batch");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n; i0 += PREP_BATCH) {
+        PrepBatch b;
+        const int m = n - i0 < PREP_BATCH ? n - i0 : PREP_BATCH;
+        int maxn = 0;
+        for (int i = 0; i < m; ++i) {
+            const fqss_prep_item& t = items[i0 + i];
+            FQSS_REQUIRE(t.W && t.Wc && t.s1 && t.s0 && t.dws && t.N > 0 && t.K > 0 && t.n_off >= 0 && t.n_off + t.N <= t.Ntot, -1,
+                         "tcn_prep_batch: bad item %d", i0 + i);
+            FQSS_REQUIRE(t.WcT || t.split, -1, "tcn_prep_batch: WcT may be NULL only for split (inference) operands");
+            FQSS_REQUIRE(!t.split || (t.wmin == nullptr && t.amin == nullptr), -1, "tcn_prep_batch: split operands are for the float model");
+            FQSS_REQUIRE((t.wmin == nullptr) == (t.wmax == nullptr) && (t.amin == nullptr) == (t.amax == nullptr), -1,
+                         "tcn_prep_batch: ranges come in pairs");
+            b.it[i] = t;
+            if (t.N > maxn) maxn = t.N;
+        }
+        FQSS_PROF("tcn_prep(batch)", s);
+        tcn_prep_batch_kernel<<<dim3(maxn, m), 128, 0, s>>>(b);
+    }
+    return check_launch("tcn_prep_batch");
 }
 
 int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int M, const float* rmin,

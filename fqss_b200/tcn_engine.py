@@ -158,9 +158,9 @@ class BlockState:
     __slots__ = ("t", "dil", "first", "has_res", "prep", "act", "blk")
 
 
-def _prep_block(t, quant, first, has_res, q_in, dev):
-    """Run the per-step weight preparation for one block; returns the dict of prepared buffers."""
-    L = _libx()
+def _prep_items(t, quant, has_res, q_in, dev, prep_items, wq_items):
+    """Allocate the prepared-weight buffers of one block and append its weight-preparation work to the batch lists
+    (three 1x1 convs -> fqss_tcn_prep_batch, the depthwise weight -> fqss_fq_weight_fwd_batch)."""
     Chid, Cio = t["W1"].shape[0], t["W1"].shape[1]
     n2 = 2 * Cio if has_res else Cio
     bf = torch.bfloat16
@@ -168,28 +168,44 @@ def _prep_block(t, quant, first, has_res, q_in, dev):
              s1_1=torch.empty(Chid, device=dev), s0_1=torch.empty(Chid, device=dev), dws1=torch.empty(Chid, device=dev),
              Wc2=torch.empty((n2, Chid), dtype=bf, device=dev), Wc2T=torch.empty((Chid, n2), dtype=bf, device=dev),
              s1_2=torch.empty(n2, device=dev), s0_2=torch.empty(n2, device=dev), dws2=torch.empty(n2, device=dev))
-    s = stream_ptr()
     qi = q_in if quant else (None, None)
-    check(L.fqss_tcn_prep(ptr(t["W1"]), ptr(t["w1min"]) or None, ptr(t["w1max"]) or None, ptr(t["b1"]) or None,
-                          ptr(qi[0]) or None, ptr(qi[1]) or None, ptr(P["Wc1"]), ptr(P["Wc1T"]), ptr(P["s1_1"]), ptr(P["s0_1"]),
-                          ptr(P["dws1"]), Chid, Cio, Chid, 0, 0, s))
-    off = 0
     q4 = (t["q4min"], t["q4max"]) if quant else (None, None)
+
+    def item(W, wmin, wmax, bias, amin, amax, Wc, WcT, s1, s0, dws, Nn, K, Ntot, off):
+        it = N.PrepItem()
+        it.W, it.wmin, it.wmax, it.bias = ptr(W), ptr(wmin) or None, ptr(wmax) or None, ptr(bias) or None
+        it.amin, it.amax = ptr(amin) or None, ptr(amax) or None
+        it.Wc, it.WcT, it.s1, it.s0, it.dws = ptr(Wc), ptr(WcT), ptr(s1), ptr(s0), ptr(dws)
+        it.N, it.K, it.Ntot, it.n_off, it.split = Nn, K, Ntot, off, 0
+        prep_items.append(it)
+    item(t["W1"], t["w1min"], t["w1max"], t["b1"], qi[0], qi[1], P["Wc1"], P["Wc1T"], P["s1_1"], P["s0_1"], P["dws1"], Chid, Cio, Chid, 0)
+    off = 0
     if has_res:
-        check(L.fqss_tcn_prep(ptr(t["Wres"]), ptr(t["wrmin"]) or None, ptr(t["wrmax"]) or None, ptr(t["bres"]) or None,
-                              ptr(q4[0]) or None, ptr(q4[1]) or None, ptr(P["Wc2"]), ptr(P["Wc2T"]), ptr(P["s1_2"]),
-                              ptr(P["s0_2"]), ptr(P["dws2"]), Cio, Chid, n2, 0, 0, s))
+        item(t["Wres"], t["wrmin"], t["wrmax"], t["bres"], q4[0], q4[1], P["Wc2"], P["Wc2T"], P["s1_2"], P["s0_2"], P["dws2"], Cio, Chid, n2, 0)
         off = Cio
-    check(L.fqss_tcn_prep(ptr(t["Wskip"]), ptr(t["wsmin"]) or None, ptr(t["wsmax"]) or None, ptr(t["bskip"]) or None,
-                          ptr(q4[0]) or None, ptr(q4[1]) or None, ptr(P["Wc2"]), ptr(P["Wc2T"]), ptr(P["s1_2"]), ptr(P["s0_2"]),
-                          ptr(P["dws2"]), Cio, Chid, n2, off, 0, s))
+    item(t["Wskip"], t["wsmin"], t["wsmax"], t["bskip"], q4[0], q4[1], P["Wc2"], P["Wc2T"], P["s1_2"], P["s0_2"], P["dws2"], Cio, Chid, n2, off)
     if quant:
         wdw = torch.empty_like(t["Wdw"], memory_format=torch.contiguous_format)
-        check(lib().fqss_fq_weight_fwd(ptr(t["Wdw"]), ptr(wdw), None, 1, Chid, t["Wdw"].shape[-1], ptr(t["wdmin"]), ptr(t["wdmax"]), 8, s))
+        it = N.WqItem()
+        it.w, it.out, it.rmin, it.rmax = ptr(t["Wdw"]), ptr(wdw), ptr(t["wdmin"]), ptr(t["wdmax"])
+        it.outer, it.ch, it.inner, it.n_bits = 1, Chid, t["Wdw"].shape[-1], 8
+        wq_items.append(it)
     else:
         wdw = t["Wdw"]
     P["wdw"] = wdw
     return P
+
+
+def _run_batches(prep_items, wq_items, wq_bwd=False):
+    L = _libx()
+    s = stream_ptr()
+    if prep_items:
+        arr = (N.PrepItem * len(prep_items))(*prep_items)
+        check(L.fqss_tcn_prep_batch(arr, len(prep_items), s))
+    if wq_items:
+        arr = (N.WqItem * len(wq_items))(*wq_items)
+        fn = L.fqss_fq_weight_bwd_batch if wq_bwd else L.fqss_fq_weight_fwd_batch
+        check(fn(arr, len(wq_items), s))
 
 
 def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
@@ -338,15 +354,25 @@ class FusedTCNFunction(Function):
         x_op = torch.empty((B, Cio, ld), dtype=torch.bfloat16, device=dev)
         qi = q_in if quant else (None, None)
         check(L.fqss_tcn_encode(ptr(x), ld, ptr(x_op), ld, B * Cio, M, ptr(qi[0]) or None, ptr(qi[1]) or None, s))
+        # pass 1: weight preparation of ALL blocks in two batched launches (weights and ranges are constant during a step)
+        tensors, preps, prep_items, wq_items = [], [], [], []
+        cur_q = q_in
+        for i in range(nb):
+            t = dict(zip(_BLOCK_SLOTS, flat[i * ns:(i + 1) * ns]))
+            has_res = (start + i) < total - 1
+            tensors.append(t)
+            preps.append(_prep_items(t, quant, has_res, cur_q, dev, prep_items, wq_items))
+            cur_q = (t["qaddmin"], t["qaddmax"])
+        _run_batches(prep_items, wq_items)
+        # pass 2: the blocks
         states = []
         cur_x, cur_op = x, x_op
         cur_skip = _as_pitched(skip_in.detach(), ld) if skip_in is not None else None
         cur_q = q_in
         for i in range(nb):
-            t = dict(zip(_BLOCK_SLOTS, flat[i * ns:(i + 1) * ns]))
+            t, P = tensors[i], preps[i]
             first, has_res = (start + i) == 0, (start + i) < total - 1
             Chid = t["W1"].shape[0]
-            P = _prep_block(t, quant, first, has_res, cur_q, dev)
             A = _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant)
             blk = TcnBlock()
             _fill_block(blk, t, P, quant, first, has_res, dils[i], B, M, ld, cur_q)
@@ -400,6 +426,7 @@ class FusedTCNFunction(Function):
                        gxd=torch.empty((B, Cio, ld), device=dev))
         ws = torch.empty(int(L.fqss_tcn_ws_bytes(B, Cio, Chid)), dtype=torch.uint8, device=dev)
         grads = [None] * ctx.nflat
+        wq_items, keep = [], []
         for i in range(nb - 1, -1, -1):
             st = states[i]
             t = st.t
@@ -423,12 +450,15 @@ class FusedTCNFunction(Function):
             # gradients w.r.t. the fake-quantised weights -> raw weights + per-channel ranges
             def wback(gq, wname, lo, hi, shape):
                 w = t[wname]
-                if quant:
+                if quant:      # queued: ONE batched launch for the weight quantisers of all blocks after the loop
                     gw = torch.empty_like(w, memory_format=torch.contiguous_format)
                     gmin, gmax = torch.empty_like(t[lo]), torch.empty_like(t[hi])
-                    ch = w.shape[0]
-                    inner = w.numel() // ch
-                    check(lib().fqss_fq_weight_bwd(ptr(gq), ptr(w), ptr(gw), ptr(gmin), ptr(gmax), 1, ch, inner, ptr(t[lo]), ptr(t[hi]), 8, s))
+                    it = N.WqItem()
+                    it.g, it.w, it.out, it.g_rmin, it.g_rmax = ptr(gq), ptr(w), ptr(gw), ptr(gmin), ptr(gmax)
+                    it.rmin, it.rmax = ptr(t[lo]), ptr(t[hi])
+                    it.outer, it.ch, it.inner, it.n_bits = 1, w.shape[0], w.numel() // w.shape[0], 8
+                    wq_items.append(it)
+                    keep.append(gq)
                     return gw, gmin, gmax
                 return gq.view(shape), None, None
             out["W1"], out["w1min"], out["w1max"] = wback(G["dW1q"], "W1", "w1min", "w1max", t["W1"].shape)
@@ -452,6 +482,8 @@ class FusedTCNFunction(Function):
             for j, name in enumerate(_BLOCK_SLOTS):
                 if t[name] is not None and name in out and out[name] is not None and ctx.needs_input_grad[3 + base + j]:
                     grads[base + j] = out[name].reshape(t[name].shape)
+        _run_batches([], wq_items, wq_bwd=True)
+        del keep
         g_skip_in = g_ss[:, :, :M] if (not states[0].first and ctx.needs_input_grad[1]) else None
         return (g_x[:, :, :M], g_skip_in, None) + tuple(grads)
 

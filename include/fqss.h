@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 8
+#define FQSS_ABI_VERSION 9
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -54,6 +54,21 @@ int fqss_fq_weight_bwd(const float* g, const float* w, float* gw, float* g_rmin,
                        void* stream);
 /* first-call observer: max_range = amax, min_range = amin over non-channel dims (qat_quant.py:373-375) */
 int fqss_weight_observe(const float* w, int outer, int ch, int inner, float* rmin, float* rmax, void* stream);
+
+/* Batched forms of the two calls above: one launch covers up to 48 weight tensors (the QAT step has ~100 of them, each
+ * a few thousand elements -- launch-bound one by one).  `items` is a HOST array. */
+typedef struct fqss_wq_item {
+    const float* g;      /* bwd: dL/d(fake-quantised weight); fwd: unused (NULL)             */
+    const float* w;      /* raw weight                                                        */
+    float* out;          /* bwd: dL/dw (may be NULL); fwd: fake-quantised weight              */
+    float* g_rmin;       /* bwd only: range gradients, `ch` entries each                      */
+    float* g_rmax;
+    const float* rmin;
+    const float* rmax;
+    int32_t outer, ch, inner, n_bits;
+} fqss_wq_item;
+int fqss_fq_weight_fwd_batch(const fqss_wq_item* items, int n, void* stream);
+int fqss_fq_weight_bwd_batch(const fqss_wq_item* items, int n, void* stream);
 
 /* Q4  activation observer: min <- a*min + (1-a)*x.min(), max likewise (qat_quant.py:228-232) */
 int fqss_act_observe(const float* x, int64_t rows, int64_t cols, int64_t ld, float* rmin, float* rmax,
@@ -154,7 +169,8 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
  *   out[b,o,m] = s1[o] * sum_k act[b,k,m] * w[o,k] + s0[o]  (+ addend[b,o,m])
  * act [B][a_rows][ld] and w [N][K] are bf16.  With integer fake-quant codes as operands the accumulation is
  * exact (order independent); s1/s0 carry the de-quantisation affine and the bias.  K % 64 == 0,
- * N % 128 == 0, ld % 8 == 0.  Outputs: out_f32 and/or out_bf16 ([B][N][ld]); addend needs out_f32.
+ * N % 128 == 0, ld % 8 == 0.  Outputs: out_f32 and/or out_bf16 ([B][N][ld]); addend needs out_f32.  s1 / s0 may be
+ * NULL (= all ones / all zeros).
  * a_rows = 0 means a_rows = K.  a_rows < K (a_rows % 64 == 0) makes reduction index k read activation row
  * k % a_rows: with act = [hi ; lo] (a_rows = 2C, x = hi + lo in bf16 pairs) and w = [w_hi | w_hi | w_lo]
  * (K = 3C) one launch computes the three-term split product hi*w_hi + lo*w_hi + hi*w_lo, i.e. an fp32-grade
@@ -243,6 +259,14 @@ typedef struct fqss_tcn_block {
 int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const float* bias, const float* amin,
                   const float* amax, void* Wc, void* WcT, float* s1, float* s0, float* dws, int N, int K, int Ntot,
                   int n_off, int split, void* stream);
+
+/* Batched fqss_tcn_prep: `items` is a HOST array; one launch covers up to 32 convolutions. */
+typedef struct fqss_prep_item {
+    const float* W; const float* wmin; const float* wmax; const float* bias; const float* amin; const float* amax;
+    void* Wc; void* WcT; float* s1; float* s0; float* dws;
+    int32_t N, K, Ntot, n_off, split, _pad;
+} fqss_prep_item;
+int fqss_tcn_prep_batch(const fqss_prep_item* items, int n, void* stream);
 
 /* fp32 values -> bf16 GEMM operand of the first block (codes w.r.t. {rmin,rmax}; NULL ranges: plain cast) */
 int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t rows, int M, const float* rmin,
