@@ -20,6 +20,7 @@
 #include "fqss_common.cuh"
 #include "tc_common.cuh"
 #include "gemm_tc.cuh"
+#include "tcn_common.cuh"
 
 namespace fqss {
 
@@ -357,6 +358,13 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 2) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 2 * NT);
+    }
+    if (EPI == EPI_EXPAND && p.rc) {
+        RowConstJob job;
+        job.stats = p.stats; job.rc = p.rc; job.B = p.B; job.n_elems = p.n_elems;
+        job.qa_min = p.q1_min; job.qa_max = p.q1_max; job.qb_min = p.q2_min; job.qb_max = p.q2_max;
+        job.qc_min = p.q3_min; job.qc_max = p.q3_max;
+        rowconst_last_cta(job, gridDim.x, (int)threadIdx.x < 2 * p.B || !stat_sm);
     }
 }
 

@@ -28,6 +28,9 @@ struct Args {
     const float* slope;
     const float* q1_min; const float* q1_max;
     double* stats;
+    // EPI_EXPAND: the last CTA turns the finished statistics into the row constants rc[RC_HDR + 2*B] (tcn_common.cuh)
+    float* rc; double n_elems;
+    const float* q2_min; const float* q2_max; const float* q3_min; const float* q3_max;
     // EPI_RESSKIP: columns [0,Nres) = residual conv, [Nres,N) = skip conv
     int n_res;                   // 128, or 0 for the last block (no residual path)
     int first_block;             // 1: skip accumulator starts here (no adds-quantiser)

@@ -49,6 +49,47 @@ __device__ __forceinline__ float prelu_f(float y, float a) { return y > 0.f ? y 
 __device__ __forceinline__ float gln_apply(const GlnRow& g, float a) { return __fadd_rn(__fmul_rn(a, g.scale), g.shift); }
 __device__ __forceinline__ float gln_xhat(const GlnRow& g, float a) { return (a - g.mu) * g.rstd; }
 
+// The row constants are produced by the LAST CTA of the kernel that completes the statistics (ticket counter in the
+// slot after the 2*B statistics doubles, zeroed together with them): no extra launch between producer and consumer.
+struct RowConstJob {
+    double* stats;                       // [2*B] sums + 1 slot used as the arrival counter
+    float* rc;                           // [RC_HDR + 2*B]
+    int B;
+    double n_elems;
+    const float *qa_min, *qa_max, *qb_min, *qb_max, *qc_min, *qc_max;   // NULL pairs are skipped
+};
+
+// Call from ALL threads of every CTA after the CTA's last contribution to job.stats has been issued.
+// `contributed`: this thread issued global atomics on job.stats (only those threads pay for the fence).
+__device__ __forceinline__ void rowconst_last_cta(const RowConstJob& j, unsigned total_ctas, bool contributed) {
+    __shared__ int is_last;
+    if (contributed) __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(reinterpret_cast<unsigned*>(j.stats + 2 * j.B), 1u);
+        is_last = (t == total_ctas - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int t = threadIdx.x;
+    if (t < 3) {
+        const float* mn = t == 0 ? j.qa_min : (t == 1 ? j.qb_min : j.qc_min);
+        const float* mx = t == 0 ? j.qa_max : (t == 1 ? j.qb_max : j.qc_max);
+        if (mn) {
+            const ActQF q = load_actqf(mn, mx, 8);
+            j.rc[4 * t] = q.mn; j.rc[4 * t + 1] = q.delta; j.rc[4 * t + 2] = q.inv; j.rc[4 * t + 3] = q.levels;
+        }
+    }
+    for (int b = t; b < j.B; b += blockDim.x) {
+        const double mean = __ldcg(j.stats + 2 * b) / j.n_elems;
+        double var = __ldcg(j.stats + 2 * b + 1) / j.n_elems - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        j.rc[RC_HDR + 2 * b] = (float)mean;
+        j.rc[RC_HDR + 1 + 2 * b] = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+    }
+}
+
 // ---- y1 -> a1 = FQ1(PReLU(y1)) -> n1 = gLN1(a1) -> a2 = FQ2(n1)
 struct Hidden1 {
     int quant;

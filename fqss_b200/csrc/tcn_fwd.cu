@@ -108,30 +108,6 @@ __global__ void tcn_prep_batch_kernel(const __grid_constant__ PrepBatch b) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Row constants: one warp turns the finished fp64 statistics into {mean, rstd} per sample and the two
-// quantisers around the gLN into {min, delta, 1/delta, levels} (layout: tcn_common.cuh).
-// ---------------------------------------------------------------------------------------------
-__global__ void tcn_rowconst_kernel(const double* __restrict__ stats, int B, double n_elems, const float* qa_min, const float* qa_max,
-                                    const float* qb_min, const float* qb_max, const float* qc_min, const float* qc_max, float* __restrict__ rc) {
-    const int t = threadIdx.x;
-    if (t < 3) {
-        const float* mn = t == 0 ? qa_min : (t == 1 ? qb_min : qc_min);
-        const float* mx = t == 0 ? qa_max : (t == 1 ? qb_max : qc_max);
-        if (mn) {
-            const ActQF q = load_actqf(mn, mx, 8);
-            rc[4 * t] = q.mn; rc[4 * t + 1] = q.delta; rc[4 * t + 2] = q.inv; rc[4 * t + 3] = q.levels;
-        }
-    }
-    for (int b = t; b < B; b += blockDim.x) {
-        const double mean = stats[2 * b] / n_elems;
-        double var = stats[2 * b + 1] / n_elems - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        rc[RC_HDR + 2 * b] = (float)mean;
-        rc[RC_HDR + 1 + 2 * b] = (float)(1.0 / sqrt(var + (double)GLN_EPS));
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
 // K2: depthwise kernel.  One CTA per (sample, channel) row.
 //   phase 0  (quantised model) tabulate code1 -> a2 = FQ2(gLN1(decode1(code1)))        256 entries
 //   phase 1  y1 (128-bit loads) -> PReLU -> code1 -> table -> a2 row in shared memory, zero halo of
@@ -259,6 +235,27 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
             atomicAdd(p.stats3 + 2 * b, vv[0]);
             atomicAdd(p.stats3 + 2 * b + 1, vv[1]);
         }
+    }
+}
+
+// Row constants after K2: with 16 K short-lived row CTAs a per-CTA arrival ticket costs more than this one-warp launch
+// (measured: +20 us on the depthwise kernel vs 6.5 us here); the GEMM (148 persistent CTAs) finalises in its last CTA.
+__global__ void tcn_rowconst_kernel(RowConstJob j) {
+    const int t = threadIdx.x;
+    if (t < 3) {
+        const float* mn = t == 0 ? j.qa_min : (t == 1 ? j.qb_min : j.qc_min);
+        const float* mx = t == 0 ? j.qa_max : (t == 1 ? j.qb_max : j.qc_max);
+        if (mn) {
+            const ActQF q = load_actqf(mn, mx, 8);
+            j.rc[4 * t] = q.mn; j.rc[4 * t + 1] = q.delta; j.rc[4 * t + 2] = q.inv; j.rc[4 * t + 3] = q.levels;
+        }
+    }
+    for (int b = t; b < j.B; b += blockDim.x) {
+        const double mean = j.stats[2 * b] / j.n_elems;
+        double var = j.stats[2 * b + 1] / j.n_elems - mean * mean;
+        var = var > 0.0 ? var : 0.0;
+        j.rc[RC_HDR + 2 * b] = (float)mean;
+        j.rc[RC_HDR + 1 + 2 * b] = (float)(1.0 / sqrt(var + (double)GLN_EPS));
     }
 }
 
@@ -488,20 +485,17 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const int rows = p->B * p->Chid;
-    cudaMemsetAsync(p->stats1, 0, (size_t)p->B * 2 * sizeof(double), s);
-    cudaMemsetAsync(p->stats3, 0, (size_t)p->B * 2 * sizeof(double), s);
+    cudaMemsetAsync(p->stats1, 0, ((size_t)p->B * 2 + 1) * sizeof(double), s);     // sums + the arrival counter of the finaliser
+    cudaMemsetAsync(p->stats3, 0, ((size_t)p->B * 2 + 1) * sizeof(double), s);
     // K1
     tcg::Args a{};
     a.B = p->B; a.M = p->M; a.K = p->Cio; a.N = p->Chid; a.ld = p->ld; a.s1 = p->s1_1; a.s0 = p->s0_1; a.quant = p->quant;
     if (p->split) { a.K = 3 * p->Cio; a.a_rows = 2 * p->Cio; }
     a.out_f32 = p->y1; a.slope = p->slope1; a.q1_min = p->q1.rmin; a.q1_max = p->q1.rmax; a.stats = p->stats1;
+    a.rc = p->rc1; a.n_elems = (double)p->Chid * (double)p->M;
+    a.q2_min = p->q2.rmin; a.q2_max = p->q2.rmax; a.q3_min = p->q3.rmin; a.q3_max = p->q3.rmax;
     rc = tcg::run(tcg::EPI_EXPAND, p->x_op, p->Wc1, a, s);
     if (rc) return rc;
-    const double n_elems = (double)p->Chid * (double)p->M;
-    {
-        FQSS_PROF("tcn_rowconst", s);
-        tcn_rowconst_kernel<<<1, 64, 0, s>>>(p->stats1, p->B, n_elems, p->q1.rmin, p->q1.rmax, p->q2.rmin, p->q2.rmax, p->q3.rmin, p->q3.rmax, p->rc1);
-    }
     // K2 / K3a
     {
         const int dpad = dw_pad(p->dil);
@@ -516,7 +510,11 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
             cfg = true;
         }
 #define FQSS_DW_LAUNCH(Q, D) do { FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s); tcn_dw_fwd_kernel<Q, D, (Q ? 256 : 128)><<<rows, (Q ? 256 : 128), smem, s>>>(*p); } while (0)
-#define FQSS_RC3_LAUNCH() do { FQSS_PROF("tcn_rowconst", s); tcn_rowconst_kernel<<<1, 64, 0, s>>>(p->stats3, p->B, n_elems, p->q3.rmin, p->q3.rmax, p->q4.rmin, p->q4.rmax, nullptr, nullptr, p->rc3); } while (0)
+        RowConstJob job3;
+        job3.stats = p->stats3; job3.rc = p->rc3; job3.B = p->B; job3.n_elems = (double)p->Chid * (double)p->M;
+        job3.qa_min = p->q3.rmin; job3.qa_max = p->q3.rmax; job3.qb_min = p->q4.rmin; job3.qb_max = p->q4.rmax;
+        job3.qc_min = nullptr; job3.qc_max = nullptr;
+#define FQSS_RC3_LAUNCH() do { FQSS_PROF("tcn_rowconst", s); tcn_rowconst_kernel<<<1, 64, 0, s>>>(job3); } while (0)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DW_LAUNCH(true, 0); else if (mode == 1) FQSS_DW_LAUNCH(true, 1);

@@ -106,8 +106,8 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
     y1 = torch.empty((B, Chid, ld), device=dev)
     y3 = torch.empty((B, Chid, ld), device=dev)
     a4 = torch.empty((B, 2 * Chid, ld), dtype=bf, device=dev)
-    st1 = torch.empty(2 * B, dtype=torch.float64, device=dev)
-    st3 = torch.empty(2 * B, dtype=torch.float64, device=dev)
+    st1 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
+    st3 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
     rc1 = torch.empty(12 + 2 * B, device=dev)
     rc3 = torch.empty(12 + 2 * B, device=dev)
     xs = [x0, torch.empty((B, Cio, ld), device=dev), torch.empty((B, Cio, ld), device=dev)]

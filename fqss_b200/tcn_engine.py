@@ -231,7 +231,7 @@ def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
 def _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant=True):
     bf = torch.bfloat16
     A = dict(y1=torch.empty((B, Chid, ld), device=dev), y3=torch.empty((B, Chid, ld), device=dev),
-             stats1=torch.empty(2 * B, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B, dtype=torch.float64, device=dev),
+             stats1=torch.empty(2 * B + 1, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B + 1, dtype=torch.float64, device=dev),
              a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), skip_y=torch.empty((B, Cio, ld), device=dev),
              skip_out=torch.empty((B, Cio, ld), device=dev), rc1=torch.empty(12 + 2 * B, device=dev),
              rc3=torch.empty(12 + 2 * B, device=dev))

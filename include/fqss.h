@@ -209,8 +209,9 @@ int fqss_wgrad_codes(const void* dY_bf16, const void* x_op_bf16, int B, int M, i
 
 /* ---------------------------------------------------------------------------------------------
  * M1  fused ConvBlock of the TCN (convtasnetq.py:11-42 after quantize_model :270-277), forward and
- *     backward, for the steady state (observers off).  Four forward launches per block (+ 2 one-warp
- *     launches that turn the gLN statistics into per-sample constants):
+ *     backward, for the steady state (observers off).  Four forward launches per block (the last CTA of K1 / K2
+ *     turns the finished gLN statistics into per-sample constants for the next kernel; stats1 / stats3 hold 2*B sums
+ *     plus one slot used as its arrival counter = 2*B + 1 doubles):
  *       K1 expand GEMM (+bias, PReLU/FQ statistics for the first gLN)          x_op  -> y1, stats1
  *       K2 depthwise kernel (PReLU+FQ, gLN+FQ on load; 3-tap dilated FIR; stats) y1   -> y3, stats3
  *       K3a hidden quantiser (PReLU+FQ, gLN+FQ -> bf16 operand)                  y3   -> a4_op
