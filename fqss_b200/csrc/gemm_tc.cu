@@ -182,12 +182,22 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t ld = p.ld;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int fold_b = -1;
+        float fold_rstd = 1.f, fold_nrm = 0.f;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int n_idx = t % nt, mrow = t / nt;
             const int b = mrow / mt, m0 = (mrow % mt) * BM;
             const int m = m0 + q * 32 + lane;
             const bool valid = m < p.M;
             float st_s = 0.f, st_ss = 0.f;
+            if (EPI == EPI_RESSKIP && p.fold_stats && b != fold_b) {      // per-sample constants of the folded gLN
+                const double mean = __ldg(p.fold_stats + 2 * b) / p.n_elems;
+                double var = __ldg(p.fold_stats + 2 * b + 1) / p.n_elems - mean * mean;
+                var = var > 0.0 ? var : 0.0;
+                fold_rstd = (float)(1.0 / sqrt(var + (double)GLN_EPS));
+                fold_nrm = -fold_rstd * (float)mean;
+                fold_b = b;
+            }
             const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + h * COLS);
             const int obase = n_idx * NT + h * COLS;      // first output channel of this warp's column group
 
@@ -280,7 +290,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             const int64_t lo_off = (int64_t)p.n_res * ld;
 #pragma unroll
                             for (int j = 0; j < CW; ++j) {
-                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                const float y = p.fold_stats ? fmaf(__uint_as_float(v[j]), fold_rstd, fmaf(fold_nrm, s1c[j], s0c[j]))
+                                                             : fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
                                 if (ry) ry[j * ld] = y;
                                 const float z = __fadd_rn(pre[j], y);
                                 xo[j * ld] = z;
@@ -294,7 +305,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         float* so = p.skip_out + i0;
 #pragma unroll
                         for (int j = 0; j < CW; ++j) {
-                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            const float y = (!p.quant && p.fold_stats) ? fmaf(__uint_as_float(v[j]), fold_rstd, fmaf(fold_nrm, s1c[j], s0c[j]))
+                                                                       : fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
                             if (sy) sy[j * ld] = y;
                             const float sk = p.quant ? actqf_fq(qskip, y) : y;
                             if (p.first_block) {

@@ -42,6 +42,10 @@ struct Args {
     const float* qskip_min; const float* qskip_max;
     const float* qadd_min; const float* qadd_max;
     const float* qadds_min; const float* qadds_max;
+    // EPI_RESSKIP, float model with the second gLN folded into this conv (fqss_tcn_prep_fold): the operand is
+    // a3 = PReLU(y3), s1 = u, s0 = v, and y = rstd_b * (acc - mu_b * u[o]) + v[o] with {mu_b, rstd_b} from these
+    // finished statistics ({sum, sum of squares} per sample over n_elems elements).  NULL: plain affine.
+    const double* fold_stats;
 };
 
 

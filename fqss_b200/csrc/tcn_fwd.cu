@@ -107,6 +107,37 @@ __global__ void tcn_prep_batch_kernel(const __grid_constant__ PrepBatch b) {
     }
 }
 
+// Float (teacher) model, inference: the second gLN is folded into the res/skip conv it feeds.  With a3 = PReLU(y3),
+// n3[c] = rstd_b * gamma_c * (a3[c] - mu_b) + beta_c and y[o] = sum_c W[o,c] n3[c] + bias[o]:
+//   y[o] = rstd_b * (sum_c (W[o,c] gamma_c) a3[c]  -  mu_b * u[o]) + v[o],   u[o] = sum_c W[o,c] gamma_c,
+//                                                                         v[o] = bias[o] + sum_c W[o,c] beta_c
+// so the depthwise kernel can hand a3 to the GEMM directly (no normalisation pass over the hidden tensor).
+// Wc = [hi | hi | lo] split of W*gamma; u -> s1, v -> s0 (fp64 sums).
+__global__ void tcn_prep_fold_kernel(const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ Wc, float* __restrict__ u,
+                                     float* __restrict__ v, int K, int n_off) {
+    __shared__ double sh[2 * 32];
+    const int o = blockIdx.x;
+    double su = 0.0, sv = 0.0;
+    __nv_bfloat16* row = Wc + (int64_t)(n_off + o) * 3 * K;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        const float w = W[(int64_t)o * K + k];
+        const float wg = __fmul_rn(w, gamma[k]);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(wg);
+        row[k] = hi;
+        row[K + k] = hi;
+        row[2 * K + k] = __float2bfloat16_rn(wg - __bfloat162float(hi));
+        su += (double)w * (double)gamma[k];
+        sv += (double)w * (double)beta[k];
+    }
+    double vv[2] = {su, sv};
+    block_sum<2>(vv, sh);
+    if (threadIdx.x == 0) {
+        u[n_off + o] = (float)vv[0];
+        v[n_off + o] = (float)(vv[1] + (bias ? (double)bias[o] : 0.0));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2: depthwise kernel.  One CTA per (sample, channel) row.
 //   phase 0  (quantised model) tabulate code1 -> a2 = FQ2(gLN1(decode1(code1)))        256 entries
@@ -173,13 +204,12 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
     const float2 bias = f2s(__ldg(p.bdw + c));
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
-    float2 qinv = f2s(0.f), qoff = f2s(0.f);
-    if (QUANT) {
-        q3 = load_actqf_rc(p.rc1 + 8);
-        qinv = f2s(q3.inv);
-        qoff = f2s(-q3.mn * q3.inv);
-    }
+    if (QUANT) q3 = load_actqf_rc(p.rc1 + 8);
     float* y3 = p.y3 + r * p.ld;
+    uint32_t* code3 = (QUANT && p.code3) ? reinterpret_cast<uint32_t*>(p.code3 + r * p.ld) : nullptr;
+    const bool fold = !QUANT && p.split == 2;
+    __nv_bfloat16* a3_hi = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + ((int64_t)b * 2 * p.Chid + c) * p.ld;
+    __nv_bfloat16* a3_lo = a3_hi + (int64_t)p.Chid * p.ld;
     // statistics of a3 = FQ3(PReLU(y3)): the quantised model accumulates the integer codes (sum c, sum c^2, exact),
     // a3 = delta*c + min is expanded at the end; the float model sums the values
     float s = 0.f, ss = 0.f;
@@ -189,12 +219,22 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
         dw_taps<DMODE>(row, v, d, L, C, R);
         const float2 o01 = __ffma2_rn(w2, lo2(R), __ffma2_rn(w1, lo2(C), __ffma2_rn(w0, lo2(L), bias)));
         const float2 o23 = __ffma2_rn(w2, hi2(R), __ffma2_rn(w1, hi2(C), __ffma2_rn(w0, hi2(L), bias)));
-        stg4(y3 + 4 * v, make_float4(o01.x, o01.y, o23.x, o23.y));
         const int nval = M - 4 * v;      // statistics over valid frames only
         const float2 z01 = make_float2(prelu_f(o01.x, slope3), prelu_f(o01.y, slope3));
         const float2 z23 = make_float2(prelu_f(o23.x, slope3), prelu_f(o23.y, slope3));
+        if (!QUANT && fold) {
+            // gLN2 is folded into the res/skip GEMM (tcn_prep_fold_kernel): its operand is a3 itself, as a [hi ; lo] pair
+            const uint2 pk = float4_to_bf16x4(z01.x, z01.y, z23.x, z23.y);
+            const float4 hv = bf16x4_to_float4(pk);
+            *reinterpret_cast<uint2*>(a3_hi + 4 * v) = pk;
+            *reinterpret_cast<uint2*>(a3_lo + 4 * v) = float4_to_bf16x4(z01.x - hv.x, z01.y - hv.y, z23.x - hv.z, z23.y - hv.w);
+        } else {
+            stg4(y3 + 4 * v, make_float4(o01.x, o01.y, o23.x, o23.y));
+        }
         if (QUANT) {
-            const float2 t01 = __ffma2_rn(z01, qinv, qoff), t23 = __ffma2_rn(z23, qinv, qoff);
+            // exact codes of FQ3 (same arithmetic as every later consumer): saved here so that the hidden quantiser and
+            // the backward sums read 1 B/frame instead of re-deriving the code from y3
+            const float2 t01 = actqf_t2(q3, z01), t23 = actqf_t2(q3, z23);
             unsigned c0 = code_u8(t01.x), c1 = code_u8(t01.y), c2 = code_u8(t23.x), c3 = code_u8(t23.y);
             if (nval < 4) {
                 c3 = 0u;
@@ -202,6 +242,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
                 if (nval < 2) c1 = 0u;
                 if (nval < 1) c0 = 0u;
             }
+            if (code3) code3[v] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
             sc += c0 + c1 + c2 + c3;
             scc += c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
         } else {
@@ -260,8 +301,8 @@ __global__ void tcn_rowconst_kernel(RowConstJob j) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K3a: hidden quantiser  y3 -> a4 operand (bf16 code / value).  Quantised model: PReLU -> code3 ->
-// table (code3 -> code4 = FQ4-code(gLN2(decode3(code3)))).  6 B/element.
+// K3a: hidden quantiser -> a4 operand (bf16 code / value).  Quantised model: code3 (saved by K2) -> per-row table
+// (code3 -> code4 = FQ4-code(gLN2(decode3(code3)))): 3 B/element.  Float model: y3 -> PReLU -> gLN2 -> [hi ; lo] pair.
 // ---------------------------------------------------------------------------------------------
 template <bool QUANT, int NTH>
 __global__ void __launch_bounds__(NTH) tcn_hidden_fq_kernel(const fqss_tcn_block p) {
@@ -269,34 +310,42 @@ __global__ void __launch_bounds__(NTH) tcn_hidden_fq_kernel(const fqss_tcn_block
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const Hidden3 h = load_hidden3(p, b, c);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + r * p.ld;
     if (QUANT) {
-        for (int i = threadIdx.x; i < 256; i += NTH) lut[i] = chain_fq_code(h.q3, h.g, h.q4, i);
+        // code3 (saved by the depthwise kernel) -> code4 through the per-row table: 1 B in, 2 B out per frame.
+        // The table holds the bf16 bit pattern of code4, so a frame costs one LDS + one PRMT.
+        unsigned short* lut16 = reinterpret_cast<unsigned short*>(lut);
+        for (int i = threadIdx.x; i < 256; i += NTH)
+            lut16[i] = __bfloat16_as_ushort(__float2bfloat16_rn(chain_fq_code(h.q3, h.g, h.q4, i)));
         __syncthreads();
+        const uint2* c3 = reinterpret_cast<const uint2*>(p.code3 + r * p.ld);       // rows are 8-byte aligned (ld % 8 == 0)
+        uint4* o16 = reinterpret_cast<uint4*>(out);
+        const int n8 = (p.M + 7) >> 3;
+        for (int v = threadIdx.x; v < n8; v += NTH) {
+            const uint2 cw = __ldg(c3 + v);
+            const uint32_t w[2] = {cw.x, cw.y};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t a0 = lut16[w[k] & 255u], a1 = lut16[(w[k] >> 8) & 255u];
+                const uint32_t a2 = lut16[(w[k] >> 16) & 255u], a3 = lut16[w[k] >> 24];
+                o[2 * k] = a0 | (a1 << 16);
+                o[2 * k + 1] = a2 | (a3 << 16);
+            }
+            o16[v] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        return;
     }
     const float* y3 = p.y3 + r * p.ld;
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + r * p.ld;
-    uint32_t* code3 = p.code3 ? reinterpret_cast<uint32_t*>(p.code3 + r * p.ld) : nullptr;
     const int nvec = (p.M + 3) >> 2;
     for (int v = threadIdx.x; v < nvec; v += NTH) {
         const float4 y = ldg4_stream(y3 + 4 * v);
-        float o0, o1, o2, o3;
-        if (QUANT) {
-            const float2 t01 = actqf_t2(h.q3, make_float2(prelu_f(y.x, h.slope), prelu_f(y.y, h.slope)));
-            const float2 t23 = actqf_t2(h.q3, make_float2(prelu_f(y.z, h.slope), prelu_f(y.w, h.slope)));
-            const unsigned i0 = code_u8(t01.x), i1 = code_u8(t01.y), i2 = code_u8(t23.x), i3 = code_u8(t23.y);
-            if (code3) code3[v] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
-            o0 = lut[i0];
-            o1 = lut[i1];
-            o2 = lut[i2];
-            o3 = lut[i3];
-        } else {
-            o0 = gln_apply(h.g, prelu_f(y.x, h.slope));
-            o1 = gln_apply(h.g, prelu_f(y.y, h.slope));
-            o2 = gln_apply(h.g, prelu_f(y.z, h.slope));
-            o3 = gln_apply(h.g, prelu_f(y.w, h.slope));
-        }
+        const float o0 = gln_apply(h.g, prelu_f(y.x, h.slope));
+        const float o1 = gln_apply(h.g, prelu_f(y.y, h.slope));
+        const float o2 = gln_apply(h.g, prelu_f(y.z, h.slope));
+        const float o3 = gln_apply(h.g, prelu_f(y.w, h.slope));
         const uint2 pk = float4_to_bf16x4(o0, o1, o2, o3);
-        if (QUANT || !p.split) {
+        if (!p.split) {
             *reinterpret_cast<uint2*>(out + 4 * v) = pk;
         } else {
             // [hi ; lo] pair: sample b owns rows [2*b*Chid, 2*(b+1)*Chid); residual = value - bf16(value)
@@ -394,12 +443,14 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
                  "%s: row too long for shared-memory staging (M=%d, dil=%d)", who, p->M, p->dil);
     FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
-    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && p->y3 && p->stats1 && p->stats3 && p->a4_op && p->skip_out && p->rc1 && p->rc3, -1,
+    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && (p->y3 || p->split == 2) && p->stats1 && p->stats3 && p->a4_op && p->skip_out && p->rc1 && p->rc3, -1,
                  "%s: missing activation buffers", who);
     FQSS_REQUIRE(!p->split || !p->quant, -1, "%s: split operands are a float-model (quant == 0) feature", who);
+    FQSS_REQUIRE(p->split >= 0 && p->split <= 2, -1, "%s: split must be 0, 1 or 2", who);
     if (p->has_res) FQSS_REQUIRE(p->x_out && p->x_out_op, -1, "%s: missing residual buffers", who);
     if (!p->first_block) FQSS_REQUIRE(p->skip_in, -1, "%s: missing skip_in", who);
     if (p->quant) {
+        FQSS_REQUIRE(p->code3, -1, "%s: the quantised path needs the code3 buffer (the depthwise kernel hands FQ3's codes to the hidden quantiser through it)", who);
         const fqss_qrange* qs[] = {&p->q1, &p->q2, &p->q3, &p->q4, &p->qskip};
         for (auto q : qs) FQSS_REQUIRE(q->rmin && q->rmax, -1, "%s: missing quantiser range", who);
         if (p->has_res) FQSS_REQUIRE(p->qres.rmin && p->qadd.rmin, -1, "%s: missing residual quantisers", who);
@@ -426,6 +477,14 @@ int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const fl
     tcn_prep_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(W, wmin, wmax, bias, amin, amax, (__nv_bfloat16*)Wc, (__nv_bfloat16*)WcT, s1,
                                                          s0, dws, K, Ntot, n_off, split);
     return check_launch("tcn_prep");
+}
+
+int fqss_tcn_prep_fold(const float* W, const float* bias, const float* gamma, const float* beta, void* Wc, float* u, float* v, int N,
+                       int K, int Ntot, int n_off, void* stream) {
+    FQSS_REQUIRE(W && gamma && beta && Wc && u && v && N > 0 && K > 0 && n_off >= 0 && n_off + N <= Ntot, -1, "tcn_prep_fold: bad argument");
+    FQSS_PROF("tcn_prep", stream);
+    tcn_prep_fold_kernel<<<N, 128, 0, (cudaStream_t)stream>>>(W, bias, gamma, beta, (__nv_bfloat16*)Wc, u, v, K, n_off);
+    return check_launch("tcn_prep_fold");
 }
 
 int fqss_tcn_prep_batch(const fqss_prep_item* items, int n, void* stream) {
@@ -524,8 +583,10 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
         } else {
             if (mode == 0) FQSS_DW_LAUNCH(false, 0); else if (mode == 1) FQSS_DW_LAUNCH(false, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(false, 2); else FQSS_DW_LAUNCH(false, 3);
-            FQSS_RC3_LAUNCH();
-            { FQSS_PROF("tcn_hidden_fq(float)", s); tcn_hidden_fq_kernel<false, 256><<<rows, 256, 0, s>>>(*p); }
+            if (p->split != 2) {
+                FQSS_RC3_LAUNCH();
+                { FQSS_PROF("tcn_hidden_fq(float)", s); tcn_hidden_fq_kernel<false, 256><<<rows, 256, 0, s>>>(*p); }
+            }
         }
 #undef FQSS_DW_LAUNCH
 #undef FQSS_RC3_LAUNCH
@@ -536,6 +597,7 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     tcg::Args k{};
     k.B = p->B; k.M = p->M; k.K = p->Chid; k.N = p->has_res ? 2 * p->Cio : p->Cio; k.ld = p->ld;
     if (p->split) { k.K = 3 * p->Chid; k.a_rows = 2 * p->Chid; k.split = 1; }
+    if (p->split == 2) { k.fold_stats = p->stats3; k.n_elems = (double)p->Chid * (double)p->M; }
     k.s1 = p->s1_2; k.s0 = p->s0_2; k.quant = p->quant;
     k.n_res = p->has_res ? p->Cio : 0; k.first_block = p->first_block;
     k.res_y = p->res_y; k.skip_y = p->skip_y; k.x_in = p->x_in; k.x_out = p->x_out; k.x_out_op = (__nv_bfloat16*)p->x_out_op;

@@ -244,10 +244,11 @@ typedef struct fqss_tcn_block {
      * 12 + 2*B floats each = {min, delta, 1/delta, levels} of up to three quantisers, then {mean, rstd} per sample
      * (rc1: q1, q2, q3 and gLN1 from stats1; rc3: q3, q4 and gLN2 from stats3) */
     float* rc1; float* rc3;
-    /* quantised model, training: the 8-bit codes of a1 = FQ1(PReLU(y1)) and a3 = FQ3(PReLU(y3)), one byte per frame
-     * ([B][Chid][ld]), written by forward so that backward stages that need only the codes (FQ2/FQ4 masks, gLN
-     * sums, tap gradients) read 1 B/element instead of re-deriving them from the fp32 pre-activations.  NULL in
-     * inference (forward skips the stores; backward then refuses to run). */
+    /* quantised model: the 8-bit codes of a1 = FQ1(PReLU(y1)) and a3 = FQ3(PReLU(y3)), one byte per frame
+     * ([B][Chid][ld]).  code3 is REQUIRED: the depthwise kernel writes it and the hidden quantiser (code3 -> FQ4
+     * code, 3 B/element) reads it instead of y3.  Both are re-read by the backward stages that need only the codes
+     * (FQ2/FQ4 masks, gLN sums, tap gradients).  code1 may be NULL in inference (forward skips the store; backward
+     * then refuses to run). */
     uint8_t* code1; uint8_t* code3;
 } fqss_tcn_block;
 
