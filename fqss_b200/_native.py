@@ -77,6 +77,7 @@ _SIGS = {
     "fqss_pw_gemm_ex": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, i32, vp]),
     "fqss_split_bf16": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, vp]),
     "fqss_tcn_prep": (i32, [vp] * 11 + [i32] * 5 + [vp]),
+    "fqss_tcn_prep_fold": (i32, [vp] * 7 + [i32] * 4 + [vp]),
     "fqss_fq_weight_fwd_batch": (i32, [C.POINTER(WqItem), i32, vp]),
     "fqss_fq_weight_bwd_batch": (i32, [C.POINTER(WqItem), i32, vp]),
     "fqss_tcn_prep_batch": (i32, [C.POINTER(PrepItem), i32, vp]),
@@ -119,7 +120,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 9:
+                if L.fqss_abi_version() != 10:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

@@ -84,13 +84,14 @@ def _prepare(model, dev):
                  s0_2=torch.empty(n2, **f32), dws2=torch.empty(n2, **f32))
         check(L.fqss_tcn_prep(ptr(t["W1"]), None, None, ptr(t["b1"]) or None, None, None, ptr(Q["Wc1"]), None, ptr(Q["s1_1"]),
                               ptr(Q["s0_1"]), ptr(Q["dws1"]), Chid, Cio, Chid, 0, 1, s))
+        # res/skip conv with the second gLN folded in (fqss_tcn_prep_fold): s1_2 = u, s0_2 = v
         off = 0
         if has_res:
-            check(L.fqss_tcn_prep(ptr(t["Wres"]), None, None, ptr(t["bres"]) or None, None, None, ptr(Q["Wc2"]), None,
-                                  ptr(Q["s1_2"]), ptr(Q["s0_2"]), ptr(Q["dws2"]), Cio, Chid, n2, 0, 1, s))
+            check(L.fqss_tcn_prep_fold(ptr(t["Wres"]), ptr(t["bres"]) or None, ptr(t["g2w"]), ptr(t["g2b"]), ptr(Q["Wc2"]),
+                                       ptr(Q["s1_2"]), ptr(Q["s0_2"]), Cio, Chid, n2, 0, s))
             off = Cio
-        check(L.fqss_tcn_prep(ptr(t["Wskip"]), None, None, ptr(t["bskip"]) or None, None, None, ptr(Q["Wc2"]), None,
-                              ptr(Q["s1_2"]), ptr(Q["s0_2"]), ptr(Q["dws2"]), Cio, Chid, n2, off, 1, s))
+        check(L.fqss_tcn_prep_fold(ptr(t["Wskip"]), ptr(t["bskip"]) or None, ptr(t["g2w"]), ptr(t["g2b"]), ptr(Q["Wc2"]),
+                                   ptr(Q["s1_2"]), ptr(Q["s0_2"]), Cio, Chid, n2, off, s))
         Q["wdw"] = t["Wdw"].detach().contiguous()
         P["blocks"].append((t, dil, has_res, Q))
     model._fqss_float_prep = (key, P)
@@ -104,7 +105,6 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
     bf = torch.bfloat16
     Chid = P["blocks"][0][0]["W1"].shape[0]
     y1 = torch.empty((B, Chid, ld), device=dev)
-    y3 = torch.empty((B, Chid, ld), device=dev)
     a4 = torch.empty((B, 2 * Chid, ld), dtype=bf, device=dev)
     st1 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
     st3 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
@@ -117,7 +117,7 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
     for i, (t, dil, has_res, Q) in enumerate(P["blocks"]):
         blk = E.TcnBlock()
         blk.B, blk.M, blk.dil, blk.quant, blk.first_block, blk.has_res = B, M, dil, 0, int(i == 0), int(has_res)
-        blk.Cio, blk.Chid, blk.split, blk.ld = Cio, Chid, 1, ld
+        blk.Cio, blk.Chid, blk.split, blk.ld = Cio, Chid, 2, ld
         for k in ("Wc1", "s1_1", "s0_1", "dws1", "Wc2", "s1_2", "s0_2", "dws2", "wdw"):
             setattr(blk, k, ptr(Q[k]))
         blk.bdw = ptr(t["bdw"])
@@ -125,7 +125,7 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
         blk.gn1_w, blk.gn1_b, blk.gn2_w, blk.gn2_b = ptr(t["g1w"]), ptr(t["g1b"]), ptr(t["g2w"]), ptr(t["g2b"])
         blk.x_op, blk.x_in = ptr(xops[cur_op]), ptr(xs[cur_x])
         blk.skip_in = ptr(skips[cur_skip]) if cur_skip is not None else None
-        blk.y1, blk.stats1, blk.y3, blk.stats3, blk.a4_op = ptr(y1), ptr(st1), ptr(y3), ptr(st3), ptr(a4)
+        blk.y1, blk.stats1, blk.y3, blk.stats3, blk.a4_op = ptr(y1), ptr(st1), None, ptr(st3), ptr(a4)
         blk.rc1, blk.rc3 = ptr(rc1), ptr(rc3)
         nxt_skip = 0 if cur_skip is None else 1 - cur_skip
         blk.skip_out = ptr(skips[nxt_skip])

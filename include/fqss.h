@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 9
+#define FQSS_ABI_VERSION 10
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -225,7 +225,10 @@ typedef struct fqss_qrange { const float* rmin; const float* rmax; } fqss_qrange
 typedef struct fqss_tcn_block {
     int32_t B, M, dil, quant, first_block, has_res, Cio, Chid;
     int32_t split;   /* quant == 0 only: *_op tensors are bf16 [hi ; lo] pairs with 2x the rows, Wc1/Wc2 are
-                        [N][3K] = [hi | hi | lo] (fp32-grade float model; forward / inference only)          */
+                        [N][3K] = [hi | hi | lo] (fp32-grade float model; forward / inference only).
+                        2: additionally the second gLN is folded into the res/skip conv (Wc2, s1_2 = u, s0_2 = v
+                        from fqss_tcn_prep_fold): K2 writes a3 = PReLU(y3) straight into a4_op, K3a is skipped and
+                        y3 / rc3 are not touched                                                              */
     int32_t _pad0;
     int64_t ld;
     /* prepared by fqss_tcn_prep (per step) */
@@ -261,6 +264,16 @@ typedef struct fqss_tcn_block {
 int fqss_tcn_prep(const float* W, const float* wmin, const float* wmax, const float* bias, const float* amin,
                   const float* amax, void* Wc, void* WcT, float* s1, float* s0, float* dws, int N, int K, int Ntot,
                   int n_off, int split, void* stream);
+
+/* Float (teacher) model, inference only: fold the block's second gLN (convtasnetq.py:31, GroupNorm(1, Chid)) into the
+ * res/skip 1x1 conv that consumes it (convtasnetq.py:33-34).  With a3 = PReLU(y3) and per-sample {mu, rstd}:
+ *   conv(gLN(a3))[o] = rstd * (sum_c (W[o,c] gamma[c]) a3[c] - mu * u[o]) + v[o]
+ *   u[o] = sum_c W[o,c] gamma[c],  v[o] = bias[o] + sum_c W[o,c] beta[c]        (fp64 sums)
+ * Wc [Ntot][3K] = [hi | hi | lo] bf16 split of W*gamma at row offset n_off; u, v [Ntot] go into s1_2 / s0_2 of a
+ * block run with split = 2 (the depthwise kernel then writes a3 as the GEMM operand and the normalisation pass over
+ * the hidden tensor disappears). */
+int fqss_tcn_prep_fold(const float* W, const float* bias, const float* gamma, const float* beta, void* Wc, float* u, float* v,
+                       int N, int K, int Ntot, int n_off, void* stream);
 
 /* Batched fqss_tcn_prep: `items` is a HOST array; one launch covers up to 32 convolutions. */
 typedef struct fqss_prep_item {
