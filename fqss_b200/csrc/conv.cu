@@ -373,8 +373,8 @@ int fqss_sconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     FQSS_REQUIRE(gy && x && w && B > 0 && Cin > 0 && Co > 0 && T >= K && K > 0 && stride > 0, -1, "sconv_bwd: bad argument");
     const int Mo = (T - K) / stride + 1;
     cudaStream_t s = (cudaStream_t)stream;
-    FQSS_PROFN("sconv_bwd", s, (gx ? 1 : 0) + (gw ? 2 : 0));
     if (gx) {
+        FQSS_PROF("sconv_bwd(dx: synthesis)", s);
         // gx[b,c,t] = sum_o sum_{m,k} w[o,c,k] gy[b,o,m]: the overlap-add kernel with weight row stride Cin*K
         FQSS_REQUIRE(Cin == 1, -1, "sconv_bwd: input gradient implemented for Cin == 1 (RQB re-encoder)");
         // samples beyond the last frame's support receive no gradient
@@ -388,6 +388,7 @@ int fqss_sconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     if (gw) {
         size_t need = (size_t)Co * Cin * K * sizeof(double);
         FQSS_REQUIRE(ws && ws_bytes >= need, -3, "sconv_bwd: workspace too small");
+        FQSS_PROFN("sconv_bwd(dw: edge_wgrad)", s, 2);
         cudaMemsetAsync(ws, 0, need, s);
         if (!(edge_geometry_ok(K, stride) && edge_wgrad(gy, ldgy, x, ldx, T, B, Cin, Co, Mo, (double*)ws, s) == 0)) {
             dim3 grid((Mo + 1023) / 1024, Co, B);
@@ -417,8 +418,8 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     FQSS_REQUIRE(gy && x && w && B > 0 && Ci > 0 && M > 0 && K > 0 && stride > 0 && K <= SC_MAXCK, -1, "tconv_bwd: bad argument");
     const int T = (M - 1) * stride + K;
     cudaStream_t s = (cudaStream_t)stream;
-    FQSS_PROFN("tconv_bwd", s, (gx ? 1 : 0) + (gw ? 2 : 0));
     if (gx) {   // gx[b,c,m] = sum_k w[c,k] gy[b, m*stride+k]  == analysis conv with Cin=1, Co=Ci
+        FQSS_PROF("tconv_bwd(dx: analysis)", s);
         if (!(edge_geometry_ok(K, stride) && aligned16(gx) && edge_analysis_fwd(gy, ldgy, T, w, gx, ldgx, B, 1, Ci, M, s) == 0)) {
             dim3 grid((M + 127) / 128, (Ci + SC_OT - 1) / SC_OT, B);
             sconv_fwd_kernel<<<grid, 128, 0, s>>>(gy, ldgy, w, gx, ldgx, 1, Ci, M, K, stride);
@@ -427,6 +428,7 @@ int fqss_tconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
     if (gw) {   // gw[c,k] = sum_{b,m} x[b,c,m] gy[b, m*stride+k]
         size_t need = (size_t)Ci * K * sizeof(double);
         FQSS_REQUIRE(ws && ws_bytes >= need, -3, "tconv_bwd: workspace too small");
+        FQSS_PROFN("tconv_bwd(dw: edge_wgrad)", s, 2);
         cudaMemsetAsync(ws, 0, need, s);
         if (!(edge_geometry_ok(K, stride) && edge_wgrad(x, ldx, gy, ldgy, T, B, 1, Ci, M, (double*)ws, s) == 0)) {
             dim3 grid((M + 1023) / 1024, Ci, B);

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) synthesis_fwd_kernel(const float* __restr
 #pragma unroll
     for (int k = 0; k < EK; ++k) a0[k] = a1[k] = 0.f;
     const float* xb = x + ((int64_t)b * Ci + cb) * ldx;
-#pragma unroll 4
+#pragma unroll 8
     for (int c = 0; c < cper; ++c) {
         const float* xr = xb + (int64_t)c * ldx;
         const float x0 = v0 ? __ldg(xr + f0) : 0.f;
@@ -142,57 +142,77 @@ __global__ void __launch_bounds__(256) synthesis_fwd_kernel(const float* __restr
 
 // ---------------------------------------------------------------------------------------------
 // weight gradient: gw[o, c*16+k] = sum_{b,m} g[b,o,m] * xs[b,c,8m+k]
-//   CTA = (frame chunk of 1024, 16 rows o, sample b); warp = 2 rows, lanes = frames; the signal window
-//   is de-interleaved in shared memory once per CTA and shared by all 16 rows.
+//   CTA = (frame chunk, 8*R rows o, sample b); warp = R rows, a lane owns 4 consecutive frames per trip.  The signal
+//   window is de-interleaved in shared memory once per CTA (xw[c][r][q] = x[c][8(m0+q)+r]) and shared by all rows, so
+//   one trip costs per lane: R 128-bit loads of g, 8*CIN x (LDS.128 + LDS.32) of the window and 64*R*CIN FMAs --
+//   the kernel sits on the FMA pipe (16*CIN FMAs per element of g) instead of on shared-memory bandwidth.
 // ---------------------------------------------------------------------------------------------
-constexpr int WG_CHUNK = 1024, WG_ROWS = 16, WG_X = WG_CHUNK + 4;
-
-template <int CIN>
+template <int CIN, int R, int CHUNK>
 __global__ void __launch_bounds__(256) edge_wgrad_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x, int64_t ldx,
                                                         int T, int Co, int Mo, double* __restrict__ acc) {
-    extern __shared__ __align__(16) float xw[];            // [CIN][8][WG_X]: xw[c][r][q] = x[c][8(m0+q)+r]
-    const int b = blockIdx.z, o0 = blockIdx.y * WG_ROWS, m0 = blockIdx.x * WG_CHUNK;
+    constexpr int WX = CHUNK + 4;                          // row stride of the window (16-byte aligned rows)
+    extern __shared__ __align__(16) float xw[];            // [CIN][8][WX]
+    const int b = blockIdx.z, o0 = blockIdx.y * (8 * R), m0 = blockIdx.x * CHUNK;
     const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
-    const int nfr = min(WG_CHUNK, Mo - m0);
+    const int nfr = min(CHUNK, Mo - m0);
     for (int c = 0; c < CIN; ++c) {
         const float* xr = x + ((int64_t)b * CIN + c) * ldx;
         const int t0 = m0 * ES;
-        for (int i = tid; i < (WG_CHUNK + 1) * ES; i += 256) {
+        for (int i = tid; i < (CHUNK + 4) * ES; i += 256) {
             const int t = t0 + i;
-            xw[((size_t)c * ES + (i & 7)) * WG_X + (i >> 3)] = (t < T) ? __ldg(xr + t) : 0.f;
+            xw[((size_t)c * ES + (i & 7)) * WX + (i >> 3)] = (t < T) ? __ldg(xr + t) : 0.f;
         }
     }
     __syncthreads();
-    const int oa = o0 + 2 * wp, ob = oa + 1;
-    const bool va = oa < Co, vb = ob < Co;
-    const float* ga = g + ((int64_t)b * Co + (va ? oa : 0)) * ldg + m0;
-    const float* gb = g + ((int64_t)b * Co + (vb ? ob : 0)) * ldg + m0;
-    float sa[CIN * EK], sb[CIN * EK];
+    const int ob = o0 + R * wp;
+    const float* gr[R];
+    bool vr[R];
 #pragma unroll
-    for (int j = 0; j < CIN * EK; ++j) sa[j] = sb[j] = 0.f;
-    for (int q = lane; q < nfr; q += 32) {
-        const float g0 = va ? __ldg(ga + q) : 0.f;
-        const float g1 = vb ? __ldg(gb + q) : 0.f;
+    for (int j = 0; j < R; ++j) {
+        vr[j] = ob + j < Co;
+        gr[j] = g + ((int64_t)b * Co + (vr[j] ? ob + j : 0)) * ldg + m0;
+    }
+    const bool vec_ok = ((ldg & 3) == 0) && ((reinterpret_cast<uintptr_t>(g) & 15) == 0) && ((m0 & 3) == 0);
+    float sa[R][CIN * EK];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int k = 0; k < CIN * EK; ++k) sa[j][k] = 0.f;
+    for (int q = 4 * lane; q < nfr; q += 128) {
+        float gv[R][4];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (vr[j] && vec_ok && q + 3 < nfr) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(gr[j] + q));
+                gv[j][0] = t.x; gv[j][1] = t.y; gv[j][2] = t.z; gv[j][3] = t.w;
+            } else {
+#pragma unroll
+                for (int f = 0; f < 4; ++f) gv[j][f] = (vr[j] && q + f < nfr) ? __ldg(gr[j] + q + f) : 0.f;
+            }
+        }
 #pragma unroll
         for (int c = 0; c < CIN; ++c)
 #pragma unroll
             for (int r = 0; r < ES; ++r) {
-                const float* row = xw + ((size_t)c * ES + r) * WG_X + q;
-                const float xlo = row[0], xhi = row[1];           // taps r and r+8
-                sa[c * EK + r] = fmaf(g0, xlo, sa[c * EK + r]);
-                sb[c * EK + r] = fmaf(g1, xlo, sb[c * EK + r]);
-                sa[c * EK + r + ES] = fmaf(g0, xhi, sa[c * EK + r + ES]);
-                sb[c * EK + r + ES] = fmaf(g1, xhi, sb[c * EK + r + ES]);
+                const float* row = xw + ((size_t)c * ES + r) * WX + q;
+                const float4 xa = *reinterpret_cast<const float4*>(row);
+                const float xv[5] = {xa.x, xa.y, xa.z, xa.w, row[4]};
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+#pragma unroll
+                    for (int f = 0; f < 4; ++f) {
+                        sa[j][c * EK + r] = fmaf(gv[j][f], xv[f], sa[j][c * EK + r]);                   // tap r reads frame q+f
+                        sa[j][c * EK + r + ES] = fmaf(gv[j][f], xv[f + 1], sa[j][c * EK + r + ES]);     // tap r+8 reads frame q+f+1
+                    }
             }
     }
 #pragma unroll
-    for (int j = 0; j < CIN * EK; ++j) {
-        const float ta = warp_sum(sa[j]), tb = warp_sum(sb[j]);
-        if (lane == 0) {
-            if (va) atomicAdd(acc + (int64_t)oa * (CIN * EK) + j, (double)ta);
-            if (vb) atomicAdd(acc + (int64_t)ob * (CIN * EK) + j, (double)tb);
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int k = 0; k < CIN * EK; ++k) {
+            const float t = warp_sum(sa[j][k]);
+            if (lane == 0 && vr[j]) atomicAdd(acc + (int64_t)(ob + j) * (CIN * EK) + k, (double)t);
         }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -223,18 +243,23 @@ int edge_synthesis_fwd(const float* x, int64_t ldx, const float* w, int64_t wstr
     return 0;
 }
 
-int edge_wgrad(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Cin, int Co, int Mo, double* acc, cudaStream_t s) {
-    if (Cin != 1 && Cin != 2) return 1;
-    const size_t smem = (size_t)Cin * ES * WG_X * sizeof(float);
+template <int CIN, int R, int CHUNK>
+static void edge_wgrad_launch(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Co, int Mo, double* acc,
+                              cudaStream_t s) {
+    constexpr size_t smem = (size_t)CIN * ES * (CHUNK + 4) * sizeof(float);
     static bool cfg = false;
     if (!cfg) {
-        cudaFuncSetAttribute(edge_wgrad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        cudaFuncSetAttribute(edge_wgrad_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        cudaFuncSetAttribute(edge_wgrad_kernel<CIN, R, CHUNK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cfg = true;
     }
-    dim3 grid((Mo + WG_CHUNK - 1) / WG_CHUNK, (Co + WG_ROWS - 1) / WG_ROWS, B);
-    if (Cin == 1) edge_wgrad_kernel<1><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
-    else edge_wgrad_kernel<2><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
+    dim3 grid((Mo + CHUNK - 1) / CHUNK, (Co + 8 * R - 1) / (8 * R), B);
+    edge_wgrad_kernel<CIN, R, CHUNK><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
+}
+
+int edge_wgrad(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Cin, int Co, int Mo, double* acc, cudaStream_t s) {
+    if (Cin != 1 && Cin != 2) return 1;
+    if (Cin == 1) edge_wgrad_launch<1, 4, 2048>(g, ldg, x, ldx, T, B, Co, Mo, acc, s);
+    else edge_wgrad_launch<2, 2, 1024>(g, ldg, x, ldx, T, B, Co, Mo, acc, s);
     return 0;
 }
 

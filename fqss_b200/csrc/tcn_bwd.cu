@@ -17,6 +17,7 @@
 //
 // The 512-wide gradient tensors travel in bf16 (the "1e-2 bf16 GEMM path"); the residual-stream and
 // skip-sum gradients (128-wide) stay fp32 end to end.
+#include <stdlib.h>
 #include <type_traits>
 
 #include "fqss_common.cuh"
@@ -199,7 +200,28 @@ __device__ __forceinline__ void mask_tail(float2& a01, float2& a23, int nval) {
         if (((M)&3) && (int)threadIdx.x == (nfull_ % (NTH_))) body(nfull_, std::true_type{});             \
     } while (0)
 
-template <int PHASE, bool QUANT, int NTH>
+// Batched variant: every thread first issues the loads of NQ quads (`load(v)` returns a plain struct of raw words), then
+// consumes them.  One row is only ~1000 quads, i.e. a handful of trips per thread, so without the batch every trip
+// exposes a full DRAM latency (ncu: > 40 % of the stall samples on the first use of the loaded word) and the bytes in
+// flight per SM stay far below what HBM needs.
+#define FQSS_ROW_LOOP_BATCH(NTH_, NQ_, load, body, M)                                                     \
+    do {                                                                                                  \
+        const int nfull_ = (M) >> 2;                                                                      \
+        for (int base_ = threadIdx.x; base_ < nfull_; base_ += (NQ_) * (NTH_)) {                          \
+            decltype(load(0)) d_[NQ_];                                                                    \
+            _Pragma("unroll") for (int k_ = 0; k_ < (NQ_); ++k_) {                                        \
+                const int v_ = base_ + k_ * (NTH_);                                                       \
+                if (v_ < nfull_) d_[k_] = load(v_);                                                       \
+            }                                                                                             \
+            _Pragma("unroll") for (int k_ = 0; k_ < (NQ_); ++k_) {                                        \
+                const int v_ = base_ + k_ * (NTH_);                                                       \
+                if (v_ < nfull_) body(v_, d_[k_], std::false_type{});                                     \
+            }                                                                                             \
+        }                                                                                                 \
+        if (((M)&3) && (int)threadIdx.x == (nfull_ % (NTH_))) body(nfull_, load(nfull_), std::true_type{}); \
+    } while (0)
+
+template <int PHASE, bool QUANT, int NTH, int NQ>
 __global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     __shared__ float tabX[256], tabD[256];
@@ -233,13 +255,21 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block 
     float2 a0 = f2s(0.f), a1 = f2s(0.f), a2 = f2s(0.f), a3 = f2s(0.f);
     constexpr bool CODES = (PHASE == 1 && QUANT);      // everything P1 needs is a function of the saved code of a3
     const uint32_t* c3 = reinterpret_cast<const uint32_t*>(p.code3 + r * p.ld);
-    auto body = [&](int v, auto tail_tag) {
+    struct Ld { float4 y; uint32_t packed; uint2 g; };
+    auto load = [&](int v) {
+        Ld d;
+        d.y = make_float4(0.f, 0.f, 0.f, 0.f);
+        d.packed = 0;
+        if (CODES) d.packed = __ldg(c3 + v);
+        else d.y = __ldg(y3 + v);
+        d.g = __ldg(ga4 + v);
+        return d;
+    };
+    auto body = [&](int v, const Ld& d, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t packed = 0;
-        if (CODES) packed = __ldg(c3 + v);
-        else y = __ldg(y3 + v);
-        const float4 gi = bf16x4_to_float4(__ldg(ga4 + v));
+        const float4 y = d.y;
+        const uint32_t packed = d.packed;
+        const float4 gi = bf16x4_to_float4(d.g);
         float2 gg[2] = {lo2(gi), hi2(gi)};
         if (TAIL) mask_tail(gg[0], gg[1], M - 4 * v);
         const float2 yy[2] = {lo2(y), hi2(y)};
@@ -299,7 +329,7 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block 
         }
         if (PHASE == 2) gy3[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOPN(NTH, body, M);
+    FQSS_ROW_LOOP_BATCH(NTH, NQ, load, body, M);
     const float s[4] = {hsum(a0), hsum(a1), PHASE == 1 ? hsum(a2) : hsum(a3), hsum(a3)};
     double v[4];
     block_sum_fd<4>(s, v, sh);
@@ -384,29 +414,41 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_sums_codes_kernel(const fqss_tcn
     }
 }
 
-// R: per-sample {S1,S2} and per-channel dgamma/dbeta from the per-row sums
-__global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, int C, const float* __restrict__ gamma,
-                                      float* __restrict__ g_gamma, float* __restrict__ g_beta, double* __restrict__ samp) {
-    __shared__ double sh[2 * 32];
+// R: per-sample {S1,S2} and per-channel dgamma/dbeta from the per-row sums.  CTAs [0,B): one sample each;
+// CTAs [B, B + ceil(C/32)): 32 channels each, 8 thread groups split the samples (the loads of one thread are independent,
+// so the whole reduction is one memory round trip deep instead of B).
+__global__ void __launch_bounds__(256) tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, int C, const float* __restrict__ gamma,
+                                                            float* __restrict__ g_gamma, float* __restrict__ g_beta, double* __restrict__ samp) {
+    __shared__ double sh[2 * 256];
     if ((int)blockIdx.x < B) {
         const int b = blockIdx.x;
         double s1 = 0.0, s2 = 0.0;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            const double gm = (double)gamma[c];
-            s1 += gm * rowacc[2 * ((int64_t)b * C + c)];
-            s2 += gm * rowacc[2 * ((int64_t)b * C + c) + 1];
+        for (int c = threadIdx.x; c < C; c += 256) {
+            const double gm = (double)__ldg(gamma + c);
+            const double2 v = *reinterpret_cast<const double2*>(rowacc + 2 * ((int64_t)b * C + c));
+            s1 += gm * v.x;
+            s2 += gm * v.y;
         }
         double v[2] = {s1, s2};
         block_sum<2>(v, sh);
         if (threadIdx.x == 0) { samp[2 * b] = v[0]; samp[2 * b + 1] = v[1]; }
     } else {
-        const int nb = gridDim.x - B;
-        for (int c = (blockIdx.x - B) * blockDim.x + threadIdx.x; c < C; c += nb * blockDim.x) {
-            double gb = 0.0, gg = 0.0;
-            for (int b = 0; b < B; ++b) {
-                gb += rowacc[2 * ((int64_t)b * C + c)];
-                gg += rowacc[2 * ((int64_t)b * C + c) + 1];
+        const int c = (blockIdx.x - B) * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+        double gb = 0.0, gg = 0.0;
+        if (c < C) {
+#pragma unroll 4
+            for (int b = grp; b < B; b += 8) {
+                const double2 v = *reinterpret_cast<const double2*>(rowacc + 2 * ((int64_t)b * C + c));
+                gb += v.x;
+                gg += v.y;
             }
+        }
+        sh[threadIdx.x] = gb;
+        sh[256 + threadIdx.x] = gg;
+        __syncthreads();
+        if (grp == 0 && c < C) {
+#pragma unroll
+            for (int k = 1; k < 8; ++k) { gb += sh[32 * k + threadIdx.x]; gg += sh[256 + 32 * k + threadIdx.x]; }
             g_beta[c] = (float)gb;
             g_gamma[c] = (float)gg;
         }
@@ -424,7 +466,7 @@ __global__ void tcn_gln_reduce_kernel(const double* __restrict__ rowacc, int B, 
 //             centre a2 is needed
 // The float model derives a2 / xhat1 from y1 directly.
 // ---------------------------------------------------------------------------------------------
-template <bool QUANT, int DMODE, int NTH>
+template <bool QUANT, int DMODE, int NTH, int NQ>
 __global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[8 * 32];
     __shared__ float tabT[256];                       // QUANT: t2 = (gLN1(decode1(code1)) - min2) / delta2
@@ -446,30 +488,45 @@ __global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p,
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
     const float2 xa1 = f2s(QUANT ? h.q1.delta * h.g.rstd : 0.f), xb1 = f2s(QUANT ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f);
     uint2* gn1o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld);
-    auto ldq = [&](int vq) -> float4 {
-        if (vq < 0 || vq >= nq) return make_float4(0.f, 0.f, 0.f, 0.f);
-        return bf16x4_to_float4(__ldg(gq + vq));
-    };
     auto ld1 = [&](int m) -> float { return (m >= 0 && m < M) ? __bfloat162float(gy3[m]) : 0.f; };
     // b0 = sum ga2*D2, b1 = sum ga2*(1-m2), b2 = sum gn1, b3 = sum gn1*xhat1 | taps: d0,d1,d2 = sum a2*g[+d,0,-d], d3 = sum g
     float2 b0 = f2s(0.f), b1 = f2s(0.f), b2 = f2s(0.f), b3 = f2s(0.f), d0 = f2s(0.f), d1 = f2s(0.f), d2 = f2s(0.f), d3 = f2s(0.f);
-    auto body = [&](int v, auto tail_tag) {
+    auto ldraw = [&](int vq) -> uint2 {
+        if (vq < 0 || vq >= nq) return make_uint2(0u, 0u);
+        return __ldg(gq + vq);
+    };
+    struct Ld { float4 y; uint32_t packed; uint2 c, a, e; };      // a / e: the quads holding the left / right taps
+    auto load = [&](int v) {
+        Ld t;
+        t.y = make_float4(0.f, 0.f, 0.f, 0.f);
+        t.packed = 0;
+        if (QUANT) t.packed = __ldg(c1 + v);
+        else t.y = __ldg(y1 + v);
+        t.c = ldraw(v);
+        const int sh = DMODE == 0 ? (d >> 2) : 1;
+        t.a = make_uint2(0u, 0u);
+        t.e = make_uint2(0u, 0u);
+        if (DMODE != 3) {
+            t.a = ldraw(v - sh);
+            t.e = ldraw(v + sh);
+        }
+        return t;
+    };
+    auto body = [&](int v, const Ld& t, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        uint32_t packed = 0;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (QUANT) packed = __ldg(c1 + v);
-        else y = __ldg(y1 + v);
-        const float4 gC = ldq(v);
+        const uint32_t packed = t.packed;
+        const float4 y = t.y;
+        const float4 gC = bf16x4_to_float4(t.c);
         float4 gL, gR;
         if (DMODE == 0) {                      // d % 4 == 0: whole quads
-            gL = ldq(v - (d >> 2));
-            gR = ldq(v + (d >> 2));
+            gL = bf16x4_to_float4(t.a);
+            gR = bf16x4_to_float4(t.e);
         } else if (DMODE == 1) {
-            const float4 a = ldq(v - 1), e = ldq(v + 1);
+            const float4 a = bf16x4_to_float4(t.a), e = bf16x4_to_float4(t.e);
             gL = make_float4(a.w, gC.x, gC.y, gC.z);
             gR = make_float4(gC.y, gC.z, gC.w, e.x);
         } else if (DMODE == 2) {
-            const float4 a = ldq(v - 1), e = ldq(v + 1);
+            const float4 a = bf16x4_to_float4(t.a), e = bf16x4_to_float4(t.e);
             gL = make_float4(a.z, a.w, gC.x, gC.y);
             gR = make_float4(gC.z, gC.w, e.x, e.y);
         } else {
@@ -521,7 +578,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p,
         }
         gn1o[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOPN(NTH, body, M);
+    FQSS_ROW_LOOP_BATCH(NTH, NQ, load, body, M);
     const float s[8] = {hsum(b0), hsum(b1), hsum(b2), hsum(b3), hsum(d0), hsum(d1), hsum(d2), hsum(d3)};
     double v[8];
     block_sum_fd<8>(s, v, sh);
@@ -539,7 +596,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p,
 // ---------------------------------------------------------------------------------------------
 // Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
 // ---------------------------------------------------------------------------------------------
-template <bool QUANT, int NTH>
+template <bool QUANT, int NTH, int NQ>
 __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
     const AccLayout L(p.B, p.Cio, p.Chid);
@@ -561,10 +618,17 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
     const float slope = h.slope;
     // a0 = sum ga1*D1, a1 = sum ga1*(1-m1), a3 = sum min(y,0)*gz, a4 = sum gy
     float2 a0 = f2s(0.f), a1 = f2s(0.f), a3 = f2s(0.f), a4 = f2s(0.f);
-    auto body = [&](int v, auto tail_tag) {
+    struct Ld { float4 y; uint2 g; };
+    auto load = [&](int v) {
+        Ld d;
+        d.y = __ldg(y1 + v);
+        d.g = __ldg(gn1 + v);
+        return d;
+    };
+    auto body = [&](int v, const Ld& d, auto tail_tag) {
         constexpr bool TAIL = decltype(tail_tag)::value;
-        const float4 y = __ldg(y1 + v);
-        const float4 gi = bf16x4_to_float4(__ldg(gn1 + v));
+        const float4 y = d.y;
+        const float4 gi = bf16x4_to_float4(d.g);
         const float2 yy[2] = {lo2(y), hi2(y)};
         const float2 gg[2] = {lo2(gi), hi2(gi)};
         float2 o[2];
@@ -602,7 +666,7 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
         }
         dY1[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
     };
-    FQSS_ROW_LOOPN(NTH, body, M);
+    FQSS_ROW_LOOP_BATCH(NTH, NQ, load, body, M);
     const float s[4] = {hsum(a0), hsum(a1), hsum(a3), hsum(a4)};
     double v[4];
     block_sum_fd<4>(s, v, sh);
@@ -641,6 +705,12 @@ __global__ void fill_consts_kernel(float* ones, float* zeros, int n) {
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// development knob: loads-in-flight batch of a row kernel, from the environment (read once per name)
+static int tune_nq(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 }  // namespace fqss
 
@@ -703,19 +773,29 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     {
         FQSS_PROF("tcn_gln2_bwd<1>", s);
         if (p->quant) tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-        else tcn_gln2_bwd_kernel<1, false, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
     }
-    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
+    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
                                                                      acc + L.samp2); }
     {
         FQSS_PROF("tcn_gln2_bwd<2>", s);
-        if (p->quant) tcn_gln2_bwd_kernel<2, true, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-        else tcn_gln2_bwd_kernel<2, false, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        if (p->quant) {
+            const int nqv = tune_nq("FQSS_NQ_P2", 4);
+            if (nqv == 1) tcn_gln2_bwd_kernel<2, true, 128, 1><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+            else if (nqv == 2) tcn_gln2_bwd_kernel<2, true, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+            else tcn_gln2_bwd_kernel<2, true, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        } else tcn_gln2_bwd_kernel<2, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
     }
     // D, R, Q
     {
         FQSS_PROF("tcn_dw_bwd", s);
-#define FQSS_DWB_LAUNCH(Q, D) tcn_dw_bwd_kernel<Q, D, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc)
+        const int nqd = tune_nq("FQSS_NQ_DW", 4);
+#define FQSS_DWB_LAUNCH(Q, D)                                                                      \
+    do {                                                                                           \
+        if (nqd == 1) tcn_dw_bwd_kernel<Q, D, 128, 1><<<rows_h, 128, 0, s>>>(*p, *g, acc);          \
+        else if (nqd == 2) tcn_dw_bwd_kernel<Q, D, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);     \
+        else tcn_dw_bwd_kernel<Q, D, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);                   \
+    } while (0)
         const int mode = dw_mode(p->dil);
         if (p->quant) {
             if (mode == 0) FQSS_DWB_LAUNCH(true, 0); else if (mode == 1) FQSS_DWB_LAUNCH(true, 1);
@@ -726,12 +806,18 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
         }
 #undef FQSS_DWB_LAUNCH
     }
-    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 255) / 256, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
+    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
                                                                      acc + L.samp1); }
     {
         FQSS_PROF("tcn_gln1_bwd", s);
-        if (p->quant) tcn_gln1_bwd_kernel<true, 256><<<rows_h, 256, 0, s>>>(*p, *g, acc);
-        else tcn_gln1_bwd_kernel<false, 256><<<rows_h, 256, 0, s>>>(*p, *g, acc);
+        if (p->quant) {
+            const int nqv = tune_nq("FQSS_NQ_Q", 14);
+            if (nqv == 1) tcn_gln1_bwd_kernel<true, 256, 1><<<rows_h, 256, 0, s>>>(*p, *g, acc);
+            else if (nqv == 2) tcn_gln1_bwd_kernel<true, 256, 2><<<rows_h, 256, 0, s>>>(*p, *g, acc);
+            else if (nqv == 4) tcn_gln1_bwd_kernel<true, 256, 4><<<rows_h, 256, 0, s>>>(*p, *g, acc);
+            else if (nqv == 12) tcn_gln1_bwd_kernel<true, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+            else tcn_gln1_bwd_kernel<true, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        } else tcn_gln1_bwd_kernel<false, 256, 2><<<rows_h, 256, 0, s>>>(*p, *g, acc);
     }
     rc = check_launch("tcn_block_bwd(hidden)");
     if (rc) return rc;
