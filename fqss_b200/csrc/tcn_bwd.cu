@@ -594,6 +594,188 @@ __global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p,
 }
 
 // ---------------------------------------------------------------------------------------------
+// P2 + D fused: both stages are local to one (sample, channel) row once the per-sample gLN2 sums exist, so one CTA
+//   phase A  g_a4 (bf16), y3 -> gLN2 / FQ3 / PReLU3 backward -> g_y3 row in SHARED memory (fp32, zero halo of `dil`)
+//   phase B  taps of g_y3 from shared memory + saved code of a1 -> depthwise / FQ2 backward -> g_n1 (bf16), sums
+// g_y3 never goes to HBM (was: 2 B/frame written + read back three times through L1), the bf16 rounding of g_y3
+// disappears, and the two block reductions become one.  HBM bytes: y3 4 + g_a4 2 + code1 1 + g_n1 2 = 9 B/frame.
+// ---------------------------------------------------------------------------------------------
+template <bool QUANT, int DMODE, int NTH, int NQ>
+__global__ void __launch_bounds__(NTH) tcn_gln2_dw_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    extern __shared__ __align__(16) float dsm[];      // [dpad | ld | dpad]
+    __shared__ double sh[11 * 32];
+    __shared__ float tabX[256], tabT[256];
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
+    const int M = p.M, d = p.dil, dpad = dw_pad(d), ld = (int)p.ld;
+    float* row = dsm + dpad;
+    const Hidden3 h3 = load_hidden3(p, b, c);
+    const Hidden1 h1 = load_hidden1(p, b, c);
+    // zero the halo and every frame from the ragged quad's end up to the pitch
+    for (int i = threadIdx.x; i < dpad; i += NTH) {
+        dsm[i] = 0.f;
+        row[ld + i] = 0.f;
+    }
+    for (int i = ((M + 3) & ~3) + threadIdx.x; i < ld; i += NTH) row[i] = 0.f;
+    if (QUANT) {
+        for (int i = threadIdx.x; i < 256; i += NTH) {
+            const float4 e = chain_bwd_entry(h3.q3, h3.g, h3.q4, i, false);      // {-, mask4, D4, xhat3}
+            tabX[i] = __uint_as_float((__float_as_uint(e.w) & ~1u) | (e.y != 0.f ? 1u : 0u));
+            tabT[i] = actqf_t(h1.q2, gln_apply(h1.g, actqf_decode(h1.q1, (float)i)));
+        }
+    }
+    __syncthreads();
+    // ---------------- phase A: gLN2 + FQ3 + PReLU3 backward -> row ----------------
+    float2 a0 = f2s(0.f), a1 = f2s(0.f), a3 = f2s(0.f);      // q3: sD, sZ; slope3
+    {
+        const float4* y3 = reinterpret_cast<const float4*>(p.y3 + r * p.ld);
+        const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+        const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
+        const float2 A = f2s(h3.g.rstd * h3.g.gamma);
+        const float2 nBc = f2s(-h3.g.rstd * invN * (float)acc[L.samp2 + 2 * b]);
+        const float2 nCc = f2s(-h3.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1]);
+        const float slope = h3.slope;
+        struct Ld { float4 y; uint2 g; };
+        auto load = [&](int v) {
+            Ld t;
+            t.y = __ldg(y3 + v);
+            t.g = __ldg(ga4 + v);
+            return t;
+        };
+        auto body = [&](int v, const Ld& t, auto tail_tag) {
+            constexpr bool TAIL = decltype(tail_tag)::value;
+            const float4 gi = bf16x4_to_float4(t.g);
+            const float2 gg[2] = {lo2(gi), hi2(gi)};
+            const float2 yy[2] = {lo2(t.y), hi2(t.y)};
+            float2 o[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float2 z = make_float2(prelu_f(yy[j].x, slope), prelu_f(yy[j].y, slope));
+                float2 xh, gn, tq = f2s(0.f);
+                unsigned ix = 0, iy = 0;
+                if (QUANT) {
+                    tq = actqf_t2(h3.q3, z);
+                    ix = code_u8(tq.x);
+                    iy = code_u8(tq.y);
+                    xh = make_float2(tabX[ix], tabX[iy]);
+                    gn = make_float2(tab_mask(xh.x) ? gg[j].x : 0.f, tab_mask(xh.y) ? gg[j].y : 0.f);
+                } else {
+                    xh = make_float2(gln_xhat(h3.g, z.x), gln_xhat(h3.g, z.y));
+                    gn = gg[j];
+                }
+                float2 ga3 = __ffma2_rn(A, gn, __ffma2_rn(xh, nCc, nBc));
+                if (TAIL) {
+                    if (4 * v + 2 * j + 1 >= M) ga3.y = 0.f;
+                    if (4 * v + 2 * j >= M) ga3.x = 0.f;
+                }
+                float2 gz = ga3;
+                if (QUANT) {
+                    const float2 cf = make_float2((float)ix, (float)iy);
+                    const float2 dd = __fadd2_rn(cf, neg2(tq));
+                    const float2 th = __fadd2_rn(tq, f2s(0.5f));
+                    const bool inx = inside_u8(th.x), iny = inside_u8(th.y);
+                    a0 = __ffma2_rn(ga3, make_float2(inx ? dd.x : cf.x, iny ? dd.y : cf.y), a0);
+                    gz = make_float2(inx ? ga3.x : 0.f, iny ? ga3.y : 0.f);
+                    a1 = __fadd2_rn(a1, __fadd2_rn(ga3, neg2(gz)));
+                }
+                o[j] = __fmul2_rn(gz, make_float2(yy[j].x > 0.f ? 1.f : slope, yy[j].y > 0.f ? 1.f : slope));
+                a3 = __ffma2_rn(make_float2(fminf(yy[j].x, 0.f), fminf(yy[j].y, 0.f)), gz, a3);
+            }
+            *reinterpret_cast<float4*>(row + 4 * v) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+        };
+        FQSS_ROW_LOOP_BATCH(NTH, NQ, load, body, M);
+    }
+    __syncthreads();
+    // ---------------- phase B: depthwise + FQ2 backward, gLN1 row sums ----------------
+    const float4* y1 = reinterpret_cast<const float4*>(p.y1 + r * p.ld);
+    const uint32_t* c1 = reinterpret_cast<const uint32_t*>(p.code1 + r * p.ld);
+    const float slope1 = h1.slope;
+    const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
+    const float2 xa1 = f2s(QUANT ? h1.q1.delta * h1.g.rstd : 0.f), xb1 = f2s(QUANT ? (h1.q1.mn - h1.g.mu) * h1.g.rstd : 0.f);
+    uint2* gn1o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    // b0 = sum ga2*D2, b1 = sum ga2*(1-m2), b2 = sum gn1, b3 = sum gn1*xhat1 | taps: d0,d1,d2 = sum a2*g[+d,0,-d], d3 = sum g
+    float2 b0 = f2s(0.f), b1 = f2s(0.f), b2 = f2s(0.f), b3 = f2s(0.f), d0 = f2s(0.f), d1 = f2s(0.f), d2 = f2s(0.f), d3 = f2s(0.f);
+    {
+        struct Ld { float4 y; uint32_t packed; };
+        auto load = [&](int v) {
+            Ld t;
+            t.y = make_float4(0.f, 0.f, 0.f, 0.f);
+            t.packed = 0;
+            if (QUANT) t.packed = __ldg(c1 + v);
+            else t.y = __ldg(y1 + v);
+            return t;
+        };
+        auto body = [&](int v, const Ld& t, auto tail_tag) {
+            constexpr bool TAIL = decltype(tail_tag)::value;
+            const uint32_t packed = t.packed;
+            float4 gL, gC, gR;
+            dw_taps<DMODE>(row, v, d, gL, gC, gR);
+            float2 o[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float2 gc = j ? hi2(gC) : lo2(gC), gl = j ? hi2(gL) : lo2(gL), gr = j ? hi2(gR) : lo2(gR);
+                // y3[m'] = sum_k w_k a2[m' + (k-1)d]  =>  d/da2[m] = w0 g[m+d] + w1 g[m] + w2 g[m-d]
+                float2 ga2 = __ffma2_rn(w0, gr, __ffma2_rn(w1, gc, __fmul2_rn(w2, gl)));
+                float2 a2, xh, gn1;
+                if (QUANT) {
+                    const unsigned ix = (packed >> (16 * j)) & 255u, iy = (packed >> (16 * j + 8)) & 255u;
+                    const float2 t2 = make_float2(tabT[ix], tabT[iy]);
+                    const float2 c2 = make_float2((float)code_u8(t2.x), (float)code_u8(t2.y));
+                    a2 = __ffma2_rn(f2s(h1.q2.delta), c2, f2s(h1.q2.mn));      // feeds only the tap-gradient sums
+                    xh = __ffma2_rn(make_float2((float)ix, (float)iy), xa1, xb1);
+                    if (TAIL) {                                   // frames >= M: no gradient, and a2 there is not part of the row
+                        if (4 * v + 2 * j + 1 >= M) { ga2.y = 0.f; a2.y = 0.f; }
+                        if (4 * v + 2 * j >= M) { ga2.x = 0.f; a2.x = 0.f; }
+                    }
+                    const float2 th = __fadd2_rn(t2, f2s(0.5f));
+                    const bool inx = inside_u8(th.x), iny = inside_u8(th.y);
+                    const float2 dd = __fadd2_rn(c2, neg2(t2));
+                    gn1 = make_float2(inx ? ga2.x : 0.f, iny ? ga2.y : 0.f);
+                    b0 = __ffma2_rn(ga2, make_float2(inx ? dd.x : c2.x, iny ? dd.y : c2.y), b0);
+                    b1 = __fadd2_rn(b1, __fadd2_rn(ga2, neg2(gn1)));
+                } else {
+                    const float2 yj = j ? hi2(t.y) : lo2(t.y);
+                    const float2 z = make_float2(prelu_f(yj.x, slope1), prelu_f(yj.y, slope1));
+                    a2 = make_float2(gln_apply(h1.g, z.x), gln_apply(h1.g, z.y));
+                    xh = make_float2(gln_xhat(h1.g, z.x), gln_xhat(h1.g, z.y));
+                    if (TAIL) {
+                        if (4 * v + 2 * j + 1 >= M) { ga2.y = 0.f; a2.y = 0.f; }
+                        if (4 * v + 2 * j >= M) { ga2.x = 0.f; a2.x = 0.f; }
+                    }
+                    gn1 = ga2;
+                }
+                d0 = __ffma2_rn(a2, gr, d0);      // dW_0 = sum_m a2[m] g[m+d]
+                d1 = __ffma2_rn(a2, gc, d1);
+                d2 = __ffma2_rn(a2, gl, d2);      // dW_2 = sum_m a2[m] g[m-d]
+                d3 = __fadd2_rn(d3, gc);
+                b2 = __fadd2_rn(b2, gn1);
+                b3 = __ffma2_rn(gn1, xh, b3);
+                o[j] = gn1;
+            }
+            gn1o[v] = float4_to_bf16x4(o[0].x, o[0].y, o[1].x, o[1].y);
+        };
+        FQSS_ROW_LOOP_BATCH(NTH, NQ, load, body, M);
+    }
+    const float s[11] = {hsum(a0), hsum(a1), hsum(a3), hsum(b0), hsum(b1), hsum(b2), hsum(b3), hsum(d0), hsum(d1), hsum(d2), hsum(d3)};
+    double v[11];
+    block_sum_fd<11>(s, v, sh);
+    if (threadIdx.x == 0) {
+        if (QUANT) {
+            atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]);
+            atomicAdd(acc + L.q + 2 * Q2, v[3]); atomicAdd(acc + L.q + 2 * Q2 + 1, v[4]);
+        }
+        atomicAdd(acc + L.slope + 1, v[2]);
+        acc[L.row1 + 2 * r] = v[5];
+        acc[L.row1 + 2 * r + 1] = v[6];
+        atomicAdd(acc + L.dwdw + 3 * c, v[7]);
+        atomicAdd(acc + L.dwdw + 3 * c + 1, v[8]);
+        atomicAdd(acc + L.dwdw + 3 * c + 2, v[9]);
+        atomicAdd(acc + L.dbdw + c, v[10]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
 // ---------------------------------------------------------------------------------------------
 template <bool QUANT, int NTH, int NQ>
@@ -777,34 +959,62 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
                                                                      acc + L.samp2); }
-    {
-        FQSS_PROF("tcn_gln2_bwd<2>", s);
-        if (p->quant) {
-            const int nqv = tune_nq("FQSS_NQ_P2", 4);
-            if (nqv == 1) tcn_gln2_bwd_kernel<2, true, 128, 1><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-            else if (nqv == 2) tcn_gln2_bwd_kernel<2, true, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-            else tcn_gln2_bwd_kernel<2, true, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-        } else tcn_gln2_bwd_kernel<2, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-    }
-    // D, R, Q
-    {
-        FQSS_PROF("tcn_dw_bwd", s);
-        const int nqd = tune_nq("FQSS_NQ_DW", 4);
-#define FQSS_DWB_LAUNCH(Q, D)                                                                      \
-    do {                                                                                           \
-        if (nqd == 1) tcn_dw_bwd_kernel<Q, D, 128, 1><<<rows_h, 128, 0, s>>>(*p, *g, acc);          \
-        else if (nqd == 2) tcn_dw_bwd_kernel<Q, D, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);     \
-        else tcn_dw_bwd_kernel<Q, D, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);                   \
-    } while (0)
+    // P2 + D (one kernel; FQSS_SPLIT_P2D=1 runs the two separate kernels instead -- development / A-B knob)
+    static const int split_p2d = tune_nq("FQSS_SPLIT_P2D", 0);
+    if (!split_p2d) {
+        const int dpad = dw_pad(p->dil);
+        const size_t smem = ((size_t)p->ld + 2 * dpad) * sizeof(float);
+        FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         const int mode = dw_mode(p->dil);
+        static const int nqf = tune_nq("FQSS_NQ_F", 4);
+        FQSS_PROF("tcn_gln2_dw_bwd", s);
+#define FQSS_F_LAUNCH(Q, D, NQv)                                                                                         \
+    do {                                                                                                                 \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(tcn_gln2_dw_bwd_kernel<Q, D, 128, NQv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        tcn_gln2_dw_bwd_kernel<Q, D, 128, NQv><<<rows_h, 128, smem, s>>>(*p, *g, acc);                                    \
+    } while (0)
+#define FQSS_F_MODE(Q, NQv)                                                                          \
+    do {                                                                                             \
+        if (mode == 0) FQSS_F_LAUNCH(Q, 0, NQv); else if (mode == 1) FQSS_F_LAUNCH(Q, 1, NQv);       \
+        else if (mode == 2) FQSS_F_LAUNCH(Q, 2, NQv); else FQSS_F_LAUNCH(Q, 3, NQv);                 \
+    } while (0)
         if (p->quant) {
-            if (mode == 0) FQSS_DWB_LAUNCH(true, 0); else if (mode == 1) FQSS_DWB_LAUNCH(true, 1);
-            else if (mode == 2) FQSS_DWB_LAUNCH(true, 2); else FQSS_DWB_LAUNCH(true, 3);
+            if (nqf == 1) FQSS_F_MODE(true, 1); else if (nqf == 2) FQSS_F_MODE(true, 2); else FQSS_F_MODE(true, 4);
         } else {
-            if (mode == 0) FQSS_DWB_LAUNCH(false, 0); else if (mode == 1) FQSS_DWB_LAUNCH(false, 1);
-            else if (mode == 2) FQSS_DWB_LAUNCH(false, 2); else FQSS_DWB_LAUNCH(false, 3);
+            FQSS_F_MODE(false, 2);
         }
+#undef FQSS_F_MODE
+#undef FQSS_F_LAUNCH
+    } else {
+    {
+            FQSS_PROF("tcn_gln2_bwd<2>", s);
+            if (p->quant) {
+                const int nqv = tune_nq("FQSS_NQ_P2", 4);
+                if (nqv == 1) tcn_gln2_bwd_kernel<2, true, 128, 1><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+                else if (nqv == 2) tcn_gln2_bwd_kernel<2, true, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+                else tcn_gln2_bwd_kernel<2, true, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+            } else tcn_gln2_bwd_kernel<2, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        }
+        // D, R, Q
+        {
+            FQSS_PROF("tcn_dw_bwd", s);
+            const int nqd = tune_nq("FQSS_NQ_DW", 4);
+#define FQSS_DWB_LAUNCH(Q, D)                                                                      \
+        do {                                                                                           \
+            if (nqd == 1) tcn_dw_bwd_kernel<Q, D, 128, 1><<<rows_h, 128, 0, s>>>(*p, *g, acc);          \
+            else if (nqd == 2) tcn_dw_bwd_kernel<Q, D, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);     \
+            else tcn_dw_bwd_kernel<Q, D, 128, 4><<<rows_h, 128, 0, s>>>(*p, *g, acc);                   \
+        } while (0)
+            const int mode = dw_mode(p->dil);
+            if (p->quant) {
+                if (mode == 0) FQSS_DWB_LAUNCH(true, 0); else if (mode == 1) FQSS_DWB_LAUNCH(true, 1);
+                else if (mode == 2) FQSS_DWB_LAUNCH(true, 2); else FQSS_DWB_LAUNCH(true, 3);
+            } else {
+                if (mode == 0) FQSS_DWB_LAUNCH(false, 0); else if (mode == 1) FQSS_DWB_LAUNCH(false, 1);
+                else if (mode == 2) FQSS_DWB_LAUNCH(false, 2); else FQSS_DWB_LAUNCH(false, 3);
+            }
 #undef FQSS_DWB_LAUNCH
+        }
     }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
                                                                      acc + L.samp1); }
