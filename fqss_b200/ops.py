@@ -258,6 +258,37 @@ class PointwiseFQ(Function):
         return None, gx1, gx2, gslope, ggamma, gbeta, gmin, gmax, None, None, None
 
 
+class Fanout2(Function):
+    """x -> (x, x) for a tensor with two consumers.  Autograd would sum the two incoming gradients with an ATen add
+    into a DENSE tensor, which the next stage then has to repack into pitched rows (a second full pass); this node
+    does the sum with the library's own add kernel straight into a pitched tensor."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x), x.view_as(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ga, gb):
+        if ga is None or gb is None:
+            return ga if gb is None else gb
+        N.require_cuda(ga, gb)
+        ga, rows, cols, lda = rows_view(ga)
+        gb, rows_b, _, ldb = rows_view(gb)
+        y = alloc_rows(ga.shape, ga.device)
+        d = _desc(N.PW_ADD, False, 8, ga, (rows, cols, lda), gb, (rows_b, cols, ldb), y, ld_of(y),
+                  None, None, None, None, 0.0, None, None, 1, 1)
+        check(lib().fqss_pw_fwd(C.byref(d), stream_ptr()))
+        return y
+
+
+def fanout2(x):
+    """Two aliases of `x` whose gradients are summed by the library (pitched) instead of by autograd (dense)."""
+    if not (x.is_cuda and x.requires_grad and torch.is_grad_enabled()):
+        return x, x
+    return Fanout2.apply(x)
+
+
 def pointwise_fq(kind, x1, x2=None, slope=None, gamma=None, beta=None, rmin=None, rmax=None, quant=False, n_bits=8, eps=0.0):
     return PointwiseFQ.apply(kind, x1, x2, slope, gamma, beta, rmin, rmax, bool(quant), int(n_bits), float(eps))
 

@@ -12,6 +12,7 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
+from ... import ops
 from ...process import postprocess, preprocess
 from ..qat_layers import Add, Mul
 from ..qat_utils import quantize_modules, replace_decoderq, replace_encoderq
@@ -134,7 +135,8 @@ class ConvTasNetQ(nn.Module):
         x = self.pre_process(x)                                    # [B, n_splitter, T]
         batch = x.shape[0]
         feats = self.encoder(x)                                    # [B, F, M]
-        masked = self.mul(self.masker(feats), feats.unsqueeze(1))  # [B, S, F, M]
+        f_mask, f_mul = ops.fanout2(feats)                         # two consumers: gradients summed by the library
+        masked = self.mul(self.masker(f_mask), f_mul.unsqueeze(1))  # [B, S, F, M]
         dec_in = masked.reshape(batch * self.n_srcs, self.enc_num_feats, -1)
         dec = self.decoder(dec_in)                                 # [n_combiner, B*S, 1, T] (or [B*S,1,T])
         dec = dec.reshape((self.n_combiner, batch, self.n_srcs, 1, -1))

@@ -289,7 +289,10 @@ class ConvTr1dDecoderQ(LayerQ):
     def forward(self, x):
         stride = self.convTr1d.stride[0]
         w_dec = self.weight_fake_quantize(self.convTr1d.weight)
-        y = self._finish(N.PW_IDENT, ops.TransposedConv1.apply(x, w_dec, stride))
+        x_dec = x
+        if self.n_combiner >= 2:      # x also feeds the residual block: sum the two gradients in the library
+            x_dec, x = ops.fanout2(x)
+        y = self._finish(N.PW_IDENT, ops.TransposedConv1.apply(x_dec, w_dec, stride))
         if self.do_mac_op:
             Ci, Co, k = self.convTr1d.weight.shape
             self.mac_op = x.shape[0] * Co * Ci * ((x.shape[-1] - 1) * stride + k) * (k // stride)

@@ -35,8 +35,10 @@ with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_sh
 evs = [e for e in prof.events() if e.device_time_total > 20 and e.name.startswith("aten::")]
 evs.sort(key=lambda e: -e.device_time_total)
 tot = 0
-for e in evs[:40]:
-    st = [f for f in (e.stack or []) if "fqss_b200" in f or "bench" in f or "scratch" in f][:3]
+for e in evs[:14]:
+    st = [f for f in (e.stack or []) if "fqss_b200" in f or "bench" in f or "scratch" in f][:4]
+    if not st:
+        st = list(e.stack or [])[:4]
     print("%8.1f us %-28s %s | %s" % (e.device_time_total, e.name, str(e.input_shapes)[:90], " <- ".join(s.split("/")[-1][:60] for s in st)))
 for e in prof.events():
     if e.name.startswith("aten::") and e.device_time_total > 0 and not e.cpu_children:
