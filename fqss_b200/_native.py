@@ -44,6 +44,10 @@ class PrepItem(C.Structure):
                 ("_pad", C.c_int32)]
 
 
+class GatherItem(C.Structure):
+    _fields_ = [("src", vp), ("offset", i64), ("numel", i64)]
+
+
 class PwGrads(C.Structure):
     _fields_ = [("g", vp), ("ldg", i64), ("gx1", vp), ("ldg1", i64), ("gx2", vp), ("ldg2", i64),
                 ("g_rmin", vp), ("g_rmax", vp), ("g_slope", vp), ("g_gamma", vp), ("g_beta", vp)]
@@ -92,6 +96,7 @@ _SIGS = {
     "fqss_split": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),
     "fqss_combine": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp]),
     "fqss_kd_loss": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, f32, vp, vp, i64, vp, sz, vp]),
+    "fqss_arena_gather": (i32, [C.POINTER(GatherItem), i32, vp, vp]),
     "fqss_arena_sumsq": (i32, [vp, i64, vp, vp, sz, vp]),
     "fqss_arena_scale_clip": (i32, [vp, i64, vp, f32, f32, vp]),
     "fqss_arena_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
@@ -120,7 +125,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 10:
+                if L.fqss_abi_version() != 11:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

@@ -557,6 +557,43 @@ int fqss_combine(const float* parts, int64_t part_stride, int64_t ld, float* y, 
     return check_launch("combine");
 }
 
+// gather: many small gradient tensors -> their slices of the flat arena, one launch per 448 tensors (the table travels
+// as a kernel parameter; nothing is allocated).  CTA (x, y) copies elements [4096 x, 4096 (x+1)) of tensor y.
+constexpr int GATHER_BATCH = 448;
+struct GatherBatch {
+    fqss_gather_item it[GATHER_BATCH];
+};
+__global__ void __launch_bounds__(256) arena_gather_kernel(const __grid_constant__ GatherBatch b, float* __restrict__ dst) {
+    const fqss_gather_item& t = b.it[blockIdx.y];
+    const int64_t lo = (int64_t)blockIdx.x * 4096;
+    if (lo >= t.numel) return;
+    const int64_t hi = lo + 4096 < t.numel ? lo + 4096 : t.numel;
+    float* out = dst + t.offset;
+    if (t.src == nullptr) {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) out[i] = 0.f;
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) out[i] = __ldg(t.src + i);
+    }
+}
+
+int fqss_arena_gather(const fqss_gather_item* items, int n, float* dst, void* stream) {
+    FQSS_REQUIRE(items && n > 0 && dst, -1, "arena_gather: bad argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i0 = 0; i0 < n; i0 += GATHER_BATCH) {
+        GatherBatch b;
+        const int m = n - i0 < GATHER_BATCH ? n - i0 : GATHER_BATCH;
+        int64_t maxn = 1;
+        for (int i = 0; i < m; ++i) {
+            b.it[i] = items[i0 + i];
+            FQSS_REQUIRE(b.it[i].numel >= 0 && b.it[i].offset >= 0, -1, "arena_gather: bad item %d", i0 + i);
+            if (b.it[i].numel > maxn) maxn = b.it[i].numel;
+        }
+        FQSS_PROF("arena_gather", s);
+        arena_gather_kernel<<<dim3((unsigned)((maxn + 4095) / 4096), m), 256, 0, s>>>(b, dst);
+    }
+    return check_launch("arena_gather");
+}
+
 int fqss_arena_sumsq(const float* g, int64_t n, float* sumsq, void* ws, size_t ws_bytes, void* stream) {
     FQSS_REQUIRE(g && sumsq && n >= 0 && aligned16(g), -1, "arena_sumsq: bad argument");
     FQSS_REQUIRE(ws && ws_bytes >= 8, -3, "arena_sumsq: workspace too small");

@@ -48,9 +48,32 @@ class ParamArena:
             self.views.append(v)
             self.grad_views.append(self.grad[off:off + n].view(p.shape))
             off += n
+        self._keep = []
+        self._gather_items = (N.GatherItem * len(self.params))()
+        off = 0
+        for i, p in enumerate(self.params):
+            self._gather_items[i].offset, self._gather_items[i].numel = off, p.numel()
+            off += p.numel()
 
     def gather_grads(self):
-        """Collect p.grad of every parameter into the gradient arena (zeros where a parameter got none)."""
+        """Collect p.grad of every parameter into the gradient arena (zeros where a parameter got none): one
+        fqss_arena_gather call (3 launches for the 948 tensors) instead of a chunked multi-tensor ATen copy."""
+        if not self.flat.is_cuda:
+            return self._gather_grads_torch()
+        items = self._gather_items
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None:
+                items[i].src = None
+            else:
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.float().contiguous()
+                    self._keep.append(g)
+                items[i].src = g.data_ptr()
+        check(lib().fqss_arena_gather(items, len(self.params), ptr(self.grad), stream_ptr()))
+        self._keep.clear()          # safe: same stream, the copies are already enqueued
+
+    def _gather_grads_torch(self):
         have_dst, have_src = [], []
         for p, gv in zip(self.params, self.grad_views):
             if p.grad is None:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 10
+#define FQSS_ABI_VERSION 11
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -334,6 +334,10 @@ int fqss_kd_loss(const float* est, int64_t lde, const float* fest, int64_t ldf, 
  *   sumsq[0] = sum g^2 (for the global-norm clip, gradient_clip_val=5.0)
  *   scale_clip: g *= pre_scale * min(1, max_norm / (sqrt(sumsq*pre_scale^2) + 1e-6))
  * ------------------------------------------------------------------------------------------- */
+/* gather the per-parameter gradient tensors into the flat arena (the buffer the all-reduce runs on): item i copies
+ * numel floats from src (NULL: zeros -- a parameter that received no gradient) to dst + offset.  `items` is a HOST array. */
+typedef struct fqss_gather_item { const float* src; int64_t offset; int64_t numel; } fqss_gather_item;
+int fqss_arena_gather(const fqss_gather_item* items, int n, float* dst, void* stream);
 int fqss_arena_sumsq(const float* g, int64_t n, float* sumsq, void* ws, size_t ws_bytes, void* stream);
 int fqss_arena_scale_clip(float* g, int64_t n, const float* sumsq, float pre_scale, float max_norm, void* stream);
 /* fused Adam step over the flat arena (torch.optim.Adam semantics, weight_decay=0, amsgrad=False) */

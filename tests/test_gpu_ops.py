@@ -289,3 +289,37 @@ def test_tcgen05_pw_gemm_exact_integer_codes(B, K, N, M):
     assert rel(o2[:, :, :M], ref + add[:, :, :M].double()) < 1e-5
     o3 = E.pw_gemm(actf.to(DEV), wf.to(DEV), s1.to(DEV), s0.to(DEV), M, out_dtype=torch.bfloat16)
     assert rel(o3[:, :, :M].float(), ref) < 5e-3
+
+
+def test_param_arena_gather_clip_adam_vs_torch():
+    """D1 tail (asteroid_librimix_trainer.py:94,132): gather of ragged gradient tensors into the flat arena (incl. a
+    parameter without gradient), global-norm clip 5.0 and Adam(lr 1e-3), against torch's own clip + Adam."""
+    from fqss_b200.parallel import ParamArena
+    torch.manual_seed(0)
+    shapes = [(1,), (512, 128, 1), (3,), (512, 1, 3), (7, 5), (1,), (4097,), (128,), (2, 3, 4)] * 60      # 540 tensors: 2 gather launches
+    ref = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    arena = ParamArena(ours)
+    opt = torch.optim.Adam(ref, lr=1e-3)
+    for step in range(3):
+        grads = [torch.randn(s, device=DEV) * (3.0 if step == 0 else 0.01) for s in shapes]
+        arena.zero_grad()
+        opt.zero_grad(set_to_none=True)
+        for i, (p, q, g) in enumerate(zip(ref, ours, grads)):
+            if i % 11 == 5:
+                continue                                    # no gradient this step
+            p.grad = g.clone()
+            q.grad = g.t().contiguous().t() if g.dim() == 2 else g.clone()      # one non-contiguous gradient layout
+        arena.gather_grads()
+        for i, gv in enumerate(arena.grad_views):
+            want = ref[i].grad if ref[i].grad is not None else torch.zeros_like(ref[i])
+            assert torch.equal(gv, want), i
+        scale = arena.allreduce_mean()
+        arena.clip_and_step(pre_scale=scale, max_norm=5.0, lr=1e-3)
+        for p in ref:                                       # torch steps only parameters that have a gradient; the
+            if p.grad is None:                              # reference (DDP find_unused) feeds zeros instead
+                p.grad = torch.zeros_like(p)
+        torch.nn.utils.clip_grad_norm_(ref, 5.0)
+        opt.step()
+        worst = max(rel(q, p) for p, q in zip(ref, ours))
+        assert worst < 1e-5, (step, worst)
