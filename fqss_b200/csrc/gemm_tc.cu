@@ -59,7 +59,9 @@ template <int NT, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by POINTER arithmetic on the shared array: the compiler keeps the address space, so reads of the
+    // per-channel constants below are LDS (an integer round trip would turn every one of them into a generic load)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     float* s1s = reinterpret_cast<float*>(smem + STAGES * stage_bytes<NT>());
     float* s0s = s1s + MAXN;
     Barriers* bar = reinterpret_cast<Barriers*>(s0s + MAXN);
@@ -190,6 +192,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m = m0 + q * 32 + lane;
             const bool valid = m < p.M;
             float st_s = 0.f, st_ss = 0.f;
+            unsigned st_c = 0u, st_cc = 0u;
             if (EPI == EPI_RESSKIP && p.fold_stats && b != fold_b) {      // per-sample constants of the folded gLN
                 const double mean = __ldg(p.fold_stats + 2 * b) / p.n_elems;
                 double var = __ldg(p.fold_stats + 2 * b + 1) / p.n_elems - mean * mean;
@@ -242,13 +245,15 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 } else if (EPI == EPI_EXPAND) {
                     float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
                     if (p.quant) {
+                        // gLN statistics of a1 = delta1 * code + min1 from INTEGER code sums (exact adds; expanded once per
+                        // tile): prelu, (z - min) * inv, one saturating conversion, IADD + IMAD per element
 #pragma unroll
                         for (int j = 0; j < CW; ++j) {
                             const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
                             of[j * ld] = y;
-                            const float a = actqf_fq_approx(q1, prelu(y, slope));
-                            st_s += a;
-                            st_ss = fmaf(a, a, st_ss);
+                            const unsigned c = code_u8(__fmul_rn(__fadd_rn(prelu(y, slope), -q1.mn), q1.inv));
+                            st_c += c;
+                            st_cc += c * c;
                         }
                     } else {
 #pragma unroll
@@ -343,14 +348,25 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(&bar->tmem_empty[acc]);
             if (EPI == EPI_EXPAND) {
-                const float ws = warp_sum(st_s), wss = warp_sum(st_ss);
+                double ds, dss;
+                if (p.quant) {
+                    // per lane <= 64 columns: sum c <= 16 320, sum c^2 <= 4.2e6; per warp x32: both fit 32 bits
+                    const unsigned wc = __reduce_add_sync(0xffffffffu, st_c), wcc = __reduce_add_sync(0xffffffffu, st_cc);
+                    const unsigned nvalid = __popc(__ballot_sync(0xffffffffu, valid)) * COLS;
+                    const double dl = (double)q1.delta, mn = (double)q1.mn, n = (double)nvalid;
+                    ds = dl * (double)wc + n * mn;
+                    dss = dl * dl * (double)wcc + 2.0 * dl * mn * (double)wc + n * mn * mn;
+                } else {
+                    ds = (double)warp_sum(st_s);
+                    dss = (double)warp_sum(st_ss);
+                }
                 if (lane == 0) {
                     if (stat_sm) {
-                        atomicAdd(stat_sm + 2 * b, (double)ws);
-                        atomicAdd(stat_sm + 2 * b + 1, (double)wss);
+                        atomicAdd(stat_sm + 2 * b, ds);
+                        atomicAdd(stat_sm + 2 * b + 1, dss);
                     } else {
-                        atomicAdd(p.stats + 2 * b, (double)ws);
-                        atomicAdd(p.stats + 2 * b + 1, (double)wss);
+                        atomicAdd(p.stats + 2 * b, ds);
+                        atomicAdd(p.stats + 2 * b + 1, dss);
                     }
                 }
             }

@@ -68,7 +68,9 @@ template <int MT, int NW>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const KArgs p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by POINTER arithmetic on the shared array: the compiler keeps the address space, so reads of the
+    // per-channel constants below are LDS (an integer round trip would turn every one of them into a generic load)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int ST = num_stages<MT, NW>();
     constexpr int SB = stage_bytes<MT, NW>();
     Bars* bar = reinterpret_cast<Bars*>(smem + ST * SB);
