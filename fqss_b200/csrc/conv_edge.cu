@@ -243,6 +243,104 @@ int edge_synthesis_fwd(const float* x, int64_t ldx, const float* w, int64_t wstr
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// weight gradient, rows on lanes (the fast path; needs 16-byte aligned rows of g):
+//   a lane owns ONE output row o and its 16*CIN tap sums; all lanes of a warp walk the same frames, so the signal
+//   window is read as 128-bit BROADCAST loads (one wavefront) and needs no de-interleaving; g reaches the lanes
+//   through a cp.async double-buffered shared tile [32 rows][128 frames] (coalesced 16-byte copies in, conflict-free
+//   128-bit reads out with a row stride of 132 floats).  Per 4 frames and lane: 1 + 10*CIN LDS.128 and 64*CIN FMAs --
+//   the FMA pipe is the bound (16*CIN FMAs per element of g), shared memory and HBM stay below it.
+//   CTA = (1024-frame chunk, 32 rows, sample); 8 warps split every 128-frame tile 16 frames each.
+// ---------------------------------------------------------------------------------------------
+constexpr int WL_CH = 1024, WL_FT = 128, WL_GS = WL_FT + 4;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc),
+                 "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int CIN>
+__global__ void __launch_bounds__(256) edge_wgrad_lanes_kernel(const float* __restrict__ g, int64_t ldg, const float* __restrict__ x,
+                                                              int64_t ldx, int T, int Co, int Mo, double* __restrict__ acc) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int XW = ES * WL_CH + 8;                     // signal samples under one chunk (+ the second half of the last frame)
+    float* xs = sm;                                        // [CIN][XW]
+    float* gs = sm + CIN * XW;                             // [2][32][WL_GS]
+    const int b = blockIdx.z, o0 = blockIdx.y * 32, m0 = blockIdx.x * WL_CH;
+    const int tid = threadIdx.x, lane = tid & 31, wp = tid >> 5;
+    const int nfr = min(WL_CH, Mo - m0);
+    const int ntiles = (nfr + WL_FT - 1) / WL_FT;
+    auto issue_tile = [&](int t, int buf) {                // 32 rows x 32 quads = 1024 16-byte copies, 4 per thread
+        float* dst = gs + buf * 32 * WL_GS;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = tid + 256 * k, row = i >> 5, qd = i & 31;
+            const int f = t * WL_FT + 4 * qd;               // first frame of the quad inside the chunk
+            int nval = nfr - f;
+            nval = nval < 0 ? 0 : (nval > 4 ? 4 : nval);
+            if (o0 + row >= Co) nval = 0;
+            const float* src = g + ((int64_t)b * Co + (o0 + row < Co ? o0 + row : 0)) * ldg + m0 + (nval ? f : 0);
+            cp_async16(dst + row * WL_GS + 4 * qd, src, 4 * nval);      // bytes beyond src-size are zero-filled
+        }
+        cp_async_commit();
+    };
+    issue_tile(0, 0);
+    for (int c = 0; c < CIN; ++c) {
+        const float* xr = x + ((int64_t)b * CIN + c) * ldx;
+        const int t0 = m0 * ES;
+        for (int i = tid; i < XW; i += 256) xs[c * XW + i] = (t0 + i < T) ? __ldg(xr + t0 + i) : 0.f;
+    }
+    float sa[CIN * EK];
+#pragma unroll
+    for (int k = 0; k < CIN * EK; ++k) sa[k] = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        if (t + 1 < ntiles) {
+            issue_tile(t + 1, (t + 1) & 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();                                   // tile t (and, first time round, the window) visible to all
+        const float* gt = gs + (t & 1) * 32 * WL_GS + lane * WL_GS + 16 * wp;
+        const int fbase = t * WL_FT + 16 * wp;               // first of this warp's 16 frames inside the chunk
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 g4 = *reinterpret_cast<const float4*>(gt + 4 * q);
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) {
+                const float4* xw = reinterpret_cast<const float4*>(xs + c * XW + ES * (fbase + 4 * q));      // 40 samples
+                float xv[40];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) {
+                    const float4 v = xw[k];
+                    xv[4 * k] = v.x; xv[4 * k + 1] = v.y; xv[4 * k + 2] = v.z; xv[4 * k + 3] = v.w;
+                }
+#pragma unroll
+                for (int f = 0; f < 4; ++f)
+#pragma unroll
+                    for (int k = 0; k < EK; ++k) sa[c * EK + k] = fmaf(gv[f], xv[ES * f + k], sa[c * EK + k]);
+            }
+        }
+        __syncthreads();                                   // everyone is done with buffer t&1 before it is refilled
+    }
+    // cross-warp reduction through shared memory (the g buffers are free now): red[wp][k][lane]
+    float* red = gs;
+#pragma unroll
+    for (int k = 0; k < CIN * EK; ++k) red[(wp * CIN * EK + k) * 32 + lane] = sa[k];
+    __syncthreads();
+    for (int i = tid; i < CIN * EK * 32; i += 256) {
+        const int k = i >> 5, row = i & 31;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[(w * CIN * EK + k) * 32 + row];
+        if (o0 + row < Co) atomicAdd(acc + (int64_t)(o0 + row) * (CIN * EK) + k, (double)s);
+    }
+}
+
 template <int CIN, int R, int CHUNK>
 static void edge_wgrad_launch(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Co, int Mo, double* acc,
                               cudaStream_t s) {
@@ -258,6 +356,19 @@ static void edge_wgrad_launch(const float* g, int64_t ldg, const float* x, int64
 
 int edge_wgrad(const float* g, int64_t ldg, const float* x, int64_t ldx, int T, int B, int Cin, int Co, int Mo, double* acc, cudaStream_t s) {
     if (Cin != 1 && Cin != 2) return 1;
+    if ((ldg & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {
+        const size_t smem = ((size_t)Cin * (ES * WL_CH + 8) + 2 * 32 * WL_GS) * sizeof(float);
+        static bool cfg = false;
+        if (!cfg) {
+            cudaFuncSetAttribute(edge_wgrad_lanes_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+            cudaFuncSetAttribute(edge_wgrad_lanes_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+            cfg = true;
+        }
+        dim3 grid((Mo + WL_CH - 1) / WL_CH, (Co + 31) / 32, B);
+        if (Cin == 1) edge_wgrad_lanes_kernel<1><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
+        else edge_wgrad_lanes_kernel<2><<<grid, 256, smem, s>>>(g, ldg, x, ldx, T, Co, Mo, acc);
+        return 0;
+    }
     if (Cin == 1) edge_wgrad_launch<1, 4, 2048>(g, ldg, x, ldx, T, B, Co, Mo, acc, s);
     else edge_wgrad_launch<2, 2, 1024>(g, ldg, x, ldx, T, B, Co, Mo, acc, s);
     return 0;
