@@ -321,18 +321,29 @@ __global__ void __launch_bounds__(NTH) tcn_hidden_fq_kernel(const fqss_tcn_block
         const uint2* c3 = reinterpret_cast<const uint2*>(p.code3 + r * p.ld);       // rows are 8-byte aligned (ld % 8 == 0)
         uint4* o16 = reinterpret_cast<uint4*>(out);
         const int n8 = (p.M + 7) >> 3;
-        for (int v = threadIdx.x; v < n8; v += NTH) {
-            const uint2 cw = __ldg(c3 + v);
-            const uint32_t w[2] = {cw.x, cw.y};
-            uint32_t o[4];
+        constexpr int NQ = 4;                       // code words in flight per thread (a row is only ~500 of them)
+        for (int base = threadIdx.x; base < n8; base += NQ * NTH) {
+            uint2 cw[NQ];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t a0 = lut16[w[k] & 255u], a1 = lut16[(w[k] >> 8) & 255u];
-                const uint32_t a2 = lut16[(w[k] >> 16) & 255u], a3 = lut16[w[k] >> 24];
-                o[2 * k] = a0 | (a1 << 16);
-                o[2 * k + 1] = a2 | (a3 << 16);
+            for (int q = 0; q < NQ; ++q) {
+                const int v = base + q * NTH;
+                cw[q] = v < n8 ? __ldg(c3 + v) : make_uint2(0u, 0u);
             }
-            o16[v] = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int v = base + q * NTH;
+                if (v >= n8) continue;
+                const uint32_t w[2] = {cw[q].x, cw[q].y};
+                uint32_t o[4];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const uint32_t a0 = lut16[w[k] & 255u], a1 = lut16[(w[k] >> 8) & 255u];
+                    const uint32_t a2 = lut16[(w[k] >> 16) & 255u], a3 = lut16[w[k] >> 24];
+                    o[2 * k] = a0 | (a1 << 16);
+                    o[2 * k + 1] = a2 | (a3 << 16);
+                }
+                o16[v] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
         }
         return;
     }
@@ -579,7 +590,13 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
             if (mode == 0) FQSS_DW_LAUNCH(true, 0); else if (mode == 1) FQSS_DW_LAUNCH(true, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(true, 2); else FQSS_DW_LAUNCH(true, 3);
             FQSS_RC3_LAUNCH();
-            { FQSS_PROF("tcn_hidden_fq", s); tcn_hidden_fq_kernel<true, 256><<<rows, 256, 0, s>>>(*p); }
+            {
+                FQSS_PROF("tcn_hidden_fq", s);
+                static const int hth = getenv("FQSS_HFQ_TH") ? atoi(getenv("FQSS_HFQ_TH")) : 128;
+                if (hth == 256) tcn_hidden_fq_kernel<true, 256><<<rows, 256, 0, s>>>(*p);
+                else if (hth == 64) tcn_hidden_fq_kernel<true, 64><<<rows, 64, 0, s>>>(*p);
+                else tcn_hidden_fq_kernel<true, 128><<<rows, 128, 0, s>>>(*p);
+            }
         } else {
             if (mode == 0) FQSS_DW_LAUNCH(false, 0); else if (mode == 1) FQSS_DW_LAUNCH(false, 1);
             else if (mode == 2) FQSS_DW_LAUNCH(false, 2); else FQSS_DW_LAUNCH(false, 3);
