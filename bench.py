@@ -149,7 +149,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ConvTasNet QAT train audio-sec/sec", "value": val, "unit": "audio-s/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, B, 1),
+            "config": dict(workload_config(args, args.per_gpu_batch, max(args.gpus, 1)), reference_sample_batch=B),
             "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": "oracle port of the reference step (bit-identical to ssi-research/FQSS on CPU), "
                                        "batch %d x 4 s per step, %d steps" % (B, args.steps)},
