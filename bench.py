@@ -42,6 +42,9 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; never a reported number)")
     ap.add_argument("--breakdown-file", default="", help="write the per-kernel attribution table of one step here")
+    ap.add_argument("--cuda-graph", type=int, default=1,
+                    help="1 (default): the timed steps replay ONE captured CUDA graph of the whole step "
+                         "(fqss_b200.graph.GraphedStep); 0: eager launches")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
                          "numbers printed by such a run are never bench values")
@@ -218,6 +221,18 @@ def run_ours(args):
         arena.clip_and_step(pre_scale=scale, max_norm=5.0, lr=1e-3)
         return loss
 
+    graphed, graph_error = None, None
+    if args.cuda_graph and not args.profile_step:
+        from fqss_b200.graph import GraphedStep
+        try:
+            graphed = GraphedStep(step, dev_batches[0], warmup=max(args.warmup, 3))
+        except Exception as e:      # same kernels either way: fall back to eager launches and say so in the line
+            graph_error = repr(e)[:200]
+            torch.cuda.synchronize()
+
+    def run_step(mix, src):
+        return graphed(mix, src) if graphed is not None else step(mix, src)
+
     def timed(n, from_host):
         if world > 1:
             dist.barrier()
@@ -226,12 +241,17 @@ def run_ours(args):
         t0 = time.time()
         e0.record()
         for i in range(n):
-            if from_host:
+            if from_host and graphed is not None:      # pinned host -> the graph's static input buffers
+                m, s = host[i % n_host]
+                mix, src = graphed.static_in
+                mix.copy_(m, non_blocking=True)
+                src.copy_(s, non_blocking=True)
+            elif from_host:
                 m, s = host[i % n_host]
                 mix, src = m.to(dev, non_blocking=True), s.to(dev, non_blocking=True)
             else:
                 mix, src = dev_batches[i % n_host]
-            loss = step(mix, src)
+            loss = run_step(mix, src)
             if from_host:
                 loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         e1.record()
@@ -260,6 +280,8 @@ def run_ours(args):
     c0 = R.launch_count()
     ms, t0, t1 = timed(args.steps, False)
     launches = R.launch_count() - c0          # kernels launched by libfqss_sm100 inside the timed region
+    if graphed is not None:                   # replays launch the captured nodes without re-entering the library
+        launches = graphed.kernels_per_replay * args.steps
     ms_e2e, _, t2 = timed(args.steps, True)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     final_loss = float(loss_host.item())
@@ -277,7 +299,9 @@ def run_ours(args):
             "config": workload_config(args, B, world),
             "e2e": {"value": val_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": B * 3 * T * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss}
+            "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
+            "launch_mode": ("one CUDA graph per step (%d library kernels per replay)" % graphed.kernels_per_replay)
+                           if graphed is not None else ("eager" + (" (graph capture failed: %s)" % graph_error if graph_error else ""))}
     if world == 1 and not args.no_roofline:
         try:
             Mfr = (T - 16) // 8 + 1

@@ -37,6 +37,7 @@ class ParamArena:
         self.exp_avg = torch.zeros_like(self.flat)
         self.exp_avg_sq = torch.zeros_like(self.flat)
         self.sumsq = torch.zeros(1, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         self.step_count = 0
         self.views, self.grad_views = [], []
         off = 0
@@ -100,9 +101,9 @@ class ParamArena:
         s = stream_ptr()
         check(lib().fqss_arena_sumsq(ptr(self.grad), n, ptr(self.sumsq), ptr(ws), ws.numel(), s))
         check(lib().fqss_arena_scale_clip(ptr(self.grad), n, ptr(self.sumsq), float(pre_scale), float(max_norm), s))
-        self.step_count += 1
-        check(lib().fqss_arena_adam(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, float(lr),
-                                    float(betas[0]), float(betas[1]), float(eps), self.step_count, s))
+        self.step_count += 1          # host mirror; the kernels read the device counter (CUDA-graph replays stay correct)
+        check(lib().fqss_arena_adam_dev(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, float(lr),
+                                        float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev), s))
 
     def zero_grad(self):
         for p in self.params:

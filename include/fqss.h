@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 11
+#define FQSS_ABI_VERSION 12
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -343,6 +343,10 @@ int fqss_arena_scale_clip(float* g, int64_t n, const float* sumsq, float pre_sca
 /* fused Adam step over the flat arena (torch.optim.Adam semantics, weight_decay=0, amsgrad=False) */
 int fqss_arena_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                     float eps, int step, void* stream);
+/* same step with the step count kept on the device: uses t = *step_dev + 1 for the bias corrections, then increments
+ * *step_dev -- nothing step-dependent is baked into the launch, so a captured CUDA graph of the step can be replayed */
+int fqss_arena_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                        float eps, int* step_dev, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement support (nothing like it in the reference): launch accounting and per-kernel-class

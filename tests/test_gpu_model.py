@@ -223,3 +223,51 @@ def test_full_size_model_vs_oracle():
     assert abs(loss.item() - loss_o) < max(3 * loss_dev, 0.15), (loss.item(), loss_o, loss_dev)
     assert (1 - our_cos) < max(3 * (1 - self_cos), 1e-2), (our_cos, self_cos)
     assert abs(ratio - 1) < 0.1
+
+
+def test_cuda_graph_step_matches_eager(golden):
+    """A captured CUDA graph of the whole QAT step (fqss_b200.graph.GraphedStep: forward, teacher, loss, backward,
+    gather, clip, Adam with the step count on the device) must move the parameters exactly like eager launches."""
+    import copy
+    from fqss_b200.graph import GraphedStep
+    from fqss_b200.losses import fqss_kd_loss
+    from fqss_b200.parallel import ParamArena
+    g, model, fmodel, calib = _prep_small(golden)
+    model2 = copy.deepcopy(model)
+    gen = torch.Generator().manual_seed(7)
+    batches = []
+    for _ in range(3):
+        src = (torch.randn(2, 2, 2400, generator=gen) * 0.05).to(DEV)
+        batches.append((src.sum(1, keepdim=True), src))
+
+    def make_step(m):
+        arena = ParamArena(list(m.parameters()))
+
+        def step(mix, src):
+            arena.zero_grad()
+            est = m(mix)
+            with torch.no_grad():
+                fest = fmodel(mix)
+            loss, _, _ = fqss_kd_loss(est, fest, src, 0.1)
+            loss.backward()
+            arena.gather_grads()
+            arena.clip_and_step(pre_scale=arena.allreduce_mean(), max_norm=5.0, lr=1e-3)
+            return loss
+        return step, arena
+    step_e, arena_e = make_step(model)
+    step_g, arena_g = make_step(model2)
+    init = arena_e.flat.clone()
+    graphed = GraphedStep(step_g, batches[0], warmup=1)
+    assert graphed.kernels_per_replay > 50
+    step_e(*batches[0])                                     # the eager twin takes the same warm-up step
+    losses_e, losses_g = [], []
+    for mix, src in batches:
+        losses_e.append(step_e(mix, src).item())
+        losses_g.append(graphed(mix, src).item())
+    torch.cuda.synchronize()
+    assert int(arena_g.step_dev.item()) == int(arena_e.step_dev.item()) == 4
+    assert max(abs(a - b) for a, b in zip(losses_e, losses_g)) < 5e-2, (losses_e, losses_g)
+    # same kernels in the same order: only the order of the fp64 atomics can differ between the two runs
+    moved = (arena_e.flat - init).norm().item()
+    diff = (arena_e.flat - arena_g.flat).norm().item()
+    assert moved > 0 and diff < 0.1 * moved, (diff, moved)
