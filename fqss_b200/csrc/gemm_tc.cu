@@ -248,12 +248,28 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         // gLN statistics of a1 = delta1 * code + min1 from INTEGER code sums (exact adds; expanded once per
                         // tile): prelu, (z - min) * inv, one saturating conversion, IADD + IMAD per element
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) {
-                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                            of[j * ld] = y;
-                            const unsigned c = code_u8(__fmul_rn(__fadd_rn(prelu(y, slope), -q1.mn), q1.inv));
-                            st_c += c;
-                            st_cc += c * c;
+                        uint8_t* oc = p.code1 ? p.code1 + ((int64_t)b * p.N + o0) * ld + m : nullptr;
+                        if (oc) {
+                            // the EXACT code of FQ1 (same arithmetic as every later consumer), stored for the depthwise
+                            // kernel and for backward: the hidden tensor is re-read as 1 B/frame instead of 4
+#pragma unroll
+                            for (int j = 0; j < CW; ++j) {
+                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                of[j * ld] = y;
+                                const unsigned c = code_u8(actqf_t(q1, prelu_f(y, slope)));
+                                oc[j * ld] = (uint8_t)c;
+                                st_c += c;
+                                st_cc += c * c;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CW; ++j) {
+                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                of[j * ld] = y;
+                                const unsigned c = code_u8(__fmul_rn(__fadd_rn(prelu(y, slope), -q1.mn), q1.inv));
+                                st_c += c;
+                                st_cc += c * c;
+                            }
                         }
                     } else {
 #pragma unroll

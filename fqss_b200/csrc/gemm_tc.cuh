@@ -28,6 +28,7 @@ struct Args {
     const float* slope;
     const float* q1_min; const float* q1_max;
     double* stats;
+    uint8_t* code1;              // EPI_EXPAND, quantised: exact 8-bit codes of FQ1(PReLU(y)) [B][N][ld] (may be NULL)
     // EPI_EXPAND: the last CTA turns the finished statistics into the row constants rc[RC_HDR + 2*B] (tcn_common.cuh)
     float* rc; double n_elems;
     const float* q2_min; const float* q2_max; const float* q3_min; const float* q3_max;

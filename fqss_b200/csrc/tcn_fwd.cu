@@ -171,26 +171,9 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
         __syncthreads();
     }
     const float* y1 = p.y1 + r * p.ld;
-    uint32_t* code1 = p.code1 ? reinterpret_cast<uint32_t*>(p.code1 + r * p.ld) : nullptr;
+    const uint32_t* code1 = reinterpret_cast<const uint32_t*>(p.code1 + r * p.ld);      // written by the expand GEMM's epilogue
     const int nvec = ld >> 2;
-    for (int v = threadIdx.x; v < nvec; v += NTH) {
-        const float4 y = ldg4_stream(y1 + 4 * v);
-        float4 a;
-        if (QUANT) {
-            const float2 t01 = actqf_t2(h.q1, make_float2(prelu_f(y.x, h.slope), prelu_f(y.y, h.slope)));
-            const float2 t23 = actqf_t2(h.q1, make_float2(prelu_f(y.z, h.slope), prelu_f(y.w, h.slope)));
-            const unsigned i0 = code_u8(t01.x), i1 = code_u8(t01.y), i2 = code_u8(t23.x), i3 = code_u8(t23.y);
-            if (code1) code1[v] = i0 | (i1 << 8) | (i2 << 16) | (i3 << 24);
-            a.x = lut[i0];
-            a.y = lut[i1];
-            a.z = lut[i2];
-            a.w = lut[i3];
-        } else {
-            a.x = gln_apply(h.g, prelu_f(y.x, h.slope));
-            a.y = gln_apply(h.g, prelu_f(y.y, h.slope));
-            a.z = gln_apply(h.g, prelu_f(y.z, h.slope));
-            a.w = gln_apply(h.g, prelu_f(y.w, h.slope));
-        }
+    auto put = [&](int v, float4 a) {
         if (4 * v + 3 >= M) {            // ragged tail / pad columns: the FIR must see zeros there
             if (4 * v + 0 >= M) a.x = 0.f;
             if (4 * v + 1 >= M) a.y = 0.f;
@@ -198,6 +181,26 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
             a.w = 0.f;
         }
         *reinterpret_cast<float4*>(row + 4 * v) = a;
+    };
+    if (QUANT) {
+        // code words first (4 in flight per thread: a row is ~1000 of them), then one table lookup per frame
+        constexpr int NQ = 4;
+        for (int base = threadIdx.x; base < nvec; base += NQ * NTH) {
+            uint32_t cw[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) cw[q] = (base + q * NTH < nvec) ? __ldg(code1 + base + q * NTH) : 0u;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int v = base + q * NTH;
+                if (v < nvec) put(v, make_float4(lut[cw[q] & 255u], lut[(cw[q] >> 8) & 255u], lut[(cw[q] >> 16) & 255u], lut[cw[q] >> 24]));
+            }
+        }
+    } else {
+        for (int v = threadIdx.x; v < nvec; v += NTH) {
+            const float4 y = ldg4_stream(y1 + 4 * v);
+            put(v, make_float4(gln_apply(h.g, prelu_f(y.x, h.slope)), gln_apply(h.g, prelu_f(y.y, h.slope)),
+                               gln_apply(h.g, prelu_f(y.z, h.slope)), gln_apply(h.g, prelu_f(y.w, h.slope))));
+        }
     }
     __syncthreads();
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
@@ -461,7 +464,7 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
     if (p->has_res) FQSS_REQUIRE(p->x_out && p->x_out_op, -1, "%s: missing residual buffers", who);
     if (!p->first_block) FQSS_REQUIRE(p->skip_in, -1, "%s: missing skip_in", who);
     if (p->quant) {
-        FQSS_REQUIRE(p->code3, -1, "%s: the quantised path needs the code3 buffer (the depthwise kernel hands FQ3's codes to the hidden quantiser through it)", who);
+        FQSS_REQUIRE(p->code1 && p->code3, -1, "%s: the quantised path needs the code buffers (the expand GEMM hands FQ1's codes to the depthwise kernel through code1, the depthwise kernel FQ3's codes to the hidden quantiser through code3)", who);
         const fqss_qrange* qs[] = {&p->q1, &p->q2, &p->q3, &p->q4, &p->qskip};
         for (auto q : qs) FQSS_REQUIRE(q->rmin && q->rmax, -1, "%s: missing quantiser range", who);
         if (p->has_res) FQSS_REQUIRE(p->qres.rmin && p->qadd.rmin, -1, "%s: missing residual quantisers", who);
@@ -561,7 +564,7 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     tcg::Args a{};
     a.B = p->B; a.M = p->M; a.K = p->Cio; a.N = p->Chid; a.ld = p->ld; a.s1 = p->s1_1; a.s0 = p->s0_1; a.quant = p->quant;
     if (p->split) { a.K = 3 * p->Cio; a.a_rows = 2 * p->Cio; }
-    a.out_f32 = p->y1; a.slope = p->slope1; a.q1_min = p->q1.rmin; a.q1_max = p->q1.rmax; a.stats = p->stats1;
+    a.out_f32 = p->y1; a.code1 = p->quant ? p->code1 : nullptr; a.slope = p->slope1; a.q1_min = p->q1.rmin; a.q1_max = p->q1.rmax; a.stats = p->stats1;
     a.rc = p->rc1; a.n_elems = (double)p->Chid * (double)p->M;
     a.q2_min = p->q2.rmin; a.q2_max = p->q2.rmax; a.q3_min = p->q3.rmin; a.q3_max = p->q3.rmax;
     rc = tcg::run(tcg::EPI_EXPAND, p->x_op, p->Wc1, a, s);

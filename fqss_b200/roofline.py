@@ -63,8 +63,8 @@ def algorithmic_bytes(B, M, Cio=128, Chid=512):
     w1, w2 = Chid * Cio * 2, 2 * Cio * Chid * 2
     return {
         # forward
-        "gemm_expand": 2 * I + w1 + 4 * H,                      # x_op bf16 in, y1 fp32 out
-        "tcn_dw_fwd": 4 * H + 4 * H + H + H,                    # y1 in, y3 + code1 + code3 (u8) out
+        "gemm_expand": 2 * I + w1 + 4 * H + H,                  # x_op bf16 in, y1 fp32 + code1 (u8) out
+        "tcn_dw_fwd": H + 4 * H + H,                            # code1 (u8) in, y3 + code3 (u8) out
         "tcn_hidden_fq": H + 2 * H,                             # code3 (u8) in, a4 operand (bf16 codes) out
         "gemm_resskip": 2 * H + w2 + 4 * I * 2 + 4 * I * 4 + 2 * I,   # a4, x_in, skip_in -> res_y, skip_y, x_out, skip_out, x_out_op
         "tcn_dw_fwd(float)": 8 * H,

@@ -248,10 +248,10 @@ typedef struct fqss_tcn_block {
      * (rc1: q1, q2, q3 and gLN1 from stats1; rc3: q3, q4 and gLN2 from stats3) */
     float* rc1; float* rc3;
     /* quantised model: the 8-bit codes of a1 = FQ1(PReLU(y1)) and a3 = FQ3(PReLU(y3)), one byte per frame
-     * ([B][Chid][ld]).  code3 is REQUIRED: the depthwise kernel writes it and the hidden quantiser (code3 -> FQ4
-     * code, 3 B/element) reads it instead of y3.  Both are re-read by the backward stages that need only the codes
-     * (FQ2/FQ4 masks, gLN sums, tap gradients).  code1 may be NULL in inference (forward skips the store; backward
-     * then refuses to run). */
+     * ([B][Chid][ld]); both REQUIRED.  The expand GEMM's epilogue writes code1 and the depthwise kernel reads it
+     * (1 B/frame instead of re-deriving the code from y1); the depthwise kernel writes code3 and the hidden quantiser
+     * (code3 -> FQ4 code, 3 B/frame) reads it.  Both are re-read by the backward stages that need only the codes
+     * (FQ2/FQ4 masks, gLN sums, tap gradients); y1 / y3 are re-read only where the continuous value matters. */
     uint8_t* code1; uint8_t* code3;
 } fqss_tcn_block;
 
