@@ -196,10 +196,20 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
             }
         }
     } else {
-        for (int v = threadIdx.x; v < nvec; v += NTH) {
-            const float4 y = ldg4_stream(y1 + 4 * v);
-            put(v, make_float4(gln_apply(h.g, prelu_f(y.x, h.slope)), gln_apply(h.g, prelu_f(y.y, h.slope)),
-                               gln_apply(h.g, prelu_f(y.z, h.slope)), gln_apply(h.g, prelu_f(y.w, h.slope))));
+        constexpr int NQ = 4;
+        for (int base = threadIdx.x; base < nvec; base += NQ * NTH) {
+            float4 yv[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                yv[q] = (base + q * NTH < nvec) ? ldg4_stream(y1 + 4 * (base + q * NTH)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const int v = base + q * NTH;
+                const float4 y = yv[q];
+                if (v < nvec)
+                    put(v, make_float4(gln_apply(h.g, prelu_f(y.x, h.slope)), gln_apply(h.g, prelu_f(y.y, h.slope)),
+                                       gln_apply(h.g, prelu_f(y.z, h.slope)), gln_apply(h.g, prelu_f(y.w, h.slope))));
+            }
         }
     }
     __syncthreads();
@@ -576,13 +586,22 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_fwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         static bool cfg = false;
         if (!cfg) {
-#define FQSS_DW_ATTR(Q, D) cudaFuncSetAttribute(tcn_dw_fwd_kernel<Q, D, (Q ? 256 : 128)>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
-            FQSS_DW_ATTR(true, 0); FQSS_DW_ATTR(true, 1); FQSS_DW_ATTR(true, 2); FQSS_DW_ATTR(true, 3);
-            FQSS_DW_ATTR(false, 0); FQSS_DW_ATTR(false, 1); FQSS_DW_ATTR(false, 2); FQSS_DW_ATTR(false, 3);
+#define FQSS_DW_ATTR(Q, D, T) cudaFuncSetAttribute(tcn_dw_fwd_kernel<Q, D, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)
+            FQSS_DW_ATTR(true, 0, 256); FQSS_DW_ATTR(true, 1, 256); FQSS_DW_ATTR(true, 2, 256); FQSS_DW_ATTR(true, 3, 256);
+            FQSS_DW_ATTR(true, 0, 128); FQSS_DW_ATTR(true, 1, 128); FQSS_DW_ATTR(true, 2, 128); FQSS_DW_ATTR(true, 3, 128);
+            FQSS_DW_ATTR(false, 0, 128); FQSS_DW_ATTR(false, 1, 128); FQSS_DW_ATTR(false, 2, 128); FQSS_DW_ATTR(false, 3, 128);
+            FQSS_DW_ATTR(false, 0, 256); FQSS_DW_ATTR(false, 1, 256); FQSS_DW_ATTR(false, 2, 256); FQSS_DW_ATTR(false, 3, 256);
 #undef FQSS_DW_ATTR
             cfg = true;
         }
-#define FQSS_DW_LAUNCH(Q, D) do { FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s); tcn_dw_fwd_kernel<Q, D, (Q ? 256 : 128)><<<rows, (Q ? 256 : 128), smem, s>>>(*p); } while (0)
+        static const int th_q = getenv("FQSS_DWF_TH") ? atoi(getenv("FQSS_DWF_TH")) : 128;
+        static const int th_f = getenv("FQSS_DWFF_TH") ? atoi(getenv("FQSS_DWFF_TH")) : 128;
+#define FQSS_DW_LAUNCH(Q, D)                                                                                   \
+    do {                                                                                                       \
+        FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s);                                                  \
+        if ((Q ? th_q : th_f) == 256) tcn_dw_fwd_kernel<Q, D, 256><<<rows, 256, smem, s>>>(*p);                \
+        else tcn_dw_fwd_kernel<Q, D, 128><<<rows, 128, smem, s>>>(*p);                                         \
+    } while (0)
         RowConstJob job3;
         job3.stats = p->stats3; job3.rc = p->rc3; job3.B = p->B; job3.n_elems = (double)p->Chid * (double)p->M;
         job3.qa_min = p->q3.rmin; job3.qa_max = p->q3.rmax; job3.qb_min = p->q4.rmin; job3.qb_max = p->q4.rmax;
