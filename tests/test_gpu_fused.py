@@ -274,3 +274,94 @@ def test_code_conv1x1_vs_torch():
     assert rel(got["gW"], W.grad) < 1e-2, rel(got["gW"], W.grad)
     assert rel(got["gb"], bias.grad) < 1e-4
     assert rel(got["gmin"], wmin.grad) < 2e-2 and rel(got["gmax"], wmax.grad) < 2e-2, (rel(got["gmin"], wmin.grad), rel(got["gmax"], wmax.grad))
+
+
+@pytest.mark.parametrize("B,M,dils", [(2, 250, (3, 5, 6, 1)), (1, 1023, (2, 7, 64, 4)), (5, 77, (1, 2, 12, 9))])
+def test_fused_float_stack_odd_shapes(B, M, dils):
+    """Edge geometry of the fused row kernels: ragged rows (M % 4 != 0, M % 8 != 0), a single sample, and dilations the
+    recipe never uses (not powers of two -> the generic tap path; dilation larger than a tile), forward and backward
+    against plain torch modules with the same bf16 operand rounding."""
+    import torch.nn.functional as F
+    from fqss_b200 import tcn_engine as E
+    from fqss_b200.qat.models.convtasnetq import ConvTasNetQ
+    torch.manual_seed(1)
+    model = ConvTasNetQ(**MED_KW).to(DEV)
+    blocks = list(model.masker.TCN)
+    assert len(blocks) == len(dils)
+    for blk, d in zip(blocks, dils):
+        blk.shared_block[3].dilation, blk.shared_block[3].padding = (d,), (d,)
+        with torch.no_grad():
+            for p in blk.parameters():
+                if p.dim() == 1:
+                    p.add_(0.1 * torch.randn_like(p))
+    x = (torch.randn(B, 128, M, device=DEV) * 0.5).requires_grad_(True)
+
+    def r16(t):
+        return t + (t.bfloat16().float() - t).detach()
+
+    def ref_block(blk, xin):
+        sb = blk.shared_block
+        h = F.prelu(F.conv1d(r16(xin), r16(sb[0].weight), sb[0].bias), sb[1].weight)
+        h = sb[2](h)
+        h = F.prelu(F.conv1d(h, sb[3].weight, sb[3].bias, padding=sb[3].padding[0], dilation=sb[3].dilation[0],
+                             groups=h.shape[1]), sb[4].weight)
+        h = r16(sb[5](h))
+        return xin + F.conv1d(h, r16(blk.res_conv.weight), blk.res_conv.bias), F.conv1d(h, r16(blk.skip_conv.weight), blk.skip_conv.bias)
+    feats, tot = x, None
+    for blk in blocks:
+        feats, skip = ref_block(blk, feats)
+        tot = skip if tot is None else tot + skip
+    gsk = torch.randn_like(tot)
+    tot.backward(gsk)
+    ref_gx = x.grad.clone()
+    ref_grads = {n: p.grad.clone() for n, p in model.masker.TCN.named_parameters() if p.grad is not None}
+    model.zero_grad()
+    x2 = x.detach().clone().requires_grad_(True)
+    _, ss = E.fused_tcn(x2, blocks, None, False, (None, None))
+    assert ss.shape == tot.shape
+    assert rel(ss, tot) < 1e-3, rel(ss, tot)
+    ss.backward(gsk)
+    assert rel(x2.grad, ref_gx) < 2e-2, rel(x2.grad, ref_gx)
+    slope_scale = max(float(g.abs().max()) for n, g in ref_grads.items() if g.numel() == 1)
+    for n, p in model.masker.TCN.named_parameters():
+        if n not in ref_grads:
+            continue
+        assert p.grad is not None, n
+        if p.numel() == 1:
+            assert abs(float(p.grad) - float(ref_grads[n])) < 3e-2 * slope_scale, (n, float(p.grad), float(ref_grads[n]))
+        else:
+            assert rel(p.grad, ref_grads[n]) < 3e-2, (n, rel(p.grad, ref_grads[n]))
+
+
+def test_fused_quant_stack_odd_shapes_vs_per_layer():
+    """Quantised stack with a ragged row length and non-power-of-two dilations: the fused engine (codes from the GEMM
+    epilogue, code tables, fused backward) against the per-layer wrappers on the same GPU, teacher-free."""
+    from fqss_b200.qat.models.convtasnetq import MaskGenerator
+    from fqss_b200.qat.models.load_model import enable_observer
+    from fqss_b200.testing import model_pair
+    model, _ = model_pair(MED_KW, DEV, seed=0)
+    for blk, d in zip(model.masker.TCN, (3, 1, 6, 2)):
+        conv = blk.shared_block[3].conv1d
+        conv.dilation, conv.padding = (d,), (d,)
+    gen = torch.Generator().manual_seed(3)
+    mix = (torch.randn(2, 2, 2014, generator=gen) * 0.05).sum(1, keepdim=True).to(DEV)      # M = 250 frames
+    with torch.no_grad():
+        model(mix)
+        model(mix)
+    enable_observer(model, False)
+    out = {}
+    for fused in (False, True):
+        MaskGenerator.use_fused = fused
+        try:
+            model.zero_grad(set_to_none=True)
+            est = model(mix)
+            est.square().mean().backward()
+            out[fused] = (est.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None})
+        finally:
+            MaskGenerator.use_fused = True
+    assert rel(out[True][0], out[False][0]) < 0.1, rel(out[True][0], out[False][0])
+    assert set(out[True][1].keys()) == set(out[False][1].keys())
+    num = sum((out[True][1][k].double() * out[False][1][k].double()).sum().item() for k in out[True][1])
+    n1 = sum(out[True][1][k].double().pow(2).sum().item() for k in out[True][1]) ** 0.5
+    n2 = sum(out[False][1][k].double().pow(2).sum().item() for k in out[False][1]) ** 0.5
+    assert num / (n1 * n2) > 0.9 and abs(n1 / n2 - 1) < 0.25, (num / (n1 * n2), n1 / n2)
