@@ -16,6 +16,7 @@
 //   warps 4-11 epilogue.  4-stage smem ring (A 16 KB + B up to 32 KB per stage), 2 TMEM accumulator
 //   stages so the epilogue of tile i overlaps the MMAs of tile i+1.  Grid = one CTA per SM.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "fqss_common.cuh"
 #include "tc_common.cuh"
@@ -55,7 +56,10 @@ __host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<NT>
 
 __device__ __forceinline__ float prelu(float y, float a) { return y > 0.f ? y : a * y; }
 
-template <int NT, int EPI>
+// LDC > 0: the row pitch is the compile-time constant LDC (the recipe's 4 s / 8 kHz segments give M = 3999, pitch
+// 4000): the per-column addresses of the epilogue become immediates of ONE base pointer per tensor instead of a
+// 64-bit pointer bump per column and tensor (12 of the ~64 instructions per output of the res/skip tail).
+template <int NT, int EPI, int LDC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args p) {
     extern __shared__ uint8_t smem_raw[];
@@ -181,7 +185,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (!p.first_block) qadds = load_actqf(p.qadds_min, p.qadds_max, 8);
         }
-        const int64_t ld = p.ld;
+        const int64_t ld = LDC > 0 ? (int64_t)LDC : p.ld;
         int acc = 0;
         uint32_t acc_phase = 0;
         int fold_b = -1;
@@ -458,12 +462,14 @@ static int make_w_map(CUtensorMap* tm, const void* base, int N, int K, int box_r
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int NT, int EPI>
+constexpr int LD_HOT = 4000;      // pitch of the recipe's segments (M = 3999): specialised epilogue addressing
+
+template <int NT, int EPI, int LDC>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, cudaStream_t s) {
     static bool configured = false;
     constexpr int smem = smem_bytes<NT>();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel<NT, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(pw_gemm_kernel<NT, EPI, LDC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("pw_gemm: cannot set %d B dynamic smem: %s", smem, cudaGetErrorString(e));
             return -4;
@@ -476,7 +482,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, c
     if (grid > tiles) grid = tiles;
     static const char* const names[] = {"gemm_store", "gemm_expand", "gemm_resskip", "gemm_dgrad_bf16", "gemm_dgrad_add", "gemm_relu_mul"};
     FQSS_PROF((a.a_rows > 0 && a.a_rows < a.K) ? (EPI == EPI_EXPAND ? "gemm_expand(split3)" : EPI == EPI_RESSKIP ? "gemm_resskip(split3)" : EPI == EPI_RELU_MUL ? "gemm_relu_mul(split3)" : "gemm_store(split3)") : names[EPI], s);
-    pw_gemm_kernel<NT, EPI><<<grid, NUM_THREADS, smem, s>>>(ta, tb, a);
+    pw_gemm_kernel<NT, EPI, LDC><<<grid, NUM_THREADS, smem, s>>>(ta, tb, a);
     return check_launch("pw_gemm");
 }
 
@@ -493,9 +499,13 @@ int run(int epi, const void* act_bf16, const void* w_bf16, const Args& a, cudaSt
     const bool wide = (a.N % 256 == 0);
     r = make_w_map(&tb, w_bf16, a.N, a.K, wide ? 256 : 128);
     FQSS_REQUIRE(r == 0, -4, "pw_gemm: cuTensorMapEncodeTiled(weights) failed (%d)", r);
-#define FQSS_GEMM_CASE(E)                                 \
-    case E:                                               \
-        return wide ? launch<256, E>(ta, tb, a, s) : launch<128, E>(ta, tb, a, s);
+    static const bool ld_spec = !(getenv("FQSS_GEMM_LDSPEC") && atoi(getenv("FQSS_GEMM_LDSPEC")) == 0);
+    const bool hot = ld_spec && a.ld == LD_HOT;
+#define FQSS_GEMM_CASE(E)                                                                                      \
+    case E:                                                                                                    \
+        if (hot && E != EPI_EXPAND) /* measured: the expand tail is faster with pointer bumps */              \
+            return wide ? launch<256, E, LD_HOT>(ta, tb, a, s) : launch<128, E, LD_HOT>(ta, tb, a, s);         \
+        return wide ? launch<256, E, 0>(ta, tb, a, s) : launch<128, E, 0>(ta, tb, a, s);
     switch (epi) {
         FQSS_GEMM_CASE(EPI_STORE)
         FQSS_GEMM_CASE(EPI_EXPAND)
