@@ -285,9 +285,25 @@ def run_ours(args):
     ms_e2e, _, t2 = timed(args.steps, True)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     final_loss = float(loss_host.item())
-    if rank != 0:
+
+    def finish():
+        """Multi-rank teardown.  A CUDA graph that captured NCCL's all-reduce keeps the communicator busy: tearing the
+        process group down with the graph alive hangs (seen at 2 GPUs), so drop the graph first, and do not let a slow
+        communicator teardown hold the job once every rank is past its last collective."""
+        nonlocal graphed
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            graphed = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            sys.stdout.flush()
+            os._exit(0)             # the result line is out; skip destroy_process_group (exit code 0 for torchrun)
+
+    if rank != 0:
+        finish()
         return
     gb = B * world
     val = gb * SEG_SECONDS * args.steps / (ms / 1e3)
@@ -323,8 +339,7 @@ def run_ours(args):
                                 "sample": "oracle port of the reference QAT step on host cores: batch %d x 4 s, %d timed steps "
                                           "after 1 warm-up (%.1f s/step)" % (Bc, len(ts), sum(ts) / len(ts))}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
