@@ -437,6 +437,8 @@ def split_input(x, n_split, n_bits=8):
     peak = torch.empty(1, device=x.device)
     ws = workspace(rows, x.device)
     check(lib().fqss_absmax(ptr(x), rows, T, ldx, ptr(peak), ptr(ws), ws.numel(), stream_ptr()))
+    from . import parallel          # data-parallel runs with global-batch parity: one peak over ALL shards
+    parallel.sync_splitter_peak_(peak)
     y = alloc_rows((B, n_split, T), x.device)
     check(lib().fqss_split(ptr(x), ldx, ptr(peak), ptr(y), ld_of(y), B, T, n_split, n_bits, stream_ptr()))
     return y

@@ -15,6 +15,54 @@ from . import _native as N
 from ._native import check, lib, ptr, stream_ptr, workspace
 
 
+# ---------------------------------------------------------------------------------------------
+# Batch-coupled quirks of the reference under data parallelism.  DEFAULT = the reference's own DDP
+# behaviour (every rank normalises / calibrates on its local shard).  With `set_global_batch_parity(True)` a sharded
+# run reproduces the single-process run on the global batch instead:
+#   (1) splitter: `x / max|x|` uses ONE scalar over the whole batch (process.py:23-24)  -> all-reduce(MAX) of 1 float
+#   (2) observers: EMA of the batch min / max (qat_quant.py:230-232); DDP never re-syncs the range parameters, so the
+#       reference's ranks silently diverge                                              -> all-reduce(MIN) of
+#       [min_range ; -max_range] after every calibration forward (the EMA is monotone in the batch statistic, so
+#       min over ranks of the updated value == the update with the global statistic, bit for bit)
+# (3) the loss `-10 log10(mean_b(...))` is not a mean of per-sample terms; the exact-global variant would all-reduce
+#     its two inner means -- NOT implemented: the path keeps the reference's per-rank loss.
+# ---------------------------------------------------------------------------------------------
+_GLOBAL_PARITY = False
+
+
+def set_global_batch_parity(on=True):
+    global _GLOBAL_PARITY
+    _GLOBAL_PARITY = bool(on)
+
+
+def global_batch_parity():
+    return _GLOBAL_PARITY and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def sync_splitter_peak_(peak, group=None):
+    """(1): in-place all-reduce(MAX) of the splitter's `max|x|` scalar when global-batch parity is on."""
+    if global_batch_parity():
+        dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=group)
+    return peak
+
+
+def sync_observer_ranges_(model, group=None):
+    """(2): make the activation-quantiser ranges of all ranks equal to what one process would have learned from the
+    global batch.  Call after every calibration forward (observer mode).  One collective over 2 x (#quantisers)
+    floats.  Returns the number of quantisers synchronised."""
+    from .qat.qat_quant import GradientActivationFakeQuantize as AQ
+    qs = [m for m in model.modules() if isinstance(m, AQ)]
+    if not qs or not global_batch_parity():
+        return 0
+    flat = torch.cat([q.min_range.data.reshape(-1) for q in qs] + [-q.max_range.data.reshape(-1) for q in qs])
+    dist.all_reduce(flat, op=dist.ReduceOp.MIN, group=group)
+    n = len(qs)
+    for i, q in enumerate(qs):
+        q.min_range.data.copy_(flat[i:i + 1].reshape(q.min_range.shape))
+        q.max_range.data.copy_((-flat[n + i:n + i + 1]).reshape(q.max_range.shape))
+    return n
+
+
 def shard_bounds(global_batch, rank, world):
     """Contiguous shard [lo, hi) of the global batch owned by `rank`."""
     if global_batch % world != 0:

@@ -87,3 +87,65 @@ def test_arena_allreduce_gloo_world2(tmp_path):
     ((net(x) - y) ** 2).mean().backward()
     full = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
     assert torch.allclose(got[:full.numel()], full, rtol=1e-5, atol=1e-6)
+
+
+def _parity_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fqss_b200 import parallel
+    from fqss_b200.qat.qat_quant import GradientActivationFakeQuantize as AQ
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(8, 1, 64, generator=g)                  # global batch; rank r owns rows [4r, 4r+4)
+    lo, hi = parallel.shard_bounds(8, rank, world)
+    xs = x[lo:hi]
+    net = torch.nn.Sequential(AQ(True), torch.nn.Identity(), AQ(True))
+    res = {}
+    for mode in (False, True):
+        parallel.set_global_batch_parity(mode)
+        for q in net:
+            if isinstance(q, AQ):
+                q.min_range.data.fill_(-0.5)
+                q.max_range.data.fill_(0.5)
+        peak = xs.abs().max().reshape(1).clone()
+        parallel.sync_splitter_peak_(peak)
+        for step in range(3):                               # three calibration passes: EMA of the batch statistics
+            for k, q in enumerate(m for m in net if isinstance(m, AQ)):
+                t = xs * (k + 1 + step)
+                q.min_range.data.mul_(0.9).add_(0.1 * t.min())      # qat_quant.py:230-231 on the local shard
+                q.max_range.data.mul_(0.9).add_(0.1 * t.max())
+            n = parallel.sync_observer_ranges_(net)
+        res[mode] = dict(peak=peak.clone(), n=n, mins=[q.min_range.data.clone() for q in net if isinstance(q, AQ)],
+                         maxs=[q.max_range.data.clone() for q in net if isinstance(q, AQ)])
+    parallel.set_global_batch_parity(False)
+    torch.save(res, os.path.join(out_dir, "parity%d.pt" % rank))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_global_batch_parity_sync_gloo_world2(tmp_path):
+    """with global-batch parity on, the splitter peak and the observer ranges of a
+    2-rank run equal those of one process on the global batch (bit for bit); off = the reference's per-rank values."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_parity_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(str(tmp_path), "parity%d.pt" % r)) for r in range(world)]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(8, 1, 64, generator=g)
+    # single-process reference on the global batch
+    mins = [torch.tensor([-0.5]), torch.tensor([-0.5])]
+    maxs = [torch.tensor([0.5]), torch.tensor([0.5])]
+    for step in range(3):
+        for k in range(2):
+            t = x * (k + 1 + step)
+            mins[k] = mins[k] * 0.9 + 0.1 * t.min()
+            maxs[k] = maxs[k] * 0.9 + 0.1 * t.max()
+    for r in range(world):
+        on, off = outs[r][True], outs[r][False]
+        assert on["n"] == 2 and off["n"] == 0
+        assert torch.equal(on["peak"], x.abs().max().reshape(1))
+        assert torch.equal(off["peak"], x[4 * r:4 * r + 4].abs().max().reshape(1))
+        for k in range(2):
+            assert torch.equal(on["mins"][k], mins[k]) and torch.equal(on["maxs"][k], maxs[k]), (r, k)
+    # without the sync the two ranks have diverged (what the reference's DDP run does)
+    assert not torch.equal(outs[0][False]["mins"][0], outs[1][False]["mins"][0])
