@@ -917,7 +917,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     FQSS_REQUIRE(!p->quant || (p->code1 && p->code3), -1, "tcn_block_bwd: forward did not save the activation codes (code1 / code3)");
     FQSS_REQUIRE(!p->split && p->skip_y && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
                  "tcn_block_bwd: block was run in inference mode (split operands / no saved pre-activations)");
-    FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->g_hid_b && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
+    FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
     FQSS_REQUIRE(!p->has_res || (g->g_x_out && g->g_xd), -1, "tcn_block_bwd: residual path needs g_x_out / g_xd");
     FQSS_REQUIRE(p->first_block || g->g_skip_in, -1, "tcn_block_bwd: g_skip_in missing");
     FQSS_REQUIRE(g->dW1q && g->db1 && g->dW2q && g->db2 && g->dwdw && g->dbdw && g->g_gn1_w && g->g_gn1_b && g->g_gn2_w && g->g_gn2_b &&
@@ -986,7 +986,8 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
 #undef FQSS_F_MODE
 #undef FQSS_F_LAUNCH
     } else {
-    {
+        FQSS_REQUIRE(g->g_hid_b, -1, "tcn_block_bwd: the two-kernel gLN2 / depthwise path needs the g_hid_b scratch");
+        {
             FQSS_PROF("tcn_gln2_bwd<2>", s);
             if (p->quant) {
                 const int nqv = tune_nq("FQSS_NQ_P2", 4);

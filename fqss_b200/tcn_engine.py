@@ -9,6 +9,7 @@ state (observers off); the per-layer wrappers in qat_layers.py remain the genera
 calibration, foreign compositions) and the definition of the drop-in API.
 """
 import ctypes as C
+import os
 
 import torch
 from torch.autograd import Function
@@ -421,9 +422,11 @@ class FusedTCNFunction(Function):
         g_x = torch.zeros((B, Cio, ld), device=dev)
         if g_xo is not None and states[-1].has_res:
             g_x[:, :, :M].copy_(g_xo)
+        # g_hid_b (g_y3) exists only for the two-kernel A/B path; the fused gLN2+depthwise kernel keeps it in shared memory
+        two_kernel = os.environ.get("FQSS_SPLIT_P2D", "0") not in ("", "0")
         scratch = dict(dY2=torch.empty((B, 2 * Cio, ld), dtype=bf, device=dev), ga=torch.empty((B, Chid, ld), dtype=bf, device=dev),
-                       gb=torch.empty((B, Chid, ld), dtype=bf, device=dev), dY1=torch.empty((B, Chid, ld), dtype=bf, device=dev),
-                       gxd=torch.empty((B, Cio, ld), device=dev))
+                       gb=torch.empty((B, Chid, ld), dtype=bf, device=dev) if two_kernel else None,
+                       dY1=torch.empty((B, Chid, ld), dtype=bf, device=dev), gxd=torch.empty((B, Cio, ld), device=dev))
         ws = torch.empty(int(L.fqss_tcn_ws_bytes(B, Cio, Chid)), dtype=torch.uint8, device=dev)
         grads = [None] * ctx.nflat
         wq_items, keep = [], []
@@ -439,7 +442,7 @@ class FusedTCNFunction(Function):
                      sl1=torch.empty(1, device=dev), sl3=torch.empty(1, device=dev), gq=torch.zeros(16, device=dev))
             g = TcnBlockGrads()
             g.g_x_out, g.g_skip_out, g.g_x_in, g.g_skip_in = ptr(g_x), ptr(g_ss), ptr(g_x), ptr(g_ss)
-            g.dY2, g.g_hid_a, g.g_hid_b, g.dY1, g.g_xd = ptr(scratch["dY2"]), ptr(scratch["ga"]), ptr(scratch["gb"]), ptr(scratch["dY1"]), ptr(scratch["gxd"])
+            g.dY2, g.g_hid_a, g.g_hid_b, g.dY1, g.g_xd = ptr(scratch["dY2"]), ptr(scratch["ga"]), ptr(scratch["gb"]) or None, ptr(scratch["dY1"]), ptr(scratch["gxd"])
             g.dW1q, g.db1, g.dW2q, g.db2, g.dwdw, g.dbdw = ptr(G["dW1q"]), ptr(G["db1"]), ptr(G["dW2q"]), ptr(G["db2"]), ptr(G["dwdw"]), ptr(G["dbdw"])
             g.g_gn1_w, g.g_gn1_b, g.g_gn2_w, g.g_gn2_b = ptr(G["g1w"]), ptr(G["g1b"]), ptr(G["g2w"]), ptr(G["g2b"])
             g.g_slope1, g.g_slope3, g.g_q = ptr(G["sl1"]), ptr(G["sl3"]), ptr(G["gq"])

@@ -290,8 +290,10 @@ int fqss_tcn_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, in
 int fqss_tcn_block_fwd(const fqss_tcn_block* blk, void* stream);
 
 /* Backward of one block.  In: g_x_out, g_skip_out (fp32 [B][Cio][ld]).  Out: g_x_in, g_skip_in (may alias the
- * inputs).  Scratch (caller-owned, reusable across blocks): dY2 bf16 [B][2Cio][ld], g_hid_a/g_hid_b bf16
- * [B][Chid][ld], dY1 bf16 [B][Chid][ld], g_xd fp32 [B][Cio][ld], wpart fp32 (fqss_tcn_ws_bytes).  Parameter
+ * inputs).  Scratch (caller-owned, reusable across blocks): dY2 bf16 [B][2Cio][ld], g_hid_a bf16
+ * [B][Chid][ld], dY1 bf16 [B][Chid][ld], g_xd fp32 [B][Cio][ld], wpart fp32 (fqss_tcn_ws_bytes); g_hid_b (bf16
+ * [B][Chid][ld]) may be NULL: the gLN2 and depthwise backward stages run as ONE kernel that keeps g_y3 in shared
+ * memory (the two-kernel variant, FQSS_SPLIT_P2D=1 in the environment, is a development A/B path).  Parameter
  * gradients are WRITTEN (not accumulated): dW1q [Chid][Cio], db1, dW2q [2Cio][Chid], db2 (w.r.t. the
  * FAKE-QUANTISED weights: run fqss_fq_weight_bwd on them), dwdw [Chid][3] (same), dbdw, g_gn*, slopes,
  * and 2 floats {g_min,g_max} per activation quantiser in g_q (order: q1,q2,q3,q4,qres,qskip,qadd,qadds). */

@@ -7,6 +7,8 @@ Outputs (all small, fp32, np.savez_compressed):
                                autograd gradients on seeded + adversarial inputs (qat_quant.py:88-147)
   tests/golden/split.npz       P1: splitter / reconstructor (process.py:10-52)
   tests/golden/loss.npz        S1/S2: PairwiseWSDR matrices (wsdr.py:46-95) + common_step loss/grad
+  tests/golden/infer.npz       process.model_infer (process.py:154-194): whole-signal and chunked overlap-add inference
+                               of a deterministic toy separator
   tests/golden/model_small.npz M1-M3/L1/L2: a reduced ConvTasNetQ (64 filters, 2x3 blocks): state_dict
                                before/after 2 observer passes, input, per-layer taps, output, teacher
                                output, FQSS loss and every parameter gradient
@@ -187,9 +189,37 @@ def gen_model_small(out):
     print("wrote", out, "loss", float(loss), "arrays", len(d), "bytes", os.path.getsize(out))
 
 
+class _ToySeparator(torch.nn.Module):
+    """Deterministic stand-in for a separator (model_infer only needs `model(x) -> [B, S, T]`): non-linear, with a
+    per-call peak normalisation like the FQSS splitter, so that chunking / padding / batching mistakes show up."""
+    n_srcs = 2
+
+    def forward(self, x):                      # x: [1, C, T] -> [1, 2, T - 3] (shorter than the input, like the codec)
+        x = x[:, 0, :]
+        x = x / x.abs().max().clamp_min(1e-8)
+        a = torch.tanh(2.0 * x)[:, :-3]
+        b = (x * x.abs())[:, 3:] * 0.5
+        return torch.stack([a, b], dim=1)
+
+
+def gen_infer(out):
+    g = torch.Generator().manual_seed(5)
+    mix = torch.randn(1, 5000, generator=g) * 0.3
+    model = _ToySeparator()
+    full = RP.model_infer(model, mix[0:1], device="cpu")
+    ola = RP.model_infer(model, mix, segment=1600, overlap=0.25, device="cpu")
+    ola2 = RP.model_infer(model, mix, segment=999, overlap=0.5, device="cpu")
+    np.savez_compressed(out, mix=_np(mix), full=_np(full), ola=_np(ola), ola2=_np(ola2))
+    print("wrote", out, "bytes", os.path.getsize(out))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "infer":
+        gen_infer(os.path.join(HERE, "infer.npz"))
+        sys.exit(0)
     torch.set_num_threads(8)
     gen_q_ops(os.path.join(HERE, "q_ops.npz"))
     gen_split(os.path.join(HERE, "split.npz"))
     gen_loss(os.path.join(HERE, "loss.npz"))
     gen_model_small(os.path.join(HERE, "model_small.npz"))
+    gen_infer(os.path.join(HERE, "infer.npz"))

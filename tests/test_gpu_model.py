@@ -271,3 +271,30 @@ def test_cuda_graph_step_matches_eager(golden):
     moved = (arena_e.flat - init).norm().item()
     diff = (arena_e.flat - arena_g.flat).norm().item()
     assert moved > 0 and diff < 0.1 * moved, (diff, moved)
+
+
+def test_model_infer_on_device(golden):
+    """process.model_infer (process.py:154-194) with the quantised model on the GPU: chunked overlap-add on the
+    device equals the same chunks composed by hand on the host."""
+    import torch.nn.functional as F
+    from fqss_b200.process import model_infer
+    g, model, fmodel, calib = _prep_small(golden)
+    gen = torch.Generator().manual_seed(9)
+    mix = (torch.randn(2, 5000, generator=gen) * 0.05).sum(0, keepdim=True)       # [1, 5000]
+    seg, ov = 2400, 0.25
+    out = model_infer(model, mix, segment=seg, overlap=ov, device=DEV)
+    assert out.shape == (2, 5000) and torch.isfinite(out).all()
+    full = model_infer(model, mix[:, :2400], device=DEV)
+    assert full.shape == (2, 2400)
+    stride = int((1 - ov) * seg)
+    w = torch.cat([torch.arange(1, seg // 2 + 1), torch.arange(seg - seg // 2, 0, -1)]).float()
+    w = w / w.max()
+    acc, sw = torch.zeros(2, 5000), torch.zeros(5000)
+    for start in range(0, 5000, stride):
+        stop = min(start + seg, 5000)
+        n = stop - start
+        chunk = F.pad(mix[:, start:stop], (0, seg - n))
+        co = model_infer(model, chunk, device=DEV)[..., :n]
+        acc[:, start:stop] += w[:n] * co
+        sw[start:stop] += w[:n]
+    assert rel(out, acc / sw) < 1e-6
