@@ -92,3 +92,39 @@ def test_full_model_parameter_count():
     quantize_model(m, dict(RECIPE_QUANT))
     assert sum(p.numel() for p in m.parameters()) == 5133123      # (SURVEY.md quotes 5 115 713; the reference itself gives 5 133 123)
     assert len(m.state_dict()) == 948
+
+
+def test_ctypes_binding_matches_header(native, tmp_path):
+    """The Python binding is hand-written: guard it against drift from include/fqss.h.  (1) every prototype's
+    parameter count equals the ctypes signature's; (2) every struct that crosses the ABI has the same size and field
+    offsets in C (gcc on the header, which must stay plain C) and in ctypes."""
+    import ctypes as C
+    import subprocess
+    from fqss_b200 import tcn_engine as E
+    hdr_path = os.path.join(ROOT, "include", "fqss.h")
+    hdr = open(hdr_path).read()
+    nocomment = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = dict((m.group(1), m.group(2)) for m in re.finditer(r"\b(fqss_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", nocomment))
+    for name, (res, args) in native._SIGS.items():
+        assert name in protos, name
+        plist = [a for a in protos[name].split(",") if a.strip() and a.strip() != "void"]
+        assert len(plist) == len(args), "%s: header has %d parameters, binding %d" % (name, len(plist), len(args))
+    structs = {"fqss_tcn_block": E.TcnBlock, "fqss_tcn_block_grads": E.TcnBlockGrads, "fqss_qrange": E.QRange,
+               "fqss_prep_item": native.PrepItem, "fqss_gather_item": native.GatherItem, "fqss_pw_desc": native.PwDesc,
+               "fqss_pw_grads": native.PwGrads, "fqss_wq_item": native.WqItem}
+    probes = {"fqss_tcn_block": ["ld", "Wc1", "q_in", "x_op", "rc1", "code3"], "fqss_tcn_block_grads": ["dY2", "dW1q", "g_q", "ws_bytes"],
+              "fqss_prep_item": ["Wc", "N", "split"], "fqss_gather_item": ["offset", "numel"], "fqss_pw_desc": ["rows", "x2", "eps", "rmax"],
+              "fqss_pw_grads": ["gx2", "g_beta"], "fqss_wq_item": ["rmin", "n_bits"], "fqss_qrange": ["rmax"]}
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "fqss.h"', 'int main(void) {']
+    for s in structs:
+        src.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (s, s))
+        for f in probes[s]:
+            src.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (s, f, s, f))
+    src += ['return 0;', '}']
+    cfile, exe = os.path.join(str(tmp_path), "abi.c"), os.path.join(str(tmp_path), "abi")
+    open(cfile, "w").write("\n".join(src))
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), cfile, "-o", exe])
+    for line in subprocess.check_output([exe], text=True).splitlines():
+        s, f, v = line.split()
+        want = C.sizeof(structs[s]) if f == "sizeof" else getattr(structs[s], f).offset
+        assert int(v) == want, "%s.%s: C %s vs ctypes %d" % (s, f, v, want)
