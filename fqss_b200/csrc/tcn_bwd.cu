@@ -954,7 +954,11 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // P1, R, P2
     {
         FQSS_PROF("tcn_gln2_bwd<1>", s);
-        if (p->quant) tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        static const int p1_th = tune_nq("FQSS_P1_TH", 128);
+        if (p->quant) {
+            if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
+            else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        }
         else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
     }
     { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
@@ -968,10 +972,15 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
         const int mode = dw_mode(p->dil);
         static const int nqf = tune_nq("FQSS_NQ_F", 4);
         FQSS_PROF("tcn_gln2_dw_bwd", s);
+        static const int f_th = tune_nq("FQSS_F_TH", 128);
 #define FQSS_F_LAUNCH(Q, D, NQv)                                                                                         \
     do {                                                                                                                 \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(tcn_gln2_dw_bwd_kernel<Q, D, 128, NQv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-        tcn_gln2_dw_bwd_kernel<Q, D, 128, NQv><<<rows_h, 128, smem, s>>>(*p, *g, acc);                                    \
+        if (smem > 48 * 1024) {                                                                                          \
+            cudaFuncSetAttribute(tcn_gln2_dw_bwd_kernel<Q, D, 128, NQv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            cudaFuncSetAttribute(tcn_gln2_dw_bwd_kernel<Q, D, 64, NQv>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);  \
+        }                                                                                                                \
+        if (f_th == 64) tcn_gln2_dw_bwd_kernel<Q, D, 64, NQv><<<rows_h, 64, smem, s>>>(*p, *g, acc);                      \
+        else tcn_gln2_dw_bwd_kernel<Q, D, 128, NQv><<<rows_h, 128, smem, s>>>(*p, *g, acc);                               \
     } while (0)
 #define FQSS_F_MODE(Q, NQv)                                                                          \
     do {                                                                                             \
