@@ -255,3 +255,29 @@ extern "C" int fqss_kd_loss(const float* est, int64_t lde, const float* fest, in
     }
     return check_launch("kd_loss");
 }
+
+// The two HBM passes and the gradient pass as separate entry points: the sufficient statistics (means + 18 centred
+// inner products per sample, fp64) and "apply per-sample coefficients" are all a pairwise SI-SDR matrix and its
+// gradient need (PairwiseWSDR as a standalone module, wsdr.py:46-95); the O(B) algebra in between is the caller's.
+extern "C" int fqss_loss_stats(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt, int B,
+                               int T, double* stats, void* stream) {
+    FQSS_REQUIRE(est && fest && tgt && stats && B > 0 && T > 0, -1, "loss_stats: bad argument");
+    FQSS_REQUIRE(lde >= T && ldf >= T && ldt >= T, -1, "loss_stats: bad pitch");
+    cudaStream_t s = (cudaStream_t)stream;
+    FQSS_PROFN("loss_stats", s, 2);
+    cudaMemsetAsync(stats, 0, (size_t)B * LS_STRIDE * sizeof(double), s);
+    dim3 grid((T + LS_CHUNK - 1) / LS_CHUNK, B);
+    loss_mean_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, stats);
+    loss_dot_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, stats);
+    return check_launch("loss_stats");
+}
+
+extern "C" int fqss_loss_grad_apply(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt,
+                                    int B, int T, const float* coef, float* gest, int64_t ldg, void* stream) {
+    FQSS_REQUIRE(est && fest && tgt && coef && gest && B > 0 && T > 0, -1, "loss_grad_apply: bad argument");
+    FQSS_REQUIRE(lde >= T && ldf >= T && ldt >= T && ldg >= T, -1, "loss_grad_apply: bad pitch");
+    FQSS_PROF("loss_grad_apply", stream);
+    dim3 g2((T + LS_THREADS - 1) / LS_THREADS, B);
+    loss_grad_kernel<<<g2, LS_THREADS, 0, (cudaStream_t)stream>>>(est, lde, fest, ldf, tgt, ldt, T, coef, gest, ldg);
+    return check_launch("loss_grad_apply");
+}

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 12
+#define FQSS_ABI_VERSION 13
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -330,6 +330,16 @@ int fqss_combine(const float* parts, int64_t part_stride, int64_t ld, float* y, 
 int fqss_kd_loss(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt,
                  int B, int T, float kd_lambda, float* out, float* gest, int64_t ldg,
                  void* ws, size_t ws_bytes, void* stream);
+
+/* The passes of fqss_kd_loss as separate entry points (PairwiseWSDR as a standalone module, wsdr.py:46-95):
+ *   fqss_loss_stats: per sample 24 doubles = SUMS of e0 e1 f0 f1 t0 t1 (divide by T for the means), then the centred
+ *     inner products ee0 ee1 ff0 ff1 tt0 tt1 | et00 et01 et10 et11 | ft00 .. ft11 | ef00 .. ef11  (xy_ij = <x_i, y_j>)
+ *   fqss_loss_grad_apply: gest[b,i,:] = c_i e_i + sum_j a_ij t_j + b_ij f_j on the CENTRED signals, coef per sample =
+ *     16 floats {a00 a01 a10 a11 | b00 b01 b10 b11 | c0 c1 | means e0 e1 f0 f1 t0 t1} */
+int fqss_loss_stats(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt, int B, int T,
+                    double* stats, void* stream);
+int fqss_loss_grad_apply(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt, int B,
+                         int T, const float* coef, float* gest, int64_t ldg, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * D1  flat gradient arena helpers for the data-parallel exchange (asteroid_librimix_trainer.py:125-135)

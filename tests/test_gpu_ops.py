@@ -323,3 +323,34 @@ def test_param_arena_gather_clip_adam_vs_torch():
         opt.step()
         worst = max(rel(q, p) for p, q in zip(ref, ours))
         assert worst < 1e-5, (step, worst)
+
+
+def test_pairwise_wsdr_module_vs_reference_and_oracle(golden):
+    """S2/S3 as standalone modules (wsdr.py:46-95 and asteroid's PITLossWrapper): the pairwise matrices of the
+    unmodified reference (tests/golden/loss.npz), gradients against the oracle's autograd, and the PIT search."""
+    from fqss_b200.wsdr import PITLossWrapper, PairwiseWSDR, pairwise_neg_sisdr, pairwise_wsisdr
+    g = golden("loss.npz")
+    est, tgt, w = T(g["est"]), T(g["tgt"]), T(g["w"])
+    pw_lin = PairwiseWSDR("sisdr", take_log=False)(est.to(DEV), tgt.to(DEV), w.to(DEV))
+    pw_log = PairwiseWSDR("sisdr", take_log=True)(est.to(DEV), tgt.to(DEV))
+    assert rel(pw_lin, T(g["pw_lin"])) < 1e-5 and rel(pw_log, T(g["pw_log"])) < 1e-5
+    # gradient of a generic scalar of the matrix, against autograd through the oracle's restatement
+    gen = torch.Generator().manual_seed(4)
+    coeff = torch.randn(3, 2, 2, generator=gen)
+    e_o = est.clone().requires_grad_(True)
+    (O.pairwise_sisdr_ratio(e_o, tgt, w) * coeff).sum().backward()
+    e_c = est.to(DEV).requires_grad_(True)
+    (-pairwise_wsisdr(e_c, tgt.to(DEV), w.to(DEV)) * coeff.to(DEV)).sum().backward()
+    assert rel(e_c.grad, e_o.grad) < 1e-4, rel(e_c.grad, e_o.grad)
+    # the recipe's validation loss: PITLossWrapper(pairwise_neg_sisdr, pit_from="pw_mtx")
+    pit = PITLossWrapper(pairwise_neg_sisdr, pit_from="pw_mtx")
+    e_c2 = est.to(DEV).requires_grad_(True)
+    loss, reordered = pit(e_c2, tgt.to(DEV), return_est=True)
+    loss.backward()
+    e_o2 = est.clone().requires_grad_(True)
+    lo, per_b = O.neg_sisdr_db_pit(e_o2, tgt)
+    lo.backward()
+    assert abs(loss.item() - lo.item()) < 2e-4 and rel(e_c2.grad, e_o2.grad) < 1e-4
+    assert torch.equal(reordered.cpu(), est[:, [1, 0]])            # the golden estimates are the targets, permuted
+    with pytest.raises(NotImplementedError):
+        PairwiseWSDR("snr")
