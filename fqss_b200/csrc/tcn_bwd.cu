@@ -888,6 +888,18 @@ __global__ void fill_consts_kernel(float* ones, float* zeros, int n) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// side stream + fork / join events of the backward pass (created once per process; one process drives one GPU)
+static cudaStream_t side_stream() {
+    static cudaStream_t st = nullptr;
+    if (!st) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    return st;
+}
+static cudaEvent_t side_event(int i) {
+    static cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    return ev[i];
+}
+
 // development knob: loads-in-flight batch of a row kernel, from the environment (read once per name)
 static int tune_nq(const char* name, int dflt) {
     const char* e = getenv(name);
@@ -947,9 +959,20 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
         rc = tcg::run(tcg::EPI_BF16, g->dY2, p->Wc2T, a, s);
         if (rc) return rc;
     }
-    // W: dW2q
+    // W: dW2q.  The split-K wgrad (one 200 KB CTA per SM, TMA + tcgen05, SM pipes nearly idle, ~47 % of HBM) and the
+    // gLN2 row-sum kernel that follows (ALU-bound, ~40 % of HBM) do not depend on each other and fit on an SM together:
+    // fork the wgrad to a side stream (inputs dY2 / db2 sums are complete after T), join before the second wgrad, which
+    // reuses the partial-tile buffer.  Works the same under stream capture (fork / join through events).
+    static const int overlap = tune_nq("FQSS_WGRAD_OVERLAP", 1);
+    cudaStream_t sw = s;
+    if (overlap) {
+        sw = side_stream();
+        cudaEventRecord(side_event(0), s);
+        cudaStreamWaitEvent(sw, side_event(0), 0);
+    }
     rc = tcw::run(g->dY2, p->a4_op, p->B, p->M, p->ld, n2, p->Chid, part, part_cap, p->quant ? p->q4.rmin : nullptr,
-                  p->quant ? p->q4.rmax : nullptr, p->dws2, acc + L.db2, g->dW2q, s);
+                  p->quant ? p->q4.rmax : nullptr, p->dws2, acc + L.db2, g->dW2q, sw);
+    if (overlap) cudaEventRecord(side_event(1), sw);      // recorded even on failure: the main stream must not wait forever
     if (rc) return rc;
     // P1, R, P2
     {
@@ -1050,6 +1073,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
         if (rc) return rc;
     }
     // W: dW1q
+    if (overlap) cudaStreamWaitEvent(s, side_event(1), 0);      // join: dW2q is final, the partial-tile buffer is free again
     rc = tcw::run(g->dY1, p->x_op, p->B, p->M, p->ld, p->Chid, p->Cio, part, part_cap, p->quant ? p->q_in.rmin : nullptr,
                   p->quant ? p->q_in.rmax : nullptr, p->dws1, acc + L.db1, g->dW1q, s);
     if (rc) return rc;
