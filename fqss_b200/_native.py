@@ -91,6 +91,7 @@ _SIGS = {
     "fqss_tcn_encode": (i32, [vp, i64, vp, i64, i64, i32, vp, vp, vp]),
     "fqss_tcn_block_fwd": (i32, [vp, vp]),
     "fqss_tcn_block_bwd": (i32, [vp, vp, vp]),
+    "fqss_set_wgrad_overlap": (i32, [i32]),
     "fqss_tcn_ws_bytes": (sz, [i32, i32, i32]),
     "fqss_absmax": (i32, [vp, i64, i64, i64, vp, vp, sz, vp]),
     "fqss_split": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),
@@ -128,7 +129,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 13:
+                if L.fqss_abi_version() != 14:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

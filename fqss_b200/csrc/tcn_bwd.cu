@@ -888,6 +888,8 @@ __global__ void fill_consts_kernel(float* ones, float* zeros, int n) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int g_wgrad_overlap = -1;      // -1: take FQSS_WGRAD_OVERLAP from the environment (default on) at first use
+
 // side stream + fork / join events of the backward pass (created once per process; one process drives one GPU)
 static cudaStream_t side_stream() {
     static cudaStream_t st = nullptr;
@@ -911,6 +913,12 @@ static int tune_nq(const char* name, int dflt) {
 using namespace fqss;
 
 extern "C" {
+
+int fqss_set_wgrad_overlap(int on) {
+    const int prev = g_wgrad_overlap;
+    g_wgrad_overlap = on;
+    return prev;
+}
 
 size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid) {
     AccLayout L(B, Cio, Chid);
@@ -963,7 +971,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // gLN2 row-sum kernel that follows (ALU-bound, ~40 % of HBM) do not depend on each other and fit on an SM together:
     // fork the wgrad to a side stream (inputs dY2 / db2 sums are complete after T), join before the second wgrad, which
     // reuses the partial-tile buffer.  Works the same under stream capture (fork / join through events).
-    static const int overlap = tune_nq("FQSS_WGRAD_OVERLAP", 1);
+    const int overlap = g_wgrad_overlap < 0 ? (g_wgrad_overlap = tune_nq("FQSS_WGRAD_OVERLAP", 1)) : g_wgrad_overlap;
     cudaStream_t sw = s;
     if (overlap) {
         sw = side_stream();

@@ -41,11 +41,15 @@ def profile(fn, repeats=1):
     L = _prof_api()
     torch.cuda.synchronize()
     L.fqss_prof_reset()
+    prev = L.fqss_set_wgrad_overlap(0)      # per-kernel timing wants every kernel alone on the stream
     L.fqss_prof_enable(1)
-    for _ in range(repeats):
-        fn()
-    torch.cuda.synchronize()
-    L.fqss_prof_enable(0)
+    try:
+        for _ in range(repeats):
+            fn()
+        torch.cuda.synchronize()
+    finally:
+        L.fqss_prof_enable(0)
+        L.fqss_set_wgrad_overlap(prev)
     out = {}
     name = C.create_string_buffer(64)
     for i in range(L.fqss_prof_nslots()):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 13
+#define FQSS_ABI_VERSION 14
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -307,6 +307,10 @@ typedef struct fqss_tcn_block_grads {
 } fqss_tcn_block_grads;
 
 size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid);
+/* 1 (default): the first weight-gradient GEMM of fqss_tcn_block_bwd runs on a library-owned side stream next to the
+ * gLN2 row-sum kernel (fork / join through events on the caller's stream; capturable); 0: everything on the caller's
+ * stream (what per-kernel timing wants); -1: back to the environment default.  Returns the previous setting. */
+int fqss_set_wgrad_overlap(int on);
 int fqss_tcn_block_bwd(const fqss_tcn_block* blk, const fqss_tcn_block_grads* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
