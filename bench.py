@@ -233,6 +233,20 @@ def run_ours(args):
     def run_step(mix, src):
         return graphed(mix, src) if graphed is not None else step(mix, src)
 
+    copy_stream = torch.cuda.Stream()
+    staging = [tuple(torch.empty_like(t) for t in dev_batches[0]) for _ in range(2)]
+    staged = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def h2d(i):
+        """Enqueue the host->device copy of step i's batch on the copy stream (after the staging slot was consumed)."""
+        m, s = host[i % n_host]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            staging[i % 2][0].copy_(m, non_blocking=True)
+            staging[i % 2][1].copy_(s, non_blocking=True)
+            staged[i % 2].record(copy_stream)
+
     def timed(n, from_host):
         if world > 1:
             dist.barrier()
@@ -240,12 +254,20 @@ def run_ours(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.time()
         e0.record()
+        if from_host and graphed is not None:
+            # prefetching loader: the H2D copy of step i+1 (pinned host -> staging buffer, copy stream) runs under the
+            # compute of step i; each step then moves its staged batch into the graph's static inputs (12 MB device copy)
+            h2d(0)
         for i in range(n):
-            if from_host and graphed is not None:      # pinned host -> the graph's static input buffers
-                m, s = host[i % n_host]
+            if from_host and graphed is not None:
+                cur = torch.cuda.current_stream()
+                cur.wait_event(staged[i % 2])                       # this step's inputs have arrived
                 mix, src = graphed.static_in
-                mix.copy_(m, non_blocking=True)
-                src.copy_(s, non_blocking=True)
+                mix.copy_(staging[i % 2][0], non_blocking=True)
+                src.copy_(staging[i % 2][1], non_blocking=True)
+                consumed[i % 2].record(cur)
+                if i + 1 < n:
+                    h2d(i + 1)
             elif from_host:
                 m, s = host[i % n_host]
                 mix, src = m.to(dev, non_blocking=True), s.to(dev, non_blocking=True)
