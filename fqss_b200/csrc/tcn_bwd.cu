@@ -881,11 +881,6 @@ __global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_b
     if (i < n2) g.db2[i] = (float)acc[L.db2 + i];
 }
 
-__global__ void fill_consts_kernel(float* ones, float* zeros, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { ones[i] = 1.f; zeros[i] = 0.f; }
-}
-
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 static int g_wgrad_overlap = -1;      // -1: take FQSS_WGRAD_OVERLAP from the environment (default on) at first use
@@ -948,8 +943,6 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     const AccLayout L(p->B, p->Cio, p->Chid);
     const size_t acc_bytes = align_up((size_t)L.total * sizeof(double), 256);
     double* acc = (double*)g->ws;
-    float* ones = (float*)((char*)g->ws + acc_bytes);
-    float* zeros = ones + 1024;
     float* part = (float*)((char*)g->ws + acc_bytes + align_up((size_t)2 * 1024 * sizeof(float), 256));
     const size_t part_cap = g->ws_bytes - ((char*)part - (char*)g->ws);
     const int n2 = p->has_res ? 2 * p->Cio : p->Cio;
