@@ -250,8 +250,7 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
                     if (p.quant) {
                         // gLN statistics of a1 = delta1 * code + min1 from INTEGER code sums (exact adds; expanded once per
-                        // tile): prelu, (z - min) * inv, one saturating conversion, IADD + IMAD per element
-#pragma unroll
+                        // tile): prelu, (z - min) / delta, one saturating conversion, IADD + IMAD per element
                         uint8_t* oc = p.code1 ? p.code1 + ((int64_t)b * p.N + o0) * ld + m : nullptr;
                         if (oc) {
                             // the EXACT code of FQ1 (same arithmetic as every later consumer), stored for the depthwise
