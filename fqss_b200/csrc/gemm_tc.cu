@@ -248,7 +248,18 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < CW; ++j) ob[j * ld] = __float2bfloat16_rn(fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]));
                 } else if (EPI == EPI_EXPAND) {
                     float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
-                    if (p.quant) {
+                    if (p.quant && !p.out_f32) {
+                        // inference: y1 is only needed by backward -- emit the FQ1 codes and the statistics, nothing else
+                        uint8_t* oc = p.code1 + ((int64_t)b * p.N + o0) * ld + m;
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            const unsigned c = code_u8(actqf_t(q1, prelu_f(y, slope)));
+                            oc[j * ld] = (uint8_t)c;
+                            st_c += c;
+                            st_cc += c * c;
+                        }
+                    } else if (p.quant) {
                         // gLN statistics of a1 = delta1 * code + min1 from INTEGER code sums (exact adds; expanded once per
                         // tile): prelu, (z - min) / delta, one saturating conversion, IADD + IMAD per element
                         uint8_t* oc = p.code1 ? p.code1 + ((int64_t)b * p.N + o0) * ld + m : nullptr;

@@ -930,7 +930,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     int rc = tcn_validate_block(p, "tcn_block_bwd");
     if (rc) return rc;
     FQSS_REQUIRE(!p->quant || (p->code1 && p->code3), -1, "tcn_block_bwd: forward did not save the activation codes (code1 / code3)");
-    FQSS_REQUIRE(!p->split && p->skip_y && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
+    FQSS_REQUIRE(!p->split && p->y1 && p->y3 && p->skip_y && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
                  "tcn_block_bwd: block was run in inference mode (split operands / no saved pre-activations)");
     FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
     FQSS_REQUIRE(!p->has_res || (g->g_x_out && g->g_xd), -1, "tcn_block_bwd: residual path needs g_x_out / g_xd");

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
             const float4 hv = bf16x4_to_float4(pk);
             *reinterpret_cast<uint2*>(a3_hi + 4 * v) = pk;
             *reinterpret_cast<uint2*>(a3_lo + 4 * v) = float4_to_bf16x4(z01.x - hv.x, z01.y - hv.y, z23.x - hv.z, z23.y - hv.w);
-        } else {
+        } else if (p.y3) {               // NULL in quantised inference: only backward reads y3 (the codes carry on)
             stg4(y3 + 4 * v, make_float4(o01.x, o01.y, o23.x, o23.y));
         }
         if (QUANT) {
@@ -467,7 +467,7 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
                  "%s: row too long for shared-memory staging (M=%d, dil=%d)", who, p->M, p->dil);
     FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
-    FQSS_REQUIRE(p->x_op && p->x_in && p->y1 && (p->y3 || p->split == 2) && p->stats1 && p->stats3 && p->a4_op && p->skip_out && p->rc1 && p->rc3, -1,
+    FQSS_REQUIRE(p->x_op && p->x_in && (p->y1 || p->quant) && (p->y3 || p->split == 2 || p->quant) && p->stats1 && p->stats3 && p->a4_op && p->skip_out && p->rc1 && p->rc3, -1,
                  "%s: missing activation buffers", who);
     FQSS_REQUIRE(!p->split || !p->quant, -1, "%s: split operands are a float-model (quant == 0) feature", who);
     FQSS_REQUIRE(p->split >= 0 && p->split <= 2, -1, "%s: split must be 0, 1 or 2", who);

@@ -491,6 +491,62 @@ class FusedTCNFunction(Function):
         return (g_x[:, :, :M], g_skip_in, None) + tuple(grads)
 
 
+def _fused_tcn_infer(x, skip_in, meta, flat):
+    """Forward-only run of the quantised stack (no_grad / nothing requires grad): the stores only backward needs (y1, y3,
+    res_y, skip_y) are skipped and ONE set of hidden-width buffers serves all blocks; block inputs / outputs ping-pong.
+    Same kernels, same codes, same result as the training forward."""
+    L = _libx()
+    quant, dils, q_in, start, total = meta
+    nb, ns = len(dils), len(_BLOCK_SLOTS)
+    dev = x.device
+    B, Cio, M = x.shape
+    ld = (M + 7) // 8 * 8
+    x = _as_pitched(x.detach(), ld)
+    s = stream_ptr()
+    bf = torch.bfloat16
+    x_op0 = torch.empty((B, Cio, ld), dtype=bf, device=dev)
+    check(L.fqss_tcn_encode(ptr(x), ld, ptr(x_op0), ld, B * Cio, M, ptr(q_in[0]), ptr(q_in[1]), s))
+    tensors, preps, prep_items, wq_items = [], [], [], []
+    cur_q = q_in
+    for i in range(nb):
+        t = dict(zip(_BLOCK_SLOTS, flat[i * ns:(i + 1) * ns]))
+        tensors.append(t)
+        preps.append(_prep_items(t, True, (start + i) < total - 1, cur_q, dev, prep_items, wq_items))
+        cur_q = (t["qaddmin"], t["qaddmax"])
+    _run_batches(prep_items, wq_items)
+    Chid = tensors[0]["W1"].shape[0]
+    hid = dict(stats1=torch.empty(2 * B + 1, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B + 1, dtype=torch.float64, device=dev),
+               a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), rc1=torch.empty(12 + 2 * B, device=dev),
+               rc3=torch.empty(12 + 2 * B, device=dev), code1=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev),
+               code3=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev))
+    xs = [torch.empty((B, Cio, ld), device=dev) for _ in range(2)]
+    xops = [torch.empty((B, Cio, ld), dtype=bf, device=dev) for _ in range(2)]
+    skips = [torch.empty((B, Cio, ld), device=dev) for _ in range(2)]
+    cur_x, cur_op = x, x_op0
+    cur_skip = _as_pitched(skip_in.detach(), ld) if skip_in is not None else None
+    cur_q = q_in
+    for i in range(nb):
+        t, P = tensors[i], preps[i]
+        first, has_res = (start + i) == 0, (start + i) < total - 1
+        blk = TcnBlock()
+        _fill_block(blk, t, P, True, first, has_res, dils[i], B, M, ld, cur_q)
+        blk.x_op, blk.x_in, blk.skip_in = ptr(cur_op), ptr(cur_x), ptr(cur_skip) or None
+        for k in ("stats1", "stats3", "a4_op", "rc1", "rc3", "code1", "code3"):
+            setattr(blk, k, ptr(hid[k]))
+        blk.y1 = blk.y3 = blk.res_y = blk.skip_y = None
+        blk.skip_out = ptr(skips[i & 1])
+        if has_res:
+            blk.x_out, blk.x_out_op = ptr(xs[i & 1]), ptr(xops[i & 1])
+        check(L.fqss_tcn_block_fwd(C.byref(blk), s))
+        if has_res:
+            cur_x, cur_op = xs[i & 1], xops[i & 1]
+        cur_skip = skips[i & 1]
+        cur_q = (t["qaddmin"], t["qaddmax"])
+    has_last_res = (start + nb - 1) < total - 1
+    x_last = cur_x[:, :, :M] if has_last_res else torch.zeros((B, Cio, M), device=dev)
+    return x_last, cur_skip[:, :, :M]
+
+
 def fused_tcn(x, blocks, adds, quant, q_in, start=0, total=None, skip_in=None):
     """Run blocks [start, start+len(blocks)) of a stack of `total` blocks.  blocks: ConvBlock modules; adds: the
     AddQ that merges each block's skip into the running sum (entry i belongs to blocks[i]; None for block 0).
@@ -501,7 +557,14 @@ def fused_tcn(x, blocks, adds, quant, q_in, start=0, total=None, skip_in=None):
         t, dil = block_tensors(blk, adds[i] if adds is not None else None, quant)
         dils.append(dil)
         flat.extend(t[k] for k in _BLOCK_SLOTS)
-    return FusedTCNFunction.apply(x, skip_in, (quant, tuple(dils), q_in, start, total), *flat)
+    meta = (quant, tuple(dils), q_in, start, total)
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in [x, skip_in] + flat)
+    if quant and not needs_grad and INFERENCE_MODE:
+        return _fused_tcn_infer(x, skip_in, meta, flat)
+    return FusedTCNFunction.apply(x, skip_in, meta, *flat)
+
+
+INFERENCE_MODE = True       # False: forward-only calls also run the training forward (tests compare the two)
 
 
 def fused_eligible(masker, x):

@@ -241,6 +241,8 @@ typedef struct fqss_tcn_block {
     fqss_qrange q_in, q1, q2, q3, q4, qres, qskip, qadd, qadds;
     /* activations */
     const void* x_op; const float* x_in; const float* skip_in;
+    /* y1 / y3 (and res_y / skip_y) are the pre-activations backward re-reads; in quantised INFERENCE they may be NULL:
+     * forward then skips those stores (the 8-bit codes carry the data on) and backward refuses to run */
     float* y1; double* stats1; float* y3; double* stats3; void* a4_op;
     float* res_y; float* skip_y; float* x_out; void* x_out_op; float* skip_out;
     /* row constants written by forward right after the statistics are complete and re-read by backward:

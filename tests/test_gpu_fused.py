@@ -365,3 +365,25 @@ def test_fused_quant_stack_odd_shapes_vs_per_layer():
     n1 = sum(out[True][1][k].double().pow(2).sum().item() for k in out[True][1]) ** 0.5
     n2 = sum(out[False][1][k].double().pow(2).sum().item() for k in out[False][1]) ** 0.5
     assert num / (n1 * n2) > 0.9 and abs(n1 / n2 - 1) < 0.25, (num / (n1 * n2), n1 / n2)
+
+
+def test_fused_inference_mode_is_bit_identical():
+    """Forward-only calls (no_grad: validation, process.model_infer) run the fused stack without the stores that only
+    backward needs and with one set of hidden buffers for all blocks: the output must equal the training forward's
+    bit for bit (same kernels, same codes)."""
+    from fqss_b200 import tcn_engine as E
+    model, fmodel, cfg, P, fP, st, mix, src = _medium_pair()
+    mixd = mix.to(DEV)
+    out_train = model(mixd).detach().clone()                  # grad enabled: training forward (saves everything)
+    with torch.no_grad():
+        out_eval = model(mixd).clone()
+        E.INFERENCE_MODE = False
+        try:
+            out_eval_full = model(mixd).clone()
+        finally:
+            E.INFERENCE_MODE = True
+    assert torch.equal(out_eval, out_train) and torch.equal(out_eval_full, out_train)
+    # and backward still works after an inference call in between
+    loss = model(mixd).square().mean()
+    loss.backward()
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
