@@ -1,19 +1,21 @@
-// tcn_bwd.cu -- backward of the fused TCN ConvBlock.  Every quantised activation is RECOMPUTED from
-// the saved pre-activations (y1, y3, res_y, skip_y) with the same device functions forward used, so
-// the straight-through masks match the forward codes exactly.  Stages (one launch each):
+// tcn_bwd.cu -- backward of the fused TCN ConvBlock.  Every quantised activation is re-derived from what forward
+// saved (8-bit codes code1 / code3 where the code is enough, the pre-activations y1, y3, res_y, skip_y where the
+// continuous value matters) with the same device functions forward used, so the straight-through masks match the
+// forward codes exactly.  Stages (one launch each):
 //
-//   T   tail          g_x_out, g_skip_out -> dY2 (bf16, res|skip rows, pre-scaled by delta_w), g_xd, g_skip_in
-//   G   dgrad GEMM    dY2 x Wc2T -> g_a4 (bf16)                                    [tcgen05]
-//   W   wgrad GEMM    dY2 x a4_op -> dW2q                                          [tcgen05, split-K]
-//   P1  gLN2 sums     g_a4, y3 -> per-row {sum g_n3, sum g_n3*xhat3}, range sums of FQ4
-//   R   reduce        per-sample S1,S2 and per-channel dgamma,dbeta
-//   P2  gLN2/FQ3/PReLU backward  g_a4, y3 -> g_y3 (bf16)
-//   D   depthwise     g_y3, y1 -> g_n1 (bf16), dW_dw, db_dw, per-row gLN1 sums, range sums of FQ2   (row in smem)
-//   R   reduce
-//   Q   gLN1/FQ1/PReLU backward  g_n1, y1 -> dY1 (bf16, pre-scaled), db1
-//   G   dgrad GEMM    dY1 x Wc1T (+ g_xd) -> g_x_in (fp32)                          [tcgen05]
-//   W   wgrad GEMM    dY1 x x_op -> dW1q                                           [tcgen05, split-K]
-//   F   finalise      fp64 accumulators -> fp32 parameter gradients
+//   T    tail          g_x_out, g_skip_out -> dY2 (bf16, res|skip rows, pre-scaled by delta_w), g_xd, g_skip_in
+//   G    dgrad GEMM    dY2 x Wc2T -> g_a4 (bf16)                                    [tcgen05]
+//   W    wgrad GEMM    dY2 x a4_op -> dW2q            [tcgen05, split-K; side stream, next to P1]
+//   P1   gLN2 sums     g_a4, code3 -> per-row {sum g_n3, sum g_n3*xhat3}, range sums of FQ4
+//   R    reduce        per-sample S1,S2 and per-channel dgamma,dbeta
+//   P2D  fused         g_a4, y3 -> gLN2/FQ3/PReLU3 backward -> g_y3 row in SHARED memory -> depthwise + FQ2 backward
+//                      (taps from shared memory, code1) -> g_n1 (bf16), dW_dw, db_dw, gLN1 row sums, range sums
+//                      (the two-kernel variant P2 + D is kept behind FQSS_SPLIT_P2D for A/B runs)
+//   R    reduce
+//   Q    gLN1/FQ1/PReLU backward  g_n1, y1 -> dY1 (bf16, pre-scaled), db1
+//   G    dgrad GEMM    dY1 x Wc1T (+ g_xd) -> g_x_in (fp32)                          [tcgen05]
+//   W    wgrad GEMM    dY1 x x_op -> dW1q                                           [tcgen05, split-K]
+//   F    finalise      fp64 accumulators -> fp32 parameter gradients
 //
 // The 512-wide gradient tensors travel in bf16 (the "1e-2 bf16 GEMM path"); the residual-stream and
 // skip-sum gradients (128-wide) stay fp32 end to end.

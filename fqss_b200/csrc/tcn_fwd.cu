@@ -1,15 +1,19 @@
 // tcn_fwd.cu -- forward of the fused TCN ConvBlock (convtasnetq.py:11-42 after quantize_model).
 //
-//   K1  tcgen05 GEMM  x_op -> y1 = W1q x + b1            epilogue: gLN statistics of a1 = FQ1(PReLU(y1))
-//   K2  this file     y1 -> [PReLU,FQ1] -> [gLN1,FQ2] -> depthwise dilated 3-tap FIR + bias -> y3
-//                     one CTA per (sample, channel) row; the whole row (M <= 8K frames) is staged in
-//                     shared memory so the dilation halo costs no extra HBM traffic; epilogue: gLN
-//                     statistics of a3 = FQ3(PReLU(y3)).  HBM bytes: read y1 + write y3 = 8 B/element.
-//   K3a this file     y3 -> [PReLU,FQ3] -> [gLN2,FQ4] -> bf16 operand (integer code)      6 B/element
+//   K1  tcgen05 GEMM  x_op -> y1 = W1q x + b1            epilogue: exact FQ1 codes (code1, 1 B/frame) and the gLN
+//                     statistics of a1 = FQ1(PReLU(y1)) as integer code sums; last CTA -> per-sample constants
+//   K2  this file     code1 -> table[gLN1, FQ2] -> depthwise dilated 3-tap FIR + bias -> y3, code3
+//                     one CTA per (sample, channel) row; the whole row (M <= 8K frames) is staged in shared memory
+//                     so the dilation halo costs no extra HBM traffic; epilogue: gLN statistics of
+//                     a3 = FQ3(PReLU(y3)).  HBM bytes: code1 1 + y3 4 + code3 1 = 6 B/frame.
+//                     Float model: y1 -> PReLU -> gLN1 -> FIR -> y3 (or, with the second gLN folded into the
+//                     res/skip conv, a3 = PReLU(y3) straight into the [hi ; lo] GEMM operand).
+//   K3a this file     code3 -> table[gLN2, FQ4] -> bf16 operand (integer code)          3 B/frame
 //   K3  tcgen05 GEMM  a4_op -> res_y / skip_y, x_out = FQ(x + FQ(res)), skip_out = FQ(skip_in + FQ(skip))
 //
-// Only pre-activation tensors (y1, y3, res_y, skip_y) and the 128-wide block outputs are stored;
-// every quantised activation is recomputed on load by its consumer (and again in backward).
+// Stored per block: the pre-activations backward re-reads (y1, y3, res_y, skip_y; skipped in inference), the
+// 8-bit codes of the two hidden quantisers and the 128-wide block outputs; every other quantised activation is
+// looked up / recomputed by its consumer (and again in backward) from the same device functions.
 #include <stdio.h>
 #include <stdlib.h>
 

@@ -3,10 +3,11 @@ ConvBlocks of the separator (`MaskGenerator.TCN` + `MaskGenerator.adds`).  Plumb
 allocation, pointer tables, launch order; all arithmetic is in csrc/tcn_fwd.cu, tcn_bwd.cu,
 gemm_tc.cu, wgrad_tc.cu.
 
-The whole stack is ONE autograd node: forward launches 4 kernels per block, backward 9, and the
-residual-stream / skip-sum gradients never leave fp32.  Used when the quantised model is in steady
-state (observers off); the per-layer wrappers in qat_layers.py remain the general path (observer
-calibration, foreign compositions) and the definition of the drop-in API.
+The whole stack is ONE autograd node: forward launches 4 kernels (+1 one-warp constants launch) per block,
+backward 12, and the residual-stream / skip-sum gradients never leave fp32.  Forward-only calls (no_grad)
+take `_fused_tcn_infer`: same kernels without the stores only backward needs.  Used when the quantised
+model is in steady state (observers off); the per-layer wrappers in qat_layers.py remain the general
+path (observer calibration, foreign compositions) and the definition of the drop-in API.
 """
 import ctypes as C
 import os
