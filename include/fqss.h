@@ -352,7 +352,8 @@ int fqss_loss_grad_apply(const float* est, int64_t lde, const float* fest, int64
  *   sumsq[0] = sum g^2 (for the global-norm clip, gradient_clip_val=5.0)
  *   scale_clip: g *= pre_scale * min(1, max_norm / (sqrt(sumsq*pre_scale^2) + 1e-6))
  * ------------------------------------------------------------------------------------------- */
-/* gather the per-parameter gradient tensors into the flat arena (the buffer the all-reduce runs on): item i copies
+/* gather the per-parameter gradient tensors into the flat arena (the buffer the all-reduce runs on -- the role of DDP's
+ * gradient bucket in the reference, pl.Trainer(strategy="ddp"), asteroid_librimix_trainer.py:125-135): item i copies
  * numel floats from src (NULL: zeros -- a parameter that received no gradient) to dst + offset.  `items` is a HOST array. */
 typedef struct fqss_gather_item { const float* src; int64_t offset; int64_t numel; } fqss_gather_item;
 int fqss_arena_gather(const fqss_gather_item* items, int n, float* dst, void* stream);
