@@ -45,6 +45,9 @@ def eligible(model, x):
         return False
     Chid, Cio = sb[0].weight.shape[0], sb[0].weight.shape[1]
     F_ = enc.out_channels
+    M = (x.shape[-1] - enc.kernel_size[0]) // enc.stride[0] + 1
+    if M < 1 or not E.rows_fit(M, max(b.shared_block[3].dilation[0] for b in mk.TCN)):
+        return False            # whole-utterance inputs beyond the row kernels' shared-memory staging: plain torch modules
     return Cio % 128 == 0 and Chid % 128 == 0 and F_ % 64 == 0 and sb[3].kernel_size[0] == 3 \
         and sb[1].weight.numel() == 1 and (F_ * model.n_srcs) % 128 == 0
 

@@ -125,3 +125,9 @@ def get_activation_quantizer(gradient_based=True, nl=False, n_bits=8):
 
 def get_weight_quantizer(gradient_based=True, weight_shape=(1, 1, 1), n_bits=8, ch_out_idx=0):
     return GradientWeightFakeQuantize(gradient_based, weight_shape, n_bits=n_bits, ch_out_idx=ch_out_idx)
+
+
+# reference names outside the ConvTasNet hot path (imported by the reference's other model files): importable placeholders
+# that raise NotImplementedError when used -- see fqss_b200/shim.py
+from ..shim import module_getattr as _module_getattr  # noqa: E402
+__getattr__ = _module_getattr("quantization.qat.qat_quant")

@@ -137,3 +137,9 @@ def replace_encoderq(model, modules_to_replace, params_dict):
 
 def replace_decoderq(model, modules_to_replace, params_dict):
     _replace_edge(model, modules_to_replace, params_dict, quant_decoderq)
+
+
+# reference names outside the ConvTasNet hot path (imported by the reference's other model files): importable placeholders
+# that raise NotImplementedError when used -- see fqss_b200/shim.py
+from ..shim import module_getattr as _module_getattr  # noqa: E402
+__getattr__ = _module_getattr("quantization.qat.qat_utils")

@@ -397,6 +397,8 @@ class FusedTCNFunction(Function):
         ctx.states = states
         ctx.meta = (quant, B, Cio, M, ld)
         ctx.nflat = len(flat)
+        if KEEP_STATES:
+            LAST_STATES[:] = states
         x_last = states[-1].act.get("x_out")
         if x_last is None:
             x_last = torch.zeros((B, Cio, M), device=dev)          # dead output of the last block
@@ -565,7 +567,17 @@ def fused_tcn(x, blocks, adds, quant, q_in, start=0, total=None, skip_in=None):
     return FusedTCNFunction.apply(x, skip_in, meta, *flat)
 
 
+KEEP_STATES = False         # True: the training forward leaves its per-block BlockState list (prepared weights, saved
+LAST_STATES = []            # activations / codes) in LAST_STATES -- read by the kernel-level parity tests, never by the product
 INFERENCE_MODE = True       # False: forward-only calls also run the training forward (tests compare the two)
+
+
+def rows_fit(M, max_dil):
+    """The fused row kernels stage one whole (sample, channel) row plus its dilation halo in shared memory
+    (csrc/tcn_fwd.cu `validate_block`): about 22 k frames.  Longer inputs (whole utterances in val.py / infer.py) take
+    the per-layer path, which has no such bound."""
+    ld = (M + 7) // 8 * 8
+    return (ld * 2 + 4 * ((max_dil + 3) & ~3) + 1280) * 4 + ld <= 200 * 1024
 
 
 def fused_eligible(masker, x):
@@ -582,6 +594,8 @@ def fused_eligible(masker, x):
         return False
     Chid, Cio = sb[0].conv1d.weight.shape[0], sb[0].conv1d.weight.shape[1]
     if Cio % 128 or Chid % 128 or sb[3].conv1d.kernel_size[0] != 3:
+        return False
+    if x.dim() != 3 or not rows_fit(x.shape[-1], max(b.shared_block[3].conv1d.dilation[0] for b in blocks)):
         return False
     for m in masker.modules():
         if isinstance(m, AQ) and (m.observing() or m.n_bits != 8):

@@ -9,6 +9,8 @@ RECIPE_QUANT = dict(qat=True, gradient_based=True, weight_quant=True, weight_n_b
                     observer=True)          # configs/convtasnet_2spks_8k.yaml:13-26
 SMALL_KW = dict(n_spks=2, kernel_size=16, stride=8, n_filters=64, bn_chan=32, hid_chan=64, n_blocks=3, n_repeats=2)
 FULL_KW = dict(n_spks=2, kernel_size=16, stride=8)
+# smallest model whose TCN is eligible for the fused tcgen05 engine (channel counts are multiples of 128)
+FUSED_SMALL_KW = dict(n_spks=2, kernel_size=16, stride=8, n_filters=128, bn_chan=128, hid_chan=128, n_blocks=2, n_repeats=1)
 
 
 def _oracle_cfg(kw):
@@ -24,6 +26,8 @@ def __getattr__(name):      # lazy: the oracle is test infrastructure, never imp
         return _oracle_cfg(SMALL_KW)
     if name == "FULL_CFG":
         return _oracle_cfg(FULL_KW)
+    if name == "FUSED_SMALL_CFG":
+        return _oracle_cfg(FUSED_SMALL_KW)
     raise AttributeError(name)
 
 
