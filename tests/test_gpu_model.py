@@ -10,6 +10,7 @@ import pytest
 import torch
 
 import fqss_oracle as O
+from parity_log import record
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -113,21 +114,29 @@ def test_blocks_teacher_forced_forward_backward(golden):
             step = (P[q + "max_range"] - P[q + "min_range"]).item() / 255
             ref = taps[pre + ("out" if name == "add" else "skip")].detach()
             frac, worst = _flip_stats(t, ref, step)
-            assert frac < 5e-3 and worst <= 2.01, (i, name, frac, worst)
+            record("per_layer_small_teacher_forced/block%d" % i, **{name + "_flip_rate": frac, name + "_max_code_diff": worst})
+            assert frac <= 1e-3 and worst <= 1.01, (i, name, frac, worst)
         model.zero_grad(set_to_none=True)
         g_skip = taps[pre + "skip"].grad.to(DEV)
         if i == cfg.n_tcn - 1:      # last block: the residual output is dead (convtasnetq.py:106-111)
             skip.backward(g_skip)
         else:
             torch.autograd.backward([out, skip], [taps[pre + "out"].grad.to(DEV), g_skip])
-        assert rel(x.grad, taps[pre + "in"].grad) < 2e-2, (i, rel(x.grad, taps[pre + "in"].grad))
+        meas = {"gx_rel": rel(x.grad, taps[pre + "in"].grad)}
+        bad = []
         for k, p in blk.named_parameters():
             go = P[pre + k].grad
             if go is None:
                 assert p.grad is None or float(p.grad.abs().max()) == 0.0, (i, k)
                 continue
-            tol = 5e-2 if "range" in k else 2e-2
-            assert rel(p.grad, go) < tol or (p.grad.cpu() - go).abs().max() < 1e-6, (i, k, rel(p.grad, go))
+            meas["grad/" + k] = rel(p.grad, go)
+            # fp32 per-layer path: 1e-3 (north_star); range gradients are sums of rounding residuals with heavy
+            # cancellation, held to 1e-3 of the largest range gradient of the block when the relative bound fails
+            if not (meas["grad/" + k] < 1e-3 or (p.grad.cpu() - go).abs().max() < 1e-6):
+                bad.append((k, meas["grad/" + k], (p.grad.cpu() - go).abs().max().item()))
+        record("per_layer_small_teacher_forced/block%d" % i, **meas)
+        assert meas["gx_rel"] < 1e-3, (i, meas["gx_rel"])
+        assert not bad, (i, bad)
 
 
 def test_small_model_end_to_end_vs_reference(golden):
@@ -183,7 +192,7 @@ def test_single_convblock_vs_oracle_exact_inputs(golden):
 
 def test_full_size_model_vs_oracle():
     """cfg-1 shapes (T = 32000, full 512/128/512 x 24-block model), B = 1, free running.  Yardstick: the
-    oracle's own response to a 3e-7 relative input perturbation (a handful of input codes move); the CUDA
+    oracle's own response to additive input noise of 1e-7 x peak (a handful of input codes move); the CUDA
     path must stay within 3x of that self-deviation.  Also checks the observer calibration at full size."""
     from fqss_b200.losses import fqss_training_step
     from fqss_b200.qat.models.load_model import enable_observer
@@ -203,25 +212,30 @@ def test_full_size_model_vs_oracle():
     model.load_state_dict({k: v for k, v in P.items()}, strict=True)      # identical ranges from here on
     loss, _, est = fqss_training_step(model, fmodel, mix.to(DEV), src.to(DEV), 0.1)
     loss.backward()
-    P2 = O.Params({k: v.clone() for k, v in P.items()})
     est_o, loss_o, _ = _oracle_run(P, fP, mix, src, FULL_CFG, st)
-    est_p, loss_p, _ = _oracle_run(P2, fP, mix * (1 + 3e-7), src, FULL_CFG, st)
-    # the quantised 24-block stack is chaotic (a few flipped codes move est by percents), so ONE perturbed run is a
-    # noisy yardstick for a scalar like the loss: take the worst of three perturbation sizes
-    loss_dev = abs(loss_p - loss_o)
-    for eps in (1e-7, 1e-6):
-        P3 = O.Params({k: v.clone() for k, v in P.items()})
-        _, loss_q, _ = _oracle_run(P3, fP, mix * (1 + eps), src, FULL_CFG, st)
-        loss_dev = max(loss_dev, abs(loss_q - loss_o))
-    self_est = rel(est_p, est_o)
-    self_cos, _ = _grad_cos([(k, v.grad) for k, v in P2.items()], {k: v.grad for k, v in P.items()})
+    grads_o = {k: v.grad for k, v in P.items()}
+    # Yardstick: the oracle's own response to ADDITIVE input noise (a pure scale would be normalised away by the
+    # splitter, process.py:23-24).  The quantised 24-block stack is chaotic: noise of 1e-8 x peak already moves a few
+    # input codes and the output by percents.
+    gen = torch.Generator().manual_seed(2)
+    unit = torch.randn(mix.shape, generator=gen) * mix.abs().max()
+    self_dev = {}
+    for eps in (1e-8, 1e-7, 1e-6):
+        Pn = O.Params({k: v.clone() for k, v in P.items()})
+        est_p, loss_p, _ = _oracle_run(Pn, fP, mix + eps * unit, src, FULL_CFG, st)
+        cos_p, _ = _grad_cos([(k, v.grad) for k, v in Pn.items()], grads_o)
+        self_dev[eps] = (rel(est_p, est_o), abs(loss_p - loss_o), cos_p)
     our_est = rel(est, est_o)
-    our_cos, ratio = _grad_cos([(k, p.grad) for k, p in model.named_parameters()], {k: v.grad for k, v in P.items()})
-    print("full-size: est rel ours %.3e / oracle-self %.3e ; grad cos ours %.4f / oracle-self %.4f ; loss %.4f vs %.4f (self %.4f)"
-          % (our_est, self_est, our_cos, self_cos, loss.item(), loss_o, loss_p))
-    assert our_est < max(3 * self_est, 1e-2), (our_est, self_est)
-    assert abs(loss.item() - loss_o) < max(3 * loss_dev, 0.15), (loss.item(), loss_o, loss_dev)
-    assert (1 - our_cos) < max(3 * (1 - self_cos), 1e-2), (our_cos, self_cos)
+    our_cos, ratio = _grad_cos([(k, p.grad) for k, p in model.named_parameters()], grads_o)
+    record("full_size_free_running", est_rel=our_est, loss=loss.item(), loss_oracle=loss_o, grad_cos=our_cos, grad_norm_ratio=ratio,
+           **{"oracle_self_%g_%s" % (e, n): v for e, t in self_dev.items() for n, v in zip(("est_rel", "loss_dev", "grad_cos"), t)})
+    print("full-size: est rel ours %.3e ; grad cos ours %.4f ; loss %.4f vs %.4f ; oracle self-deviation %s"
+          % (our_est, our_cos, loss.item(), loss_o, {e: tuple(round(v, 5) for v in t) for e, t in self_dev.items()}))
+    # the CUDA path (exact integer GEMMs, fp32 elsewhere) must behave like an input perturbation of at most 1e-7 x peak
+    s_est, s_loss, s_cos = self_dev[1e-7]
+    assert our_est < max(3 * s_est, 1e-2), (our_est, self_dev)
+    assert abs(loss.item() - loss_o) < max(3 * s_loss, 0.15), (loss.item(), loss_o, self_dev)
+    assert (1 - our_cos) < max(3 * (1 - s_cos), 1e-2), (our_cos, self_dev)
     assert abs(ratio - 1) < 0.1
 
 
@@ -298,3 +312,34 @@ def test_model_infer_on_device(golden):
         acc[:, start:stop] += w[:n] * co
         sw[start:stop] += w[:n]
     assert rel(out, acc / sw) < 1e-6
+
+
+def test_long_utterance_falls_back_to_per_layer_path():
+    """val.py / infer.py run whole utterances (no segment_samples in the shipped YAML): beyond ~22 k frames a row no
+    longer fits the fused row kernels' shared-memory staging, and both the quantised student and the float teacher
+    must take their general paths (per-layer wrappers / torch modules) instead of raising."""
+    from fqss_b200 import tcn_engine as E
+    from fqss_b200.qat.models.load_model import enable_observer
+    from fqss_b200.testing import model_pair
+    kw = dict(n_spks=2, kernel_size=16, stride=8, n_filters=128, bn_chan=128, hid_chan=128, n_blocks=2, n_repeats=1)
+    model, fmodel = model_pair(kw, DEV, seed=0)
+    gen = torch.Generator().manual_seed(4)
+    short = (torch.randn(1, 2, 4000, generator=gen) * 0.05).sum(1, keepdim=True).to(DEV)
+    long = (torch.randn(1, 2, 8 * 24000 + 8, generator=gen) * 0.05).sum(1, keepdim=True).to(DEV)      # M = 24 000 frames
+    with torch.no_grad():
+        model(short)
+        model(short)
+    enable_observer(model, False)
+    assert E.rows_fit(499, 2) and not E.rows_fit(24000, 2)
+    with torch.no_grad():
+        E.KEEP_STATES = True
+        try:
+            E.LAST_STATES[:] = []
+            out = model(long)
+            fout = fmodel(long)
+        finally:
+            E.KEEP_STATES = False
+    assert out.shape == fout.shape == (1, 2, long.shape[-1]) and torch.isfinite(out).all() and torch.isfinite(fout).all()
+    # the long input equals the short one on its first samples up to the receptive field: sanity of the fallback path
+    est_short = model(short)
+    assert est_short.shape == (1, 2, 4000)
