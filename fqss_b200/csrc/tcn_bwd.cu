@@ -25,46 +25,10 @@
 #include "fqss_common.cuh"
 #include "gemm_tc.cuh"
 #include "tcn_common.cuh"
+#include "tcn_bwd_common.cuh"
 #include "wgrad_tc.cuh"
 
 namespace fqss {
-
-int num_sms();
-
-// fp64 accumulator block inside the workspace
-struct AccLayout {
-    int64_t q, slope, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, total;
-    __host__ __device__ AccLayout(int B, int Cio, int Chid) {
-        int64_t o = 0;
-        q = o; o += 16;
-        slope = o; o += 2;
-        db1 = o; o += Chid;
-        db2 = o; o += 2 * Cio;
-        dbdw = o; o += Chid;
-        dwdw = o; o += 3 * Chid;
-        row1 = o; o += 2 * (int64_t)B * Chid;
-        row2 = o; o += 2 * (int64_t)B * Chid;
-        samp1 = o; o += 2 * B;
-        samp2 = o; o += 2 * B;
-        total = o;
-    }
-};
-
-enum { Q1 = 0, Q2 = 1, Q3 = 2, Q4 = 3, QRES = 4, QSKIP = 5, QADD = 6, QADDS = 7 };
-
-__device__ __forceinline__ float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-// ---------------------------------------------------------------------------------------------
-// Row kernels.  One CTA per (sample, channel) row, every thread handles 4 consecutive frames per trip
-// (128-bit fp32 / 64-bit bf16 accesses), per-row constants and the code-indexed tables are built once
-// per CTA, partial sums are reduced fp32 -> warp -> fp64.  Frames m >= M (row padding up to ld) carry
-// no gradient: inputs are masked on load, outputs there are written as zeros.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_bf16x4(__nv_bfloat16* p, float a, float b, float c, float d) {
-    *reinterpret_cast<uint2*>(p) = float4_to_bf16x4(a, b, c, d);
-}
-__device__ __forceinline__ float4 ld_f4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ float f4_get(const float4& v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
 
 // ---------------------------------------------------------------------------------------------
 // T: tail backward over the 128-wide tensors.  grid = B*Cio rows.
@@ -178,51 +142,6 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
 // P1 / P2: gLN2 + FQ4 (+ FQ3 + PReLU3 in P2).  grid = B*Chid rows.  g_a4 in g_hid_a (bf16).
 // Everything downstream of FQ3 is a function of the 8-bit code of a3: tabX = xhat3 | mask4, tabD = D4.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
-__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
-__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
-__device__ __forceinline__ float hsum(float2 v) { return v.x + v.y; }
-// zero the components of a frame quad that lie at or beyond M (only the last quad of a row is affected)
-__device__ __forceinline__ void mask_tail(float2& a01, float2& a23, int nval) {
-    if (nval < 4) {
-        a23.y = 0.f;
-        if (nval < 3) a23.x = 0.f;
-        if (nval < 2) a01.y = 0.f;
-        if (nval < 1) a01.x = 0.f;
-    }
-}
-
-// Row loops run mask-free over the full frame quads (v < M/4); the one ragged quad of a row (M % 4 frames) is
-// handled once, by one thread, through the same body with TAIL = true.  Quads that are entirely padding
-// (ld - M >= 4) are never read or written.
-#define FQSS_ROW_LOOPN(NTH_, body, M)                                                                           \
-    do {                                                                                                  \
-        const int nfull_ = (M) >> 2;                                                                      \
-        for (int v_ = threadIdx.x; v_ < nfull_; v_ += (NTH_)) body(v_, std::false_type{});                \
-        if (((M)&3) && (int)threadIdx.x == (nfull_ % (NTH_))) body(nfull_, std::true_type{});             \
-    } while (0)
-
-// Batched variant: every thread first issues the loads of NQ quads (`load(v)` returns a plain struct of raw words), then
-// consumes them.  One row is only ~1000 quads, i.e. a handful of trips per thread, so without the batch every trip
-// exposes a full DRAM latency (ncu: > 40 % of the stall samples on the first use of the loaded word) and the bytes in
-// flight per SM stay far below what HBM needs.
-#define FQSS_ROW_LOOP_BATCH(NTH_, NQ_, load, body, M)                                                     \
-    do {                                                                                                  \
-        const int nfull_ = (M) >> 2;                                                                      \
-        for (int base_ = threadIdx.x; base_ < nfull_; base_ += (NQ_) * (NTH_)) {                          \
-            decltype(load(0)) d_[NQ_];                                                                    \
-            _Pragma("unroll") for (int k_ = 0; k_ < (NQ_); ++k_) {                                        \
-                const int v_ = base_ + k_ * (NTH_);                                                       \
-                if (v_ < nfull_) d_[k_] = load(v_);                                                       \
-            }                                                                                             \
-            _Pragma("unroll") for (int k_ = 0; k_ < (NQ_); ++k_) {                                        \
-                const int v_ = base_ + k_ * (NTH_);                                                       \
-                if (v_ < nfull_) body(v_, d_[k_], std::false_type{});                                     \
-            }                                                                                             \
-        }                                                                                                 \
-        if (((M)&3) && (int)threadIdx.x == (nfull_ % (NTH_))) body(nfull_, load(nfull_), std::true_type{}); \
-    } while (0)
-
 template <int PHASE, bool QUANT, int NTH, int NQ>
 __global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[4 * 32];
@@ -777,6 +696,13 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_dw_bwd_kernel(const fqss_tcn_blo
     }
 }
 
+
+}  // namespace fqss
+
+#include "tcn_rows.cuh"
+
+namespace fqss {
+
 // ---------------------------------------------------------------------------------------------
 // Q: gLN1 + FQ1 + PReLU1 backward: g_n1 (bf16, g_hid_a), y1 -> dY1 (bf16, pre-scaled by delta_w1), db1
 // ---------------------------------------------------------------------------------------------
@@ -862,10 +788,16 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
 }
 
 // F: fp64 accumulators -> fp32 outputs
-__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc) {
+__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc, int rows_persist) {
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (rows_persist && i < p.Chid) {      // the persistent-row kernels accumulate dgamma / dbeta here (no reduce launch)
+        g.g_gn1_b[i] = (float)acc[L.gln1 + 2 * i];
+        g.g_gn1_w[i] = (float)acc[L.gln1 + 2 * i + 1];
+        g.g_gn2_b[i] = (float)acc[L.gln2 + 2 * i];
+        g.g_gn2_w[i] = (float)acc[L.gln2 + 2 * i + 1];
+    }
     if (i < 8 && p.quant) {
         const double sD = acc[L.q + 2 * i], sZ = acc[L.q + 2 * i + 1];
         g.g_q[2 * i] = (float)(sZ - sD / 255.0);      // d/d min_range
@@ -903,6 +835,26 @@ static cudaEvent_t side_event(int i) {
 static int tune_nq(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
+}
+
+// persistent-row grid: exactly one resident wave of CTAs; jobs = (channel, RJ consecutive samples) dealt round-robin.
+// RJ is chosen so that every CTA gets about four jobs (balance) while the per-channel flushes stay rare.
+struct RowGrid { int grid, rj; };
+template <typename K>
+static RowGrid row_grid(K kernel, int nth, size_t smem, int B, int Chid) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nth, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    const int slots = num_sms() * per_sm;
+    static const int forced = tune_nq("FQSS_ROW_RJ", 0);
+    int rj = forced > 0 ? forced : (int)(((int64_t)B * Chid) / (4 * (int64_t)slots));
+    if (rj < 1) rj = 1;
+    if (rj > 8) rj = 8;
+    if (rj > B) rj = B;
+    const int njobs = ((B + rj - 1) / rj) * Chid;
+    RowGrid r;
+    r.grid = njobs < slots ? njobs : slots;
+    r.rj = rj;
+    return r;
 }
 
 }  // namespace fqss
@@ -978,20 +930,50 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (overlap) cudaEventRecord(side_event(1), sw);      // recorded even on failure: the main stream must not wait forever
     if (rc) return rc;
     // P1, R, P2
-    {
-        FQSS_PROF("tcn_gln2_bwd<1>", s);
-        static const int p1_th = tune_nq("FQSS_P1_TH", 128);
-        if (p->quant) {
-            if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
-            else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+    // quantised model: persistent-row kernels (one CTA per channel walks a range of samples; no reduce launches)
+    static const int rows_persist_env = tune_nq("FQSS_ROWS_PERSIST", 0);      // experimental (slower than the per-row kernels on B200: see DESIGN.md)
+    const bool rows_persist = p->quant && rows_persist_env;
+    if (rows_persist) {
+        FQSS_PROF("tcn_gln2_sums_rows", s);
+        const RowGrid rg = row_grid(tcn_gln2_sums_rows_kernel<128, 4, 8>, 128, 0, p->B, p->Chid);
+        tcn_gln2_sums_rows_kernel<128, 4, 8><<<rg.grid, 128, 0, s>>>(*p, *g, acc, rg.rj);
+    } else {
+        {
+            FQSS_PROF("tcn_gln2_bwd<1>", s);
+            static const int p1_th = tune_nq("FQSS_P1_TH", 128);
+            if (p->quant) {
+                if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
+                else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+            }
+            else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
         }
-        else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
+                                                                         acc + L.samp2); }
     }
-    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
-                                                                     acc + L.samp2); }
     // P2 + D (one kernel; FQSS_SPLIT_P2D=1 runs the two separate kernels instead -- development / A-B knob)
     static const int split_p2d = tune_nq("FQSS_SPLIT_P2D", 0);
-    if (!split_p2d) {
+    if (rows_persist) {
+        const size_t smem = p2d_rows_smem(p->ld, p->dil);
+        FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
+        const int mode = dw_mode(p->dil);
+        FQSS_PROF("tcn_gln2_dw_bwd_rows", s);
+#define FQSS_FR_LAUNCH1(D, TH, MB)                                                                                          \
+    do {                                                                                                                   \
+        cudaFuncSetAttribute(tcn_gln2_dw_bwd_rows_kernel<D, TH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        const RowGrid rg = row_grid(tcn_gln2_dw_bwd_rows_kernel<D, TH, MB>, TH, smem, p->B, p->Chid);                      \
+        tcn_gln2_dw_bwd_rows_kernel<D, TH, MB><<<rg.grid, TH, smem, s>>>(*p, *g, acc, rg.rj);                              \
+    } while (0)
+        // development knob FQSS_FR_VAR: CTA width / CTAs per SM = 0: 256 / 3 (80 registers), 1: 128 / 3, 2: 256 / 2
+        static const int fr_var = tune_nq("FQSS_FR_VAR", 0);
+#define FQSS_FR_LAUNCH(D)                                                                  \
+    do {                                                                                   \
+        if (fr_var == 1) FQSS_FR_LAUNCH1(D, 128, 3); else if (fr_var == 2) FQSS_FR_LAUNCH1(D, 256, 2); \
+        else FQSS_FR_LAUNCH1(D, 256, 3);                                                   \
+    } while (0)
+        if (mode == 0) FQSS_FR_LAUNCH(0); else if (mode == 1) FQSS_FR_LAUNCH(1); else if (mode == 2) FQSS_FR_LAUNCH(2); else FQSS_FR_LAUNCH(3);
+#undef FQSS_FR_LAUNCH1
+#undef FQSS_FR_LAUNCH
+    } else if (!split_p2d) {
         const int dpad = dw_pad(p->dil);
         const size_t smem = ((size_t)p->ld + 2 * dpad) * sizeof(float);
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
@@ -1052,8 +1034,10 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
 #undef FQSS_DWB_LAUNCH
         }
     }
-    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
-                                                                     acc + L.samp1); }
+    if (!rows_persist) {
+        FQSS_PROF("tcn_gln_reduce", s);
+        tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b, acc + L.samp1);
+    }
     {
         FQSS_PROF("tcn_gln1_bwd", s);
         if (p->quant) {
@@ -1082,7 +1066,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (rc) return rc;
     // F
     const int nf = p->Chid > n2 ? p->Chid : n2;
-    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc); }
+    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc, rows_persist ? 1 : 0); }
     return check_launch("tcn_block_bwd(finalize)");
 }
 
