@@ -788,16 +788,10 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
 }
 
 // F: fp64 accumulators -> fp32 outputs
-__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc, int rows_persist) {
+__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc) {
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (rows_persist && i < p.Chid) {      // the persistent-row kernels accumulate dgamma / dbeta here (no reduce launch)
-        g.g_gn1_b[i] = (float)acc[L.gln1 + 2 * i];
-        g.g_gn1_w[i] = (float)acc[L.gln1 + 2 * i + 1];
-        g.g_gn2_b[i] = (float)acc[L.gln2 + 2 * i];
-        g.g_gn2_w[i] = (float)acc[L.gln2 + 2 * i + 1];
-    }
     if (i < 8 && p.quant) {
         const double sD = acc[L.q + 2 * i], sZ = acc[L.q + 2 * i + 1];
         g.g_q[2 * i] = (float)(sZ - sD / 255.0);      // d/d min_range
@@ -835,26 +829,6 @@ static cudaEvent_t side_event(int i) {
 static int tune_nq(const char* name, int dflt) {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
-}
-
-// persistent-row grid: exactly one resident wave of CTAs; jobs = (channel, RJ consecutive samples) dealt round-robin.
-// RJ is chosen so that every CTA gets about four jobs (balance) while the per-channel flushes stay rare.
-struct RowGrid { int grid, rj; };
-template <typename K>
-static RowGrid row_grid(K kernel, int nth, size_t smem, int B, int Chid) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nth, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int slots = num_sms() * per_sm;
-    static const int forced = tune_nq("FQSS_ROW_RJ", 0);
-    int rj = forced > 0 ? forced : (int)(((int64_t)B * Chid) / (4 * (int64_t)slots));
-    if (rj < 1) rj = 1;
-    if (rj > 8) rj = 8;
-    if (rj > B) rj = B;
-    const int njobs = ((B + rj - 1) / rj) * Chid;
-    RowGrid r;
-    r.grid = njobs < slots ? njobs : slots;
-    r.rj = rj;
-    return r;
 }
 
 }  // namespace fqss
@@ -930,49 +904,42 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (overlap) cudaEventRecord(side_event(1), sw);      // recorded even on failure: the main stream must not wait forever
     if (rc) return rc;
     // P1, R, P2
-    // quantised model: persistent-row kernels (one CTA per channel walks a range of samples; no reduce launches)
-    static const int rows_persist_env = tune_nq("FQSS_ROWS_PERSIST", 0);      // experimental (slower than the per-row kernels on B200: see DESIGN.md)
-    const bool rows_persist = p->quant && rows_persist_env;
-    if (rows_persist) {
-        FQSS_PROF("tcn_gln2_sums_rows", s);
-        const RowGrid rg = row_grid(tcn_gln2_sums_rows_kernel<128, 4, 8>, 128, 0, p->B, p->Chid);
-        tcn_gln2_sums_rows_kernel<128, 4, 8><<<rg.grid, 128, 0, s>>>(*p, *g, acc, rg.rj);
-    } else {
-        {
-            FQSS_PROF("tcn_gln2_bwd<1>", s);
-            static const int p1_th = tune_nq("FQSS_P1_TH", 128);
-            if (p->quant) {
-                if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
-                else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-            }
-            else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+    {
+        FQSS_PROF("tcn_gln2_bwd<1>", s);
+        static const int p1_th = tune_nq("FQSS_P1_TH", 128);
+        if (p->quant) {
+            if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
+            else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
         }
-        { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
-                                                                         acc + L.samp2); }
+        else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
     }
+    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
+                                                                     acc + L.samp2); }
     // P2 + D (one kernel; FQSS_SPLIT_P2D=1 runs the two separate kernels instead -- development / A-B knob)
     static const int split_p2d = tune_nq("FQSS_SPLIT_P2D", 0);
-    if (rows_persist) {
-        const size_t smem = p2d_rows_smem(p->ld, p->dil);
+    // quantised model: the instruction-lean fused kernel (tcn_rows.cuh); FQSS_LEAN_P2D=0 keeps the first version for A/B runs
+    static const int lean_p2d = tune_nq("FQSS_LEAN_P2D", 1);
+    if (p->quant && lean_p2d && !split_p2d) {
+        const size_t smem = p2d_lean_smem(p->ld, p->dil);
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         const int mode = dw_mode(p->dil);
-        FQSS_PROF("tcn_gln2_dw_bwd_rows", s);
-#define FQSS_FR_LAUNCH1(D, TH, MB)                                                                                          \
+        FQSS_PROF("tcn_gln2_dw_bwd", s);
+#define FQSS_FL_LAUNCH1(D, NQv, MB)                                                                                         \
     do {                                                                                                                   \
-        cudaFuncSetAttribute(tcn_gln2_dw_bwd_rows_kernel<D, TH, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
-        const RowGrid rg = row_grid(tcn_gln2_dw_bwd_rows_kernel<D, TH, MB>, TH, smem, p->B, p->Chid);                      \
-        tcn_gln2_dw_bwd_rows_kernel<D, TH, MB><<<rg.grid, TH, smem, s>>>(*p, *g, acc, rg.rj);                              \
+        if (smem > 48 * 1024)                                                                                              \
+            cudaFuncSetAttribute(tcn_gln2_dw_bwd_lean_kernel<D, 128, NQv, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+        tcn_gln2_dw_bwd_lean_kernel<D, 128, NQv, MB><<<rows_h, 128, smem, s>>>(*p, *g, acc);                               \
     } while (0)
-        // development knob FQSS_FR_VAR: CTA width / CTAs per SM = 0: 256 / 3 (80 registers), 1: 128 / 3, 2: 256 / 2
-        static const int fr_var = tune_nq("FQSS_FR_VAR", 0);
-#define FQSS_FR_LAUNCH(D)                                                                  \
+        // development knob FQSS_FL_VAR: quads in flight / CTAs per SM = 0: 4 / 7, 1: 4 / 6, 2: 2 / 7
+        static const int fl_var = tune_nq("FQSS_FL_VAR", 0);
+#define FQSS_FL_LAUNCH(D)                                                                  \
     do {                                                                                   \
-        if (fr_var == 1) FQSS_FR_LAUNCH1(D, 128, 3); else if (fr_var == 2) FQSS_FR_LAUNCH1(D, 256, 2); \
-        else FQSS_FR_LAUNCH1(D, 256, 3);                                                   \
+        if (fl_var == 1) FQSS_FL_LAUNCH1(D, 4, 6); else if (fl_var == 2) FQSS_FL_LAUNCH1(D, 2, 7); \
+        else FQSS_FL_LAUNCH1(D, 4, 7);                                                     \
     } while (0)
-        if (mode == 0) FQSS_FR_LAUNCH(0); else if (mode == 1) FQSS_FR_LAUNCH(1); else if (mode == 2) FQSS_FR_LAUNCH(2); else FQSS_FR_LAUNCH(3);
-#undef FQSS_FR_LAUNCH1
-#undef FQSS_FR_LAUNCH
+        if (mode == 0) FQSS_FL_LAUNCH(0); else if (mode == 1) FQSS_FL_LAUNCH(1); else if (mode == 2) FQSS_FL_LAUNCH(2); else FQSS_FL_LAUNCH(3);
+#undef FQSS_FL_LAUNCH1
+#undef FQSS_FL_LAUNCH
     } else if (!split_p2d) {
         const int dpad = dw_pad(p->dil);
         const size_t smem = ((size_t)p->ld + 2 * dpad) * sizeof(float);
@@ -1034,10 +1001,8 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
 #undef FQSS_DWB_LAUNCH
         }
     }
-    if (!rows_persist) {
-        FQSS_PROF("tcn_gln_reduce", s);
-        tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b, acc + L.samp1);
-    }
+    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
+                                                                     acc + L.samp1); }
     {
         FQSS_PROF("tcn_gln1_bwd", s);
         if (p->quant) {
@@ -1066,7 +1031,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (rc) return rc;
     // F
     const int nf = p->Chid > n2 ? p->Chid : n2;
-    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc, rows_persist ? 1 : 0); }
+    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc); }
     return check_launch("tcn_block_bwd(finalize)");
 }
 

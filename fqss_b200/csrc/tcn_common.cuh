@@ -22,10 +22,12 @@ struct GlnRow {
 };
 
 // Row constants (written once per block by tcn_rowconst_kernel, tcn_fwd.cu): rc[0..3] / rc[4..7] / rc[8..11] = {min,
-// delta, 1/delta, levels} of the quantiser before the gLN / after it / after the next op; rc[12+2b], rc[13+2b] = mean,
-// rstd of sample b.  Loading
-// them costs a handful of uniform LDGs per thread instead of fp64 divisions and a square root.
-constexpr int RC_HDR = 12;
+// delta, 1/delta, levels} of the quantiser before the gLN / after it / after the next op; rc[12], rc[13] = the exact
+// clipping thresholds of the FIRST quantiser in the domain of its input z: z_lo = min{z : (z - min)/delta >= -0.5},
+// z_hi = min{z : (z - min)/delta >= levels + 0.5} (the quotient is monotone in z, so lo <= z < hi is the forward's STE
+// mask -0.5 <= t < levels + 0.5 bit for bit, without a division per element); rc[RC_HDR+2b], rc[RC_HDR+1+2b] = mean,
+// rstd of sample b.  Loading them costs a handful of uniform LDGs per thread instead of fp64 divisions and a square root.
+constexpr int RC_HDR = 16;
 __device__ __forceinline__ ActQF load_actqf_rc(const float* __restrict__ rc) {
     ActQF q;
     q.mn = __ldg(rc);
@@ -43,6 +45,23 @@ __device__ __forceinline__ GlnRow load_gln_row(const float* __restrict__ rc, int
     g.scale = __fmul_rn(g.rstd, g.gamma);
     g.shift = __fadd_rn(__fmul_rn(-g.scale, g.mu), __ldg(gb + c));
     return g;
+}
+
+// smallest float z with (z - min) / delta >= target (IEEE division; bit-identical to actqf_t wherever that is finite):
+// bisection over the order-preserving integer image of the floats
+__device__ __forceinline__ unsigned f2key(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
+__device__ inline float fq_threshold(float mn, float delta, float target) {
+    unsigned lo = f2key(-3.0e38f), hi = f2key(3.0e38f);
+    while (hi - lo > 1u) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        const float t = __fdiv_rn(__fsub_rn(key2f(mid), mn), delta);
+        if (t >= target) hi = mid; else lo = mid;
+    }
+    return key2f(hi);
 }
 
 __device__ __forceinline__ float prelu_f(float y, float a) { return y > 0.f ? y : __fmul_rn(a, y); }
@@ -80,6 +99,10 @@ __device__ __forceinline__ void rowconst_last_cta(const RowConstJob& j, unsigned
             const ActQF q = load_actqf(mn, mx, 8);
             j.rc[4 * t] = q.mn; j.rc[4 * t + 1] = q.delta; j.rc[4 * t + 2] = q.inv; j.rc[4 * t + 3] = q.levels;
         }
+    }
+    if ((t == 32 || t == 33) && j.qa_min) {      // clipping thresholds of the first quantiser (a warp of its own: 32 dependent divisions)
+        const ActQF q = load_actqf(j.qa_min, j.qa_max, 8);
+        j.rc[12 + (t - 32)] = fq_threshold(q.mn, q.delta, t == 32 ? -0.5f : q.levels + 0.5f);
     }
     for (int b = t; b < j.B; b += blockDim.x) {
         const double mean = __ldcg(j.stats + 2 * b) / j.n_elems;

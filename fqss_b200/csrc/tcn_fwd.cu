@@ -308,6 +308,10 @@ __global__ void tcn_rowconst_kernel(RowConstJob j) {
             j.rc[4 * t] = q.mn; j.rc[4 * t + 1] = q.delta; j.rc[4 * t + 2] = q.inv; j.rc[4 * t + 3] = q.levels;
         }
     }
+    if ((t == 32 || t == 33) && j.qa_min) {      // clipping thresholds of the first quantiser (tcn_common.cuh)
+        const ActQF q = load_actqf(j.qa_min, j.qa_max, 8);
+        j.rc[12 + (t - 32)] = fq_threshold(q.mn, q.delta, t == 32 ? -0.5f : q.levels + 0.5f);
+    }
     for (int b = t; b < j.B; b += blockDim.x) {
         const double mean = j.stats[2 * b] / j.n_elems;
         double var = j.stats[2 * b + 1] / j.n_elems - mean * mean;

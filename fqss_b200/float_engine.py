@@ -111,8 +111,8 @@ def _tcn_infer(x0, P, B, Cio, M, ld, dev):
     a4 = torch.empty((B, 2 * Chid, ld), dtype=bf, device=dev)
     st1 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
     st3 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
-    rc1 = torch.empty(12 + 2 * B, device=dev)
-    rc3 = torch.empty(12 + 2 * B, device=dev)
+    rc1 = torch.empty(16 + 2 * B, device=dev)
+    rc3 = torch.empty(16 + 2 * B, device=dev)
     xs = [x0, torch.empty((B, Cio, ld), device=dev), torch.empty((B, Cio, ld), device=dev)]
     xops = [E.split_bf16_acts(x0[:, :, :M], ld), torch.empty((B, 2 * Cio, ld), dtype=bf, device=dev)]
     skips = [torch.empty((B, Cio, ld), device=dev), torch.empty((B, Cio, ld), device=dev)]

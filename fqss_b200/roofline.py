@@ -78,9 +78,7 @@ def algorithmic_bytes(B, M, Cio=128, Chid=512):
         "gemm_dgrad_bf16": 2 * 2 * I + w2 + 2 * H,              # dY2 in, g_a4 bf16 out
         "tcn_gln2_bwd<1>": H + 2 * H,                           # code3 (u8), g_a4 (bf16) in (sums out)
         "tcn_gln2_bwd<2>": 4 * H + 2 * H + 2 * H,               # y3, g_a4 in, g_y3 bf16 out
-        "tcn_gln2_dw_bwd": 4 * H + 2 * H + H + 2 * H,           # y3, g_a4 (bf16), code1 (u8) in, g_n1 bf16 out (fused P2 + D)
-        "tcn_gln2_sums_rows": H + 2 * H,                        # persistent-row P1: code3 (u8), g_a4 (bf16) in
-        "tcn_gln2_dw_bwd_rows": 4 * H + 2 * H + H + H + 2 * H,  # persistent-row P2D: y3, g_a4, code3, code1 in, g_n1 bf16 out
+        "tcn_gln2_dw_bwd": 4 * H + 2 * H + H + H + 2 * H,       # y3, g_a4 (bf16), code3, code1 (u8) in, g_n1 bf16 out (fused P2 + D)
         "tcn_dw_bwd": H + 2 * H + 2 * H,                        # code1 (u8), g_y3 in, g_n1 bf16 out
         "tcn_gln1_bwd": 4 * H + 2 * H + 2 * H,                  # y1, g_n1 in, dY1 bf16 out
         "gemm_dgrad_add": 2 * H + w1 + 4 * I + 4 * I,           # dY1, g_xd in, g_x_in out

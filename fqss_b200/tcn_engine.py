@@ -235,8 +235,8 @@ def _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant=True):
     A = dict(y1=torch.empty((B, Chid, ld), device=dev), y3=torch.empty((B, Chid, ld), device=dev),
              stats1=torch.empty(2 * B + 1, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B + 1, dtype=torch.float64, device=dev),
              a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), skip_y=torch.empty((B, Cio, ld), device=dev),
-             skip_out=torch.empty((B, Cio, ld), device=dev), rc1=torch.empty(12 + 2 * B, device=dev),
-             rc3=torch.empty(12 + 2 * B, device=dev))
+             skip_out=torch.empty((B, Cio, ld), device=dev), rc1=torch.empty(16 + 2 * B, device=dev),
+             rc3=torch.empty(16 + 2 * B, device=dev))
     if quant:
         A.update(code1=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev),
                  code3=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev))
@@ -519,8 +519,8 @@ def _fused_tcn_infer(x, skip_in, meta, flat):
     _run_batches(prep_items, wq_items)
     Chid = tensors[0]["W1"].shape[0]
     hid = dict(stats1=torch.empty(2 * B + 1, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B + 1, dtype=torch.float64, device=dev),
-               a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), rc1=torch.empty(12 + 2 * B, device=dev),
-               rc3=torch.empty(12 + 2 * B, device=dev), code1=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev),
+               a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), rc1=torch.empty(16 + 2 * B, device=dev),
+               rc3=torch.empty(16 + 2 * B, device=dev), code1=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev),
                code3=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev))
     xs = [torch.empty((B, Cio, ld), device=dev) for _ in range(2)]
     xops = [torch.empty((B, Cio, ld), dtype=bf, device=dev) for _ in range(2)]

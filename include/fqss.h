@@ -246,7 +246,8 @@ typedef struct fqss_tcn_block {
     float* y1; double* stats1; float* y3; double* stats3; void* a4_op;
     float* res_y; float* skip_y; float* x_out; void* x_out_op; float* skip_out;
     /* row constants written by forward right after the statistics are complete and re-read by backward:
-     * 12 + 2*B floats each = {min, delta, 1/delta, levels} of up to three quantisers, then {mean, rstd} per sample
+     * 16 + 2*B floats each = {min, delta, 1/delta, levels} of up to three quantisers, the two exact clipping thresholds of
+     * the first one (z_lo, z_hi), two pad words, then {mean, rstd} per sample
      * (rc1: q1, q2, q3 and gLN1 from stats1; rc3: q3, q4 and gLN2 from stats3) */
     float* rc1; float* rc3;
     /* quantised model: the 8-bit codes of a1 = FQ1(PReLU(y1)) and a3 = FQ3(PReLU(y3)), one byte per frame

@@ -84,8 +84,8 @@ def _decode(code, rmin, rmax):
 def _gln_from_rc(a, rc, gamma, beta, B):
     """gln_apply of csrc/tcn_common.cuh with the kernel's own per-sample constants: scale = rstd*gamma,
     shift = (-scale*mu) + beta, n = a*scale + shift -- every op separately rounded, as on the device."""
-    mu = rc[12:12 + 2 * B:2].reshape(B, 1, 1)
-    rstd = rc[13:13 + 2 * B:2].reshape(B, 1, 1)
+    mu = rc[16:16 + 2 * B:2].reshape(B, 1, 1)
+    rstd = rc[17:17 + 2 * B:2].reshape(B, 1, 1)
     scale = rstd * gamma.reshape(1, -1, 1)
     shift = (-scale) * mu + beta.reshape(1, -1, 1)
     return a * scale + shift
@@ -159,8 +159,8 @@ def _exact_chain(model, i, x, skip_in, tag):
     mu64 = a1.double().mean(dim=(1, 2))
     rstd64 = 1.0 / torch.sqrt(a1.double().var(dim=(1, 2), unbiased=False) + 1e-8)
     rc1 = A["rc1"]
-    out["gln1_mu_rel"] = ((rc1[12:12 + 2 * B:2].double() - mu64).abs() / (mu64.abs() + 1e-12)).max().item()
-    out["gln1_rstd_rel"] = ((rc1[13:13 + 2 * B:2].double() - rstd64).abs() / rstd64).max().item()
+    out["gln1_mu_rel"] = ((rc1[16:16 + 2 * B:2].double() - mu64).abs() / (mu64.abs() + 1e-12)).max().item()
+    out["gln1_rstd_rel"] = ((rc1[17:17 + 2 * B:2].double() - rstd64).abs() / rstd64).max().item()
     assert out["gln1_mu_rel"] < 1e-5 and out["gln1_rstd_rel"] < 1e-6, (tag, out)
     # ---- a2 = FQ2(gLN1(a1)) with the kernel's constants, depthwise conv -> y3 (fp32 round-off), code3 exact
     n1 = _gln_from_rc(a1, rc1, sb[2].groupnorm.weight.detach().cpu(), sb[2].groupnorm.bias.detach().cpu(), B)
@@ -184,8 +184,8 @@ def _exact_chain(model, i, x, skip_in, tag):
     rc3 = A["rc3"]
     mu64 = a3.double().mean(dim=(1, 2))
     rstd64 = 1.0 / torch.sqrt(a3.double().var(dim=(1, 2), unbiased=False) + 1e-8)
-    out["gln2_mu_rel"] = ((rc3[12:12 + 2 * B:2].double() - mu64).abs() / (mu64.abs() + 1e-12)).max().item()
-    out["gln2_rstd_rel"] = ((rc3[13:13 + 2 * B:2].double() - rstd64).abs() / rstd64).max().item()
+    out["gln2_mu_rel"] = ((rc3[16:16 + 2 * B:2].double() - mu64).abs() / (mu64.abs() + 1e-12)).max().item()
+    out["gln2_rstd_rel"] = ((rc3[17:17 + 2 * B:2].double() - rstd64).abs() / rstd64).max().item()
     assert out["gln2_mu_rel"] < 1e-5 and out["gln2_rstd_rel"] < 1e-6, (tag, out)
     n3 = _gln_from_rc(a3, rc3, sb[5].groupnorm.weight.detach().cpu(), sb[5].groupnorm.bias.detach().cpu(), B)
     q4min, q4max = _q(sb[5])
