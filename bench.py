@@ -45,6 +45,13 @@ def parse():
     ap.add_argument("--cuda-graph", type=int, default=1,
                     help="1 (default): the timed steps replay ONE captured CUDA graph of the whole step "
                          "(fqss_b200.graph.GraphedStep); 0: eager launches")
+    ap.add_argument("--verify-dp", type=int, default=-1,
+                    help="data-parallel correctness check before the result line: one seeded global batch run sharded over the "
+                         "N ranks (global-batch parity switches on) and again on rank 0 alone; reports the relative difference "
+                         "of loss and averaged gradient arena.  -1 (default): on when N > 1")
+    ap.add_argument("--strong", type=int, default=-1,
+                    help="also time BASELINE configs[1] read literally (global batch 32 split over the N GPUs) and add it to "
+                         "the line as `strong`.  -1 (default): on when N > 1")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra step with cudaProfilerStart/Stop (for `ncu --profile-from-start off`); "
                          "numbers printed by such a run are never bench values")
@@ -308,13 +315,97 @@ def run_ours(args):
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     final_loss = float(loss_host.item())
 
+    # ---- BASELINE configs[1] read literally: global batch 32 split over the N GPUs (strong scaling) ----
+    strong = None
+    want_strong = (args.strong == 1 or (args.strong < 0 and world > 1)) and not args.global_batch and not args.profile_step
+    if want_strong and 32 % world == 0:
+        Bs = 32 // world
+        sb = [(m[:Bs].contiguous(), s_[:Bs].contiguous()) for m, s_ in dev_batches]
+        g2 = None
+        try:
+            if args.cuda_graph:
+                from fqss_b200.graph import GraphedStep
+                g2 = GraphedStep(step, sb[0], warmup=3)
+        except Exception:
+            g2 = None
+            torch.cuda.synchronize()
+        run2 = (lambda m, s_: g2(m, s_)) if g2 is not None else step
+
+        def timed2(n):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(n):
+                run2(*sb[i % n_host])
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        timed2(3)
+        ms_s = timed2(args.steps)
+        strong = {"global_batch": 32, "per_gpu_batch": Bs, "ms_per_step": ms_s / args.steps,
+                  "value": 32 * SEG_SECONDS * args.steps / (ms_s / 1e3), "unit": "audio-s/s", "scaling": "strong",
+                  "launch_mode": "cuda graph" if g2 is not None else "eager"}
+        if g2 is not None:
+            g2.graph.reset()
+            g2 = None
+
+    # ---- data-parallel correctness: the same seeded global batch on N ranks and on rank 0 alone ----
+    dp_check = None
+    if (args.verify_dp == 1 or (args.verify_dp < 0 and world > 1)) and world > 1 and not args.profile_step:
+        from fqss_b200 import parallel as PL
+        Gv = 8 if 8 % world == 0 else world
+        g = torch.Generator().manual_seed(4242)
+        src_g = (torch.randn(Gv, 2, T, generator=g) * 0.05).to(dev)
+        mix_g = src_g.sum(1, keepdim=True)
+        lo, hi = PL.shard_bounds(Gv, rank, world)
+
+        def fwd_bwd(mix, src):
+            arena.zero_grad()
+            est = model(mix)
+            with torch.no_grad():
+                fest = fmodel(mix)
+            loss, _, _ = fqss_kd_loss(est, fest, src, 0.1)
+            loss.backward()
+            arena.gather_grads()
+            return loss.detach().clone()
+        PL.set_global_batch_parity(True)           # splitter peak (MAX), loss means (SUM): global-batch semantics
+        try:
+            loss_dp = fwd_bwd(mix_g[lo:hi].contiguous(), src_g[lo:hi].contiguous())
+            scale = arena.allreduce_mean()
+            g_dp = arena.grad.clone().mul_(scale)
+        finally:
+            PL.set_global_batch_parity(False)
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            loss_1 = fwd_bwd(mix_g, src_g)         # one process, the whole global batch, no collective
+            g_1 = arena.grad
+            num = (g_dp - g_1).double().norm().item()
+            den = g_1.double().norm().item()
+            dp_check = {"global_batch": Gv, "ranks": world, "loss_dp": float(loss_dp), "loss_single": float(loss_1),
+                        "loss_rel_diff": abs(float(loss_dp) - float(loss_1)) / max(abs(float(loss_1)), 1e-30),
+                        "grad_rel_l2_diff": num / max(den, 1e-30),
+                        "grad_max_abs_diff_over_max": ((g_dp - g_1).abs().max() / g_1.abs().max().clamp_min(1e-30)).item(),
+                        "what": "all-reduced mean gradient arena (5.1 M floats) and loss of one seeded global batch on %d ranks "
+                                "vs the same batch on rank 0 alone; splitter peak and loss means synchronised "
+                                "(fqss_b200.parallel.set_global_batch_parity)" % world}
+        torch.cuda.synchronize()
+        dist.barrier()
+
     def finish():
-        """Multi-rank teardown.  A CUDA graph that captured NCCL's all-reduce keeps the communicator busy: tearing the
-        process group down with the graph alive hangs (seen at 2 GPUs), so drop the graph first, and do not let a slow
-        communicator teardown hold the job once every rank is past its last collective."""
+        """Multi-rank teardown: every captured graph is destroyed BEFORE the process group (a live graph that captured
+        NCCL's all-reduce keeps the communicator busy and destroy_process_group then waits forever); a watchdog ends the
+        process if the communicator teardown still does not return."""
         nonlocal graphed
         sys.stdout.flush()
         if world > 1:
+            if graphed is not None:
+                graphed.graph.reset()
             graphed = None
             import gc
             gc.collect()
@@ -322,7 +413,14 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
             sys.stdout.flush()
-            os._exit(0)             # the result line is out; skip destroy_process_group (exit code 0 for torchrun)
+            done = threading.Event()
+
+            def watchdog():
+                if not done.wait(30.0):
+                    os._exit(0)         # result line is out and every rank is past its last collective
+            threading.Thread(target=watchdog, daemon=True).start()
+            dist.destroy_process_group()
+            done.set()
 
     if rank != 0:
         finish()
@@ -340,6 +438,13 @@ def run_ours(args):
             "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
             "launch_mode": ("one CUDA graph per step (%d library kernels per replay)" % graphed.kernels_per_replay)
                            if graphed is not None else ("eager" + (" (graph capture failed: %s)" % graph_error if graph_error else ""))}
+    if strong is not None:
+        line["strong"] = strong
+    elif world == 1 and not args.global_batch and B == 32:
+        line["strong"] = {"global_batch": 32, "per_gpu_batch": 32, "ms_per_step": ms / args.steps, "value": val, "unit": "audio-s/s",
+                          "scaling": "strong", "note": "N = 1: identical to the weak-scaling configuration"}
+    if dp_check is not None:
+        line["dp_check"] = dp_check
     if world == 1 and not args.no_roofline:
         try:
             Mfr = (T - 16) // 8 + 1

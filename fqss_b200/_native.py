@@ -97,6 +97,7 @@ _SIGS = {
     "fqss_split": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, vp]),
     "fqss_combine": (i32, [vp, i64, i64, vp, i64, i64, i32, i32, i32, vp]),
     "fqss_kd_loss": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, f32, vp, vp, i64, vp, sz, vp]),
+    "fqss_kd_loss_dp": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, f32, vp, vp, i64, vp, sz, vp, i32, vp]),
     "fqss_loss_stats": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, vp, vp]),
     "fqss_loss_grad_apply": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, vp, vp, i64, vp]),
     "fqss_arena_gather": (i32, [C.POINTER(GatherItem), i32, vp, vp]),
@@ -129,7 +130,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 14:
+                if L.fqss_abi_version() != 15:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

@@ -131,8 +131,12 @@ __device__ __forceinline__ void rho_grad(const Rho& r, double d, double& ce, dou
 }
 
 // one block, thread b handles sample b (B <= 1024)
+// means_io: NULL = single-process semantics.  phase 0: write the LOCAL means {kd, task, val} there and stop (the caller
+// averages them over the data-parallel ranks); phase 1: take {kd, task, val} from there -- the means over the GLOBAL batch --
+// for the logarithm, while the per-sample coefficients keep 1/(2 B_local), so that the mean over ranks of the per-rank
+// gradients is the gradient of the global-batch loss (mysystem.py:145 under DDP).
 __global__ void loss_finalize_kernel(const double* __restrict__ st, int B, int T, float kd_lambda, float* __restrict__ out,
-                                     float* __restrict__ coef, int want_grad) {
+                                     float* __restrict__ coef, int want_grad, double* __restrict__ means_io, int phase) {
     __shared__ double sh[3 * 32];
     const int b = threadIdx.x;
     double kd_b = 0.0, task_b = 0.0, val_b = 0.0;
@@ -168,8 +172,13 @@ __global__ void loss_finalize_kernel(const double* __restrict__ st, int B, int T
     double v[3] = {kd_b, task_b, val_b};
     block_sum<3>(v, sh);
     __shared__ double tot[3];
-    if (threadIdx.x == 0) { tot[0] = v[0] / B; tot[1] = v[1] / B; tot[2] = v[2] / B; }
+    if (threadIdx.x == 0) {
+        tot[0] = v[0] / B; tot[1] = v[1] / B; tot[2] = v[2] / B;
+        if (means_io && phase == 0) { means_io[0] = tot[0]; means_io[1] = tot[1]; means_io[2] = tot[2]; }
+        if (means_io && phase == 1) { tot[0] = means_io[0]; tot[1] = means_io[1]; tot[2] = means_io[2]; }
+    }
     __syncthreads();
+    if (means_io && phase == 0) return;
     const double kd = tot[0], task = tot[1];
     const double A = (1.0 - (double)kd_lambda) * task + (double)kd_lambda * kd + LEPS;
     if (threadIdx.x == 0) {
@@ -248,12 +257,47 @@ extern "C" int fqss_kd_loss(const float* est, int64_t lde, const float* fest, in
     loss_mean_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, st);
     loss_dot_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, st);
     int threads = ((B + 31) / 32) * 32;
-    loss_finalize_kernel<<<1, threads, 0, s>>>(st, B, T, kd_lambda, out, coef, gest != nullptr);
+    loss_finalize_kernel<<<1, threads, 0, s>>>(st, B, T, kd_lambda, out, coef, gest != nullptr, nullptr, 0);
     if (gest) {
         dim3 g2((T + LS_THREADS - 1) / LS_THREADS, B);
         loss_grad_kernel<<<g2, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, coef, gest, ldg);
     }
     return check_launch("kd_loss");
+}
+
+// Data-parallel variant with the loss of the GLOBAL batch: phase 0 = statistics + the local means {kd, task, val} (fp64, on the
+// device) into `means`; the caller averages `means` over the ranks (one 3-double all-reduce); phase 1 = loss, logged values
+// and dL/dest from those means.  `ws` must be the same, untouched buffer in both phases (it carries the statistics).
+extern "C" int fqss_kd_loss_dp(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt, int B,
+                               int T, float kd_lambda, float* out, float* gest, int64_t ldg, void* ws, size_t ws_bytes,
+                               double* means, int phase, void* stream) {
+    FQSS_REQUIRE(est && fest && tgt && means && B > 0 && B <= 1024 && T > 0 && (phase == 0 || phase == 1), -1,
+                 "kd_loss_dp: bad argument (1 <= B <= 1024, phase 0 | 1)");
+    FQSS_REQUIRE(phase == 0 || out, -1, "kd_loss_dp: phase 1 needs the output vector");
+    FQSS_REQUIRE(lde >= T && ldf >= T && ldt >= T && (!gest || ldg >= T), -1, "kd_loss_dp: bad pitch");
+    size_t st_bytes = (size_t)B * LS_STRIDE * sizeof(double);
+    size_t need = st_bytes + (size_t)B * LC_STRIDE * sizeof(float);
+    FQSS_REQUIRE(ws && ws_bytes >= need, -3, "kd_loss_dp: workspace too small (%zu < %zu)", ws_bytes, need);
+    cudaStream_t s = (cudaStream_t)stream;
+    double* st = (double*)ws;
+    float* coef = (float*)((char*)ws + st_bytes);
+    int threads = ((B + 31) / 32) * 32;
+    if (phase == 0) {
+        FQSS_PROFN("kd_loss", s, 3);
+        cudaMemsetAsync(st, 0, st_bytes, s);
+        dim3 grid((T + LS_CHUNK - 1) / LS_CHUNK, B);
+        loss_mean_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, st);
+        loss_dot_kernel<<<grid, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, st);
+        loss_finalize_kernel<<<1, threads, 0, s>>>(st, B, T, kd_lambda, nullptr, coef, 0, means, 0);
+    } else {
+        FQSS_PROFN("kd_loss", s, gest ? 2 : 1);
+        loss_finalize_kernel<<<1, threads, 0, s>>>(st, B, T, kd_lambda, out, coef, gest != nullptr, means, 1);
+        if (gest) {
+            dim3 g2((T + LS_THREADS - 1) / LS_THREADS, B);
+            loss_grad_kernel<<<g2, LS_THREADS, 0, s>>>(est, lde, fest, ldf, tgt, ldt, T, coef, gest, ldg);
+        }
+    }
+    return check_launch("kd_loss_dp");
 }
 
 // The two HBM passes and the gradient pass as separate entry points: the sufficient statistics (means + 18 centred

@@ -489,6 +489,20 @@ class KDLoss(Function):
         out = torch.empty(3, device=est.device)
         gest = alloc_rows(est.shape, est.device) if est.requires_grad else None
         ws = workspace(B * 8, est.device)
+        from . import parallel
+        if parallel.global_batch_parity():
+            # loss of the GLOBAL batch (mysystem.py:145 takes the log of batch means): local means -> one all-reduce of
+            # 3 doubles -> loss / gradient from the global means (include/fqss.h, fqss_kd_loss_dp)
+            import torch.distributed as dist
+            means = torch.empty(3, dtype=torch.float64, device=est.device)
+            args = (ptr(est_r), lde, ptr(fest_r), ldf, ptr(tgt_r), ldt, B, T, float(kd_lambda))
+            check(lib().fqss_kd_loss_dp(*args, None, None, 0, ptr(ws), ws.numel(), ptr(means), 0, stream_ptr()))
+            dist.all_reduce(means, op=dist.ReduceOp.SUM)
+            means.mul_(1.0 / dist.get_world_size())
+            check(lib().fqss_kd_loss_dp(*args, ptr(out), ptr(gest) or None, ld_of(gest) if gest is not None else 0, ptr(ws),
+                                        ws.numel(), ptr(means), 1, stream_ptr()))
+            ctx.gest = gest
+            return out
         check(lib().fqss_kd_loss(ptr(est_r), lde, ptr(fest_r), ldf, ptr(tgt_r), ldt, B, T, float(kd_lambda), ptr(out),
                                  ptr(gest) or None, ld_of(gest) if gest is not None else 0, ptr(ws), ws.numel(),
                                  stream_ptr()))

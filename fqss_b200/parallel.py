@@ -24,8 +24,12 @@ from ._native import check, lib, ptr, stream_ptr, workspace
 #       reference's ranks silently diverge                                              -> all-reduce(MIN) of
 #       [min_range ; -max_range] after every calibration forward (the EMA is monotone in the batch statistic, so
 #       min over ranks of the updated value == the update with the global statistic, bit for bit)
-# (3) the loss `-10 log10(mean_b(...))` is not a mean of per-sample terms; the exact-global variant would all-reduce
-#     its two inner means -- NOT implemented: the path keeps the reference's per-rank loss.
+#   (3) loss: `-10 log10(mean_b(...))` (mysystem.py:145) is not a mean of per-sample terms, so DDP's mean of per-rank
+#       gradients is not the gradient of the global-batch loss                         -> all-reduce(SUM) of the three
+#       local means {kd, task, val} (3 doubles) between the statistics pass and the gradient pass of the loss kernel
+#       (ops.KDLoss -> fqss_kd_loss_dp); per-sample weights keep 1/(2 B_local), so the arena's mean over ranks is exact.
+# With all three on, an n-rank step equals the one-process step on the concatenated batch up to fp32 summation order
+# (`bench.py --verify-dp`, run by default at world size > 1, reports the measured difference).
 # ---------------------------------------------------------------------------------------------
 _GLOBAL_PARITY = False
 

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 14
+#define FQSS_ABI_VERSION 15
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -337,6 +337,17 @@ int fqss_combine(const float* parts, int64_t part_stride, int64_t ld, float* y, 
 int fqss_kd_loss(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt,
                  int B, int T, float kd_lambda, float* out, float* gest, int64_t ldg,
                  void* ws, size_t ws_bytes, void* stream);
+
+/* fqss_kd_loss under data parallelism with the loss of the GLOBAL batch (mysystem.py:145 takes
+ * -10 log10 of batch MEANS, so the mean of per-rank gradients is not the gradient of the global-batch loss).
+ *   phase 0: statistics + the local means {kd, task, val} (3 doubles on the device) into `means`;
+ *   the caller averages `means` over the ranks (one all-reduce of 3 doubles; equal shards);
+ *   phase 1: out[0..2] from the averaged means; dL/dest with per-sample weights 1/(2 B_local), so that the mean over
+ *            ranks of the per-rank gradients (DDP, asteroid_librimix_trainer.py:125-135) is the global-batch gradient.
+ * `ws` carries the statistics from phase 0 to phase 1 and must not be touched in between. */
+int fqss_kd_loss_dp(const float* est, int64_t lde, const float* fest, int64_t ldf, const float* tgt, int64_t ldt,
+                    int B, int T, float kd_lambda, float* out, float* gest, int64_t ldg,
+                    void* ws, size_t ws_bytes, double* means, int phase, void* stream);
 
 /* The passes of fqss_kd_loss as separate entry points (PairwiseWSDR as a standalone module, wsdr.py:46-95):
  *   fqss_loss_stats: per sample 24 doubles = SUMS of e0 e1 f0 f1 t0 t1 (divide by T for the means), then the centred

@@ -17,7 +17,7 @@ import torch
 import torch.nn.functional as F
 
 import fqss_oracle as O
-from parity_log import record
+from parity_log import reassociated_pointwise_convs, record
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -278,23 +278,30 @@ def _teacher_forced(model, i, B, seed, tag, chunk=8):
     torch.autograd.backward([xo, ss], [g_out.to(DEV), g_skip.to(DEV)])
     torch.cuda.synchronize()
     # oracle: same sub-graph, chunked over the batch (the block is per-sample; parameter gradients accumulate)
-    P = _oracle_params(model).leafify()
     st = O.QuantState(observe=False, weights_seen=True)
     pre = "masker.TCN.%d." % i
-    outs, skips, gxs, gss = [], [], [], []
-    for b0 in range(0, B, chunk):
-        sl = slice(b0, min(B, b0 + chunk))
-        ctx = O._Ctx(P, cfg, st, True, None)
-        xin = x[sl].cpu().clone().requires_grad_(True)
-        out_o, skip_o = O._tcn_block(ctx, i, xin)
-        sin = None
-        if i > 0:
-            sin = skip_in[sl].cpu().clone().requires_grad_(True)
-            skip_o = ctx.aq("masker.adds.%d.activation_fake_quantize" % (i - 1), sin + skip_o)
-        torch.autograd.backward([out_o, skip_o], [g_out[sl], g_skip[sl]])
-        outs.append(out_o.detach()); skips.append(skip_o.detach()); gxs.append(xin.grad)
-        if sin is not None:
-            gss.append(sin.grad)
+
+    def oracle_block():
+        P = _oracle_params(model).leafify()
+        outs, skips, gxs, gss = [], [], [], []
+        for b0 in range(0, B, chunk):
+            sl = slice(b0, min(B, b0 + chunk))
+            ctx = O._Ctx(P, cfg, st, True, None)
+            xin = x[sl].cpu().clone().requires_grad_(True)
+            out_o, skip_o = O._tcn_block(ctx, i, xin)
+            sin = None
+            if i > 0:
+                sin = skip_in[sl].cpu().clone().requires_grad_(True)
+                skip_o = ctx.aq("masker.adds.%d.activation_fake_quantize" % (i - 1), sin + skip_o)
+            torch.autograd.backward([out_o, skip_o], [g_out[sl], g_skip[sl]])
+            outs.append(out_o.detach()); skips.append(skip_o.detach()); gxs.append(xin.grad)
+            if sin is not None:
+                gss.append(sin.grad)
+        return P, outs, skips, gxs, gss
+    P, outs, skips, gxs, gss = oracle_block()
+    # the same oracle with its 1x1 convolutions summed in another channel order: the reference's own reassociation noise
+    with reassociated_pointwise_convs():
+        P2, outs2, _, gxs2, _ = oracle_block()
     out_o, skip_o, gx_o = torch.cat(outs), torch.cat(skips), torch.cat(gxs)
     m = {}
     for name, ours, ref, qmod in (("out", xo, out_o, model.masker.TCN[i].add), ("skip", ss, skip_o, model.masker.adds[i - 1] if i > 0 else model.masker.TCN[i].skip_conv)):
@@ -306,32 +313,48 @@ def _teacher_forced(model, i, B, seed, tag, chunk=8):
     m["gx_rel"] = rel(xg.grad, gx_o)
     if gss:
         m["gskip_in_rel"] = rel(sg.grad, torch.cat(gss))
-    worst_w, worst_r, worst_small = ("", 0.0), ("", 0.0), ("", 0.0)
-    gmax = max(float(P[pre + k].grad.abs().max()) for k, _ in model.masker.TCN[i].named_parameters() if P[pre + k].grad is not None)
-    for k, p in model.masker.TCN[i].named_parameters():
-        go = P[pre + k].grad
-        if go is None:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, (tag, k)
-            continue
-        assert p.grad is not None, (tag, k)
-        r = rel(p.grad, go)
-        m["grad/" + k] = r
-        if "range" in k:
-            if r > worst_r[1]:
-                worst_r = (k, r)
-        elif p.numel() == 1:
-            if r > worst_small[1]:
-                worst_small = (k, r)
-        elif r > worst_w[1]:
-            worst_w = (k, r)
+    m["oracle_self_out_flip_rate"] = ((torch.cat(outs2) - out_o).abs() > 0.5 * ((_q(model.masker.TCN[i].add)[1] - _q(model.masker.TCN[i].add)[0]) / 255).item()).float().mean().item()
+    m["oracle_self_gx_rel"] = rel(torch.cat(gxs2), gx_o)
+    # per parameter: our deviation from the oracle, and the oracle's deviation from its reassociated self
+    excess = ("", 0.0)
+    names = [(k, p.grad, P[pre + k].grad, P2[pre + k].grad) for k, p in model.masker.TCN[i].named_parameters()]
     if i > 0:
         ka = "masker.adds.%d.activation_fake_quantize." % (i - 1)
         q = model.masker.adds[i - 1].activation_fake_quantize
-        for nm, p in (("min_range", q.min_range), ("max_range", q.max_range)):
-            m["grad/adds." + nm] = rel(p.grad, P[ka + nm].grad)
-            worst_r = max(worst_r, ("adds." + nm, m["grad/adds." + nm]), key=lambda t: t[1])
-    m["worst_tensor_grad"], m["worst_range_grad"], m["worst_scalar_grad"] = worst_w[1], worst_r[1], worst_small[1]
-    m["worst_tensor_grad_name"], m["worst_range_grad_name"], m["worst_scalar_grad_name"] = worst_w[0], worst_r[0], worst_small[0]
+        names += [("adds." + nm, pp.grad, P[ka + nm].grad, P2[ka + nm].grad) for nm, pp in (("min_range", q.min_range), ("max_range", q.max_range))]
+    # Scalar parameters (activation ranges, PReLU slopes) are single sums over ~10^7 elements of rounding residuals /
+    # clipped gradients with heavy cancellation: the relative error of ONE such number is ill-conditioned (the oracle moves
+    # some of them by 10 % against itself).  They are judged (a) as a group -- rel-L2 over the vector of the block's scalar
+    # gradients -- and (b) each one against max(1e-2 |ref|, 3 x the oracle's own move, 1e-2 x the group's rms).
+    sc = [(k, ours, go, go2) for k, ours, go, go2 in names if go is not None and go.numel() == 1]
+    v_ours = torch.stack([o.detach().cpu().reshape(()) for _, o, _, _ in sc]).double()
+    v_ref = torch.stack([g_.reshape(()) for _, _, g_, _ in sc]).double()
+    v_ref2 = torch.stack([g_.reshape(()) for _, _, _, g_ in sc]).double()
+    m["scalar_vec_rel"], m["oracle_self_scalar_vec_rel"] = rel(v_ours, v_ref), rel(v_ref2, v_ref)
+    rms = float(v_ref.pow(2).mean().sqrt())
+    for k, ours, go, go2 in names:
+        if go is None:
+            assert ours is None or float(ours.abs().max()) == 0.0, (tag, k)
+            continue
+        assert ours is not None, (tag, k)
+        r, r_self = rel(ours, go), rel(go2, go)
+        m["grad/" + k] = r
+        m["oracle_self/" + k] = r_self
+        if go.numel() == 1:
+            err = abs(float(ours) - float(go))
+            # 3e-2: a PReLU-slope / range gradient behind a gLN is the small remainder of a projection that the gLN backward
+            # removes (its output is orthogonal to {1, xhat}); the bf16 rounding of the 512-wide gradient tensors (the
+            # documented 1e-2 tier) breaks that orthogonality at 2^-9 and the remainder sees it amplified
+            bound = max(3e-2 * abs(float(go)), 3.0 * abs(float(go2) - float(go)), 1e-2 * rms)
+            ratio = err / bound
+        else:
+            # tensors: the bf16-GEMM tier (north_star 1e-2), or 3x what the reference's own reassociation does to this tensor
+            # (per-channel weight-range gradients are sums of dWq x rounding residual over the fan-in: 2e-2)
+            ratio = r / max(2e-2 if "range" in k else 1e-2, 3.0 * r_self)
+        if ratio > excess[1]:
+            excess = (k, ratio)
+    m["worst_ratio_to_bound"], m["worst_ratio_name"] = excess[1], excess[0]
+    m["worst_tensor_grad"] = max(v for k, v in m.items() if k.startswith("grad/") and k.endswith(("conv1d.weight", "conv1d.bias", "groupnorm.weight", "groupnorm.bias")))
     record("teacher_forced/" + tag, **m)
     return m
 
@@ -343,9 +366,11 @@ def _assert_teacher_forced(m, tag):
     assert m["skip_flip_rate"] <= 1e-3 and m["skip_max_code_diff"] <= 1.01, (tag, m)
     assert m["gx_rel"] < 1e-2, (tag, m)
     assert m.get("gskip_in_rel", 0.0) < 1e-3, (tag, m)                # fp32 end to end
-    assert m["worst_tensor_grad"] < 1e-2, (tag, m)
-    assert m["worst_range_grad"] < 1e-2, (tag, m)
-    assert m["worst_scalar_grad"] < 1e-2, (tag, m)
+    assert m["worst_tensor_grad"] < 1e-2, (tag, m)                    # weights, biases, gLN affine: 1e-2 outright
+    # range / slope gradients are sums of rounding residuals and of clipped elements: +-1 code moves (which the oracle
+    # produces against ITSELF at the same rate when only its summation order changes) decide them
+    assert m["scalar_vec_rel"] <= max(1e-2, 3.0 * m["oracle_self_scalar_vec_rel"]), (tag, m["scalar_vec_rel"], m["oracle_self_scalar_vec_rel"])
+    assert m["worst_ratio_to_bound"] <= 1.0, (tag, m["worst_ratio_name"], m)
 
 
 @pytest.mark.parametrize("i", [0, 7])
