@@ -209,9 +209,14 @@ def run_ours(args):
         host.append((src.sum(1, keepdim=True).pin_memory(), src))
     dev_batches = [(m.to(dev), s.to(dev)) for m, s in host]
     # calibration: 2 observer passes, then steady state
+    from fqss_b200 import parallel as PL
     with torch.no_grad():
         for _ in range(2):
             model(dev_batches[0][0][: min(B, 4)])
+            if world > 1:       # every rank learns the ranges one process would learn from the global calibration batch
+                PL.set_global_batch_parity(True)
+                PL.sync_observer_ranges_(model)
+                PL.set_global_batch_parity(False)
     enable_observer(model, False)
     arena = ParamArena(list(model.parameters()))
     loss_host = torch.zeros(1).pin_memory()
@@ -357,7 +362,6 @@ def run_ours(args):
     # ---- data-parallel correctness: the same seeded global batch on N ranks and on rank 0 alone ----
     dp_check = None
     if (args.verify_dp == 1 or (args.verify_dp < 0 and world > 1)) and world > 1 and not args.profile_step:
-        from fqss_b200 import parallel as PL
         Gv = 8 if 8 % world == 0 else world
         g = torch.Generator().manual_seed(4242)
         src_g = (torch.randn(Gv, 2, T, generator=g) * 0.05).to(dev)
