@@ -788,10 +788,16 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
 }
 
 // F: fp64 accumulators -> fp32 outputs
-__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc) {
+__global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc, int gln_from_acc) {
     const AccLayout L(p.B, p.Cio, p.Chid);
     const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gln_from_acc && i < p.Chid) {      // the lean row kernels accumulate dgamma / dbeta here (no reduce launch)
+        g.g_gn1_b[i] = (float)acc[L.gln1 + 2 * i];
+        g.g_gn1_w[i] = (float)acc[L.gln1 + 2 * i + 1];
+        g.g_gn2_b[i] = (float)acc[L.gln2 + 2 * i];
+        g.g_gn2_w[i] = (float)acc[L.gln2 + 2 * i + 1];
+    }
     if (i < 8 && p.quant) {
         const double sD = acc[L.q + 2 * i], sZ = acc[L.q + 2 * i + 1];
         g.g_q[2 * i] = (float)(sZ - sD / 255.0);      // d/d min_range
@@ -904,22 +910,29 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (overlap) cudaEventRecord(side_event(1), sw);      // recorded even on failure: the main stream must not wait forever
     if (rc) return rc;
     // P1, R, P2
-    {
-        FQSS_PROF("tcn_gln2_bwd<1>", s);
-        static const int p1_th = tune_nq("FQSS_P1_TH", 128);
-        if (p->quant) {
-            if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
-            else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-        }
-        else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
-    }
-    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
-                                                                     acc + L.samp2); }
-    // P2 + D (one kernel; FQSS_SPLIT_P2D=1 runs the two separate kernels instead -- development / A-B knob)
     static const int split_p2d = tune_nq("FQSS_SPLIT_P2D", 0);
-    // quantised model: the instruction-lean fused kernel (tcn_rows.cuh); FQSS_LEAN_P2D=0 keeps the first version for A/B runs
-    static const int lean_p2d = tune_nq("FQSS_LEAN_P2D", 1);
-    if (p->quant && lean_p2d && !split_p2d) {
+    static const int lean_env = tune_nq("FQSS_LEAN_P2D", 1);
+    // quantised model: the instruction-lean row kernels (tcn_rows.cuh); they add their gLN sums straight into the
+    // accumulator block, so the two reduce launches disappear.  FQSS_LEAN_P2D=0 keeps the first versions for A/B runs.
+    const bool lean = p->quant && lean_env && !split_p2d;
+    if (lean) {
+        FQSS_PROF("tcn_gln2_sums", s);
+        tcn_gln2_sums_lean_kernel<128, 4><<<rows_h, 128, P1_LEAN_SMEM, s>>>(*p, *g, acc);
+    } else {
+        {
+            FQSS_PROF("tcn_gln2_bwd<1>", s);
+            static const int p1_th = tune_nq("FQSS_P1_TH", 128);
+            if (p->quant) {
+                if (p1_th == 64) tcn_gln2_sums_codes_kernel<4, 64><<<rows_h, 64, 0, s>>>(*p, *g, acc);
+                else tcn_gln2_sums_codes_kernel<4, 128><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+            }
+            else tcn_gln2_bwd_kernel<1, false, 128, 2><<<rows_h, 128, 0, s>>>(*p, *g, acc);
+        }
+        { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row2, p->B, p->Chid, p->gn2_w, g->g_gn2_w, g->g_gn2_b,
+                                                                         acc + L.samp2); }
+    }
+    // P2 + D (one kernel; FQSS_SPLIT_P2D=1 runs the two separate kernels instead -- development / A-B knob)
+    if (lean) {
         const size_t smem = p2d_lean_smem(p->ld, p->dil);
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_bwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         const int mode = dw_mode(p->dil);
@@ -1001,8 +1014,10 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
 #undef FQSS_DWB_LAUNCH
         }
     }
-    { FQSS_PROF("tcn_gln_reduce", s); tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b,
-                                                                     acc + L.samp1); }
+    if (!lean) {
+        FQSS_PROF("tcn_gln_reduce", s);
+        tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b, acc + L.samp1);
+    }
     {
         FQSS_PROF("tcn_gln1_bwd", s);
         if (p->quant) {
@@ -1031,7 +1046,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     if (rc) return rc;
     // F
     const int nf = p->Chid > n2 ? p->Chid : n2;
-    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc); }
+    { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc, lean ? 1 : 0); }
     return check_launch("tcn_block_bwd(finalize)");
 }
 

@@ -12,7 +12,7 @@ int num_sms();
 
 // fp64 accumulator block inside the workspace
 struct AccLayout {
-    int64_t q, slope, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, total;
+    int64_t q, slope, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, gln1, gln2, total;
     __host__ __device__ AccLayout(int B, int Cio, int Chid) {
         int64_t o = 0;
         q = o; o += 16;
@@ -25,6 +25,8 @@ struct AccLayout {
         row2 = o; o += 2 * (int64_t)B * Chid;
         samp1 = o; o += 2 * B;
         samp2 = o; o += 2 * B;
+        gln1 = o; o += 2 * Chid;          // {dbeta, dgamma} per channel, accumulated by the quantised row kernels (no reduce launch)
+        gln2 = o; o += 2 * Chid;
         total = o;
     }
 };

@@ -287,14 +287,110 @@ __global__ void __launch_bounds__(NTH, MINB) tcn_gln2_dw_bwd_lean_kernel(const f
         } else if (w == 2) {
             // xhat1 = (delta1*c + min1 - mu1) * rstd1 = xa * (8c) + xb
             const double xa = 0.125 * (double)h1.q1.delta * (double)h1.g.rstd, xb = ((double)h1.q1.mn - (double)h1.g.mu) * (double)h1.g.rstd;
-            acc[L.row1 + 2 * r] = x0;
-            acc[L.row1 + 2 * r + 1] = xa * (x1 - (double)tbB * x0) + xb * x0;
+            const double s3 = xa * (x1 - (double)tbB * x0) + xb * x0;      // sum gn1 * xhat1
+            const double gm = (double)h1.g.gamma;
+            atomicAdd(acc + L.samp1 + 2 * b, gm * x0);                    // per-sample gLN1 sums (no reduce launch)
+            atomicAdd(acc + L.samp1 + 2 * b + 1, gm * s3);
+            atomicAdd(acc + L.gln1 + 2 * c, x0);                           // dbeta1, dgamma1
+            atomicAdd(acc + L.gln1 + 2 * c + 1, s3);
             atomicAdd(acc + L.dbdw + c, x2);
         } else {
             atomicAdd(acc + L.dwdw + 3 * c, x0);
             atomicAdd(acc + L.dwdw + 3 * c + 1, x1);
             atomicAdd(acc + L.dwdw + 3 * c + 2, x2);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// P1 (quantised): g_a4 (bf16), code3 -> per-sample gLN2 sums, dgamma2 / dbeta2, range sums of FQ4.  Everything is a
+// function of the saved code of a3: one LDS.32 (D4', shifted by MASK_OFF where FQ4 clips) per frame; xhat3 is an FMA
+// on the float of the table address.  3 B/frame of HBM traffic, so the first trip's loads are issued before the
+// constants and the table.  dynamic shared memory: [slack to a 1 KB boundary | table 1 KB | 4 x 128 floats]
+// ---------------------------------------------------------------------------------------------
+constexpr size_t P1_LEAN_SMEM = 1024 + 1024 + 4 * 128 * sizeof(float);
+
+template <int NTH, int NQ>
+__global__ void __launch_bounds__(NTH) tcn_gln2_sums_lean_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
+    extern __shared__ __align__(16) uint8_t dsm_raw[];
+    static_assert(NTH == 128, "P1_LEAN_SMEM sizes the reduction scratch for 128 threads");
+    const AccLayout L(p.B, p.Cio, p.Chid);
+    const int64_t r = blockIdx.x;
+    const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
+    const int M = p.M;
+    const int nq = (M + 3) >> 2;
+    const uint32_t* c3 = reinterpret_cast<const uint32_t*>(p.code3 + r * p.ld);
+    const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    uint32_t cw[NQ];
+    uint2 gw[NQ];
+    auto issue = [&](int base) {
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const int v = base + k * NTH;
+            const bool ok = v < nq;
+            cw[k] = ok ? __ldg(c3 + v) : 0u;
+            gw[k] = ok ? __ldg(ga4 + v) : make_uint2(0u, 0u);
+        }
+    };
+    issue(threadIdx.x);
+    const uint32_t raw_s = smem_addr(dsm_raw);
+    const uint32_t tab_s = (raw_s + 1023u) & ~1023u;
+    float* tabD = reinterpret_cast<float*>(dsm_raw + (tab_s - raw_s));
+    float* red = tabD + 256;
+    const uint32_t tb = vreg(tab_s);
+    const Hidden3 h = load_hidden3(p, b, c);
+    for (int i = threadIdx.x; i < 256; i += NTH) {
+        const float4 e = chain_bwd_entry(h.q3, h.g, h.q4, i, false);        // {-, mask4, D4, xhat3}
+        tabD[i] = e.y != 0.f ? e.z : e.z + MASK_OFF;
+    }
+    __syncthreads();
+    // a0 = sum g*D4' (two scalar lanes), a1 = sum g*(1-m4), s2 = sum gn, scf = sum gn*(tb + 4c)
+    float a0x = 0.f, a0y = 0.f;
+    float2 a1 = f2s(0.f), s2 = f2s(0.f), scf = f2s(0.f);
+    for (int base = threadIdx.x; base < nq; base += NQ * NTH) {
+        if (base != (int)threadIdx.x) issue(base);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) {
+            const int v = base + k * NTH;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t w = j ? gw[k].y : gw[k].x;
+                float gx = bf16lo(w), gy = bf16hi(w);
+                if (4 * v + 3 >= M) {                 // ragged quad (and the zero words of quads beyond the row): no gradient at frames >= M
+                    if (4 * v + 2 * j + 1 >= M) gy = 0.f;
+                    if (4 * v + 2 * j >= M) gx = 0.f;
+                }
+                const uint32_t ax = tab_addr<2>(cw[k], 2 * j, tb), ay = tab_addr<2>(cw[k], 2 * j + 1, tb);
+                const float dx = lds32(ax), dy = lds32(ay);
+                const float2 gg = make_float2(gx, gy);
+                const float2 gn = make_float2(dx < MASK_CUT ? gx : 0.f, dy < MASK_CUT ? gy : 0.f);
+                a0x = fmaf(gx, dx, a0x);
+                a0y = fmaf(gy, dy, a0y);
+                a1 = __fadd2_rn(a1, __fadd2_rn(gg, neg2(gn)));
+                s2 = __fadd2_rn(s2, gn);
+                scf = __ffma2_rn(gn, make_float2((float)ax, (float)ay), scf);
+            }
+        }
+    }
+    const float sv[4] = {a0x + a0y, hsum(a1), hsum(s2), hsum(scf)};
+    float t1[1];
+    block_sums_t<NTH, 4>(sv, red, t1);
+    // every warp now holds ONE of the four totals in lane 0; combine through shared memory
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t1[0];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double x0 = (double)red[0], x1 = (double)red[1], x2 = (double)red[2], x3 = (double)red[3];
+        atomicAdd(acc + L.q + 2 * Q4, x0 - (double)MASK_OFF * x1);
+        atomicAdd(acc + L.q + 2 * Q4 + 1, x1);
+        // xhat3 = (delta3*c + min3 - mu) * rstd = xa * (4c) + xb
+        const double xa = 0.25 * (double)h.q3.delta * (double)h.g.rstd, xb = ((double)h.q3.mn - (double)h.g.mu) * (double)h.g.rstd;
+        const double s3 = xa * (x3 - (double)tb * x2) + xb * x2;
+        const double gm = (double)h.g.gamma;
+        atomicAdd(acc + L.samp2 + 2 * b, gm * x2);
+        atomicAdd(acc + L.samp2 + 2 * b + 1, gm * s3);
+        atomicAdd(acc + L.gln2 + 2 * c, x2);
+        atomicAdd(acc + L.gln2 + 2 * c + 1, s3);
     }
 }
 

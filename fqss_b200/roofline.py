@@ -77,6 +77,7 @@ def algorithmic_bytes(B, M, Cio=128, Chid=512):
         "tcn_tail_bwd": 4 * I * 6 + 4 * I * 2 + 2 * I * 2,      # g_x, g_skip, res_y, skip_y, x_in, skip_in -> g_xd, g_skip_in, dY2
         "gemm_dgrad_bf16": 2 * 2 * I + w2 + 2 * H,              # dY2 in, g_a4 bf16 out
         "tcn_gln2_bwd<1>": H + 2 * H,                           # code3 (u8), g_a4 (bf16) in (sums out)
+        "tcn_gln2_sums": H + 2 * H,                             # same pass, instruction-lean kernel (tcn_rows.cuh)
         "tcn_gln2_bwd<2>": 4 * H + 2 * H + 2 * H,               # y3, g_a4 in, g_y3 bf16 out
         "tcn_gln2_dw_bwd": 4 * H + 2 * H + H + H + 2 * H,       # y3, g_a4 (bf16), code3, code1 (u8) in, g_n1 bf16 out (fused P2 + D)
         "tcn_dw_bwd": H + 2 * H + 2 * H,                        # code1 (u8), g_y3 in, g_n1 bf16 out
