@@ -108,6 +108,11 @@ _SIGS = {
     "fqss_prof_enable": (i32, [i32]),
     "fqss_prof_reset": (i32, []),
     "fqss_prof_nslots": (i32, []),
+    "fqss_split_ex": (i32, [vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, i32, vp]),
+    "fqss_cln_fwd": (i32, [vp, i64, vp, vp, f32, vp, i64, vp, vp, i32, i32, i32, vp]),
+    "fqss_cln_bwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, i32, i32, i32, vp, sz, vp]),
+    "fqss_ola_fwd": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, vp]),
+    "fqss_ola_bwd": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, vp]),
     "fqss_prof_read": (i32, [i32, C.c_char_p, i32, C.POINTER(f64), C.POINTER(i64), C.POINTER(i64)]),
     "fqss_launch_count": (i64, []),
 }

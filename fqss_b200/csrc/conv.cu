@@ -211,7 +211,7 @@ __global__ void dwconv_finalize_kernel(const double* __restrict__ acc, float* gw
 //   block = 128 frames x SC_OT output channels; weights broadcast from shared memory
 // =============================================================================================
 constexpr int SC_OT = 32;
-constexpr int SC_MAXCK = 64;     // Cin*K <= 64 (2 x 16 in the recipe)
+constexpr int SC_MAXCK = 96;     // Cin*K <= 96 (2 x 16 in the speech recipe, 4 x 20 in the music model)
 
 __global__ void __launch_bounds__(128) sconv_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                        float* __restrict__ y, int64_t ldy, int Cin, int Co, int Mo, int K,

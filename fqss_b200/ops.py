@@ -425,23 +425,93 @@ class TransposedConv1(Function):
 # =============================================================================================
 # P1: splitter / reconstructor
 # =============================================================================================
-def split_input(x, n_split, n_bits=8):
-    """process.preprocess for n_splitter >= 2: [B,1,T] -> [B,n_split,T] (no gradient: model input)."""
+def split_input(x, n_split, n_bits=8, normalize=True):
+    """process.preprocess for n_splitter >= 2: [B,C,T] -> [B,n_split*C,T] (no gradient: model input).
+    normalize=True: x / max|x| with threshold 1 (the speech recipe, process.py:23-24); False: threshold = max|x|
+    (ConvTasNetMusicQ.pre_process, convtasnetq_music.py:233-234)."""
     N.require_cuda(x)
     if x.dim() == 2:
         x = x.unsqueeze(1)
-    if x.dim() != 3 or x.shape[1] != 1:
-        raise N.FqssError("splitter expects [B,T] or [B,1,T] (mono), got %s" % (tuple(x.shape),))
+    if x.dim() != 3:
+        raise N.FqssError("splitter expects [B,T] or [B,C,T], got %s" % (tuple(x.shape),))
     x, rows, T, ldx = rows_view(x.detach())
-    B = x.shape[0]
+    B, Cc = x.shape[0], x.shape[1]
     peak = torch.empty(1, device=x.device)
     ws = workspace(rows, x.device)
     check(lib().fqss_absmax(ptr(x), rows, T, ldx, ptr(peak), ptr(ws), ws.numel(), stream_ptr()))
     from . import parallel          # data-parallel runs with global-batch parity: one peak over ALL shards (SURVEY 8e)
     parallel.sync_splitter_peak_(peak)
-    y = alloc_rows((B, n_split, T), x.device)
-    check(lib().fqss_split(ptr(x), ldx, ptr(peak), ptr(y), ld_of(y), B, T, n_split, n_bits, stream_ptr()))
+    y = alloc_rows((B, n_split * Cc, T), x.device)
+    if Cc == 1 and normalize:
+        check(lib().fqss_split(ptr(x), ldx, ptr(peak), ptr(y), ld_of(y), B, T, n_split, n_bits, stream_ptr()))
+    else:
+        check(lib().fqss_split_ex(ptr(x), ldx, ptr(peak), ptr(y), ld_of(y), B, Cc, T, n_split, n_bits, int(bool(normalize)),
+                                  stream_ptr()))
     return y
+
+
+class ChannelLayerNorm(Function):
+    """nn.LayerNorm(C) over the CHANNEL axis of an NCL tensor, per frame (ChannelWiseLayerNorm,
+    convtasnetq_music.py:32-50): y[b,c,m] = (x - mean_bm) * rstd_bm * gamma_c + beta_c."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        N.require_cuda(x, gamma, beta)
+        if x.dim() != 3:
+            raise N.FqssError("channel layer norm expects [B,C,M]")
+        x, rows, M, ld = rows_view(x)
+        B, Cc = x.shape[0], x.shape[1]
+        y = alloc_rows(x.shape, x.device)
+        mean, rstd = torch.empty((B, M), device=x.device), torch.empty((B, M), device=x.device)
+        g_, b_ = gamma.detach().contiguous(), beta.detach().contiguous()
+        check(lib().fqss_cln_fwd(ptr(x), ld, ptr(g_), ptr(b_), float(eps), ptr(y), ld_of(y), ptr(mean), ptr(rstd), B, Cc, M,
+                                 stream_ptr()))
+        ctx.save_for_backward(x, g_, mean, rstd)
+        ctx.meta = (B, Cc, M, ld)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        B, Cc, M, ld = ctx.meta
+        g, _, _, ldg = rows_view(g)
+        gx = alloc_rows(x.shape, x.device) if ctx.needs_input_grad[0] else None
+        want_aff = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        gg = torch.empty(Cc, device=x.device) if want_aff else None
+        gb = torch.empty(Cc, device=x.device) if want_aff else None
+        ws = workspace(Cc, x.device)
+        check(lib().fqss_cln_bwd(ptr(g), ldg, ptr(x), ld, ptr(gamma), ptr(mean), ptr(rstd), ptr(gx) or None,
+                                 ld_of(gx) if gx is not None else 0, ptr(gg) or None, ptr(gb) or None, B, Cc, M, ptr(ws), ws.numel(),
+                                 stream_ptr()))
+        return gx, gg, gb, None
+
+
+class OverlapAdd(Function):
+    """overlap_and_add (convtasnetq_music.py:10-30) of Linear-decoder outputs kept channels-first:
+    y [..., A*L, K] (row (a, j) = sample j of audio channel a, column k = frame) -> [..., A, (K-1)*H + L]."""
+
+    @staticmethod
+    def forward(ctx, y, A, L, H):
+        N.require_cuda(y)
+        y, rows, K, ldy = rows_view(y)
+        if y.shape[-2] != A * L:
+            raise N.FqssError("overlap_add: expected %d rows per item, got %d" % (A * L, y.shape[-2]))
+        R = rows // (A * L)
+        T = (K - 1) * H + L
+        out = alloc_rows(tuple(y.shape[:-2]) + (A, T), y.device)
+        check(lib().fqss_ola_fwd(ptr(y), ldy, ptr(out), ld_of(out), R, A, L, H, K, stream_ptr()))
+        ctx.meta = (tuple(y.shape), R, A, L, H, K)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        shape, R, A, L, H, K = ctx.meta
+        g, _, _, ldo = rows_view(g)
+        gy = alloc_rows(shape, g.device)
+        check(lib().fqss_ola_bwd(ptr(g), ldo, ptr(gy), ld_of(gy), R, A, L, H, K, stream_ptr()))
+        return gy, None, None, None
 
 
 class Combine(Function):

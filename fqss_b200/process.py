@@ -20,9 +20,9 @@ def preprocess(x, n_splitter=1, n_bits=8, sign=True, normalize=True):
     if x.dim() == 2:
         x = x.unsqueeze(1)
     if n_splitter > 1:
-        if not (sign and normalize):
-            raise NotImplementedError("splitter kernel implements the recipe's signed, normalised mode")
-        return ops.split_input(x, n_splitter, n_bits)
+        if not sign:
+            raise NotImplementedError("splitter kernel implements the recipes' signed mode")
+        return ops.split_input(x, n_splitter, n_bits, normalize=normalize)
     return x
 
 

@@ -1,10 +1,11 @@
-"""B200 mirror of `quantization/qat/models/load_model.py` restricted to the ConvTasNet recipe
+"""B200 mirror of `quantization/qat/models/load_model.py` restricted to the ConvTasNet recipes (speech and music)
 (create_model :21-51, quantize_model :53-74, enable_observer :16-19, create_pretrained_model :76-102)."""
 import torch
 
 from ..qat_layers import LayerQ
 from ..qat_quant import GradientActivationFakeQuantize, GradientWeightFakeQuantize
 from .convtasnetq import ConvTasNetQ
+from .convtasnetq_music import ConvTasNetMusicQ
 
 
 def set_mac_op(model, mode=False):
@@ -21,10 +22,13 @@ def enable_observer(model, mode=False):
 
 def create_model(model_cfg):
     name = model_cfg["name"]
-    if name != "ConvTasNet":
-        raise NotImplementedError("fqss_b200 covers the ConvTasNet recipe; model %r is out of scope" % name)
-    return ConvTasNetQ(n_spks=model_cfg.get("n_src", 1), kernel_size=model_cfg.get("kernel_size", 32),
-                       stride=model_cfg.get("stride", 16))
+    if name == "ConvTasNet":
+        return ConvTasNetQ(n_spks=model_cfg.get("n_src", 1), kernel_size=model_cfg.get("kernel_size", 32),
+                           stride=model_cfg.get("stride", 16))
+    if name == "ConvTasNetMusic":
+        return ConvTasNetMusicQ(sources=model_cfg.get("sources", ["drums", "bass", "other", "vocals"]),
+                                kernel=model_cfg.get("kernel_size", 20), stride=model_cfg.get("stride", 10))
+    raise NotImplementedError("fqss_b200 covers the ConvTasNet recipes (speech, music); model %r is out of scope" % name)
 
 
 def quantize_model(model, quant_cfg):

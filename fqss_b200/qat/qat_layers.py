@@ -183,6 +183,29 @@ class GroupNormQ(LayerQ):
         return self._finish(N.PW_GLN, x, gamma=gn.weight, beta=gn.bias, eps=gn.eps)
 
 
+class LayerNormQ(LayerQ):
+    """nn.LayerNorm + FQ (qat_layers.py:455-468).  The one use on the scoped paths is ConvTasNetMusicQ's channel-wise cLN
+    (convtasnetq_music.py:32-50): the module is handed `x.transpose(1, 2)` of an NCL tensor and normalises its last axis =
+    the channels of every frame.  The kernel works on the NCL tensor itself (threads along frames), so the transposes stay
+    views."""
+
+    def __init__(self, layernorm, gradient_based=True, act_quant=True, act_n_bits=8):
+        super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
+        if not isinstance(layernorm, nn.LayerNorm):
+            raise Exception("LayerNormQ wraps LayerNorm, got %s" % type(layernorm))
+        self.layernorm = layernorm
+
+    def forward(self, x):
+        ln = self.layernorm
+        if len(ln.normalized_shape) != 1 or not ln.elementwise_affine or ln.bias is None or x.dim() != 3 \
+                or x.shape[-1] != ln.normalized_shape[0]:
+            raise NotImplementedError("LayerNormQ: only LayerNorm(C) over the last axis of [B, M, C] (channel-wise cLN) has a kernel")
+        if self.do_mac_op:
+            self.mac_op = 2 * x.numel()
+        y = ops.ChannelLayerNorm.apply(x.transpose(1, 2), ln.weight, ln.bias, ln.eps)      # [B, C, M]
+        return self._finish(N.PW_IDENT, y).transpose(1, 2)
+
+
 class NlQ(LayerQ):
     def __init__(self, nl, gradient_based=True, act_quant=True, act_n_bits=8):
         super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_n_bits=act_n_bits)
@@ -244,15 +267,23 @@ class ResidualErrorBlock(LayerQ):
                  weight_n_bits=8, train_res_dec=False):
         super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_nl_quantizer=act_nl_quantizer,
                          act_n_bits=act_n_bits)
-        if type(decoder) is not nn.ConvTranspose1d or train_res_dec:
-            raise NotImplementedError("RQB is implemented for the ConvTranspose1d decoder without train_res_dec")
-        if decoder.bias is not None or decoder.padding[0] or decoder.output_padding[0] or decoder.dilation[0] != 1:
+        if train_res_dec or decoder.bias is not None:
+            raise NotImplementedError("RQB is implemented for bias-free decoders without train_res_dec")
+        self.train_res_dec = train_res_dec
+        self.decoder_bias = None
+        if type(decoder) is nn.Linear:       # ConvTasNetMusicQ: per-frame Linear decoder (qat_layers.py:1110-1121)
+            self.decoder_type = nn.Linear
+            self.residual_encoder = nn.Linear(decoder.out_features, decoder.in_features, bias=False).to(decoder.weight.device)
+            self.weight_fake_quantize = (get_weight_quantizer(gradient_based, self.residual_encoder.weight.shape,
+                                                              n_bits=weight_n_bits) if weight_quant else nn.Identity())
+            return
+        if type(decoder) is not nn.ConvTranspose1d:
+            raise NotImplementedError("RQB is implemented for ConvTranspose1d and Linear decoders")
+        if decoder.padding[0] or decoder.output_padding[0] or decoder.dilation[0] != 1:
             raise NotImplementedError("decoder geometry not on the ConvTasNet path")
         self.decoder_type = nn.ConvTranspose1d
-        self.train_res_dec = train_res_dec
         self.residual_encoder = nn.Conv1d(decoder.out_channels, decoder.in_channels, decoder.kernel_size,
                                           stride=decoder.stride, bias=False).to(decoder.weight.device)
-        self.decoder_bias = None
         self.decoder_kernel, self.decoder_stride = decoder.kernel_size, decoder.stride
         self.decoder_padding, self.decoder_output_padding = decoder.padding, decoder.output_padding
         self.decoder_dilation, self.decoder_groups = decoder.dilation, decoder.groups
@@ -261,6 +292,11 @@ class ResidualErrorBlock(LayerQ):
                                                           n_bits=weight_n_bits) if weight_quant else nn.Identity())
 
     def forward(self, Y, y_q, w_decoder):
+        if self.decoder_type is nn.Linear:
+            # channels-first: Y [R, N, K] features, y_q [R, F, K] quantised decoder output; the Linear layers are 1x1 convs
+            Yq = ops.Conv1x1.apply(y_q, self.weight_fake_quantize(self.residual_encoder.weight).unsqueeze(-1), None)
+            Y1 = self._finish(N.PW_SUB, Y, Yq)
+            return ops.Conv1x1.apply(Y1, w_decoder.unsqueeze(-1), None)
         Yq = ops.StridedConv.apply(y_q, self.weight_fake_quantize(self.residual_encoder.weight), self.decoder_stride[0])
         Y1 = self._finish(N.PW_SUB, Y, Yq)
         return ops.TransposedConv1.apply(Y1, w_decoder, self.decoder_stride[0])
@@ -304,6 +340,54 @@ class ConvTr1dDecoderQ(LayerQ):
             y = self._finish(N.PW_IDENT, x, quantizer=self.activation_fake_quantize_residual)
             outs.append(y)
         return torch.stack(outs)
+
+
+class LinearDecoderQ(LayerQ):
+    """Per-frame nn.Linear decoder + out-FQ (+ RQB) of ConvTasNetMusicQ (qat_layers.py:1256-1302).  `forward` keeps the
+    reference's contract ([..., K, N] -> [n_combiner, ..., K, F]); the arithmetic runs channels-first (`forward_ncl`:
+    [R, N, K] -> [n_combiner, R, F, K]), where the Linear layers are 1x1 convolutions and every transpose is a view."""
+
+    def __init__(self, decoder, n_combiner=1, gradient_based=True, weight_quant=True, weight_n_bits=8, act_quant=True,
+                 inout_nl_quant=False, act_n_bits=8, out_quant=True, out_act_n_bits=8, train_res_dec=False):
+        super().__init__(gradient_based=gradient_based, weight_quant=weight_quant, act_quant=out_quant,
+                         act_nl_quantizer=inout_nl_quant, weight_shape=decoder[0].weight.shape,
+                         act_n_bits=out_act_n_bits, weight_n_bits=weight_n_bits)
+        if not isinstance(decoder[0], nn.Linear):
+            raise Exception("LinearDecoderQ wraps Linear, got %s" % type(decoder[0]))
+        if decoder[0].bias is not None:
+            raise NotImplementedError("decoder bias is not on the ConvTasNetMusic path")
+        self.linear = decoder[0]
+        self.n_combiner = n_combiner
+        if self.n_combiner >= 2:
+            self.residual_error_block = ResidualErrorBlock(self.linear, gradient_based, weight_quant, act_quant,
+                                                           act_n_bits=act_n_bits, weight_n_bits=weight_n_bits,
+                                                           train_res_dec=train_res_dec)
+            self.activation_fake_quantize_residual = (get_activation_quantizer(gradient_based, n_bits=out_act_n_bits)
+                                                      if out_quant else nn.Identity())
+
+    def forward_ncl(self, x):
+        w_dec = self.weight_fake_quantize(self.linear.weight)
+        x_dec = x
+        if self.n_combiner >= 2:      # x also feeds the residual block: sum the two gradients in the library
+            x_dec, x = ops.fanout2(x)
+        y = self._finish(N.PW_IDENT, ops.Conv1x1.apply(x_dec, w_dec.unsqueeze(-1), None))
+        if self.do_mac_op:
+            self.mac_op = x.numel() * w_dec.shape[0]
+        if self.n_combiner == 1:
+            return y.unsqueeze(0)
+        outs = [y]
+        for _ in range(1, self.n_combiner):
+            x = self.residual_error_block(x, y, w_dec)
+            y = self._finish(N.PW_IDENT, x, quantizer=self.activation_fake_quantize_residual)
+            outs.append(y)
+        return torch.stack(outs)
+
+    def forward(self, x):
+        lead = x.shape[:-2]
+        K, Nf = x.shape[-2], x.shape[-1]
+        out = self.forward_ncl(x.transpose(-1, -2).reshape(-1, Nf, K))           # [n, R, F, K]
+        out = out.reshape((out.shape[0],) + tuple(lead) + (out.shape[-2], K)).transpose(-1, -2)
+        return out if self.n_combiner >= 2 else out[0]
 
 
 # reference names outside the ConvTasNet hot path (imported by the reference's other model files): importable placeholders

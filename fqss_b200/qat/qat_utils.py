@@ -84,7 +84,17 @@ def quant_decoderq(decoder, p):
                                    act_quant=p.get("act_quant", True), act_n_bits=p.get("act_n_bits", 8),
                                    inout_nl_quant=p.get("inout_nl_quant", False), out_quant=p.get("out_quant", True),
                                    out_act_n_bits=p.get("out_act_n_bits", 8))
-    raise NotImplementedError("decoder type %s is out of scope (ConvTasNet ConvTranspose1d decoder only)" % type(decoder[0]).__name__)
+    if isinstance(decoder[0], nn.Linear):
+        return QL.LinearDecoderQ(decoder, n_combiner=p.get("n_combiner", 1), gradient_based=p.get("gradient_based", True),
+                                 weight_quant=p.get("weight_quant", True), weight_n_bits=p.get("weight_n_bits", 8),
+                                 act_quant=p.get("act_quant", True), act_n_bits=p.get("act_n_bits", 8),
+                                 inout_nl_quant=p.get("inout_nl_quant", False), out_quant=p.get("out_quant", True),
+                                 out_act_n_bits=p.get("out_act_n_bits", 8), train_res_dec=p.get("train_res_dec", False))
+    raise NotImplementedError("decoder type %s is out of scope (ConvTranspose1d and Linear decoders only)" % type(decoder[0]).__name__)
+
+
+def quant_layernorm(layernorm, p):
+    return QL.LayerNormQ(layernorm, **_common(p))
 
 
 OP_LIST_TO_QUANTIZE_METHOD = {
@@ -92,6 +102,7 @@ OP_LIST_TO_QUANTIZE_METHOD = {
     (nn.Conv1d, nn.PReLU): quant_conv1d_nl,
     (nn.Conv1d, nn.ReLU): quant_conv1d_nl,
     (nn.GroupNorm): quant_groupnorm,
+    (nn.LayerNorm): quant_layernorm,
     (nn.PReLU): quant_nl,
     (nn.ReLU): quant_nl,
     (QL.Add): quant_add,

@@ -360,6 +360,25 @@ int fqss_loss_grad_apply(const float* est, int64_t lde, const float* fest, int64
                          int T, const float* coef, float* gest, int64_t ldg, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * ConvTasNetMusicQ: the pieces beyond the speech path
+ *   fqss_split_ex: process.preprocess for C input channels, normalize = 1 (x / peak, threshold 1; the speech recipe) or 0
+ *     (threshold = peak; convtasnetq_music.py:233-234); y[b, s*C + c, :] = s-th part of channel c (process.py:16-36)
+ *   fqss_cln_fwd/bwd: channel-wise LayerNorm = nn.LayerNorm(C) over the channel axis of [B, C, M] per frame
+ *     (ChannelWiseLayerNorm, convtasnetq_music.py:32-50; LayerNormQ, qat_layers.py:455-468); mean / rstd: [B, M]
+ *   fqss_ola_fwd/bwd: overlap_and_add (convtasnetq_music.py:10-30) of rows [R, A*L, K] (Linear-decoder outputs, frame k in
+ *     column k) to [R, A, (K-1)*H + L]
+ * ------------------------------------------------------------------------------------------- */
+int fqss_split_ex(const float* x, int64_t ldx, const float* peak, float* y, int64_t ldy, int B, int C, int T, int n_split,
+                  int n_bits, int normalize, void* stream);
+int fqss_cln_fwd(const float* x, int64_t ld, const float* gamma, const float* beta, float eps, float* y, int64_t ldy,
+                 float* mean, float* rstd, int B, int C, int M, void* stream);
+int fqss_cln_bwd(const float* g, int64_t ldg, const float* x, int64_t ld, const float* gamma, const float* mean,
+                 const float* rstd, float* gx, int64_t ldgx, float* ggamma, float* gbeta, int B, int C, int M,
+                 void* ws, size_t ws_bytes, void* stream);
+int fqss_ola_fwd(const float* y, int64_t ldy, float* out, int64_t ldo, int64_t R, int A, int L, int H, int K, void* stream);
+int fqss_ola_bwd(const float* gout, int64_t ldo, float* gy, int64_t ldy, int64_t R, int A, int L, int H, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * D1  flat gradient arena helpers for the data-parallel exchange (asteroid_librimix_trainer.py:125-135)
  *   sumsq[0] = sum g^2 (for the global-norm clip, gradient_clip_val=5.0)
  *   scale_clip: g *= pre_scale * min(1, max_norm / (sqrt(sumsq*pre_scale^2) + 1e-6))
