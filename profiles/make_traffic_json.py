@@ -14,7 +14,8 @@ CLASS = [  # (regex on the demangled kernel name, kernel class used by csrc/prof
     (r"tcn_dw_fwd_kernel<\(?(bool\))?(1|true)", "tcn_dw_fwd"), (r"tcn_dw_fwd_kernel<\(?(bool\))?(0|false)", "tcn_dw_fwd(float)"),
     (r"tcn_hidden_fq_kernel<\(?(bool\))?(1|true)", "tcn_hidden_fq"), (r"tcn_hidden_fq_kernel<\(?(bool\))?(0|false)", "tcn_hidden_fq(float)"),
     (r"tcn_tail_bwd_kernel", "tcn_tail_bwd"), (r"tcn_gln2_bwd_kernel<\(?(int\))?1", "tcn_gln2_bwd<1>"),
-    (r"tcn_gln2_sums_codes_kernel", "tcn_gln2_bwd<1>"), (r"tcn_gln2_dw_bwd_kernel", "tcn_gln2_dw_bwd"),
+    (r"tcn_gln2_sums_codes_kernel", "tcn_gln2_bwd<1>"), (r"tcn_gln2_sums_lean_kernel", "tcn_gln2_sums"),
+    (r"tcn_gln2_dw_bwd(_lean)?_kernel", "tcn_gln2_dw_bwd"),
     (r"tcn_gln2_bwd_kernel<\(?(int\))?2", "tcn_gln2_bwd<2>"), (r"tcn_dw_bwd_kernel", "tcn_dw_bwd"), (r"tcn_gln1_bwd_kernel", "tcn_gln1_bwd"),
     (r"pw_gemm_kernel<\(?(int\))?\d+, \(?(int\))?1[,>]", "gemm_expand"), (r"pw_gemm_kernel<\(?(int\))?\d+, \(?(int\))?2[,>]", "gemm_resskip"),
     (r"pw_gemm_kernel<\(?(int\))?\d+, \(?(int\))?3[,>]", "gemm_dgrad_bf16"), (r"pw_gemm_kernel<\(?(int\))?\d+, \(?(int\))?4[,>]", "gemm_dgrad_add"),
