@@ -6,11 +6,13 @@
 // {64 frames x rows} with 128B swizzle feed the MMA directly.  The output is tiny (<= 256x512) and
 // the reduction is long (B*M ~ 128K), so the work is split along K: every CTA owns a contiguous range
 // of 64-frame chunks, keeps a [MT*128] x [NW] fp32 accumulator in TMEM (MT*NW <= 512 columns) for the
-// whole range and writes ONE partial tile at the end; a small second kernel reduces the partials
-// deterministically and applies the de-quantisation affine:
+// whole range and writes ONE partial tile at the end; after a grid-wide barrier (the grid is co-resident) the same kernel
+// reduces the partials deterministically (split order), every CTA one slice, and applies the de-quantisation affine:
 //   dWq[o,i] = (da * G[o,i]) / dws[o] + min_a * db[o]
 // (X holds integer codes c with x = da*c + min_a; dY was pre-scaled by dws[o] for the dgrad GEMM).
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "fqss_common.cuh"
 #include "tc_common.cuh"
@@ -44,34 +46,47 @@ static EncodeTiledFn encode_tiled() {
 }
 
 struct __align__(8) Bars {
-    uint64_t full[4];
-    uint64_t empty[4];
+    uint64_t full[8];
+    uint64_t empty[8];
     uint64_t done;
     uint32_t tmem_base;
 };
 
 template <int MT, int NW>
 __host__ __device__ constexpr int stage_bytes() { return (MT * 128 + NW) * BKF * 2; }
+// as many stages as fit ~208 KB (one CTA per SM): the loop is latency-bound, not tensor-bound, so what counts is the number
+// of bytes in flight per SM (ncu r01e: 2-3 stages of 64-80 KB left the TMA pipeline starved, dram 47 %)
+template <int MT, int NW, int OCC = 1>
+__host__ __device__ constexpr int num_stages() {
+    return (208 * 1024 / OCC) / stage_bytes<MT, NW>() > 8 ? 8 : (208 * 1024 / OCC) / stage_bytes<MT, NW>();
+}
 template <int MT, int NW>
-__host__ __device__ constexpr int num_stages() { return stage_bytes<MT, NW>() > 72 * 1024 ? 2 : 3; }
-template <int MT, int NW>
-__host__ __device__ constexpr int smem_bytes() { return num_stages<MT, NW>() * stage_bytes<MT, NW>() + (int)sizeof(Bars) + 1024; }
+__host__ __device__ constexpr uint32_t tmem_cols() { return MT * NW <= 128 ? 128u : (MT * NW <= 256 ? 256u : 512u); }
+template <int MT, int NW, int OCC = 1>
+__host__ __device__ constexpr int smem_bytes() { return num_stages<MT, NW, OCC>() * stage_bytes<MT, NW>() + (int)sizeof(Bars) + 1024; }
 
 struct KArgs {
     int B, M, O, I;           // O rows of dY, I rows of X
     int chunks_per_sample;    // ceil(M / 64)
     int nsplit;               // gridDim.x
     float* part;              // [nsplit][O][I]
+    // fused finalisation (after a grid-wide barrier every CTA reduces its slice of the partial tiles in split order)
+    unsigned int* ctr;        // zeroed arrival counter
+    const float* amin;
+    const float* amax;
+    const float* dws;
+    const double* db;
+    float* dWq;
 };
 
-template <int MT, int NW>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int MT, int NW, int OCC>
+__global__ void __launch_bounds__(NUM_THREADS, OCC)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const KArgs p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by POINTER arithmetic on the shared array: the compiler keeps the address space, so reads of the
     // per-channel constants below are LDS (an integer round trip would turn every one of them into a generic load)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr int ST = num_stages<MT, NW>();
+    constexpr int ST = num_stages<MT, NW, OCC>();
     constexpr int SB = stage_bytes<MT, NW>();
     Bars* bar = reinterpret_cast<Bars*>(smem + ST * SB);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +111,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
         mbar_init(&bar->done, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(&bar->tmem_base, 512);
+    if (warp == 2) tmem_alloc(&bar->tmem_base, tmem_cols<MT, NW>());
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -173,26 +188,48 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CU
     __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, tmem_cols<MT, NW>());
     }
-}
-
-// dWq[o,i] = (da * sum_p part[p][o][i]) / dws[o] + min_a * db[o]
-__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ part, int nsplit, int O, int I,
-                                                            const float* __restrict__ amin, const float* __restrict__ amax,
-                                                            const float* __restrict__ dws, const double* __restrict__ db,
-                                                            float* __restrict__ dWq) {
-    const int64_t n = (int64_t)O * I;
-    float da = 1.f, mn = 0.f;
-    if (amin) {
-        mn = __ldg(amin);
-        da = __fdiv_rn(__fsub_rn(__ldg(amax), mn), 255.f);
+    // ---- grid-wide barrier (all CTAs are co-resident: the grid never exceeds OCC CTAs per SM), then the deterministic
+    // reduction of the partial tiles, distributed over the whole grid:
+    //   dWq[o,i] = (da * sum_s part[s][o][i]) / dws[o] + min_a * db[o]          (summed in split order s = 0, 1, ...)
+    const unsigned int nctas = gridDim.x * gridDim.y;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(p.ctr, 1u);
+        unsigned int seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.ctr) : "memory");
+            if (seen < nctas) __nanosleep(100);
+        } while (seen < nctas);
+        __threadfence();
     }
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        const int o = (int)(e / I);
-        float acc = 0.f;
-        for (int s = 0; s < nsplit; ++s) acc += __ldg(part + (int64_t)s * n + e);
-        dWq[e] = (da * acc) / __ldg(dws + o) + mn * (float)db[o];
+    __syncthreads();
+    {
+        const int64_t n = (int64_t)p.O * p.I;
+        const int64_t nq = n >> 2;                              // float4 quads (I is a multiple of 128)
+        float da = 1.f, mn = 0.f;
+        if (p.amin) {
+            mn = __ldg(p.amin);
+            da = __fdiv_rn(__fsub_rn(__ldg(p.amax), mn), 255.f);
+        }
+        const int64_t cta = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        for (int64_t qd = cta * NUM_THREADS + threadIdx.x; qd < nq; qd += (int64_t)nctas * NUM_THREADS) {
+            const int64_t e = qd << 2;
+            const int o = (int)(e / p.I);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int sp = 0; sp < p.nsplit; ++sp) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part + (int64_t)sp * n + e));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const float ds = __ldg(p.dws + o), zb = mn * (float)p.db[o];
+            float4 r;
+            r.x = (da * acc.x) / ds + zb;
+            r.y = (da * acc.y) / ds + zb;
+            r.z = (da * acc.z) / ds + zb;
+            r.w = (da * acc.w) / ds + zb;
+            *reinterpret_cast<float4*>(p.dWq + e) = r;
+        }
     }
 }
 
@@ -209,12 +246,12 @@ static int make_map(CUtensorMap* tm, const void* base, int B, int C, int M, int6
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int MT, int NW>
+template <int MT, int NW, int OCC = 1>
 static int launch(const CUtensorMap& ty, const CUtensorMap& tx, const KArgs& a, int gy, cudaStream_t s) {
     static bool configured = false;
-    constexpr int smem = smem_bytes<MT, NW>();
+    constexpr int smem = smem_bytes<MT, NW, OCC>();
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<MT, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<MT, NW, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) {
             set_error("wgrad: cannot set %d B dynamic smem: %s", smem, cudaGetErrorString(e));
             return -4;
@@ -222,41 +259,72 @@ static int launch(const CUtensorMap& ty, const CUtensorMap& tx, const KArgs& a, 
         configured = true;
     }
     FQSS_PROF("wgrad", s);
-    wgrad_kernel<MT, NW><<<dim3(a.nsplit, gy), NUM_THREADS, smem, s>>>(ty, tx, a);
+    wgrad_kernel<MT, NW, OCC><<<dim3(a.nsplit, gy), NUM_THREADS, smem, s>>>(ty, tx, a);
     return check_launch("wgrad");
 }
 
-int plan_splits(int B, int M, int O, int I) {
-    const int NW = I >= 256 ? 256 : 128;
+// tile shape per CTA: MT 128-row blocks of dY x NW rows of X.  Smaller tiles = smaller stages = more stages (bytes) in flight.
+// FQSS_WGRAD_CFG (development knob): 0 = the round-1 shapes (largest tile that fits TMEM), 1 = <2,128> / <2,128>,
+// 2 = <2,128> / <1,256>, 3 (default, measured best: 52 / 62 us vs 71 / 77 for cfg 0) = <1,128> everywhere with 6 stages,
+// 4 = <1,128> with two CTAs per SM (3 stages each; slower).
+static void pick_tile(int O, int I, int* MT, int* NW, int* OCC) {
+    static const int cfg = getenv("FQSS_WGRAD_CFG") ? atoi(getenv("FQSS_WGRAD_CFG")) : 3;
     const int ot = O / 128;
-    const int MT = (ot >= 4 && NW == 128) ? 4 : (ot >= 2 ? 2 : 1);
-    const int gy = (ot / MT) * (I / NW);
-    int ns = num_sms() / gy;
+    *OCC = 1;
+    if (cfg == 4) {
+        *NW = 128;
+        *MT = 1;
+        *OCC = 2;
+        return;
+    }
+    if (cfg == 0) {
+        *NW = I >= 256 ? 256 : 128;
+        *MT = (ot >= 4 && *NW == 128) ? 4 : (ot >= 2 ? 2 : 1);
+    } else if (cfg == 3) {
+        *NW = 128;
+        *MT = 1;
+    } else if (cfg == 2 && I >= 256 && I > O) {
+        *NW = 256;
+        *MT = 1;
+    } else {
+        *NW = 128;
+        *MT = ot >= 2 ? 2 : 1;
+    }
+}
+
+int plan_splits(int B, int M, int O, int I) {
+    int MT, NW, OCC;
+    pick_tile(O, I, &MT, &NW, &OCC);
+    const int gy = (O / 128 / MT) * (I / NW);
+    int ns = OCC * num_sms() / gy;
     const int total = B * ((M + BKF - 1) / BKF);
     if (ns > total) ns = total;
     if (ns < 1) ns = 1;
     return ns;
 }
 
-size_t part_bytes(int B, int M, int O, int I) { return (size_t)plan_splits(B, M, O, I) * O * I * sizeof(float); }
+size_t part_bytes(int B, int M, int O, int I) { return (size_t)plan_splits(B, M, O, I) * O * I * sizeof(float) + 256; }
 
 int run(const void* dY, const void* X, int B, int M, int64_t ld, int O, int I, float* part, size_t part_cap, const float* amin,
         const float* amax, const float* dws, const double* db, float* dWq, cudaStream_t s) {
     FQSS_REQUIRE(dY && X && part && dws && db && dWq, -1, "wgrad: null argument");
     FQSS_REQUIRE(O % 128 == 0 && I % 128 == 0 && O >= 128 && I >= 128, -1, "wgrad: O and I must be multiples of 128 (O=%d I=%d)", O, I);
     FQSS_REQUIRE(ld >= M && ld % 8 == 0, -2, "wgrad: bad pitch");
-    const int NW = I >= 256 ? 256 : 128;
-    FQSS_REQUIRE(I % NW == 0, -1, "wgrad: I=%d not a multiple of %d", I, NW);
+    int MT, NW, OCC;
+    pick_tile(O, I, &MT, &NW, &OCC);
     const int ot = O / 128;
-    const int MT = (ot >= 4 && NW == 128) ? 4 : (ot >= 2 ? 2 : 1);
-    FQSS_REQUIRE(ot % MT == 0, -1, "wgrad: O=%d not a multiple of %d", O, MT * 128);
+    FQSS_REQUIRE(I % NW == 0 && ot % MT == 0, -1, "wgrad: O=%d I=%d do not tile by %dx%d", O, I, MT * 128, NW);
     const int gy = (ot / MT) * (I / NW);
     KArgs a;
     a.B = B; a.M = M; a.O = O; a.I = I;
     a.chunks_per_sample = (M + BKF - 1) / BKF;
     a.nsplit = plan_splits(B, M, O, I);
     a.part = part;
-    FQSS_REQUIRE(part_cap >= (size_t)a.nsplit * O * I * sizeof(float), -3, "wgrad: partial buffer too small");
+    FQSS_REQUIRE(part_cap >= (size_t)a.nsplit * O * I * sizeof(float) + 256, -3, "wgrad: partial buffer too small");
+    a.ctr = reinterpret_cast<unsigned int*>(part + (size_t)a.nsplit * O * I);
+    a.amin = amin; a.amax = amax; a.dws = dws; a.db = db; a.dWq = dWq;
+    FQSS_REQUIRE(a.nsplit * gy <= OCC * num_sms(), -4, "wgrad: grid of %d CTAs would not be co-resident", a.nsplit * gy);
+    if (cudaMemsetAsync(a.ctr, 0, 2 * sizeof(unsigned int), s) != cudaSuccess) return check_launch("wgrad(counter memset)");
     CUtensorMap ty, tx;
     int r = make_map(&ty, dY, B, O, M, ld, 128);
     FQSS_REQUIRE(r == 0, -4, "wgrad: cuTensorMapEncodeTiled(dY) failed (%d)", r);
@@ -265,18 +333,13 @@ int run(const void* dY, const void* X, int B, int M, int64_t ld, int O, int I, f
     if (NW == 128) {
         if (MT == 4) r = launch<4, 128>(ty, tx, a, gy, s);
         else if (MT == 2) r = launch<2, 128>(ty, tx, a, gy, s);
+        else if (OCC == 2) r = launch<1, 128, 2>(ty, tx, a, gy, s);
         else r = launch<1, 128>(ty, tx, a, gy, s);
     } else {
         if (MT == 2) r = launch<2, 256>(ty, tx, a, gy, s);
         else r = launch<1, 256>(ty, tx, a, gy, s);
     }
-    if (r) return r;
-    const int64_t n = (int64_t)O * I;
-    int grid = (int)((n + 255) / 256);
-    if (grid > num_sms() * 4) grid = num_sms() * 4;
-    FQSS_PROF("wgrad_finalize", s);
-    wgrad_finalize_kernel<<<grid, 256, 0, s>>>(part, a.nsplit, O, I, amin, amax, dws, db, dWq);
-    return check_launch("wgrad_finalize");
+    return r;
 }
 
 }  // namespace tcw
