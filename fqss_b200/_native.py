@@ -105,6 +105,9 @@ _SIGS = {
     "fqss_arena_scale_clip": (i32, [vp, i64, vp, f32, f32, vp]),
     "fqss_arena_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
     "fqss_arena_adam_dev": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]),
+    "fqss_fq_affine_tensor": (i32, [vp, vp, vp, vp, i64, f32, i32, i32, i32, vp]),
+    "fqss_fq_affine_channel": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, i32, i32, vp]),
+    "fqss_fq_affine_bwd": (i32, [vp, vp, vp, i64, vp]),
     "fqss_prof_enable": (i32, [i32]),
     "fqss_prof_reset": (i32, []),
     "fqss_prof_nslots": (i32, []),
@@ -135,7 +138,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 15:
+                if L.fqss_abi_version() != 16:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

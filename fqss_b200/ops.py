@@ -163,6 +163,77 @@ def weight_codes(w, rmin, rmax, axis=0, n_bits=8):
     return code
 
 
+# =============================================================================================
+# X1: export-time quantisers (torch.fake_quantize_per_{tensor,channel}_affine arithmetic; qat_quant.py:15-72)
+# =============================================================================================
+class FakeQuantAffineTensor(Function):
+    @staticmethod
+    def forward(ctx, x, scale, zero_point, qmin, qmax):
+        N.require_cuda(x)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        mask = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device) if x.requires_grad else None
+        rc = lib().fqss_fq_affine_tensor(ptr(xc), ptr(y), ptr(mask) or None, None, xc.numel(), float(scale), int(zero_point),
+                                         int(qmin), int(qmax), stream_ptr())
+        if rc == -1 and b"zero_point" in lib().fqss_last_error():
+            raise RuntimeError(lib().fqss_last_error().decode())        # ATen's own error type and text
+        check(rc)
+        ctx.mask = mask
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous()
+        gx = torch.empty_like(g)
+        check(lib().fqss_fq_affine_bwd(ptr(g), ptr(ctx.mask), ptr(gx), g.numel(), stream_ptr()))
+        return gx, None, None, None, None
+
+
+class FakeQuantAffineChannel(Function):
+    @staticmethod
+    def forward(ctx, x, scales, axis, qmin, qmax):
+        N.require_cuda(x, scales)
+        xc = x.contiguous()
+        outer, ch, inner = _w_geometry(xc, axis)
+        if scales.numel() != ch:
+            raise RuntimeError("Expected `scale` to have the same length as the quantised axis (%d vs %d)" % (scales.numel(), ch))
+        y = torch.empty_like(xc)
+        mask = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device) if x.requires_grad else None
+        check(lib().fqss_fq_affine_channel(ptr(xc), ptr(y), ptr(mask) or None, None, outer, ch, inner, ptr(scales), int(qmin),
+                                           int(qmax), stream_ptr()))
+        ctx.mask = mask
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        g = g.contiguous()
+        gx = torch.empty_like(g)
+        check(lib().fqss_fq_affine_bwd(ptr(g), ptr(ctx.mask), ptr(gx), g.numel(), stream_ptr()))
+        return gx, None, None, None, None
+
+
+def affine_codes_tensor(x, scale, zero_point, qmin, qmax):
+    """(y, int32 clamped integer codes) of the per-tensor export quantiser."""
+    xc = x.contiguous()
+    y = torch.empty_like(xc)
+    code = torch.empty(xc.shape, dtype=torch.int32, device=xc.device)
+    check(lib().fqss_fq_affine_tensor(ptr(xc), ptr(y), None, ptr(code), xc.numel(), float(scale), int(zero_point), int(qmin),
+                                      int(qmax), stream_ptr()))
+    return y, code
+
+
+def affine_codes_channel(x, scales, axis, qmin, qmax):
+    xc = x.contiguous()
+    outer, ch, inner = _w_geometry(xc, axis)
+    y = torch.empty_like(xc)
+    code = torch.empty(xc.shape, dtype=torch.int32, device=xc.device)
+    check(lib().fqss_fq_affine_channel(ptr(xc), ptr(y), None, ptr(code), outer, ch, inner, ptr(scales), int(qmin), int(qmax),
+                                       stream_ptr()))
+    return y, code
+
+
 def weight_observe_(w, rmin, rmax, axis):
     N.require_cuda(w, rmin, rmax)
     wc = w.detach().contiguous()

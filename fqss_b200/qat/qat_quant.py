@@ -6,8 +6,9 @@ reference; the arithmetic runs in libfqss_sm100.so (no torch elementwise chain, 
   GradientActivationFakeQuantize ......... qat_quant.py:206-242
   GradientWeightFakeQuantize ............. qat_quant.py:350-381
   get_activation_quantizer / get_weight_quantizer ... :384-396
+  TorchWeightFakeQuantize / TorchActivationFakeQuantize / TorchDymActivationFakeQuantize (export) ... :15-72
 Not provided (never reached by the ConvTasNet recipe): mu-law quantiser (`nl=True`), MSE-histogram
-observer, dynamic quantiser, export-only Torch*FakeQuantize, scale_grad=True.
+observer, the dynamic training quantiser, scale_grad=True.
 """
 import torch
 import torch.nn as nn
@@ -115,6 +116,64 @@ class GradientWeightFakeQuantize(nn.Module):
             self.observer_mode = False
             return w
         return ops.FakeQuantWeight.apply(w, self.min_range, self.max_range, self.axis, self.n_bits)
+
+
+# ---------------------------------------------------------------------------------------------
+# export-time quantisers (qat_quant.py:15-72): learned ranges -> (scale, zero-point), evaluated with the arithmetic of
+# torch.fake_quantize_per_{tensor,channel}_affine (csrc/export.cu)
+# ---------------------------------------------------------------------------------------------
+class TorchWeightFakeQuantize(nn.Module):
+    def __init__(self, quantizer):
+        super().__init__()
+        with torch.no_grad():
+            bound = torch.maximum(torch.abs(quantizer.min_range), torch.abs(quantizer.max_range))
+            scales = bound / (2 ** (quantizer.n_bits - int(quantizer.sign)))
+        self.scales = scales.flatten()
+        self.zero_points = torch.zeros_like(self.scales)
+        self.axis = quantizer.axis
+        self.sign = quantizer.sign
+        self.n_bits = quantizer.n_bits
+
+    def forward(self, x):
+        qmin = -2 ** (self.n_bits - 1) if self.sign else 0
+        qmax = 2 ** (self.n_bits - 1) - 1 if self.sign else 2 ** self.n_bits - 1
+        return ops.FakeQuantAffineChannel.apply(x, self.scales, self.axis, qmin, qmax)
+
+
+class TorchActivationFakeQuantize(nn.Module):
+    def __init__(self, quantizer):
+        super().__init__()
+        # host arithmetic, as in the reference (an export-time read): torch's CUDA `tensor / python_scalar` multiplies by the
+        # reciprocal and would differ from the IEEE quotient by an ulp
+        lo, hi = quantizer.min_range.detach().cpu(), quantizer.max_range.detach().cpu()
+        scale = (hi - lo) / (2 ** quantizer.n_bits - 1)
+        self.scale = float(scale)                       # export-time host read, as in the reference (:43)
+        zp = int(torch.round(lo / self.scale))
+        self.zero_point = -zp if float(lo) < 0 else zp  # the reference keeps a positive minimum's zero-point as is (:45)
+        self.n_bits = quantizer.n_bits
+
+    def forward(self, x):
+        return ops.FakeQuantAffineTensor.apply(x, self.scale, self.zero_point, 0, 2 ** self.n_bits - 1)
+
+
+class TorchDymActivationFakeQuantize(nn.Module):
+    def __init__(self, quantizer):
+        super().__init__()
+        self.n_bits = quantizer.n_bits
+        self.factor = quantizer.factor
+
+    def forward(self, x):
+        lo_t = torch.zeros(1, device=x.device)
+        hi_t = torch.zeros(1, device=x.device)
+        ops.act_observe_(x.detach(), lo_t, hi_t, 0.0)   # alpha = 0: ranges <- 0*0 + 1*min(x), max(x) (device reduction)
+        lo, hi = self.factor * float(lo_t), self.factor * float(hi_t)
+        import numpy as np
+        f32 = np.float32
+        scale32 = f32(f32(f32(hi) - f32(lo)) / f32(2 ** self.n_bits - 1))
+        scale = float(scale32)
+        zp = int(np.rint(f32(f32(lo) / scale32)))
+        zp = -zp if lo < 0 else zp
+        return ops.FakeQuantAffineTensor.apply(x, scale, zp, 0, 2 ** self.n_bits - 1)
 
 
 def get_activation_quantizer(gradient_based=True, nl=False, n_bits=8):

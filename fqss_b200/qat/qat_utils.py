@@ -11,6 +11,7 @@ import copy
 import torch.nn as nn
 
 from . import qat_layers as QL
+from . import qat_quant as QQ
 
 
 def _resolve(root, dotted):
@@ -148,6 +149,31 @@ def replace_encoderq(model, modules_to_replace, params_dict):
 
 def replace_decoderq(model, modules_to_replace, params_dict):
     _replace_edge(model, modules_to_replace, params_dict, quant_decoderq)
+
+
+# export: swap a learned quantiser for its torch-affine counterpart (qat_utils.py:246-349)
+def torch_weight_quantizer(quantizer):
+    return QQ.TorchWeightFakeQuantize(quantizer)
+
+
+def torch_activation_quantizer(quantizer):
+    return QQ.TorchActivationFakeQuantize(quantizer)
+
+
+def torch_dym_activation_quantizer(quantizer):
+    return QQ.TorchDymActivationFakeQuantize(quantizer)
+
+
+def replace_weight_quantizer(model, module_to_replace, module):
+    _assign(model, module_to_replace, torch_weight_quantizer(module))
+
+
+def replace_activation_quantizer(model, module_to_replace, module):
+    _assign(model, module_to_replace, torch_activation_quantizer(module))
+
+
+def replace_dym_activation_quantizer(model, module_to_replace, module):
+    _assign(model, module_to_replace, torch_dym_activation_quantizer(module))
 
 
 # reference names outside the ConvTasNet hot path (imported by the reference's other model files): importable placeholders

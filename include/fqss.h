@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 15
+#define FQSS_ABI_VERSION 16
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -377,6 +377,23 @@ int fqss_cln_bwd(const float* g, int64_t ldg, const float* x, int64_t ld, const 
                  void* ws, size_t ws_bytes, void* stream);
 int fqss_ola_fwd(const float* y, int64_t ldy, float* out, int64_t ldo, int64_t R, int A, int L, int H, int K, void* stream);
 int fqss_ola_bwd(const float* gout, int64_t ldo, float* gy, int64_t ldy, int64_t R, int A, int L, int H, int K, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * X1  export-time quantisers (qat_quant.py:15-72: TorchWeightFakeQuantize, TorchActivationFakeQuantize,
+ *     TorchDymActivationFakeQuantize; installed by qat_utils.py:334-349 replace_*_quantizer).  The reference evaluates
+ *     torch.fake_quantize_per_tensor_affine / _per_channel_affine on (scale, zero-point) pairs derived from the learned
+ *     ranges; these entry points restate that arithmetic:
+ *         inv = 1.0f / scale;  q = nearbyint(x * inv) + zero_point;  y = (clamp(q, qmin, qmax) - zero_point) * scale
+ *     mask (optional, 1 byte/elem) = qmin <= q <= qmax (the op's straight-through mask); code (optional, int32) = the
+ *     clamped q, i.e. the integer a deployment toolchain stores.  A zero_point outside [qmin, qmax] is refused with
+ *     ATen's own message (the reference's export of a range that excludes zero fails the same way).
+ *     channel form: x viewed as [outer][ch][inner], scales[ch], zero-points 0.
+ * ------------------------------------------------------------------------------------------- */
+int fqss_fq_affine_tensor(const float* x, float* y, uint8_t* mask, int32_t* code, int64_t n, float scale, int zero_point,
+                          int qmin, int qmax, void* stream);
+int fqss_fq_affine_channel(const float* x, float* y, uint8_t* mask, int32_t* code, int outer, int ch, int inner,
+                           const float* scales, int qmin, int qmax, void* stream);
+int fqss_fq_affine_bwd(const float* g, const uint8_t* mask, float* gx, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * D1  flat gradient arena helpers for the data-parallel exchange (asteroid_librimix_trainer.py:125-135)

@@ -9,6 +9,8 @@ Outputs (all small, fp32, np.savez_compressed):
   tests/golden/loss.npz        S1/S2: PairwiseWSDR matrices (wsdr.py:46-95) + common_step loss/grad
   tests/golden/infer.npz       process.model_infer (process.py:154-194): whole-signal and chunked overlap-add inference
                                of a deterministic toy separator
+  tests/golden/export.npz      X1: the export-time quantisers TorchActivationFakeQuantize / TorchWeightFakeQuantize
+                               (qat_quant.py:15-53): scale, zero-point, outputs and gradients on seeded + boundary inputs
   tests/golden/model_small.npz M1-M3/L1/L2: a reduced ConvTasNetQ (64 filters, 2x3 blocks): state_dict
                                before/after 2 observer passes, input, per-layer taps, output, teacher
                                output, FQSS loss and every parameter gradient
@@ -141,6 +143,57 @@ def gen_loss(out):
     print("wrote", out, "loss", float(loss))
 
 
+def gen_export(out):
+    """Export-time quantisers of the unmodified reference (torch.fake_quantize_* on CPU)."""
+    d = {}
+    cases = [(-0.5, 0.5), (-1.7320508, 3.1415927), (0.0, 6.0), (0.25, 0.75), (-3e-3, 2e-3), (-7.3, 0.01)]
+    for ci, (lo, hi) in enumerate(cases):
+        q = RQ.GradientActivationFakeQuantize(True)
+        with torch.no_grad():
+            q.min_range.fill_(lo)
+            q.max_range.fill_(hi)
+            t = RQ.TorchActivationFakeQuantize(q)
+        x = adversarial_act_input(torch.tensor([lo]), torch.tensor([hi]), seed=40 + ci)
+        g = torch.Generator().manual_seed(400 + ci)
+        # scale-grid boundaries of the EXPORT quantiser as well (its grid differs from the training one)
+        k = torch.arange(-130, 130, dtype=torch.float32)
+        x = torch.cat([x, (k + 0.5) * t.scale, torch.nextafter((k + 0.5) * t.scale, torch.tensor(1e30))]).requires_grad_(True)
+        y = t(x)
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go)
+        d.update({f"act{ci}_range": np.array([lo, hi], np.float32), f"act{ci}_scale": np.array(t.scale, np.float64),
+                  f"act{ci}_zp": np.array(t.zero_point), f"act{ci}_x": _np(x), f"act{ci}_y": _np(y), f"act{ci}_go": _np(go),
+                  f"act{ci}_gx": _np(x.grad)})
+    for ci, (shape, axis) in enumerate([((16, 8, 1), 0), ((8, 1, 3), 0), ((12, 2, 16), 0), ((24, 1, 16), 1)]):
+        g = torch.Generator().manual_seed(500 + ci)
+        w = (torch.randn(shape, generator=g) * 0.2).requires_grad_(True)
+        q = RQ.GradientWeightFakeQuantize(True, shape, n_bits=8, ch_out_idx=axis)
+        q(w)
+        with torch.no_grad():
+            q.max_range.mul_(0.8)
+            t = RQ.TorchWeightFakeQuantize(q)
+        y = t(w)
+        go = torch.randn(y.shape, generator=g)
+        y.backward(go)
+        d.update({f"w{ci}_w": _np(w), f"w{ci}_axis": np.array(axis), f"w{ci}_min": _np(q.min_range), f"w{ci}_max": _np(q.max_range),
+                  f"w{ci}_scales": _np(t.scales), f"w{ci}_y": _np(y), f"w{ci}_go": _np(go), f"w{ci}_gw": _np(w.grad)})
+    # error behaviour: a range that excludes zero on the negative side cannot be exported (zero_point lands beyond quant_max)
+    q = RQ.GradientActivationFakeQuantize(True)
+    with torch.no_grad():
+        q.min_range.fill_(-2.0)
+        q.max_range.fill_(-0.5)
+        t = RQ.TorchActivationFakeQuantize(q)
+    try:
+        t(torch.zeros(4))
+        msg = ""
+    except RuntimeError as e:
+        msg = str(e)
+    d["neg_range_error"] = np.array(msg)
+    d["neg_range_zp"] = np.array(t.zero_point)
+    np.savez_compressed(out, **d)
+    print("wrote", out, len(d), "arrays; negative-range error:", msg)
+
+
 def gen_model_small(out):
     import fqss_oracle as O
     model, fmodel, LM = R.build_reference_model(CK.SMALL, CK.QCFG, seed=0)
@@ -214,6 +267,9 @@ def gen_infer(out):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "export":
+        gen_export(os.path.join(HERE, "export.npz"))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "infer":
         gen_infer(os.path.join(HERE, "infer.npz"))
         sys.exit(0)
@@ -223,3 +279,4 @@ if __name__ == "__main__":
     gen_loss(os.path.join(HERE, "loss.npz"))
     gen_model_small(os.path.join(HERE, "model_small.npz"))
     gen_infer(os.path.join(HERE, "infer.npz"))
+    gen_export(os.path.join(HERE, "export.npz"))
