@@ -171,8 +171,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr bool HAS_PRE = (EPI == EPI_RESSKIP || EPI == EPI_ADD || EPI == EPI_RELU_MUL);
         constexpr int CW = HAS_PRE ? 8 : 16;    // columns per chunk (two chunks live in registers)
         static_assert(COLS % (2 * CW) == 0, "chunk pipeline needs an even number of chunks");
-        ActQF q1, qres, qskip, qadd, qadds;
+        ActQF q1, qres, qskip, qadd, qadds, qm, qp;
         float slope = 0.f;
+        if (EPI == EPI_RELU_MUL && p.quant) {
+            qm = load_actqf(p.qm_min, p.qm_max, 8);
+            qp = load_actqf(p.qp_min, p.qp_max, 8);
+        }
         if (EPI == EPI_EXPAND) {
             slope = __ldg(p.slope);
             if (p.quant) q1 = load_actqf(p.q1_min, p.q1_max, 8);
@@ -297,10 +301,22 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 } else if (EPI == EPI_ADD || EPI == EPI_RELU_MUL) {
                     float* of = p.out_f32 + ((int64_t)b * p.N + o0) * ld + m;
+                    if (EPI == EPI_RELU_MUL && p.quant) {
+                        // mask head of the quantised model: FQ_m(relu(y)) * features -> FQ_p, both quantisers exact
+                        float* ys = p.y_save ? p.y_save + ((int64_t)b * p.N + o0) * ld + m : nullptr;
 #pragma unroll
-                    for (int j = 0; j < CW; ++j) {
-                        const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                        of[j * ld] = (EPI == EPI_ADD) ? y + pre[j] : fmaxf(y, 0.f) * pre[j];
+                        for (int j = 0; j < CW; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            if (ys) ys[j * ld] = y;
+                            const float vm = actqf_fq(qm, fmaxf(y, 0.f));
+                            of[j * ld] = actqf_fq(qp, __fmul_rn(vm, pre[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CW; ++j) {
+                            const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                            of[j * ld] = (EPI == EPI_ADD) ? y + pre[j] : fmaxf(y, 0.f) * pre[j];
+                        }
                     }
                 } else if (EPI == EPI_RESSKIP) {
                     const bool is_res = o0 < p.n_res;           // warp-uniform: a chunk never straddles the two convs
@@ -564,6 +580,19 @@ int fqss_pw_gemm_ex(const void* act_bf16, const void* w_bf16, const float* s1, c
         epi = tcg::EPI_BF16;
     }
     return tcg::run(epi, act_bf16, w_bf16, a, (cudaStream_t)stream);
+}
+
+// Mask head of the quantised model in the GEMM epilogue (see fqss.h).
+int fqss_mask_head_fwd(const void* x_op_bf16, const void* w_bf16, const float* s1, const float* s0, const float* feats, int C,
+                       const float* qm_min, const float* qm_max, const float* qp_min, const float* qp_max, float* y_save,
+                       float* masked, int B, int K, int N, int M, int64_t ld, void* stream) {
+    FQSS_REQUIRE(feats && masked && qm_min && qm_max && qp_min && qp_max, -1, "mask_head_fwd: null argument");
+    FQSS_REQUIRE(C > 0 && N % C == 0 && C % 32 == 0, -1, "mask_head_fwd: N=%d must be a multiple of C=%d, C a multiple of 32", N, C);
+    tcg::Args a{};
+    a.B = B; a.M = M; a.K = K; a.N = N; a.ld = ld; a.s1 = s1; a.s0 = s0; a.quant = 1; a.a_rows = 0;
+    a.out_f32 = masked; a.addend = feats; a.mul_C = C; a.y_save = y_save;
+    a.qm_min = qm_min; a.qm_max = qm_max; a.qp_min = qp_min; a.qp_max = qp_max;
+    return tcg::run(tcg::EPI_RELU_MUL, x_op_bf16, w_bf16, a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -24,6 +24,10 @@ struct Args {
     // EPI_ADD: addend [B][N][ld].  EPI_RELU_MUL: multiplicand [B][mul_C][ld], out = relu(y) * addend[b][o % mul_C][m]
     const float* addend;
     int mul_C;
+    // EPI_RELU_MUL, quantised model (the mask head: Conv1dNlQ(ReLU) + MulQ, convtasnetq.py:97-99,203): out =
+    // FQ_p(FQ_m(relu(y)) * addend); y_save (may be NULL) keeps the pre-activation for backward
+    const float* qm_min; const float* qm_max; const float* qp_min; const float* qp_max;
+    float* y_save;
     // EPI_EXPAND: gLN statistics of FQ(PReLU(y)) -> stats[2*B] (double, pre-zeroed)
     const float* slope;
     const float* q1_min; const float* q1_max;

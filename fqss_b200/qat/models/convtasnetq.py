@@ -72,9 +72,8 @@ class MaskGenerator(nn.Module):
 
     use_fused = True      # class-level switch: False forces the per-layer wrappers (tests / debugging)
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        batch = x.shape[0]
-        from ... import tcn_engine as E
+    def _skip_total(self, x, E):
+        """bottleneck + TCN stack -> running skip sum (the input of the mask head)."""
         feats = self._conv_after(self.bottleneck[0], self.bottleneck[1], x, E)
         if self.use_fused and E.fused_eligible(self, feats):
             q = self.bottleneck[1].activation_fake_quantize
@@ -85,9 +84,35 @@ class MaskGenerator(nn.Module):
             for i, block in enumerate(self.TCN[1:]):
                 feats, skip = block(feats)
                 total = self.adds[i](total, skip)
+        return total
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        batch = x.shape[0]
+        from ... import tcn_engine as E
+        total = self._skip_total(x, E)
         out = self._conv_after(self.mask_net[0], self.mask_net[1], total, E)
         out = self.mask_net[2](out)          # Identity after quantize_model (the ReLU moved into mask_net[1])
         return out.reshape(batch, self.n_srcs, self.input_dim, -1)
+
+    def masked_features(self, x: torch.Tensor, feats: torch.Tensor, mul_layer) -> Optional[torch.Tensor]:
+        """`mul_layer(self(x), feats.unsqueeze(1))` with the mask head (mask conv + ReLU + FQ, x features + FQ) fused into
+        the mask GEMM's epilogue; None when the layers are not in the quantised steady state the fused kernel covers
+        (the caller then composes the modules as the reference does, convtasnetq.py:202-203)."""
+        from ... import tcn_engine as E
+        if not self.use_fused or not isinstance(self.mask_net[2], nn.Identity):
+            return None
+        first, conv_layer = self.mask_net[0], self.mask_net[1]
+        q_in = getattr(first, "activation_fake_quantize", None)
+        # cheap structural checks first: nothing is computed unless the fused path will be taken
+        if q_in is None or not E.mask_head_eligible(conv_layer, q_in, mul_layer, _Meta(x, self.bottleneck[1].conv1d.out_channels), feats):
+            return None
+        total = self._skip_total(x, E)
+        h = first(total)
+        out = E.mask_head(conv_layer, q_in, mul_layer, h, feats)
+        conv_layer.calc_mac_op(h.shape)
+        if mul_layer.do_mac_op:
+            mul_layer.mac_op = out.numel()
+        return out.reshape(x.shape[0], self.n_srcs, self.input_dim, -1)
 
     def _conv_after(self, first, conv_layer, x, E):
         """conv_layer(first(x)); when `first` ends in an 8-bit activation quantiser and `conv_layer` is a quantised 1x1
@@ -101,6 +126,16 @@ class MaskGenerator(nn.Module):
             kind, slope = _nl_kind(getattr(conv_layer, "nl", None))
             return conv_layer._finish(kind, y, slope=slope)
         return conv_layer(h)
+
+
+class _Meta:
+    """Shape / placement stand-in for a tensor that has not been computed yet (eligibility checks only)."""
+
+    def __init__(self, like, channels):
+        self.is_cuda, self.dtype, self.shape = like.is_cuda, like.dtype, (like.shape[0], channels, like.shape[2])
+
+    def dim(self):
+        return 3
 
 
 class ConvTasNetQ(nn.Module):
@@ -136,7 +171,9 @@ class ConvTasNetQ(nn.Module):
         batch = x.shape[0]
         feats = self.encoder(x)                                    # [B, F, M]
         f_mask, f_mul = ops.fanout2(feats)                         # two consumers: gradients summed by the library
-        masked = self.mul(self.masker(f_mask), f_mul.unsqueeze(1))  # [B, S, F, M]
+        masked = self.masker.masked_features(f_mask, f_mul, self.mul)   # fused mask head; None: not applicable
+        if masked is None:
+            masked = self.mul(self.masker(f_mask), f_mul.unsqueeze(1))  # [B, S, F, M]
         dec_in = masked.reshape(batch * self.n_srcs, self.enc_num_feats, -1)
         dec = self.decoder(dec_in)                                 # [n_combiner, B*S, 1, T] (or [B*S,1,T])
         dec = dec.reshape((self.n_combiner, batch, self.n_srcs, 1, -1))

@@ -336,6 +336,94 @@ def code_conv(layer, q_in, x):
     return CodeConv1x1.apply(x, q_in.min_range, q_in.max_range, conv.weight, wq.min_range, wq.max_range, conv.bias)
 
 
+class MaskHead(Function):
+    """Mask head of the quantised separator (convtasnetq.py:97-99, :203): 1x1 conv bn -> S*F on integer-code operands, ReLU +
+    FQ_m and `* feats` + FQ_p in the GEMM epilogue (fqss_mask_head_fwd); backward of the whole elementwise tail in one pass
+    (fqss_mask_head_bwd) feeding the dgrad / wgrad GEMMs.  x: output of the preceding 8-bit quantiser (qmin, qmax)."""
+
+    @staticmethod
+    def forward(ctx, x, qmin, qmax, W, wmin, wmax, bias, qm_min, qm_max, feats, qp_min, qp_max):
+        N.require_cuda(x, qmin, qmax, W, wmin, wmax, bias, qm_min, qm_max, feats, qp_min, qp_max)
+        L = _libx()
+        B, Ci, M = x.shape
+        Co, Cf = W.shape[0], feats.shape[1]
+        ld = (M + 7) // 8 * 8
+        dev = x.device
+        s = stream_ptr()
+        xv = _as_pitched(x.detach(), ld)
+        fv = _as_pitched(feats.detach(), ld)
+        x_op = torch.empty((B, Ci, ld), dtype=torch.bfloat16, device=dev)
+        check(L.fqss_tcn_encode(ptr(xv), ld, ptr(x_op), ld, B * Ci, M, ptr(qmin), ptr(qmax), s))
+        bf = torch.bfloat16
+        Wc, WcT = torch.empty((Co, Ci), dtype=bf, device=dev), torch.empty((Ci, Co), dtype=bf, device=dev)
+        s1, s0, dws = torch.empty(Co, device=dev), torch.empty(Co, device=dev), torch.empty(Co, device=dev)
+        check(L.fqss_tcn_prep(ptr(W.detach().reshape(Co, Ci)), ptr(wmin), ptr(wmax), ptr(bias) or None, ptr(qmin), ptr(qmax), ptr(Wc),
+                              ptr(WcT), ptr(s1), ptr(s0), ptr(dws), Co, Ci, Co, 0, 0, s))
+        train = any(ctx.needs_input_grad)        # (grad mode is always off inside Function.forward)
+        y = torch.empty((B, Co, ld), device=dev) if train else None
+        out = torch.empty((B, Co, ld), device=dev)
+        check(L.fqss_mask_head_fwd(ptr(x_op), ptr(Wc), ptr(s1), ptr(s0), ptr(fv), Cf, ptr(qm_min), ptr(qm_max), ptr(qp_min),
+                                   ptr(qp_max), ptr(y) or None, ptr(out), B, Ci, Co, M, ld, s))
+        ctx.save_for_backward(x_op, WcT, dws, W, wmin, wmax, qmin, qmax, y, fv, qm_min, qm_max, qp_min, qp_max)
+        ctx.meta = (B, Ci, Co, Cf, M, ld, bias is not None)
+        return out[:, :, :M]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        L = _libx()
+        x_op, WcT, dws, W, wmin, wmax, qmin, qmax, y, fv, qm_min, qm_max, qp_min, qp_max = ctx.saved_tensors
+        B, Ci, Co, Cf, M, ld, has_bias = ctx.meta
+        dev = g.device
+        s = stream_ptr()
+        g = _as_pitched(g, ld)
+        dY = torch.empty((B, Co, ld), dtype=torch.bfloat16, device=dev)
+        g_feats = torch.empty((B, Cf, ld), device=dev)
+        g_q = torch.empty(4, device=dev)
+        g_bias = torch.empty(Co, device=dev) if has_bias else None
+        db = torch.empty(Co, dtype=torch.float64, device=dev)
+        ws = torch.empty(int(L.fqss_mask_head_ws_bytes(Co)), dtype=torch.uint8, device=dev)
+        check(L.fqss_mask_head_bwd(ptr(g), ld, ptr(y), ptr(fv), ptr(dws), ptr(qm_min), ptr(qm_max), ptr(qp_min), ptr(qp_max), ptr(dY),
+                                   ptr(g_feats), ptr(g_q), ptr(g_bias) or None, ptr(db), B, Cf, Co // Cf, M, ld, ptr(ws), ws.numel(), s))
+        gx = None
+        if ctx.needs_input_grad[0]:
+            gx = pw_gemm(dY, WcT, torch.ones(Ci, device=dev), torch.zeros(Ci, device=dev), M)[:, :, :M]
+        dWq = torch.empty((Co, Ci), device=dev)
+        ws2 = torch.empty(int(L.fqss_wgrad_codes_ws_bytes(B, M, Co, Ci)), dtype=torch.uint8, device=dev)
+        check(L.fqss_wgrad_codes(ptr(dY), ptr(x_op), B, M, ld, Co, Ci, ptr(qmin), ptr(qmax), ptr(dws), ptr(db), ptr(dWq), ptr(ws2),
+                                 ws2.numel(), s))
+        gW = torch.empty_like(W, memory_format=torch.contiguous_format)
+        gwmin, gwmax = torch.empty_like(wmin), torch.empty_like(wmax)
+        check(lib().fqss_fq_weight_bwd(ptr(dWq), ptr(W), ptr(gW), ptr(gwmin), ptr(gwmax), 1, Co, Ci, ptr(wmin), ptr(wmax), 8, s))
+        return (gx, None, None, gW, gwmin, gwmax, g_bias, g_q[0:1].reshape(qm_min.shape), g_q[1:2].reshape(qm_max.shape),
+                g_feats[:, :, :M], g_q[2:3].reshape(qp_min.shape), g_q[3:4].reshape(qp_max.shape))
+
+
+def mask_head_eligible(conv_layer, q_in, mul_layer, h, feats):
+    """True when `mul_layer(conv_layer(h), feats)` (ReLU mask conv + MulQ, both 8-bit, steady state) can run as MaskHead."""
+    from .qat import qat_layers as QL
+    from .qat.qat_quant import GradientActivationFakeQuantize as AQ
+    if not isinstance(conv_layer, QL.Conv1dNlQ) or not isinstance(conv_layer.nl, torch.nn.ReLU) or not isinstance(mul_layer, QL.MulQ):
+        return False
+    qm, qp = conv_layer.activation_fake_quantize, mul_layer.activation_fake_quantize
+    for q in (qm, qp):
+        if not isinstance(q, AQ) or q.observing() or q.n_bits != 8:
+            return False
+    if not code_conv_eligible(conv_layer, q_in, h):
+        return False
+    if not feats.is_cuda or feats.dtype != torch.float32 or feats.dim() != 3 or feats.shape[0] != h.shape[0] or feats.shape[2] != h.shape[2]:
+        return False
+    Cf = feats.shape[1]
+    return Cf % 32 == 0 and conv_layer.conv1d.out_channels % Cf == 0
+
+
+def mask_head(conv_layer, q_in, mul_layer, h, feats):
+    conv, wq = conv_layer.conv1d, conv_layer.weight_fake_quantize
+    qm, qp = conv_layer.activation_fake_quantize, mul_layer.activation_fake_quantize
+    return MaskHead.apply(h, q_in.min_range, q_in.max_range, conv.weight, wq.min_range, wq.max_range, conv.bias,
+                          qm.min_range, qm.max_range, feats, qp.min_range, qp.max_range)
+
+
 class FusedTCNFunction(Function):
     @staticmethod
     def forward(ctx, x, skip_in, meta, *flat):

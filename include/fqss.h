@@ -379,6 +379,25 @@ int fqss_ola_fwd(const float* y, int64_t ldy, float* out, int64_t ldo, int64_t R
 int fqss_ola_bwd(const float* gout, int64_t ldo, float* gy, int64_t ldy, int64_t R, int A, int L, int H, int K, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * M2  mask head of the quantised separator as ONE GEMM + ONE backward pass (models/convtasnetq.py:97-99: mask_net[1..2] =
+ *     Conv1dNlQ(1x1 bn->S*F, ReLU), qat_layers.py:188-212; :203 `self.mul(masks, feats)` = MulQ, qat_layers.py:86-96):
+ *       y = s1[o]*sum_k x_op[b,k,m]*w[o,k] + s0[o] ;  mask = FQ_m(relu(y)) ;  masked[b,o,m] = FQ_p(mask * feats[b, o % C, m])
+ *     fwd: tcgen05 GEMM on integer-code operands (as fqss_pw_gemm), both quantisers exact in the epilogue; y_save (may be
+ *          NULL: inference) keeps the pre-activation for backward.  N = S*C output channels, speaker-major.
+ *     bwd: one pass over (g, y_save, feats): dY = bf16(dws[o]*dL/dy) (operand of the dgrad / wgrad GEMMs), g_feats (summed
+ *          over the S speakers), g_q = {g_min_m, g_max_m, g_min_p, g_max_p}, bias gradient (g_bias fp32 [N], may be NULL;
+ *          db_f64 [N] the same sums in fp64 for fqss_wgrad_codes, may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int fqss_mask_head_fwd(const void* x_op_bf16, const void* w_bf16, const float* s1, const float* s0, const float* feats, int C,
+                       const float* qm_min, const float* qm_max, const float* qp_min, const float* qp_max, float* y_save,
+                       float* masked, int B, int K, int N, int M, int64_t ld, void* stream);
+size_t fqss_mask_head_ws_bytes(int N);
+int fqss_mask_head_bwd(const float* g, int64_t ldg, const float* y, const float* feats, const float* dws, const float* qm_min,
+                       const float* qm_max, const float* qp_min, const float* qp_max, void* dY_bf16, float* g_feats, float* g_q,
+                       float* g_bias, double* db_f64, int B, int C, int S, int M, int64_t ld, void* ws, size_t ws_bytes,
+                       void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * X1  export-time quantisers (qat_quant.py:15-72: TorchWeightFakeQuantize, TorchActivationFakeQuantize,
  *     TorchDymActivationFakeQuantize; installed by qat_utils.py:334-349 replace_*_quantizer).  The reference evaluates
  *     torch.fake_quantize_per_tensor_affine / _per_channel_affine on (scale, zero-point) pairs derived from the learned

@@ -419,3 +419,59 @@ def test_fused_inference_mode_is_bit_identical():
     loss = model(mixd).square().mean()
     loss.backward()
     assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+
+
+@pytest.mark.parametrize("B,M", [(3, 1003), (2, 3999)])
+def test_mask_head_fused_vs_layers_and_oracle(B, M):
+    """Mask head (convtasnetq.py:97-99, :203) in the GEMM epilogue + one backward pass (tcn_engine.MaskHead) against
+    (a) the composition of the per-layer kernels it replaces -- forward bit-identical, gradients to summation round-off --
+    and (b) the oracle's quantisers applied to the kernel's own pre-activation: both quantised outputs bit-exact."""
+    from fqss_b200 import ops, tcn_engine as E
+    from fqss_b200 import _native as NN
+    torch.manual_seed(5)
+    Ci, Cf, S = 128, 128, 2
+    Co = S * Cf
+    qmin, qmax = torch.tensor([-0.2], device=DEV), torch.tensor([3.1], device=DEV)
+    delta = torch.div(qmax - qmin, torch.full_like(qmax, 255.0))
+    x = (delta * torch.randint(0, 256, (B, Ci, M), device=DEV).float() + qmin).requires_grad_(True)
+    W = (torch.randn(Co, Ci, 1, device=DEV) * 0.05).requires_grad_(True)
+    bias = (torch.randn(Co, device=DEV) * 0.1).requires_grad_(True)
+    wmax = W.detach().amax(dim=(1, 2), keepdim=True).clone().requires_grad_(True)
+    wmin = W.detach().amin(dim=(1, 2), keepdim=True).clone().requires_grad_(True)
+    feats = (torch.randn(B, Cf, M, device=DEV) * 0.7).requires_grad_(True)
+    qm = [torch.tensor([0.0], device=DEV, requires_grad=True), torch.tensor([1.2], device=DEV, requires_grad=True)]   # clips high
+    qp = [torch.tensor([-0.9], device=DEV, requires_grad=True), torch.tensor([1.1], device=DEV, requires_grad=True)]  # clips both sides
+    leaves = [x, W, bias, wmin, wmax, feats] + qm + qp
+    g = torch.randn(B, Co, M, device=DEV)
+
+    def grads():
+        out = [t.grad.clone() for t in leaves]
+        for t in leaves:
+            t.grad = None
+        return out
+
+    E.KEEP_STATES = False
+    got = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1])
+    got.backward(g)
+    g_fused = grads()
+    # (a) the layers it replaces: code-operand conv -> ReLU + FQ -> x feats + FQ
+    y = E.CodeConv1x1.apply(x, qmin, qmax, W, wmin, wmax, bias)
+    mask = ops.pointwise_fq(NN.PW_RELU, y, None, None, None, None, qm[0], qm[1], True, 8, 0.0)
+    ref = ops.pointwise_fq(NN.PW_MUL, mask.reshape(B, S, Cf, M), feats.unsqueeze(1), None, None, None, qp[0], qp[1], True, 8, 0.0)
+    ref = ref.reshape(B, Co, M)
+    ref.backward(g)
+    g_layers = grads()
+    assert torch.equal(got.detach(), ref.detach())
+    names = ["x", "W", "bias", "wmin", "wmax", "feats", "qm_min", "qm_max", "qp_min", "qp_max"]
+    for n, a, b in zip(names, g_fused, g_layers):
+        # tensors: same arithmetic per element; range / weight-range gradients: full-tensor fp32 sums in a different order
+        assert rel(a, b) < (2e-4 if n.startswith(("q", "w")) else 2e-5), (n, rel(a, b))
+    # (b) oracle quantisers on the kernel's own pre-activation
+    yc = y.detach().cpu()
+    mo = O.fq_act(torch.relu(yc), qm[0].detach().cpu(), qm[1].detach().cpu())
+    po = O.fq_act(mo.reshape(B, S, Cf, M) * feats.detach().cpu().unsqueeze(1), qp[0].detach().cpu(), qp[1].detach().cpu())
+    assert torch.equal(got.detach().cpu(), po.reshape(B, Co, M))
+    # inference call (no grad): same values, no saved pre-activation
+    with torch.no_grad():
+        inf = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1])
+    assert torch.equal(inf, got.detach())
