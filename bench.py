@@ -183,7 +183,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from fqss_b200 import _native as N
-    from fqss_b200.losses import fqss_kd_loss
+    from fqss_b200.losses import fqss_kd_loss, fqss_training_step
     from fqss_b200.parallel import ParamArena
     from fqss_b200.qat.models.load_model import enable_observer
     from fqss_b200.testing import FULL_KW, SMALL_KW, model_pair
@@ -223,10 +223,7 @@ def run_ours(args):
 
     def step(mix, src):
         arena.zero_grad()
-        est = model(mix)
-        with torch.no_grad():
-            fest = fmodel(mix)
-        loss, _, _ = fqss_kd_loss(est, fest, src, 0.1)
+        loss, _, _ = fqss_training_step(model, fmodel, mix, src, 0.1)   # teacher forward on a side stream next to the student's
         loss.backward()
         arena.gather_grads()
         scale = arena.allreduce_mean()

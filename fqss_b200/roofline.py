@@ -42,6 +42,8 @@ def profile(fn, repeats=1):
     torch.cuda.synchronize()
     L.fqss_prof_reset()
     prev = L.fqss_set_wgrad_overlap(0)      # per-kernel timing wants every kernel alone on the stream
+    from . import losses
+    prev_t = losses.set_teacher_overlap(False)
     L.fqss_prof_enable(1)
     try:
         for _ in range(repeats):
@@ -50,6 +52,7 @@ def profile(fn, repeats=1):
     finally:
         L.fqss_prof_enable(0)
         L.fqss_set_wgrad_overlap(prev)
+        losses.set_teacher_overlap(prev_t)
     out = {}
     name = C.create_string_buffer(64)
     for i in range(L.fqss_prof_nslots()):
