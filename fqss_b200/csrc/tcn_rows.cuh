@@ -17,7 +17,7 @@
 //
 // A persistent variant (one resident wave of CTAs walking over rows, inputs by cp.async) was measured slower on B200:
 // with ~100 registers per thread it cannot keep enough loads in flight; one short-lived CTA per row with 4 quads of
-// loads in flight per thread and 7 CTAs per SM can (profiles/rows_experiments_r02.txt).
+// loads in flight per thread and 7 CTAs per SM can (A/B runs: profiles/gpu_r02[b-j].sh).
 #pragma once
 #include "tcn_bwd_common.cuh"
 
