@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--impl", default="fqss_b200", choices=["fqss_b200", "reference"])
     ap.add_argument("--per-gpu-batch", type=int, default=32)
     ap.add_argument("--global-batch", type=int, default=0, help=">0: strong scaling with this global batch")
+    ap.add_argument("--workload", default="speech", choices=["speech", "music"],
+                    help="speech (default): BASELINE configs[1], the graded line.  music: BASELINE configs[4] (ConvTasNetMusicQ, "
+                         "4 stems, stereo 44.1 kHz, 80 000-sample segments, batch 8 per GPU) -- an extra line, single GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; never a reported number)")
@@ -470,9 +473,121 @@ def run_ours(args):
     finish()
 
 
+# ---------------------------------------------------------------------------------------------
+# extra workload: BASELINE configs[4], the music recipe (configs/convtasnet_music.yaml, musdbhq_train.py:45-137)
+# ---------------------------------------------------------------------------------------------
+def run_music(args):
+    """One training step of the music recipe per timed step: fake-quantised ConvTasNetMusicQ forward (4 stems, stereo,
+    40 blocks, dilation <= 512, 7 999 frames), float teacher forward, centre trim, L1 + new-SDR-weighted KD loss, backward,
+    Adam (lr 1e-4, no clipping: musdbhq_train.py:120-128 computes the norm for display only).  Everything on libfqss_sm100
+    kernels (the teacher is the same module tree with quantisation disabled, so it runs on the same wrappers)."""
+    import copy
+    import torch
+    from fqss_b200 import _native as N
+    from fqss_b200 import roofline as R
+    from fqss_b200.losses import music_training_step
+    from fqss_b200.parallel import ParamArena
+    from fqss_b200.qat.models.convtasnetq_music import ConvTasNetMusicQ
+    from fqss_b200.qat.models.load_model import enable_observer, quantize_model
+    from fqss_b200.testing import RECIPE_QUANT
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the fqss_b200 arm has no CPU fallback)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --workload music is a single-GPU line")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    N.lib()
+    B = 8 if args.per_gpu_batch == 32 else args.per_gpu_batch        # recipe batch (convtasnet_music.yaml: batch_size 8)
+    Tm, SR = 80000, 44100
+    torch.manual_seed(0)
+    kw = dict(n_repeats=1, n_blocks=3, n_filters=64, bn_chan=64, hid_chan=128) if args.small else {}
+    model = ConvTasNetMusicQ(**kw)
+    fmodel = quantize_model(copy.deepcopy(model), dict(RECIPE_QUANT, weight_quant=False, act_quant=False, out_quant=False,
+                                                       n_splitter=1, n_combiner=1)).to(dev)
+    model = quantize_model(model, dict(RECIPE_QUANT)).to(dev)
+    for p in fmodel.parameters():
+        p.requires_grad_(False)
+    gen = torch.Generator().manual_seed(7)
+    host = []
+    for _ in range(2):
+        src = (torch.randn(B, 4, 2, Tm, generator=gen) * 0.1).pin_memory()
+        host.append((src.sum(1).pin_memory(), src))
+    dev_batches = [(m.to(dev), s.to(dev)) for m, s in host]
+    with torch.no_grad():
+        for _ in range(2):
+            model(dev_batches[0][0][:2])
+            fmodel(dev_batches[0][0][:1])
+    enable_observer(model, False)
+    enable_observer(fmodel, False)
+    arena = ParamArena(list(model.parameters()))
+
+    def step(mix, src):
+        arena.zero_grad()
+        loss, _, _, _ = music_training_step(model, fmodel, mix, src, 0.1)
+        loss.backward()
+        arena.gather_grads()
+        arena.clip_and_step(pre_scale=1.0, max_norm=float("inf"), lr=1e-4)
+        return loss
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step(*dev_batches[i % 2])
+    torch.cuda.synchronize()
+    c0 = R.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    tw0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(*dev_batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = R.launch_count() - c0
+    # end to end: the same steps fed from pinned host memory, loss read back every step
+    loss_host = torch.zeros(1).pin_memory()
+    e0.record()
+    for i in range(args.steps):
+        m, s_ = host[i % 2]
+        loss = step(m.to(dev, non_blocking=True), s_.to(dev, non_blocking=True))
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop(tw0, tw1)
+    secs = B * Tm / SR
+    line = {"metric": "ConvTasNetMusic QAT train audio-sec/sec", "value": secs * args.steps / (ms / 1e3), "unit": "audio-s/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (8-bit fake-quant codes)", "data": "synthetic",
+            "config": {"workload": "ConvTasNet music 4-stem 44.1 kHz QAT (W8A8, splitter/combiner 2/2, L1 + new-SDR-weighted KD vs float "
+                                   "teacher, lambda 0.1) on synthetic stereo 80 000-sample segments", "global_batch": B, "per_gpu_batch": B,
+                       "segment_samples": Tm, "sample_rate": SR, "parallelism": "dp1", "small_debug_model": bool(args.small),
+                       "l2": "activations per step exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": secs * args.steps / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * 5 * 2 * Tm * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss_host.item()),
+            "launch_mode": "eager (per-layer wrappers; the fused TCN engine covers the speech model's blocks only)",
+            "note": "extra line (BASELINE configs[4]); the graded line is the default speech workload"}
+    if not args.no_roofline:
+        try:
+            prof = R.profile(lambda: step(*dev_batches[0]), 1)
+            tot = sum(v["ms"] for v in prof.values())
+            line["kernels"] = [{"kernel": k, "ms_per_step": round(v["ms"], 3), "launches_per_step": v["kernels"],
+                                "share": round(v["ms"] / tot, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:10]]
+        except Exception as e:
+            line["kernels"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "music":
+        run_music(a)
     else:
         run_ours(a)

@@ -105,6 +105,8 @@ _SIGS = {
     "fqss_arena_scale_clip": (i32, [vp, i64, vp, f32, f32, vp]),
     "fqss_arena_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
     "fqss_arena_adam_dev": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]),
+    "fqss_music_loss_ws_bytes": (sz, [i32]),
+    "fqss_music_kd_loss": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, f32, vp, vp, i64, vp, sz, vp]),
     "fqss_mask_head_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
     "fqss_mask_head_ws_bytes": (sz, [i32]),
     "fqss_mask_head_bwd": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp, sz, vp]),

@@ -73,3 +73,27 @@ def fqss_validation_loss(model, inputs, targets):
     with torch.no_grad():
         est = model(inputs)
         return ops.kd_loss(est, est, targets, 0.0)[2]
+
+
+def center_trim(tensor, reference):
+    """Centre-trim the last axis of `tensor` to the length of `reference` (tensor or int); an odd surplus loses its extra
+    sample on the right (train_env/tasnet_musdbhq/musdbhq_utils.py:16-29).  A view."""
+    ref = reference.size(-1) if hasattr(reference, "size") else int(reference)
+    delta = tensor.size(-1) - ref
+    if delta < 0:
+        raise ValueError("tensor must be larger than reference. Delta is %d." % delta)
+    return tensor[..., delta // 2:tensor.size(-1) - (delta - delta // 2)] if delta else tensor
+
+
+def music_training_step(model, fmodel, mix, sources, kd_lambda=0.1):
+    """One training step's forward of the music recipe (musdbhq_train.py:76-109): student, float teacher (no grad), centre
+    trim of the sources, L1 task loss + new-SDR-weighted L1 distillation loss as one fused reduction.
+    -> (loss, kd term, task term, wavs)."""
+    wavs = model(mix)
+    src = center_trim(sources, wavs)
+    fwavs = None
+    if kd_lambda > 0 and fmodel is not None:
+        with torch.no_grad():
+            fwavs = fmodel(mix).detach()
+    out = ops.music_kd_loss(wavs, fwavs, src, kd_lambda)
+    return out[0], out[1].detach(), out[2].detach(), wavs

@@ -357,7 +357,11 @@ def fanout2(x):
     """Two aliases of `x` whose gradients are summed by the library (pitched) instead of by autograd (dense)."""
     if not (x.is_cuda and x.requires_grad and torch.is_grad_enabled()):
         return x, x
-    return Fanout2.apply(x)
+    a, b = Fanout2.apply(x)
+    src = getattr(x, "_fq_src", None)       # the 8-bit quantiser that produced x (qat_layers.LayerQ._finish): both aliases carry it
+    if src is not None:
+        a._fq_src = b._fq_src = src
+    return a, b
 
 
 def pointwise_fq(kind, x1, x2=None, slope=None, gamma=None, beta=None, rmin=None, rmax=None, quant=False, n_bits=8, eps=0.0):
@@ -663,3 +667,43 @@ class KDLoss(Function):
 
 def kd_loss(est, fest, tgt, kd_lambda=0.1):
     return KDLoss.apply(est, fest, tgt, kd_lambda)
+
+
+# =============================================================================================
+# music recipe: L1 + SDR-weighted KD loss (train_env/tasnet_musdbhq/musdbhq_train.py:87-109)
+# =============================================================================================
+class MusicKDLoss(Function):
+    """returns a 3-vector [loss, kd term, task term]; gradient flows from element 0 to wavs."""
+
+    @staticmethod
+    def forward(ctx, wavs, fwavs, sources, kd_lambda):
+        N.require_cuda(wavs, fwavs, sources)
+        if wavs.dim() < 2 or wavs.shape != sources.shape or (fwavs is not None and fwavs.shape != wavs.shape):
+            raise N.FqssError("music_kd_loss expects wavs / fwavs / sources of one shape [B, ..., T]")
+        B, T = wavs.shape[0], wavs.shape[-1]
+        w_r, rows, _, ldw = rows_view(wavs)
+        s_r, _, _, lds = rows_view(sources.detach())
+        f_r, ldf = None, 0
+        if fwavs is not None:
+            f_r, _, _, ldf = rows_view(fwavs.detach())
+        out = torch.empty(3, device=wavs.device)
+        g = alloc_rows(wavs.shape, wavs.device) if ctx.needs_input_grad[0] else None
+        ws = torch.empty(int(lib().fqss_music_loss_ws_bytes(B)), dtype=torch.uint8, device=wavs.device)
+        check(lib().fqss_music_kd_loss(ptr(w_r), ldw, ptr(f_r) or None, ldf, ptr(s_r), lds, B, rows // B, T, float(kd_lambda),
+                                       ptr(out), ptr(g) or None, ld_of(g) if g is not None else 0, ptr(ws), ws.numel(),
+                                       stream_ptr()))
+        ctx.g = g
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        g = ctx.g
+        ctx.g = None
+        if g is None:
+            return None, None, None, None
+        return g * gout[0], None, None, None
+
+
+def music_kd_loss(wavs, fwavs, sources, kd_lambda=0.1):
+    return MusicKDLoss.apply(wavs, fwavs, sources, kd_lambda)

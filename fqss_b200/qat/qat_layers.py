@@ -57,7 +57,9 @@ class LayerQ(nn.Module):
                 y = ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, quant=False, eps=eps)
                 q.observe_(y)
                 return y
-            return ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, q.min_range, q.max_range, True, q.n_bits, eps)
+            y = ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, q.min_range, q.max_range, True, q.n_bits, eps)
+            y._fq_src = q         # tag: y lies on q's grid -- a quantised 1x1 conv consuming THIS tensor object runs on the
+            return y              # tensor cores with integer-code operands (_conv1d_q); views / copies drop the tag
         if isinstance(q, nn.Identity):
             return ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, quant=False, eps=eps)
         raise NotImplementedError("unsupported activation quantiser %s" % type(q).__name__)
@@ -89,6 +91,26 @@ def _conv1d(x, w, conv):
         return ops.StridedConv.apply(x, w, s)
     raise NotImplementedError("Conv1d geometry k=%d s=%d p=%d d=%d groups=%d bias=%s is not on the FQSS ConvTasNet path"
                               % (k, s, p, d, g, conv.bias is not None))
+
+
+TENSOR_CORE_CONV1X1 = True      # False: every 1x1 conv of the per-layer wrappers stays on the fp32 SIMT kernels (tests / A/B)
+
+
+def _conv1d_q(layer, x):
+    """conv part of Conv1dQ / Conv1dNlQ.forward.  A 1x1 conv whose input carries the tag of the 8-bit quantiser that produced
+    it, with an 8-bit per-channel weight quantiser in steady state, is the code-operand tcgen05 GEMM of the fused engine
+    (tcn_engine.CodeConv1x1: exact integer accumulation, quantised weights never materialised); an un-quantised 1x1 conv under
+    no_grad (the float teacher of a recipe without a dedicated engine) takes the split-bf16 tcgen05 GEMM (fp32-grade, 2^-16);
+    everything else the per-layer SIMT kernels."""
+    from .. import tcn_engine as E
+    conv = layer.conv1d
+    if TENSOR_CORE_CONV1X1 and conv.kernel_size[0] == 1 and x.is_cuda and x.dim() == 3:
+        q_in = getattr(x, "_fq_src", None)
+        if q_in is not None and E.code_conv_eligible(layer, q_in, x):
+            return E.code_conv(layer, q_in, x)
+        if isinstance(layer.weight_fake_quantize, nn.Identity) and E.float_conv_eligible(conv, x):
+            return E.float_conv(conv, x)
+    return _conv1d(x, layer.weight_fake_quantize(conv.weight), conv)
 
 
 def _conv_out_len(conv, L):
@@ -139,7 +161,7 @@ class Conv1dQ(LayerQ):
         self.conv1d = conv1d
 
     def forward(self, x):
-        y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
+        y = _conv1d_q(self, x)
         self.calc_mac_op(x.shape)
         return self._finish(N.PW_IDENT, y)
 
@@ -159,7 +181,7 @@ class Conv1dNlQ(LayerQ):
         self.nl = nl
 
     def forward(self, x):
-        y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
+        y = _conv1d_q(self, x)
         self.calc_mac_op(x.shape)
         kind, slope = _nl_kind(self.nl)
         return self._finish(kind, y, slope=slope)

@@ -336,6 +336,35 @@ def code_conv(layer, q_in, x):
     return CodeConv1x1.apply(x, q_in.min_range, q_in.max_range, conv.weight, wq.min_range, wq.max_range, conv.bias)
 
 
+def float_conv_eligible(conv, x):
+    """Un-quantised 1x1 conv, forward only (no gradient wanted anywhere): the split-bf16 tcgen05 GEMM applies."""
+    if torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad):
+        return False
+    if conv.kernel_size[0] != 1 or conv.stride[0] != 1 or conv.padding[0] != 0 or conv.groups != 1 or x.dtype != torch.float32:
+        return False
+    return conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0 and conv.out_channels <= 1024 and conv.weight.is_contiguous()
+
+
+_FLOAT_W = {}
+
+
+def float_conv(conv, x):
+    """y = conv1x1(x) with fp32-grade accuracy on the bf16 tensor pipe: x = hi + lo, three-term product (float_engine's scheme)."""
+    B, Ci, M = x.shape
+    ld = (M + 7) // 8 * 8
+    w = conv.weight
+    key = (w.data_ptr(), w._version, conv.bias.data_ptr() if conv.bias is not None else 0)
+    ent = _FLOAT_W.get(id(conv))
+    if ent is None or ent[0] != key:
+        Co = w.shape[0]
+        ones = torch.ones(Co, device=w.device)
+        b = conv.bias.detach().clone() if conv.bias is not None else torch.zeros(Co, device=w.device)
+        ent = (key, split_bf16_weights(w), ones, b)
+        _FLOAT_W[id(conv)] = ent
+    y = pw_gemm(split_bf16_acts(x.detach(), ld), ent[1], ent[2], ent[3], M)
+    return y[:, :, :M]
+
+
 class MaskHead(Function):
     """Mask head of the quantised separator (convtasnetq.py:97-99, :203): 1x1 conv bn -> S*F on integer-code operands, ReLU +
     FQ_m and `* feats` + FQ_p in the GEMM epilogue (fqss_mask_head_fwd); backward of the whole elementwise tail in one pass

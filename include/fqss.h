@@ -338,6 +338,16 @@ int fqss_kd_loss(const float* est, int64_t lde, const float* fest, int64_t ldf, 
                  int B, int T, float kd_lambda, float* out, float* gest, int64_t ldg,
                  void* ws, size_t ws_bytes, void* stream);
 
+/* KD training loss of the music recipe (train_env/tasnet_musdbhq/musdbhq_train.py:87-109; new-SDR process.py:70-75;
+ * loss_fn = nn.L1Loss, :249).  wavs / fwavs / sources: [B items][R rows per item][T] row tensors (row pitches ld*);
+ * per item a = 10^((nsdr(fwavs,src) - nsdr(wavs,src))/10) (no gradient), loss = (1-lambda) L1(wavs,src) +
+ * lambda mean_i a_i L1(wavs_i, fwavs_i); fwavs == NULL or lambda == 0: loss = L1(wavs, src) (:109).
+ * out[0] = loss, out[1] = kd term, out[2] = task term; g (may be NULL) = dL/dwavs with pitch ldg. */
+size_t fqss_music_loss_ws_bytes(int B);
+int fqss_music_kd_loss(const float* wavs, int64_t ldw, const float* fwavs, int64_t ldf, const float* sources, int64_t lds,
+                       int B, int R, int T, float kd_lambda, float* out, float* g, int64_t ldg, void* ws, size_t ws_bytes,
+                       void* stream);
+
 /* fqss_kd_loss under data parallelism with the loss of the GLOBAL batch (mysystem.py:145 takes
  * -10 log10 of batch MEANS, so the mean of per-rank gradients is not the gradient of the global-batch loss).
  *   phase 0: statistics + the local means {kd, task, val} (3 doubles on the device) into `means`;

@@ -147,3 +147,38 @@ def calibrate_music(P: Params, x, cfg: MusicConfig, passes: int = 2) -> QuantSta
     st.observe = False
     st.weights_seen = True
     return st
+
+
+# --------------------------------------------------------------------------------------
+# training loss of the music recipe (train_env/tasnet_musdbhq/musdbhq_train.py:76-109)
+# --------------------------------------------------------------------------------------
+def center_trim(tensor, reference):
+    """musdbhq_utils.py:16-29."""
+    ref = reference.size(-1) if hasattr(reference, "size") else int(reference)
+    delta = tensor.size(-1) - ref
+    if delta < 0:
+        raise ValueError("tensor must be larger than reference")
+    return tensor[..., delta // 2:-(delta - delta // 2)] if delta else tensor
+
+
+def new_sdr_db(ref, sig, eps=1e-7):
+    """process.py:70-75 (MDX new-SDR), a python float: 10 log10 of an fp32 ratio."""
+    import numpy as np
+    r = (torch.sum(torch.square(ref)) + eps) / (torch.sum(torch.square(ref - sig)) + eps)
+    return 10 * np.log10(r.item())
+
+
+def music_kd_loss(wavs, fwavs, sources, kd_lambda=0.1):
+    """musdbhq_train.py:87-109 with loss_fn = nn.L1Loss() (:249): per-item new-SDR weights (note the argument order of the
+    call sites: the ESTIMATE is passed as `ref`), weighted per-item L1 distillation term, batch L1 task term.
+    -> (loss, kd term, task term); kd_lambda == 0 or fwavs None: loss = task."""
+    task = F.l1_loss(wavs, sources)
+    if not (kd_lambda > 0) or fwavs is None:
+        return task, torch.zeros(()), task
+    n = wavs.shape[0]
+    with torch.no_grad():
+        sdr = torch.Tensor([new_sdr_db(fwavs[i:i + 1], sources[i:i + 1]) for i in range(n)])
+        sdrq = torch.Tensor([new_sdr_db(wavs[i:i + 1], sources[i:i + 1]) for i in range(n)])
+        w = 10 ** ((sdr - sdrq) / 10)
+    kd = torch.mean(w * torch.stack([F.l1_loss(wavs[i:i + 1], fwavs[i:i + 1]) for i in range(n)], dim=0))
+    return (1 - kd_lambda) * task + kd_lambda * kd, kd, task

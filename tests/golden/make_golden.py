@@ -11,6 +11,8 @@ Outputs (all small, fp32, np.savez_compressed):
                                of a deterministic toy separator
   tests/golden/export.npz      X1: the export-time quantisers TorchActivationFakeQuantize / TorchWeightFakeQuantize
                                (qat_quant.py:15-53): scale, zero-point, outputs and gradients on seeded + boundary inputs
+  tests/golden/music_loss.npz  the KD training loss of the music recipe (musdbhq_train.py:87-109) computed with the
+                               reference's own calc_nsdr (process.py:70-75), center_trim and nn.L1Loss: loss, terms, gradient
   tests/golden/model_small.npz M1-M3/L1/L2: a reduced ConvTasNetQ (64 filters, 2x3 blocks): state_dict
                                before/after 2 observer passes, input, per-layer taps, output, teacher
                                output, FQSS loss and every parameter gradient
@@ -194,6 +196,42 @@ def gen_export(out):
     print("wrote", out, len(d), "arrays; negative-range error:", msg)
 
 
+def gen_music_loss(out):
+    """The loss lines of the reference's training loop (musdbhq_train.py:83-109) on seeded tensors.  The loop is not a
+    function in the reference, so its few lines are composed here from the reference's OWN helpers: process.calc_nsdr,
+    musdbhq_utils.center_trim and nn.L1Loss (musdbhq_train.py:249)."""
+    sys.path.insert(0, os.path.join(R.REFERENCE_ROOT, "train_env", "tasnet_musdbhq"))
+    from musdbhq_utils import center_trim
+    g = torch.Generator().manual_seed(21)
+    B, S, C, Tw, Ts = 3, 4, 2, 1210, 1237
+    sources_full = torch.randn(B, S, C, Ts, generator=g) * 0.1
+    trimmed = center_trim(sources_full, Tw)
+    wavs = (trimmed + 0.03 * torch.randn(B, S, C, Tw, generator=g)).clone().requires_grad_(True)
+    fwavs = trimmed + 0.01 * torch.randn(B, S, C, Tw, generator=g) * torch.tensor([0.5, 1.0, 3.0]).view(B, 1, 1, 1)
+    wavs.data[0, 0, 0, :5] = trimmed[0, 0, 0, :5]                   # exact zeros of w - s: sign(0) = 0
+    loss_fn = torch.nn.L1Loss()
+    kd_lambda = 0.1
+    sources = center_trim(sources_full, wavs)
+    sdrs, sdrqs = [], []
+    with torch.no_grad():
+        for i in range(len(fwavs)):
+            sdrs.append(RP.calc_nsdr(fwavs[i:i + 1], sources[i:i + 1]))
+            sdrqs.append(RP.calc_nsdr(wavs[i:i + 1], sources[i:i + 1]))
+        w = 10 ** ((torch.Tensor(sdrs) - torch.Tensor(sdrqs)) / 10)
+    kd_loss = torch.mean(w * torch.stack([loss_fn(wavs[i:i + 1], fwavs[i:i + 1]) for i in range(len(fwavs))], dim=0))
+    task_loss = loss_fn(wavs, sources)
+    loss = (1 - kd_lambda) * task_loss + kd_lambda * kd_loss
+    loss.backward()
+    g_kd = wavs.grad.clone()
+    wavs.grad = None
+    loss0 = loss_fn(wavs, sources)
+    loss0.backward()
+    np.savez_compressed(out, sources_full=_np(sources_full), wavs=_np(wavs), fwavs=_np(fwavs), kd_lambda=np.float32(kd_lambda),
+                        w=_np(w), loss=_np(loss), kd=_np(kd_loss), task=_np(task_loss), g=_np(g_kd), loss0=_np(loss0),
+                        g0=_np(wavs.grad))
+    print("wrote", out, "loss", float(loss), "weights", w.tolist())
+
+
 def gen_model_small(out):
     import fqss_oracle as O
     model, fmodel, LM = R.build_reference_model(CK.SMALL, CK.QCFG, seed=0)
@@ -267,6 +305,9 @@ def gen_infer(out):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "music_loss":
+        gen_music_loss(os.path.join(HERE, "music_loss.npz"))
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "export":
         gen_export(os.path.join(HERE, "export.npz"))
         sys.exit(0)
@@ -280,3 +321,4 @@ if __name__ == "__main__":
     gen_model_small(os.path.join(HERE, "model_small.npz"))
     gen_infer(os.path.join(HERE, "infer.npz"))
     gen_export(os.path.join(HERE, "export.npz"))
+    gen_music_loss(os.path.join(HERE, "music_loss.npz"))
