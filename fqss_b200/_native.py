@@ -107,7 +107,14 @@ _SIGS = {
     "fqss_arena_adam_dev": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]),
     "fqss_music_loss_ws_bytes": (sz, [i32]),
     "fqss_music_kd_loss": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, f32, vp, vp, i64, vp, sz, vp]),
-    "fqss_mask_head_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
+    "fqss_mask_head_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
+    "fqss_pw_gemm_nstore": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
+    "fqss_frames_split": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp]),
+    "fqss_frames_encode": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "fqss_edge_dec_prep": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
+    "fqss_edge_enc_prep": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+    "fqss_sub_fq_codes": (i32, [vp, i64, vp, i64, vp, i64, i64, i32, vp, vp, vp]),
+    "fqss_dec_wgrad_fold": (i32, [vp, vp, i32, i32, vp]),
     "fqss_mask_head_ws_bytes": (sz, [i32]),
     "fqss_mask_head_bwd": (i32, [vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp, sz, vp]),
     "fqss_fq_affine_tensor": (i32, [vp, vp, vp, vp, i64, f32, i32, i32, i32, vp]),
@@ -143,7 +150,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 16:
+                if L.fqss_abi_version() != 17:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

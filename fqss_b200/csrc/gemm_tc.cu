@@ -237,7 +237,8 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const float* s1c = s1s + o0;
                 const float* s0c = s0s + o0;
                 if (EPI == EPI_STORE) {
-                    const int64_t base = ((int64_t)b * p.N + o0) * ld + m;
+                    if (p.n_store > 0 && o0 >= p.n_store) return;        // warp-uniform: columns beyond the kept ones
+                    const int64_t base = ((int64_t)b * (p.n_store > 0 ? p.n_store : p.N) + o0) * ld + m;
                     float* of = p.out_f32 ? p.out_f32 + base : nullptr;
                     __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + base : nullptr;
 #pragma unroll
@@ -304,12 +305,15 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (EPI == EPI_RELU_MUL && p.quant) {
                         // mask head of the quantised model: FQ_m(relu(y)) * features -> FQ_p, both quantisers exact
                         float* ys = p.y_save ? p.y_save + ((int64_t)b * p.N + o0) * ld + m : nullptr;
+                        __nv_bfloat16* oc = p.out_bf16 ? p.out_bf16 + ((int64_t)b * p.N + o0) * ld + m : nullptr;
 #pragma unroll
                         for (int j = 0; j < CW; ++j) {
                             const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
                             if (ys) ys[j * ld] = y;
                             const float vm = actqf_fq(qm, fmaxf(y, 0.f));
-                            of[j * ld] = actqf_fq(qp, __fmul_rn(vm, pre[j]));
+                            const float c = actqf_code(qp, __fmul_rn(vm, pre[j]));
+                            of[j * ld] = actqf_decode(qp, c);
+                            if (oc) oc[j * ld] = __float2bfloat16_rn(c);      // the decoder GEMM's operand: the code itself
                         }
                     } else {
 #pragma unroll
@@ -507,7 +511,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const Args& a, c
     int grid = num_sms();
     if (grid > tiles) grid = tiles;
     static const char* const names[] = {"gemm_store", "gemm_expand", "gemm_resskip", "gemm_dgrad_bf16", "gemm_dgrad_add", "gemm_relu_mul"};
-    FQSS_PROF((a.a_rows > 0 && a.a_rows < a.K) ? (EPI == EPI_EXPAND ? "gemm_expand(split3)" : EPI == EPI_RESSKIP ? "gemm_resskip(split3)" : EPI == EPI_RELU_MUL ? "gemm_relu_mul(split3)" : "gemm_store(split3)") : names[EPI], s);
+    FQSS_PROF(a.prof ? a.prof : (a.a_rows > 0 && a.a_rows < a.K) ? (EPI == EPI_EXPAND ? "gemm_expand(split3)" : EPI == EPI_RESSKIP ? "gemm_resskip(split3)" : EPI == EPI_RELU_MUL ? "gemm_relu_mul(split3)" : "gemm_store(split3)") : names[EPI], s);
     pw_gemm_kernel<NT, EPI, LDC><<<grid, NUM_THREADS, smem, s>>>(ta, tb, a);
     return check_launch("pw_gemm");
 }
@@ -582,15 +586,25 @@ int fqss_pw_gemm_ex(const void* act_bf16, const void* w_bf16, const float* s1, c
     return tcg::run(epi, act_bf16, w_bf16, a, (cudaStream_t)stream);
 }
 
+// fqss_pw_gemm with only the first n_store output channels stored (out_f32: [B][n_store][ld]); see fqss.h
+int fqss_pw_gemm_nstore(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32, int n_store,
+                        int B, int K, int N, int M, int64_t ld, void* stream) {
+    FQSS_REQUIRE(out_f32 && n_store > 0 && n_store <= N && n_store % 16 == 0, -1, "pw_gemm_nstore: n_store must be a multiple of 16 in (0, N]");
+    tcg::Args a{};
+    a.B = B; a.M = M; a.K = K; a.N = N; a.ld = ld; a.s1 = s1; a.s0 = s0; a.quant = 0; a.a_rows = 0;
+    a.out_f32 = out_f32; a.n_store = n_store; a.prof = "gemm_frames";
+    return tcg::run(tcg::EPI_STORE, act_bf16, w_bf16, a, (cudaStream_t)stream);
+}
+
 // Mask head of the quantised model in the GEMM epilogue (see fqss.h).
 int fqss_mask_head_fwd(const void* x_op_bf16, const void* w_bf16, const float* s1, const float* s0, const float* feats, int C,
                        const float* qm_min, const float* qm_max, const float* qp_min, const float* qp_max, float* y_save,
-                       float* masked, int B, int K, int N, int M, int64_t ld, void* stream) {
+                       float* masked, void* masked_codes_bf16, int B, int K, int N, int M, int64_t ld, void* stream) {
     FQSS_REQUIRE(feats && masked && qm_min && qm_max && qp_min && qp_max, -1, "mask_head_fwd: null argument");
     FQSS_REQUIRE(C > 0 && N % C == 0 && C % 32 == 0, -1, "mask_head_fwd: N=%d must be a multiple of C=%d, C a multiple of 32", N, C);
     tcg::Args a{};
     a.B = B; a.M = M; a.K = K; a.N = N; a.ld = ld; a.s1 = s1; a.s0 = s0; a.quant = 1; a.a_rows = 0;
-    a.out_f32 = masked; a.addend = feats; a.mul_C = C; a.y_save = y_save;
+    a.out_f32 = masked; a.out_bf16 = (__nv_bfloat16*)masked_codes_bf16; a.addend = feats; a.mul_C = C; a.y_save = y_save;
     a.qm_min = qm_min; a.qm_max = qm_max; a.qp_min = qp_min; a.qp_max = qp_max;
     return tcg::run(tcg::EPI_RELU_MUL, x_op_bf16, w_bf16, a, (cudaStream_t)stream);
 }

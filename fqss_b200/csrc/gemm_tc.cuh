@@ -28,6 +28,10 @@ struct Args {
     // FQ_p(FQ_m(relu(y)) * addend); y_save (may be NULL) keeps the pre-activation for backward
     const float* qm_min; const float* qm_max; const float* qp_min; const float* qp_max;
     float* y_save;
+    // EPI_STORE: > 0 limits the stored output channels to [0, n_store) (a multiple of 16; the decoder GEMM computes 128
+    // columns for the tensor core's shape and keeps the 16 taps)
+    int n_store;
+    const char* prof;      // profiler class of the launch (NULL: named after the epilogue)
     // EPI_EXPAND: gLN statistics of FQ(PReLU(y)) -> stats[2*B] (double, pre-zeroed)
     const float* slope;
     const float* q1_min; const float* q1_max;

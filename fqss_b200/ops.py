@@ -500,6 +500,17 @@ class TransposedConv1(Function):
 # =============================================================================================
 # P1: splitter / reconstructor
 # =============================================================================================
+_SPLIT_GRID = {}
+
+
+def _splitter_grid(device):
+    g = _SPLIT_GRID.get(device)
+    if g is None:
+        g = (torch.full((1,), -1.0, device=device), torch.full((1,), 127.0 / 128.0, device=device))
+        _SPLIT_GRID[device] = g
+    return g
+
+
 def split_input(x, n_split, n_bits=8, normalize=True):
     """process.preprocess for n_splitter >= 2: [B,C,T] -> [B,n_split*C,T] (no gradient: model input).
     normalize=True: x / max|x| with threshold 1 (the speech recipe, process.py:23-24); False: threshold = max|x|
@@ -522,6 +533,10 @@ def split_input(x, n_split, n_bits=8, normalize=True):
     else:
         check(lib().fqss_split_ex(ptr(x), ldx, ptr(peak), ptr(y), ld_of(y), B, Cc, T, n_split, n_bits, int(bool(normalize)),
                                   stream_ptr()))
+    if normalize and n_bits == 8:
+        # every part is k/128 with k in [-128, 127] (process.py:10-14): an 8-bit grid {min = -1, max = 127/128}; the encoder's
+        # tensor-core path (edge_engine.FramedCodeConv) re-reads the parts as integer codes
+        y._fq_grid = _splitter_grid(x.device)
     return y
 
 

@@ -94,7 +94,7 @@ class MaskGenerator(nn.Module):
         out = self.mask_net[2](out)          # Identity after quantize_model (the ReLU moved into mask_net[1])
         return out.reshape(batch, self.n_srcs, self.input_dim, -1)
 
-    def masked_features(self, x: torch.Tensor, feats: torch.Tensor, mul_layer) -> Optional[torch.Tensor]:
+    def masked_features(self, x: torch.Tensor, feats: torch.Tensor, mul_layer, want_codes=False) -> Optional[torch.Tensor]:
         """`mul_layer(self(x), feats.unsqueeze(1))` with the mask head (mask conv + ReLU + FQ, x features + FQ) fused into
         the mask GEMM's epilogue; None when the layers are not in the quantised steady state the fused kernel covers
         (the caller then composes the modules as the reference does, convtasnetq.py:202-203)."""
@@ -108,11 +108,14 @@ class MaskGenerator(nn.Module):
             return None
         total = self._skip_total(x, E)
         h = first(total)
-        out = E.mask_head(conv_layer, q_in, mul_layer, h, feats)
+        out, codes = E.mask_head(conv_layer, q_in, mul_layer, h, feats, want_codes)
         conv_layer.calc_mac_op(h.shape)
         if mul_layer.do_mac_op:
             mul_layer.mac_op = out.numel()
-        return out.reshape(x.shape[0], self.n_srcs, self.input_dim, -1)
+        res = out.reshape(x.shape[0], self.n_srcs, self.input_dim, -1)
+        res._fq_src = mul_layer.activation_fake_quantize     # the masked features lie on the MulQ quantiser's grid ...
+        res._fq_codes = codes                                # ... and exist as integer codes too ([B, S*F, ld] bf16, or None)
+        return res
 
     def _conv_after(self, first, conv_layer, x, E):
         """conv_layer(first(x)); when `first` ends in an 8-bit activation quantiser and `conv_layer` is a quantised 1x1
@@ -171,10 +174,17 @@ class ConvTasNetQ(nn.Module):
         batch = x.shape[0]
         feats = self.encoder(x)                                    # [B, F, M]
         f_mask, f_mul = ops.fanout2(feats)                         # two consumers: gradients summed by the library
-        masked = self.masker.masked_features(f_mask, f_mul, self.mul)   # fused mask head; None: not applicable
+        from ... import edge_engine as EE
+        masked = self.masker.masked_features(f_mask, f_mul, self.mul,   # fused mask head; None: not applicable
+                                             want_codes=EE.decoder_wants_codes(self.decoder))
         if masked is None:
             masked = self.mul(self.masker(f_mask), f_mul.unsqueeze(1))  # [B, S, F, M]
         dec_in = masked.reshape(batch * self.n_srcs, self.enc_num_feats, -1)
+        src, codes = getattr(masked, "_fq_src", None), getattr(masked, "_fq_codes", None)
+        if src is not None:          # a reshape drops the producer tag; the decoder's tensor-core path needs it
+            dec_in._fq_src = src
+            if codes is not None:
+                dec_in._fq_codes = codes.view(batch * self.n_srcs, self.enc_num_feats, codes.shape[-1])
         dec = self.decoder(dec_in)                                 # [n_combiner, B*S, 1, T] (or [B*S,1,T])
         dec = dec.reshape((self.n_combiner, batch, self.n_srcs, 1, -1))
         return self.post_process(dec)                              # [B, S, T]

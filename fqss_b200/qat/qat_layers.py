@@ -271,9 +271,17 @@ class Conv1dEncoderQ(LayerQ):
             self.conv1d = grown
 
     def forward(self, x):
+        from .. import edge_engine as EE
+        grid = getattr(x, "_fq_grid", None)          # the splitter's 8-bit grid (ops.split_input)
         if not isinstance(self.in_quantizer, nn.Identity):
             x = self.in_quantizer(x)
-        y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
+            q = self.in_quantizer
+            grid = (q.min_range, q.max_range) if EE._steady_aq(q) else None
+        if EE.framed_conv_eligible(self.conv1d, self.weight_fake_quantize, x, grid):
+            # input on an 8-bit grid, 8-bit weights: one integer-code tcgen05 GEMM over the framed input
+            y = EE.framed_conv(self.conv1d, self.weight_fake_quantize, x, grid)
+        else:
+            y = _conv1d(x, self.weight_fake_quantize(self.conv1d.weight), self.conv1d)
         if self.do_mac_op:
             Co, Ci, k = self.conv1d.weight.shape
             self.mac_op = x.shape[0] * Ci * Co * _conv_out_len(self.conv1d, x.shape[-1]) * k
@@ -313,13 +321,24 @@ class ResidualErrorBlock(LayerQ):
         self.weight_fake_quantize = (get_weight_quantizer(gradient_based, self.residual_encoder.weight.shape,
                                                           n_bits=weight_n_bits) if weight_quant else nn.Identity())
 
+    def reencode(self, y_q):
+        """Yq = residual_encoder(y_q) with the fake-quantised re-encoder weight (qat_layers.py:1189); y_q lies on the grid of
+        the decoder's output quantiser, so the conv runs as an integer-code GEMM when that quantiser is in steady state."""
+        from .. import edge_engine as EE
+        conv, wq = self.residual_encoder, self.weight_fake_quantize
+        src = getattr(y_q, "_fq_src", None)
+        grid = (src.min_range, src.max_range) if EE._steady_aq(src) else None
+        if EE.framed_conv_eligible(conv, wq, y_q, grid):
+            return EE.framed_conv(conv, wq, y_q, grid)
+        return ops.StridedConv.apply(y_q, wq(conv.weight), self.decoder_stride[0])
+
     def forward(self, Y, y_q, w_decoder):
         if self.decoder_type is nn.Linear:
             # channels-first: Y [R, N, K] features, y_q [R, F, K] quantised decoder output; the Linear layers are 1x1 convs
             Yq = ops.Conv1x1.apply(y_q, self.weight_fake_quantize(self.residual_encoder.weight).unsqueeze(-1), None)
             Y1 = self._finish(N.PW_SUB, Y, Yq)
             return ops.Conv1x1.apply(Y1, w_decoder.unsqueeze(-1), None)
-        Yq = ops.StridedConv.apply(y_q, self.weight_fake_quantize(self.residual_encoder.weight), self.decoder_stride[0])
+        Yq = self.reencode(y_q)
         Y1 = self._finish(N.PW_SUB, Y, Yq)
         return ops.TransposedConv1.apply(Y1, w_decoder, self.decoder_stride[0])
 
@@ -345,6 +364,9 @@ class ConvTr1dDecoderQ(LayerQ):
                                                       if out_quant else nn.Identity())
 
     def forward(self, x):
+        from .. import edge_engine as EE
+        if EE.decoder_eligible(self, x):       # features on an 8-bit grid, 8-bit weights: integer-code tcgen05 GEMMs + overlap-add
+            return EE.decoder_forward(self, x)
         stride = self.convTr1d.stride[0]
         w_dec = self.weight_fake_quantize(self.convTr1d.weight)
         x_dec = x

@@ -371,7 +371,7 @@ class MaskHead(Function):
     (fqss_mask_head_bwd) feeding the dgrad / wgrad GEMMs.  x: output of the preceding 8-bit quantiser (qmin, qmax)."""
 
     @staticmethod
-    def forward(ctx, x, qmin, qmax, W, wmin, wmax, bias, qm_min, qm_max, feats, qp_min, qp_max):
+    def forward(ctx, x, qmin, qmax, W, wmin, wmax, bias, qm_min, qm_max, feats, qp_min, qp_max, want_codes=False):
         N.require_cuda(x, qmin, qmax, W, wmin, wmax, bias, qm_min, qm_max, feats, qp_min, qp_max)
         L = _libx()
         B, Ci, M = x.shape
@@ -391,15 +391,18 @@ class MaskHead(Function):
         train = any(ctx.needs_input_grad)        # (grad mode is always off inside Function.forward)
         y = torch.empty((B, Co, ld), device=dev) if train else None
         out = torch.empty((B, Co, ld), device=dev)
+        # the FQ_p codes of the masked features as a bf16 GEMM operand: what the decoder's tensor-core path reads
+        codes = torch.empty((B, Co, ld), dtype=bf, device=dev) if want_codes else torch.empty(0, dtype=bf, device=dev)
         check(L.fqss_mask_head_fwd(ptr(x_op), ptr(Wc), ptr(s1), ptr(s0), ptr(fv), Cf, ptr(qm_min), ptr(qm_max), ptr(qp_min),
-                                   ptr(qp_max), ptr(y) or None, ptr(out), B, Ci, Co, M, ld, s))
+                                   ptr(qp_max), ptr(y) or None, ptr(out), ptr(codes) if want_codes else None, B, Ci, Co, M, ld, s))
+        ctx.mark_non_differentiable(codes)
         ctx.save_for_backward(x_op, WcT, dws, W, wmin, wmax, qmin, qmax, y, fv, qm_min, qm_max, qp_min, qp_max)
         ctx.meta = (B, Ci, Co, Cf, M, ld, bias is not None)
-        return out[:, :, :M]
+        return out[:, :, :M], codes
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, g):
+    def backward(ctx, g, _g_codes=None):
         L = _libx()
         x_op, WcT, dws, W, wmin, wmax, qmin, qmax, y, fv, qm_min, qm_max, qp_min, qp_max = ctx.saved_tensors
         B, Ci, Co, Cf, M, ld, has_bias = ctx.meta
@@ -425,7 +428,7 @@ class MaskHead(Function):
         gwmin, gwmax = torch.empty_like(wmin), torch.empty_like(wmax)
         check(lib().fqss_fq_weight_bwd(ptr(dWq), ptr(W), ptr(gW), ptr(gwmin), ptr(gwmax), 1, Co, Ci, ptr(wmin), ptr(wmax), 8, s))
         return (gx, None, None, gW, gwmin, gwmax, g_bias, g_q[0:1].reshape(qm_min.shape), g_q[1:2].reshape(qm_max.shape),
-                g_feats[:, :, :M], g_q[2:3].reshape(qp_min.shape), g_q[3:4].reshape(qp_max.shape))
+                g_feats[:, :, :M], g_q[2:3].reshape(qp_min.shape), g_q[3:4].reshape(qp_max.shape), None)
 
 
 def mask_head_eligible(conv_layer, q_in, mul_layer, h, feats):
@@ -446,11 +449,13 @@ def mask_head_eligible(conv_layer, q_in, mul_layer, h, feats):
     return Cf % 32 == 0 and conv_layer.conv1d.out_channels % Cf == 0
 
 
-def mask_head(conv_layer, q_in, mul_layer, h, feats):
+def mask_head(conv_layer, q_in, mul_layer, h, feats, want_codes=False):
+    """-> (masked features [B, S*F, M] on the grid of the MulQ quantiser, their bf16 integer codes [B, S*F, ld] or None)."""
     conv, wq = conv_layer.conv1d, conv_layer.weight_fake_quantize
     qm, qp = conv_layer.activation_fake_quantize, mul_layer.activation_fake_quantize
-    return MaskHead.apply(h, q_in.min_range, q_in.max_range, conv.weight, wq.min_range, wq.max_range, conv.bias,
-                          qm.min_range, qm.max_range, feats, qp.min_range, qp.max_range)
+    out, codes = MaskHead.apply(h, q_in.min_range, q_in.max_range, conv.weight, wq.min_range, wq.max_range, conv.bias,
+                                qm.min_range, qm.max_range, feats, qp.min_range, qp.max_range, bool(want_codes))
+    return out, (codes if want_codes else None)
 
 
 class FusedTCNFunction(Function):

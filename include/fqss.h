@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 16
+#define FQSS_ABI_VERSION 17
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -400,12 +400,43 @@ int fqss_ola_bwd(const float* gout, int64_t ldo, float* gy, int64_t ldy, int64_t
  * ------------------------------------------------------------------------------------------- */
 int fqss_mask_head_fwd(const void* x_op_bf16, const void* w_bf16, const float* s1, const float* s0, const float* feats, int C,
                        const float* qm_min, const float* qm_max, const float* qp_min, const float* qp_max, float* y_save,
-                       float* masked, int B, int K, int N, int M, int64_t ld, void* stream);
+                       float* masked, void* masked_codes_bf16 /* may be NULL: the FQ_p codes as the decoder GEMM's operand */,
+                       int B, int K, int N, int M, int64_t ld, void* stream);
 size_t fqss_mask_head_ws_bytes(int N);
 int fqss_mask_head_bwd(const float* g, int64_t ldg, const float* y, const float* feats, const float* dws, const float* qm_min,
                        const float* qm_max, const float* qp_min, const float* qp_max, void* dY_bf16, float* g_feats, float* g_q,
                        float* g_bias, double* db_f64, int B, int C, int S, int M, int64_t ld, void* ws, size_t ws_bytes,
                        void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * L2  the filterbank edges on the tcgen05 GEMM (Conv1dEncoderQ qat_layers.py:993-1046, ConvTr1dDecoderQ :1305-1361,
+ *     ResidualErrorBlock :1105-1220).  The transposed conv to one channel is an overlap-add of per-frame tap vectors,
+ *       frames[r,k,m] = sum_o w[o,k] Y[r,o,m]   (a GEMM over the filters, taps as output channels; fqss_pw_gemm_nstore keeps
+ *       the 16 real columns of the 128 the tensor core computes),   y = fqss_ola_fwd(frames);
+ *     its gradients use the framed output gradient as a split-bf16 operand (fqss_frames_split: rows 0..L-1 hi, L..2L-1 lo,
+ *     zero up to 128; rowsum[2L] = fp64 sums of those rows): dgrad = fqss_pw_gemm(frames_split, [c | c | 0]) and wgrad =
+ *     fqss_wgrad_codes(frames_split, Y codes) folded by fqss_dec_wgrad_fold (hi + lo rows, transposed to [F][L]).
+ *     fqss_frames_encode frames a signal on an 8-bit grid into integer codes [R][KP][ld] (encoder-side operand, KP >= C*L rows);
+ *     fqss_sub_fq_codes is the RQB's FQ(Y - Yq) (qat_layers.py:1195) producing the codes the second decode consumes.
+ * ------------------------------------------------------------------------------------------- */
+int fqss_pw_gemm_nstore(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32, int n_store,
+                        int B, int K, int N, int M, int64_t ld, void* stream);
+int fqss_frames_split(const float* g, int64_t ldg, void* out_bf16, int64_t ldo, int64_t R, int M, int L, int H,
+                      int zero_rows /* 0: only rows < 2L are written (the caller keeps the others zero) */, double* rowsum,
+                      void* stream);
+int fqss_frames_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t R, int C, int M, int L, int H, int KP,
+                       const float* rmin, const float* rmax, void* stream);
+int fqss_sub_fq_codes(const float* a, int64_t lda, const float* b, int64_t ldb, void* out_bf16, int64_t ldo, int64_t rows, int M,
+                      const float* rmin, const float* rmax, void* stream);
+int fqss_dec_wgrad_fold(const float* part, float* dWq, int F, int L, void* stream);
+/* operand preparation (one tiny launch each).  Decoder weight W [F][L] with its per-tensor quantiser and the quantiser
+ * {amin, amax} of the incoming codes: Wc [128][F] bf16 (row k < L = code[.,k]), WT [F][128] bf16 = [code | code | 0], s1/s0
+ * [128] (forward affine; zero beyond L), dgs [F] = weight step (dgrad scale).  Encoder-type weight W [N][Kr] (Kr = C*L) with
+ * per-output-channel ranges: Wc [N][KP] bf16 codes (zero beyond Kr), s1/s0 [N]. */
+int fqss_edge_dec_prep(const float* W, const float* wmin, const float* wmax, const float* amin, const float* amax, void* Wc,
+                       void* WT, float* s1, float* s0, float* dgs, int F, int L, void* stream);
+int fqss_edge_enc_prep(const float* W, const float* wmin, const float* wmax, const float* amin, const float* amax, void* Wc,
+                       float* s1, float* s0, int N, int Kr, int KP, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * X1  export-time quantisers (qat_quant.py:15-72: TorchWeightFakeQuantize, TorchActivationFakeQuantize,

@@ -451,7 +451,7 @@ def test_mask_head_fused_vs_layers_and_oracle(B, M):
         return out
 
     E.KEEP_STATES = False
-    got = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1])
+    got, _ = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1])
     got.backward(g)
     g_fused = grads()
     # (a) the layers it replaces: code-operand conv -> ReLU + FQ -> x feats + FQ
@@ -473,5 +473,9 @@ def test_mask_head_fused_vs_layers_and_oracle(B, M):
     assert torch.equal(got.detach().cpu(), po.reshape(B, Co, M))
     # inference call (no grad): same values, no saved pre-activation
     with torch.no_grad():
-        inf = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1])
-    assert torch.equal(inf, got.detach())
+        inf, _ = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1])
+        inf2, codes = E.MaskHead.apply(x, qmin, qmax, W, wmin, wmax, bias, qm[0], qm[1], feats, qp[0], qp[1], True)
+    assert torch.equal(inf, got.detach()) and torch.equal(inf2, inf)
+    # the decoder GEMM's operand: the same tensor as integer codes of the MulQ quantiser (oracle's code function)
+    co = O.act_codes(po.reshape(B, Co, M), qp[0].detach().cpu(), qp[1].detach().cpu(), 8)
+    assert torch.equal(codes[:, :, :M].float().cpu(), co.detach())
