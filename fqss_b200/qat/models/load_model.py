@@ -6,6 +6,7 @@ from ..qat_layers import LayerQ
 from ..qat_quant import GradientActivationFakeQuantize, GradientWeightFakeQuantize
 from .convtasnetq import ConvTasNetQ
 from .convtasnetq_music import ConvTasNetMusicQ
+from .dptnetq import DPTNetQ
 
 
 def set_mac_op(model, mode=False):
@@ -25,10 +26,12 @@ def create_model(model_cfg):
     if name == "ConvTasNet":
         return ConvTasNetQ(n_spks=model_cfg.get("n_src", 1), kernel_size=model_cfg.get("kernel_size", 32),
                            stride=model_cfg.get("stride", 16))
+    if name == "DPTNet":
+        return DPTNetQ(n_spks=model_cfg.get("n_src", 2), kernel_size=model_cfg.get("kernel_size", 2))
     if name == "ConvTasNetMusic":
         return ConvTasNetMusicQ(sources=model_cfg.get("sources", ["drums", "bass", "other", "vocals"]),
                                 kernel=model_cfg.get("kernel_size", 20), stride=model_cfg.get("stride", 10))
-    raise NotImplementedError("fqss_b200 covers the ConvTasNet recipes (speech, music); model %r is out of scope" % name)
+    raise NotImplementedError("fqss_b200 covers the ConvTasNet recipes (speech, music) and DPTNet; model %r is out of scope" % name)
 
 
 def quantize_model(model, quant_cfg):

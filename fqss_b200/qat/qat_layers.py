@@ -12,6 +12,7 @@ import math
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import _native as N
 from .. import ops
@@ -63,6 +64,9 @@ class LayerQ(nn.Module):
         if isinstance(q, nn.Identity):
             return ops.pointwise_fq(kind, x1, x2, slope, gamma, beta, quant=False, eps=eps)
         raise NotImplementedError("unsupported activation quantiser %s" % type(q).__name__)
+
+
+_TORCH_NL = (nn.Tanh, nn.Sigmoid, nn.GELU, nn.LeakyReLU)      # nonlinearities without a fused kernel (DPTNetQ / SepformerQ gates)
 
 
 def _nl_kind(nl):
@@ -147,6 +151,8 @@ class MulQ(LayerQ):
         self.mul = mul
 
     def forward(self, x1, x2):
+        if torch.is_tensor(x2) and x1.dim() == 4 and x2.dim() == 4 and x1.shape[1] == 1 and x2.shape[1] > 1:
+            x1, x2 = x2, x1          # DPTNetQ multiplies (features[:, None], masks): the kernel broadcasts its SECOND operand
         if self.do_mac_op:
             self.mac_op = x1.numel()
         return self._finish(N.PW_MUL, x1, x2)
@@ -183,6 +189,8 @@ class Conv1dNlQ(LayerQ):
     def forward(self, x):
         y = _conv1d_q(self, x)
         self.calc_mac_op(x.shape)
+        if isinstance(self.nl, _TORCH_NL):      # gates of the sequence models (tanh / sigmoid): torch evaluates the nl, the
+            return self._finish(N.PW_IDENT, self.nl(y))     # quantiser runs on the library's kernel
         kind, slope = _nl_kind(self.nl)
         return self._finish(kind, y, slope=slope)
 
@@ -219,6 +227,12 @@ class LayerNormQ(LayerQ):
 
     def forward(self, x):
         ln = self.layernorm
+        if x.stride(-1) == 1 and x.shape[-1] > 1:
+            # feature-last tensors of the sequence models (DPTNetQ / SepformerQ: [seq, batch, d]): torch normalises, the
+            # quantiser runs on the library's kernel (see qat_layers_seq.py for the scope of that row)
+            if self.do_mac_op:
+                self.mac_op = 2 * x.numel()
+            return self.activation_fake_quantize(F.layer_norm(x, ln.normalized_shape, ln.weight, ln.bias, ln.eps))
         if len(ln.normalized_shape) != 1 or not ln.elementwise_affine or ln.bias is None or x.dim() != 3 \
                 or x.shape[-1] != ln.normalized_shape[0]:
             raise NotImplementedError("LayerNormQ: only LayerNorm(C) over the last axis of [B, M, C] (channel-wise cLN) has a kernel")
@@ -234,6 +248,8 @@ class NlQ(LayerQ):
         self.nl = nl
 
     def forward(self, x):
+        if isinstance(self.nl, _TORCH_NL):
+            return self._finish(N.PW_IDENT, self.nl(x))
         kind, slope = _nl_kind(self.nl)
         return self._finish(kind, x, slope=slope)
 
@@ -434,7 +450,15 @@ class LinearDecoderQ(LayerQ):
         return out if self.n_combiner >= 2 else out[0]
 
 
+# sequence-model layers (DPTNetQ / SepformerQ) live in qat_layers_seq.py; the reference keeps them in this module
+def _export_seq():
+    from . import qat_layers_seq as QS
+    for name in ("Const", "Div", "ConstQ", "DivQ", "LinearQ", "LinearNlQ", "Conv2dQ", "Conv2dNlQ", "LSTMQ", "MultiheadAttentionQ"):
+        globals()[name] = getattr(QS, name)
+
+
 # reference names outside the ConvTasNet hot path (imported by the reference's other model files): importable placeholders
 # that raise NotImplementedError when used -- see fqss_b200/shim.py
 from ..shim import module_getattr as _module_getattr  # noqa: E402
 __getattr__ = _module_getattr("quantization.qat.qat_layers")
+_export_seq()

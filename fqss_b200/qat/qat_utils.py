@@ -11,6 +11,7 @@ import copy
 import torch.nn as nn
 
 from . import qat_layers as QL
+from . import qat_layers_seq as QS
 from . import qat_quant as QQ
 
 
@@ -98,6 +99,38 @@ def quant_layernorm(layernorm, p):
     return QL.LayerNormQ(layernorm, **_common(p))
 
 
+def quant_conv2d(conv2d, p):
+    return QS.Conv2dQ(conv2d, **_weighted(p))
+
+
+def quant_conv2d_nl(conv2d, nl, p):
+    return QS.Conv2dNlQ(conv2d, nl, **_weighted(p))
+
+
+def quant_linear(linear, p):
+    return QS.LinearQ(linear, **_weighted(p))
+
+
+def quant_linear_nl(linear, nl, p):
+    return QS.LinearNlQ(linear, nl, **_weighted(p))
+
+
+def quant_lstm(lstm, p):
+    return QS.LSTMQ(lstm, **_weighted(p))
+
+
+def quant_mha(mha, p):
+    return QS.MultiheadAttentionQ(mha, **_weighted(p))
+
+
+def quant_const(const, p):
+    return QS.ConstQ(const, **_common(p))
+
+
+def quant_div(div, p):
+    return QS.DivQ(div, **_common(p))
+
+
 OP_LIST_TO_QUANTIZE_METHOD = {
     (nn.Conv1d): quant_conv1d,
     (nn.Conv1d, nn.PReLU): quant_conv1d_nl,
@@ -109,6 +142,20 @@ OP_LIST_TO_QUANTIZE_METHOD = {
     (QL.Add): quant_add,
     (QL.Sub): quant_sub,
     (QL.Mul): quant_mul,
+    # sequence models (DPTNetQ / SepformerQ; reference table qat_utils.py:354-401)
+    (nn.Conv1d, nn.Tanh): quant_conv1d_nl,
+    (nn.Conv1d, nn.Sigmoid): quant_conv1d_nl,
+    (nn.Conv2d): quant_conv2d,
+    (nn.Conv2d, nn.PReLU): quant_conv2d_nl,
+    (nn.Conv2d, nn.ReLU): quant_conv2d_nl,
+    (nn.Linear): quant_linear,
+    (nn.Linear, nn.ReLU): quant_linear_nl,
+    (nn.LSTM): quant_lstm,
+    (nn.MultiheadAttention): quant_mha,
+    (nn.Tanh): quant_nl,
+    (nn.Sigmoid): quant_nl,
+    (QS.Const): quant_const,
+    (QS.Div): quant_div,
 }
 
 
