@@ -272,7 +272,12 @@ def decoder_wants_codes(layer):
         return False
     if not _steady_wq(layer.weight_fake_quantize, 1) or layer.n_combiner > 2:
         return False
-    return layer.n_combiner == 1 or _steady_aq(layer.residual_error_block.activation_fake_quantize)
+    if layer.n_combiner == 1:
+        return True
+    rqb = layer.residual_error_block
+    if rqb.train_res_dec and not _steady_wq(rqb.weight_fake_quantize_dec, 1):
+        return False
+    return _steady_aq(rqb.activation_fake_quantize)
 
 
 def decoder_eligible(layer, x):
@@ -301,7 +306,9 @@ def decoder_forward(layer, x):
     rqb = layer.residual_error_block
     Yq = rqb.reencode(y)
     rq = rqb.activation_fake_quantize
-    y1_pre = SubFQDecode.apply(x_r, Yq, rq.min_range, rq.max_range, w_dec, dec.weight, wq.min_range, wq.max_range, H)
+    Wr, wqr = rqb.decode_weight(dec, wq)            # the decoder's own filterbank, or the block's (train_res_dec)
+    w_res = w_dec if Wr is dec.weight else wqr(Wr)
+    y1_pre = SubFQDecode.apply(x_r, Yq, rq.min_range, rq.max_range, w_res, Wr, wqr.min_range, wqr.max_range, H)
     y1 = layer._finish(N.PW_IDENT, y1_pre, quantizer=layer.activation_fake_quantize_residual)
     return torch.stack([y, y1])
 

@@ -7,6 +7,7 @@ from ..qat_quant import GradientActivationFakeQuantize, GradientWeightFakeQuanti
 from .convtasnetq import ConvTasNetQ
 from .convtasnetq_music import ConvTasNetMusicQ
 from .dptnetq import DPTNetQ
+from .sepformerq import SepformerQ
 
 
 def set_mac_op(model, mode=False):
@@ -28,10 +29,13 @@ def create_model(model_cfg):
                            stride=model_cfg.get("stride", 16))
     if name == "DPTNet":
         return DPTNetQ(n_spks=model_cfg.get("n_src", 2), kernel_size=model_cfg.get("kernel_size", 2))
+    if name == "Sepformer":
+        return SepformerQ(n_spks=model_cfg.get("n_src", 2), kernel_size=model_cfg.get("kernel_size", 16),
+                          stride=model_cfg.get("stride", 8))
     if name == "ConvTasNetMusic":
         return ConvTasNetMusicQ(sources=model_cfg.get("sources", ["drums", "bass", "other", "vocals"]),
                                 kernel=model_cfg.get("kernel_size", 20), stride=model_cfg.get("stride", 10))
-    raise NotImplementedError("fqss_b200 covers the ConvTasNet recipes (speech, music) and DPTNet; model %r is out of scope" % name)
+    raise NotImplementedError("fqss_b200 covers the ConvTasNet recipes (speech, music), DPTNet and Sepformer; model %r is out of scope" % name)
 
 
 def quantize_model(model, quant_cfg):

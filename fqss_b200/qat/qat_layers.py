@@ -129,6 +129,8 @@ class AddQ(LayerQ):
         self.add = add
 
     def forward(self, x1, x2):
+        if x1.shape != x2.shape:         # e.g. SepformerQ's positional table [1, T, F] added to [B, T, F]
+            x1, x2 = torch.broadcast_tensors(x1, x2)
         return self._finish(N.PW_ADD, x1, x2)
 
 
@@ -210,6 +212,10 @@ class GroupNormQ(LayerQ):
             raise NotImplementedError("only gLN = GroupNorm(1, C, affine=True) is on the ConvTasNet path")
         if self.do_mac_op:
             self.mac_op = 2 * x.numel()
+        if x.dim() == 4:        # [B, C, K, S] chunked features of the dual-path models: per-sample statistics over (C, K, S)
+            B, Cc, K, S = x.shape
+            y = self._finish(N.PW_GLN, x.reshape(B, Cc, K * S), gamma=gn.weight, beta=gn.bias, eps=gn.eps)
+            return y.reshape(B, Cc, K, S)
         return self._finish(N.PW_GLN, x, gamma=gn.weight, beta=gn.bias, eps=gn.eps)
 
 
@@ -313,8 +319,8 @@ class ResidualErrorBlock(LayerQ):
                  weight_n_bits=8, train_res_dec=False):
         super().__init__(gradient_based=gradient_based, act_quant=act_quant, act_nl_quantizer=act_nl_quantizer,
                          act_n_bits=act_n_bits)
-        if train_res_dec or decoder.bias is not None:
-            raise NotImplementedError("RQB is implemented for bias-free decoders without train_res_dec")
+        if decoder.bias is not None or (train_res_dec and type(decoder) is not nn.ConvTranspose1d):
+            raise NotImplementedError("RQB is implemented for bias-free decoders (train_res_dec: ConvTranspose1d only)")
         self.train_res_dec = train_res_dec
         self.decoder_bias = None
         if type(decoder) is nn.Linear:       # ConvTasNetMusicQ: per-frame Linear decoder (qat_layers.py:1110-1121)
@@ -334,8 +340,20 @@ class ResidualErrorBlock(LayerQ):
         self.decoder_padding, self.decoder_output_padding = decoder.padding, decoder.output_padding
         self.decoder_dilation, self.decoder_groups = decoder.dilation, decoder.groups
         self.decoder_in_channels, self.decoder_out_channels = decoder.in_channels, decoder.out_channels
+        if train_res_dec:       # SepformerQ: the residual is decoded by its own trainable filterbank (qat_layers.py:1138-1147)
+            self.residual_decoder = nn.ConvTranspose1d(decoder.in_channels, decoder.out_channels, decoder.kernel_size,
+                                                       stride=decoder.stride, bias=False).to(decoder.weight.device)
+            self.weight_fake_quantize_dec = (get_weight_quantizer(gradient_based, self.residual_decoder.weight.shape, ch_out_idx=1,
+                                                                  n_bits=weight_n_bits) if weight_quant else nn.Identity())
         self.weight_fake_quantize = (get_weight_quantizer(gradient_based, self.residual_encoder.weight.shape,
                                                           n_bits=weight_n_bits) if weight_quant else nn.Identity())
+
+    def decode_weight(self, dec, wq):
+        """(raw weight, its quantiser) of the filterbank that decodes the residual: the block's own when train_res_dec, else
+        the decoder's (`dec`, `wq`)."""
+        if self.train_res_dec:
+            return self.residual_decoder.weight, self.weight_fake_quantize_dec
+        return dec.weight, wq
 
     def reencode(self, y_q):
         """Yq = residual_encoder(y_q) with the fake-quantised re-encoder weight (qat_layers.py:1189); y_q lies on the grid of
@@ -356,6 +374,8 @@ class ResidualErrorBlock(LayerQ):
             return ops.Conv1x1.apply(Y1, w_decoder.unsqueeze(-1), None)
         Yq = self.reencode(y_q)
         Y1 = self._finish(N.PW_SUB, Y, Yq)
+        if self.train_res_dec:
+            w_decoder = self.weight_fake_quantize_dec(self.residual_decoder.weight)
         return ops.TransposedConv1.apply(Y1, w_decoder, self.decoder_stride[0])
 
 

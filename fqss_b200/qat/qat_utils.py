@@ -85,13 +85,13 @@ def quant_decoderq(decoder, p):
                                    weight_quant=p.get("weight_quant", True), weight_n_bits=p.get("weight_n_bits", 8),
                                    act_quant=p.get("act_quant", True), act_n_bits=p.get("act_n_bits", 8),
                                    inout_nl_quant=p.get("inout_nl_quant", False), out_quant=p.get("out_quant", True),
-                                   out_act_n_bits=p.get("out_act_n_bits", 8))
+                                   out_act_n_bits=p.get("out_act_n_bits", 8), train_res_dec=bool(p.get("train_res_dec", False)))
     if isinstance(decoder[0], nn.Linear):
         return QL.LinearDecoderQ(decoder, n_combiner=p.get("n_combiner", 1), gradient_based=p.get("gradient_based", True),
                                  weight_quant=p.get("weight_quant", True), weight_n_bits=p.get("weight_n_bits", 8),
                                  act_quant=p.get("act_quant", True), act_n_bits=p.get("act_n_bits", 8),
                                  inout_nl_quant=p.get("inout_nl_quant", False), out_quant=p.get("out_quant", True),
-                                 out_act_n_bits=p.get("out_act_n_bits", 8), train_res_dec=p.get("train_res_dec", False))
+                                 out_act_n_bits=p.get("out_act_n_bits", 8), train_res_dec=bool(p.get("train_res_dec", False)))
     raise NotImplementedError("decoder type %s is out of scope (ConvTranspose1d and Linear decoders only)" % type(decoder[0]).__name__)
 
 

@@ -5,10 +5,11 @@
 After `install()` the reference's own callers -- `quantization/qat/models/load_model.py:21-102`,
 `train_env/train_utils.py:8-27`, `train_env/asteroid_librimix/mysystem.py:88-151` -- run UNCHANGED: their
 `from quantization.qat...` / `from train_env.asteroid_librimix.wsdr import *` imports resolve to the mirrors in
-`fqss_b200`.  Only the ConvTasNet recipe is in scope: the names the reference's other model files import from
-`quantization.qat.qat_layers / qat_utils / qat_quant` (Const, Div, LinearQ, LSTMQ, ...) exist as placeholders so that the
-un-shimmed `load_model.py` (which imports all five models at its top, `load_model.py:2-6`) still imports; USING one of
-them raises NotImplementedError naming the scope.
+`fqss_b200`.  In scope: the ConvTasNet recipes (speech, music) and the sequence models DPTNetQ / SepformerQ; the names the
+reference's remaining model files (the Demucs family) import from `quantization.qat.qat_layers / qat_utils / qat_quant`
+(Conv2dEncoderQ, ConvTr2dDecoderQ, EmbeddingQ, BatchNormQ, ...) exist as placeholders so that the un-shimmed `load_model.py`
+(which imports all five models at its top, `load_model.py:2-6`) still imports; USING one of them raises NotImplementedError
+naming the scope.
 """
 import sys
 import types
@@ -23,7 +24,7 @@ def out_of_scope(module_name, name):
     key = (module_name, name)
     if key in _PLACEHOLDER_CACHE:
         return _PLACEHOLDER_CACHE[key]
-    msg = ("%s.%s is outside the scope of fqss_b200 (the fake-quantised ConvTasNet QAT path); run that model without "
+    msg = ("%s.%s is outside the scope of fqss_b200 (the fake-quantised ConvTasNet / DPTNet / Sepformer QAT paths); run that model without "
            "fqss_b200.shim.install()" % (module_name, name))
     if name[:1].isupper():
         def __init__(self, *a, **kw):
@@ -52,6 +53,9 @@ _ALIASES = {
     "quantization.qat.qat_layers": "fqss_b200.qat.qat_layers",
     "quantization.qat.qat_utils": "fqss_b200.qat.qat_utils",
     "quantization.qat.models.convtasnetq": "fqss_b200.qat.models.convtasnetq",
+    "quantization.qat.models.convtasnetq_music": "fqss_b200.qat.models.convtasnetq_music",
+    "quantization.qat.models.dptnetq": "fqss_b200.qat.models.dptnetq",
+    "quantization.qat.models.sepformerq": "fqss_b200.qat.models.sepformerq",
     "train_env.asteroid_librimix.wsdr": "fqss_b200.wsdr",
 }
 

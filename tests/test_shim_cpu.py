@@ -54,21 +54,20 @@ LM.set_mac_op(model, True)
 import train_env.asteroid_librimix.mysystem as MS
 assert MS.PairwiseWSDR.__module__ == "fqss_b200.wsdr" and MS.PITLossWrapper.__module__ == "fqss_b200.wsdr"
 # --- out of scope: importable, not usable
-from quantization.qat.qat_layers import Const, LinearQ
-for cls in (Const, LinearQ):
+from quantization.qat.qat_layers import EmbeddingQ, BatchNormQ, Conv2dEncoderQ
+for cls in (EmbeddingQ, BatchNormQ, Conv2dEncoderQ):
     try:
         cls()
     except NotImplementedError as e:
         assert "outside the scope" in str(e)
     else:
         raise AssertionError("placeholder was usable")
-dpt = LM.create_model(dict(name="DPTNet"))          # the float graph is plain torch: still constructible
-try:
-    LM.quantize_model(dpt, dict(mc["quantization"]))
-except NotImplementedError:
-    pass
-else:
-    raise AssertionError("quantising DPTNet must be refused under the shim")
+# --- the sequence models through the reference's factory: our mirrors, quantised by the reference's quantize_model
+for name, mod, nq in (("DPTNet", "fqss_b200.qat.models.dptnetq", None), ("Sepformer", "fqss_b200.qat.models.sepformerq", None)):
+    m = LM.create_model(dict(name=name, n_src=2))
+    assert type(m).__module__ == mod, type(m).__module__
+    m = LM.quantize_model(m, dict(mc["quantization"]))
+    assert any(isinstance(q, AQ) for q in m.modules()) and m.n_splitter == 2
 print("SHIM-OK")
 """
 
