@@ -38,9 +38,10 @@ def parse():
     ap.add_argument("--impl", default="fqss_b200", choices=["fqss_b200", "reference"])
     ap.add_argument("--per-gpu-batch", type=int, default=32)
     ap.add_argument("--global-batch", type=int, default=0, help=">0: strong scaling with this global batch")
-    ap.add_argument("--workload", default="speech", choices=["speech", "music"],
+    ap.add_argument("--workload", default="speech", choices=["speech", "music", "dptnet", "sepformer"],
                     help="speech (default): BASELINE configs[1], the graded line.  music: BASELINE configs[4] (ConvTasNetMusicQ, "
-                         "4 stems, stereo 44.1 kHz, 80 000-sample segments, batch 8 per GPU) -- an extra line, single GPU")
+                         "4 stems, stereo 44.1 kHz, 80 000-sample segments, batch 8 per GPU); dptnet / sepformer: BASELINE configs[2] / [3] "
+                         "(batch 1, 3 s / 4 s at 8 kHz) -- extra lines, single GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--small", action="store_true", help="reduced model (debug only; never a reported number)")
@@ -583,11 +584,114 @@ def run_music(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# extra workloads: BASELINE configs[2] / [3], the sequence models (configs/dptnet_2spks_8k.yaml, sepformer_2spks_8k.yaml)
+# ---------------------------------------------------------------------------------------------
+def run_seq(args):
+    """One QAT step of DPTNetQ / SepformerQ per timed step: fake-quantised student forward, float teacher forward, the FQSS
+    KD SI-SDR loss (fused kernel), backward, global-norm clip + Adam on the flat arena.  Quantisers, filterbanks, norms and
+    gates run on libfqss_sm100; attention / LSTM / Linear float math on torch (qat_layers_seq.py)."""
+    import copy
+    import torch
+    from fqss_b200 import _native as N
+    from fqss_b200 import roofline as R
+    from fqss_b200.losses import fqss_training_step
+    from fqss_b200.parallel import ParamArena
+    from fqss_b200.qat.models.load_model import create_model, enable_observer, quantize_model
+    from fqss_b200.testing import RECIPE_QUANT
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the fqss_b200 arm has no CPU fallback)")
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("bench.py --workload %s is a single-GPU line" % args.workload)
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    N.lib()
+    name, secs_seg, lr = ("DPTNet", 3.0, 4e-4) if args.workload == "dptnet" else ("Sepformer", 4.0, 1.5e-4)
+    B = 1 if args.per_gpu_batch == 32 else args.per_gpu_batch          # recipe batch size: 1 (both YAMLs)
+    Ts = int(secs_seg * SAMPLE_RATE)
+    torch.manual_seed(0)
+    cfg = dict(name=name, n_src=2, kernel_size=2) if name == "DPTNet" else dict(name=name, n_src=2, kernel_size=16, stride=8)
+    model = create_model(cfg)
+    fmodel = copy.deepcopy(model).to(dev)
+    model = quantize_model(model, dict(RECIPE_QUANT)).to(dev)
+    for p in fmodel.parameters():
+        p.requires_grad_(False)
+    gen = torch.Generator().manual_seed(7)
+    host = []
+    for _ in range(2):
+        src = (torch.randn(B, 2, Ts, generator=gen) * 0.05).pin_memory()
+        host.append((src.sum(1, keepdim=True).pin_memory(), src))
+    dev_batches = [(m.to(dev), s_.to(dev)) for m, s_ in host]
+    with torch.no_grad():
+        model(dev_batches[0][0]); model(dev_batches[0][0])
+    enable_observer(model, False)
+    arena = ParamArena(list(model.parameters()))
+
+    def step(mix, src):
+        arena.zero_grad()
+        loss, _, est = fqss_training_step(model, fmodel, mix, src[..., :], 0.1, overlap_teacher=False)
+        loss.backward()
+        arena.gather_grads()
+        arena.clip_and_step(pre_scale=1.0, max_norm=5.0, lr=lr)
+        return loss
+
+    # the estimate is a few samples shorter / longer than the segment for some geometries: trim the targets once
+    with torch.no_grad():
+        Te = model(dev_batches[0][0]).shape[-1]
+    dev_batches = [(m, s_[..., :Te].contiguous()) for m, s_ in dev_batches]
+    W = max(args.warmup, 3)
+    for i in range(W):
+        step(*dev_batches[i % 2])
+    torch.cuda.synchronize()
+    c0 = R.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    time.sleep(0.3)
+    tw0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = step(*dev_batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    tw1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = R.launch_count() - c0
+    loss_host = torch.zeros(1).pin_memory()
+    e0.record()
+    for i in range(args.steps):
+        m, s_ = host[i % 2]
+        loss = step(m.to(dev, non_blocking=True), s_.to(dev, non_blocking=True)[..., :Te].contiguous())
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    clocks = sampler.stop(tw0, tw1)
+    secs = B * secs_seg
+    line = {"metric": "%s QAT train audio-sec/sec" % name, "value": secs * args.steps / (ms / 1e3), "unit": "audio-s/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": W, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (8-bit fake-quant codes)", "data": "synthetic",
+            "config": {"workload": "%s 2spk 8 kHz QAT (W8A8, splitter/combiner 2/2, KD SI-SDR vs float teacher, lambda 0.1), "
+                                   "%.0f s segments" % (name, secs_seg), "global_batch": B, "per_gpu_batch": B,
+                       "segment_s": secs_seg, "sample_rate": SAMPLE_RATE, "parallelism": "dp1",
+                       "l2": "no explicit flush (extra line, not the graded workload)"},
+            "e2e": {"value": secs * args.steps / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * 3 * Ts * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss_host.item()),
+            "launch_mode": "eager; library kernels for quantisers / filterbanks / norms / gates / loss / optimizer, torch for "
+                           "attention, LSTM and Linear float math",
+            "note": "extra line (BASELINE configs[%d]); the graded line is the default speech workload" % (2 if name == "DPTNet" else 3)}
+    print(json.dumps(line), flush=True)
+
+
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
     elif a.workload == "music":
         run_music(a)
+    elif a.workload in ("dptnet", "sepformer"):
+        run_seq(a)
     else:
         run_ours(a)
