@@ -312,12 +312,22 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     from fqss_b200 import roofline as R
+    # the end-to-end loop (the headline number) is timed first, the HBM-resident loop second: the board heats up over the first
+    # seconds of load and the second loop runs ~1.3 % slower whatever it is (measured by alternating the two loops:
+    # FQSS_BENCH_DRIFT=1); the copies themselves cost ~0.1 ms per step
+    ms_e2e, t0, _ = timed(args.steps, True)
     c0 = R.launch_count()
-    ms, t0, t1 = timed(args.steps, False)
+    ms, _, t2 = timed(args.steps, False)
+    t1 = t2
     launches = R.launch_count() - c0          # kernels launched by libfqss_sm100 inside the timed region
     if graphed is not None:                   # replays launch the captured nodes without re-entering the library
         launches = graphed.kernels_per_replay * args.steps
-    ms_e2e, _, t2 = timed(args.steps, True)
+    drift = None
+    if os.environ.get("FQSS_BENCH_DRIFT"):      # diagnostic: alternate the two loops again (clock / thermal drift vs a real e2e cost)
+        drift = [timed(args.steps, False)[0] / args.steps, timed(args.steps, True)[0] / args.steps,
+                 timed(args.steps, False)[0] / args.steps, timed(args.steps, True)[0] / args.steps]
+        if rank == 0:
+            print("drift check (ms/step: resident, e2e, resident, e2e):", drift, flush=True)
     clocks = sampler.stop(t0, t2) if rank == 0 else None
     final_loss = float(loss_host.item())
 
@@ -643,6 +653,16 @@ def run_seq(args):
     for i in range(W):
         step(*dev_batches[i % 2])
     torch.cuda.synchronize()
+    # the eager step is bound by host-side launch work (thousands of small kernels per step): replay it as ONE CUDA graph
+    graphed, graph_error = None, None
+    if args.cuda_graph:
+        from fqss_b200.graph import GraphedStep
+        try:
+            graphed = GraphedStep(step, dev_batches[0], warmup=2)
+        except Exception as e:
+            graph_error = repr(e)[:200]
+            torch.cuda.synchronize()
+    run = (lambda m, s_: graphed(m, s_)) if graphed is not None else step
     c0 = R.launch_count()
     sampler = ClockSampler(0)
     sampler.start()
@@ -651,17 +671,17 @@ def run_seq(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        loss = step(*dev_batches[i % 2])
+        loss = run(*dev_batches[i % 2])
     e1.record()
     torch.cuda.synchronize()
     tw1 = time.time()
     ms = e0.elapsed_time(e1)
-    launches = R.launch_count() - c0
+    launches = graphed.kernels_per_replay * args.steps if graphed is not None else R.launch_count() - c0
     loss_host = torch.zeros(1).pin_memory()
     e0.record()
     for i in range(args.steps):
         m, s_ = host[i % 2]
-        loss = step(m.to(dev, non_blocking=True), s_.to(dev, non_blocking=True)[..., :Te].contiguous())
+        loss = run(m.to(dev, non_blocking=True), s_.to(dev, non_blocking=True)[..., :Te].contiguous())
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.current_stream().synchronize()
     e1.record()
@@ -679,9 +699,19 @@ def run_seq(args):
             "e2e": {"value": secs * args.steps / (ms_e2e / 1e3), "unit": "audio-s/s", "h2d_bytes_per_step": B * 3 * Ts * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "final_loss": float(loss_host.item()),
-            "launch_mode": "eager; library kernels for quantisers / filterbanks / norms / gates / loss / optimizer, torch for "
-                           "attention, LSTM and Linear float math",
+            "launch_mode": ("one CUDA graph per step" if graphed is not None else "eager (graph capture failed: %s)" % graph_error
+                            if args.cuda_graph else "eager") + "; library kernels for quantisers / filterbanks / norms / gates / "
+                           "LSTM recurrence / loss / optimizer, torch for attention and Linear float math",
             "note": "extra line (BASELINE configs[%d]); the graded line is the default speech workload" % (2 if name == "DPTNet" else 3)}
+    if not args.no_roofline:
+        try:
+            prof = R.profile(lambda: step(*dev_batches[0]), 1)
+            tot = sum(v["ms"] for v in prof.values())
+            line["library_kernel_ms_per_step"] = round(tot, 3)
+            line["kernels"] = [{"kernel": k, "ms_per_step": round(v["ms"], 3), "launches_per_step": v["kernels"]}
+                               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]]
+        except Exception as e:
+            line["kernels"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
 
 

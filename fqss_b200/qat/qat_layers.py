@@ -470,15 +470,18 @@ class LinearDecoderQ(LayerQ):
         return out if self.n_combiner >= 2 else out[0]
 
 
-# sequence-model layers (DPTNetQ / SepformerQ) live in qat_layers_seq.py; the reference keeps them in this module
-def _export_seq():
-    from . import qat_layers_seq as QS
-    for name in ("Const", "Div", "ConstQ", "DivQ", "LinearQ", "LinearNlQ", "Conv2dQ", "Conv2dNlQ", "LSTMQ", "MultiheadAttentionQ"):
-        globals()[name] = getattr(QS, name)
-
-
-# reference names outside the ConvTasNet hot path (imported by the reference's other model files): importable placeholders
-# that raise NotImplementedError when used -- see fqss_b200/shim.py
+# sequence-model layers (DPTNetQ / SepformerQ) live in qat_layers_seq.py; the reference keeps them in this module, so they are
+# resolved lazily here (qat_layers_seq imports LayerQ from this module).  Any other reference name outside the scoped paths
+# (imported by the reference's remaining model files) is an importable placeholder that raises NotImplementedError when used --
+# see fqss_b200/shim.py
 from ..shim import module_getattr as _module_getattr  # noqa: E402
-__getattr__ = _module_getattr("quantization.qat.qat_layers")
-_export_seq()
+
+_SEQ_NAMES = ("Const", "Div", "ConstQ", "DivQ", "LinearQ", "LinearNlQ", "Conv2dQ", "Conv2dNlQ", "LSTMQ", "MultiheadAttentionQ")
+_placeholder = _module_getattr("quantization.qat.qat_layers")
+
+
+def __getattr__(name):
+    if name in _SEQ_NAMES:
+        from . import qat_layers_seq as QS
+        return getattr(QS, name)
+    return _placeholder(name)

@@ -4,10 +4,11 @@ reference's attribute names (= state-dict keys) and constructor signatures.
 
 Scope of the native code on this row: every QUANTISER -- per-channel weight fake-quant, per-tensor activation fake-quant
 with learnable ranges, observers, their straight-through backward and range gradients -- runs on the sm_100a kernels of
-libfqss_sm100 (csrc/fq_ops.cu: bit-exact against the reference's arithmetic, no host syncs).  The dense float math between
-two quantisers (F.linear, the LSTM recurrence, the attention products and softmax) is delegated to torch, as in the
-reference itself (which calls _VF.lstm / torch.bmm): these models are the "next" rows of the scope table, not the hot
-path, and have no dedicated GEMM / recurrence kernels here.
+libfqss_sm100 (csrc/fq_ops.cu: bit-exact against the reference's arithmetic, no host syncs), and so does the LSTM RECURRENCE
+(csrc/lstm.cu: the 8-bit codes of the fake-quantised recurrent weights stay in registers for the whole sequence, forward
+and backward).  The remaining dense float math between two quantisers (F.linear incl. the LSTM's batched input projection,
+the attention products and softmax) is delegated to torch, as in the reference itself (which calls _VF.lstm / torch.bmm):
+these models are the "next" rows of the scope table, not the hot path.
 """
 import math
 
@@ -16,8 +17,58 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import _VF
 
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from .. import _native as N
+from .._native import check, lib, ptr, stream_ptr
 from .qat_layers import LayerQ
-from .qat_quant import get_activation_quantizer, get_weight_quantizer
+from .qat_quant import GradientWeightFakeQuantize, get_activation_quantizer, get_weight_quantizer
+
+import os as _os
+
+NATIVE_LSTM = _os.environ.get("FQSS_NATIVE_LSTM", "1") not in ("", "0")      # False: the recurrence of LSTMQ stays on torch's LSTM (A/B runs, tests)
+
+
+class LSTMRecurrence(Function):
+    """h_t of a one-layer (bi)directional LSTM from its input projections gx [D,T,N,4H], on the register-resident integer-code
+    kernels of csrc/lstm.cu.  whh_fq [D,4H,H] (the fake-quantised recurrent weights) carries the autograd edge; the kernels
+    re-derive the same codes / steps from the raw weights and their quantiser ranges."""
+
+    @staticmethod
+    def forward(ctx, gx, whh_fq, W0, W1, mn0, mn1, mx0, mx1):
+        N.require_cuda(gx, whh_fq, W0, W1, mn0, mn1, mx0, mx1)
+        D, T, nb, G = gx.shape
+        H = G // 4
+        gx = gx.contiguous()
+        dev = gx.device
+        out = torch.empty((T, nb, D * H), device=dev)
+        gates = torch.empty((D, T, nb, G), device=dev)
+        cseq = torch.empty((D, T, nb, H), device=dev)
+        W0c, W1c = W0.detach().contiguous(), (W1.detach().contiguous() if W1 is not None else None)
+        check(lib().fqss_lstm_rec_fwd(ptr(gx), ptr(W0c), ptr(W1c) or None, ptr(mn0), ptr(mn1) or None, ptr(mx0), ptr(mx1) or None,
+                                      ptr(out), ptr(gates), ptr(cseq), T, nb, H, D, stream_ptr()))
+        ctx.save_for_backward(out, gates, cseq, W0c, W1c, mn0, mn1, mx0, mx1)
+        ctx.dims = (D, T, nb, H)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        out, gates, cseq, W0c, W1c, mn0, mn1, mx0, mx1 = ctx.saved_tensors
+        D, T, nb, H = ctx.dims
+        dout = dout.contiguous()
+        dG = torch.empty((D, T, nb, 4 * H), device=dout.device)
+        check(lib().fqss_lstm_rec_bwd(ptr(dout), ptr(gates), ptr(cseq), ptr(W0c), ptr(W1c) or None, ptr(mn0), ptr(mn1) or None, ptr(mx0),
+                                      ptr(mx1) or None, ptr(dG), T, nb, H, D, stream_ptr()))
+        # dW_hh[d] = sum_t dG[d, t]^T h_{t-1}: one batched GEMM per direction on the previous hidden states
+        zero = out.new_zeros(1, nb, H)
+        dW = []
+        for d in range(D):
+            hd = out[:, :, d * H:(d + 1) * H]
+            hprev = torch.cat([zero, hd[:-1]], 0) if d == 0 else torch.cat([hd[1:], zero], 0)
+            dW.append(dG[d].reshape(T * nb, 4 * H).t() @ hprev.reshape(T * nb, H))
+        return dG, torch.stack(dW), None, None, None, None, None, None
 
 
 class Const(nn.Module):
@@ -126,7 +177,42 @@ class LSTMQ(LayerQ):
                 self.weight_quantizers_dict[name] = (get_weight_quantizer(gradient_based, w.shape, n_bits=weight_n_bits)
                                                      if weight_quant else nn.Identity())
 
+    def _native_ok(self, x):
+        lstm = self.lstm
+        if not NATIVE_LSTM or not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3:
+            return False
+        if lstm.num_layers != 1 or lstm.proj_size != 0 or not lstm.bias or lstm.hidden_size not in (32, 64, 128):
+            return False
+        for name in lstm._flat_weights_names:
+            if name.startswith("weight_hh"):
+                q = self.weight_quantizers_dict[name]
+                if not isinstance(q, GradientWeightFakeQuantize) or q.observer_mode or q.n_bits != 8 or q.axis != 0:
+                    return False
+        return True
+
+    def _forward_native(self, x):
+        """Input projections of all steps as one GEMM per direction (torch), the recurrence on csrc/lstm.cu."""
+        lstm = self.lstm
+        if lstm.batch_first:
+            x = x.transpose(0, 1)
+        gx, whh, raw, mn, mx = [], [], [], [], []
+        for sfx in ("", "_reverse")[: self.num_directions]:
+            q_ih, q_hh = self.weight_quantizers_dict["weight_ih_l0" + sfx], self.weight_quantizers_dict["weight_hh_l0" + sfx]
+            w_ih, w_hh = getattr(lstm, "weight_ih_l0" + sfx), getattr(lstm, "weight_hh_l0" + sfx)
+            bias = getattr(lstm, "bias_ih_l0" + sfx) + getattr(lstm, "bias_hh_l0" + sfx)
+            gx.append(F.linear(x, q_ih(w_ih), bias))
+            whh.append(q_hh(w_hh))
+            raw.append(w_hh)
+            mn.append(q_hh.min_range)
+            mx.append(q_hh.max_range)
+        two = self.num_directions == 2
+        y = LSTMRecurrence.apply(torch.stack(gx), torch.stack(whh), raw[0], raw[1] if two else None, mn[0], mn[1] if two else None,
+                                 mx[0], mx[1] if two else None)
+        return y.transpose(0, 1) if lstm.batch_first else y
+
     def forward(self, x):
+        if self._native_ok(x):
+            return [self.activation_fake_quantize(self._forward_native(x))]
         lstm = self.lstm
         flat = []
         for name in lstm._flat_weights_names:

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 17
+#define FQSS_ABI_VERSION 18
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -437,6 +437,26 @@ int fqss_edge_dec_prep(const float* W, const float* wmin, const float* wmax, con
                        void* WT, float* s1, float* s0, float* dgs, int F, int L, void* stream);
 int fqss_edge_enc_prep(const float* W, const float* wmin, const float* wmax, const float* amin, const float* amax, void* Wc,
                        float* s1, float* s0, int N, int Kr, int KP, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * R1  recurrence of the quantised LSTM (LSTMQ, qat_layers.py:571-613: nn.LSTM evaluated with fake-quantised weights, zero
+ *     initial state; DPTNetQ's improved transformer layer, models/dptnetq.py:57-97).  One layer, D = 1 or 2 directions
+ *     (direction 1 runs the sequence backwards), hidden size H in {32, 64, 128}, gate order i, f, g, o as torch.
+ *       gx    [D][T][N][4H]  input projections x W_ih^T + b_ih + b_hh of every step (a batched GEMM outside)
+ *       whh*  [4H][H] raw recurrent weights of direction 0 / 1, wmin* / wmax* [4H] the ranges of their per-row 8-bit
+ *             quantisers: the kernels derive the integer codes and steps themselves (same arithmetic as fqss_fq_weight_fwd)
+ *             and keep the codes register-resident for all T steps
+ *       out   [T][N][D*H]    hidden states (direction d in columns d*H .. d*H+H-1)
+ *       gates [D][T][N][4H]  activated gates, cseq [D][T][N][H] cell states (saved for backward)
+ *     bwd: dout [T][N][D*H] -> dG [D][T][N][4H], the gradient of gx (= of the pre-activations); the weight gradient is
+ *          dG^T h_{t-1} summed over steps, a batched GEMM outside.
+ * ------------------------------------------------------------------------------------------- */
+int fqss_lstm_rec_fwd(const float* gx, const float* whh0, const float* whh1, const float* wmin0, const float* wmin1,
+                      const float* wmax0, const float* wmax1, float* out, float* gates, float* cseq, int T, int N, int H, int D,
+                      void* stream);
+int fqss_lstm_rec_bwd(const float* dout, const float* gates, const float* cseq, const float* whh0, const float* whh1,
+                      const float* wmin0, const float* wmin1, const float* wmax0, const float* wmax1, float* dG, int T, int N,
+                      int H, int D, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * X1  export-time quantisers (qat_quant.py:15-72: TorchWeightFakeQuantize, TorchActivationFakeQuantize,
