@@ -111,6 +111,9 @@ _SIGS = {
     "fqss_pw_gemm_nstore": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
     "fqss_frames_split": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp]),
     "fqss_frames_encode": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "fqss_attn_smem_bytes": (sz, [i32, i32, i32]),
+    "fqss_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
+    "fqss_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "fqss_lstm_rec_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "fqss_lstm_rec_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "fqss_edge_dec_prep": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
@@ -152,7 +155,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 18:
+                if L.fqss_abi_version() != 19:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

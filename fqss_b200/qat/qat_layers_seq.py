@@ -4,10 +4,11 @@ reference's attribute names (= state-dict keys) and constructor signatures.
 
 Scope of the native code on this row: every QUANTISER -- per-channel weight fake-quant, per-tensor activation fake-quant
 with learnable ranges, observers, their straight-through backward and range gradients -- runs on the sm_100a kernels of
-libfqss_sm100 (csrc/fq_ops.cu: bit-exact against the reference's arithmetic, no host syncs), and so does the LSTM RECURRENCE
+libfqss_sm100 (csrc/fq_ops.cu: bit-exact against the reference's arithmetic, no host syncs), and so do the LSTM RECURRENCE
 (csrc/lstm.cu: the 8-bit codes of the fake-quantised recurrent weights stay in registers for the whole sequence, forward
-and backward).  The remaining dense float math between two quantisers (F.linear incl. the LSTM's batched input projection,
-the attention products and softmax) is delegated to torch, as in the reference itself (which calls _VF.lstm / torch.bmm):
+and backward) and the ATTENTION CORE softmax(q k^T) v (csrc/attention.cu: one pass per direction, the score tensor is never
+materialised).  The remaining dense float math between two quantisers (F.linear incl. the LSTM's batched input projection
+and the attention's in / out projections, LayerNorm) is delegated to torch, as in the reference itself (which calls _VF.lstm / torch.bmm):
 these models are the "next" rows of the scope table, not the hot path.
 """
 import math
@@ -28,6 +29,47 @@ from .qat_quant import GradientWeightFakeQuantize, get_activation_quantizer, get
 import os as _os
 
 NATIVE_LSTM = _os.environ.get("FQSS_NATIVE_LSTM", "1") not in ("", "0")      # False: the recurrence of LSTMQ stays on torch's LSTM (A/B runs, tests)
+
+
+NATIVE_ATTENTION = _os.environ.get("FQSS_NATIVE_ATTENTION", "1") not in ("", "0")      # False: torch.bmm / softmax / bmm
+
+
+class SmallHeadAttention(Function):
+    """o = softmax(q k^T) v per (batch, head) on csrc/attention.cu (scores never materialised); q [BH,Lq,hd], k / v [BH,Lk,hd]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v):
+        N.require_cuda(q, k, v)
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        BH, Lq, hd = q.shape
+        Lk = k.shape[1]
+        o = torch.empty_like(q)
+        lse = torch.empty((BH, Lq), device=q.device)
+        check(lib().fqss_attn_fwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), BH, Lq, Lk, hd, stream_ptr()))
+        ctx.save_for_backward(q, k, v, o, lse)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        BH, Lq, hd = q.shape
+        Lk = k.shape[1]
+        do = do.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        ws = torch.empty((BH, Lq), device=q.device)
+        check(lib().fqss_attn_bwd(ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dq), ptr(dk), ptr(dv), ptr(ws), BH, Lq, Lk, hd,
+                                  stream_ptr()))
+        return dq, dk, dv
+
+
+def attention_eligible(q, k, observing):
+    """The fused kernel covers fp32 CUDA tensors, head sizes 8 / 16 / 32 and heads whose K, V fit shared memory; while the
+    (result-discarding) score / softmax quantisers of the reference still observe, the scores must exist: library path."""
+    if not NATIVE_ATTENTION or observing or not q.is_cuda or q.dtype != torch.float32 or q.shape[0] >= 65536:
+        return False
+    hd = q.shape[-1]
+    return hd in (8, 16, 32) and int(lib().fqss_attn_smem_bytes(q.shape[1], k.shape[1], hd)) <= 200 * 1024
 
 
 class LSTMRecurrence(Function):
@@ -288,11 +330,17 @@ class MultiheadAttentionQ(LayerQ):
         k = K.reshape(Lk, nb * H, hd).permute(1, 0, 2)
         v = V.reshape(Lv, nb * H, hd).permute(1, 0, 2)
         q = self.activation_fake_quantize_div(q / math.sqrt(hd))
-        attn = torch.bmm(q, k.transpose(-2, -1))
-        self._observe_only(self.activation_fake_quantize_attn, attn)        # qat_layers.py:934: `attn - fq(attn)`, result discarded
-        attn = torch.softmax(attn, dim=-1)
-        self._observe_only(self.activation_fake_quantize_softmax, attn)     # qat_layers.py:936: likewise
-        heads = self.activation_fake_quantize_head(torch.bmm(attn, v))
+        observing = any(hasattr(m, "observing") and m.observing()
+                        for m in (self.activation_fake_quantize_attn, self.activation_fake_quantize_softmax))
+        if attention_eligible(q, k, observing):
+            ctxv = SmallHeadAttention.apply(q, k, v)                            # csrc/attention.cu: one pass, no score tensor
+        else:
+            attn = torch.bmm(q, k.transpose(-2, -1))
+            self._observe_only(self.activation_fake_quantize_attn, attn)        # qat_layers.py:934: `attn - fq(attn)`, result discarded
+            attn = torch.softmax(attn, dim=-1)
+            self._observe_only(self.activation_fake_quantize_softmax, attn)     # qat_layers.py:936: likewise
+            ctxv = torch.bmm(attn, v)
+        heads = self.activation_fake_quantize_head(ctxv)
         flat = heads.transpose(1, 0).reshape(Lq * nb, E)
         y = F.linear(flat, Wo, mha.out_proj.bias).reshape(Lq, nb, self.do)
         if self.do_mac_op:

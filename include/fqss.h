@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 18
+#define FQSS_ABI_VERSION 19
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -457,6 +457,17 @@ int fqss_lstm_rec_fwd(const float* gx, const float* whh0, const float* whh1, con
 int fqss_lstm_rec_bwd(const float* dout, const float* gates, const float* cseq, const float* whh0, const float* whh1,
                       const float* wmin0, const float* wmin1, const float* wmax0, const float* wmax1, float* dG, int T, int N,
                       int H, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * R2  attention core of MultiheadAttentionQ (qat_layers.py:926-939: between the quantiser of q / sqrt(d) and the quantiser of
+ *     the head outputs):  o = softmax(q k^T) v  per (batch, head) for small heads (HD in {8, 16, 32}), scores never
+ *     materialised.  q, o, dO, dq [BH][Lq][HD]; k, v, dk, dv [BH][Lk][HD]; lse [BH][Lq] (row log-sum-exp, saved by fwd);
+ *     delta_ws [BH][Lq] scratch.  One head's K, V (or Q, dO) must fit shared memory: fqss_attn_smem_bytes <= 200 KB.
+ * ------------------------------------------------------------------------------------------- */
+size_t fqss_attn_smem_bytes(int Lq, int Lk, int HD);
+int fqss_attn_fwd(const float* q, const float* k, const float* v, float* o, float* lse, int BH, int Lq, int Lk, int HD, void* stream);
+int fqss_attn_bwd(const float* q, const float* k, const float* v, const float* o, const float* dO, const float* lse, float* dq,
+                  float* dk, float* dv, float* delta_ws, int BH, int Lq, int Lk, int HD, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * X1  export-time quantisers (qat_quant.py:15-72: TorchWeightFakeQuantize, TorchActivationFakeQuantize,
