@@ -104,13 +104,15 @@ _SIGS = {
     "fqss_arena_sumsq": (i32, [vp, i64, vp, vp, sz, vp]),
     "fqss_arena_scale_clip": (i32, [vp, i64, vp, f32, f32, vp]),
     "fqss_arena_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, vp]),
-    "fqss_arena_adam_dev": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp]),
+    "fqss_arena_adam_dev": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, vp, vp, vp]),
     "fqss_music_loss_ws_bytes": (sz, [i32]),
     "fqss_music_kd_loss": (i32, [vp, i64, vp, i64, vp, i64, i32, i32, i32, f32, vp, vp, i64, vp, sz, vp]),
     "fqss_mask_head_fwd": (i32, [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i64, vp]),
     "fqss_pw_gemm_nstore": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i64, vp]),
     "fqss_frames_split": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, vp, vp]),
     "fqss_frames_encode": (i32, [vp, i64, vp, i64, i64, i32, i32, i32, i32, i32, vp, vp, vp]),
+    "fqss_set_bwd_tail_side": (i32, [i32]),
+    "fqss_tcn_bwd_join": (i32, [vp]),
     "fqss_attn_smem_bytes": (sz, [i32, i32, i32]),
     "fqss_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
     "fqss_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
@@ -155,7 +157,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 19:
+                if L.fqss_abi_version() != 20:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

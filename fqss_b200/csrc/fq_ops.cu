@@ -409,7 +409,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 // Adam with the step count on the DEVICE (graph-capturable: nothing about the step is baked into the launch)
 __global__ void __launch_bounds__(256) adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                       float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                                                      const int* __restrict__ step) {
+                                                      const int* __restrict__ step, const float* __restrict__ lr_dev) {
+    if (lr_dev) lr = __ldg(lr_dev);          // learning rate read from the device: a scheduler can change it between graph replays
     const float t = (float)(*step + 1);
     const float bc1 = 1.f - powf(b1, t);
     const float bc2_sqrt = sqrtf(1.f - powf(b2, t));
@@ -642,11 +643,11 @@ int fqss_arena_adam(float* p, const float* g, float* m, float* v, int64_t n, flo
 }
 
 int fqss_arena_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                        int* step_dev, void* stream) {
+                        int* step_dev, const float* lr_dev, void* stream) {
     FQSS_REQUIRE(p && g && m && v && n >= 0 && step_dev, -1, "arena_adam_dev: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     FQSS_PROFN("arena_adam", s, 2);
-    if (n > 0) adam_dev_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev);
+    if (n > 0) adam_dev_kernel<<<grid_for(n, 256, 8), 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, lr_dev);
     incr_kernel<<<1, 1, 0, s>>>(step_dev);
     return check_launch("arena_adam_dev");
 }

@@ -825,11 +825,20 @@ static cudaStream_t side_stream() {
     if (!st) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
     return st;
 }
-static cudaEvent_t side_event(int i) {
-    static cudaEvent_t ev[2] = {nullptr, nullptr};
+static cudaEvent_t side_event(int i) {      // 0 / 1: fork / done of the dW2 wgrad; 2: fork of the block tail; 3, 4: tail done (per accumulator)
+    static cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     if (!ev[i]) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
     return ev[i];
 }
+
+// "Tail on the side stream" (fqss_set_bwd_tail_side): the second weight-gradient GEMM of a block and the finalise kernel
+// leave the main stream as well, so the next block's backward starts right after this block's last dgrad GEMM.  Nothing on
+// the chain consumes their outputs (parameter gradients, read after the whole stack: fqss_tcn_bwd_join orders that); the
+// reuse hazards of the shared scratch are ordered by events: dY2 (next block's tail kernel vs this block's dW2 wgrad),
+// dY1 (next block's gLN1 kernel vs this block's dW1 wgrad), and the fp64 accumulator block, which is double-buffered.
+static int g_tail_side = 0;
+static int g_flip = 0;
+static bool g_pend_w2 = false, g_pend_tail[2] = {false, false};
 
 // development knob: loads-in-flight batch of a row kernel, from the environment (read once per name)
 static int tune_nq(const char* name, int dflt) {
@@ -849,9 +858,25 @@ int fqss_set_wgrad_overlap(int on) {
     return prev;
 }
 
+int fqss_set_bwd_tail_side(int on) {
+    const int prev = g_tail_side;
+    g_tail_side = on;
+    return prev;
+}
+
+// Orders everything the backward calls since the last join left on the side stream before later work on `stream`.
+int fqss_tcn_bwd_join(void* stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (g_pend_w2) cudaStreamWaitEvent(s, side_event(1), 0);
+    for (int i = 0; i < 2; ++i)
+        if (g_pend_tail[i]) cudaStreamWaitEvent(s, side_event(3 + i), 0);
+    g_pend_w2 = g_pend_tail[0] = g_pend_tail[1] = false;
+    return check_launch("tcn_bwd_join");
+}
+
 size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid) {
     AccLayout L(B, Cio, Chid);
-    size_t acc = align_up((size_t)L.total * sizeof(double), 256);
+    size_t acc = 2 * align_up((size_t)L.total * sizeof(double), 256);      // two accumulator blocks (alternating per call)
     size_t cst = align_up((size_t)2 * 1024 * sizeof(float), 256);
     // the partial buffer is sized for the longest sequence the row kernels accept (M <= 16K); the actual need
     // depends only on the split count, which is capped by the SM count
@@ -876,8 +901,17 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     cudaStream_t s = (cudaStream_t)stream;
     const AccLayout L(p->B, p->Cio, p->Chid);
     const size_t acc_bytes = align_up((size_t)L.total * sizeof(double), 256);
-    double* acc = (double*)g->ws;
-    float* part = (float*)((char*)g->ws + acc_bytes + align_up((size_t)2 * 1024 * sizeof(float), 256));
+    const int overlap = g_wgrad_overlap < 0 ? (g_wgrad_overlap = tune_nq("FQSS_WGRAD_OVERLAP", 1)) : g_wgrad_overlap;
+    const bool tail_side = overlap && g_tail_side;
+    int flip = 0;
+    if (tail_side) {
+        flip = g_flip;
+        g_flip ^= 1;
+        if (g_pend_w2) cudaStreamWaitEvent(s, side_event(1), 0);               // previous block's dW2 wgrad still reads dY2
+        if (g_pend_tail[flip]) cudaStreamWaitEvent(s, side_event(3 + flip), 0);  // this accumulator's previous finalise
+    }
+    double* acc = (double*)((char*)g->ws + (size_t)flip * acc_bytes);
+    float* part = (float*)((char*)g->ws + 2 * acc_bytes + align_up((size_t)2 * 1024 * sizeof(float), 256));
     const size_t part_cap = g->ws_bytes - ((char*)part - (char*)g->ws);
     const int n2 = p->has_res ? 2 * p->Cio : p->Cio;
     const int rows_h = p->B * p->Chid, rows_io = p->B * p->Cio;
@@ -898,7 +932,6 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     // gLN2 row-sum kernel that follows (ALU-bound, ~40 % of HBM) do not depend on each other and fit on an SM together:
     // fork the wgrad to a side stream (inputs dY2 / db2 sums are complete after T), join before the second wgrad, which
     // reuses the partial-tile buffer.  Works the same under stream capture (fork / join through events).
-    const int overlap = g_wgrad_overlap < 0 ? (g_wgrad_overlap = tune_nq("FQSS_WGRAD_OVERLAP", 1)) : g_wgrad_overlap;
     cudaStream_t sw = s;
     if (overlap) {
         sw = side_stream();
@@ -908,6 +941,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     rc = tcw::run(g->dY2, p->a4_op, p->B, p->M, p->ld, n2, p->Chid, part, part_cap, p->quant ? p->q4.rmin : nullptr,
                   p->quant ? p->q4.rmax : nullptr, p->dws2, acc + L.db2, g->dW2q, sw);
     if (overlap) cudaEventRecord(side_event(1), sw);      // recorded even on failure: the main stream must not wait forever
+    if (tail_side) g_pend_w2 = true;
     if (rc) return rc;
     // P1, R, P2
     static const int split_p2d = tune_nq("FQSS_SPLIT_P2D", 0);
@@ -1018,6 +1052,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
         FQSS_PROF("tcn_gln_reduce", s);
         tcn_gln_reduce_kernel<<<p->B + (p->Chid + 31) / 32, 256, 0, s>>>(acc + L.row1, p->B, p->Chid, p->gn1_w, g->g_gn1_w, g->g_gn1_b, acc + L.samp1);
     }
+    if (tail_side && g_pend_tail[flip ^ 1]) cudaStreamWaitEvent(s, side_event(3 + (flip ^ 1)), 0);   // previous block's dW1 wgrad still reads dY1
     {
         FQSS_PROF("tcn_gln1_bwd", s);
         if (p->quant) {
@@ -1031,6 +1066,18 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     }
     rc = check_launch("tcn_block_bwd(hidden)");
     if (rc) return rc;
+    const int nf = p->Chid > n2 ? p->Chid : n2;
+    if (tail_side) {
+        // W (dW1q) + F on the side stream, behind the dW2 wgrad (same partial-tile buffer, stream order)
+        cudaEventRecord(side_event(2), s);
+        cudaStreamWaitEvent(sw, side_event(2), 0);
+        rc = tcw::run(g->dY1, p->x_op, p->B, p->M, p->ld, p->Chid, p->Cio, part, part_cap, p->quant ? p->q_in.rmin : nullptr,
+                      p->quant ? p->q_in.rmax : nullptr, p->dws1, acc + L.db1, g->dW1q, sw);
+        { FQSS_PROF("tcn_bwd_misc", sw); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, sw>>>(*p, *g, acc, lean ? 1 : 0); }
+        cudaEventRecord(side_event(3 + flip), sw);
+        g_pend_tail[flip] = true;
+        if (rc) return rc;
+    }
     // G: g_x_in = Wc1T-GEMM(dY1) (+ g_xd)   (K = Chid, N = Cio) -> fp32
     {
         tcg::Args a{};
@@ -1039,13 +1086,13 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
         rc = tcg::run(p->has_res ? tcg::EPI_ADD : tcg::EPI_STORE, g->dY1, p->Wc1T, a, s);
         if (rc) return rc;
     }
+    if (tail_side) return check_launch("tcn_block_bwd(tail on the side stream)");
     // W: dW1q
     if (overlap) cudaStreamWaitEvent(s, side_event(1), 0);      // join: dW2q is final, the partial-tile buffer is free again
     rc = tcw::run(g->dY1, p->x_op, p->B, p->M, p->ld, p->Chid, p->Cio, part, part_cap, p->quant ? p->q_in.rmin : nullptr,
                   p->quant ? p->q_in.rmax : nullptr, p->dws1, acc + L.db1, g->dW1q, s);
     if (rc) return rc;
     // F
-    const int nf = p->Chid > n2 ? p->Chid : n2;
     { FQSS_PROF("tcn_bwd_misc", s); tcn_bwd_finalize_kernel<<<(nf + 255) / 256, 256, 0, s>>>(*p, *g, acc, lean ? 1 : 0); }
     return check_launch("tcn_block_bwd(finalize)");
 }

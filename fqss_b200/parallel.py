@@ -145,6 +145,13 @@ class ParamArena:
             return 1.0 / dist.get_world_size(group)
         return 1.0
 
+    def set_lr(self, lr):
+        """Learning rate kept on the device: `clip_and_step` then reads it at run time, so a scheduler (the recipe's
+        ReduceLROnPlateau `half_lr`, asteroid_librimix_trainer.py:96-97) takes effect under a replayed CUDA graph too."""
+        if getattr(self, "lr_dev", None) is None:
+            self.lr_dev = torch.empty(1, device=self.flat.device)
+        self.lr_dev.fill_(float(lr))
+
     def clip_and_step(self, pre_scale=1.0, max_norm=5.0, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         if not self.flat.is_cuda:
             raise N.FqssError("ParamArena.clip_and_step needs CUDA (no CPU fallback)")
@@ -155,7 +162,8 @@ class ParamArena:
         check(lib().fqss_arena_scale_clip(ptr(self.grad), n, ptr(self.sumsq), float(pre_scale), float(max_norm), s))
         self.step_count += 1          # host mirror; the kernels read the device counter (CUDA-graph replays stay correct)
         check(lib().fqss_arena_adam_dev(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, float(lr),
-                                        float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev), s))
+                                        float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev),
+                                        ptr(getattr(self, "lr_dev", None)) or None, s))
 
     def zero_grad(self):
         for p in self.params:

@@ -52,10 +52,14 @@ class TcnBlockGrads(C.Structure):
 _L = None
 
 
+BWD_TAIL_SIDE = os.environ.get("FQSS_BWD_TAIL_SIDE", "1") not in ("", "0")     # see fqss_set_bwd_tail_side (include/fqss.h)
+
+
 def _libx():
     global _L
     if _L is None:
         L = lib()
+        L.fqss_set_bwd_tail_side(1 if BWD_TAIL_SIDE else 0)
         L.fqss_tcn_block_fwd.argtypes = [C.POINTER(TcnBlock), vp]
         L.fqss_tcn_block_bwd.argtypes = [C.POINTER(TcnBlock), C.POINTER(TcnBlockGrads), vp]
         _L = L
@@ -610,6 +614,7 @@ class FusedTCNFunction(Function):
             for j, name in enumerate(_BLOCK_SLOTS):
                 if t[name] is not None and name in out and out[name] is not None and ctx.needs_input_grad[3 + base + j]:
                     grads[base + j] = out[name].reshape(t[name].shape)
+        check(L.fqss_tcn_bwd_join(s))        # the blocks' weight-gradient tails ran on the library's side stream
         _run_batches([], wq_items, wq_bwd=True)
         del keep
         g_skip_in = g_ss[:, :, :M] if (not states[0].first and ctx.needs_input_grad[1]) else None

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 19
+#define FQSS_ABI_VERSION 20
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -314,6 +314,12 @@ size_t fqss_tcn_ws_bytes(int B, int Cio, int Chid);
  * gLN2 row-sum kernel (fork / join through events on the caller's stream; capturable); 0: everything on the caller's
  * stream (what per-kernel timing wants); -1: back to the environment default.  Returns the previous setting. */
 int fqss_set_wgrad_overlap(int on);
+/* 1: the second weight-gradient GEMM and the finalise kernel of fqss_tcn_block_bwd run on the library's side stream too, so the
+ * next block's backward starts right after this block's last dgrad GEMM (scratch reuse ordered by events, accumulator block
+ * double-buffered).  The caller MUST then call fqss_tcn_bwd_join(stream) after the last block and before anything reads the
+ * parameter gradients.  Default 0 (every call returns with all its work ordered on `stream`).  Returns the previous setting. */
+int fqss_set_bwd_tail_side(int on);
+int fqss_tcn_bwd_join(void* stream);
 int fqss_tcn_block_bwd(const fqss_tcn_block* blk, const fqss_tcn_block_grads* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -504,7 +510,9 @@ int fqss_arena_adam(float* p, const float* g, float* m, float* v, int64_t n, flo
 /* same step with the step count kept on the device: uses t = *step_dev + 1 for the bias corrections, then increments
  * *step_dev -- nothing step-dependent is baked into the launch, so a captured CUDA graph of the step can be replayed */
 int fqss_arena_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                        float eps, int* step_dev, void* stream);
+                        float eps, int* step_dev, const float* lr_dev /* may be NULL; else the learning rate is read from
+                        the device at run time (schedulers such as half_lr keep working under a captured graph) */,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Measurement support (nothing like it in the reference): launch accounting and per-kernel-class

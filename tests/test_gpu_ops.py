@@ -325,6 +325,51 @@ def test_param_arena_gather_clip_adam_vs_torch():
         assert worst < 1e-5, (step, worst)
 
 
+def test_param_arena_device_lr_under_cuda_graph():
+    """The learning rate lives on the device (ParamArena.set_lr): a scheduler's change takes effect in a REPLAYED CUDA graph
+    (the recipe's half_lr = ReduceLROnPlateau, asteroid_librimix_trainer.py:96-97); checked against torch.optim.Adam stepped
+    with the same schedule."""
+    from fqss_b200.parallel import ParamArena
+    torch.manual_seed(0)
+    ref = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in [(1000,), (33, 7)]]
+    ours = [torch.nn.Parameter(p.detach().clone()) for p in ref]
+    arena = ParamArena(ours)
+    arena.set_lr(1e-3)
+    gs = [torch.randn_like(p) * 0.01 for p in ref]
+    static_g = [g.clone() for g in gs]
+
+    def step():
+        for q, g in zip(ours, static_g):
+            q.grad = g
+        arena.gather_grads()
+        arena.clip_and_step(pre_scale=1.0, max_norm=5.0, lr=123.0)      # the scalar is ignored once set_lr was called
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    opt = torch.optim.Adam(ref, lr=1e-3)
+    lrs = [1e-3, 5e-4, 5e-4, 2.5e-4]          # the warm-up step ran for real (capturing executes nothing), then three replays
+    for i, lr in enumerate(lrs):
+        if i >= 1:
+            arena.set_lr(lr)
+            graph.replay()
+        for grp in opt.param_groups:
+            grp["lr"] = lr
+        for p, g in zip(ref, gs):
+            p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_(ref, 5.0)
+        opt.step()
+    torch.cuda.synchronize()
+    worst = max(rel(q, p) for p, q in zip(ref, ours))
+    assert worst < 1e-5, worst
+
+
 def test_pairwise_wsdr_module_vs_reference_and_oracle(golden):
     """S2/S3 as standalone modules (wsdr.py:46-95 and asteroid's PITLossWrapper): the pairwise matrices of the
     unmodified reference (tests/golden/loss.npz), gradients against the oracle's autograd, and the PIT search."""
