@@ -112,7 +112,7 @@ class ParamArena:
         """Collect p.grad of every parameter into the gradient arena (zeros where a parameter got none): one
         fqss_arena_gather call (3 launches for the 948 tensors) instead of a chunked multi-tensor ATen copy."""
         if not self.flat.is_cuda:
-            return self._gather_grads_torch()
+            raise N.FqssError("ParamArena.gather_grads needs CUDA (no CPU fallback)")
         items = self._gather_items
         for i, p in enumerate(self.params):
             g = p.grad
@@ -125,17 +125,6 @@ class ParamArena:
                 items[i].src = g.data_ptr()
         check(lib().fqss_arena_gather(items, len(self.params), ptr(self.grad), stream_ptr()))
         self._keep.clear()          # safe: same stream, the copies are already enqueued
-
-    def _gather_grads_torch(self):
-        have_dst, have_src = [], []
-        for p, gv in zip(self.params, self.grad_views):
-            if p.grad is None:
-                gv.zero_()
-            else:
-                have_dst.append(gv)
-                have_src.append(p.grad)
-        if have_dst:
-            torch._foreach_copy_(have_dst, have_src)
 
     def allreduce_mean(self, group=None):
         """The one exchange step of the path.  Returns the 1/world factor still to be applied (folded

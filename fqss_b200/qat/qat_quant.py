@@ -87,6 +87,23 @@ class GradientActivationFakeQuantize(nn.Module):
         return ops.FakeQuantAct.apply(x, self.min_range, self.max_range, self.n_bits)
 
 
+def ranges_ok(model):
+    """0-dim bool tensor ON THE DEVICE: every activation quantiser of `model` has max_range > min_range and finite ranges,
+    every weight quantiser a non-zero finite range.  The reference asserts `max_range >= min_range` on the host in every
+    forward call (qat_quant.py:238, one sync per quantiser per step); the kernels never sync, so the check is a separate,
+    cheap call for the training loop to make once per epoch / validation (`assert bool(ranges_ok(model))`)."""
+    spans = []
+    for m in model.modules():
+        if isinstance(m, GradientActivationFakeQuantize):
+            spans.append((m.max_range.detach() - m.min_range.detach()).reshape(-1))
+        elif isinstance(m, GradientWeightFakeQuantize) and not m.observer_mode:
+            spans.append(torch.maximum(m.min_range.detach().abs(), m.max_range.detach().abs()).reshape(-1))
+    if not spans:
+        return torch.ones((), dtype=torch.bool)
+    v = torch.cat(spans)
+    return torch.isfinite(v).all() & (v > 0).all()
+
+
 class GradientWeightFakeQuantize(nn.Module):
     """Per-output-channel symmetric signed weight quantiser; first call captures amin/amax."""
 

@@ -128,3 +128,15 @@ def test_ctypes_binding_matches_header(native, tmp_path):
         s, f, v = line.split()
         want = C.sizeof(structs[s]) if f == "sizeof" else getattr(structs[s], f).offset
         assert int(v) == want, "%s.%s: C %s vs ctypes %d" % (s, f, v, want)
+
+
+def test_ranges_ok_flags_crossed_or_degenerate_ranges():
+    """Sync-free stand-in for the reference's per-call `assert max_range >= min_range` (qat_quant.py:238)."""
+    import torch
+    from fqss_b200.qat.qat_quant import GradientActivationFakeQuantize, ranges_ok
+    m = torch.nn.Sequential(GradientActivationFakeQuantize(True), GradientActivationFakeQuantize(True))
+    assert bool(ranges_ok(m))
+    m[1].max_range.data.fill_(-1.0)
+    assert not bool(ranges_ok(m))
+    m[1].max_range.data.fill_(float("nan"))
+    assert not bool(ranges_ok(m))

@@ -31,6 +31,15 @@ def _toy(seed=0):
     return net, dead
 
 
+def _gather_on_host(arena):
+    """Host stand-in for fqss_arena_gather (the product gathers on the GPU only): p.grad -> the arena's gradient views."""
+    for p, gv in zip(arena.params, arena.grad_views):
+        if p.grad is None:
+            gv.zero_()
+        else:
+            gv.copy_(p.grad)
+
+
 def _worker(rank, world, port, gb, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -44,7 +53,7 @@ def _worker(rank, world, port, gb, out_dir):
     lo, hi = shard_bounds(gb, rank, world)
     loss = ((net(x[lo:hi]) - y[lo:hi]) ** 2).mean()     # per-rank loss on the local shard (reference DDP semantics)
     loss.backward()
-    arena.gather_grads()
+    _gather_on_host(arena)
     scale = arena.allreduce_mean()
     torch.save({"grad": arena.grad.clone() * scale, "scale": scale, "lo": lo, "hi": hi,
                 "flat_is_param": all(p.data_ptr() == v.data_ptr() for p, v in zip(params, arena.views))},
