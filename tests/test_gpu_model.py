@@ -343,3 +343,30 @@ def test_long_utterance_falls_back_to_per_layer_path():
     # the long input equals the short one on its first samples up to the receptive field: sanity of the fallback path
     est_short = model(short)
     assert est_short.shape == (1, 2, 4000)
+
+
+def test_training_step_is_bit_reproducible():
+    """Run-to-run reproducibility (the reference sets cudnn.deterministic, utils.py:13): the same QAT step of the full model
+    run three times from the same state gives the same loss and the same 940 gradient tensors BIT FOR BIT.  The kernels
+    accumulate range / tap / bias sums with fp64 atomics (order-dependent at the 1e-16 level, far below the fp32 rounding of
+    the stored gradient); the split-K weight-gradient reduction is ordered; integer code sums are exact."""
+    from fqss_b200.testing import FULL_KW, model_pair
+    from fqss_b200.losses import fqss_training_step
+    from fqss_b200.qat.models.load_model import enable_observer
+    model, fmodel = model_pair(FULL_KW, DEV, seed=0)
+    g = torch.Generator().manual_seed(3)
+    src = (torch.randn(3, 2, 32000, generator=g) * 0.05).to(DEV)
+    mix = src.sum(1, keepdim=True)
+    with torch.no_grad():
+        model(mix[:2]); model(mix[:2])
+    enable_observer(model, False)
+    runs = []
+    for _ in range(3):
+        model.zero_grad(set_to_none=True)
+        loss, _, _ = fqss_training_step(model, fmodel, mix, src, 0.1)
+        loss.backward()
+        runs.append((loss.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}))
+    for r in (1, 2):
+        assert torch.equal(runs[0][0], runs[r][0])
+        diff = [k for k in runs[0][1] if not torch.equal(runs[0][1][k], runs[r][1][k])]
+        assert not diff, diff[:8]
