@@ -85,13 +85,14 @@ _SCRATCH = {}
 
 def _frames_operand(R, ld, dev):
     """bf16 [R,128,ld] operand of the framed gradient: rows >= 2L stay zero for the life of the buffer (fqss_frames_split
-    rewrites only the real rows), one buffer per (device, stream, shape) -- launches on a stream are ordered."""
-    key = ("G", dev.index, torch.cuda.current_stream(dev).cuda_stream, R, ld)
-    buf = _SCRATCH.get(key)
-    if buf is None:
-        buf = torch.zeros((R, 128, ld), dtype=BF, device=dev)
-        _SCRATCH[key] = buf
-    return buf
+    rewrites only the real rows).  ONE buffer per (device, stream) -- launches on a stream are ordered, and a new shape
+    (another utterance length) replaces the old buffer instead of accumulating."""
+    key = ("G", dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ent = _SCRATCH.get(key)
+    if ent is None or ent[0] != (R, ld):
+        ent = ((R, ld), torch.zeros((R, 128, ld), dtype=BF, device=dev))
+        _SCRATCH[key] = ent
+    return ent[1]
 
 
 def _ones128(dev):
