@@ -84,15 +84,10 @@ _SCRATCH = {}
 
 
 def _frames_operand(R, ld, dev):
-    """bf16 [R,128,ld] operand of the framed gradient: rows >= 2L stay zero for the life of the buffer (fqss_frames_split
-    rewrites only the real rows).  ONE buffer per (device, stream) -- launches on a stream are ordered, and a new shape
-    (another utterance length) replaces the old buffer instead of accumulating."""
-    key = ("G", dev.index, torch.cuda.current_stream(dev).cuda_stream)
-    ent = _SCRATCH.get(key)
-    if ent is None or ent[0] != (R, ld):
-        ent = ((R, ld), torch.zeros((R, 128, ld), dtype=BF, device=dev))
-        _SCRATCH[key] = ent
-    return ent[1]
+    """bf16 [R,128,ld] operand of the framed gradient, zero-initialised: fqss_frames_split writes the 2L real rows, the padding
+    rows up to the tile height must be zero.  A fresh tensor per call (a 65 MB memset at the recipe's size, ~15 us): a cached
+    buffer would be baked into captured CUDA graphs and could not be released safely."""
+    return torch.zeros((R, 128, ld), dtype=BF, device=dev)
 
 
 def _ones128(dev):
