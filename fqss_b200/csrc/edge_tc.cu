@@ -6,8 +6,8 @@
 //               output of an 8-bit quantiser, w is fake-quantised per tensor) followed by fqss_ola_fwd
 //   encoder  y[r,o,m] = sum_{c,k} w[o,c,k] x[r,c,8m+k]    =  GEMM over the 16*C taps of the framed input
 //
-//   fqss_frames_split    g [R][T]  -> bf16 [R][128][ld]: rows 0..15 = hi(g[r, 8m+k]), rows 16..31 = lo, others 0; the framed
-//                        output gradient as a split-bf16 operand (fp32-grade: hi + lo carries 16 mantissa bits) of the
+//   fqss_frames_split    g [R][T]  -> bf16 [R][128][ld]: rows 0..15 = hi(g[r, 8m+k]), rows 16..31 = mid, 32..47 = lo, others 0; the
+//                        framed output gradient as a three-term bf16 operand (hi + mid + lo = the fp32 value: 24 mantissa bits) of the
 //                        decoder's dgrad / wgrad GEMMs, plus the fp64 row sums the wgrad affine needs
 //   fqss_frames_encode   x [R][C][T] on an 8-bit grid -> bf16 codes [R][KP][ld]: row c*16+k = code(x[r,c,8m+k]), others 0
 //   fqss_sub_fq_codes    Y1 = FQ(Y - Yq) (RQB, qat_layers.py:1195) as bf16 codes only: the decoder GEMM's next operand
@@ -21,7 +21,7 @@ int num_sms();
 
 constexpr int ET_THREADS = 256;
 
-// grid (ceil(M/256), 2L or 128, R): one thread = one (row, frame)
+// grid (ceil(M/256), 3L or 128, R): one thread = one (row, frame)
 __global__ void __launch_bounds__(ET_THREADS) frames_split_kernel(const float* __restrict__ g, int64_t ldg, __nv_bfloat16* __restrict__ out,
                                                                  int64_t ldo, int M, int L, int H, double* __restrict__ rowsum) {
     __shared__ double sh[32];
@@ -30,13 +30,16 @@ __global__ void __launch_bounds__(ET_THREADS) frames_split_kernel(const float* _
     const int64_t row = r * 128 + j;
     const int m = blockIdx.x * ET_THREADS + threadIdx.x;
     float v = 0.f;
-    if (j < 2 * L && m < M) {
-        const float x = __ldg(g + r * ldg + (int64_t)m * H + (j < L ? j : j - L));
-        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-        v = j < L ? __bfloat162float(hi) : __bfloat162float(__float2bfloat16_rn(x - __bfloat162float(hi)));
+    if (j < 3 * L && m < M) {
+        // x = hi + mid + lo, three bf16 terms: 24 mantissa bits, i.e. the fp32 value exactly (up to denormal tails)
+        const int part = j / L;
+        const float x = __ldg(g + r * ldg + (int64_t)m * H + (j - part * L));
+        const float hi = __bfloat162float(__float2bfloat16_rn(x));
+        const float mid = __bfloat162float(__float2bfloat16_rn(x - hi));
+        v = part == 0 ? hi : (part == 1 ? mid : __bfloat162float(__float2bfloat16_rn((x - hi) - mid)));
     }
     if (m < M) out[row * ldo + m] = __float2bfloat16_rn(v);        // exact: v is a bf16 value
-    if (rowsum && j < 2 * L) {                                     // block-uniform branch
+    if (rowsum && j < 3 * L) {                                     // block-uniform branch
         double s = (double)warp_sum(v);
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         if (lane == 0) sh[wid] = s;
@@ -80,17 +83,17 @@ __global__ void __launch_bounds__(ET_THREADS) sub_fq_codes_kernel(const float* _
     }
 }
 
-// part [128][F] (rows 0..L-1: hi frames, L..2L-1: lo frames) -> dWq [F][L]
+// part [128][F] (rows 0..L-1: hi frames, L..2L-1: mid, 2L..3L-1: lo) -> dWq [F][L]
 __global__ void dec_wgrad_fold_kernel(const float* __restrict__ part, float* __restrict__ dWq, int F, int L) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= F * L) return;
     const int o = i / L, k = i - o * L;
-    dWq[i] = part[(int64_t)k * F + o] + part[(int64_t)(L + k) * F + o];
+    dWq[i] = (part[(int64_t)k * F + o] + part[(int64_t)(L + k) * F + o]) + part[(int64_t)(2 * L + k) * F + o];
 }
 
 // Decoder weight W [F][L] (ConvTranspose1d F -> 1, per-TENSOR symmetric quantiser: ch_out_idx = 1) as GEMM operands:
 //   Wc [128][F]: row k < L = code[.,k]            (forward: frames[k] = sum_o code[o,k] * act_code[o])
-//   WT [F][128]: [code | code | 0]                (dgrad on the split [hi ; lo] framed gradient)
+//   WT [F][128]: [code | code | code | 0]         (dgrad on the split [hi ; mid ; lo] framed gradient)
 //   s1[k] = dw * da, s0[k] = dw * min_a * sum_o code[o,k]   (k < L; zero beyond), dgs[o] = dw
 __global__ void __launch_bounds__(256) dec_prep_kernel(const float* __restrict__ W, const float* wmin, const float* wmax, const float* amin,
                                                        const float* amax, __nv_bfloat16* __restrict__ Wc, __nv_bfloat16* __restrict__ WT,
@@ -102,8 +105,8 @@ __global__ void __launch_bounds__(256) dec_prep_kernel(const float* __restrict__
     for (int i = threadIdx.x; i < 8 * 128; i += blockDim.x) {
         const int o = o0 + (i >> 7), j = i & 127;
         if (o >= F) continue;
-        const int k = j < L ? j : j - L;
-        const float c = j < 2 * L ? wq_code(wq, __ldg(W + (int64_t)o * L + k)) : 0.f;
+        const int k = j % L;
+        const float c = j < 3 * L ? wq_code(wq, __ldg(W + (int64_t)o * L + k)) : 0.f;
         WT[(int64_t)o * 128 + j] = __float2bfloat16_rn(c);
     }
     for (int i = threadIdx.x; i < 8 * 128; i += blockDim.x) {
@@ -158,12 +161,12 @@ extern "C" {
 
 int fqss_frames_split(const float* g, int64_t ldg, void* out_bf16, int64_t ldo, int64_t R, int M, int L, int H, int zero_rows,
                       double* rowsum, void* stream) {
-    FQSS_REQUIRE(g && out_bf16 && R > 0 && R < 65536 && M > 0 && L > 0 && 2 * L <= 128 && H > 0 && ldo >= M && ldg >= (int64_t)(M - 1) * H + L, -1,
+    FQSS_REQUIRE(g && out_bf16 && R > 0 && R < 65536 && M > 0 && L > 0 && 3 * L <= 128 && H > 0 && ldo >= M && ldg >= (int64_t)(M - 1) * H + L, -1,
                  "frames_split: bad argument");
     cudaStream_t s = (cudaStream_t)stream;
     FQSS_PROF("frames_split", s);
-    if (rowsum) cudaMemsetAsync(rowsum, 0, (size_t)2 * L * sizeof(double), s);
-    frames_split_kernel<<<dim3((M + ET_THREADS - 1) / ET_THREADS, (unsigned)(zero_rows ? 128 : 2 * L), (unsigned)R), ET_THREADS, 0, s>>>(
+    if (rowsum) cudaMemsetAsync(rowsum, 0, (size_t)3 * L * sizeof(double), s);
+    frames_split_kernel<<<dim3((M + ET_THREADS - 1) / ET_THREADS, (unsigned)(zero_rows ? 128 : 3 * L), (unsigned)R), ET_THREADS, 0, s>>>(
         g, ldg, (__nv_bfloat16*)out_bf16, ldo, M, L, H, rowsum);
     return check_launch("frames_split");
 }
@@ -180,7 +183,7 @@ int fqss_frames_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo,
 
 int fqss_edge_dec_prep(const float* W, const float* wmin, const float* wmax, const float* amin, const float* amax, void* Wc,
                        void* WT, float* s1, float* s0, float* dgs, int F, int L, void* stream) {
-    FQSS_REQUIRE(W && wmin && wmax && amin && amax && Wc && WT && s1 && s0 && dgs && F > 0 && L > 0 && 2 * L <= 128, -1,
+    FQSS_REQUIRE(W && wmin && wmax && amin && amax && Wc && WT && s1 && s0 && dgs && F > 0 && L > 0 && 3 * L <= 128, -1,
                  "edge_dec_prep: bad argument");
     FQSS_PROF("edge_prep", stream);
     dec_prep_kernel<<<(F + 7) / 8, 256, 0, (cudaStream_t)stream>>>(W, wmin, wmax, amin, amax, (__nv_bfloat16*)Wc, (__nv_bfloat16*)WT, s1, s0, dgs, F, L);
@@ -210,7 +213,7 @@ int fqss_sub_fq_codes(const float* a, int64_t lda, const float* b, int64_t ldb, 
 }
 
 int fqss_dec_wgrad_fold(const float* part, float* dWq, int F, int L, void* stream) {
-    FQSS_REQUIRE(part && dWq && F > 0 && L > 0 && 2 * L <= 128, -1, "dec_wgrad_fold: bad argument");
+    FQSS_REQUIRE(part && dWq && F > 0 && L > 0 && 3 * L <= 128, -1, "dec_wgrad_fold: bad argument");
     FQSS_PROF("dec_wgrad_fold", stream);
     dec_wgrad_fold_kernel<<<(F * L + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, dWq, F, L);
     return check_launch("dec_wgrad_fold");

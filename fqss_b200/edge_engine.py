@@ -12,9 +12,9 @@ differs from the reference's fp32 conv only by the final affine  s1 * acc + s0, 
 convolutions of the ConvBlocks.  The tensor core computes 128 columns (its minimum N here) and the epilogue keeps the L real
 ones (fqss_pw_gemm_nstore); fqss_ola_fwd adds the frames up.
 
-Backward.  The framed output gradient G[r, k, m] = g[r, 8m + k] becomes a split-bf16 operand [hi ; lo] (fp32-grade:
-16 mantissa bits): dgrad = fqss_pw_gemm(G, [code | code | 0]) * dw, wgrad = fqss_wgrad_codes(G, Y codes) folded over
-(hi, lo) by fqss_dec_wgrad_fold.  The 524 MB feature tensor is read as 2-byte codes by all three GEMMs (the SIMT kernels
+Backward.  The framed output gradient G[r, k, m] = g[r, 8m + k] becomes a three-term bf16 operand [hi ; mid ; lo] (together
+the fp32 value: the operand is padded to 128 rows anyway, so the third term is free): dgrad = fqss_pw_gemm(G, [code | code |
+code | 0]) * dw, wgrad = fqss_wgrad_codes(G, Y codes) folded over (hi, mid, lo) by fqss_dec_wgrad_fold.  The 524 MB feature tensor is read as 2-byte codes by all three GEMMs (the SIMT kernels
 of conv_edge.cu read it as fp32 and are FMA-bound at 0.4 of HBM).
 
 RQB.  FQ(Y - Yq) is produced as codes only (fqss_sub_fq_codes: the fp32 residual tensor is never written); its backward is
@@ -84,7 +84,7 @@ _SCRATCH = {}
 
 
 def _frames_operand(R, ld, dev):
-    """bf16 [R,128,ld] operand of the framed gradient, zero-initialised: fqss_frames_split writes the 2L real rows, the padding
+    """bf16 [R,128,ld] operand of the framed gradient, zero-initialised: fqss_frames_split writes the 3L real rows, the padding
     rows up to the tile height must be zero.  A fresh tensor per call (a 65 MB memset at the recipe's size, ~15 us): a cached
     buffer would be baked into captured CUDA graphs and could not be released safely."""
     return torch.zeros((R, 128, ld), dtype=BF, device=dev)
@@ -264,7 +264,7 @@ def decoder_wants_codes(layer):
         return False
     dec = layer.convTr1d
     F, L = dec.in_channels, dec.kernel_size[0]
-    if F % 128 or F > 1024 or L % 16 or 2 * L > 128 or dec.out_channels != 1:
+    if F % 128 or F > 1024 or L % 16 or 3 * L > 128 or dec.out_channels != 1:
         return False
     if not _steady_wq(layer.weight_fake_quantize, 1) or layer.n_combiner > 2:
         return False

@@ -419,16 +419,17 @@ int fqss_mask_head_bwd(const float* g, int64_t ldg, const float* y, const float*
  *     ResidualErrorBlock :1105-1220).  The transposed conv to one channel is an overlap-add of per-frame tap vectors,
  *       frames[r,k,m] = sum_o w[o,k] Y[r,o,m]   (a GEMM over the filters, taps as output channels; fqss_pw_gemm_nstore keeps
  *       the 16 real columns of the 128 the tensor core computes),   y = fqss_ola_fwd(frames);
- *     its gradients use the framed output gradient as a split-bf16 operand (fqss_frames_split: rows 0..L-1 hi, L..2L-1 lo,
- *     zero up to 128; rowsum[2L] = fp64 sums of those rows): dgrad = fqss_pw_gemm(frames_split, [c | c | 0]) and wgrad =
- *     fqss_wgrad_codes(frames_split, Y codes) folded by fqss_dec_wgrad_fold (hi + lo rows, transposed to [F][L]).
+ *     its gradients use the framed output gradient as a three-term bf16 operand (fqss_frames_split: rows 0..L-1 hi, L..2L-1
+ *     mid, 2L..3L-1 lo -- together the fp32 value --, zero up to 128; rowsum[3L] = fp64 sums of those rows; 3L <= 128): dgrad =
+ *     fqss_pw_gemm(frames_split, [c | c | c | 0]) and wgrad =
+ *     fqss_wgrad_codes(frames_split, Y codes) folded by fqss_dec_wgrad_fold (hi + mid + lo rows, transposed to [F][L]).
  *     fqss_frames_encode frames a signal on an 8-bit grid into integer codes [R][KP][ld] (encoder-side operand, KP >= C*L rows);
  *     fqss_sub_fq_codes is the RQB's FQ(Y - Yq) (qat_layers.py:1195) producing the codes the second decode consumes.
  * ------------------------------------------------------------------------------------------- */
 int fqss_pw_gemm_nstore(const void* act_bf16, const void* w_bf16, const float* s1, const float* s0, float* out_f32, int n_store,
                         int B, int K, int N, int M, int64_t ld, void* stream);
 int fqss_frames_split(const float* g, int64_t ldg, void* out_bf16, int64_t ldo, int64_t R, int M, int L, int H,
-                      int zero_rows /* 0: only rows < 2L are written (the caller keeps the others zero) */, double* rowsum,
+                      int zero_rows /* 0: only rows < 3L are written (the caller keeps the others zero) */, double* rowsum,
                       void* stream);
 int fqss_frames_encode(const float* x, int64_t ldx, void* out_bf16, int64_t ldo, int64_t R, int C, int M, int L, int H, int KP,
                        const float* rmin, const float* rmax, void* stream);

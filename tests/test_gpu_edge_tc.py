@@ -3,7 +3,7 @@ ConvTr1dDecoderQ qat_layers.py:1305-1361, ResidualErrorBlock :1105-1220, Conv1dE
 
 Each GEMM-path op against the fp64 definition of the conv it replaces (its operands are integer codes, so the forward differs
 from the exact result only by the final affine: 1e-6), its gradients against fp64 autograd (the framed output gradient is a
-split-bf16 operand: 2^-16 per element, bound 1e-4), the RQB tail against the per-layer composition of the library, and the
+three-term bf16 operand = the fp32 value: bound 2e-6), the RQB tail against the per-layer composition of the library, and the
 whole decoder / encoder layers teacher-forced against the ORACLE on a model wide enough for the tensor-core tiles (128
 filters): output codes on the oracle's grid (rare +-1 moves), gradients to the fp32-path tolerance 1e-3."""
 import numpy as np
@@ -42,7 +42,7 @@ def _dec_weight(Fn, L, seed):
     return W, wmin, wmax, wq
 
 
-@pytest.mark.parametrize("R,Fn,M,L,H", [(3, 128, 77, 16, 8), (2, 256, 500, 16, 8), (1, 128, 129, 32, 16)])
+@pytest.mark.parametrize("R,Fn,M,L,H", [(3, 128, 77, 16, 8), (2, 256, 500, 16, 8), (1, 128, 129, 32, 16)])      # 3L <= 128
 def test_decode_codes_vs_fp64(R, Fn, M, L, H):
     from fqss_b200 import edge_engine as EE
     x, code, qmin, qmax = _on_grid((R, Fn, M), -0.3, 1.7, 1)
@@ -60,7 +60,7 @@ def test_decode_codes_vs_fp64(R, Fn, M, L, H):
     ref.backward(g.double())
     e_gx, e_gw = rel(xg.grad, xd.grad), rel(wqg.grad, wd.grad)
     record("edge_tc/decode_codes_R%d_F%d_M%d_L%d" % (R, Fn, M, L), fwd=e_fwd, gx=e_gx, gw=e_gw)
-    assert e_fwd < 1e-6 and e_gx < 1e-4 and e_gw < 1e-4, (e_fwd, e_gx, e_gw)
+    assert e_fwd < 1e-6 and e_gx < 2e-6 and e_gw < 2e-6, (e_fwd, e_gx, e_gw)      # three-term split: fp32-exact operand
     # the same tensor handed over as integer codes (what the mask head emits): identical result
     ld = (M + 7) // 8 * 8
     cb = torch.zeros((R, Fn, ld), dtype=torch.bfloat16, device=DEV)
