@@ -127,11 +127,11 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
     if (threadIdx.x == 0) {
         if (p.quant) {
             if (p.has_res) {
-                atomicAdd(acc + L.q + 2 * QADD, v[0]); atomicAdd(acc + L.q + 2 * QADD + 1, v[1]);
-                atomicAdd(acc + L.q + 2 * QRES, v[2]); atomicAdd(acc + L.q + 2 * QRES + 1, v[3]);
+                atomicAdd(acc + L.qs(o) + 2 * QADD, v[0]); atomicAdd(acc + L.qs(o) + 2 * QADD + 1, v[1]);
+                atomicAdd(acc + L.qs(o) + 2 * QRES, v[2]); atomicAdd(acc + L.qs(o) + 2 * QRES + 1, v[3]);
             }
-            if (!p.first_block) { atomicAdd(acc + L.q + 2 * QADDS, v[4]); atomicAdd(acc + L.q + 2 * QADDS + 1, v[5]); }
-            atomicAdd(acc + L.q + 2 * QSKIP, v[6]); atomicAdd(acc + L.q + 2 * QSKIP + 1, v[7]);
+            if (!p.first_block) { atomicAdd(acc + L.qs(o) + 2 * QADDS, v[4]); atomicAdd(acc + L.qs(o) + 2 * QADDS + 1, v[5]); }
+            atomicAdd(acc + L.qs(o) + 2 * QSKIP, v[6]); atomicAdd(acc + L.qs(o) + 2 * QSKIP + 1, v[7]);
         }
         if (p.has_res) atomicAdd(acc + L.db2 + o, v[8]);
         atomicAdd(acc + L.db2 + (p.has_res ? p.Cio : 0) + o, v[9]);
@@ -256,12 +256,12 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block 
     block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
         if (PHASE == 1) {
-            if (QUANT) { atomicAdd(acc + L.q + 2 * Q4, v[0]); atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]); }
+            if (QUANT) { atomicAdd(acc + L.qs(c) + 2 * Q4, v[0]); atomicAdd(acc + L.qs(c) + 2 * Q4 + 1, v[1]); }
             acc[L.row2 + 2 * r] = v[2];
             acc[L.row2 + 2 * r + 1] = v[3];
         } else {
-            if (QUANT) { atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]); }
-            atomicAdd(acc + L.slope + 1, v[2]);
+            if (QUANT) { atomicAdd(acc + L.qs(c) + 2 * Q3, v[0]); atomicAdd(acc + L.qs(c) + 2 * Q3 + 1, v[1]); }
+            atomicAdd(acc + L.qs(c) + AccLayout::SLOPE_OFF + 1, v[2]);
         }
     }
 }
@@ -328,8 +328,8 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_sums_codes_kernel(const fqss_tcn
     double v[4];
     block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
-        atomicAdd(acc + L.q + 2 * Q4, v[0]);
-        atomicAdd(acc + L.q + 2 * Q4 + 1, v[1]);
+        atomicAdd(acc + L.qs(c) + 2 * Q4, v[0]);
+        atomicAdd(acc + L.qs(c) + 2 * Q4 + 1, v[1]);
         acc[L.row2 + 2 * r] = v[2];
         acc[L.row2 + 2 * r + 1] = v[3];
     }
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_bwd_kernel(const fqss_tcn_block p,
     double v[8];
     block_sum_fd<8>(s, v, sh);
     if (threadIdx.x == 0) {
-        if (QUANT) { atomicAdd(acc + L.q + 2 * Q2, v[0]); atomicAdd(acc + L.q + 2 * Q2 + 1, v[1]); }
+        if (QUANT) { atomicAdd(acc + L.qs(c) + 2 * Q2, v[0]); atomicAdd(acc + L.qs(c) + 2 * Q2 + 1, v[1]); }
         acc[L.row1 + 2 * r] = v[2];
         acc[L.row1 + 2 * r + 1] = v[3];
         atomicAdd(acc + L.dwdw + 3 * c, v[4]);
@@ -683,10 +683,10 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_dw_bwd_kernel(const fqss_tcn_blo
     block_sum_fd<11>(s, v, sh);
     if (threadIdx.x == 0) {
         if (QUANT) {
-            atomicAdd(acc + L.q + 2 * Q3, v[0]); atomicAdd(acc + L.q + 2 * Q3 + 1, v[1]);
-            atomicAdd(acc + L.q + 2 * Q2, v[3]); atomicAdd(acc + L.q + 2 * Q2 + 1, v[4]);
+            atomicAdd(acc + L.qs(c) + 2 * Q3, v[0]); atomicAdd(acc + L.qs(c) + 2 * Q3 + 1, v[1]);
+            atomicAdd(acc + L.qs(c) + 2 * Q2, v[3]); atomicAdd(acc + L.qs(c) + 2 * Q2 + 1, v[4]);
         }
-        atomicAdd(acc + L.slope + 1, v[2]);
+        atomicAdd(acc + L.qs(c) + AccLayout::SLOPE_OFF + 1, v[2]);
         acc[L.row1 + 2 * r] = v[5];
         acc[L.row1 + 2 * r + 1] = v[6];
         atomicAdd(acc + L.dwdw + 3 * c, v[7]);
@@ -781,8 +781,8 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
     double v[4];
     block_sum_fd<4>(s, v, sh);
     if (threadIdx.x == 0) {
-        if (QUANT) { atomicAdd(acc + L.q + 2 * Q1, v[0]); atomicAdd(acc + L.q + 2 * Q1 + 1, v[1]); }
-        atomicAdd(acc + L.slope, v[2]);
+        if (QUANT) { atomicAdd(acc + L.qs(c) + 2 * Q1, v[0]); atomicAdd(acc + L.qs(c) + 2 * Q1 + 1, v[1]); }
+        atomicAdd(acc + L.qs(c) + AccLayout::SLOPE_OFF, v[2]);
         atomicAdd(acc + L.db1 + c, v[3]);
     }
 }
@@ -799,13 +799,18 @@ __global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_b
         g.g_gn2_w[i] = (float)acc[L.gln2 + 2 * i + 1];
     }
     if (i < 8 && p.quant) {
-        const double sD = acc[L.q + 2 * i], sZ = acc[L.q + 2 * i + 1];
+        double sD = 0.0, sZ = 0.0;
+        for (int k = 0; k < AccLayout::NSLOT; ++k) {
+            sD += acc[L.qs(k) + 2 * i];
+            sZ += acc[L.qs(k) + 2 * i + 1];
+        }
         g.g_q[2 * i] = (float)(sZ - sD / 255.0);      // d/d min_range
         g.g_q[2 * i + 1] = (float)(sD / 255.0);       // d/d max_range
     }
-    if (i == 0) {
-        g.g_slope1[0] = (float)acc[L.slope];
-        g.g_slope3[0] = (float)acc[L.slope + 1];
+    if (i == 8 || i == 9) {
+        double sl = 0.0;
+        for (int k = 0; k < AccLayout::NSLOT; ++k) sl += acc[L.qs(k) + AccLayout::SLOPE_OFF + (i - 8)];
+        (i == 8 ? g.g_slope1 : g.g_slope3)[0] = (float)sl;
     }
     if (i < p.Chid) {
         g.db1[i] = (float)acc[L.db1 + i];

@@ -12,11 +12,16 @@ int num_sms();
 
 // fp64 accumulator block inside the workspace
 struct AccLayout {
-    int64_t q, slope, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, gln1, gln2, total;
+    // Sums every row CTA of a launch adds to (the range sums of the eight activation quantisers, the two PReLU slopes) are
+    // spread over NSLOT copies, one per 256-byte line, chosen by the CTA's channel: 16 K fp64 atomics of one launch on ONE
+    // address serialise in L2 (measured on B200: 18 us of the 71 us gLN2 sums kernel, and the backlog slows the next kernel).
+    // The finalise kernel adds the copies in slot order.
+    static constexpr int NSLOT = 32, SLOT_STRIDE = 32, SLOPE_OFF = 16;
+    int64_t glob, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, gln1, gln2, total;
+    __host__ __device__ int64_t qs(int slot) const { return glob + (int64_t)(slot & (NSLOT - 1)) * SLOT_STRIDE; }
     __host__ __device__ AccLayout(int B, int Cio, int Chid) {
         int64_t o = 0;
-        q = o; o += 16;
-        slope = o; o += 2;
+        glob = o; o += (int64_t)NSLOT * SLOT_STRIDE;      // per slot: [16 range sums | 2 slope sums | pad]
         db1 = o; o += Chid;
         db2 = o; o += 2 * Cio;
         dbdw = o; o += Chid;

@@ -259,6 +259,37 @@ __device__ __forceinline__ uint2 float4_to_bf16x4(float a, float b, float c, flo
 __device__ __forceinline__ uint2 ldg_bf16x4(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
 
 // ---------------------------------------------------------------------------------------------
+// shared-memory table lookups of the row kernels: tables sit on a (256 << SH)-byte boundary, so the address of the entry
+// of `byte k of w` is SHF + LOP3
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+// shared-memory address of table entry `byte k of w` : ((w >> s) & (255 << SH)) | base   (base aligned to 256 << SH)
+template <int SH>
+__device__ __forceinline__ uint32_t tab_addr(uint32_t w, int k, uint32_t base) {
+    const int s = 8 * k - SH;
+    return ((s >= 0 ? (w >> s) : (w << -s)) & (255u << SH)) | base;
+}
+// keep a CTA-uniform value in a VECTOR register: the element loops use these as FSEL / LOP3 operands, which cannot read the
+// uniform register file, so a uniform-register copy costs one extra move per use
+__device__ __forceinline__ float vreg(float x) {
+    asm volatile("mov.b32 %0, %0;" : "+f"(x));
+    return x;
+}
+__device__ __forceinline__ uint32_t vreg(uint32_t x) {
+    asm volatile("mov.b32 %0, %0;" : "+r"(x));
+    return x;
+}
+// ---------------------------------------------------------------------------------------------
 // dilated 3-tap reads from a shared-memory row with a zero halo of dw_pad(d) floats on both sides
 // ---------------------------------------------------------------------------------------------
 template <int DMODE>

@@ -17,6 +17,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "fqss_common.cuh"
 #include "gemm_tc.cuh"
 #include "tcn_common.cuh"
@@ -156,15 +158,19 @@ __device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z,
 
 template <bool QUANT, int DMODE, int NTH>
 __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p) {
-    extern __shared__ __align__(16) float dsm[];     // [dpad | ld | dpad] a2 row with zero halo, then the table
+    // dynamic shared memory: [slack to a 1 KB boundary | table 1 KB | dpad | ld | dpad]: a2 row with a zero halo
+    extern __shared__ __align__(16) uint8_t dsm_raw[];
     __shared__ double sh[2 * 32];
     __shared__ unsigned shi[2 * 8];
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const int M = p.M, d = p.dil, dpad = dw_pad(d);
     const int ld = (int)p.ld;
+    const uint32_t raw_s = smem_addr(dsm_raw);
+    const uint32_t tab_s = (raw_s + 1023u) & ~1023u;
+    float* lut = reinterpret_cast<float*>(dsm_raw + (tab_s - raw_s));
+    float* dsm = lut + 256;
     float* row = dsm + dpad;
-    float* lut = dsm + ld + 2 * dpad;
     const Hidden1 h = load_hidden1(p, b, c);
     for (int i = threadIdx.x; i < dpad; i += NTH) {
         dsm[i] = 0.f;
@@ -176,7 +182,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
     }
     const float* y1 = p.y1 + r * p.ld;
     const uint32_t* code1 = reinterpret_cast<const uint32_t*>(p.code1 + r * p.ld);      // written by the expand GEMM's epilogue
-    const int nvec = ld >> 2;
+    const int nvec = ld >> 2, nfull = M >> 2;
     auto put = [&](int v, float4 a) {
         if (4 * v + 3 >= M) {            // ragged tail / pad columns: the FIR must see zeros there
             if (4 * v + 0 >= M) a.x = 0.f;
@@ -187,34 +193,43 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
         *reinterpret_cast<float4*>(row + 4 * v) = a;
     };
     if (QUANT) {
-        // code words first (4 in flight per thread: a row is ~1000 of them), then one table lookup per frame
+        // code words first (4 in flight per thread: a row is ~1000 of them), then one table lookup per frame (SHF + LOP3 +
+        // LDS); the full quads run without frame checks, the ragged / pad quads (at most two) go through put()
         constexpr int NQ = 4;
-        for (int base = threadIdx.x; base < nvec; base += NQ * NTH) {
+        const uint32_t tb = vreg(tab_s);
+        auto look = [&](uint32_t w) {
+            return make_float4(lds32(tab_addr<2>(w, 0, tb)), lds32(tab_addr<2>(w, 1, tb)), lds32(tab_addr<2>(w, 2, tb)),
+                               lds32(tab_addr<2>(w, 3, tb)));
+        };
+        for (int base = threadIdx.x; base < nfull; base += NQ * NTH) {
             uint32_t cw[NQ];
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) cw[q] = (base + q * NTH < nvec) ? __ldg(code1 + base + q * NTH) : 0u;
+            for (int q = 0; q < NQ; ++q) cw[q] = (base + q * NTH < nfull) ? __ldg(code1 + base + q * NTH) : 0u;
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const int v = base + q * NTH;
-                if (v < nvec) put(v, make_float4(lut[cw[q] & 255u], lut[(cw[q] >> 8) & 255u], lut[(cw[q] >> 16) & 255u], lut[cw[q] >> 24]));
+                if (v < nfull) *reinterpret_cast<float4*>(row + 4 * v) = look(cw[q]);
             }
         }
+        for (int v = nfull + threadIdx.x; v < nvec; v += NTH) put(v, look(__ldg(code1 + v)));
     } else {
         constexpr int NQ = 4;
-        for (int base = threadIdx.x; base < nvec; base += NQ * NTH) {
+        auto norm = [&](const float4 y) {
+            return make_float4(gln_apply(h.g, prelu_f(y.x, h.slope)), gln_apply(h.g, prelu_f(y.y, h.slope)),
+                               gln_apply(h.g, prelu_f(y.z, h.slope)), gln_apply(h.g, prelu_f(y.w, h.slope)));
+        };
+        for (int base = threadIdx.x; base < nfull; base += NQ * NTH) {
             float4 yv[NQ];
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                yv[q] = (base + q * NTH < nvec) ? ldg4_stream(y1 + 4 * (base + q * NTH)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                yv[q] = (base + q * NTH < nfull) ? ldg4_stream(y1 + 4 * (base + q * NTH)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const int v = base + q * NTH;
-                const float4 y = yv[q];
-                if (v < nvec)
-                    put(v, make_float4(gln_apply(h.g, prelu_f(y.x, h.slope)), gln_apply(h.g, prelu_f(y.y, h.slope)),
-                                       gln_apply(h.g, prelu_f(y.z, h.slope)), gln_apply(h.g, prelu_f(y.w, h.slope))));
+                if (v < nfull) *reinterpret_cast<float4*>(row + 4 * v) = norm(yv[q]);
             }
         }
+        for (int v = nfull + threadIdx.x; v < nvec; v += NTH) put(v, norm(ldg4_stream(y1 + 4 * v)));
     }
     __syncthreads();
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
@@ -227,16 +242,17 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
     const bool fold = !QUANT && p.split == 2;
     __nv_bfloat16* a3_hi = reinterpret_cast<__nv_bfloat16*>(p.a4_op) + ((int64_t)b * 2 * p.Chid + c) * p.ld;
     __nv_bfloat16* a3_lo = a3_hi + (int64_t)p.Chid * p.ld;
-    // statistics of a3 = FQ3(PReLU(y3)): the quantised model accumulates the integer codes (sum c, sum c^2, exact),
-    // a3 = delta*c + min is expanded at the end; the float model sums the values
+    // statistics of a3 = FQ3(PReLU(y3)): the quantised model accumulates the integer codes (sum c, sum c^2, exact; one
+    // IDP.4A each on the packed code word), a3 = delta*c + min is expanded at the end; the float model sums the values
     float s = 0.f, ss = 0.f;
     unsigned sc = 0u, scc = 0u;
-    for (int v = threadIdx.x; v < nvec; v += NTH) {
+    const bool st_y3 = p.y3 != nullptr;      // NULL in quantised inference: only backward reads y3 (the codes carry on)
+    auto body = [&](int v, auto tail_tag) {
+        constexpr bool TAIL = decltype(tail_tag)::value;
         float4 L, C, R;
         dw_taps<DMODE>(row, v, d, L, C, R);
         const float2 o01 = __ffma2_rn(w2, lo2(R), __ffma2_rn(w1, lo2(C), __ffma2_rn(w0, lo2(L), bias)));
         const float2 o23 = __ffma2_rn(w2, hi2(R), __ffma2_rn(w1, hi2(C), __ffma2_rn(w0, hi2(L), bias)));
-        const int nval = M - 4 * v;      // statistics over valid frames only
         const float2 z01 = make_float2(prelu_f(o01.x, slope3), prelu_f(o01.y, slope3));
         const float2 z23 = make_float2(prelu_f(o23.x, slope3), prelu_f(o23.y, slope3));
         if (!QUANT && fold) {
@@ -245,7 +261,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
             const float4 hv = bf16x4_to_float4(pk);
             *reinterpret_cast<uint2*>(a3_hi + 4 * v) = pk;
             *reinterpret_cast<uint2*>(a3_lo + 4 * v) = float4_to_bf16x4(z01.x - hv.x, z01.y - hv.y, z23.x - hv.z, z23.y - hv.w);
-        } else if (p.y3) {               // NULL in quantised inference: only backward reads y3 (the codes carry on)
+        } else if (st_y3) {
             stg4(y3 + 4 * v, make_float4(o01.x, o01.y, o23.x, o23.y));
         }
         if (QUANT) {
@@ -253,16 +269,19 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
             // the backward sums read 1 B/frame instead of re-deriving the code from y3
             const float2 t01 = actqf_t2(q3, z01), t23 = actqf_t2(q3, z23);
             unsigned c0 = code_u8(t01.x), c1 = code_u8(t01.y), c2 = code_u8(t23.x), c3 = code_u8(t23.y);
-            if (nval < 4) {
+            if (TAIL) {                  // statistics over valid frames only; codes at frames >= M are stored as 0
+                const int nval = M - 4 * v;
                 c3 = 0u;
                 if (nval < 3) c2 = 0u;
                 if (nval < 2) c1 = 0u;
                 if (nval < 1) c0 = 0u;
             }
-            if (code3) code3[v] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
-            sc += c0 + c1 + c2 + c3;
-            scc += c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+            const unsigned word = __byte_perm(__byte_perm(c0, c1, 0x1140), __byte_perm(c2, c3, 0x1140), 0x5410);
+            if (code3) code3[v] = word;
+            sc = __dp4a(word, 0x01010101u, sc);
+            scc = __dp4a(word, word, scc);
         } else {
+            const int nval = TAIL ? M - 4 * v : 4;
             float z[4] = {z01.x, z01.y, z23.x, z23.y};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -271,7 +290,9 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
                 ss = fmaf(a3, a3, ss);
             }
         }
-    }
+    };
+    for (int v = threadIdx.x; v < nfull; v += NTH) body(v, std::false_type{});
+    for (int v = nfull + threadIdx.x; v < nvec; v += NTH) body(v, std::true_type{});
     if (QUANT) {
         sc = __reduce_add_sync(0xffffffffu, sc);
         scc = __reduce_add_sync(0xffffffffu, scc);
@@ -590,7 +611,7 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     // K2 / K3a
     {
         const int dpad = dw_pad(p->dil);
-        const size_t smem = ((size_t)p->ld + 2 * dpad + 256) * sizeof(float);
+        const size_t smem = 2048 + ((size_t)p->ld + 2 * dpad) * sizeof(float);      // slack to a 1 KB boundary + table + row with halo
         FQSS_REQUIRE(smem <= 200 * 1024, -1, "tcn_block_fwd: row + dilation halo do not fit shared memory (M=%d, dil=%d)", p->M, p->dil);
         static bool cfg = false;
         if (!cfg) {

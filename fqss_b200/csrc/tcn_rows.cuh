@@ -23,33 +23,6 @@
 
 namespace fqss {
 
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float2 lds64(uint32_t a) {
-    float2 v;
-    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ float lds32(uint32_t a) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
-    return v;
-}
-// shared-memory address of table entry `byte k of w` : ((w >> s) & (255 << SH)) | base   (base aligned to 256 << SH)
-template <int SH>
-__device__ __forceinline__ uint32_t tab_addr(uint32_t w, int k, uint32_t base) {
-    const int s = 8 * k - SH;
-    return ((s >= 0 ? (w >> s) : (w << -s)) & (255u << SH)) | base;
-}
-// keep a CTA-uniform value in a VECTOR register: the element loops use these as FSEL / LOP3 operands, which cannot read the
-// uniform register file, so a uniform-register copy costs one extra move per use
-__device__ __forceinline__ float vreg(float x) {
-    asm volatile("mov.b32 %0, %0;" : "+f"(x));
-    return x;
-}
-__device__ __forceinline__ uint32_t vreg(uint32_t x) {
-    asm volatile("mov.b32 %0, %0;" : "+r"(x));
-    return x;
-}
 // x if lo <= z < hi else 0 -- two compares feeding ONE select (setp.ge, then setp.lt.and)
 __device__ __forceinline__ float sel_in(float x, float z, float lo, float hi) {
     float r;
@@ -278,12 +251,12 @@ __global__ void __launch_bounds__(NTH, MINB) tcn_gln2_dw_bwd_lean_kernel(const f
         const double x0 = (double)t3[0], x1 = (double)t3[1], x2 = (double)t3[2];
         if (w == 0) {
             // sD(q3) = sum_in gz*(c - t) + 255 * sum_above (ga3 - gz);  sum u*(ta + 8c) = ta * sum u + 8 * 255 * sum_above u
-            atomicAdd(acc + L.q + 2 * Q3, x0 * (double)h3.q3.inv + 0.125 * (x1 - (double)ta * x2));
-            atomicAdd(acc + L.q + 2 * Q3 + 1, x2);
+            atomicAdd(acc + L.qs(c) + 2 * Q3, x0 * (double)h3.q3.inv + 0.125 * (x1 - (double)ta * x2));
+            atomicAdd(acc + L.qs(c) + 2 * Q3 + 1, x2);
         } else if (w == 1) {
-            atomicAdd(acc + L.slope + 1, x0);
-            atomicAdd(acc + L.q + 2 * Q2, x1 - (double)MASK_OFF * x2);
-            atomicAdd(acc + L.q + 2 * Q2 + 1, x2);
+            atomicAdd(acc + L.qs(c) + AccLayout::SLOPE_OFF + 1, x0);
+            atomicAdd(acc + L.qs(c) + 2 * Q2, x1 - (double)MASK_OFF * x2);
+            atomicAdd(acc + L.qs(c) + 2 * Q2 + 1, x2);
         } else if (w == 2) {
             // xhat1 = (delta1*c + min1 - mu1) * rstd1 = xa * (8c) + xb
             const double xa = 0.125 * (double)h1.q1.delta * (double)h1.g.rstd, xb = ((double)h1.q1.mn - (double)h1.g.mu) * (double)h1.g.rstd;
@@ -318,16 +291,18 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_sums_lean_kernel(const fqss_tcn_
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Chid), c = (int)(r % p.Chid);
     const int M = p.M;
-    const int nq = (M + 3) >> 2;
     const uint32_t* c3 = reinterpret_cast<const uint32_t*>(p.code3 + r * p.ld);
     const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
+    const int nfull = M >> 2;
     uint32_t cw[NQ];
     uint2 gw[NQ];
+    // quads beyond the last full one load as zeros: a zero gradient adds nothing to any of the four sums (every table entry
+    // is finite), so the element loop runs without frame checks; the ragged quad (M % 4 frames) is handled once, below
     auto issue = [&](int base) {
 #pragma unroll
         for (int k = 0; k < NQ; ++k) {
             const int v = base + k * NTH;
-            const bool ok = v < nq;
+            const bool ok = v < nfull;
             cw[k] = ok ? __ldg(c3 + v) : 0u;
             gw[k] = ok ? __ldg(ga4 + v) : make_uint2(0u, 0u);
         }
@@ -344,35 +319,31 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_sums_lean_kernel(const fqss_tcn_
         tabD[i] = e.y != 0.f ? e.z : e.z + MASK_OFF;
     }
     __syncthreads();
-    // a0 = sum g*D4' (two scalar lanes), a1 = sum g*(1-m4), s2 = sum gn, scf = sum gn*(tb + 4c)
-    float a0x = 0.f, a0y = 0.f;
-    float2 a1 = f2s(0.f), s2 = f2s(0.f), scf = f2s(0.f);
-    for (int base = threadIdx.x; base < nq; base += NQ * NTH) {
+    // a0 = sum g*D4', a1 = sum g*(1-m4), s2 = sum gn, scf = sum gn*(tb + 4c)  -- all as frame pairs (packed FP32x2)
+    float2 a0 = f2s(0.f), a1 = f2s(0.f), s2 = f2s(0.f), scf = f2s(0.f);
+    auto quad = [&](const uint32_t cq, const uint2 gq, const int nval) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t w = j ? gq.y : gq.x;
+            float2 gg = make_float2(bf16lo(w), bf16hi(w));
+            if (2 * j + 1 >= nval) gg.y = 0.f;        // nval = 4 in the loop: folded away
+            if (2 * j >= nval) gg.x = 0.f;
+            const uint32_t ax = tab_addr<2>(cq, 2 * j, tb), ay = tab_addr<2>(cq, 2 * j + 1, tb);
+            const float2 dd = make_float2(lds32(ax), lds32(ay));
+            const float2 gn = make_float2(dd.x < MASK_CUT ? gg.x : 0.f, dd.y < MASK_CUT ? gg.y : 0.f);
+            a0 = __ffma2_rn(gg, dd, a0);
+            a1 = __fadd2_rn(a1, __fadd2_rn(gg, neg2(gn)));
+            s2 = __fadd2_rn(s2, gn);
+            scf = __ffma2_rn(gn, make_float2((float)ax, (float)ay), scf);
+        }
+    };
+    for (int base = threadIdx.x; base < nfull; base += NQ * NTH) {
         if (base != (int)threadIdx.x) issue(base);
 #pragma unroll
-        for (int k = 0; k < NQ; ++k) {
-            const int v = base + k * NTH;
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint32_t w = j ? gw[k].y : gw[k].x;
-                float gx = bf16lo(w), gy = bf16hi(w);
-                if (4 * v + 3 >= M) {                 // ragged quad (and the zero words of quads beyond the row): no gradient at frames >= M
-                    if (4 * v + 2 * j + 1 >= M) gy = 0.f;
-                    if (4 * v + 2 * j >= M) gx = 0.f;
-                }
-                const uint32_t ax = tab_addr<2>(cw[k], 2 * j, tb), ay = tab_addr<2>(cw[k], 2 * j + 1, tb);
-                const float dx = lds32(ax), dy = lds32(ay);
-                const float2 gg = make_float2(gx, gy);
-                const float2 gn = make_float2(dx < MASK_CUT ? gx : 0.f, dy < MASK_CUT ? gy : 0.f);
-                a0x = fmaf(gx, dx, a0x);
-                a0y = fmaf(gy, dy, a0y);
-                a1 = __fadd2_rn(a1, __fadd2_rn(gg, neg2(gn)));
-                s2 = __fadd2_rn(s2, gn);
-                scf = __ffma2_rn(gn, make_float2((float)ax, (float)ay), scf);
-            }
-        }
+        for (int k = 0; k < NQ; ++k) quad(cw[k], gw[k], 4);
     }
-    const float sv[4] = {a0x + a0y, hsum(a1), hsum(s2), hsum(scf)};
+    if ((M & 3) && (int)threadIdx.x == (nfull % NTH)) quad(__ldg(c3 + nfull), __ldg(ga4 + nfull), M & 3);
+    const float sv[4] = {hsum(a0), hsum(a1), hsum(s2), hsum(scf)};
     float t1[1];
     block_sums_t<NTH, 4>(sv, red, t1);
     // every warp now holds ONE of the four totals in lane 0; combine through shared memory
@@ -381,8 +352,8 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_sums_lean_kernel(const fqss_tcn_
     __syncthreads();
     if (threadIdx.x == 0) {
         const double x0 = (double)red[0], x1 = (double)red[1], x2 = (double)red[2], x3 = (double)red[3];
-        atomicAdd(acc + L.q + 2 * Q4, x0 - (double)MASK_OFF * x1);
-        atomicAdd(acc + L.q + 2 * Q4 + 1, x1);
+        atomicAdd(acc + L.qs(c) + 2 * Q4, x0 - (double)MASK_OFF * x1);
+        atomicAdd(acc + L.qs(c) + 2 * Q4 + 1, x1);
         // xhat3 = (delta3*c + min3 - mu) * rstd = xa * (4c) + xb
         const double xa = 0.25 * (double)h.q3.delta * (double)h.g.rstd, xb = ((double)h.q3.mn - (double)h.g.mu) * (double)h.g.rstd;
         const double s3 = xa * (x3 - (double)tb * x2) + xb * x2;
