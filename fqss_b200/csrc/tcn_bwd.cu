@@ -956,7 +956,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     const bool lean = p->quant && lean_env && !split_p2d;
     if (lean) {
         FQSS_PROF("tcn_gln2_sums", s);
-        tcn_gln2_sums_lean_kernel<128, 4><<<rows_h, 128, P1_LEAN_SMEM, s>>>(*p, *g, acc);
+        tcn_gln2_sums_lean_kernel<128, 8><<<rows_h, 128, P1_LEAN_SMEM, s>>>(*p, *g, acc);
     } else {
         {
             FQSS_PROF("tcn_gln2_bwd<1>", s);

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
     if (QUANT) {
         // code words first (4 in flight per thread: a row is ~1000 of them), then one table lookup per frame (SHF + LOP3 +
         // LDS); the full quads run without frame checks, the ragged / pad quads (at most two) go through put()
-        constexpr int NQ = 4;
+        constexpr int NQ = 8;
         const uint32_t tb = vreg(tab_s);
         auto look = [&](uint32_t w) {
             return make_float4(lds32(tab_addr<2>(w, 0, tb)), lds32(tab_addr<2>(w, 1, tb)), lds32(tab_addr<2>(w, 2, tb)),
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
         }
         for (int v = nfull + threadIdx.x; v < nvec; v += NTH) put(v, look(__ldg(code1 + v)));
     } else {
-        constexpr int NQ = 4;
+        constexpr int NQ = 8;
         auto norm = [&](const float4 y) {
             return make_float4(gln_apply(h.g, prelu_f(y.x, h.slope)), gln_apply(h.g, prelu_f(y.y, h.slope)),
                                gln_apply(h.g, prelu_f(y.z, h.slope)), gln_apply(h.g, prelu_f(y.w, h.slope)));
