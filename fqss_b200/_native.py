@@ -10,7 +10,8 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libfqss_sm100.so")
+# FQSS_LIB_PATH: development knob -- A/B runs of two builds of the library inside one GPU session
+LIB_PATH = os.environ.get("FQSS_LIB_PATH") or os.path.join(_HERE, "_lib", "libfqss_sm100.so")
 
 _lib = None
 _lock = threading.Lock()

@@ -167,8 +167,10 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_bwd_kernel(const fqss_tcn_block 
     if (PHASE == 2) {
         const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
         A = f2s(h.g.rstd * h.g.gamma);
-        nBc = f2s(-h.g.rstd * invN * (float)acc[L.samp2 + 2 * b]);
-        nCc = f2s(-h.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1]);
+        double sm1, sm2;
+        samp_get(acc, L, 2, b, sm1, sm2);
+        nBc = f2s(-h.g.rstd * invN * (float)sm1);
+        nCc = f2s(-h.g.rstd * invN * (float)sm2);
     }
     const float slope = h.slope;
     // P1: a0 = sum g*D4, a1 = sum g*(1-m4), a2 = sum g*m4, a3 = sum g*m4*xhat     (q4: sD = a0, sZ = a1)
@@ -554,8 +556,10 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_dw_bwd_kernel(const fqss_tcn_blo
         const uint2* ga4 = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(g.g_hid_a) + r * p.ld);
         const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
         const float2 A = f2s(h3.g.rstd * h3.g.gamma);
-        const float2 nBc = f2s(-h3.g.rstd * invN * (float)acc[L.samp2 + 2 * b]);
-        const float2 nCc = f2s(-h3.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1]);
+        double sm1, sm2;
+        samp_get(acc, L, 2, b, sm1, sm2);
+        const float2 nBc = f2s(-h3.g.rstd * invN * (float)sm1);
+        const float2 nCc = f2s(-h3.g.rstd * invN * (float)sm2);
         const float slope = h3.slope;
         struct Ld { float4 y; uint2 g; };
         auto load = [&](int v) {
@@ -719,8 +723,10 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
     uint2* dY1 = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(g.dY1) + r * p.ld);
     const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
     const float2 A2 = f2s(h.g.rstd * h.g.gamma);
-    const float2 nBc = f2s(-h.g.rstd * invN * (float)acc[L.samp1 + 2 * b]);
-    const float2 nCc = f2s(-h.g.rstd * invN * (float)acc[L.samp1 + 2 * b + 1]);
+    double sm1, sm2;
+    samp_get(acc, L, 1, b, sm1, sm2);
+    const float2 nBc = f2s(-h.g.rstd * invN * (float)sm1);
+    const float2 nCc = f2s(-h.g.rstd * invN * (float)sm2);
     // xhat1 = (a1 - mu) * rstd with a1 = delta1 * code + min1  ->  one FMA on the code
     const float2 xa = f2s(QUANT ? h.q1.delta * h.g.rstd : 0.f);
     const float2 xb = f2s(QUANT ? (h.q1.mn - h.g.mu) * h.g.rstd : 0.f);

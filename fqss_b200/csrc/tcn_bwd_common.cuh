@@ -17,7 +17,15 @@ struct AccLayout {
     // address serialise in L2 (measured on B200: 18 us of the 71 us gLN2 sums kernel, and the backlog slows the next kernel).
     // The finalise kernel adds the copies in slot order.
     static constexpr int NSLOT = 32, SLOT_STRIDE = 32, SLOPE_OFF = 16;
-    int64_t glob, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, gln1, gln2, total;
+    // The per-sample gLN sums {S1, S2} of the lean row kernels are split the same way over NSS copies chosen by the channel
+    // (sslot1 / sslot2; the 512 row CTAs of a sample run back to back, so their atomics queue on one sector).  The readers --
+    // every CTA of the next row kernel, at its start -- add samp + all copies (samp_get), so NSS stays small: measured on one
+    // B200 in one session (scratch/gpu_ab.sh), gLN2 sums / fused gLN2+depthwise / gLN1 kernels: 1 copy 55.4 / 166.4 / 95.6 us,
+    // 2 copies 48.9 / 158.9 / 94.9 us, 8 copies 49.0 / 169.0 / 98.0 us.  The non-lean path's reduce kernel writes samp1 / samp2
+    // and leaves the copies zero.
+    static constexpr int NSS = 2;
+    int64_t glob, db1, db2, dbdw, dwdw, row1, row2, samp1, samp2, sslot1, sslot2, gln1, gln2, total;
+    __host__ __device__ int64_t ss(int64_t base, int b, int slot) const { return base + ((int64_t)b * NSS + (slot & (NSS - 1))) * 4; }
     __host__ __device__ int64_t qs(int slot) const { return glob + (int64_t)(slot & (NSLOT - 1)) * SLOT_STRIDE; }
     __host__ __device__ AccLayout(int B, int Cio, int Chid) {
         int64_t o = 0;
@@ -30,11 +38,27 @@ struct AccLayout {
         row2 = o; o += 2 * (int64_t)B * Chid;
         samp1 = o; o += 2 * B;
         samp2 = o; o += 2 * B;
+        o = (o + 3) & ~(int64_t)3;                   // 32-byte aligned: the readers use 16-byte loads
+        sslot1 = o; o += (int64_t)B * NSS * 4;      // per (sample, copy): {S1, S2, pad, pad} -- one 32-byte sector each
+        sslot2 = o; o += (int64_t)B * NSS * 4;
         gln1 = o; o += 2 * Chid;          // {dbeta, dgamma} per channel, accumulated by the quantised row kernels (no reduce launch)
         gln2 = o; o += 2 * Chid;
         total = o;
     }
 };
+
+// per-sample gLN sums of sample b: the reduce kernel's entry plus the NSS atomic copies (independent loads, one round trip)
+__device__ __forceinline__ void samp_get(const double* acc, const AccLayout& L, int which, int b, double& s1, double& s2) {
+    const int64_t base = which == 1 ? L.samp1 : L.samp2, sb = which == 1 ? L.sslot1 : L.sslot2;
+    double a = acc[base + 2 * b], c = acc[base + 2 * b + 1];
+    double2 v[AccLayout::NSS];
+#pragma unroll
+    for (int k = 0; k < AccLayout::NSS; ++k) v[k] = *reinterpret_cast<const double2*>(acc + L.ss(sb, b, k));
+#pragma unroll
+    for (int k = 0; k < AccLayout::NSS; ++k) { a += v[k].x; c += v[k].y; }
+    s1 = a;
+    s2 = c;
+}
 
 enum { Q1 = 0, Q2 = 1, Q3 = 2, Q4 = 3, QRES = 4, QSKIP = 5, QADD = 6, QADDS = 7 };
 

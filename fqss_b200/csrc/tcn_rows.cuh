@@ -123,8 +123,10 @@ __global__ void __launch_bounds__(NTH, MINB) tcn_gln2_dw_bwd_lean_kernel(const f
     {
         const float invN = __fdividef(1.f, (float)p.Chid * (float)p.M);
         const float A = h3.g.rstd * h3.g.gamma;
-        const float nB = -h3.g.rstd * invN * (float)acc[L.samp2 + 2 * b];
-        const float nC = -h3.g.rstd * invN * (float)acc[L.samp2 + 2 * b + 1];
+        double sm1, sm2;
+        samp_get(acc, L, 2, b, sm1, sm2);
+        const float nB = -h3.g.rstd * invN * (float)sm1;
+        const float nC = -h3.g.rstd * invN * (float)sm2;
         for (int i = threadIdx.x; i < 256; i += NTH) {
             const float4 e = chain_bwd_entry(h3.q3, h3.g, h3.q4, i, false);            // {-, mask4, D4, xhat3}
             tabA[i] = make_float2(fmaf(e.w, nC, nB), e.y != 0.f ? A : 0.f);
@@ -262,8 +264,8 @@ __global__ void __launch_bounds__(NTH, MINB) tcn_gln2_dw_bwd_lean_kernel(const f
             const double xa = 0.125 * (double)h1.q1.delta * (double)h1.g.rstd, xb = ((double)h1.q1.mn - (double)h1.g.mu) * (double)h1.g.rstd;
             const double s3 = xa * (x1 - (double)tbB * x0) + xb * x0;      // sum gn1 * xhat1
             const double gm = (double)h1.g.gamma;
-            atomicAdd(acc + L.samp1 + 2 * b, gm * x0);                    // per-sample gLN1 sums (no reduce launch)
-            atomicAdd(acc + L.samp1 + 2 * b + 1, gm * s3);
+            atomicAdd(acc + L.ss(L.sslot1, b, c), gm * x0);               // per-sample gLN1 sums (no reduce launch)
+            atomicAdd(acc + L.ss(L.sslot1, b, c) + 1, gm * s3);
             atomicAdd(acc + L.gln1 + 2 * c, x0);                           // dbeta1, dgamma1
             atomicAdd(acc + L.gln1 + 2 * c + 1, s3);
             atomicAdd(acc + L.dbdw + c, x2);
@@ -358,8 +360,8 @@ __global__ void __launch_bounds__(NTH) tcn_gln2_sums_lean_kernel(const fqss_tcn_
         const double xa = 0.25 * (double)h.q3.delta * (double)h.g.rstd, xb = ((double)h.q3.mn - (double)h.g.mu) * (double)h.g.rstd;
         const double s3 = xa * (x3 - (double)tb * x2) + xb * x2;
         const double gm = (double)h.g.gamma;
-        atomicAdd(acc + L.samp2 + 2 * b, gm * x2);
-        atomicAdd(acc + L.samp2 + 2 * b + 1, gm * s3);
+        atomicAdd(acc + L.ss(L.sslot2, b, c), gm * x2);
+        atomicAdd(acc + L.ss(L.sslot2, b, c) + 1, gm * s3);
         atomicAdd(acc + L.gln2 + 2 * c, x2);
         atomicAdd(acc + L.gln2 + 2 * c + 1, s3);
     }
