@@ -159,6 +159,48 @@ __global__ void __launch_bounds__(256) dwconv_fwd_kernel(const float* __restrict
     y[row * ldy + m] = acc + (bias ? __ldg(bias + c) : 0.f);
 }
 
+// K = 3 on 16-byte aligned rows: one thread = 4 consecutive frames (128-bit loads of the centre quad and, for dil % 4 == 0,
+// of both tap quads; 128-bit store).  Same tap order and fp32 FMA chain as the scalar kernel, so the results are bit-identical.
+__global__ void __launch_bounds__(256) dwconv3_fwd_vec_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y, int64_t ldy,
+                                                             int C, int M, int dil) {
+    const int64_t row = blockIdx.x;
+    const int c = (int)(row % C);
+    const int m0 = 4 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (m0 >= M) return;
+    const float* xr = x + row * ldx;
+    const float w0 = __ldg(w + c * 3), w1 = __ldg(w + c * 3 + 1), w2 = __ldg(w + c * 3 + 2);
+    const float bb = bias ? __ldg(bias + c) : 0.f;
+    const bool full = m0 + 3 < M, al = (dil & 3) == 0;
+    float xc[4], xl[4], xq[4];
+    auto quad = [&](float (&o)[4], int j0, bool vec) {
+        if (vec) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(xr + j0));
+            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i;
+                o[i] = (j >= 0 && j < M) ? __ldg(xr + j) : 0.f;
+            }
+        }
+    };
+    quad(xc, m0, full);
+    quad(xl, m0 - dil, al && m0 - dil >= 0 && m0 - dil + 3 < M);
+    quad(xq, m0 + dil, al && m0 + dil + 3 < M);
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = fmaf(w2, xq[i], fmaf(w1, xc[i], fmaf(w0, xl[i], 0.f))) + bb;
+    float* yr = y + row * ldy + m0;
+    if (full) {
+        *reinterpret_cast<float4*>(yr) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (m0 + i < M) yr[i] = o[i];
+    }
+}
+
 // gx[j] = sum_k w[k] gy[j - (k-half)*dil];  per-row partial dW / dbias -> fp64 accumulators
 __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x,
                                                         int64_t ldx, const float* __restrict__ w, float* __restrict__ gx,
@@ -195,6 +237,75 @@ __global__ void __launch_bounds__(256) dwconv_bwd_kernel(const float* __restrict
     block_sum<DW_MAXK + 1>(v, sh);
     if (threadIdx.x == 0) {
         for (int k = 0; k < K; ++k) atomicAdd(acc + c * (DW_MAXK + 1) + k, v[k]);
+        atomicAdd(acc + c * (DW_MAXK + 1) + DW_MAXK, v[DW_MAXK]);
+    }
+}
+
+// K = 3 on 16-byte aligned rows: one thread = 4 consecutive frames per trip, 128-bit accesses (see dwconv3_fwd_vec_kernel);
+// gx keeps the scalar kernel's tap order (bit-identical), the dW / dbias partial sums are fp32 per thread, fp64 beyond
+__global__ void __launch_bounds__(256) dwconv3_bwd_vec_kernel(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x,
+                                                             int64_t ldx, const float* __restrict__ w, float* __restrict__ gx,
+                                                             int64_t ldgx, int C, int M, int dil, double* __restrict__ acc) {
+    __shared__ double sh[(DW_MAXK + 1) * 32];
+    const int64_t row = blockIdx.x;
+    const int c = (int)(row % C);
+    const float* gr = gy + row * ldgy;
+    const float* xr = x + row * ldx;
+    const float w0 = __ldg(w + c * 3), w1 = __ldg(w + c * 3 + 1), w2 = __ldg(w + c * 3 + 2);
+    const bool al = (dil & 3) == 0;
+    auto quad = [&](const float* src, float (&o)[4], int j0, bool vec) {
+        if (vec) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(src + j0));
+            o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int j = j0 + i;
+                o[i] = (j >= 0 && j < M) ? __ldg(src + j) : 0.f;
+            }
+        }
+    };
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, pb = 0.f;
+    const int nq = (M + 3) >> 2;
+    for (int v = threadIdx.x; v < nq; v += blockDim.x) {
+        const int m0 = 4 * v;
+        const bool full = m0 + 3 < M;
+        const bool vl = al && m0 - dil >= 0 && m0 - dil + 3 < M, vr = al && m0 + dil + 3 < M;
+        float gc[4], gl[4], gq[4], xc[4], xl[4], xq[4];
+        quad(gr, gc, m0, full);
+        quad(xr, xc, m0, full);
+        quad(xr, xl, m0 - dil, vl);
+        quad(xr, xq, m0 + dil, vr);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {          // dW[k] += gy[m] * x[m + (k-1) dil] (gy is zero beyond M by the guarded load)
+            p0 = fmaf(gc[i], xl[i], p0);
+            p1 = fmaf(gc[i], xc[i], p1);
+            p2 = fmaf(gc[i], xq[i], p2);
+            pb += gc[i];
+        }
+        if (gx) {
+            quad(gr, gl, m0 - dil, vl);
+            quad(gr, gq, m0 + dil, vr);
+            float o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[i] = fmaf(w2, gl[i], fmaf(w1, gc[i], fmaf(w0, gq[i], 0.f)));
+            float* gxr = gx + row * ldgx + m0;
+            if (full) {
+                *reinterpret_cast<float4*>(gxr) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (m0 + i < M) gxr[i] = o[i];
+            }
+        }
+    }
+    double v[DW_MAXK + 1];
+#pragma unroll
+    for (int k = 0; k <= DW_MAXK; ++k) v[k] = 0.0;
+    v[0] = (double)p0; v[1] = (double)p1; v[2] = (double)p2; v[DW_MAXK] = (double)pb;
+    block_sum<DW_MAXK + 1>(v, sh);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 3; ++k) atomicAdd(acc + c * (DW_MAXK + 1) + k, v[k]);
         atomicAdd(acc + c * (DW_MAXK + 1) + DW_MAXK, v[DW_MAXK]);
     }
 }
@@ -334,9 +445,14 @@ int fqss_dwconv_fwd(const float* x, int64_t ldx, const float* w, const float* bi
                     int K, int dil, void* stream) {
     FQSS_REQUIRE(x && w && y && B > 0 && C > 0 && M > 0 && K >= 1 && K <= DW_MAXK && (K & 1) && dil >= 1 && ldx >= M && ldy >= M,
                  -1, "dwconv_fwd: bad argument (odd K <= %d)", DW_MAXK);
-    dim3 grid(B * C, (M + 255) / 256);
     FQSS_PROF("dwconv_fwd(layer)", stream);
-    dwconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y, ldy, C, M, K, dil);
+    if (K == 3 && ldx % 4 == 0 && ldy % 4 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {
+        dim3 grid(B * C, ((M + 3) / 4 + 255) / 256);
+        dwconv3_fwd_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y, ldy, C, M, dil);
+    } else {
+        dim3 grid(B * C, (M + 255) / 256);
+        dwconv_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, y, ldy, C, M, K, dil);
+    }
     return check_launch("dwconv_fwd");
 }
 
@@ -349,7 +465,9 @@ int fqss_dwconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, 
     cudaStream_t s = (cudaStream_t)stream;
     FQSS_PROFN("dwconv_bwd(layer)", s, 2);
     cudaMemsetAsync(ws, 0, need, s);
-    dwconv_bwd_kernel<<<B * C, 256, 0, s>>>(gy, ldgy, x, ldx, w, gx, ldgx, C, M, K, dil, (double*)ws);
+    const bool a16 = (((uintptr_t)gy | (uintptr_t)x | (uintptr_t)gx) & 15) == 0 && ldgy % 4 == 0 && ldx % 4 == 0 && (!gx || ldgx % 4 == 0);
+    if (K == 3 && a16) dwconv3_bwd_vec_kernel<<<B * C, 256, 0, s>>>(gy, ldgy, x, ldx, w, gx, ldgx, C, M, dil, (double*)ws);
+    else dwconv_bwd_kernel<<<B * C, 256, 0, s>>>(gy, ldgy, x, ldx, w, gx, ldgx, C, M, K, dil, (double*)ws);
     dwconv_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>((const double*)ws, gw, gbias, C, K);
     return check_launch("dwconv_bwd");
 }

@@ -202,10 +202,12 @@ def test_conv1x1_vs_torch(B, Ci, Co, M):
         assert rel(a, bb) < 1e-5
 
 
-@pytest.mark.parametrize("dil", [1, 4, 128])
-def test_depthwise_vs_torch(dil):
+@pytest.mark.parametrize("dil,M", [(1, 1000), (4, 1000), (128, 1000), (2, 1003), (128, 999), (512, 1999), (8, 6)])
+def test_depthwise_vs_torch(dil, M):
+    """Per-layer depthwise conv (vectorised K = 3 kernels on aligned rows; ragged row ends, dilations that are / are not a
+    multiple of the vector width, halos longer than the row)."""
     from fqss_b200 import ops
-    B, C, M = 2, 16, 1000
+    B, C = 2, 16
     gen = torch.Generator().manual_seed(dil)
     x, w, b = torch.randn(B, C, M, generator=gen), torch.randn(C, 1, 3, generator=gen), torch.randn(C, generator=gen)
     go = torch.randn(B, C, M, generator=gen)
