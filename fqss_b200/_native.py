@@ -158,7 +158,7 @@ def lib():
                     fn = getattr(L, name)
                     fn.restype = res
                     fn.argtypes = args
-                if L.fqss_abi_version() != 20:
+                if L.fqss_abi_version() != 21:
                     raise RuntimeError("fqss_b200: ABI version mismatch (%d)" % L.fqss_abi_version())
                 _lib = L
     return _lib

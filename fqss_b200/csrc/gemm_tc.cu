@@ -182,12 +182,12 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (p.quant) q1 = load_actqf(p.q1_min, p.q1_max, 8);
         }
         if (EPI == EPI_RESSKIP && p.quant) {
-            qskip = load_actqf(p.qskip_min, p.qskip_max, 8);
+            if (p.N > p.n_res) qskip = load_actqf(p.qskip_min, p.qskip_max, 8);      // no skip columns: skip-less block
             if (p.n_res) {
                 qres = load_actqf(p.qres_min, p.qres_max, 8);
                 qadd = load_actqf(p.qadd_min, p.qadd_max, 8);
             }
-            if (!p.first_block) qadds = load_actqf(p.qadds_min, p.qadds_max, 8);
+            if (!p.first_block && p.N > p.n_res) qadds = load_actqf(p.qadds_min, p.qadds_max, 8);
         }
         const int64_t ld = LDC > 0 ? (int64_t)LDC : p.ld;
         int acc = 0;

@@ -44,19 +44,20 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Cio), o = (int)(r % p.Cio);
     const int M = p.M;
-    const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
+    const bool has_skip = !p.no_skip;
+    const int n2 = (p.has_res ? p.Cio : 0) + (has_skip ? p.Cio : 0);
     if (p.quant && threadIdx.x == 0) {
-        tq.qskip = load_actqf(p.qskip.rmin, p.qskip.rmax, 8);
+        if (has_skip) tq.qskip = load_actqf(p.qskip.rmin, p.qskip.rmax, 8);
         if (p.has_res) {
             tq.qres = load_actqf(p.qres.rmin, p.qres.rmax, 8);
             tq.qadd = load_actqf(p.qadd.rmin, p.qadd.rmax, 8);
         }
-        if (!p.first_block) tq.qadds = load_actqf(p.qadds.rmin, p.qadds.rmax, 8);
+        if (!p.first_block && has_skip) tq.qadds = load_actqf(p.qadds.rmin, p.qadds.rmax, 8);
     }
     __syncthreads();
     const ActQF qres = tq.qres, qskip = tq.qskip, qadd = tq.qadd, qadds = tq.qadds;
     const float sc_res = p.has_res ? __ldg(p.dws2 + o) : 0.f;
-    const float sc_skip = __ldg(p.dws2 + (p.has_res ? p.Cio : 0) + o);
+    const float sc_skip = has_skip ? __ldg(p.dws2 + (p.has_res ? p.Cio : 0) + o) : 0.f;
     __nv_bfloat16* dY = reinterpret_cast<__nv_bfloat16*>(g.dY2);
     __nv_bfloat16* dres = dY + ((int64_t)b * n2 + o) * p.ld;
     __nv_bfloat16* dskip = dY + ((int64_t)b * n2 + (p.has_res ? p.Cio : 0) + o) * p.ld;
@@ -75,9 +76,11 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
             ry = ldg4_stream(p.res_y + i);
             if (p.quant) xin = ldg4_stream(p.x_in + i);
         }
-        gso = ld_f4(g.g_skip_out + i);
-        sy = ldg4_stream(p.skip_y + i);
-        if (p.quant && !p.first_block) sin = ldg4_stream(p.skip_in + i);
+        if (has_skip) {
+            gso = ld_f4(g.g_skip_out + i);
+            sy = ldg4_stream(p.skip_y + i);
+            if (p.quant && !p.first_block) sin = ldg4_stream(p.skip_in + i);
+        }
         if (p.has_res) {
             float gz[4], gr[4];
 #pragma unroll
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
             stg4(g.g_xd + i, make_float4(gz[0], gz[1], gz[2], gz[3]));
             st_bf16x4(dres + m0, gr[0] * sc_res, gr[1] * sc_res, gr[2] * sc_res, gr[3] * sc_res);
         }
-        {
+        if (has_skip) {
             float gz[4], gs[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -130,11 +133,11 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
                 atomicAdd(acc + L.qs(o) + 2 * QADD, v[0]); atomicAdd(acc + L.qs(o) + 2 * QADD + 1, v[1]);
                 atomicAdd(acc + L.qs(o) + 2 * QRES, v[2]); atomicAdd(acc + L.qs(o) + 2 * QRES + 1, v[3]);
             }
-            if (!p.first_block) { atomicAdd(acc + L.qs(o) + 2 * QADDS, v[4]); atomicAdd(acc + L.qs(o) + 2 * QADDS + 1, v[5]); }
-            atomicAdd(acc + L.qs(o) + 2 * QSKIP, v[6]); atomicAdd(acc + L.qs(o) + 2 * QSKIP + 1, v[7]);
+            if (!p.first_block && has_skip) { atomicAdd(acc + L.qs(o) + 2 * QADDS, v[4]); atomicAdd(acc + L.qs(o) + 2 * QADDS + 1, v[5]); }
+            if (has_skip) { atomicAdd(acc + L.qs(o) + 2 * QSKIP, v[6]); atomicAdd(acc + L.qs(o) + 2 * QSKIP + 1, v[7]); }
         }
         if (p.has_res) atomicAdd(acc + L.db2 + o, v[8]);
-        atomicAdd(acc + L.db2 + (p.has_res ? p.Cio : 0) + o, v[9]);
+        if (has_skip) atomicAdd(acc + L.db2 + (p.has_res ? p.Cio : 0) + o, v[9]);
     }
 }
 
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(NTH) tcn_gln1_bwd_kernel(const fqss_tcn_block 
 // F: fp64 accumulators -> fp32 outputs
 __global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, const double* __restrict__ acc, int gln_from_acc) {
     const AccLayout L(p.B, p.Cio, p.Chid);
-    const int n2 = p.has_res ? 2 * p.Cio : p.Cio;
+    const int n2 = (p.has_res ? p.Cio : 0) + (p.no_skip ? 0 : p.Cio);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (gln_from_acc && i < p.Chid) {      // the lean row kernels accumulate dgamma / dbeta here (no reduce launch)
         g.g_gn1_b[i] = (float)acc[L.gln1 + 2 * i];
@@ -900,11 +903,11 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     int rc = tcn_validate_block(p, "tcn_block_bwd");
     if (rc) return rc;
     FQSS_REQUIRE(!p->quant || (p->code1 && p->code3), -1, "tcn_block_bwd: forward did not save the activation codes (code1 / code3)");
-    FQSS_REQUIRE(!p->split && p->y1 && p->y3 && p->skip_y && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
+    FQSS_REQUIRE(!p->split && p->y1 && p->y3 && (p->skip_y || p->no_skip) && (!p->has_res || p->res_y) && p->Wc1T && p->Wc2T, -1,
                  "tcn_block_bwd: block was run in inference mode (split operands / no saved pre-activations)");
-    FQSS_REQUIRE(g && g->g_skip_out && g->g_x_in && g->dY2 && g->g_hid_a && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
+    FQSS_REQUIRE(g && (g->g_skip_out || p->no_skip) && g->g_x_in && g->dY2 && g->g_hid_a && g->dY1 && g->ws, -1, "tcn_block_bwd: null buffer");
     FQSS_REQUIRE(!p->has_res || (g->g_x_out && g->g_xd), -1, "tcn_block_bwd: residual path needs g_x_out / g_xd");
-    FQSS_REQUIRE(p->first_block || g->g_skip_in, -1, "tcn_block_bwd: g_skip_in missing");
+    FQSS_REQUIRE(p->first_block || p->no_skip || g->g_skip_in, -1, "tcn_block_bwd: g_skip_in missing");
     FQSS_REQUIRE(g->dW1q && g->db1 && g->dW2q && g->db2 && g->dwdw && g->dbdw && g->g_gn1_w && g->g_gn1_b && g->g_gn2_w && g->g_gn2_b &&
                      g->g_slope1 && g->g_slope3 && g->g_q, -1, "tcn_block_bwd: null parameter-gradient output");
     FQSS_REQUIRE(g->ws_bytes >= fqss_tcn_ws_bytes(p->B, p->Cio, p->Chid), -3, "tcn_block_bwd: workspace too small");
@@ -924,7 +927,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
     double* acc = (double*)((char*)g->ws + (size_t)flip * acc_bytes);
     float* part = (float*)((char*)g->ws + 2 * acc_bytes + align_up((size_t)2 * 1024 * sizeof(float), 256));
     const size_t part_cap = g->ws_bytes - ((char*)part - (char*)g->ws);
-    const int n2 = p->has_res ? 2 * p->Cio : p->Cio;
+    const int n2 = (p->has_res ? p->Cio : 0) + (p->no_skip ? 0 : p->Cio);
     const int rows_h = p->B * p->Chid, rows_io = p->B * p->Cio;
 
     cudaMemsetAsync(acc, 0, (size_t)L.total * sizeof(double), s);

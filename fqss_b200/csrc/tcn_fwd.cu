@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
     }
     __syncthreads();
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
-    const float2 bias = f2s(__ldg(p.bdw + c));
+    const float2 bias = f2s(p.bdw ? __ldg(p.bdw + c) : 0.f);
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
     if (QUANT) q3 = load_actqf_rc(p.rc1 + 8);
@@ -494,20 +494,21 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
     FQSS_REQUIRE(p->ld >= p->M && p->ld % 8 == 0, -2, "%s: ld must be >= M and a multiple of 8", who);
     FQSS_REQUIRE(((size_t)p->ld * 2 + 4 * (size_t)((p->dil + 3) & ~3) + 1280) * sizeof(float) + (size_t)p->ld <= 200 * 1024, -1,
                  "%s: row too long for shared-memory staging (M=%d, dil=%d)", who, p->M, p->dil);
-    FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
+    FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw, -1, "%s: block not prepared", who);
+    FQSS_REQUIRE(p->no_skip == 0 || (p->no_skip == 1 && p->has_res), -1, "%s: no_skip must be 0 or 1, and a skip-less block needs the residual path", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
-    FQSS_REQUIRE(p->x_op && p->x_in && (p->y1 || p->quant) && (p->y3 || p->split == 2 || p->quant) && p->stats1 && p->stats3 && p->a4_op && p->skip_out && p->rc1 && p->rc3, -1,
+    FQSS_REQUIRE(p->x_op && p->x_in && (p->y1 || p->quant) && (p->y3 || p->split == 2 || p->quant) && p->stats1 && p->stats3 && p->a4_op && (p->skip_out || p->no_skip) && p->rc1 && p->rc3, -1,
                  "%s: missing activation buffers", who);
     FQSS_REQUIRE(!p->split || !p->quant, -1, "%s: split operands are a float-model (quant == 0) feature", who);
     FQSS_REQUIRE(p->split >= 0 && p->split <= 2, -1, "%s: split must be 0, 1 or 2", who);
     if (p->has_res) FQSS_REQUIRE(p->x_out && p->x_out_op, -1, "%s: missing residual buffers", who);
-    if (!p->first_block) FQSS_REQUIRE(p->skip_in, -1, "%s: missing skip_in", who);
+    if (!p->first_block && !p->no_skip) FQSS_REQUIRE(p->skip_in, -1, "%s: missing skip_in", who);
     if (p->quant) {
         FQSS_REQUIRE(p->code1 && p->code3, -1, "%s: the quantised path needs the code buffers (the expand GEMM hands FQ1's codes to the depthwise kernel through code1, the depthwise kernel FQ3's codes to the hidden quantiser through code3)", who);
         const fqss_qrange* qs[] = {&p->q1, &p->q2, &p->q3, &p->q4, &p->qskip};
-        for (auto q : qs) FQSS_REQUIRE(q->rmin && q->rmax, -1, "%s: missing quantiser range", who);
+        for (auto q : qs) FQSS_REQUIRE((q->rmin && q->rmax) || (q == &p->qskip && p->no_skip), -1, "%s: missing quantiser range", who);
         if (p->has_res) FQSS_REQUIRE(p->qres.rmin && p->qadd.rmin, -1, "%s: missing residual quantisers", who);
-        if (!p->first_block) FQSS_REQUIRE(p->qadds.rmin, -1, "%s: missing skip-sum quantiser", who);
+        if (!p->first_block && !p->no_skip) FQSS_REQUIRE(p->qadds.rmin, -1, "%s: missing skip-sum quantiser", who);
     }
     return 0;
 }
@@ -663,7 +664,7 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
     if (rc) return rc;
     // K3
     tcg::Args k{};
-    k.B = p->B; k.M = p->M; k.K = p->Chid; k.N = p->has_res ? 2 * p->Cio : p->Cio; k.ld = p->ld;
+    k.B = p->B; k.M = p->M; k.K = p->Chid; k.N = (p->has_res ? p->Cio : 0) + (p->no_skip ? 0 : p->Cio); k.ld = p->ld;
     if (p->split) { k.K = 3 * p->Chid; k.a_rows = 2 * p->Chid; k.split = 1; }
     if (p->split == 2) { k.fold_stats = p->stats3; k.n_elems = (double)p->Chid * (double)p->M; }
     k.s1 = p->s1_2; k.s0 = p->s0_2; k.quant = p->quant;

@@ -7,8 +7,9 @@ splitter (`fqss_split_ex`), the channel-wise LayerNorm (`fqss_cln_fwd/bwd`), the
 convolutions and the overlap-add (`fqss_ola_fwd/bwd`).
 
 Everything stays channels-first ([B, C, K]); the reference's transposes around LayerNorm / Linear are views here.
-The TCN blocks run on the per-layer wrappers (the fused tcgen05 engine of the speech model expects blocks with a skip
-path; these blocks have a residual path only)."""
+In the quantised steady state the TCN blocks run on the fused tcgen05 engine of the speech model in its skip-less mode
+(`fqss_tcn_block.no_skip`: these blocks have a residual path only); observer calibration, the float teacher and shapes the
+engine does not cover stay on the per-layer wrappers."""
 import torch
 import torch.nn as nn
 
@@ -90,9 +91,22 @@ class MaskGenerator(nn.Module):
         self.network = nn.Sequential(ChannelWiseLayerNorm(N, eps=EPS), nn.Conv1d(N, B, 1, bias=False),
                                      nn.Sequential(*repeats), nn.Conv1d(B, C * N, 1, bias=False), act)
 
+    use_fused = True      # class-level switch: False forces the per-layer wrappers (tests / debugging)
+
     def forward(self, mixture_w):
         M, N, K = mixture_w.size()
-        return self.network(mixture_w).reshape(M, self.C, N, K)
+        from ... import tcn_engine as E
+        net = self.network
+        if self.use_fused and E.fused_eligible_noskip(self, mixture_w):
+            # quantised steady state: the 40 blocks run as ONE autograd node on the fused engine (no_skip blocks:
+            # expand GEMM, depthwise row kernel, hidden quantiser, residual GEMM; fused backward), everything around them
+            # on the per-layer wrappers as before
+            h = net[1](net[0](mixture_w))
+            q = net[1].activation_fake_quantize
+            blocks = [b for rep in net[2] for b in rep]
+            h, _ = E.fused_tcn(h, blocks, None, True, (q.min_range, q.max_range), start=0, total=len(blocks) + 1)
+            return net[4](net[3](h)).reshape(M, self.C, N, K)
+        return net(mixture_w).reshape(M, self.C, N, K)
 
 
 class ConvTasNetMusicQ(nn.Module):

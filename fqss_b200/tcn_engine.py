@@ -28,7 +28,7 @@ class QRange(C.Structure):
 
 class TcnBlock(C.Structure):
     _fields_ = [("B", C.c_int32), ("M", C.c_int32), ("dil", C.c_int32), ("quant", C.c_int32), ("first_block", C.c_int32),
-                ("has_res", C.c_int32), ("Cio", C.c_int32), ("Chid", C.c_int32), ("split", C.c_int32), ("_pad0", C.c_int32),
+                ("has_res", C.c_int32), ("Cio", C.c_int32), ("Chid", C.c_int32), ("split", C.c_int32), ("no_skip", C.c_int32),
                 ("ld", i64),
                 ("Wc1", vp), ("Wc1T", vp), ("s1_1", vp), ("s0_1", vp), ("dws1", vp),
                 ("Wc2", vp), ("Wc2T", vp), ("s1_2", vp), ("s0_2", vp), ("dws2", vp),
@@ -129,8 +129,31 @@ def _wq(mod):
     return q.min_range, q.max_range
 
 
+def block_tensors_noskip(block):
+    """dict slot -> tensor (or None) for a quantised skip-less ConvBlock (ConvTasNetMusicQ, convtasnetq_music.py:141-199:
+    net = [Conv1dNlQ, -, GroupNormQ, DepthwiseSeparableConv(net = [Conv1dNlQ, -, GroupNormQ, Conv1dQ])], add = AddQ)."""
+    c1, n1 = block.net[0], block.net[2]
+    ds = block.net[3].net
+    dw, n2, res = ds[0], ds[2], ds[3]
+    d = dict(W1=c1.conv1d.weight, b1=c1.conv1d.bias, slope1=c1.nl.weight, g1w=n1.groupnorm.weight, g1b=n1.groupnorm.bias,
+             Wdw=dw.conv1d.weight, bdw=dw.conv1d.bias, slope3=dw.nl.weight, g2w=n2.groupnorm.weight, g2b=n2.groupnorm.bias,
+             Wres=res.conv1d.weight, bres=res.conv1d.bias)
+    d["w1min"], d["w1max"] = _wq(c1)
+    d["wdmin"], d["wdmax"] = _wq(dw)
+    d["wrmin"], d["wrmax"] = _wq(res)
+    d["q1min"], d["q1max"] = _aq(c1)
+    d["q2min"], d["q2max"] = _aq(n1)
+    d["q3min"], d["q3max"] = _aq(dw)
+    d["q4min"], d["q4max"] = _aq(n2)
+    d["qresmin"], d["qresmax"] = _aq(res)
+    d["qaddmin"], d["qaddmax"] = _aq(block.add)
+    return {k: d.get(k) for k in _BLOCK_SLOTS}, dw.conv1d.dilation[0]
+
+
 def block_tensors(block, adds_mod, quant):
     """dict slot -> tensor (or None) for a quantised (`quant`) or float ConvBlock."""
+    if not hasattr(block, "shared_block"):
+        return block_tensors_noskip(block)
     sb = block.shared_block
     if quant:
         c1, n1, dw, n2 = sb[0], sb[2], sb[3], sb[5]
@@ -168,7 +191,8 @@ def _prep_items(t, quant, has_res, q_in, dev, prep_items, wq_items):
     """Allocate the prepared-weight buffers of one block and append its weight-preparation work to the batch lists
     (three 1x1 convs -> fqss_tcn_prep_batch, the depthwise weight -> fqss_fq_weight_fwd_batch)."""
     Chid, Cio = t["W1"].shape[0], t["W1"].shape[1]
-    n2 = 2 * Cio if has_res else Cio
+    has_skip = t["Wskip"] is not None
+    n2 = (Cio if has_res else 0) + (Cio if has_skip else 0)
     bf = torch.bfloat16
     P = dict(Wc1=torch.empty((Chid, Cio), dtype=bf, device=dev), Wc1T=torch.empty((Cio, Chid), dtype=bf, device=dev),
              s1_1=torch.empty(Chid, device=dev), s0_1=torch.empty(Chid, device=dev), dws1=torch.empty(Chid, device=dev),
@@ -189,7 +213,8 @@ def _prep_items(t, quant, has_res, q_in, dev, prep_items, wq_items):
     if has_res:
         item(t["Wres"], t["wrmin"], t["wrmax"], t["bres"], q4[0], q4[1], P["Wc2"], P["Wc2T"], P["s1_2"], P["s0_2"], P["dws2"], Cio, Chid, n2, 0)
         off = Cio
-    item(t["Wskip"], t["wsmin"], t["wsmax"], t["bskip"], q4[0], q4[1], P["Wc2"], P["Wc2T"], P["s1_2"], P["s0_2"], P["dws2"], Cio, Chid, n2, off)
+    if has_skip:
+        item(t["Wskip"], t["wsmin"], t["wsmax"], t["bskip"], q4[0], q4[1], P["Wc2"], P["Wc2T"], P["s1_2"], P["s0_2"], P["dws2"], Cio, Chid, n2, off)
     if quant:
         wdw = torch.empty_like(t["Wdw"], memory_format=torch.contiguous_format)
         it = N.WqItem()
@@ -217,9 +242,10 @@ def _run_batches(prep_items, wq_items, wq_bwd=False):
 def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
     blk.B, blk.M, blk.dil, blk.quant, blk.first_block, blk.has_res = B, M, dil, int(quant), int(first), int(has_res)
     blk.Chid, blk.Cio, blk.ld = t["W1"].shape[0], t["W1"].shape[1], ld
+    blk.no_skip = int(t["Wskip"] is None)
     for k in ("Wc1", "Wc1T", "s1_1", "s0_1", "dws1", "Wc2", "Wc2T", "s1_2", "s0_2", "dws2", "wdw"):
         setattr(blk, k, ptr(P[k]))
-    blk.bdw = ptr(t["bdw"])
+    blk.bdw = ptr(t["bdw"]) or None
     blk.slope1, blk.slope3 = ptr(t["slope1"]), ptr(t["slope3"])
     blk.gn1_w, blk.gn1_b, blk.gn2_w, blk.gn2_b = ptr(t["g1w"]), ptr(t["g1b"]), ptr(t["g2w"]), ptr(t["g2b"])
 
@@ -234,13 +260,14 @@ def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
         setattr(blk, name, qr(t[lo], t[hi]))
 
 
-def _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant=True):
+def _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant=True, has_skip=True):
     bf = torch.bfloat16
     A = dict(y1=torch.empty((B, Chid, ld), device=dev), y3=torch.empty((B, Chid, ld), device=dev),
              stats1=torch.empty(2 * B + 1, dtype=torch.float64, device=dev), stats3=torch.empty(2 * B + 1, dtype=torch.float64, device=dev),
-             a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), skip_y=torch.empty((B, Cio, ld), device=dev),
-             skip_out=torch.empty((B, Cio, ld), device=dev), rc1=torch.empty(16 + 2 * B, device=dev),
-             rc3=torch.empty(16 + 2 * B, device=dev))
+             a4_op=torch.empty((B, Chid, ld), dtype=bf, device=dev), rc1=torch.empty(16 + 2 * B, device=dev),
+             rc3=torch.empty(16 + 2 * B, device=dev), skip_y=None, skip_out=None)
+    if has_skip:
+        A.update(skip_y=torch.empty((B, Cio, ld), device=dev), skip_out=torch.empty((B, Cio, ld), device=dev))
     if quant:
         A.update(code1=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev),
                  code3=torch.empty((B, Chid, ld), dtype=torch.uint8, device=dev))
@@ -501,12 +528,13 @@ class FusedTCNFunction(Function):
             t, P = tensors[i], preps[i]
             first, has_res = (start + i) == 0, (start + i) < total - 1
             Chid = t["W1"].shape[0]
-            A = _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant)
+            has_skip = t["Wskip"] is not None
+            A = _alloc_acts(B, Cio, Chid, ld, has_res, dev, quant, has_skip)
             blk = TcnBlock()
             _fill_block(blk, t, P, quant, first, has_res, dils[i], B, M, ld, cur_q)
             blk.x_op, blk.x_in, blk.skip_in = ptr(cur_op), ptr(cur_x), ptr(cur_skip) or None
             for k in ("y1", "stats1", "y3", "stats3", "a4_op", "skip_y", "skip_out", "rc1", "rc3"):
-                setattr(blk, k, ptr(A[k]))
+                setattr(blk, k, ptr(A[k]) or None)
             if has_res:
                 blk.res_y, blk.x_out, blk.x_out_op = ptr(A["res_y"]), ptr(A["x_out"]), ptr(A["x_out_op"])
             if quant:
@@ -530,6 +558,10 @@ class FusedTCNFunction(Function):
             x_last = torch.zeros((B, Cio, M), device=dev)          # dead output of the last block
             ctx.mark_non_differentiable(x_last)
             return x_last, cur_skip[:, :, :M]
+        if cur_skip is None:                                       # skip-less stack: there is no skip sum
+            no_skip_sum = torch.zeros(1, device=dev)
+            ctx.mark_non_differentiable(no_skip_sum)
+            return x_last[:, :, :M], no_skip_sum
         return x_last[:, :, :M], cur_skip[:, :, :M]
 
     @staticmethod
@@ -539,21 +571,22 @@ class FusedTCNFunction(Function):
         quant, B, Cio, M, ld = ctx.meta
         states = ctx.states
         ctx.states = None
-        dev = g_skip.device
+        dev = (g_skip if g_skip is not None else g_xo).device
         nb = len(states)
+        has_skip = states[0].t["Wskip"] is not None
         ns = len(_BLOCK_SLOTS)
         Chid = states[0].t["W1"].shape[0]
         bf = torch.bfloat16
         s = stream_ptr()
-        g_ss = torch.zeros((B, Cio, ld), device=dev)
-        if g_skip is not None:
+        g_ss = torch.zeros((B, Cio, ld), device=dev) if has_skip else None
+        if g_skip is not None and has_skip:
             g_ss[:, :, :M].copy_(g_skip)
         g_x = torch.zeros((B, Cio, ld), device=dev)
         if g_xo is not None and states[-1].has_res:
             g_x[:, :, :M].copy_(g_xo)
         # g_hid_b (g_y3) exists only for the two-kernel A/B path; the fused gLN2+depthwise kernel keeps it in shared memory
         two_kernel = os.environ.get("FQSS_SPLIT_P2D", "0") not in ("", "0")
-        scratch = dict(dY2=torch.empty((B, 2 * Cio, ld), dtype=bf, device=dev), ga=torch.empty((B, Chid, ld), dtype=bf, device=dev),
+        scratch = dict(dY2=torch.empty((B, (2 if has_skip else 1) * Cio, ld), dtype=bf, device=dev), ga=torch.empty((B, Chid, ld), dtype=bf, device=dev),
                        gb=torch.empty((B, Chid, ld), dtype=bf, device=dev) if two_kernel else None,
                        dY1=torch.empty((B, Chid, ld), dtype=bf, device=dev), gxd=torch.empty((B, Cio, ld), device=dev))
         ws = torch.empty(int(L.fqss_tcn_ws_bytes(B, Cio, Chid)), dtype=torch.uint8, device=dev)
@@ -562,7 +595,7 @@ class FusedTCNFunction(Function):
         for i in range(nb - 1, -1, -1):
             st = states[i]
             t = st.t
-            n2 = 2 * Cio if st.has_res else Cio
+            n2 = (Cio if st.has_res else 0) + (Cio if has_skip else 0)
             G = dict(dW1q=torch.empty((Chid, Cio), device=dev), db1=torch.empty(Chid, device=dev),
                      dW2q=torch.empty((n2, Chid), device=dev), db2=torch.empty(n2, device=dev),
                      dwdw=torch.empty((Chid, 3), device=dev), dbdw=torch.empty(Chid, device=dev),
@@ -570,7 +603,7 @@ class FusedTCNFunction(Function):
                      g2w=torch.empty(Chid, device=dev), g2b=torch.empty(Chid, device=dev),
                      sl1=torch.empty(1, device=dev), sl3=torch.empty(1, device=dev), gq=torch.zeros(16, device=dev))
             g = TcnBlockGrads()
-            g.g_x_out, g.g_skip_out, g.g_x_in, g.g_skip_in = ptr(g_x), ptr(g_ss), ptr(g_x), ptr(g_ss)
+            g.g_x_out, g.g_skip_out, g.g_x_in, g.g_skip_in = ptr(g_x), ptr(g_ss) or None, ptr(g_x), ptr(g_ss) or None
             g.dY2, g.g_hid_a, g.g_hid_b, g.dY1, g.g_xd = ptr(scratch["dY2"]), ptr(scratch["ga"]), ptr(scratch["gb"]) or None, ptr(scratch["dY1"]), ptr(scratch["gxd"])
             g.dW1q, g.db1, g.dW2q, g.db2, g.dwdw, g.dbdw = ptr(G["dW1q"]), ptr(G["db1"]), ptr(G["dW2q"]), ptr(G["db2"]), ptr(G["dwdw"]), ptr(G["dbdw"])
             g.g_gn1_w, g.g_gn1_b, g.g_gn2_w, g.g_gn2_b = ptr(G["g1w"]), ptr(G["g1b"]), ptr(G["g2w"]), ptr(G["g2b"])
@@ -602,8 +635,9 @@ class FusedTCNFunction(Function):
                 out["Wres"], out["wrmin"], out["wrmax"] = wback(G["dW2q"][:Cio], "Wres", "wrmin", "wrmax", t["Wres"].shape)
                 out["bres"] = G["db2"][:Cio]
                 off = Cio
-            out["Wskip"], out["wsmin"], out["wsmax"] = wback(G["dW2q"][off:off + Cio], "Wskip", "wsmin", "wsmax", t["Wskip"].shape)
-            out["bskip"] = G["db2"][off:off + Cio]
+            if has_skip:
+                out["Wskip"], out["wsmin"], out["wsmax"] = wback(G["dW2q"][off:off + Cio], "Wskip", "wsmin", "wsmax", t["Wskip"].shape)
+                out["bskip"] = G["db2"][off:off + Cio]
             out["slope1"], out["slope3"] = G["sl1"], G["sl3"]
             out["g1w"], out["g1b"], out["g2w"], out["g2b"] = G["g1w"], G["g1b"], G["g2w"], G["g2b"]
             if quant:
@@ -617,7 +651,7 @@ class FusedTCNFunction(Function):
         check(L.fqss_tcn_bwd_join(s))        # the blocks' weight-gradient tails ran on the library's side stream
         _run_batches([], wq_items, wq_bwd=True)
         del keep
-        g_skip_in = g_ss[:, :, :M] if (not states[0].first and ctx.needs_input_grad[1]) else None
+        g_skip_in = g_ss[:, :, :M] if (has_skip and not states[0].first and ctx.needs_input_grad[1]) else None
         return (g_x[:, :, :M], g_skip_in, None) + tuple(grads)
 
 
@@ -705,6 +739,45 @@ def rows_fit(M, max_dil):
     the per-layer path, which has no such bound."""
     ld = (M + 7) // 8 * 8
     return (ld * 2 + 4 * ((max_dil + 3) & ~3) + 1280) * 4 + ld <= 200 * 1024
+
+
+def fused_eligible_noskip(masker, x):
+    """True when the music model's MaskGenerator (convtasnetq_music.py:53-114) can hand its skip-less block stack to the
+    fused engine: quantised, observers off, 8-bit, channel counts the GEMM tiles cover, rows that fit shared memory."""
+    from .qat import qat_layers as QL
+    from .qat.qat_quant import GradientActivationFakeQuantize as AQ, GradientWeightFakeQuantize as WQm
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3:
+        return False
+    net = masker.network
+    if not isinstance(net[1], QL.Conv1dQ) or isinstance(net[1].activation_fake_quantize, torch.nn.Identity):
+        return False
+    blocks = [b for rep in net[2] for b in rep]
+    b0 = blocks[0]
+    if not hasattr(b0, "net") or not hasattr(b0.net[3], "net"):
+        return False
+    ds = b0.net[3].net
+    if not (isinstance(b0.net[0], QL.Conv1dNlQ) and isinstance(b0.net[2], QL.GroupNormQ) and isinstance(ds[0], QL.Conv1dNlQ)
+            and isinstance(ds[2], QL.GroupNormQ) and isinstance(ds[3], QL.Conv1dQ) and isinstance(b0.add, QL.AddQ)):
+        return False
+    Chid, Cio = b0.net[0].conv1d.weight.shape[0], b0.net[0].conv1d.weight.shape[1]
+    if Cio % 128 or Chid % 128 or ds[0].conv1d.kernel_size[0] != 3 or ds[0].conv1d.groups != Chid:
+        return False
+    if not rows_fit(x.shape[-1], max(b.net[3].net[0].conv1d.dilation[0] for b in blocks)):
+        return False
+    for blk in blocks:
+        for m in blk.modules():
+            if isinstance(m, AQ) and (m.observing() or m.n_bits != 8):
+                return False
+            if isinstance(m, WQm) and (m.observer_mode or m.n_bits != 8):
+                return False
+            if isinstance(m, QL.LayerQ) and type(m).__name__ in ("Conv1dNlQ", "Conv1dQ") and isinstance(m.weight_fake_quantize, torch.nn.Identity):
+                return False
+            if isinstance(m, QL.LayerQ) and isinstance(m.activation_fake_quantize, torch.nn.Identity):
+                return False
+            if isinstance(m, torch.nn.PReLU) and m.weight.numel() != 1:
+                return False
+    q = net[1].activation_fake_quantize
+    return not q.observing() and q.n_bits == 8
 
 
 def fused_eligible(masker, x):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FQSS_ABI_VERSION 20
+#define FQSS_ABI_VERSION 21
 
 int fqss_abi_version(void);
 const char* fqss_last_error(void);
@@ -229,7 +229,11 @@ typedef struct fqss_tcn_block {
                         2: additionally the second gLN is folded into the res/skip conv (Wc2, s1_2 = u, s0_2 = v
                         from fqss_tcn_prep_fold): K2 writes a3 = PReLU(y3) straight into a4_op, K3a is skipped and
                         y3 / rc3 are not touched                                                              */
-    int32_t _pad0;
+    int32_t no_skip; /* 1: the block has no skip conv and no skip sum (ConvTasNetMusicQ, convtasnetq_music.py:141-199: 1x1 -> PReLU ->
+                        gLN -> depthwise -> PReLU -> gLN -> 1x1, plus the residual): the second GEMM is the residual conv alone
+                        (Wc2 [Cio][Chid]); needs has_res = 1; skip_in / skip_y / skip_out / qskip / qadds and, in backward,
+                        g_skip_out / g_skip_in are ignored (may be NULL); dY2 is [B][Cio][ld], dW2q [Cio][Chid].  bdw may be
+                        NULL (bias-free depthwise conv) in either mode                                                 */
     int64_t ld;
     /* prepared by fqss_tcn_prep (per step) */
     const void* Wc1;  const void* Wc1T; const float* s1_1; const float* s0_1; const float* dws1;   /* expand [Chid,Cio] */

@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(native):
     for name in sorted(declared):
         assert hasattr(lib, name), "header declares %s but the library does not export it" % name
     assert set(native.EXPORTED) == declared, (set(native.EXPORTED) ^ declared)
-    assert lib.fqss_abi_version() == 20
+    assert lib.fqss_abi_version() == 21
     assert lib.fqss_ws_bytes(1024) >= 4096
 
 
