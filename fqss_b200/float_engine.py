@@ -170,3 +170,111 @@ def forward(model, x):
         if out is None:
             raise N.FqssError("float engine: a float model with an output combiner is not on the FQSS path")
         return model.post_process(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# Skip-less block stack of the music model's float teacher (convtasnetq_music.py:53-199 with quantisation disabled:
+# musdbhq_train.py builds the teacher from the same module tree).  Forward only; the layers around the stack stay on the
+# per-layer wrappers.
+# ---------------------------------------------------------------------------------------------
+def _noskip_blocks(masker):
+    return [b for rep in masker.network[2] for b in rep]
+
+
+def noskip_eligible(masker, x):
+    """True when `masker` is the music MaskGenerator with every quantiser disabled and nothing needs a gradient."""
+    from .qat import qat_layers as QL
+    if not (x.is_cuda and x.dtype == torch.float32 and x.dim() == 3):
+        return False
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in masker.parameters())):
+        return False
+    blocks = _noskip_blocks(masker)
+    b0 = blocks[0]
+    if not hasattr(b0, "net") or not hasattr(b0.net[3], "net"):
+        return False
+    ds = b0.net[3].net
+    if not (isinstance(b0.net[0], QL.Conv1dNlQ) and isinstance(b0.net[2], QL.GroupNormQ) and isinstance(ds[0], QL.Conv1dNlQ)
+            and isinstance(ds[2], QL.GroupNormQ) and isinstance(ds[3], QL.Conv1dQ) and isinstance(b0.add, QL.AddQ)):
+        return False
+    for blk in blocks:
+        for m in blk.modules():
+            if isinstance(m, QL.LayerQ) and not (isinstance(m.activation_fake_quantize, nn.Identity)
+                                                 and isinstance(m.weight_fake_quantize, nn.Identity)):
+                return False
+            if isinstance(m, nn.PReLU) and m.weight.numel() != 1:
+                return False
+    Chid, Cio = b0.net[0].conv1d.weight.shape[0], b0.net[0].conv1d.weight.shape[1]
+    if Cio % 128 or Chid % 128 or ds[0].conv1d.kernel_size[0] != 3 or ds[0].conv1d.groups != Chid:
+        return False
+    return E.rows_fit(x.shape[-1], max(b.net[3].net[0].conv1d.dilation[0] for b in blocks))
+
+
+def _prepare_noskip(masker, dev):
+    blocks = _noskip_blocks(masker)
+    key = tuple((p.data_ptr(), p._version) for b in blocks for p in b.parameters())
+    cache = getattr(masker, "_fqss_float_prep", None)
+    if cache is not None and cache[0] == key:
+        return cache[1]
+    L = E._libx()
+    s = stream_ptr()
+    f32 = dict(device=dev, dtype=torch.float32)
+    bf = torch.bfloat16
+    out = []
+    for blk in blocks:
+        t, dil = E.block_tensors_noskip(blk)
+        Chid, Cio = t["W1"].shape[0], t["W1"].shape[1]
+        Q = dict(Wc1=torch.empty((Chid, 3 * Cio), dtype=bf, device=dev), s1_1=torch.empty(Chid, **f32),
+                 s0_1=torch.empty(Chid, **f32), dws1=torch.empty(Chid, **f32),
+                 Wc2=torch.empty((Cio, 3 * Chid), dtype=bf, device=dev), s1_2=torch.empty(Cio, **f32),
+                 s0_2=torch.empty(Cio, **f32), dws2=torch.empty(Cio, **f32))
+        check(L.fqss_tcn_prep(ptr(t["W1"]), None, None, ptr(t["b1"]) or None, None, None, ptr(Q["Wc1"]), None, ptr(Q["s1_1"]),
+                              ptr(Q["s0_1"]), ptr(Q["dws1"]), Chid, Cio, Chid, 0, 1, s))
+        # residual 1x1 conv with the block's second gLN folded in (fqss_tcn_prep_fold): s1_2 = u, s0_2 = v
+        check(L.fqss_tcn_prep_fold(ptr(t["Wres"]), ptr(t["bres"]) or None, ptr(t["g2w"]), ptr(t["g2b"]), ptr(Q["Wc2"]),
+                                   ptr(Q["s1_2"]), ptr(Q["s0_2"]), Cio, Chid, Cio, 0, s))
+        Q["wdw"] = t["Wdw"].detach().contiguous()
+        out.append((t, dil, Q))
+    masker._fqss_float_prep = (key, out)
+    return out
+
+
+def tcn_noskip_infer(masker, h):
+    """The float block stack of the music MaskGenerator on the fused engine: h [B,Cio,M] -> [B,Cio,M]."""
+    N.require_cuda(h)
+    dev = h.device
+    L = E._libx()
+    s = stream_ptr()
+    bf = torch.bfloat16
+    with torch.no_grad():
+        P = _prepare_noskip(masker, dev)
+        B, Cio, M = h.shape
+        ld = (M + 7) // 8 * 8
+        x0 = E._as_pitched(h.detach(), ld)
+        x0 = x0 if x0.shape[-1] == ld else x0.as_strided((B, Cio, ld), (Cio * ld, ld, 1))
+        Chid = P[0][0]["W1"].shape[0]
+        y1 = torch.empty((B, Chid, ld), device=dev)
+        a4 = torch.empty((B, 2 * Chid, ld), dtype=bf, device=dev)
+        st1 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
+        st3 = torch.empty(2 * B + 1, dtype=torch.float64, device=dev)
+        rc1 = torch.empty(16 + 2 * B, device=dev)
+        rc3 = torch.empty(16 + 2 * B, device=dev)
+        xs = [x0, torch.empty((B, Cio, ld), device=dev), torch.empty((B, Cio, ld), device=dev)]
+        xops = [E.split_bf16_acts(x0[:, :, :M], ld), torch.empty((B, 2 * Cio, ld), dtype=bf, device=dev)]
+        cur_x, cur_op = 0, 0
+        for i, (t, dil, Q) in enumerate(P):
+            blk = E.TcnBlock()
+            blk.B, blk.M, blk.dil, blk.quant, blk.first_block, blk.has_res, blk.no_skip = B, M, dil, 0, int(i == 0), 1, 1
+            blk.Cio, blk.Chid, blk.split, blk.ld = Cio, Chid, 2, ld
+            for k in ("Wc1", "s1_1", "s0_1", "dws1", "Wc2", "s1_2", "s0_2", "dws2", "wdw"):
+                setattr(blk, k, ptr(Q[k]))
+            blk.bdw = ptr(t["bdw"]) or None
+            blk.slope1, blk.slope3 = ptr(t["slope1"]), ptr(t["slope3"])
+            blk.gn1_w, blk.gn1_b, blk.gn2_w, blk.gn2_b = ptr(t["g1w"]), ptr(t["g1b"]), ptr(t["g2w"]), ptr(t["g2b"])
+            blk.x_op, blk.x_in = ptr(xops[cur_op]), ptr(xs[cur_x])
+            blk.y1, blk.stats1, blk.y3, blk.stats3, blk.a4_op = ptr(y1), ptr(st1), None, ptr(st3), ptr(a4)
+            blk.rc1, blk.rc3 = ptr(rc1), ptr(rc3)
+            nxt_x = 1 if cur_x != 1 else 2
+            blk.x_out, blk.x_out_op = ptr(xs[nxt_x]), ptr(xops[1 - cur_op])
+            check(L.fqss_tcn_block_fwd(C.byref(blk), s))
+            cur_x, cur_op = nxt_x, 1 - cur_op
+        return xs[cur_x][:, :, :M]

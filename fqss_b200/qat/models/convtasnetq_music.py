@@ -106,6 +106,12 @@ class MaskGenerator(nn.Module):
             blocks = [b for rep in net[2] for b in rep]
             h, _ = E.fused_tcn(h, blocks, None, True, (q.min_range, q.max_range), start=0, total=len(blocks) + 1)
             return net[4](net[3](h)).reshape(M, self.C, N, K)
+        from ... import float_engine as FE
+        if self.use_fused and FE.noskip_eligible(self, mixture_w):
+            # the recipe's float teacher (same module tree, quantisation disabled) under no_grad: the block stack on the
+            # fused engine's float mode (split-bf16 GEMMs, second gLN folded into the residual conv, 3 kernels per block)
+            h = FE.tcn_noskip_infer(self, net[1](net[0](mixture_w)))
+            return net[4](net[3](h)).reshape(M, self.C, N, K)
         return net(mixture_w).reshape(M, self.C, N, K)
 
 
