@@ -146,7 +146,11 @@ class ConvTasNetMusicQ(nn.Module):
         Nf, K = masked.shape[-2], masked.shape[-1]
         dec = self.decoder
         if hasattr(dec, "forward_ncl"):                              # LinearDecoderQ: channels-first, [n, B*S, A*L, K]
-            out = dec.forward_ncl(masked.reshape(B * self.n_srcs, Nf, K))
+            dec_in = masked.reshape(B * self.n_srcs, Nf, K)
+            src = getattr(masked, "_fq_src", None)
+            if src is not None:
+                dec_in._fq_src = src                                 # still on the MulQ quantiser's grid: code-operand GEMMs
+            out = dec.forward_ncl(dec_in)
         else:                                                        # float nn.Linear: the reference's frame-major call
             out = dec(torch.transpose(masked, 2, 3)).transpose(2, 3).reshape(1, B * self.n_srcs, -1, K)
         out = ops.OverlapAdd.apply(out, self.audio_channels, out.shape[-2] // self.audio_channels, self.stride)

@@ -117,6 +117,18 @@ def _conv1d_q(layer, x):
     return _conv1d(x, layer.weight_fake_quantize(conv.weight), conv)
 
 
+def _linear_1x1(x, weight, wq):
+    """Per-frame Linear layer of the music model's decoder / RQB (qat_layers.py:1110-1121, 1256-1302) as a channels-first 1x1
+    conv: on the code-operand tcgen05 GEMM when `x` carries the tag of the steady 8-bit quantiser that produced it and the
+    weight quantiser is an 8-bit per-row one in steady state (40-row / 40-column shapes are zero-padded to the tiles,
+    tcn_engine.CodeConv1x1); the fp32 SIMT kernel on the materialised fake-quantised weight otherwise."""
+    from .. import tcn_engine as E
+    src = getattr(x, "_fq_src", None)
+    if TENSOR_CORE_CONV1X1 and src is not None and E.code_linear_eligible(weight, wq, src, x):
+        return E.CodeConv1x1.apply(x, src.min_range, src.max_range, weight, wq.min_range, wq.max_range, None)
+    return ops.Conv1x1.apply(x, wq(weight).unsqueeze(-1), None)
+
+
 def _conv_out_len(conv, L):
     return math.floor((L + 2 * conv.padding[0] - conv.dilation[0] * (conv.kernel_size[0] - 1) - 1) / conv.stride[0] + 1)
 
@@ -369,8 +381,10 @@ class ResidualErrorBlock(LayerQ):
     def forward(self, Y, y_q, w_decoder):
         if self.decoder_type is nn.Linear:
             # channels-first: Y [R, N, K] features, y_q [R, F, K] quantised decoder output; the Linear layers are 1x1 convs
-            Yq = ops.Conv1x1.apply(y_q, self.weight_fake_quantize(self.residual_encoder.weight).unsqueeze(-1), None)
+            Yq = _linear_1x1(y_q, self.residual_encoder.weight, self.weight_fake_quantize)
             Y1 = self._finish(N.PW_SUB, Y, Yq)
+            if isinstance(w_decoder, tuple):      # (raw weight, its quantiser): LinearDecoderQ hands both over
+                return _linear_1x1(Y1, w_decoder[0], w_decoder[1])
             return ops.Conv1x1.apply(Y1, w_decoder.unsqueeze(-1), None)
         Yq = self.reencode(y_q)
         Y1 = self._finish(N.PW_SUB, Y, Yq)
@@ -446,13 +460,18 @@ class LinearDecoderQ(LayerQ):
                                                       if out_quant else nn.Identity())
 
     def forward_ncl(self, x):
-        w_dec = self.weight_fake_quantize(self.linear.weight)
+        from .. import tcn_engine as E
+        src = getattr(x, "_fq_src", None)
+        tc = TENSOR_CORE_CONV1X1 and src is not None and E.code_linear_eligible(self.linear.weight, self.weight_fake_quantize, src, x)
+        # per-layer route: the weight quantiser is applied ONCE per forward and its output shared with the RQB, as in the
+        # reference (its observer counts calls); tensor-core route: raw weight + quantiser, the codes are derived in the GEMM prep
+        w_dec = (self.linear.weight, self.weight_fake_quantize) if tc else self.weight_fake_quantize(self.linear.weight)
         x_dec = x
         if self.n_combiner >= 2:      # x also feeds the residual block: sum the two gradients in the library
             x_dec, x = ops.fanout2(x)
-        y = self._finish(N.PW_IDENT, ops.Conv1x1.apply(x_dec, w_dec.unsqueeze(-1), None))
+        y = self._finish(N.PW_IDENT, _linear_1x1(x_dec, *w_dec) if tc else ops.Conv1x1.apply(x_dec, w_dec.unsqueeze(-1), None))
         if self.do_mac_op:
-            self.mac_op = x.numel() * w_dec.shape[0]
+            self.mac_op = x.numel() * self.linear.weight.shape[0]
         if self.n_combiner == 1:
             return y.unsqueeze(0)
         outs = [y]

@@ -290,7 +290,10 @@ def _as_pitched(x, ld):
 class CodeConv1x1(Function):
     """1x1 conv whose input is the output of an 8-bit activation quantiser and whose weight is fake-quantised per output
     channel (the bottleneck and mask convs, qat_layers.py:137-141, 202-207): both operands become integer codes on the
-    tcgen05 GEMM, exactly as inside the ConvBlocks.  Returns the pre-activation y = conv(x, FQ(W)) + bias (fp32)."""
+    tcgen05 GEMM, exactly as inside the ConvBlocks.  Returns the pre-activation y = conv(x, FQ(W)) + bias (fp32).
+    Channel counts the tiles do not cover (the music model's 40-row Linear decoder / RQB, convtasnetq_music.py:260) are
+    zero-padded to the next multiple of 128: a zero weight has code 0, so the padding adds exact
+    zeros to the integer sums."""
 
     @staticmethod
     def forward(ctx, x, qmin, qmax, W, wmin, wmax, bias):
@@ -298,22 +301,40 @@ class CodeConv1x1(Function):
         L = _libx()
         B, Ci, M = x.shape
         Co = W.shape[0]
+        Cip, Cop = (Ci + 127) // 128 * 128, (Co + 127) // 128 * 128      # Cip is also the dgrad GEMM's N
         ld = (M + 7) // 8 * 8
         dev = x.device
         s = stream_ptr()
         xv = _as_pitched(x.detach(), ld)
-        x_op = torch.empty((B, Ci, ld), dtype=torch.bfloat16, device=dev)
-        check(L.fqss_tcn_encode(ptr(xv), ld, ptr(x_op), ld, B * Ci, M, ptr(qmin), ptr(qmax), s))
-        Wf = W.detach().reshape(Co, Ci)
         bf = torch.bfloat16
-        Wc, WcT = torch.empty((Co, Ci), dtype=bf, device=dev), torch.empty((Ci, Co), dtype=bf, device=dev)
-        s1, s0, dws = torch.empty(Co, device=dev), torch.empty(Co, device=dev), torch.empty(Co, device=dev)
-        check(L.fqss_tcn_prep(ptr(Wf), ptr(wmin), ptr(wmax), ptr(bias) or None, ptr(qmin), ptr(qmax), ptr(Wc), ptr(WcT), ptr(s1),
-                              ptr(s0), ptr(dws), Co, Ci, Co, 0, 0, s))
+        if Cip == Ci:
+            x_op = torch.empty((B, Ci, ld), dtype=bf, device=dev)
+            check(L.fqss_tcn_encode(ptr(xv), ld, ptr(x_op), ld, B * Ci, M, ptr(qmin), ptr(qmax), s))
+        else:
+            tmp = torch.empty((B, Ci, ld), dtype=bf, device=dev)
+            check(L.fqss_tcn_encode(ptr(xv), ld, ptr(tmp), ld, B * Ci, M, ptr(qmin), ptr(qmax), s))
+            x_op = torch.zeros((B, Cip, ld), dtype=bf, device=dev)
+            x_op[:, :Ci, :M].copy_(tmp[:, :, :M])
+        Wf = W.detach().reshape(Co, Ci)
+        wmn, wmx, bs = wmin, wmax, bias
+        if (Cip, Cop) != (Ci, Co):
+            Wp = torch.zeros((Cop, Cip), device=dev)
+            Wp[:Co, :Ci].copy_(Wf)
+            Wf = Wp
+            wmn, wmx = torch.full((Cop,), -1.0, device=dev), torch.full((Cop,), 1.0, device=dev)
+            wmn[:Co].copy_(wmin.detach().reshape(-1))
+            wmx[:Co].copy_(wmax.detach().reshape(-1))
+            if bias is not None:
+                bs = torch.zeros(Cop, device=dev)
+                bs[:Co].copy_(bias.detach())
+        Wc, WcT = torch.empty((Cop, Cip), dtype=bf, device=dev), torch.empty((Cip, Cop), dtype=bf, device=dev)
+        s1, s0, dws = torch.empty(Cop, device=dev), torch.empty(Cop, device=dev), torch.empty(Cop, device=dev)
+        check(L.fqss_tcn_prep(ptr(Wf), ptr(wmn), ptr(wmx), ptr(bs) or None, ptr(qmin), ptr(qmax), ptr(Wc), ptr(WcT), ptr(s1),
+                              ptr(s0), ptr(dws), Cop, Cip, Cop, 0, 0, s))
         y = pw_gemm(x_op, Wc, s1, s0, M)
         ctx.save_for_backward(x_op, WcT, dws, W, wmin, wmax, qmin, qmax)
         ctx.meta = (B, Ci, Co, M, ld, bias is not None)
-        return y[:, :, :M]
+        return y[:, :Co, :M]
 
     @staticmethod
     @once_differentiable
@@ -321,19 +342,28 @@ class CodeConv1x1(Function):
         L = _libx()
         x_op, WcT, dws, W, wmin, wmax, qmin, qmax = ctx.saved_tensors
         B, Ci, Co, M, ld, has_bias = ctx.meta
+        Cip, Cop = (Ci + 127) // 128 * 128, (Co + 127) // 128 * 128      # Cip is also the dgrad GEMM's N
         dev = gy.device
         s = stream_ptr()
-        gy = _as_pitched(gy, ld)
-        dY = torch.empty((B, Co, ld), dtype=torch.bfloat16, device=dev)
-        db = torch.empty(Co, dtype=torch.float64, device=dev)
-        check(L.fqss_rowscale_bf16(ptr(gy), ld, ptr(dY), ld, B * Co, M, Co, ptr(dws), ptr(db), s))
+        if Cop == Co:
+            gy = _as_pitched(gy, ld)
+        else:
+            gp = torch.zeros((B, Cop, ld), device=dev)
+            gp[:, :Co, :M].copy_(gy)
+            gy = gp
+        dY = torch.empty((B, Cop, ld), dtype=torch.bfloat16, device=dev)
+        db = torch.empty(Cop, dtype=torch.float64, device=dev)
+        check(L.fqss_rowscale_bf16(ptr(gy), ld, ptr(dY), ld, B * Cop, M, Cop, ptr(dws), ptr(db), s))
         gx = None
         if ctx.needs_input_grad[0]:
-            gx = pw_gemm(dY, WcT, torch.ones(Ci, device=dev), torch.zeros(Ci, device=dev), M)[:, :, :M]
-        dWq = torch.empty((Co, Ci), device=dev)
-        ws = torch.empty(int(L.fqss_wgrad_codes_ws_bytes(B, M, Co, Ci)), dtype=torch.uint8, device=dev)
-        check(L.fqss_wgrad_codes(ptr(dY), ptr(x_op), B, M, ld, Co, Ci, ptr(qmin), ptr(qmax), ptr(dws), ptr(db), ptr(dWq), ptr(ws),
+            gx = pw_gemm(dY, WcT, torch.ones(Cip, device=dev), torch.zeros(Cip, device=dev), M)[:, :Ci, :M]
+        dWq = torch.empty((Cop, Cip), device=dev)
+        ws = torch.empty(int(L.fqss_wgrad_codes_ws_bytes(B, M, Cop, Cip)), dtype=torch.uint8, device=dev)
+        check(L.fqss_wgrad_codes(ptr(dY), ptr(x_op), B, M, ld, Cop, Cip, ptr(qmin), ptr(qmax), ptr(dws), ptr(db), ptr(dWq), ptr(ws),
                                  ws.numel(), s))
+        if (Cip, Cop) != (Ci, Co):
+            dWq = dWq[:Co, :Ci].contiguous()
+            db = db[:Co]
         gW = torch.empty_like(W, memory_format=torch.contiguous_format)
         gwmin, gwmax = torch.empty_like(wmin), torch.empty_like(wmax)
         check(lib().fqss_fq_weight_bwd(ptr(dWq), ptr(W), ptr(gW), ptr(gwmin), ptr(gwmax), 1, Co, Ci, ptr(wmin), ptr(wmax), 8, s))
@@ -353,8 +383,26 @@ def code_conv_eligible(layer, q_in, x):
         return False
     if not isinstance(q_in, AQ) or q_in.observing() or q_in.n_bits != 8:
         return False
-    return conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0 and conv.out_channels <= 1024 \
-        and W_contig(conv.weight)
+    # channel counts that are not tile multiples are zero-padded by CodeConv1x1; worth it only where the tensor is large
+    # enough for the SIMT kernel to hurt (the music model's 40-row decoder / RQB convs over 256 K frames)
+    aligned = conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0
+    padded = min(conv.in_channels, conv.out_channels) >= 32 and x.shape[0] * x.shape[2] >= (1 << 16)
+    return (aligned or padded) and conv.out_channels <= 1024 and W_contig(conv.weight)
+
+
+def code_linear_eligible(weight, wq, q_in, x):
+    """Same test as code_conv_eligible for a bare [out, in] weight with its quantiser (the music model's Linear decoder / RQB)."""
+    from .qat.qat_quant import GradientActivationFakeQuantize as AQ, GradientWeightFakeQuantize as WQm
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        return False
+    if not isinstance(wq, WQm) or wq.observer_mode or wq.n_bits != 8 or wq.min_range.numel() != weight.shape[0]:
+        return False
+    if not isinstance(q_in, AQ) or q_in.observing() or q_in.n_bits != 8:
+        return False
+    Co, Ci = weight.shape
+    aligned = Ci % 64 == 0 and Co % 128 == 0
+    padded = min(Ci, Co) >= 32 and x.shape[0] * x.shape[2] >= (1 << 16)
+    return (aligned or padded) and Co <= 1024 and weight.is_contiguous()
 
 
 def W_contig(w):
@@ -373,7 +421,8 @@ def float_conv_eligible(conv, x):
         return False
     if conv.kernel_size[0] != 1 or conv.stride[0] != 1 or conv.padding[0] != 0 or conv.groups != 1 or x.dtype != torch.float32:
         return False
-    return conv.in_channels % 64 == 0 and conv.out_channels % 128 == 0 and conv.out_channels <= 1024 and conv.weight.is_contiguous()
+    padded = conv.out_channels >= 32 and x.shape[0] * x.shape[2] >= (1 << 16)          # output rows zero-padded to 128 (float_conv)
+    return conv.in_channels % 64 == 0 and (conv.out_channels % 128 == 0 or padded) and conv.out_channels <= 1024 and conv.weight.is_contiguous()
 
 
 _FLOAT_W = {}
@@ -388,12 +437,20 @@ def float_conv(conv, x):
     ent = _FLOAT_W.get(id(conv))
     if ent is None or ent[0] != key:
         Co = w.shape[0]
-        ones = torch.ones(Co, device=w.device)
-        b = conv.bias.detach().clone() if conv.bias is not None else torch.zeros(Co, device=w.device)
-        ent = (key, split_bf16_weights(w), ones, b)
+        Cop = (Co + 127) // 128 * 128
+        wf = w.detach().reshape(Co, -1)
+        if Cop != Co:
+            wp = torch.zeros((Cop, wf.shape[1]), device=w.device)
+            wp[:Co].copy_(wf)
+            wf = wp
+        ones = torch.ones(Cop, device=w.device)
+        b = torch.zeros(Cop, device=w.device)
+        if conv.bias is not None:
+            b[:Co].copy_(conv.bias.detach())
+        ent = (key, split_bf16_weights(wf), ones, b)
         _FLOAT_W[id(conv)] = ent
     y = pw_gemm(split_bf16_acts(x.detach(), ld), ent[1], ent[2], ent[3], M)
-    return y[:, :, :M]
+    return y[:, :w.shape[0], :M]
 
 
 class MaskHead(Function):

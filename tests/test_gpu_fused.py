@@ -273,13 +273,15 @@ def test_float_teacher_engine_vs_torch_and_oracle():
     assert rel(got3, got) > 1e-4
 
 
-def test_code_conv1x1_vs_torch():
+@pytest.mark.parametrize("B,Ci,Co,M", [(3, 128, 256, 1003), (3, 256, 40, 1003), (2, 40, 256, 777), (2, 192, 72, 100)])
+def test_code_conv1x1_vs_torch(B, Ci, Co, M):
     """Bottleneck / mask 1x1 convs on integer-code operands (tcn_engine.CodeConv1x1) against the fp32 definition
-    conv1d(x, FQ_w(W)) + b with autograd through the weight quantiser (qat_quant.py:126-135)."""
+    conv1d(x, FQ_w(W)) + b with autograd through the weight quantiser (qat_quant.py:126-135); channel counts the GEMM tiles
+    do not cover (the music model's 40-row Linear decoder and its RQB re-encoder, convtasnetq_music.py:260) are zero-padded
+    inside the op."""
     import torch.nn.functional as F
     from fqss_b200 import tcn_engine as E
     torch.manual_seed(3)
-    B, Ci, Co, M = 3, 128, 256, 1003
     qmin, qmax = torch.tensor([-1.3], device=DEV), torch.tensor([2.1], device=DEV)
     delta = torch.div(qmax - qmin, torch.full_like(qmax, 255.0))
     codes = torch.randint(0, 256, (B, Ci, M), device=DEV).float()
