@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SASS opcode histogram of the hot kernels of libfqss_sm100.so (proof that the Blackwell path is what ships):
 UTCHMMA / UTCQMMA (tcgen05.mma), LDTM (tcgen05.ld), UTMALDG (TMA loads), UTCBAR (tcgen05.commit), SYNCS (mbarrier), ...
-usage: python profiles/sass_hist.py [lib.so] > profiles/sass_r02.txt"""
+usage: python profiles/sass_hist.py [lib.so] > profiles/sass_r03.txt"""
 import collections
 import re
 import subprocess
