@@ -600,6 +600,23 @@ def run_music(args):
             tot = sum(v["ms"] for v in prof.values())
             line["kernels"] = [{"kernel": k, "ms_per_step": round(v["ms"], 3), "launches_per_step": v["kernels"],
                                 "share": round(v["ms"] / tot, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:10]]
+            # HBM fraction of the fused row kernels at this workload's geometry (M = 7 999 frames, dilation <= 512: the row
+            # plus its halo takes 38-42 KB of shared memory per CTA).  The byte formulas of the hidden-width kernels are those
+            # of the speech blocks (roofline.algorithmic_bytes); the skip-less tail kernel moves the residual branch only.
+            if not args.small:
+                sep = model.separator.network
+                Cio, Chid = sep[1].conv1d.out_channels, sep[2][0][0].net[0].conv1d.out_channels
+                Mf = (Tm - model.kernel) // model.stride + 1
+                table = R.algorithmic_bytes(B, Mf, Cio, Chid)
+                table["tcn_tail_bwd"] = 4 * B * Cio * Mf * 3 + 4 * B * Cio * Mf + 2 * B * Cio * Mf      # g_x, res_y, x_in -> g_xd, dY2
+                peak, how = R.measured_peaks()
+                rows = {}
+                for k in ("tcn_gln2_dw_bwd", "tcn_tail_bwd", "tcn_gln1_bwd", "tcn_dw_fwd", "tcn_dw_fwd(float)", "tcn_gln2_sums", "tcn_hidden_fq"):
+                    v = prof.get(k)
+                    if v and v["scopes"]:
+                        us = v["ms"] / v["scopes"] * 1e3
+                        rows[k] = {"avg_launch_us": round(us, 1), "frac": round(table[k] / (us * 1e-6) / 1e9 / peak, 3)}
+                line["row_kernel_hbm_frac"] = {"peak_gbs": peak, "peak_source": how, "frames": Mf, "kernels": rows}
         except Exception as e:
             line["kernels"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
