@@ -624,8 +624,12 @@ int fqss_tcn_block_fwd(const fqss_tcn_block* p, void* stream) {
 #undef FQSS_DW_ATTR
             cfg = true;
         }
-        static const int th_q = getenv("FQSS_DWF_TH") ? atoi(getenv("FQSS_DWF_TH")) : 128;
-        static const int th_f = getenv("FQSS_DWFF_TH") ? atoi(getenv("FQSS_DWFF_TH")) : 128;
+        // CTA width: 128 threads for the speech rows (M = 3 999: measured 80 vs 87 us quantised, 98 vs 132 us float), 256 for
+        // long rows (music, M = 7 999: 49.3 vs 51.8 us, 57.4 vs 59.5 us); FQSS_DWF_TH / FQSS_DWFF_TH override
+        static const int env_q = getenv("FQSS_DWF_TH") ? atoi(getenv("FQSS_DWF_TH")) : 0;
+        static const int env_f = getenv("FQSS_DWFF_TH") ? atoi(getenv("FQSS_DWFF_TH")) : 0;
+        const int th_q = env_q ? env_q : (p->M > 6000 ? 256 : 128);
+        const int th_f = env_f ? env_f : (p->M > 6000 ? 256 : 128);
 #define FQSS_DW_LAUNCH(Q, D)                                                                                   \
     do {                                                                                                       \
         FQSS_PROF(Q ? "tcn_dw_fwd" : "tcn_dw_fwd(float)", s);                                                  \
