@@ -37,6 +37,9 @@ struct TailQ {
     ActQF qres, qskip, qadd, qadds;
 };
 
+// HAS_SKIP = false: skip-less block (fqss_tcn_block.no_skip) -- the residual branch alone moves half the bytes per trip, so
+// NQ = 2 frame quads are requested before the first is consumed (bytes in flight per SM decide: 80 -> 56 us at M = 7 999)
+template <bool HAS_SKIP, int NQ>
 __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tcn_block p, const fqss_tcn_block_grads g, double* acc) {
     __shared__ double sh[10 * 32];
     __shared__ TailQ tq;
@@ -44,7 +47,7 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
     const int64_t r = blockIdx.x;
     const int b = (int)(r / p.Cio), o = (int)(r % p.Cio);
     const int M = p.M;
-    const bool has_skip = !p.no_skip;
+    constexpr bool has_skip = HAS_SKIP;
     const int n2 = (p.has_res ? p.Cio : 0) + (has_skip ? p.Cio : 0);
     if (p.quant && threadIdx.x == 0) {
         if (has_skip) tq.qskip = load_actqf(p.qskip.rmin, p.qskip.rmax, 8);
@@ -66,21 +69,27 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
     for (int i = 0; i < 10; ++i) s[i] = 0.f;      // 0,1 qadd | 2,3 qres | 4,5 qadds | 6,7 qskip | 8 db_res | 9 db_skip
     const int nvec = (int)(p.ld >> 2);
     const int64_t rb = r * p.ld;
-    for (int v = threadIdx.x; v < nvec; v += ROW_THREADS) {
-        const int m0 = 4 * v;
-        const int64_t i = rb + m0;
-        float4 gxo, ry, xin, gso, sy, sin;
-        // issue every load of this trip before the first use
+    struct TailLd { float4 gxo, ry, xin, gso, sy, sin; };
+    // issue every load of a trip before the first use
+    auto load = [&](int v) {
+        TailLd t;
+        const int64_t i = rb + 4 * v;
         if (p.has_res) {
-            gxo = ld_f4(g.g_x_out + i);
-            ry = ldg4_stream(p.res_y + i);
-            if (p.quant) xin = ldg4_stream(p.x_in + i);
+            t.gxo = ld_f4(g.g_x_out + i);
+            t.ry = ldg4_stream(p.res_y + i);
+            if (p.quant) t.xin = ldg4_stream(p.x_in + i);
         }
         if (has_skip) {
-            gso = ld_f4(g.g_skip_out + i);
-            sy = ldg4_stream(p.skip_y + i);
-            if (p.quant && !p.first_block) sin = ldg4_stream(p.skip_in + i);
+            t.gso = ld_f4(g.g_skip_out + i);
+            t.sy = ldg4_stream(p.skip_y + i);
+            if (p.quant && !p.first_block) t.sin = ldg4_stream(p.skip_in + i);
         }
+        return t;
+    };
+    auto body = [&](int v, const TailLd& t) {
+        const int m0 = 4 * v;
+        const int64_t i = rb + m0;
+        const float4 gxo = t.gxo, ry = t.ry, xin = t.xin, gso = t.gso, sy = t.sy, sin = t.sin;
         if (p.has_res) {
             float gz[4], gr[4];
 #pragma unroll
@@ -124,6 +133,15 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_tail_bwd_kernel(const fqss_tc
             if (!p.first_block) stg4(g.g_skip_in + i, make_float4(gz[0], gz[1], gz[2], gz[3]));
             st_bf16x4(dskip + m0, gs[0] * sc_skip, gs[1] * sc_skip, gs[2] * sc_skip, gs[3] * sc_skip);
         }
+    };
+    for (int base = threadIdx.x; base < nvec; base += NQ * ROW_THREADS) {
+        TailLd d[NQ];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+            if (base + k * ROW_THREADS < nvec) d[k] = load(base + k * ROW_THREADS);
+#pragma unroll
+        for (int k = 0; k < NQ; ++k)
+            if (base + k * ROW_THREADS < nvec) body(base + k * ROW_THREADS, d[k]);
     }
     double v[10];
     block_sum_fd<10>(s, v, sh);
@@ -932,7 +950,11 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
 
     cudaMemsetAsync(acc, 0, (size_t)L.total * sizeof(double), s);
     // T
-    { FQSS_PROF("tcn_tail_bwd", s); tcn_tail_bwd_kernel<<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc); }
+    {
+        FQSS_PROF("tcn_tail_bwd", s);
+        if (p->no_skip) tcn_tail_bwd_kernel<false, 2><<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc);
+        else tcn_tail_bwd_kernel<true, 1><<<rows_io, ROW_THREADS, 0, s>>>(*p, *g, acc);
+    }
     rc = check_launch("tcn_block_bwd(tail)");
     if (rc) return rc;
     // G: g_a4 = Wc2T-GEMM(dY2)   (K = n2, N = Chid) -> bf16
