@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(NTH) tcn_dw_fwd_kernel(const fqss_tcn_block p)
     }
     __syncthreads();
     const float2 w0 = f2s(__ldg(p.wdw + c * 3)), w1 = f2s(__ldg(p.wdw + c * 3 + 1)), w2 = f2s(__ldg(p.wdw + c * 3 + 2));
-    const float2 bias = f2s(p.bdw ? __ldg(p.bdw + c) : 0.f);
+    const float2 bias = f2s(__ldg(p.bdw + c));
     const float slope3 = __ldg(p.slope3);
     ActQF q3;
     if (QUANT) q3 = load_actqf_rc(p.rc1 + 8);
@@ -494,7 +494,7 @@ static int validate_block(const fqss_tcn_block* p, const char* who) {
     FQSS_REQUIRE(p->ld >= p->M && p->ld % 8 == 0, -2, "%s: ld must be >= M and a multiple of 8", who);
     FQSS_REQUIRE(((size_t)p->ld * 2 + 4 * (size_t)((p->dil + 3) & ~3) + 1280) * sizeof(float) + (size_t)p->ld <= 200 * 1024, -1,
                  "%s: row too long for shared-memory staging (M=%d, dil=%d)", who, p->M, p->dil);
-    FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw, -1, "%s: block not prepared", who);
+    FQSS_REQUIRE(p->Wc1 && p->Wc2 && p->s1_1 && p->s0_1 && p->s1_2 && p->s0_2 && p->wdw && p->bdw, -1, "%s: block not prepared", who);
     FQSS_REQUIRE(p->no_skip == 0 || (p->no_skip == 1 && p->has_res), -1, "%s: no_skip must be 0 or 1, and a skip-less block needs the residual path", who);
     FQSS_REQUIRE(p->slope1 && p->slope3 && p->gn1_w && p->gn1_b && p->gn2_w && p->gn2_b, -1, "%s: missing layer parameters", who);
     FQSS_REQUIRE(p->x_op && p->x_in && (p->y1 || p->quant) && (p->y3 || p->split == 2 || p->quant) && p->stats1 && p->stats3 && p->a4_op && (p->skip_out || p->no_skip) && p->rc1 && p->rc3, -1,

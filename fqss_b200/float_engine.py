@@ -267,7 +267,7 @@ def tcn_noskip_infer(masker, h):
             blk.Cio, blk.Chid, blk.split, blk.ld = Cio, Chid, 2, ld
             for k in ("Wc1", "s1_1", "s0_1", "dws1", "Wc2", "s1_2", "s0_2", "dws2", "wdw"):
                 setattr(blk, k, ptr(Q[k]))
-            blk.bdw = ptr(t["bdw"]) or None
+            blk.bdw = ptr(t["bdw"]) if t["bdw"] is not None else ptr(E.zero_bias(Chid, dev))
             blk.slope1, blk.slope3 = ptr(t["slope1"]), ptr(t["slope3"])
             blk.gn1_w, blk.gn1_b, blk.gn2_w, blk.gn2_b = ptr(t["g1w"]), ptr(t["g1b"]), ptr(t["g2w"]), ptr(t["g2b"])
             blk.x_op, blk.x_in = ptr(xops[cur_op]), ptr(xs[cur_x])

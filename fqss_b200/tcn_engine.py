@@ -115,6 +115,19 @@ _BLOCK_SLOTS = ("W1", "b1", "w1min", "w1max", "slope1", "q1min", "q1max", "g1w",
                 "qskipmin", "qskipmax", "qaddmin", "qaddmax", "qaddsmin", "qaddsmax")
 
 
+_ZERO_BIAS = {}
+
+
+def zero_bias(n, dev):
+    """Zero vector standing in for the bias of a bias-free depthwise conv (the music model's): the row kernels read bdw
+    unconditionally (a NULL test in the kernel cost the speech model's float kernel 2 us per launch)."""
+    key = (n, dev)
+    z = _ZERO_BIAS.get(key)
+    if z is None:
+        z = _ZERO_BIAS[key] = torch.zeros(n, device=dev)
+    return z
+
+
 def _aq(mod):
     q = getattr(mod, "activation_fake_quantize", None)
     if q is None or isinstance(q, torch.nn.Identity):
@@ -245,7 +258,7 @@ def _fill_block(blk, t, P, quant, first, has_res, dil, B, M, ld, q_in):
     blk.no_skip = int(t["Wskip"] is None)
     for k in ("Wc1", "Wc1T", "s1_1", "s0_1", "dws1", "Wc2", "Wc2T", "s1_2", "s0_2", "dws2", "wdw"):
         setattr(blk, k, ptr(P[k]))
-    blk.bdw = ptr(t["bdw"]) or None
+    blk.bdw = ptr(t["bdw"]) if t["bdw"] is not None else ptr(zero_bias(t["W1"].shape[0], t["W1"].device))
     blk.slope1, blk.slope3 = ptr(t["slope1"]), ptr(t["slope3"])
     blk.gn1_w, blk.gn1_b, blk.gn2_w, blk.gn2_b = ptr(t["g1w"]), ptr(t["g1b"]), ptr(t["g2w"]), ptr(t["g2b"])
 

@@ -232,8 +232,8 @@ typedef struct fqss_tcn_block {
     int32_t no_skip; /* 1: the block has no skip conv and no skip sum (ConvTasNetMusicQ, convtasnetq_music.py:141-199: 1x1 -> PReLU ->
                         gLN -> depthwise -> PReLU -> gLN -> 1x1, plus the residual): the second GEMM is the residual conv alone
                         (Wc2 [Cio][Chid]); needs has_res = 1; skip_in / skip_y / skip_out / qskip / qadds and, in backward,
-                        g_skip_out / g_skip_in are ignored (may be NULL); dY2 is [B][Cio][ld], dW2q [Cio][Chid].  bdw may be
-                        NULL (bias-free depthwise conv) in either mode                                                 */
+                        g_skip_out / g_skip_in are ignored (may be NULL); dY2 is [B][Cio][ld], dW2q [Cio][Chid].  A bias-free
+                        depthwise conv passes a zero vector as bdw                                                     */
     int64_t ld;
     /* prepared by fqss_tcn_prep (per step) */
     const void* Wc1;  const void* Wc1T; const float* s1_1; const float* s0_1; const float* dws1;   /* expand [Chid,Cio] */
