@@ -20,6 +20,8 @@
 
 #include "fqss_common.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
+
 #include "gemm_tc.cuh"
 #include "tcn_common.cuh"
 
@@ -39,6 +41,10 @@ constexpr int EPI_WARPS = 16;      // 4 per TMEM lane quarter: the fused tails a
 constexpr int NUM_THREADS = 128 + EPI_WARPS * 32;
 constexpr int MAXN = 1024;
 constexpr int STAT_MAXB = 256;     // samples whose gLN statistics are accumulated in shared memory (EPI_EXPAND)
+constexpr int STAT_PRIVB = 64;     // up to this many samples every epilogue warp owns a PRIVATE row of the accumulators: plain
+                                   // read-modify-write instead of fp64 shared-memory atomics, which are CAS loops and, with the 16
+                                   // warps of a CTA finishing the same tile together, took ~10 % of the expand GEMM's stall samples
+constexpr int STAT_SMEM = (2 * STAT_MAXB > EPI_WARPS * 2 * STAT_PRIVB ? 2 * STAT_MAXB : EPI_WARPS * 2 * STAT_PRIVB) * 8;
 
 struct __align__(8) Barriers {
     uint64_t full[STAGES];
@@ -52,7 +58,7 @@ template <int NT>
 __host__ __device__ constexpr int stage_bytes() { return A_STAGE_BYTES + NT * BK * 2; }
 
 template <int NT>
-__host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<NT>() + 2 * MAXN * 4 + (int)sizeof(Barriers) + 2 * STAT_MAXB * 8 + 1024; }
+__host__ __device__ constexpr int smem_bytes() { return STAGES * stage_bytes<NT>() + 2 * MAXN * 4 + (int)sizeof(Barriers) + STAT_SMEM + 1024; }
 
 __device__ __forceinline__ float prelu(float y, float a) { return y > 0.f ? y : a * y; }
 
@@ -70,8 +76,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float* s0s = s1s + MAXN;
     Barriers* bar = reinterpret_cast<Barriers*>(s0s + MAXN);
     double* stat_sm = (EPI == EPI_EXPAND && p.B <= STAT_MAXB) ? reinterpret_cast<double*>(bar + 1) : nullptr;
+    const bool stat_priv = stat_sm && p.B <= STAT_PRIVB;
     if (stat_sm) {
-        for (int i = threadIdx.x; i < 2 * p.B; i += NUM_THREADS) stat_sm[i] = 0.0;
+        for (int i = threadIdx.x; i < 2 * p.B * (stat_priv ? EPI_WARPS : 1); i += NUM_THREADS) stat_sm[i] = 0.0;
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -329,47 +336,86 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (is_res) {                               // residual conv -> FQ -> (x + res) -> FQ
                         float* ry = p.res_y ? p.res_y + i0 : nullptr;
                         float* xo = p.x_out + i0;
+                        // CTA-uniform switches resolved once per chunk (see the skip branch below)
+                        using T = std::true_type;
+                        using F = std::false_type;
+                        const bool save = ry != nullptr;
                         if (p.quant) {
                             __nv_bfloat16* xop = p.x_out_op + i0;
+                            auto cols = [&](auto save_tag) {
+                                constexpr bool SAVE = decltype(save_tag)::value;
 #pragma unroll
-                            for (int j = 0; j < CW; ++j) {
-                                const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                if (ry) ry[j * ld] = y;
-                                const float z = __fadd_rn(pre[j], actqf_fq(qres, y));
-                                const float c = actqf_code(qadd, z);
-                                xo[j * ld] = actqf_decode(qadd, c);
-                                xop[j * ld] = __float2bfloat16_rn(c);
-                            }
+                                for (int j = 0; j < CW; ++j) {
+                                    const float y = fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                    if (SAVE) ry[j * ld] = y;
+                                    const float z = __fadd_rn(pre[j], actqf_fq(qres, y));
+                                    const float c = actqf_code(qadd, z);
+                                    xo[j * ld] = actqf_decode(qadd, c);
+                                    xop[j * ld] = __float2bfloat16_rn(c);
+                                }
+                            };
+                            if (save) cols(T{}); else cols(F{});
                         } else {
                             __nv_bfloat16* xop = p.x_out_op + (p.split ? ((int64_t)b * 2 * p.n_res + o0) * ld + m : i0);
                             const int64_t lo_off = (int64_t)p.n_res * ld;
+                            auto cols = [&](auto save_tag, auto fold_tag, auto split_tag) {
+                                constexpr bool SAVE = decltype(save_tag)::value, FOLD = decltype(fold_tag)::value, SPLIT = decltype(split_tag)::value;
 #pragma unroll
-                            for (int j = 0; j < CW; ++j) {
-                                const float y = p.fold_stats ? fmaf(__uint_as_float(v[j]), fold_rstd, fmaf(fold_nrm, s1c[j], s0c[j]))
-                                                             : fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                                if (ry) ry[j * ld] = y;
-                                const float z = __fadd_rn(pre[j], y);
-                                xo[j * ld] = z;
-                                const __nv_bfloat16 hi = __float2bfloat16_rn(z);
-                                xop[j * ld] = hi;
-                                if (p.split) xop[j * ld + lo_off] = __float2bfloat16_rn(z - __bfloat162float(hi));
+                                for (int j = 0; j < CW; ++j) {
+                                    const float y = FOLD ? fmaf(__uint_as_float(v[j]), fold_rstd, fmaf(fold_nrm, s1c[j], s0c[j]))
+                                                         : fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                    if (SAVE) ry[j * ld] = y;
+                                    const float z = __fadd_rn(pre[j], y);
+                                    xo[j * ld] = z;
+                                    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
+                                    xop[j * ld] = hi;
+                                    if (SPLIT) xop[j * ld + lo_off] = __float2bfloat16_rn(z - __bfloat162float(hi));
+                                }
+                            };
+                            const bool fold = p.fold_stats != nullptr, split = p.split != 0;
+                            if (save) {
+                                if (fold) { if (split) cols(T{}, T{}, T{}); else cols(T{}, T{}, F{}); }
+                                else { if (split) cols(T{}, F{}, T{}); else cols(T{}, F{}, F{}); }
+                            } else {
+                                if (fold) { if (split) cols(F{}, T{}, T{}); else cols(F{}, T{}, F{}); }
+                                else { if (split) cols(F{}, F{}, T{}); else cols(F{}, F{}, F{}); }
                             }
                         }
                     } else {                                    // skip conv -> FQ -> (skip_sum + skip) -> FQ
                         float* sy = p.skip_y ? p.skip_y + i0 : nullptr;
                         float* so = p.skip_out + i0;
+                        // The CTA-uniform switches are resolved ONCE per chunk, outside the column loop: with them inside, every
+                        // column was its own basic block (three uniform branches per element in the SASS) and the quantiser chains
+                        // of the CW columns -- division, conversion, FMA, each a ~20-cycle dependent chain -- could not overlap
+                        auto cols = [&](auto q_tag, auto first_tag, auto save_tag, auto fold_tag) {
+                            constexpr bool Q = decltype(q_tag)::value, FIRST = decltype(first_tag)::value;
+                            constexpr bool SAVE = decltype(save_tag)::value, FOLD = decltype(fold_tag)::value;
 #pragma unroll
-                        for (int j = 0; j < CW; ++j) {
-                            const float y = (!p.quant && p.fold_stats) ? fmaf(__uint_as_float(v[j]), fold_rstd, fmaf(fold_nrm, s1c[j], s0c[j]))
-                                                                       : fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
-                            if (sy) sy[j * ld] = y;
-                            const float sk = p.quant ? actqf_fq(qskip, y) : y;
-                            if (p.first_block) {
-                                so[j * ld] = sk;
-                            } else {
-                                const float z = __fadd_rn(pre[j], sk);
-                                so[j * ld] = p.quant ? actqf_fq(qadds, z) : z;
+                            for (int j = 0; j < CW; ++j) {
+                                const float y = FOLD ? fmaf(__uint_as_float(v[j]), fold_rstd, fmaf(fold_nrm, s1c[j], s0c[j]))
+                                                     : fmaf(__uint_as_float(v[j]), s1c[j], s0c[j]);
+                                if (SAVE) sy[j * ld] = y;
+                                const float sk = Q ? actqf_fq(qskip, y) : y;
+                                if (FIRST) {
+                                    so[j * ld] = sk;
+                                } else {
+                                    const float z = __fadd_rn(pre[j], sk);
+                                    so[j * ld] = Q ? actqf_fq(qadds, z) : z;
+                                }
                             }
+                        };
+                        using T = std::true_type;
+                        using F = std::false_type;
+                        const bool save = sy != nullptr;
+                        if (p.quant) {
+                            if (p.first_block) { if (save) cols(T{}, T{}, T{}, F{}); else cols(T{}, T{}, F{}, F{}); }
+                            else { if (save) cols(T{}, F{}, T{}, F{}); else cols(T{}, F{}, F{}, F{}); }
+                        } else if (p.fold_stats) {
+                            if (p.first_block) { if (save) cols(F{}, T{}, T{}, T{}); else cols(F{}, T{}, F{}, T{}); }
+                            else { if (save) cols(F{}, F{}, T{}, T{}); else cols(F{}, F{}, F{}, T{}); }
+                        } else {
+                            if (p.first_block) { if (save) cols(F{}, T{}, T{}, F{}); else cols(F{}, T{}, F{}, F{}); }
+                            else { if (save) cols(F{}, F{}, T{}, F{}); else cols(F{}, F{}, F{}, F{}); }
                         }
                     }
                 }
@@ -411,7 +457,11 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     dss = (double)warp_sum(st_ss);
                 }
                 if (lane == 0) {
-                    if (stat_sm) {
+                    if (stat_priv) {
+                        double* row = stat_sm + (warp - 4) * 2 * p.B + 2 * b;
+                        row[0] += ds;
+                        row[1] += dss;
+                    } else if (stat_sm) {
                         atomicAdd(stat_sm + 2 * b, ds);
                         atomicAdd(stat_sm + 2 * b + 1, dss);
                     } else {
@@ -429,7 +479,9 @@ pw_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // one pair of global atomics per (CTA, sample) instead of one per (warp, tile): the per-sample accumulators
         // are otherwise hit by every epilogue warp of every CTA working on the same sample at the same time
         for (int i = threadIdx.x; i < 2 * p.B; i += NUM_THREADS) {
-            const double v = stat_sm[i];
+            double v = stat_sm[i];
+            if (stat_priv)
+                for (int w = 1; w < EPI_WARPS; ++w) v += stat_sm[w * 2 * p.B + i];      // fixed order
             if (v != 0.0) atomicAdd(p.stats + i, v);
         }
     }
