@@ -599,7 +599,7 @@ def run_music(args):
             prof = R.profile(lambda: step(*dev_batches[0]), 1)
             tot = sum(v["ms"] for v in prof.values())
             line["kernels"] = [{"kernel": k, "ms_per_step": round(v["ms"], 3), "launches_per_step": v["kernels"],
-                                "share": round(v["ms"] / tot, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:10]]
+                                "share": round(v["ms"] / tot, 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:int(os.environ.get("FQSS_BENCH_TOPK", "10"))]]
             # HBM fraction of the fused row kernels at this workload's geometry (M = 7 999 frames, dilation <= 512: the row
             # plus its halo takes 38-42 KB of shared memory per CTA).  The byte formulas of the hidden-width kernels are those
             # of the speech blocks (roofline.algorithmic_bytes); the skip-less tail kernel moves the residual branch only.

@@ -105,6 +105,7 @@ class MaskGenerator(nn.Module):
             q = net[1].activation_fake_quantize
             blocks = [b for rep in net[2] for b in rep]
             h, _ = E.fused_tcn(h, blocks, None, True, (q.min_range, q.max_range), start=0, total=len(blocks) + 1)
+            h._fq_src = blocks[-1].add.activation_fake_quantize      # on the last AddQ's grid: the mask conv runs on code operands
             return net[4](net[3](h)).reshape(M, self.C, N, K)
         from ... import float_engine as FE
         if self.use_fused and FE.noskip_eligible(self, mixture_w):

@@ -126,6 +126,8 @@ def _linear_1x1(x, weight, wq):
     src = getattr(x, "_fq_src", None)
     if TENSOR_CORE_CONV1X1 and src is not None and E.code_linear_eligible(weight, wq, src, x):
         return E.CodeConv1x1.apply(x, src.min_range, src.max_range, weight, wq.min_range, wq.max_range, None)
+    if TENSOR_CORE_CONV1X1 and isinstance(wq, nn.Identity) and E.float_linear_eligible(weight, x):
+        return E.float_linear(weight, x)          # un-quantised teacher under no_grad: split-bf16 GEMM (fp32-grade)
     return ops.Conv1x1.apply(x, wq(weight).unsqueeze(-1), None)
 
 
@@ -469,7 +471,11 @@ class LinearDecoderQ(LayerQ):
         x_dec = x
         if self.n_combiner >= 2:      # x also feeds the residual block: sum the two gradients in the library
             x_dec, x = ops.fanout2(x)
-        y = self._finish(N.PW_IDENT, _linear_1x1(x_dec, *w_dec) if tc else ops.Conv1x1.apply(x_dec, w_dec.unsqueeze(-1), None))
+        if tc or isinstance(self.weight_fake_quantize, nn.Identity):
+            y_lin = _linear_1x1(x_dec, self.linear.weight, self.weight_fake_quantize)
+        else:
+            y_lin = ops.Conv1x1.apply(x_dec, w_dec.unsqueeze(-1), None)
+        y = self._finish(N.PW_IDENT, y_lin)
         if self.do_mac_op:
             self.mac_op = x.numel() * self.linear.weight.shape[0]
         if self.n_combiner == 1:

@@ -466,6 +466,35 @@ def float_conv(conv, x):
     return y[:, :w.shape[0], :M]
 
 
+def float_linear_eligible(weight, x):
+    """Un-quantised per-frame Linear layer as a channels-first 1x1 conv, forward only (the music teacher's decoder)."""
+    if torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad):
+        return False
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 3 or weight.dim() != 2 or x.shape[1] != weight.shape[1]:
+        return False
+    Co, Ci = weight.shape
+    padded = Co >= 32 and x.shape[0] * x.shape[2] >= (1 << 16)
+    return Ci % 64 == 0 and (Co % 128 == 0 or padded) and Co <= 1024 and weight.is_contiguous()
+
+
+class _BareConv:
+    """Adapter: float_conv() keys its split-weight cache on a module with .weight / .bias."""
+    __slots__ = ("weight", "bias")
+
+    def __init__(self, weight):
+        self.weight, self.bias = weight, None
+
+
+_BARE = {}
+
+
+def float_linear(weight, x):
+    ent = _BARE.get(id(weight))
+    if ent is None or ent.weight is not weight:
+        ent = _BARE[id(weight)] = _BareConv(weight)
+    return float_conv(ent, x)
+
+
 class MaskHead(Function):
     """Mask head of the quantised separator (convtasnetq.py:97-99, :203): 1x1 conv bn -> S*F on integer-code operands, ReLU +
     FQ_m and `* feats` + FQ_p in the GEMM epilogue (fqss_mask_head_fwd); backward of the whole elementwise tail in one pass
