@@ -395,6 +395,49 @@ __global__ void __launch_bounds__(256) sconv_gw_kernel(const float* __restrict__
     }
 }
 
+// Tiled variant for geometries the kernel-16 / hop-8 kernels of conv_edge.cu do not cover (the music encoder: Cin = 4,
+// K = 20, hop 10): one CTA = GW_OT output channels x all Cin*K taps over GW_MF frames.  The input span of the chunk (all
+// channels) and the GW_OT gradient rows are staged in shared memory once; thread (tap j, group q) owns the sums of tap j
+// for GW_OT / 4 output channels over the whole chunk -- no cross-thread reduction, one fp64 atomic per sum.  Per frame and
+// thread: one LDS of x (consecutive taps -> consecutive banks) and GW_OT / 4 broadcast LDS of gy.
+constexpr int GW_OT = 8, GW_MF = 256;
+
+__global__ void __launch_bounds__(4 * SC_MAXCK) sconv_gw_tile_kernel(const float* __restrict__ gy, int64_t ldgy, const float* __restrict__ x,
+                                                                     int64_t ldx, int T, int Cin, int Co, int Mo, int K, int stride,
+                                                                     double* __restrict__ acc) {
+    extern __shared__ float gsm[];                     // [Cin][span] input, then [GW_OT][GW_MF] gradient
+    const int b = blockIdx.z, o0 = blockIdx.y * GW_OT, m0 = blockIdx.x * GW_MF;
+    const int CK = Cin * K, nm = min(GW_MF, Mo - m0);
+    const int span = (GW_MF - 1) * stride + K;
+    float* xs = gsm;
+    float* gs = gsm + (size_t)Cin * span;
+    const int64_t t0 = (int64_t)m0 * stride;
+    for (int i = threadIdx.x; i < Cin * span; i += blockDim.x) {
+        const int c = i / span, t = i - c * span;
+        xs[i] = (t0 + t < T) ? __ldg(x + ((int64_t)b * Cin + c) * ldx + t0 + t) : 0.f;
+    }
+    for (int i = threadIdx.x; i < GW_OT * GW_MF; i += blockDim.x) {
+        const int o = i / GW_MF, m = i - o * GW_MF;
+        gs[i] = (o0 + o < Co && m < nm) ? __ldg(gy + ((int64_t)b * Co + o0 + o) * ldgy + m0 + m) : 0.f;
+    }
+    __syncthreads();
+    const int j = threadIdx.x % CK, q = threadIdx.x / CK;          // blockDim.x == 4 * CK
+    const int c = j / K, k = j - c * K;
+    const float* xr = xs + (size_t)c * span + k;
+    const float* g0 = gs + (size_t)(2 * q) * GW_MF;
+    const float* g1 = g0 + GW_MF;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 4
+    for (int m = 0; m < GW_MF; ++m) {                               // frames beyond nm carry zero gradient
+        const float xv = xr[m * stride];
+        s0 = fmaf(g0[m], xv, s0);
+        s1 = fmaf(g1[m], xv, s1);
+    }
+    const int oa = o0 + 2 * q, ob = oa + 1;
+    if (oa < Co) atomicAdd(acc + (int64_t)oa * CK + j, (double)s0);
+    if (ob < Co) atomicAdd(acc + (int64_t)ob * CK + j, (double)s1);
+}
+
 }  // namespace fqss
 
 using namespace fqss;
@@ -509,8 +552,17 @@ int fqss_sconv_bwd(const float* gy, int64_t ldgy, const float* x, int64_t ldx, c
         FQSS_PROFN("sconv_bwd(dw: edge_wgrad)", s, 2);
         cudaMemsetAsync(ws, 0, need, s);
         if (!(edge_geometry_ok(K, stride) && edge_wgrad(gy, ldgy, x, ldx, T, B, Cin, Co, Mo, (double*)ws, s) == 0)) {
-            dim3 grid((Mo + 1023) / 1024, Co, B);
-            sconv_gw_kernel<<<grid, 256, 0, s>>>(gy, ldgy, x, ldx, Cin, Co, Mo, K, stride, (double*)ws);
+            const int CK = Cin * K;
+            const size_t smem = ((size_t)Cin * ((GW_MF - 1) * stride + K) + (size_t)GW_OT * GW_MF) * sizeof(float);
+            if (CK <= SC_MAXCK && smem <= 160 * 1024 && (int64_t)B * Mo >= 4096) {
+                static bool cfg = false;
+                if (!cfg) { cudaFuncSetAttribute(sconv_gw_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); cfg = true; }
+                dim3 grid((Mo + GW_MF - 1) / GW_MF, (Co + GW_OT - 1) / GW_OT, B);
+                sconv_gw_tile_kernel<<<grid, 4 * CK, smem, s>>>(gy, ldgy, x, ldx, T, Cin, Co, Mo, K, stride, (double*)ws);
+            } else {
+                dim3 grid((Mo + 1023) / 1024, Co, B);
+                sconv_gw_kernel<<<grid, 256, 0, s>>>(gy, ldgy, x, ldx, Cin, Co, Mo, K, stride, (double*)ws);
+            }
         }
         int n = Co * Cin * K;
         f64_store_kernel<<<(n + 255) / 256, 256, 0, s>>>((const double*)ws, gw, n);

@@ -219,7 +219,8 @@ def test_depthwise_vs_torch(dil, M):
 
 
 @pytest.mark.parametrize("Cin,B,Co,T_,K,s", [(1, 3, 48, 1208, 16, 8), (2, 3, 48, 1208, 16, 8), (2, 2, 512, 32000, 16, 8),
-                                             (1, 2, 512, 32000, 16, 8), (1, 2, 40, 1003, 16, 8), (1, 2, 24, 700, 10, 5)])
+                                             (1, 2, 512, 32000, 16, 8), (1, 2, 40, 1003, 16, 8), (1, 2, 24, 700, 10, 5),
+                                             (4, 2, 44, 30007, 20, 10)])      # the music encoder's geometry: tiled generic wgrad
 def test_strided_and_transposed_conv_vs_torch(Cin, B, Co, T_, K, s):
     """Encoder / RQB re-encoder / decoder filterbank convs (tiled kernels for kernel 16 / hop 8, generic otherwise):
     forward, input gradient and weight gradient against torch fp32; ragged tails (T not a multiple of the hop)."""
