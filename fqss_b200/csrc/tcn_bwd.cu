@@ -826,17 +826,25 @@ __global__ void tcn_bwd_finalize_kernel(const fqss_tcn_block p, const fqss_tcn_b
         g.g_gn2_w[i] = (float)acc[L.gln2 + 2 * i + 1];
     }
     if (i < 8 && p.quant) {
+        double2 v[AccLayout::NSLOT];          // all slot loads in flight at once (one L2 round trip, not NSLOT)
+#pragma unroll
+        for (int k = 0; k < AccLayout::NSLOT; ++k) v[k] = *reinterpret_cast<const double2*>(acc + L.qs(k) + 2 * i);
         double sD = 0.0, sZ = 0.0;
+#pragma unroll
         for (int k = 0; k < AccLayout::NSLOT; ++k) {
-            sD += acc[L.qs(k) + 2 * i];
-            sZ += acc[L.qs(k) + 2 * i + 1];
+            sD += v[k].x;
+            sZ += v[k].y;
         }
         g.g_q[2 * i] = (float)(sZ - sD / 255.0);      // d/d min_range
         g.g_q[2 * i + 1] = (float)(sD / 255.0);       // d/d max_range
     }
     if (i == 8 || i == 9) {
+        double w[AccLayout::NSLOT];
+#pragma unroll
+        for (int k = 0; k < AccLayout::NSLOT; ++k) w[k] = acc[L.qs(k) + AccLayout::SLOPE_OFF + (i - 8)];
         double sl = 0.0;
-        for (int k = 0; k < AccLayout::NSLOT; ++k) sl += acc[L.qs(k) + AccLayout::SLOPE_OFF + (i - 8)];
+#pragma unroll
+        for (int k = 0; k < AccLayout::NSLOT; ++k) sl += w[k];
         (i == 8 ? g.g_slope1 : g.g_slope3)[0] = (float)sl;
     }
     if (i < p.Chid) {
