@@ -124,25 +124,38 @@ __global__ void __launch_bounds__(PW_THREADS) pw_fwd_kernel(const fqss_pw_desc d
     __shared__ float sh5[5];
     const int64_t row = blockIdx.x;
     const int64_t chunk0 = (int64_t)blockIdx.y * PW_CHUNK;
+    const float* r1 = d.x1 + row * d.ld1;
+    const float* r2 = pw_binary<KIND>() ? d.x2 + x2_row<KIND>(d, row) * d.ld2 : nullptr;
+    float* ry = d.y + row * d.ldy;
+    // the CTA's data is requested BEFORE the row constants and the quantiser constants are derived (a barrier, an fp64
+    // division / square root and dependent loads): the CTA lives for 16 elements per thread, so "constants, then data"
+    // in sequence exposes two memory round trips per CTA
+    float a[PW_QUADS][4], b[PW_QUADS][4];
+#pragma unroll
+    for (int qd = 0; qd < PW_QUADS; ++qd) {
+        const int64_t c0 = chunk0 + ((int64_t)qd * PW_THREADS + threadIdx.x) * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[qd][k] = b[qd][k] = 0.f;
+        if (c0 < d.cols) {
+            const int nv = (int)min((int64_t)4, d.cols - c0);
+            ld_quad(r1 + c0, nv, VEC, a[qd]);
+            if (pw_binary<KIND>()) ld_quad(r2 + c0, nv, VEC, b[qd]);
+        }
+    }
     RowCtx rc;
     if (KIND == FQSS_PW_PRELU) rc.slope = __ldg(d.slope);
     if (KIND == FQSS_PW_GLN) gln_row_consts(d, row, rc, sh5);
     ActQF q;
     if (d.quant) q = load_actqf(d.rmin, d.rmax, d.n_bits);
-    const float* r1 = d.x1 + row * d.ld1;
-    const float* r2 = pw_binary<KIND>() ? d.x2 + x2_row<KIND>(d, row) * d.ld2 : nullptr;
-    float* ry = d.y + row * d.ldy;
 #pragma unroll
     for (int qd = 0; qd < PW_QUADS; ++qd) {
         const int64_t c0 = chunk0 + ((int64_t)qd * PW_THREADS + threadIdx.x) * 4;
         if (c0 >= d.cols) break;
         const int nv = (int)min((int64_t)4, d.cols - c0);
-        float a[4], b[4] = {0.f, 0.f, 0.f, 0.f}, o[4];
-        ld_quad(r1 + c0, nv, VEC, a);
-        if (pw_binary<KIND>()) ld_quad(r2 + c0, nv, VEC, b);
+        float o[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float z = pw_z<KIND>(a[k], b[k], rc);
+            const float z = pw_z<KIND>(a[qd][k], b[qd][k], rc);
             o[k] = d.quant ? actqf_fq(q, z) : z;
         }
         st_quad(ry + c0, nv, VEC, o);
