@@ -480,9 +480,20 @@ __global__ void __launch_bounds__(ROW_THREADS) tcn_encode_kernel(const float* __
     ActQF q;
     const bool quant = rmin != nullptr;
     if (quant) q = load_actqf(rmin, rmax, 8);
-    for (int m = threadIdx.x; m < M; m += ROW_THREADS) {
-        float v = x[r * ldx + m];
-        out[r * ldo + m] = __float2bfloat16_rn(quant ? actqf_code(q, v) : v);
+    const float* xr = x + r * ldx;
+    __nv_bfloat16* orow = out + r * ldo;
+    // 128-bit loads / 64-bit stores over the full frame quads of aligned rows (the scalar loop ran at ~0.3 of HBM), scalar tail
+    const bool vec = (ldx & 3) == 0 && (ldo & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 7) == 0;
+    const int nfull = vec ? (M >> 2) : 0;
+    for (int v4 = threadIdx.x; v4 < nfull; v4 += ROW_THREADS) {
+        const float4 v = ldg4(xr + 4 * v4);
+        const float c0 = quant ? actqf_code(q, v.x) : v.x, c1 = quant ? actqf_code(q, v.y) : v.y;
+        const float c2 = quant ? actqf_code(q, v.z) : v.z, c3 = quant ? actqf_code(q, v.w) : v.w;
+        *reinterpret_cast<uint2*>(orow + 4 * v4) = float4_to_bf16x4(c0, c1, c2, c3);
+    }
+    for (int m = 4 * nfull + threadIdx.x; m < M; m += ROW_THREADS) {
+        float v = xr[m];
+        orow[m] = __float2bfloat16_rn(quant ? actqf_code(q, v) : v);
     }
 }
 
