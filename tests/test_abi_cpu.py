@@ -112,7 +112,7 @@ def test_ctypes_binding_matches_header(native, tmp_path):
     structs = {"fqss_tcn_block": E.TcnBlock, "fqss_tcn_block_grads": E.TcnBlockGrads, "fqss_qrange": E.QRange,
                "fqss_prep_item": native.PrepItem, "fqss_gather_item": native.GatherItem, "fqss_pw_desc": native.PwDesc,
                "fqss_pw_grads": native.PwGrads, "fqss_wq_item": native.WqItem}
-    probes = {"fqss_tcn_block": ["ld", "Wc1", "q_in", "x_op", "rc1", "code3"], "fqss_tcn_block_grads": ["dY2", "dW1q", "g_q", "ws_bytes"],
+    probes = {"fqss_tcn_block": ["no_skip", "ld", "Wc1", "q_in", "x_op", "rc1", "code3"], "fqss_tcn_block_grads": ["dY2", "dW1q", "g_q", "ws_bytes"],
               "fqss_prep_item": ["Wc", "N", "split"], "fqss_gather_item": ["offset", "numel"], "fqss_pw_desc": ["rows", "x2", "eps", "rmax"],
               "fqss_pw_grads": ["gx2", "g_beta"], "fqss_wq_item": ["rmin", "n_bits"], "fqss_qrange": ["rmax"]}
     src = ['#include <stdio.h>', '#include <stddef.h>', '#include "fqss.h"', 'int main(void) {']
@@ -140,3 +140,33 @@ def test_ranges_ok_flags_crossed_or_degenerate_ranges():
     assert not bool(ranges_ok(m))
     m[1].max_range.data.fill_(float("nan"))
     assert not bool(ranges_ok(m))
+
+
+def test_skipless_block_plumbing_on_cpu():
+    """Host-side plumbing of the fused engine's skip-less mode (ConvTasNetMusicQ blocks, convtasnetq_music.py:117-176): the
+    block -> slot mapping names the right parameters, blocks without a skip conv leave the skip slots empty, and the
+    eligibility tests refuse CPU tensors / un-calibrated models (the product path then stays on the per-layer wrappers,
+    which raise on non-CUDA input: no CPU fallback anywhere)."""
+    import torch
+    from fqss_b200 import float_engine as FE
+    from fqss_b200 import tcn_engine as E
+    from fqss_b200.qat.models.convtasnetq_music import ConvTasNetMusicQ
+    from fqss_b200.qat.models.load_model import quantize_model
+    from fqss_b200.testing import RECIPE_QUANT
+    torch.manual_seed(0)
+    m = quantize_model(ConvTasNetMusicQ(sources=["a", "b"], n_filters=128, bn_chan=128, hid_chan=256, n_blocks=2, n_repeats=1),
+                       dict(RECIPE_QUANT))
+    blk = m.separator.network[2][0][1]
+    t, dil = E.block_tensors(blk, None, True)
+    assert dil == 2 and set(t) == set(E._BLOCK_SLOTS)
+    assert t["W1"] is blk.net[0].conv1d.weight and t["Wdw"] is blk.net[3].net[0].conv1d.weight
+    assert t["Wres"] is blk.net[3].net[3].conv1d.weight and t["slope3"] is blk.net[3].net[0].nl.weight
+    assert t["qaddmin"] is blk.add.activation_fake_quantize.min_range
+    for k in ("Wskip", "bskip", "wsmin", "wsmax", "qskipmin", "qskipmax", "qaddsmin", "qaddsmax", "b1", "bdw", "bres"):
+        assert t[k] is None, k
+    x = torch.zeros(1, 128, 64)
+    assert not E.fused_eligible_noskip(m.separator, x) and not FE.noskip_eligible(m.separator, x)
+    # the ctypes mirror of fqss_tcn_block carries the flag where the header puts it
+    b = E.TcnBlock()
+    b.no_skip = 1
+    assert b.no_skip == 1 and E.TcnBlock.no_skip.offset == E.TcnBlock.split.offset + 4
