@@ -860,10 +860,22 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static int g_wgrad_overlap = -1;      // -1: take FQSS_WGRAD_OVERLAP from the environment (default on) at first use
 
 // side stream + fork / join events of the backward pass (created once per process; one process drives one GPU)
+static int g_side_device = -1;      // the device the side stream / events were created on
 static cudaStream_t side_stream() {
     static cudaStream_t st = nullptr;
-    if (!st) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (!st) {
+        cudaGetDevice(&g_side_device);
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    }
     return st;
+}
+// The statics above belong to ONE device (the launch contract is one process per GPU): a call from another device would
+// record events on a foreign stream -- refuse it loudly instead.
+static bool side_device_ok() {
+    if (g_side_device < 0) return true;
+    int dev = -1;
+    cudaGetDevice(&dev);
+    return dev == g_side_device;
 }
 static cudaEvent_t side_event(int i) {      // 0 / 1: fork / done of the dW2 wgrad; 2: fork of the block tail; 3, 4: tail done (per accumulator)
     static cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -938,6 +950,7 @@ int fqss_tcn_block_bwd(const fqss_tcn_block* p, const fqss_tcn_block_grads* g, v
                      g->g_slope1 && g->g_slope3 && g->g_q, -1, "tcn_block_bwd: null parameter-gradient output");
     FQSS_REQUIRE(g->ws_bytes >= fqss_tcn_ws_bytes(p->B, p->Cio, p->Chid), -3, "tcn_block_bwd: workspace too small");
     FQSS_REQUIRE(p->Chid <= 1024 && 2 * p->Cio <= 1024, -1, "tcn_block_bwd: channel count too large");
+    FQSS_REQUIRE(side_device_ok(), -1, "tcn_block_bwd: the library's side stream belongs to device %d (one process drives one GPU)", g_side_device);
     cudaStream_t s = (cudaStream_t)stream;
     const AccLayout L(p->B, p->Cio, p->Chid);
     const size_t acc_bytes = align_up((size_t)L.total * sizeof(double), 256);
