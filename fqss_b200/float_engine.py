@@ -52,8 +52,16 @@ def eligible(model, x):
         and sb[1].weight.numel() == 1 and (F_ * model.n_srcs) % 128 == 0
 
 
+def _generation(params):
+    """parallel.param_generation() if any of `params` lives in a ParamArena (updated in place by kernels that do not touch
+    torch's version counters), else 0: the frozen teacher's prepared weights stay cached across steps."""
+    from . import parallel
+    return parallel.param_generation() if any(getattr(p, "_fqss_in_arena", False) for p in params) else 0
+
+
 def _versions(model):
-    return tuple((p.data_ptr(), p._version) for p in model.parameters())
+    ps = list(model.parameters())
+    return (_generation(ps),) + tuple((p.data_ptr(), p._version) for p in ps)
 
 
 def _prepare(model, dev):
@@ -211,7 +219,8 @@ def noskip_eligible(masker, x):
 
 def _prepare_noskip(masker, dev):
     blocks = _noskip_blocks(masker)
-    key = tuple((p.data_ptr(), p._version) for b in blocks for p in b.parameters())
+    ps = [p for b in blocks for p in b.parameters()]
+    key = (_generation(ps),) + tuple((p.data_ptr(), p._version) for p in ps)
     cache = getattr(masker, "_fqss_float_prep", None)
     if cache is not None and cache[0] == key:
         return cache[1]

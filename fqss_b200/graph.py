@@ -40,4 +40,6 @@ class GraphedStep:
             if src.data_ptr() != dst.data_ptr():
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        from . import parallel
+        parallel.bump_param_generation()      # a replayed step may contain an optimizer update (see parallel.param_generation)
         return self.static_out

@@ -34,6 +34,21 @@ from ._native import check, lib, ptr, stream_ptr, workspace
 _GLOBAL_PARITY = False
 
 
+# Parameters updated by the arena kernels change IN PLACE without touching torch's version counters; caches of prepared
+# weights (float_engine / tcn_engine: split-bf16 operands of un-quantised convs) add this counter to their key.  Bumped by
+# every optimizer step, eager or replayed (graph.GraphedStep calls it per replay).
+_PARAM_GENERATION = 0
+
+
+def param_generation():
+    return _PARAM_GENERATION
+
+
+def bump_param_generation():
+    global _PARAM_GENERATION
+    _PARAM_GENERATION += 1
+
+
 def set_global_batch_parity(on=True):
     global _GLOBAL_PARITY
     _GLOBAL_PARITY = bool(on)
@@ -81,6 +96,8 @@ class ParamArena:
 
     def __init__(self, params):
         self.params = [p for p in params]
+        for p in self.params:
+            p._fqss_in_arena = True       # caches of prepared weights key on param_generation() for these (float_engine._generation)
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device
         pad = (-self.numel) % 4
@@ -150,6 +167,7 @@ class ParamArena:
         check(lib().fqss_arena_sumsq(ptr(self.grad), n, ptr(self.sumsq), ptr(ws), ws.numel(), s))
         check(lib().fqss_arena_scale_clip(ptr(self.grad), n, ptr(self.sumsq), float(pre_scale), float(max_norm), s))
         self.step_count += 1          # host mirror; the kernels read the device counter (CUDA-graph replays stay correct)
+        bump_param_generation()       # prepared-weight caches keyed on torch's version counters would otherwise go stale
         check(lib().fqss_arena_adam_dev(ptr(self.flat), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq), n, float(lr),
                                         float(betas[0]), float(betas[1]), float(eps), ptr(self.step_dev),
                                         ptr(getattr(self, "lr_dev", None)) or None, s))

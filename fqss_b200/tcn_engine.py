@@ -446,7 +446,9 @@ def float_conv(conv, x):
     B, Ci, M = x.shape
     ld = (M + 7) // 8 * 8
     w = conv.weight
-    key = (w.data_ptr(), w._version, conv.bias.data_ptr() if conv.bias is not None else 0)
+    from . import parallel
+    gen = parallel.param_generation() if getattr(w, "_fqss_in_arena", False) else 0
+    key = (w.data_ptr(), w._version, gen, conv.bias.data_ptr() if conv.bias is not None else 0)
     ent = _FLOAT_W.get(id(conv))
     if ent is None or ent[0] != key:
         Co = w.shape[0]

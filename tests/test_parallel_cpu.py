@@ -158,3 +158,18 @@ def test_global_batch_parity_sync_gloo_world2(tmp_path):
             assert torch.equal(on["mins"][k], mins[k]) and torch.equal(on["maxs"][k], maxs[k]), (r, k)
     # without the sync the two ranks have diverged (what the reference's DDP run does)
     assert not torch.equal(outs[0][False]["mins"][0], outs[1][False]["mins"][0])
+
+
+def test_param_generation_keys_prepared_weight_caches():
+    """Arena kernels update parameters in place without touching torch's version counters: caches of prepared weights add
+    parallel.param_generation() to their key for parameters that live in an arena, and only for those (the frozen teacher's
+    prepared operands must stay cached across steps)."""
+    import torch
+    from fqss_b200 import float_engine as FE
+    from fqss_b200 import parallel
+    a, b = torch.nn.Linear(4, 4), torch.nn.Linear(4, 4)
+    for p in a.parameters():
+        p._fqss_in_arena = True          # what ParamArena.__init__ does (it needs CUDA tensors)
+    k_a, k_b = FE._versions(a), FE._versions(b)
+    parallel.bump_param_generation()
+    assert FE._versions(a) != k_a and FE._versions(b) == k_b
