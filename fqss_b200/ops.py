@@ -74,6 +74,13 @@ def rows_view(t):
     return t, rows, cols, ld
 
 
+def _aligned_contig(t):
+    """Contiguous AND 16-byte aligned (the flat quantiser kernels use 128-bit accesses): a contiguous view into the middle of
+    a buffer is repacked instead of being refused by the library."""
+    t = t.contiguous()
+    return t if t.data_ptr() % 16 == 0 else t.clone(memory_format=torch.contiguous_format)
+
+
 def _scalar_like(p):
     return torch.empty_like(p, memory_format=torch.contiguous_format)
 
@@ -85,7 +92,7 @@ class FakeQuantAct(Function):
     @staticmethod
     def forward(ctx, x, rmin, rmax, n_bits):
         N.require_cuda(x, rmin, rmax)
-        xc = x.contiguous()
+        xc = _aligned_contig(x)
         y = torch.empty_like(xc)
         check(lib().fqss_fq_act_fwd(ptr(xc), ptr(y), None, xc.numel(), ptr(rmin), ptr(rmax), n_bits, stream_ptr()))
         ctx.save_for_backward(xc, rmin, rmax)
@@ -96,7 +103,7 @@ class FakeQuantAct(Function):
     @once_differentiable
     def backward(ctx, g):
         x, rmin, rmax = ctx.saved_tensors
-        g = g.contiguous()
+        g = _aligned_contig(g)
         gx = torch.empty_like(x)
         gmin, gmax = _scalar_like(rmin), _scalar_like(rmax)
         ws = workspace(0, x.device)
@@ -108,7 +115,7 @@ class FakeQuantAct(Function):
 def fake_quant_codes(x, rmin, rmax, n_bits=8):
     """(y, uint8 codes) of the activation quantiser -- test / export helper."""
     N.require_cuda(x, rmin, rmax)
-    xc = x.contiguous()
+    xc = _aligned_contig(x)
     y = torch.empty_like(xc)
     code = torch.empty(xc.shape, dtype=torch.uint8, device=xc.device)
     check(lib().fqss_fq_act_fwd(ptr(xc), ptr(y), ptr(code), xc.numel(), ptr(rmin), ptr(rmax), n_bits, stream_ptr()))

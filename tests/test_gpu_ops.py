@@ -402,3 +402,18 @@ def test_pairwise_wsdr_module_vs_reference_and_oracle(golden):
     assert torch.equal(reordered.cpu(), est[:, [1, 0]])            # the golden estimates are the targets, permuted
     with pytest.raises(NotImplementedError):
         PairwiseWSDR("snr")
+
+
+def test_fake_quant_act_unaligned_contiguous_view():
+    """A contiguous view that starts in the middle of a buffer (4-byte aligned only) is repacked, not refused (ADVICE)."""
+    from fqss_b200 import ops
+    base = torch.randn(4101, device=DEV)
+    x = base[1:].requires_grad_(True)                 # contiguous, data_ptr % 16 == 4
+    assert x.is_contiguous() and x.data_ptr() % 16 != 0
+    rmin, rmax = torch.tensor([-1.5], device=DEV, requires_grad=True), torch.tensor([2.0], device=DEV, requires_grad=True)
+    y = ops.FakeQuantAct.apply(x, rmin, rmax, 8)
+    ref = ops.FakeQuantAct.apply(base[1:].clone().requires_grad_(True), rmin, rmax, 8)
+    assert torch.equal(y, ref)
+    g = torch.randn(4101, device=DEV)[1:]
+    y.backward(g)
+    assert x.grad is not None and torch.isfinite(x.grad).all()
